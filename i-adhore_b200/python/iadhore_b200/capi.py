@@ -1,0 +1,331 @@
+"""ctypes binding of the C-ABI in include/iadhore_b200.h.
+
+The same binding drives the product library (`libiadhore_b200.so`, prefix
+``iadh_``) and -- from tests / bench cpu_baseline only -- the oracle
+(`oracle/liboracle.so`, prefix ``oracle_``), which exports the identical
+interface.  The product path never loads the oracle and has no CPU fallback:
+`load_product()` raises if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..", ".."))
+PRODUCT_LIB = os.path.join(REPO, "i-adhore_b200", "csrc", "libiadhore_b200.so")
+ORACLE_LIB = os.path.join(REPO, "oracle", "liboracle.so")
+
+F_STRAND, F_GAP, F_MASKED = 1, 2, 4
+MH_NONE, MH_BONFERRONI, MH_FDR = 0, 1, 2
+
+
+class DatasetDesc(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("list_off", C.POINTER(C.c_int64)),
+                ("fam", C.POINTER(C.c_int32)), ("gid", C.POINTER(C.c_int32)),
+                ("num_id", C.POINTER(C.c_int32)), ("flags", C.POINTER(C.c_uint8))]
+
+
+class Params(C.Structure):
+    _fields_ = [("n_gaps", C.c_int32), ("gaps", C.c_int32 * 10), ("gap_size", C.c_int32),
+                ("cluster_gap", C.c_int32), ("anchor_points", C.c_int32), ("mult_hyp", C.c_int32),
+                ("q_value", C.c_double), ("prob_cutoff", C.c_double)]
+
+
+class ProfileDesc(C.Structure):
+    _fields_ = [("n_segments", C.c_int32), ("length", C.c_int32), ("x_object_id", C.c_int32),
+                ("fam", C.POINTER(C.c_int32)), ("gid", C.POINTER(C.c_int32)),
+                ("num_id", C.POINTER(C.c_int32)), ("flags", C.POINTER(C.c_uint8))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_ghm", C.c_int64), ("n_dots", C.c_int64), ("n_multiplicons", C.c_int64),
+                ("n_baseclusters", C.c_int64), ("n_anchorpoints", C.c_int64),
+                ("build_ms", C.c_double), ("cluster_ms", C.c_double), ("total_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
+           "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
+           "free_result", "build_dots", "omxn", "last_error", "version"]
+
+
+def gap_sizes(gap_size: int) -> List[int]:
+    """Settings::getGapSizes (Settings.cpp:585-598): <=10 distinct round(3^(1+i*step))."""
+    import math
+    step = (math.log(gap_size) / math.log(3) - 1) / 9
+    out: List[int] = []
+    for i in range(10):
+        v = int(math.floor(math.pow(3, 1 + i * step) + 0.5))  # C round(): half away from zero (positive)
+        if i == 0 or v != out[-1]:
+            out.append(v)
+    return out
+
+
+@dataclass
+class Dataset:
+    """Flattened DataSet (after tandem remap), host side (numpy)."""
+    list_off: np.ndarray
+    fam: np.ndarray
+    gid: np.ndarray
+    num_id: np.ndarray
+    flags: np.ndarray
+
+    @property
+    def n_lists(self) -> int:
+        return len(self.list_off) - 1
+
+    def size(self, l: int) -> int:
+        return int(self.list_off[l + 1] - self.list_off[l])
+
+
+@dataclass
+class Profile:
+    S: int
+    L: int
+    x_object_id: int
+    fam: np.ndarray
+    gid: np.ndarray
+    num_id: np.ndarray
+    flags: np.ndarray
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Result:
+    def __init__(self, bytes_: bytes, ghm_index: np.ndarray, stats: dict):
+        self.bytes = bytes_
+        self.ghm_index = ghm_index
+        self.stats = stats
+
+    @property
+    def n_multiplicons(self) -> int:
+        return struct.unpack_from("<i", self.bytes, 0)[0]
+
+
+class Engine:
+    """One context of a library exporting the iadhore_b200.h interface."""
+
+    def __init__(self, lib_path: str, prefix: str, ds: Dataset, device: int = 0):
+        if not os.path.exists(lib_path):
+            raise RuntimeError(f"{lib_path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.lib = C.CDLL(lib_path)
+        self.prefix = prefix
+        f = lambda n: getattr(self.lib, prefix + n)
+        self._f = f
+        f("last_error").restype = C.c_char_p
+        f("version").restype = C.c_char_p
+        f("result_bytes").restype = C.POINTER(C.c_uint8)
+        f("result_ghm_index").restype = C.POINTER(C.c_int32)
+        f("destroy").restype = None
+        f("free_result").restype = None
+        self.ds = ds
+        self._keep = [np.ascontiguousarray(ds.list_off, dtype=np.int64),
+                      np.ascontiguousarray(ds.fam, dtype=np.int32),
+                      np.ascontiguousarray(ds.gid, dtype=np.int32),
+                      np.ascontiguousarray(ds.num_id, dtype=np.int32),
+                      np.ascontiguousarray(ds.flags, dtype=np.uint8)]
+        d = DatasetDesc(ds.n_lists, _p(self._keep[0], C.c_int64), _p(self._keep[1], C.c_int32),
+                        _p(self._keep[2], C.c_int32), _p(self._keep[3], C.c_int32),
+                        _p(self._keep[4], C.c_uint8))
+        self.ctx = C.c_void_p()
+        self._chk(f("create")(C.byref(d), C.c_int(device), C.byref(self.ctx)))
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}* failed ({rc}): {self._f('last_error')().decode()}")
+
+    def close(self):
+        if self.ctx:
+            self._f("destroy")(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, gap_size=30, cluster_gap=35, anchor_points=3, mult_hyp=MH_BONFERRONI,
+                   q_value=0.75, prob_cutoff=0.01, gaps: Optional[Sequence[int]] = None):
+        g = list(gaps) if gaps is not None else gap_sizes(gap_size)
+        p = Params()
+        p.n_gaps = len(g)
+        for i in range(10):
+            p.gaps[i] = g[i] if i < len(g) else 0
+        p.gap_size, p.cluster_gap, p.anchor_points, p.mult_hyp = gap_size, cluster_gap, anchor_points, mult_hyp
+        p.q_value, p.prob_cutoff = q_value, prob_cutoff
+        self._chk(self._f("set_params")(self.ctx, C.byref(p)))
+
+    def _take(self, res) -> Result:
+        n = C.c_size_t()
+        ptr = self._f("result_bytes")(res, C.byref(n))
+        b = C.string_at(ptr, n.value)
+        m = C.c_size_t()
+        gp = self._f("result_ghm_index")(res, C.byref(m))
+        gi = np.ctypeslib.as_array(gp, shape=(m.value,)).copy() if m.value else np.zeros(0, np.int32)
+        st = Stats()
+        self._chk(self._f("result_stats")(res, C.byref(st)))
+        self._f("free_result")(res)
+        return Result(b, gi, st.as_dict())
+
+    def level2_all_pairs(self, rank: int = 0, n_ranks: int = 1) -> Result:
+        res = C.c_void_p()
+        self._chk(self._f("level2_all_pairs")(self.ctx, C.c_int(rank), C.c_int(n_ranks), C.byref(res)))
+        return self._take(res)
+
+    def level2_pairs(self, xs: Sequence[int], ys: Sequence[int]) -> Result:
+        xa = np.ascontiguousarray(xs, dtype=np.int32)
+        ya = np.ascontiguousarray(ys, dtype=np.int32)
+        res = C.c_void_p()
+        self._chk(self._f("level2_pairs")(self.ctx, _p(xa, C.c_int32), _p(ya, C.c_int32),
+                                          C.c_int64(len(xa)), C.byref(res)))
+        return self._take(res)
+
+    def mask_range(self, lst: int, begin: int, end: int):
+        self._chk(self._f("mask_range")(self.ctx, C.c_int32(lst), C.c_int32(begin), C.c_int32(end)))
+
+    def clear_masks(self):
+        self._chk(self._f("clear_masks")(self.ctx))
+
+    def _pdesc(self, p: Profile):
+        keep = [np.ascontiguousarray(p.fam, dtype=np.int32), np.ascontiguousarray(p.gid, dtype=np.int32),
+                np.ascontiguousarray(p.num_id, dtype=np.int32), np.ascontiguousarray(p.flags, dtype=np.uint8)]
+        d = ProfileDesc(p.S, p.L, p.x_object_id, _p(keep[0], C.c_int32), _p(keep[1], C.c_int32),
+                        _p(keep[2], C.c_int32), _p(keep[3], C.c_uint8))
+        return d, keep
+
+    def profile_search(self, p: Profile, rank: int = 0, n_ranks: int = 1) -> Result:
+        d, keep = self._pdesc(p)
+        res = C.c_void_p()
+        self._chk(self._f("profile_search")(self.ctx, C.byref(d), C.c_int(rank), C.c_int(n_ranks), C.byref(res)))
+        return self._take(res)
+
+    def build_dots(self, xs: Sequence[int], ys: Sequence[int], profile: Optional[Profile] = None):
+        """-> list of (dots_o0 [n,2], dots_o1 [n,2]) per GHM."""
+        xa = np.ascontiguousarray(xs, dtype=np.int32)
+        ya = np.ascontiguousarray(ys, dtype=np.int32)
+        cnt = C.POINTER(C.c_int64)()
+        dots = C.POINTER(C.c_int32)()
+        nd = C.c_int64()
+        if profile is not None:
+            d, keep = self._pdesc(profile)
+            pd = C.byref(d)
+        else:
+            pd = None
+        self._chk(self._f("build_dots")(self.ctx, pd, _p(xa, C.c_int32), _p(ya, C.c_int32), C.c_int64(len(ya)),
+                                        C.byref(cnt), C.byref(dots), C.byref(nd)))
+        n = len(ya)
+        cn = np.ctypeslib.as_array(cnt, shape=(2 * n,)).copy() if n else np.zeros(0, np.int64)
+        dd = np.ctypeslib.as_array(dots, shape=(nd.value, 2)).copy() if nd.value else np.zeros((0, 2), np.int32)
+        out = []
+        k = 0
+        for i in range(n):
+            a = dd[k:k + cn[2 * i]]
+            k += cn[2 * i]
+            b = dd[k:k + cn[2 * i + 1]]
+            k += cn[2 * i + 1]
+            out.append((a, b))
+        return out
+
+    def omxn(self, x: np.ndarray, n: np.ndarray) -> np.ndarray:
+        xa = np.ascontiguousarray(x, dtype=np.float64)
+        na = np.ascontiguousarray(n, dtype=np.int32)
+        out = np.zeros_like(xa)
+        self._chk(self._f("omxn")(self.ctx, _p(xa, C.c_double), _p(na, C.c_int32), C.c_int64(len(xa)), _p(out, C.c_double)))
+        return out
+
+    def version(self) -> str:
+        return self._f("version")().decode()
+
+
+def load_product(ds: Dataset, device: int = 0) -> Engine:
+    """The B200 path.  Fails loudly when the CUDA library is missing (no fallback)."""
+    return Engine(PRODUCT_LIB, "iadh_", ds, device)
+
+
+# ---------------------------------------------------------------------------
+# parsing of the packed multiplicon stream (Multiplicon.cpp:210-264)
+
+@dataclass
+class PCluster:
+    p: float
+    orient: int
+    stats: Tuple[float, ...]  # a, b, avg_x, var_x, mrss, x_end1, x_end2, y_end1, y_end2
+    was_twisted: int
+    bounds: Tuple[int, int, int, int]
+    aps: np.ndarray  # [n,5] gx, gy, x, y, real
+
+
+@dataclass
+class PMultiplicon:
+    x_object_id: int
+    y_object_id: int
+    level: int
+    redundant: int
+    bounds: Tuple[int, int, int, int]
+    clusters: List[PCluster]
+
+
+def parse_packed(b: bytes) -> List[PMultiplicon]:
+    off = 0
+    (n,) = struct.unpack_from("<i", b, off)
+    off += 4
+    out = []
+    for _ in range(n):
+        xo, yo, lv, red, bx, ex, by, ey, nc = struct.unpack_from("<iiiBiiiii", b, off)
+        off += 33
+        cl = []
+        for _ in range(nc):
+            p, orient = struct.unpack_from("<dB", b, off)
+            off += 9
+            st = struct.unpack_from("<9d", b, off)
+            off += 72
+            tw, cbx, cex, cby, cey, nap = struct.unpack_from("<Biiiii", b, off)
+            off += 21
+            raw = np.frombuffer(b, dtype=np.uint8, count=17 * nap, offset=off).reshape(nap, 17)
+            off += 17 * nap
+            ints = raw[:, :16].copy().view("<i4").reshape(nap, 4)
+            aps = np.concatenate([ints, raw[:, 16:17].astype(np.int32)], axis=1)
+            cl.append(PCluster(p, orient, st, tw, (cbx, cex, cby, cey), aps))
+        out.append(PMultiplicon(xo, yo, lv, red, (bx, ex, by, ey), cl))
+    assert off == len(b), (off, len(b))
+    return out
+
+
+def compare_packed(got: bytes, want: bytes, rtol_p: float = 1e-12) -> Optional[str]:
+    """None if equal: every integer/index/flag field bit-exact, regression doubles
+    bit-exact, p-values within rtol_p relative (north_star tolerance)."""
+    if got == want:
+        return None
+    g, w = parse_packed(got), parse_packed(want)
+    if len(g) != len(w):
+        return f"multiplicon count {len(g)} != {len(w)}"
+    for i, (a, b) in enumerate(zip(g, w)):
+        if (a.x_object_id, a.y_object_id, a.level, a.redundant, a.bounds) != (b.x_object_id, b.y_object_id, b.level, b.redundant, b.bounds):
+            return f"multiplicon {i} header differs: {a} vs {b}"
+        if len(a.clusters) != len(b.clusters):
+            return f"multiplicon {i}: cluster count {len(a.clusters)} != {len(b.clusters)}"
+        for j, (ca, cb) in enumerate(zip(a.clusters, b.clusters)):
+            if (ca.orient, ca.was_twisted, ca.bounds) != (cb.orient, cb.was_twisted, cb.bounds):
+                return f"multiplicon {i} cluster {j} header differs"
+            if ca.aps.shape != cb.aps.shape or not np.array_equal(ca.aps, cb.aps):
+                return f"multiplicon {i} cluster {j} anchor points differ"
+            sa = struct.pack("<9d", *ca.stats)
+            sb = struct.pack("<9d", *cb.stats)
+            if sa != sb:
+                return f"multiplicon {i} cluster {j} regression stats differ: {ca.stats} vs {cb.stats}"
+            if ca.p != cb.p:
+                denom = max(abs(cb.p), 1e-300)
+                if abs(ca.p - cb.p) / denom > rtol_p:
+                    return f"multiplicon {i} cluster {j} p-value {ca.p!r} vs {cb.p!r}"
+    return None

@@ -1,0 +1,221 @@
+"""Deterministic synthetic genome generator.
+
+Produces gene lists + a gene->family table in the reference's own input formats
+(``<gene><strand>`` one per line, `GeneList.cpp:9-38`; ``gene<TAB>family`` lines,
+`GeneFamily.cpp:3-48`) plus an ``.ini`` (`Settings.cpp:23-293`), so the same
+workload can be fed to the unmodified reference binary and to the B200 path.
+
+Model: an ancestral order of `n_anc` genes (each its own family, random strand);
+per genome an optional whole-genome duplication, `k_inv` random inversions
+(strand flipping), per-gene retention `r`, tandem insertion prob `t`
+(same family, same strand, adjacent) and noise genes from random families; the
+genome is then split into equally sized lists.  The RNG is a private
+SplitMix64, so files are bit-identical on every python / numpy version.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+MASK64 = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed: int):
+        self.s = seed & MASK64
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & MASK64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK64
+        return z ^ (z >> 31)
+
+    def below(self, n: int) -> int:
+        return self.next() % n
+
+    def unit(self) -> float:
+        return (self.next() >> 11) / float(1 << 53)
+
+
+@dataclass
+class GenomeSpec:
+    name: str
+    n_lists: int
+    genes_per_list: int
+    wgd: bool
+    seed: int
+
+
+@dataclass
+class SynthConfig:
+    name: str
+    n_families: int
+    genomes: List[GenomeSpec]
+    k_inv: int = 30
+    r_wgd: float = 0.45
+    r_plain: float = 0.8
+    t_tandem: float = 0.06
+    noise: float = 0.15
+    anc_seed: int = 7
+    n_anc: int | None = None  # ancestral gene count (default: one gene per family)
+    # reference settings (shipped defaults of datasetI/II)
+    gap_size: int = 30
+    cluster_gap: int = 35
+    q_value: float = 0.75
+    prob_cutoff: float = 0.01
+    anchor_points: int = 3
+    tandem_gap: int | None = None
+    level_2_only: bool = False
+    mult_hyp: str | None = None  # None -> reference default (Bonferroni)
+    extra: Dict[str, str] = field(default_factory=dict)
+
+
+Gene = Tuple[str, bool, int]  # (gene id, strand '+' == True, family)
+
+
+def _ancestor(cfg: SynthConfig) -> List[Tuple[int, bool]]:
+    rng = SplitMix64(cfg.anc_seed)
+    if cfg.n_anc is None or cfg.n_anc == cfg.n_families:
+        return [(f, bool(rng.next() & 1)) for f in range(cfg.n_families)]
+    return [(rng.below(cfg.n_families), bool(rng.next() & 1)) for _ in range(cfg.n_anc)]
+
+
+def make_genome(cfg: SynthConfig, spec: GenomeSpec) -> List[List[Gene]]:
+    rng = SplitMix64(spec.seed)
+    anc = _ancestor(cfg)
+    chrom = list(anc) + (list(anc) if spec.wgd else [])
+    n = len(chrom)
+    for _ in range(cfg.k_inv):
+        a = rng.below(n)
+        ln = 1 + rng.below(max(2, n // 20))
+        b = min(n, a + ln)
+        seg = [(f, not s) for (f, s) in reversed(chrom[a:b])]
+        chrom[a:b] = seg
+    r = cfg.r_wgd if spec.wgd else cfg.r_plain
+    out: List[Tuple[int, bool]] = []
+    for (f, s) in chrom:
+        if rng.unit() < r:
+            out.append((f, s))
+            while rng.unit() < cfg.t_tandem:
+                out.append((f, s if rng.unit() < 0.8 else (not s)))
+        if rng.unit() < cfg.noise:
+            out.append((rng.below(cfg.n_families), bool(rng.next() & 1)))
+    target = spec.n_lists * spec.genes_per_list
+    while len(out) < target:  # pad with noise genes at random positions
+        pos = rng.below(len(out) + 1)
+        out.insert(pos, (rng.below(cfg.n_families), bool(rng.next() & 1)))
+    out = out[:target]
+    lists: List[List[Gene]] = []
+    k = 0
+    for li in range(spec.n_lists):
+        lst = []
+        for _ in range(spec.genes_per_list):
+            f, s = out[k]
+            lst.append((f"{spec.name}g{k:06d}", s, f))
+            k += 1
+        lists.append(lst)
+    return lists
+
+
+def generate(cfg: SynthConfig) -> Dict[str, List[List[Gene]]]:
+    return {g.name: make_genome(cfg, g) for g in cfg.genomes}
+
+
+def write_reference_inputs(cfg: SynthConfig, outdir: str, data=None, n_threads: int = 1) -> str:
+    """Write lists/, families.tsv and <name>.ini; returns the ini path."""
+    if data is None:
+        data = generate(cfg)
+    os.makedirs(outdir, exist_ok=True)
+    fam_lines = []
+    ini = []
+    for g in cfg.genomes:
+        ini.append(f"genome= {g.name}")
+        gdir = os.path.join(outdir, "lists", g.name)
+        os.makedirs(gdir, exist_ok=True)
+        for li, lst in enumerate(data[g.name]):
+            fn = os.path.join(gdir, f"{li}.lst")
+            with open(fn, "w") as fh:
+                for (gid, s, f) in lst:
+                    fh.write(f"{gid}{'+' if s else '-'}\n")
+                    fam_lines.append(f"{gid}\tF{f}\n")
+            ini.append(f"l{li} {fn}")
+        ini.append("")
+    fam_fn = os.path.join(outdir, "families.tsv")
+    with open(fam_fn, "w") as fh:
+        fh.writelines(fam_lines)
+    os.makedirs(os.path.join(outdir, "out"), exist_ok=True)
+    ini += [
+        f"blast_table= {fam_fn}",
+        f"output_path= {os.path.join(outdir, 'out')}/",
+        "table_type= family",
+        f"gap_size= {cfg.gap_size}",
+        f"cluster_gap= {cfg.cluster_gap}",
+        f"q_value= {cfg.q_value}",
+        f"prob_cutoff= {cfg.prob_cutoff}",
+        f"anchor_points= {cfg.anchor_points}",
+        "alignment_method= gg2",
+        f"level_2_only= {'true' if cfg.level_2_only else 'false'}",
+        f"number_of_threads= {n_threads}",
+        "visualizeAlignment= false",
+        "verbose_output= false",
+    ]
+    if cfg.tandem_gap is not None:
+        ini.append(f"tandem_gap= {cfg.tandem_gap}")
+    if cfg.mult_hyp is not None:
+        ini.append(f"multiple_hypothesis_correction= {cfg.mult_hyp}")
+    for k, v in cfg.extra.items():
+        ini.append(f"{k}= {v}")
+    ini_fn = os.path.join(outdir, f"{cfg.name}.ini")
+    with open(ini_fn, "w") as fh:
+        fh.write("\n".join(ini) + "\n")
+    return ini_fn
+
+
+# ---------------------------------------------------------------------------
+# named configurations (BASELINE.json "configs", concretised in SURVEY.md 8d)
+# ---------------------------------------------------------------------------
+
+def config_tiny(seed: int = 11, mult_hyp=None, n_genomes: int = 3) -> SynthConfig:
+    """seconds-scale planted-duplication set used by the CPU test-suite."""
+    return SynthConfig(
+        name=f"tiny{seed}", n_families=400,
+        genomes=[GenomeSpec(f"t{g}", 2, 260 if g % 2 == 0 else 220, g % 2 == 0, seed * 100 + g)
+                 for g in range(n_genomes)],
+        k_inv=6, mult_hyp=mult_hyp)
+
+
+def config_small(seed: int = 21, mult_hyp=None) -> SynthConfig:
+    return SynthConfig(
+        name=f"small{seed}", n_families=3000,
+        genomes=[GenomeSpec(f"s{g}", 3, 1200, g % 2 == 0, seed * 100 + g) for g in range(4)],
+        k_inv=12, mult_hyp=mult_hyp)
+
+
+def config_c3(scale: float = 1.0) -> SynthConfig:
+    """C3: 10 genomes x 30k genes as 10 lists x 3000; F=20000."""
+    gpl = max(30, int(3000 * scale))
+    fam = max(200, int(20000 * scale))
+    return SynthConfig(
+        name="c3" if scale == 1.0 else f"c3s{scale:g}", n_families=fam, n_anc=int(fam * 1.4),
+        genomes=[GenomeSpec(f"c{g}", 10, gpl, g % 2 == 0, 1000 + g) for g in range(10)])
+
+
+def config_c4(scale: float = 1.0) -> SynthConfig:
+    """C4: 50 genomes x 25k genes as 10 lists x 2500; F=20000."""
+    gpl = max(30, int(2500 * scale))
+    fam = max(200, int(20000 * scale))
+    return SynthConfig(
+        name="c4" if scale == 1.0 else f"c4s{scale:g}", n_families=fam, n_anc=int(fam * 1.2),
+        genomes=[GenomeSpec(f"d{g}", 10, gpl, g % 2 == 0, 2000 + g) for g in range(50)])
+
+
+def config_c5(scale: float = 1.0) -> SynthConfig:
+    """C5 density stress: 4 genomes x 100k genes as 3 lists; F=2000; tandem-rich."""
+    gpl = max(60, int(33333 * scale))
+    fam = max(40, int(2000 * scale))
+    return SynthConfig(
+        name="c5" if scale == 1.0 else f"c5s{scale:g}", n_families=fam, n_anc=gpl * 3,
+        genomes=[GenomeSpec(f"e{g}", 3, gpl, g % 2 == 0, 3000 + g) for g in range(4)],
+        t_tandem=0.3, tandem_gap=10, level_2_only=True)

@@ -1,0 +1,163 @@
+/*
+ * iadhore_b200.h -- C-ABI of the B200-native collinearity engine.
+ *
+ * Drop-in boundary for i-ADHoRe 3.0's data-parallel hot path:
+ * the reference has no plugin ABI, so these entry points are exactly what a shim
+ * replacing DataSet::parallelLevel2ADHoReDyn (levelTwo.cpp:177-292) and
+ * DataSet::parallelProfileSearch (higherLevel.cpp:252-326) binds.  Everything the
+ * reference computes inside GHM::buildMatrix / GHMProfile::buildMatrix / GHM::run
+ * (GHM.cpp:34-148,157-219; GHMProfile.cpp:17-136; BaseCluster.cpp; Cluster.cpp) runs on
+ * the GPU behind these calls; results come back in the reference's own MPI wire format
+ * (Multiplicon::packMultiplicons, Multiplicon.cpp:242-264), so the host rehydrates them
+ * with the reference's unpack constructors (Multiplicon.cpp:19-96, 266-297).
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types.  All functions return 0 on
+ * success, non-zero on error (never throw); iadh_last_error() describes the last failure
+ * of the calling thread.  A context is single-caller (the reference calls the two drivers
+ * from the master thread only).  There is NO CPU fallback: iadh_create fails if no
+ * CUDA device is usable.
+ */
+#ifndef IADHORE_B200_H
+#define IADHORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IADH_OK 0
+#define IADH_ERR_ARG 1
+#define IADH_ERR_CUDA 2
+#define IADH_ERR_STATE 3
+#define IADH_ERR_CAPACITY 4
+
+/* element flag bits (dataset and profile descriptors) */
+#define IADH_F_STRAND 1u /* ListElement::getOrientation() (ListElement.h) */
+#define IADH_F_GAP 2u    /* profile only: ListElement::isGap()            */
+#define IADH_F_MASKED 4u /* dataset only: ListElement::isMasked()         */
+
+/* multiple-hypothesis correction, values of enum MultHypCor (Settings.h:23-27) */
+#define IADH_MH_NONE 0
+#define IADH_MH_BONFERRONI 1
+#define IADH_MH_FDR 2
+
+typedef struct iadh_ctx iadh_ctx;
+typedef struct iadh_result iadh_result;
+
+/* The DataSet after mapGenes() + remapTandems() + sortGeneLists() (iADHoRe.cpp:62-75),
+ * flattened: list l owns elements [list_off[l], list_off[l+1]) = its
+ * GeneList::getRemappedElements() in order.  List index == GeneList::getID().
+ *   fam     dense id of Gene::getFamily()          (GHM.cpp:49,59)
+ *   gid     dense id of the Gene::getID() string   (GHM.cpp:68; Gene.cpp:20)
+ *   num_id  ListElement::getNumID()                (GHM.cpp:691)
+ *   flags   IADH_F_STRAND | IADH_F_MASKED
+ * Two lists are "identical" (GHM.cpp:19-22) iff they are the same list index. */
+typedef struct {
+    int32_t n_lists;
+    const int64_t* list_off; /* n_lists + 1 */
+    const int32_t* fam;
+    const int32_t* gid;
+    const int32_t* num_id;
+    const uint8_t* flags;
+} iadh_dataset_desc;
+
+/* Settings surface consumed by the hot path (Settings.h:82-161, Settings.cpp:585-598). */
+typedef struct {
+    int32_t n_gaps;   /* number of valid entries of gaps[] (Settings::getGapSizes) */
+    int32_t gaps[10];
+    int32_t gap_size;
+    int32_t cluster_gap;
+    int32_t anchor_points;
+    int32_t mult_hyp; /* IADH_MH_* */
+    double q_value;
+    double prob_cutoff;
+} iadh_params;
+
+/* One aligned Profile (Profile.h: getSegments(), all S segments have L positions):
+ * element (s, x) is at index s*L + x.  flags = IADH_F_STRAND | IADH_F_GAP; fam/gid/num_id
+ * are ignored for gaps.  x_object_id = getSegments()[0]->getID() (GHMProfile.cpp:13). */
+typedef struct {
+    int32_t n_segments; /* S; multiplicon level of the results is S + 1 */
+    int32_t length;     /* L */
+    int32_t x_object_id;
+    const int32_t* fam;
+    const int32_t* gid;
+    const int32_t* num_id;
+    const uint8_t* flags;
+} iadh_profile_desc;
+
+typedef struct {
+    int64_t n_ghm;           /* GHMs evaluated (list pairs or profile x list)            */
+    int64_t n_dots;          /* anchor-point candidates emitted by the build kernels      */
+    int64_t n_multiplicons;  /* multiplicons in the packed stream                         */
+    int64_t n_baseclusters;
+    int64_t n_anchorpoints;
+    double build_ms;         /* device time of the GHM build kernels (CUDA events)        */
+    double cluster_ms;       /* device time of the clustering kernel                      */
+    double total_ms;         /* device time of the whole call incl. copies                */
+    int64_t kernel_launches; /* kernels launched by this call                             */
+    int64_t h2d_bytes, d2h_bytes;
+} iadh_stats;
+
+/* Replaces: DataSet ownership of the flattened lists; called once after
+ * DataSet::sortGeneLists() (iADHoRe.cpp:75).  `device` = CUDA ordinal. */
+int iadh_create(const iadh_dataset_desc* ds, int device, iadh_ctx** out);
+void iadh_destroy(iadh_ctx* ctx);
+
+/* Replaces: the Settings getters read inside GHM::runCollinear (GHM.cpp:157-219). */
+int iadh_set_params(iadh_ctx* ctx, const iadh_params* p);
+
+/* Replaces: DataSet::level2ADHoRe over every list pair (levelTwo.cpp:32-96) in the
+ * 1-thread order of getSomeWorkL2 (levelTwo.cpp:113-175) over lists sorted big->small
+ * (DataSet.cpp:1088-1105).  rank/n_ranks shard the pair sequence by the greedy
+ * least-loaded rule of getProcForPackage (levelTwo.cpp:98-111,142-148); the result holds
+ * this rank's multiplicons in sequence order.  Use rank=0,n_ranks=1 for everything. */
+int iadh_level2_all_pairs(iadh_ctx* ctx, int rank, int n_ranks, iadh_result** out);
+
+/* Same work for an explicit pair list (x_list[i], y_list[i]); results in that order. */
+int iadh_level2_pairs(iadh_ctx* ctx, const int32_t* x_list, const int32_t* y_list,
+                      int64_t n_pairs, iadh_result** out);
+
+/* Replaces: GeneList::mask (GeneList.cpp:283-287) as called at higherLevel.cpp:165-171. */
+int iadh_mask_range(iadh_ctx* ctx, int32_t list, int32_t begin, int32_t end);
+int iadh_clear_masks(iadh_ctx* ctx);
+
+/* Replaces: DataSet::profileSearch over every list (higherLevel.cpp:32-48) for one
+ * profile: lists big->small in the static partition of ParToolBox::statPartWorklSort
+ * (parallel.cpp:96-156) for (rank, n_ranks); lists with fewer than anchor_points unmasked
+ * elements are skipped (higherLevel.cpp:40-41).  Multiplicons are returned BEFORE the
+ * homolog-count filter of GHMProfile.cpp:129-132 (it needs the parent's Link set, host
+ * state); the shim re-applies it after unpacking. */
+int iadh_profile_search(iadh_ctx* ctx, const iadh_profile_desc* profile, int rank, int n_ranks,
+                        iadh_result** out);
+
+/* Packed stream, byte-for-byte Multiplicon::packMultiplicons (Multiplicon.cpp:242-264):
+ * int32 nMultiplicons, then per multiplicon the 33-byte header, per base cluster the
+ * 102-byte header (BaseCluster.cpp:751-797), per anchor point 17 bytes (AnchorPoint.h:103). */
+const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n_bytes);
+/* Per multiplicon: index of the GHM (position in the pair / list sequence) it came from. */
+const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n_multiplicons);
+int iadh_result_stats(const iadh_result* r, iadh_stats* out);
+void iadh_free_result(iadh_result* r);
+
+/* Test/measurement hook: the dot sets of the build kernels alone (GHM.cpp:34-85 /
+ * GHMProfile.cpp:17-59) for explicit L2 pairs or, if profile != NULL, for profile x
+ * y_list[i].  Writes per GHM counts cnt[2*i+o] and the concatenated (x,y) int32 pairs
+ * (orientation 0 block then orientation 1 block per GHM, each sorted by x then y) into a
+ * library-owned buffer valid until the next call on ctx. */
+int iadh_build_dots(iadh_ctx* ctx, const iadh_profile_desc* profile, const int32_t* x_list,
+                    const int32_t* y_list, int64_t n, const int64_t** cnt_out,
+                    const int32_t** dots_out, int64_t* n_dots_out);
+
+/* hpmath::omxn (hpmath.cpp:18-36) evaluated on the device for n inputs (KAT hook). */
+int iadh_omxn(iadh_ctx* ctx, const double* x, const int32_t* n, int64_t count, double* out);
+
+const char* iadh_last_error(void);
+const char* iadh_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IADHORE_B200_H */

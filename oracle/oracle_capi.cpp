@@ -1,0 +1,328 @@
+// TEST INFRASTRUCTURE -- not part of the product (see oracle_core.h).
+//
+// The oracle behind the same C interface as include/iadhore_b200.h (prefix oracle_
+// instead of iadh_), so a parity test drives both with identical calls.
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/iadhore_b200.h"
+#include "oracle_core.h"
+
+using namespace oracle;
+
+struct oracle_ctx {
+    std::vector<List> lists;
+    std::vector<int> index_to_list;
+    Params prm;
+    int n_threads = 1;
+};
+
+struct oracle_result {
+    std::vector<uint8_t> bytes;
+    std::vector<int32_t> ghm_index;
+    iadh_stats stats;
+    // build_dots scratch
+    std::vector<int64_t> cnt;
+    std::vector<int32_t> dots;
+};
+
+static thread_local std::string g_err;
+
+// DataSet.cpp:1088-1105: multimap<weight,list> walked in reverse => size descending,
+// equal sizes in descending list index (T10)
+static void sort_lists(oracle_ctx* c)
+{
+    std::multimap<uint64_t, unsigned> w;
+    for (unsigned l = 0; l < c->lists.size(); l++) w.insert(std::make_pair((uint64_t)c->lists[l].size(), l));
+    c->index_to_list.clear();
+    for (std::multimap<uint64_t, unsigned>::reverse_iterator it = w.rbegin(); it != w.rend(); ++it)
+        c->index_to_list.push_back(it->second);
+}
+
+// levelTwo.cpp:113-175 (pair walk) + 98-111 (least-loaded rank)
+static void pair_sequence(const oracle_ctx* c, int rank, int n_ranks, std::vector<std::pair<int, int>>& out)
+{
+    unsigned n = c->lists.size();
+    std::vector<uint64_t> wpp(n_ranks, 0);
+    unsigned cX = 0, cY = 0;
+    while (cX < n) {
+        unsigned lX = c->index_to_list[cX], lY = c->index_to_list[cY];
+        uint64_t weight = (unsigned)c->lists[lX].size() * (unsigned)c->lists[lY].size();
+        unsigned sp = 0;
+        for (unsigned p = 0; p < wpp.size(); p++)
+            if (wpp[p] < wpp[sp]) sp = p;
+        wpp[sp] += weight;
+        if ((int)sp == rank) out.push_back(std::make_pair((int)lX, (int)lY));
+        if ((cX - cY) < 2) {
+            if (cX == cY && cX == n - 1) break;
+            unsigned newD = cX + cY + 1;
+            cX = (newD < n) ? newD : n - 1;
+            cY = (newD < n) ? 0 : newD - n + 1;
+        } else {
+            cX--;
+            cY++;
+        }
+    }
+}
+
+// parallel.cpp:96-156: LPT partition of the size-sorted lists over n_ranks packages
+static void list_partition(const oracle_ctx* c, int rank, int n_ranks, std::vector<int>& out)
+{
+    std::multimap<uint64_t, unsigned> w;
+    for (unsigned l = 0; l < c->lists.size(); l++) w.insert(std::make_pair((uint64_t)c->lists[l].size(), l));
+    std::vector<uint64_t> wpp(n_ranks, 0);
+    for (std::multimap<uint64_t, unsigned>::reverse_iterator it = w.rbegin(); it != w.rend(); ++it) {
+        unsigned sp = 0;
+        for (unsigned p = 0; p < wpp.size(); p++)
+            if (wpp[p] < wpp[sp]) sp = p;
+        wpp[sp] += it->first;
+        if ((int)sp == rank) out.push_back((int)it->second);
+    }
+}
+
+extern "C" {
+
+int oracle_create(const iadh_dataset_desc* ds, int /*device*/, oracle_ctx** out)
+{
+    if (!ds || !out || ds->n_lists < 0) { g_err = "bad dataset"; return IADH_ERR_ARG; }
+    oracle_ctx* c = new oracle_ctx();
+    c->lists.resize(ds->n_lists);
+    for (int l = 0; l < ds->n_lists; l++) {
+        List& L = c->lists[l];
+        L.id = l;
+        for (int64_t i = ds->list_off[l]; i < ds->list_off[l + 1]; i++) {
+            L.fam.push_back(ds->fam[i]);
+            L.gid.push_back(ds->gid[i]);
+            L.num_id.push_back(ds->num_id[i]);
+            L.strand.push_back((ds->flags[i] & IADH_F_STRAND) ? 1 : 0);
+            L.masked.push_back((ds->flags[i] & IADH_F_MASKED) ? 1 : 0);
+        }
+    }
+    sort_lists(c);
+    c->prm.n_gaps = gap_sizes(30, c->prm.gaps);
+    *out = c;
+    return IADH_OK;
+}
+
+void oracle_destroy(oracle_ctx* c) { delete c; }
+
+int oracle_set_threads(oracle_ctx* c, int n) { c->n_threads = n < 1 ? 1 : n; return IADH_OK; }
+
+int oracle_set_params(oracle_ctx* c, const iadh_params* p)
+{
+    c->prm.n_gaps = p->n_gaps;
+    for (int i = 0; i < 10; i++) c->prm.gaps[i] = i < p->n_gaps ? p->gaps[i] : 0;
+    c->prm.gap_size = p->gap_size;
+    c->prm.cluster_gap = p->cluster_gap;
+    c->prm.anchor_points = p->anchor_points;
+    c->prm.mult_hyp = p->mult_hyp;
+    c->prm.q_value = p->q_value;
+    c->prm.prob_cutoff = p->prob_cutoff;
+    return IADH_OK;
+}
+
+}  // extern "C"
+
+struct GhmOut {
+    std::vector<uint8_t> bytes;
+    int n_mult = 0;
+    int64_t dots = 0, ncl = 0, nap = 0;
+    double build_s = 0, run_s = 0;
+};
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static void run_pair(const oracle_ctx* c, int lx, int ly, GhmOut& o)
+{
+    GHMInput g;
+    double t0 = now_s();
+    build_l2(c->lists[lx], c->lists[ly], lx == ly, g);
+    double t1 = now_s();
+    o.dots = g.cnt[0] + g.cnt[1];
+    std::vector<Cluster> cl;
+    std::vector<Multiplicon> ms;
+    run_collinear(g, c->prm, cl, ms);
+    set_multiplicons_l2(c->lists[lx], c->lists[ly], cl, ms);
+    o.build_s = t1 - t0;
+    o.run_s = now_s() - t1;
+    pack(cl, ms, o.bytes, o.n_mult);
+    for (const Multiplicon& m : ms) {
+        o.ncl += m.clusters.size();
+        for (int ci : m.clusters) o.nap += cl[ci].aps.size();
+    }
+}
+
+static void run_profile(const oracle_ctx* c, const Profile& P, int ly, GhmOut& o)
+{
+    GHMInput g;
+    double t0 = now_s();
+    build_hl(P, c->lists[ly], g);
+    double t1 = now_s();
+    o.dots = g.cnt[0] + g.cnt[1];
+    std::vector<Cluster> cl;
+    std::vector<Multiplicon> ms;
+    run_collinear(g, c->prm, cl, ms);
+    set_multiplicons_hl(P, c->lists[ly], cl, ms);
+    o.build_s = t1 - t0;
+    o.run_s = now_s() - t1;
+    pack(cl, ms, o.bytes, o.n_mult);
+    for (const Multiplicon& m : ms) {
+        o.ncl += m.clusters.size();
+        for (int ci : m.clusters) o.nap += cl[ci].aps.size();
+    }
+}
+
+template <typename F>
+static oracle_result* run_many(const oracle_ctx* c, size_t n, F fn)
+{
+    std::vector<GhmOut> outs(n);
+    double t0 = now_s();
+    int nt = c->n_threads;
+    if (nt <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) fn(i, outs[i]);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                for (size_t i = t; i < n; i += nt) fn(i, outs[i]);
+            });
+        for (std::thread& t : th) t.join();
+    }
+    double t1 = now_s();
+    oracle_result* r = new oracle_result();
+    memset(&r->stats, 0, sizeof(r->stats));
+    int32_t total = 0;
+    r->bytes.resize(4);
+    for (size_t i = 0; i < n; i++) {
+        r->bytes.insert(r->bytes.end(), outs[i].bytes.begin(), outs[i].bytes.end());
+        for (int k = 0; k < outs[i].n_mult; k++) r->ghm_index.push_back((int32_t)i);
+        total += outs[i].n_mult;
+        r->stats.n_dots += outs[i].dots;
+        r->stats.n_baseclusters += outs[i].ncl;
+        r->stats.n_anchorpoints += outs[i].nap;
+        r->stats.build_ms += outs[i].build_s * 1e3;
+        r->stats.cluster_ms += outs[i].run_s * 1e3;
+    }
+    memcpy(r->bytes.data(), &total, 4);
+    r->stats.n_ghm = (int64_t)n;
+    r->stats.n_multiplicons = total;
+    r->stats.total_ms = (t1 - t0) * 1e3;
+    return r;
+}
+
+extern "C" {
+
+int oracle_level2_pairs(oracle_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, oracle_result** out)
+{
+    *out = run_many(c, (size_t)n, [&](size_t i, GhmOut& o) { run_pair(c, xs[i], ys[i], o); });
+    return IADH_OK;
+}
+
+int oracle_level2_all_pairs(oracle_ctx* c, int rank, int n_ranks, oracle_result** out)
+{
+    std::vector<std::pair<int, int>> seq;
+    pair_sequence(c, rank, n_ranks, seq);
+    *out = run_many(c, seq.size(), [&](size_t i, GhmOut& o) { run_pair(c, seq[i].first, seq[i].second, o); });
+    return IADH_OK;
+}
+
+int oracle_mask_range(oracle_ctx* c, int32_t list, int32_t begin, int32_t end)
+{
+    if (list < 0 || list >= (int)c->lists.size()) { g_err = "bad list"; return IADH_ERR_ARG; }
+    for (int i = begin; i <= end; i++) c->lists[list].masked[i] = 1;
+    return IADH_OK;
+}
+
+int oracle_clear_masks(oracle_ctx* c)
+{
+    for (List& l : c->lists) std::fill(l.masked.begin(), l.masked.end(), 0);
+    return IADH_OK;
+}
+
+}  // extern "C"
+static void to_profile(const iadh_profile_desc* p, Profile& P)
+{
+    P.S = p->n_segments;
+    P.L = p->length;
+    P.x_object_id = p->x_object_id;
+    size_t n = (size_t)P.S * P.L;
+    P.fam.assign(p->fam, p->fam + n);
+    P.gid.assign(p->gid, p->gid + n);
+    P.num_id.assign(p->num_id, p->num_id + n);
+    P.flags.assign(p->flags, p->flags + n);
+}
+
+extern "C" {
+int oracle_profile_search(oracle_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, oracle_result** out)
+{
+    Profile P;
+    to_profile(p, P);
+    std::vector<int> part, lists;
+    list_partition(c, rank, n_ranks, part);
+    for (int l : part) {  // higherLevel.cpp:40-41
+        unsigned masked = 0;
+        for (uint8_t m : c->lists[l].masked) masked += m;
+        if ((unsigned)c->lists[l].size() - masked >= (unsigned)c->prm.anchor_points) lists.push_back(l);
+    }
+    *out = run_many(c, lists.size(), [&](size_t i, GhmOut& o) { run_profile(c, P, lists[i], o); });
+    return IADH_OK;
+}
+
+const uint8_t* oracle_result_bytes(const oracle_result* r, size_t* n)
+{
+    *n = r->bytes.size();
+    return r->bytes.data();
+}
+const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
+{
+    *n = r->ghm_index.size();
+    return r->ghm_index.data();
+}
+int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; return IADH_OK; }
+void oracle_free_result(oracle_result* r) { delete r; }
+
+static oracle_result g_scratch;
+int oracle_build_dots(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys,
+                      int64_t n, const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)
+{
+    Profile P;
+    if (p) to_profile(p, P);
+    g_scratch.cnt.clear();
+    g_scratch.dots.clear();
+    for (int64_t i = 0; i < n; i++) {
+        GHMInput g;
+        if (p) build_hl(P, c->lists[ys[i]], g);
+        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g);
+        for (int o = 0; o < 2; o++) {
+            g_scratch.cnt.push_back((int64_t)g.dots[o].size());
+            for (const std::pair<int, int>& d : g.dots[o]) {
+                g_scratch.dots.push_back(d.first);
+                g_scratch.dots.push_back(d.second);
+            }
+        }
+    }
+    *cnt_out = g_scratch.cnt.data();
+    *dots_out = g_scratch.dots.data();
+    *n_dots_out = (int64_t)g_scratch.dots.size() / 2;
+    return IADH_OK;
+}
+
+int oracle_omxn(oracle_ctx*, const double* x, const int32_t* n, int64_t count, double* out)
+{
+    for (int64_t i = 0; i < count; i++) out[i] = omxn(x[i], n[i]);
+    return IADH_OK;
+}
+
+int oracle_gap_sizes(int gap_size, int32_t* gaps) { return gap_sizes(gap_size, gaps); }
+
+const char* oracle_last_error(void) { return g_err.c_str(); }
+const char* oracle_version(void) { return "oracle-port-1"; }
+
+}  // extern "C"

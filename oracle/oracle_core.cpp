@@ -1,0 +1,757 @@
+// TEST INFRASTRUCTURE -- not part of the product (see oracle_core.h).
+//
+// Sequential CPU restatement of the collinear hot path of i-ADHoRe 3.0.  Written
+// against SURVEY.md Appendix A; each function names the reference lines it
+// follows.  Build with -ffp-contract=off: the reference is plain x86-64 -O3 and
+// contains no fused multiply-adds, and every FP expression below keeps the
+// reference's evaluation order.
+#include "oracle_core.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace oracle {
+
+// ---------------------------------------------------------------------------
+// Cluster.cpp:5-25
+static inline int dpd_i(int x1, int y1, int x2, int y2)
+{
+    int dx = std::abs(x1 - x2), dy = std::abs(y1 - y2);
+    return dx < dy ? 2 * dy - dx : 2 * dx - dy;
+}
+static inline double dpd_d(double x1, double y1, double x2, double y2)
+{
+    double dx = std::fabs(x1 - x2), dy = std::fabs(y1 - y2);
+    return dx < dy ? 2 * dy - dx : 2 * dx - dy;
+}
+
+// Settings.cpp:585-598
+int gap_sizes(int gap_size, int* gaps)
+{
+    int nr = 0;
+    double step = (std::log(gap_size) / std::log(3) - 1) / 9;
+    for (int i = 0; i < 10; i++) {
+        int value = (int)std::round(std::pow(3, (1 + (i * step))));
+        if (i == 0 || value != gaps[nr - 1]) gaps[nr++] = value;
+    }
+    for (int i = nr; i < 10; i++) gaps[i] = 0;
+    return nr;
+}
+
+// hpmath.cpp:18-36
+double omxn(double x, int n)
+{
+    if (std::abs(x) > 0.1) return std::pow(1.0 - x, n);
+    const double epsilon = std::abs(x * DBL_EPSILON);
+    double term = 1.0, result = term;
+    int i = 0;
+    while ((std::abs(term) > epsilon) && i != n) {
+        i++;
+        term = -term * (n - i + 1.0) / (i * 1.0) * x;
+        result += term;
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------
+// GHM.cpp:34-85: family-hash join, family mode.  Masks are ignored (T11).
+void build_l2(const List& X, const List& Y, bool identical, GHMInput& g)
+{
+    g.dots[0].clear();
+    g.dots[1].clear();
+    g.cnt[0] = g.cnt[1] = 0;
+    std::map<int, std::vector<int>> tree;  // family -> y positions, ascending
+    for (int y = 0; y < Y.size(); y++) tree[Y.fam[y]].push_back(y);
+    for (int x = 0; x < X.size(); x++) {
+        std::map<int, std::vector<int>>::const_iterator it = tree.find(X.fam[x]);
+        if (it == tree.end()) continue;
+        for (int y : it->second) {
+            if (identical && y > x) continue;      // GHM.cpp:64
+            if (X.gid[x] == Y.gid[y]) continue;    // GHM.cpp:68 (ID strings, T15)
+            int o = (X.strand[x] == Y.strand[y]) ? 1 : 0;
+            g.dots[o].insert(std::make_pair(x, y));
+            g.cnt[o]++;
+        }
+    }
+    // GHM.cpp:221-236, 32-bit unsigned arithmetic (T8); level 2 => no masked rows
+    unsigned int nx = (unsigned)X.size(), ny = (unsigned)Y.size();
+    g.area = identical ? (unsigned int)(nx * (nx - 1) / 2) : (unsigned int)(nx * ny);
+    g.level = 2;
+    g.x_object_id = X.id;
+    g.y_object_id = Y.id;
+}
+
+// GHMProfile.cpp:17-59: every segment, every non-gap position against every
+// non-gap, non-masked y element (ListElement.cpp:20-30), same family and a
+// different gene ID (Gene.cpp:17-30); counted on first insert only.
+void build_hl(const Profile& P, const List& Y, GHMInput& g)
+{
+    g.dots[0].clear();
+    g.dots[1].clear();
+    g.cnt[0] = g.cnt[1] = 0;
+    for (int s = 0; s < P.S; s++)
+        for (int x = 0; x < P.L; x++) {
+            int k = s * P.L + x;
+            if (P.flags[k] & 2) continue;
+            for (int y = 0; y < Y.size(); y++) {
+                if (Y.masked[y]) continue;
+                if (P.fam[k] != Y.fam[y] || P.gid[k] == Y.gid[y]) continue;
+                int o = ((P.flags[k] & 1) == Y.strand[y]) ? 1 : 0;
+                if (g.dots[o].insert(std::make_pair(x, y)).second) g.cnt[o]++;
+            }
+        }
+    // GHM.cpp:221-236 with level > 2: masked rows are subtracted; |X| = L
+    unsigned int masked = 0;
+    for (int y = 0; y < Y.size(); y++) masked += Y.masked[y] ? 1 : 0;
+    unsigned int nx = (unsigned)P.L, ny = (unsigned)Y.size();
+    g.area = (unsigned int)(nx * (ny - masked));
+    g.level = P.S + 1;               // GHMProfile.cpp:14
+    g.x_object_id = P.x_object_id;   // GHM base x_object = segment 0 (GHMProfile.cpp:13)
+    g.y_object_id = Y.id;
+}
+
+// ---------------------------------------------------------------------------
+// BaseCluster arithmetic
+
+// multiset<AnchorPoint>::insert: after the last element with x <= X
+static void ap_insert(Cluster& c, const AP& p)
+{
+    std::vector<AP>::iterator it = c.aps.begin();
+    // upper_bound on x
+    it = std::upper_bound(c.aps.begin(), c.aps.end(), p.x,
+                          [](int x, const AP& q) { return x < q.x; });
+    c.aps.insert(it, p);
+    c.b = 0.0;  // BaseCluster.cpp:60,84
+}
+static void add_ap(Cluster& c, int x, int y)
+{
+    AP p;
+    p.x = x;
+    p.y = y;
+    ap_insert(c, p);
+}
+// set<AnchorPoint>::insert on x: a second point with the same x is dropped
+static void add_backbone(Cluster& c, int x, int y)
+{
+    std::vector<std::pair<int, int>>::iterator it = std::lower_bound(
+        c.backbone.begin(), c.backbone.end(), x,
+        [](const std::pair<int, int>& q, int xx) { return q.first < xx; });
+    if (it != c.backbone.end() && it->first == x) return;
+    c.backbone.insert(it, std::make_pair(x, y));
+}
+
+// BaseCluster.cpp:146-180 / 182-221.  Sums of int products (T7) held in doubles.
+static double r2_from(const Cluster& c, const Cluster* other, int X, int Y)
+{
+    double sum_x = 0, sum_y = 0, sum_xy = 0, sum_x2 = 0, sum_y2 = 0;
+    unsigned int n = 0;
+    for (const AP& e : c.aps) {
+        sum_x += e.x; sum_y += e.y; sum_xy += e.x * e.y; sum_x2 += e.x * e.x; sum_y2 += e.y * e.y;
+        n++;
+    }
+    if (other) {
+        for (const AP& e : other->aps) {
+            sum_x += e.x; sum_y += e.y; sum_xy += e.x * e.y; sum_x2 += e.x * e.x; sum_y2 += e.y * e.y;
+            n++;
+        }
+    } else if (X != 0 || Y != 0) {  // T6: (0,0) is silently ignored
+        sum_x += X; sum_y += Y; sum_xy += X * Y; sum_x2 += X * X; sum_y2 += Y * Y;
+        n++;
+    }
+    double value = ((sum_x2 - sum_x * sum_x / n) * (sum_y2 - sum_y * sum_y / n));
+    if (value == 0) return -1;
+    double r = (sum_xy - (sum_x * sum_y / n)) / std::sqrt(value);
+    return r * r;
+}
+
+// BaseCluster.cpp:266-291
+static void regression(Cluster& c)
+{
+    double N = (double)c.aps.size();
+    if (N < 3.0) return;
+    double sum_x = 0.0, sum_y = 0.0, sum_xy = 0.0, sum_x2 = 0.0;
+    for (const AP& e : c.aps) {
+        sum_x += e.x; sum_y += e.y; sum_xy += e.x * e.y; sum_x2 += e.x * e.x;
+    }
+    c.avg_x = sum_x / N;
+    double avg_y = sum_y / N;
+    c.var_x = (sum_x2 - N * c.avg_x * c.avg_x) / (N - 1.0);
+    double cov_xy = (sum_xy - N * c.avg_x * avg_y) / (N - 1.0);
+    c.b = cov_xy / c.var_x;
+    c.a = avg_y - c.b * c.avg_x;
+}
+
+// BaseCluster.cpp:238-264
+static void update_stats(Cluster& c)
+{
+    if (c.b != 0.0) return;
+    int N = (int)c.aps.size();
+    regression(c);
+    c.var_x = 0.0;
+    c.mrss = 0.0;
+    for (const AP& e : c.aps) {
+        double y_est = c.b * e.x + c.a;
+        c.mrss += (e.y - y_est) * (e.y - y_est);
+        c.var_x += (e.x - c.avg_x) * (e.x - c.avg_x);
+    }
+    c.mrss = c.mrss / (N - 2);
+    c.var_x = c.var_x / (N - 1);
+    c.x_end1 = (unsigned int)c.aps.front().x;
+    c.x_end2 = (unsigned int)c.aps.back().x;
+    c.y_end1 = c.x_end1 * c.b + c.a;
+    c.y_end2 = c.x_end2 * c.b + c.a;
+}
+
+// BaseCluster.cpp:293-304
+static double dist_to_point(const Cluster& c, int x, int y)
+{
+    if (x >= c.x_end1 && x <= c.x_end2) return 0;
+    if ((double)x < c.x_end1) return dpd_d((double)x, (double)y, c.x_end1, c.y_end1);
+    return dpd_d((double)x, (double)y, c.x_end2, c.y_end2);
+}
+
+// BaseCluster.cpp:306-336
+static bool in_interval(Cluster& c, int x, int y)
+{
+    update_stats(c);
+    double n = (double)c.aps.size();
+    double pi = 1.96 * std::sqrt(c.mrss) *
+                std::sqrt(1.0 + 1.0 / n + (x - c.avg_x) * (x - c.avg_x) / (n - 1) / c.var_x);
+    double up = (c.a + c.b * x) + pi;
+    double down = (c.a + c.b * x) - pi;
+    return y >= down && y <= up;
+}
+
+// BaseCluster.cpp:353-364
+static bool intersect(double x1, double y1, double x2, double y2, double x3, double y3,
+                      double x4, double y4)
+{
+    double ud = (y4 - y3) * (x2 - x1) - (x4 - x3) * (y2 - y1);
+    if (ud != 0) {
+        double ua = ((x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3)) / ud;
+        double ub = ((x2 - x1) * (y1 - y3) - (y2 - y1) * (x1 - x3)) / ud;
+        if (ua >= 0 && ua <= 1 && ub >= 0 && ub <= 1) return true;
+    }
+    return false;
+}
+static inline double mind(double a, double b) { return (a < b) ? a : b; }
+static inline double maxd(double a, double b) { return (a > b) ? a : b; }
+
+// BaseCluster.cpp:376-396
+static double point_line_dpd(double x1, double y1, double x2, double y2, double x3, double y3)
+{
+    double dx = x2 - x1, dy = y2 - y1, x0, y0;
+    if ((dx == 0) && (dy == 0)) {
+        x0 = x1;
+        y0 = y1;
+    } else {
+        double t = ((x3 - x1) * dx + (y3 - y1) * dy) / (dx * dx + dy * dy);
+        t = mind(maxd(0, t), 1);
+        x0 = x1 + t * dx;
+        y0 = y1 + t * dy;
+    }
+    return dpd_d(x0, y0, x3, y3);
+}
+
+// BaseCluster.cpp:398-465
+static double dist_to_cluster(Cluster& A, Cluster& B)
+{
+    update_stats(A);
+    update_stats(B);
+    if (intersect(A.x_end1, A.y_end1, A.x_end2, A.y_end2, B.x_end1, B.y_end1, B.x_end2, B.y_end2))
+        return 0;
+    double lo = point_line_dpd(A.x_end1, A.y_end1, A.x_end2, A.y_end2, B.x_end1, B.y_end1);
+    lo = mind(lo, point_line_dpd(A.x_end1, A.y_end1, A.x_end2, A.y_end2, B.x_end2, B.y_end2));
+    lo = mind(lo, point_line_dpd(B.x_end1, B.y_end1, B.x_end2, B.y_end2, A.x_end1, A.y_end1));
+    lo = mind(lo, point_line_dpd(B.x_end1, B.y_end1, B.x_end2, B.y_end2, A.x_end2, A.y_end2));
+    const AP &s1 = A.aps.front(), &e1 = A.aps.back(), &s2 = B.aps.front(), &e2 = B.aps.back();
+    lo = mind(lo, (double)dpd_i(s1.x, s1.y, s2.x, s2.y));
+    lo = mind(lo, (double)dpd_i(s1.x, s1.y, e2.x, e2.y));
+    lo = mind(lo, (double)dpd_i(e1.x, e1.y, s2.x, s2.y));
+    lo = mind(lo, (double)dpd_i(e1.x, e1.y, e2.x, e2.y));
+    lo = mind(lo, point_line_dpd(A.x_end1, A.y_end1, A.x_end2, A.y_end2, s2.x, s2.y));
+    lo = mind(lo, point_line_dpd(A.x_end1, A.y_end1, A.x_end2, A.y_end2, e2.x, e2.y));
+    lo = mind(lo, point_line_dpd(B.x_end1, B.y_end1, B.x_end2, B.y_end2, s1.x, s1.y));
+    lo = mind(lo, point_line_dpd(B.x_end1, B.y_end1, B.x_end2, B.y_end2, e1.x, e1.y));
+    return lo;
+}
+
+// BaseCluster.cpp:491-546
+static bool partial_overlap(Cluster& A, Cluster& B)
+{
+    update_stats(A);
+    update_stats(B);
+    int x1min = A.aps.front().x, x1max = A.aps.back().x;
+    for (const AP& e : B.aps)
+        if (e.x >= x1min && e.x <= x1max)
+            if (!in_interval(A, e.x, e.y)) return false;
+    int x2min = B.aps.front().x, x2max = B.aps.back().x;
+    for (const AP& e : A.aps)
+        if (e.x >= x2min && e.x <= x2max)
+            if (!in_interval(B, e.x, e.y)) return false;
+    return true;
+}
+
+// BaseCluster.cpp:338-351
+static void merge_with(Cluster& A, const Cluster& B)
+{
+    for (const AP& e : B.aps) add_ap(A, e.x, e.y);
+    for (const std::pair<int, int>& q : B.backbone) add_backbone(A, q.first, q.second);
+    A.b = 0.0;
+    update_stats(A);
+}
+
+// BaseCluster.cpp:548-590 (including the never-advancing it2 quirk, T6)
+static double calc_probability(Cluster& c, double area, double points)
+{
+    double density = (double)points / (double)area;
+    double probability = 1.0;
+    for (size_t i = 1; i < c.backbone.size(); i++) {
+        double distance = dpd_d(c.backbone[i - 1].first, c.backbone[i - 1].second,
+                                c.backbone[i].first, c.backbone[i].second);
+        int cc = (int)std::ceil(0.5 * distance * distance);
+        double p_i = 1.0 - std::pow(1.0 - density, cc);
+        probability *= p_i;
+    }
+    // duplicates of the FIRST anchor point are erased; b is not touched
+    if (!c.aps.empty()) {
+        AP first = c.aps.front();
+        std::vector<AP> keep;
+        keep.push_back(first);
+        for (size_t i = 1; i < c.aps.size(); i++)
+            if (!(c.aps[i].x == first.x && c.aps[i].y == first.y)) keep.push_back(c.aps[i]);
+        c.aps.swap(keep);
+    }
+    return probability;
+}
+
+// BaseCluster.cpp:700-719
+static void twist(Cluster& c)
+{
+    int max_y = c.aps.front().y, min_y = c.aps.front().y;
+    for (const AP& e : c.aps) {
+        max_y = std::max(max_y, e.y);
+        min_y = std::min(min_y, e.y);
+    }
+    for (AP& e : c.aps) e.y = max_y + min_y - e.y;  // x-keyed order is unchanged
+    c.b = 0.0;
+    update_stats(c);
+}
+
+static unsigned real_count(const Cluster& c)
+{
+    unsigned n = 0;
+    for (const AP& e : c.aps) n += e.real ? 1 : 0;
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// GHM pipeline state
+
+struct GHMState {
+    GHMInput& g;
+    const Params& prm;
+    // clusters live in a pool; BC[o] holds pool indices in vector order
+    std::vector<Cluster>& pool;
+    std::vector<int> BC[2];
+    std::vector<Multiplicon>& mults;
+    GHMState(GHMInput& g_, const Params& p_, std::vector<Cluster>& pool_, std::vector<Multiplicon>& m_)
+        : g(g_), prm(p_), pool(pool_), mults(m_) {}
+};
+
+// GHM.cpp:238-285
+static void seed_chain(const DotSet& mat, Cluster& c, int gap)
+{
+    bool orientation = c.orient;
+    int refX = c.aps.front().x, refY = c.aps.front().y;
+    while (true) {
+        int loX = refX + 1, hiX = refX + gap;
+        int loY = orientation ? refY + 1 : refY - gap;
+        int hiY = orientation ? refY + gap : refY - 1;
+        int closestX = 0, closestY = 0, closestDpd = gap + 1;
+        DotSet::const_iterator it = mat.lower_bound(std::make_pair(loX, INT32_MIN));
+        for (; it != mat.end() && it->first <= hiX; ++it) {
+            int x = it->first, y = it->second;
+            if (y < loY || y > hiY) continue;
+            int d = dpd_i(refX, refY, x, y);
+            if (d < closestDpd) {
+                closestDpd = d;
+                closestX = x;
+                closestY = y;
+            }
+        }
+        if (closestDpd == gap + 1) return;
+        add_ap(c, closestX, closestY);
+        add_backbone(c, closestX, closestY);
+        refX = closestX;
+        refY = closestY;
+    }
+}
+
+// GHM.cpp:287-324
+static void seed_base_clusters(GHMState& s, int gap, int orientation)
+{
+    DotSet& mat = s.g.dots[orientation];
+    DotSet::iterator it = mat.begin();
+    while (it != mat.end()) {
+        Cluster c;
+        c.orient = orientation != 0;
+        add_ap(c, it->first, it->second);
+        add_backbone(c, it->first, it->second);
+        seed_chain(mat, c, gap);
+        if (c.aps.size() > 2 && r2_from(c, NULL, 0, 0) >= s.prm.q_value) {
+            update_stats(c);
+            std::pair<int, int> cur = *it;
+            for (const AP& e : c.aps) mat.erase(std::make_pair(e.x, e.y));
+            it = mat.upper_bound(cur);
+            s.pool.push_back(c);
+            s.BC[orientation].push_back((int)s.pool.size() - 1);
+        } else {
+            ++it;
+        }
+    }
+}
+
+// GHM.cpp:331-390
+static void enrich_clusters(GHMState& s, int gap, int clusterOrientation, int ghmOrientation)
+{
+    std::vector<int> clusters(s.BC[clusterOrientation]);
+    DotSet& mat = s.g.dots[ghmOrientation];
+    const double q = s.prm.q_value;
+    while (!clusters.empty()) {
+        std::vector<int> next;
+        std::vector<bool> changed(clusters.size(), false);
+        DotSet::iterator it = mat.begin();
+        while (it != mat.end()) {
+            int x = it->first, y = it->second;
+            double closestDistance = gap + 1;
+            int closest = -1;
+            for (size_t k = 0; k < clusters.size(); k++) {
+                Cluster& c = s.pool[clusters[k]];
+                update_stats(c);
+                double distance = dist_to_point(c, x, y);
+                if (distance >= closestDistance) continue;
+                if (r2_from(c, NULL, x, y) >= q && in_interval(c, x, y)) {
+                    closestDistance = distance;
+                    closest = (int)k;
+                }
+            }
+            if (closest != -1) {
+                Cluster& c = s.pool[clusters[closest]];
+                add_ap(c, x, y);
+                update_stats(c);
+                if (!changed[closest]) {
+                    next.push_back(clusters[closest]);
+                    changed[closest] = true;
+                }
+                it = mat.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        clusters.swap(next);
+    }
+}
+
+// GHM.cpp:406-444; returns positions in BC[orientI] / BC[orientJ]
+static bool closest_clusters(GHMState& s, int gap, int orientI, int orientJ, int& ci, int& cj)
+{
+    std::vector<int>& bcI = s.BC[orientI];
+    std::vector<int>& bcJ = s.BC[orientJ];
+    double closestDistance = gap + 1;
+    for (size_t i = 0; i < bcI.size(); i++) {
+        size_t j = (orientI == orientJ) ? i + 1 : 0;
+        for (; j < bcJ.size(); j++) {
+            Cluster& cI = s.pool[bcI[i]];
+            Cluster& cJ = s.pool[bcJ[j]];
+            if (cI.mult >= 0 && cJ.mult >= 0 && cI.mult == cJ.mult) continue;
+            double distance = dist_to_cluster(cI, cJ);
+            if (distance < closestDistance) {
+                if (partial_overlap(cI, cJ)) {
+                    if (r2_from(cI, &cJ, 0, 0) >= s.prm.q_value) {
+                        ci = (int)i;
+                        cj = (int)j;
+                        closestDistance = distance;
+                    }
+                }
+            }
+        }
+    }
+    return closestDistance < gap + 1;
+}
+
+// GHM.cpp:392-404
+static void join_clusters(GHMState& s, int gap, int orient)
+{
+    int i, j;
+    while (closest_clusters(s, gap, orient, orient, i, j)) {
+        merge_with(s.pool[s.BC[orient][i]], s.pool[s.BC[orient][j]]);
+        s.BC[orient].erase(s.BC[orient].begin() + j);
+    }
+}
+
+// GHM.cpp:446-469 (none), 481-503 (Bonferroni), 516-540 (FDR)
+static void filter_clusters(GHMState& s)
+{
+    const double cutoff = s.prm.prob_cutoff;
+    for (int orient = 0; orient < 2; orient++) {
+        std::vector<int>& bc = s.BC[orient];
+        if (s.prm.mult_hyp == 2) {
+            for (int idx : bc) {
+                Cluster& c = s.pool[idx];
+                c.p = calc_probability(c, (double)s.g.area, (double)s.g.cnt[orient]);
+            }
+            std::vector<Cluster>& pool = s.pool;
+            std::sort(bc.begin(), bc.end(), [&pool](int l, int r) { return pool[l].p < pool[r].p; });
+            size_t k;
+            for (k = 0; k < bc.size(); k++)
+                if (s.pool[bc[k]].p > (int)(k + 1) * cutoff / s.g.cnt[orient]) break;
+            bc.erase(bc.begin() + k, bc.end());  // NOT re-inserted into the matrix (T6)
+        } else {
+            size_t i = 0;
+            while (i < bc.size()) {
+                Cluster& c = s.pool[bc[i]];
+                c.p = calc_probability(c, (double)s.g.area, (double)s.g.cnt[orient]);
+                double thr = (s.prm.mult_hyp == 1) ? (cutoff / s.g.cnt[orient]) : cutoff;
+                if (c.p > thr) {
+                    for (const AP& e : c.aps) s.g.dots[orient].insert(std::make_pair(e.x, e.y));
+                    bc.erase(bc.begin() + i);
+                } else {
+                    i++;
+                }
+            }
+        }
+    }
+}
+
+// GHM.cpp:542-625
+static void cluster_clusters(GHMState& s)
+{
+    const int clusterGap = s.prm.cluster_gap;
+    bool join_flag = true;
+    while (join_flag) {
+        join_flag = false;
+        for (int k = 0; k < 4; k++) {
+            int or_x = (k < 2) ? 1 : 0;
+            int or_y = (k % 2 == 0) ? 1 : 0;
+            bool was_twisted = (or_x != or_y);
+            if (was_twisted)
+                for (int idx : s.BC[or_y]) twist(s.pool[idx]);
+            int pi = -1, pj = -1;
+            bool found = closest_clusters(s, clusterGap, or_x, or_y, pi, pj);
+            if (was_twisted)
+                for (int idx : s.BC[or_y]) twist(s.pool[idx]);
+            if (found && (!was_twisted || !s.pool[s.BC[or_x][pi]].was_twisted)) {
+                int cI = s.BC[or_x][pi], cJ = s.BC[or_y][pj];
+                s.pool[cJ].was_twisted = was_twisted;
+                join_flag = true;
+                if (s.pool[cI].mult >= 0 && s.pool[cJ].mult >= 0) {
+                    int mi = s.pool[cI].mult, mj = s.pool[cJ].mult;
+                    for (int c : s.mults[mj].clusters) {
+                        s.pool[c].mult = mi;
+                        s.mults[mi].clusters.push_back(c);
+                    }
+                    s.mults[mj].clusters.clear();
+                } else if (s.pool[cI].mult >= 0 || s.pool[cJ].mult >= 0) {
+                    if (s.pool[cI].mult < 0) std::swap(cI, cJ);
+                    s.pool[cJ].mult = s.pool[cI].mult;
+                    s.mults[s.pool[cI].mult].clusters.push_back(cJ);
+                } else {
+                    Multiplicon m;
+                    m.x_object_id = s.g.x_object_id;
+                    m.y_object_id = s.g.y_object_id;
+                    m.level = s.g.level;
+                    m.clusters.push_back(cI);
+                    m.clusters.push_back(cJ);
+                    s.mults.push_back(m);
+                    s.pool[cI].mult = s.pool[cJ].mult = (int)s.mults.size() - 1;
+                }
+            }
+        }
+    }
+    for (int k = 0; k < 2; k++)
+        for (int idx : s.BC[k])
+            if (s.pool[idx].mult < 0) {
+                Multiplicon m;
+                m.x_object_id = s.g.x_object_id;
+                m.y_object_id = s.g.y_object_id;
+                m.level = s.g.level;
+                s.pool[idx].was_twisted = false;
+                m.clusters.push_back(idx);
+                s.mults.push_back(m);
+                s.pool[idx].mult = (int)s.mults.size() - 1;
+            }
+    // drop empty multiplicons and those with too few real anchor points
+    std::vector<Multiplicon> kept;
+    for (Multiplicon& m : s.mults) {
+        unsigned cnt = 0;
+        for (int c : m.clusters) cnt += real_count(s.pool[c]);
+        if (m.clusters.empty() || cnt < (unsigned)s.prm.anchor_points) continue;
+        kept.push_back(m);
+    }
+    s.mults.swap(kept);
+}
+
+// GHM.cpp:157-219 (everything except setMultiplicons)
+void run_collinear(GHMInput& g, const Params& prm, std::vector<Cluster>& clusters,
+                   std::vector<Multiplicon>& mults)
+{
+    clusters.clear();
+    mults.clear();
+    if ((g.cnt[0] + g.cnt[1]) < (unsigned int)prm.anchor_points) return;
+    GHMState s(g, prm, clusters, mults);
+    for (int i = 0; i < 10 && i < prm.n_gaps && prm.gaps[i] > 0; i++) {
+        seed_base_clusters(s, prm.gaps[i], 0);
+        enrich_clusters(s, prm.gaps[i], 0, 0);
+        join_clusters(s, prm.gaps[i], 0);
+        seed_base_clusters(s, prm.gaps[i], 1);
+        enrich_clusters(s, prm.gaps[i], 1, 1);
+        join_clusters(s, prm.gaps[i], 1);
+    }
+    for (int rep = 0; rep < 2; rep++) {
+        enrich_clusters(s, prm.gap_size, 0, 0);
+        enrich_clusters(s, prm.gap_size, 1, 1);
+        enrich_clusters(s, prm.gap_size, 1, 0);
+        enrich_clusters(s, prm.gap_size, 0, 1);
+        if (rep == 0) filter_clusters(s);
+    }
+    cluster_clusters(s);
+}
+
+// Cluster.h:27-33 + BaseCluster.cpp:99-140 + Multiplicon.cpp:135-193
+static void set_bounds(std::vector<Cluster>& clusters, Multiplicon& m)
+{
+    bool first = true;
+    for (int ci : m.clusters) {
+        Cluster& c = clusters[ci];
+        unsigned lx = c.aps.front().x, hx = c.aps.back().x;
+        unsigned ly = c.aps.front().y, hy = c.aps.front().y;
+        for (const AP& e : c.aps) {
+            ly = std::min<unsigned>(ly, e.y);
+            hy = std::max<unsigned>(hy, e.y);
+        }
+        if (first || real_count(c) > 0) {
+            if (first) {
+                m.begin_x = lx; m.end_x = hx; m.begin_y = ly; m.end_y = hy;
+            } else {
+                if (lx < (unsigned)m.begin_x) m.begin_x = lx;
+                if (hx > (unsigned)m.end_x) m.end_x = hx;
+                if (ly < (unsigned)m.begin_y) m.begin_y = ly;
+                if (hy > (unsigned)m.end_y) m.end_y = hy;
+            }
+        }
+        first = false;
+        c.begin_x = lx; c.end_x = hx; c.begin_y = ly; c.end_y = hy;
+    }
+}
+
+// GHM.cpp:671-701
+void set_multiplicons_l2(const List& X, const List& Y, std::vector<Cluster>& clusters,
+                         std::vector<Multiplicon>& mults)
+{
+    for (Multiplicon& m : mults) {
+        set_bounds(clusters, m);
+        for (int ci : m.clusters)
+            for (AP& e : clusters[ci].aps) {
+                e.gx = X.num_id[e.x];
+                e.gy = Y.num_id[e.y];
+            }
+    }
+}
+
+// GHMProfile.cpp:68-136 (without the createHomologs filter, which needs host state)
+void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& clusters,
+                         std::vector<Multiplicon>& mults)
+{
+    for (Multiplicon& m : mults) {
+        set_bounds(clusters, m);
+        for (int ci : m.clusters) {
+            Cluster& c = clusters[ci];
+            // filterDuplicates (BaseCluster.cpp:63-75): unique (x,y), sorted by x then y
+            std::vector<AP> uniq(c.aps);
+            std::stable_sort(uniq.begin(), uniq.end(), [](const AP& l, const AP& r) {
+                return l.x != r.x ? l.x < r.x : l.y < r.y;
+            });
+            uniq.erase(std::unique(uniq.begin(), uniq.end(),
+                                   [](const AP& l, const AP& r) { return l.x == r.x && l.y == r.y; }),
+                       uniq.end());
+            c.aps.swap(uniq);
+            std::vector<AP> falses;
+            for (AP& e : c.aps) {
+                bool first_match = false;
+                for (int n = 0; n < P.S; n++) {
+                    int k = n * P.L + e.x;
+                    if (P.flags[k] & 2) continue;
+                    if (!(P.fam[k] == Y.fam[e.y] && P.gid[k] != Y.gid[e.y])) continue;
+                    if (first_match) {
+                        AP f;
+                        f.gx = P.num_id[k]; f.gy = Y.num_id[e.y]; f.x = e.x; f.y = e.y; f.real = false;
+                        falses.push_back(f);
+                    } else {
+                        e.gx = P.num_id[k];
+                        e.gy = Y.num_id[e.y];
+                        first_match = true;
+                    }
+                }
+            }
+            for (const AP& f : falses) ap_insert(c, f);  // sets b = 0.0 (BaseCluster.cpp:82-85)
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+static void put(std::vector<uint8_t>& out, const T& v)
+{
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    out.insert(out.end(), p, p + sizeof(T));
+}
+
+void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& mults,
+          std::vector<uint8_t>& out, int& n_mult_total)
+{
+    for (const Multiplicon& m : mults) {
+        put<int32_t>(out, m.x_object_id);
+        put<int32_t>(out, m.y_object_id);
+        put<int32_t>(out, m.level);
+        put<uint8_t>(out, 0);  // isRedundant
+        put<int32_t>(out, m.begin_x);
+        put<int32_t>(out, m.end_x);
+        put<int32_t>(out, m.begin_y);
+        put<int32_t>(out, m.end_y);
+        put<int32_t>(out, (int32_t)m.clusters.size());
+        for (int ci : m.clusters) {
+            const Cluster& c = clusters[ci];
+            put<double>(out, c.p);
+            put<uint8_t>(out, c.orient ? 1 : 0);
+            put<double>(out, c.a);
+            put<double>(out, c.b);
+            put<double>(out, c.avg_x);
+            put<double>(out, c.var_x);
+            put<double>(out, c.mrss);
+            put<double>(out, c.x_end1);
+            put<double>(out, c.x_end2);
+            put<double>(out, c.y_end1);
+            put<double>(out, c.y_end2);
+            put<uint8_t>(out, c.was_twisted ? 1 : 0);
+            put<int32_t>(out, c.begin_x);
+            put<int32_t>(out, c.end_x);
+            put<int32_t>(out, c.begin_y);
+            put<int32_t>(out, c.end_y);
+            put<int32_t>(out, (int32_t)c.aps.size());
+            for (const AP& e : c.aps) {
+                put<int32_t>(out, e.gx);
+                put<int32_t>(out, e.gy);
+                put<int32_t>(out, e.x);
+                put<int32_t>(out, e.y);
+                put<uint8_t>(out, e.real ? 1 : 0);
+            }
+        }
+        n_mult_total++;
+    }
+}
+
+}  // namespace oracle
