@@ -1,0 +1,276 @@
+// K1: GHM / GHMProfile anchor-point matrix build (family-hash join).
+//
+// Replaces GHM::buildMatrixFast (GHM.cpp:34-85) and GHMProfile::buildMatrix
+// (GHMProfile.cpp:17-59; ListElement::matchingPositions ListElement.cpp:20-30;
+// Gene::isPairWith Gene.cpp:17-30).  The reference hashes family *strings* per pair (L2)
+// or brute-forces S*L*|Y| string compares (HL); here families are dense ints and a
+// dataset-wide CSR (family -> ascending global element indices) is built once, so a
+// column's partners inside list Y are one binary search into its family bucket.
+//
+// Work decomposition: one warp per tile of 32 consecutive columns of one GHM, lane = column.
+// Pass 1 counts dots per (tile, orientation) and per GHM; after a per-GHM exclusive scan of
+// the tile counts, pass 2 re-walks the buckets and writes the dots as packed keys
+// (x<<16|y), already in the (x ascending, y ascending) order of the reference's
+// map<int,set<int>> -- no sort needed.  HBM-bound: algorithmic bytes per GHM are
+// 5*(|X|+|Y|) element bytes read + 4*D key bytes written.
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int lo, int hi, int v)
+{
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total)
+{
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+// find the GHM owning global tile index t: largest g with tile_prefix[g] <= t
+__device__ __forceinline__ int find_ghm(const int64_t* __restrict__ tile_prefix, int n_ghm, int64_t t)
+{
+    int lo = 0, hi = n_ghm;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_prefix[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// L2: column x of list X against list Y (GHM.cpp:52-84).  Masks are ignored.
+template <bool FILL>
+__device__ __forceinline__ void l2_column(const DatasetDev& ds, int xg, int x, int64_t yoff, int ylen,
+                                          bool identical, int& c0, int& c1, uint32_t* __restrict__ keys,
+                                          int64_t o0, int64_t o1)
+{
+    const int f = ds.fam[xg];
+    const int gx = ds.gid[xg];
+    const int sx = ds.flags[xg] & 1;
+    const int b0 = ds.fam_ptr[f], b1 = ds.fam_ptr[f + 1];
+    int m = lower_bound_i32(ds.fam_members, b0, b1, (int)yoff);
+    const int yend = (int)(yoff + ylen);
+    for (; m < b1; m++) {
+        const int yg = ds.fam_members[m];
+        if (yg >= yend) break;
+        const int y = yg - (int)yoff;
+        if (identical && y > x) break;      // GHM.cpp:64 (members ascend, so all later y fail too)
+        if (ds.gid[yg] == gx) continue;     // GHM.cpp:68
+        if ((ds.flags[yg] & 1) == sx) {
+            if (FILL) keys[o1 + c1] = MAKE_KEY(x, y);
+            c1++;
+        } else {
+            if (FILL) keys[o0 + c0] = MAKE_KEY(x, y);
+            c0++;
+        }
+    }
+}
+
+// HL: column x of the profile (all segments, merged through the column's groups) against the
+// non-masked elements of list Y (GHMProfile.cpp:25-57).  Emits every y once per orientation,
+// ascending.
+template <bool FILL>
+__device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev& pf, int x, int64_t yoff,
+                                          int ylen, int& c0, int& c1, uint32_t* __restrict__ keys, int64_t o0,
+                                          int64_t o1)
+{
+    const int g0 = pf.col_ptr[x], g1 = pf.col_ptr[x + 1];
+    if (g0 == g1) return;
+    const int yend = (int)(yoff + ylen);
+    int last = (int)yoff - 1;  // global index of the last candidate handled
+    while (true) {
+        int best = yend;
+        for (int g = g0; g < g1; g++) {
+            const int f = pf.grp_fam[g];
+            const int b0 = ds.fam_ptr[f], b1 = ds.fam_ptr[f + 1];
+            const int m = lower_bound_i32(ds.fam_members, b0, b1, last + 1);
+            if (m < b1) {
+                const int yg = ds.fam_members[m];
+                if (yg < best) best = yg;
+            }
+        }
+        if (best >= yend) break;
+        last = best;
+        const uint8_t fl = ds.flags[best];
+        if (fl & 4) continue;  // masked y elements are invisible (ListElement.cpp:25)
+        const int fy = ds.fam[best], gy = ds.gid[best], sy = fl & 1;
+        bool e0 = false, e1 = false;
+        for (int g = g0; g < g1; g++) {
+            if (pf.grp_fam[g] != fy) continue;
+            const int gg = pf.grp_gid[g];
+            if (gg >= 0 && gg == gy) continue;  // Gene.cpp:20: ID != other.ID
+            if (pf.grp_strand[g] == sy) e1 = true;
+            else e0 = true;
+        }
+        const int y = best - (int)yoff;
+        if (e0) {
+            if (FILL) keys[o0 + c0] = MAKE_KEY(x, y);
+            c0++;
+        }
+        if (e1) {
+            if (FILL) keys[o1 + c1] = MAKE_KEY(x, y);
+            c1++;
+        }
+    }
+}
+
+template <bool HL, bool FILL>
+__global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf, GhmTask* __restrict__ tasks,
+                                                    int n_ghm, const int64_t* __restrict__ tile_prefix,
+                                                    int64_t n_tiles, uint32_t* __restrict__ tile_cnt,
+                                                    const uint32_t* __restrict__ tile_off,
+                                                    uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
+        const int g = find_ghm(tile_prefix, n_ghm, t);
+        const GhmTask task = tasks[g];
+        const int x0 = (int)(t - tile_prefix[g]) * 32;
+        const int64_t yoff = ds.list_off[task.y_list];
+        const int ylen = (int)(ds.list_off[task.y_list + 1] - yoff);
+        int nx;
+        int64_t xoff = 0;
+        if (HL) nx = pf.L;
+        else {
+            xoff = ds.list_off[task.x_list];
+            nx = (int)(ds.list_off[task.x_list + 1] - xoff);
+        }
+        const int x = x0 + lane;
+        int c0 = 0, c1 = 0;
+        if (!FILL) {
+            if (x < nx) {
+                if (HL) hl_column<false>(ds, pf, x, yoff, ylen, c0, c1, nullptr, 0, 0);
+                else l2_column<false>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, nullptr, 0, 0);
+            }
+            int t0, t1;
+            warp_excl_scan(c0, lane, t0);
+            warp_excl_scan(c1, lane, t1);
+            // per-lane counts are kept (2 x uint16 would overflow for huge families): the fill
+            // pass recomputes them; only tile totals are stored.
+            if (lane == 0) {
+                tile_cnt[2 * t] = (uint32_t)t0;
+                tile_cnt[2 * t + 1] = (uint32_t)t1;
+                if (t0) atomicAdd(&tasks[g].cnt[0], (uint32_t)t0);
+                if (t1) atomicAdd(&tasks[g].cnt[1], (uint32_t)t1);
+            }
+        } else {
+            // pass 2: lane offsets = tile offset + exclusive scan of the recomputed lane counts
+            if (x < nx) {
+                if (HL) hl_column<false>(ds, pf, x, yoff, ylen, c0, c1, nullptr, 0, 0);
+                else l2_column<false>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, nullptr, 0, 0);
+            }
+            int t0, t1;
+            const int e0 = warp_excl_scan(c0, lane, t0);
+            const int e1 = warp_excl_scan(c1, lane, t1);
+            if (t0 + t1 == 0) continue;
+            const int64_t base0 = task.dot_off + tile_off[2 * t];
+            const int64_t base1 = task.dot_off + task.cnt[0] + tile_off[2 * t + 1];
+            c0 = c1 = 0;
+            if (x < nx) {
+                if (HL) hl_column<true>(ds, pf, x, yoff, ylen, c0, c1, keys, base0 + e0, base1 + e1);
+                else l2_column<true>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, keys, base0 + e0, base1 + e1);
+            }
+        }
+    }
+}
+
+// per-GHM exclusive scan of the tile counts (one warp per GHM)
+__global__ void __launch_bounds__(256) tile_scan_kernel(const int64_t* __restrict__ tile_prefix, int n_ghm,
+                                                        const uint32_t* __restrict__ tile_cnt,
+                                                        uint32_t* __restrict__ tile_off)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_ghm) return;
+    const int64_t t0 = tile_prefix[g], t1 = tile_prefix[g + 1];
+    int run0 = 0, run1 = 0;
+    for (int64_t t = t0; t < t1; t += 32) {
+        const int64_t tt = t + lane;
+        int a = 0, b = 0;
+        if (tt < t1) {
+            a = (int)tile_cnt[2 * tt];
+            b = (int)tile_cnt[2 * tt + 1];
+        }
+        int ta, tb;
+        const int ea = warp_excl_scan(a, lane, ta);
+        const int eb = warp_excl_scan(b, lane, tb);
+        if (tt < t1) {
+            tile_off[2 * tt] = (uint32_t)(run0 + ea);
+            tile_off[2 * tt + 1] = (uint32_t)(run1 + eb);
+        }
+        run0 += ta;
+        run1 += tb;
+    }
+}
+
+// GeneList::mask (GeneList.cpp:283-287)
+__global__ void mask_kernel(uint8_t* flags, int64_t begin, int64_t end, int set)
+{
+    int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= end) flags[i] = set ? (flags[i] | 4) : (flags[i] & ~4);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+
+static inline int grid_for(int64_t warps_needed, int sm_count)
+{
+    int64_t blocks = (warps_needed + 7) / 8;
+    int64_t cap = (int64_t)sm_count * 8;  // 8 CTAs x 256 threads = 2048 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+void launch_build_count(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmTask* tasks, int n_ghm,
+                        const int64_t* tile_prefix, int64_t n_tiles, uint32_t* tile_cnt, int sm_count,
+                        cudaStream_t st)
+{
+    if (n_tiles == 0) return;
+    int grid = grid_for(n_tiles, sm_count);
+    if (hl) build_kernel<true, false><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, tile_cnt, nullptr, nullptr);
+    else build_kernel<false, false><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, tile_cnt, nullptr, nullptr);
+}
+
+void launch_tile_scan(const int64_t* tile_prefix, int n_ghm, const uint32_t* tile_cnt, uint32_t* tile_off,
+                      cudaStream_t st)
+{
+    if (n_ghm == 0) return;
+    tile_scan_kernel<<<(n_ghm + 7) / 8, 256, 0, st>>>(tile_prefix, n_ghm, tile_cnt, tile_off);
+}
+
+void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmTask* tasks, int n_ghm,
+                       const int64_t* tile_prefix, int64_t n_tiles, const uint32_t* tile_off, uint32_t* keys,
+                       int sm_count, cudaStream_t st)
+{
+    if (n_tiles == 0) return;
+    int grid = grid_for(n_tiles, sm_count);
+    if (hl) build_kernel<true, true><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
+    else build_kernel<false, true><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
+}
+
+void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st)
+{
+    int64_t n = end - begin + 1;
+    if (n <= 0) return;
+    mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, begin, end, set);
+}

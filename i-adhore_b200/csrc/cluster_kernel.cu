@@ -1,0 +1,1014 @@
+// K2: collinear-cluster detection inside one GHM -- one CTA per GHM, persistent grid.
+//
+// Replaces GHM::runCollinear (GHM.cpp:157-219) and everything below it: seedBaseClusters
+// (GHM.cpp:238-324), enrichClusters (331-390), joinClusters / getClosestClusters (392-444),
+// filterBaseClusters{,BF,FDR} (446-540) with BaseCluster::calculateProbability
+// (BaseCluster.cpp:548-590), clusterClusters / twistClusters (542-632).
+//
+// The reference's passes are order-dependent greedy loops; results must be bit-identical, so
+// the CTA never reorders *decisions*.  It parallelises the search inside each decision:
+//   seed   : successor pointers nxt[d] (argmin-dpd dot in d's window) are computed for all dots
+//            in parallel; chains are pointer walks; 256 start dots are evaluated at once and the
+//            first accepted one (in dot order) is committed, then only pointers into erased
+//            dots are repaired.
+//   enrich : 256 dots x all active clusters evaluated at once; the first assignable dot is
+//            committed, later dots of the batch re-test only the changed cluster.
+//   join   : all cluster pairs evaluated in parallel, lexicographic-first minimum reduced.
+// State lives in a per-GHM workspace in HBM (L2-resident for all but the densest GHMs).
+#include <cuda_runtime.h>
+
+#include "cluster_math.cuh"
+#include "common.h"
+#include "workspace.h"
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = NT / 32;
+
+struct Ghm {
+    uint32_t* key[2];
+    uint8_t* alive[2];
+    int nk[2];
+    int* nxt;
+    uint32_t* pool;
+    uint8_t* pflag;
+    int pool_cap, pool_used;
+    ClusterRec* cl;
+    int ncl, cl_cap;
+    int* bc[2];
+    int nbc[2];
+    int* act;
+    int* act_next;
+    uint8_t* changed;
+    MultRec* mult;
+    int nmult;
+    int* out_mults;
+    uint32_t* tmp;
+    int tmp_cap;
+    int status;
+    // task constants
+    uint32_t cnt[2];
+    double area;
+    int level;
+};
+
+struct Red {
+    double d[NW];
+    long long k[NW];
+    int i[NW];
+};
+
+// ---- block reductions -------------------------------------------------------------------
+
+// minimum int over the block (INT_MAX = none); two barriers
+__device__ int block_min_int(int v, int* sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int r = sh[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) r = min(r, sh[i]);
+    __syncthreads();
+    return r;
+}
+
+// lexicographic minimum of (dist, idx); idx < 0 = none
+__device__ void block_min_pair(double& d, long long& k, Red* sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, s);
+        const long long ok = __shfl_xor_sync(0xffffffffu, k, s);
+        if (ok >= 0 && (k < 0 || od < d || (od == d && ok < k))) {
+            d = od;
+            k = ok;
+        }
+    }
+    if (lane == 0) {
+        sh->d[w] = d;
+        sh->k[w] = k;
+    }
+    __syncthreads();
+    d = sh->d[0];
+    k = sh->k[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) {
+        const double od = sh->d[i];
+        const long long ok = sh->k[i];
+        if (ok >= 0 && (k < 0 || od < d || (od == d && ok < k))) {
+            d = od;
+            k = ok;
+        }
+    }
+    __syncthreads();
+}
+
+// ---- AP pool ------------------------------------------------------------------------------
+
+__device__ int pool_alloc(Ghm& g, int n)
+{
+    // single-thread contexts only
+    if (g.pool_used + n > g.pool_cap) {
+        g.status = 1;
+        return -1;
+    }
+    const int off = g.pool_used;
+    g.pool_used += n;
+    return off;
+}
+
+__device__ __forceinline__ int next_cap(int n)
+{
+    int c = 8;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+// multiset<AnchorPoint>::insert (BaseCluster.cpp:58-61): after the last AP with x <= X
+__device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
+{
+    if (c.n == c.cap) {
+        const int ncap = c.cap * 2;
+        const int noff = pool_alloc(g, ncap);
+        if (noff < 0) return false;
+        for (int i = 0; i < c.n; i++) {
+            g.pool[noff + i] = g.pool[c.off + i];
+            g.pflag[noff + i] = g.pflag[c.off + i];
+        }
+        c.off = noff;
+        c.cap = ncap;
+    }
+    const int x = KEY_X(key);
+    int lo = 0, hi = c.n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEY_X(g.pool[c.off + mid]) <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    for (int i = c.n; i > lo; i--) {
+        g.pool[c.off + i] = g.pool[c.off + i - 1];
+        g.pflag[c.off + i] = g.pflag[c.off + i - 1];
+    }
+    g.pool[c.off + lo] = key;
+    g.pflag[c.off + lo] = 0;
+    c.n++;
+    const long long X = x, Y = KEY_Y(key);
+    c.sx += X; c.sy += Y; c.sxy += X * Y; c.sxx += X * X; c.syy += Y * Y;
+    return true;
+}
+
+// BaseCluster::mergeWith (BaseCluster.cpp:338-351): B's APs are inserted one by one, i.e. a
+// stable merge with A's APs first on equal x; B's backbone points are dropped where A already
+// has a backbone point with the same x (set<AnchorPoint> on x).
+__device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B)
+{
+    const int n = A.n + B.n;
+    if (n > A.cap) {
+        const int ncap = next_cap(n);
+        const int noff = pool_alloc(g, ncap);
+        if (noff < 0) return false;
+        for (int i = 0; i < A.n; i++) {
+            g.pool[noff + i] = g.pool[A.off + i];
+            g.pflag[noff + i] = g.pflag[A.off + i];
+        }
+        A.off = noff;
+        A.cap = ncap;
+    }
+    int ia = A.n - 1, ib = B.n - 1, k = n - 1;
+    while (ib >= 0) {
+        const uint32_t kb = g.pool[B.off + ib];
+        if (ia >= 0 && KEY_X(g.pool[A.off + ia]) > KEY_X(kb)) {
+            g.pool[A.off + k] = g.pool[A.off + ia];
+            g.pflag[A.off + k] = g.pflag[A.off + ia];
+            ia--;
+        } else {
+            uint8_t fl = g.pflag[B.off + ib];
+            if (fl) {
+                for (int j = ia; j >= 0 && KEY_X(g.pool[A.off + j]) == KEY_X(kb); j--)
+                    if (g.pflag[A.off + j]) {
+                        fl = 0;
+                        break;
+                    }
+            }
+            g.pool[A.off + k] = kb;
+            g.pflag[A.off + k] = fl;
+            ib--;
+        }
+        k--;
+    }
+    A.n = n;
+    A.sx += B.sx; A.sy += B.sy; A.sxy += B.sxy; A.sxx += B.sxx; A.syy += B.syy;
+    cm::update_stats(A, g.pool);
+    return true;
+}
+
+// ---- seed ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ int lower_bound_key(const uint32_t* a, int lo, int hi, uint32_t v)
+{
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// GHM::seedBaseCluster inner search (GHM.cpp:248-276): closest alive dot in the window, strict
+// '<' so the first in (x,y) order wins ties; only dpd <= gap qualifies.
+__device__ int window_next(const uint32_t* key, const uint8_t* alive, int n, int i,
+                           int gap, int orient)
+{
+    const uint32_t k = key[i];
+    const int rx = KEY_X(k), ry = KEY_Y(k);
+    const int loY = orient ? ry + 1 : ry - gap;
+    const int hiY = orient ? ry + gap : ry - 1;
+    const int hiX = rx + gap;
+    int best = gap + 1, bj = -1;
+    int j = lower_bound_key(key, i + 1, n, MAKE_KEY(rx + 1, 0));
+    for (; j < n; j++) {
+        const uint32_t kj = key[j];
+        const int x = KEY_X(kj);
+        if (x > hiX) break;
+        const int y = KEY_Y(kj);
+        if (y < loY || y > hiY || !alive[j]) continue;
+        const int d = cm::dpd_i(rx, ry, x, y);
+        if (d < best) {
+            best = d;
+            bj = j;
+        }
+    }
+    return bj;
+}
+
+// GHM::seedBaseClusters (GHM.cpp:287-324)
+__device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s)
+{
+    const int tid = threadIdx.x;
+    const uint32_t* key = g.key[o];
+    uint8_t* alive = g.alive[o];
+    const int n = g.nk[o];
+    int* nxt = g.nxt;
+    for (int i = tid; i < n; i += NT) nxt[i] = alive[i] ? window_next(key, alive, n, i, gap, o) : -1;
+    __syncthreads();
+    int base = 0;
+    while (base < n) {
+        const int i = base + tid;
+        bool acc = false;
+        if (i < n && alive[i] && nxt[i] >= 0 && nxt[nxt[i]] >= 0) {
+            long long sx = 0, sy = 0, sxy = 0, sxx = 0, syy = 0;
+            unsigned len = 0;
+            for (int j = i; j >= 0; j = nxt[j]) {
+                const uint32_t k = key[j];
+                const long long x = KEY_X(k), y = KEY_Y(k);
+                sx += x; sy += y; sxy += x * y; sxx += x * x; syy += y * y;
+                len++;
+            }
+            acc = cm::r2_sums(sx, sy, sxy, sxx, syy, len) >= q;  // len > 2 by construction
+        }
+        const int first = block_min_int(acc ? tid : 0x7fffffff, sh_i);
+        if (first == 0x7fffffff) {
+            base += NT;
+            continue;
+        }
+        if (tid == first) {
+            // commit: new base cluster from the chain (GHM.cpp:301-311)
+            int len = 0;
+            for (int j = i; j >= 0; j = nxt[j]) len++;
+            const int cap = next_cap(len + (len >> 1));
+            const int off = pool_alloc(g, cap);
+            if (off >= 0 && g.ncl < g.cl_cap) {
+                ClusterRec& c = g.cl[g.ncl];
+                c.off = off; c.cap = cap; c.n = len;
+                c.mult = -1; c.mnext = -1; c.orient = (unsigned char)o; c.was_twisted = 0; c.dead = 0;
+                c.a = 0; c.b = 0; c.avg_x = 0; c.p = 0;
+                int w = 0, lastj = i;
+                for (int j = i; j >= 0; j = nxt[j]) {
+                    g.pool[off + w] = key[j];
+                    g.pflag[off + w] = 1;
+                    alive[j] = 0;
+                    lastj = j;
+                    w++;
+                }
+                cm::recompute_sums(c, g.pool);
+                cm::update_stats(c, g.pool);
+                g.bc[o][g.nbc[o]++] = g.ncl;
+                g.ncl++;
+                sh_s[0] = lastj;
+            } else {
+                g.status = 1;
+                sh_s[0] = -1;
+            }
+        }
+        __syncthreads();
+        if (g.status) return;
+        {
+            // repair successor pointers that point into the erased chain
+            const int lastj = sh_s[0];
+            const int cx = KEY_X(key[base + first]);
+            const int lo = lower_bound_key(key, 0, n, MAKE_KEY(max(cx - gap, 0), 0));
+            for (int j = lo + tid; j < lastj; j += NT)
+                if (alive[j] && nxt[j] >= 0 && !alive[nxt[j]]) nxt[j] = window_next(key, alive, n, j, gap, o);
+        }
+        base = base + first + 1;
+        __syncthreads();
+    }
+}
+
+// ---- enrich -------------------------------------------------------------------------------
+
+// one (dot, cluster) test of GHM::enrichClusters (GHM.cpp:352-365)
+__device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
+{
+    dist = cm::dist_to_point(c, x, y);
+    if (dist >= limit) return false;
+    return cm::r2_with_point(c, x, y) >= q && cm::in_interval(c, x, y);
+}
+
+__device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i, int* sh_s)
+{
+    const int tid = threadIdx.x;
+    const uint32_t* key = g.key[om];
+    uint8_t* alive = g.alive[om];
+    const int n = g.nk[om];
+    int nact = g.nbc[oc];
+    for (int i = tid; i < nact; i += NT) g.act[i] = g.bc[oc][i];
+    __syncthreads();
+    int* act = g.act;
+    int* act_next = g.act_next;
+    while (nact > 0) {
+        for (int i = tid; i < nact; i += NT) g.changed[i] = 0;
+        if (tid == 0) sh_s[1] = 0;  // number of clusters in the next round
+        __syncthreads();
+        for (int base = 0; base < n; base += NT) {
+            const int i = base + tid;
+            bool mine = (i < n) && alive[i];
+            int x = 0, y = 0;
+            double bd = gap + 1;
+            int bk = -1;
+            if (mine) {
+                x = KEY_X(key[i]);
+                y = KEY_Y(key[i]);
+                for (int k = 0; k < nact; k++) {
+                    double d;
+                    if (enrich_test(g.cl[act[k]], x, y, bd, q, d)) {
+                        bd = d;
+                        bk = k;
+                    }
+                }
+            }
+            int from = 0;
+            while (true) {
+                const int first = block_min_int((bk >= 0 && tid >= from) ? tid : 0x7fffffff, sh_i);
+                if (first == 0x7fffffff) break;
+                if (tid == first) {
+                    ClusterRec& c = g.cl[act[bk]];
+                    if (insert_ap(g, c, key[i])) {
+                        cm::update_stats(c, g.pool);
+                        if (!g.changed[bk]) {
+                            g.changed[bk] = 1;
+                            act_next[sh_s[1]++] = act[bk];
+                        }
+                        alive[i] = 0;
+                    }
+                    sh_s[0] = bk;
+                    bk = -1;
+                    mine = false;
+                }
+                __syncthreads();
+                if (g.status) return;
+                const int kc = sh_s[0];
+                if (mine && tid > first) {
+                    if (bk == kc) {
+                        bd = gap + 1;
+                        bk = -1;
+                        for (int k = 0; k < nact; k++) {
+                            double d;
+                            if (enrich_test(g.cl[act[k]], x, y, bd, q, d)) {
+                                bd = d;
+                                bk = k;
+                            }
+                        }
+                    } else {
+                        double d;
+                        // the changed cluster wins if strictly closer, or equally close and earlier
+                        const double limit = (bk >= 0 && kc < bk) ? nextafter(bd, 1e300) : bd;
+                        if (enrich_test(g.cl[act[kc]], x, y, limit, q, d)) {
+                            bd = d;
+                            bk = kc;
+                        }
+                    }
+                }
+                from = first + 1;
+                // (block_min_int's barriers order these reads against the next commit)
+            }
+        }
+        __syncthreads();
+        nact = sh_s[1];
+        int* t = act;
+        act = act_next;
+        act_next = t;
+        __syncthreads();
+    }
+}
+
+// ---- join / closest clusters ---------------------------------------------------------------
+
+// GHM::getClosestClusters (GHM.cpp:406-444): first (i,j) in lexicographic order attaining the
+// minimum distance < gap+1 among pairs passing the interval and r^2 tests.
+__device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double q, int& pi, int& pj, Red* red)
+{
+    const int ni = g.nbc[oi], nj = g.nbc[oj];
+    const bool same = (oi == oj);
+    const long long total = (long long)ni * nj;
+    double bd = gap + 1;
+    long long bk = -1;
+    for (long long idx = threadIdx.x; idx < total; idx += NT) {
+        const int i = (int)(idx / nj), j = (int)(idx - (long long)i * nj);
+        if (same && j <= i) continue;
+        const ClusterRec& cI = g.cl[g.bc[oi][i]];
+        const ClusterRec& cJ = g.cl[g.bc[oj][j]];
+        if (cI.mult >= 0 && cI.mult == cJ.mult) continue;
+        // exact cheap rejection: every candidate distance of distanceToCluster is a dpd between a
+        // point with x in A's x-range and one with x in B's, and dpd >= |dx|
+        const double xgap = cm::maxd(cI.x_end1 - cJ.x_end2, cJ.x_end1 - cI.x_end2);
+        if (xgap >= bd) continue;
+        const double d = cm::dist_to_cluster(cI, cJ, g.pool[cI.off], g.pool[cI.off + cI.n - 1], g.pool[cJ.off],
+                                             g.pool[cJ.off + cJ.n - 1]);
+        if (d < bd) {
+            if (cm::r2_merged(cI, cJ) >= q && cm::partial_overlap(cI, cJ, g.pool)) {
+                bd = d;
+                bk = idx;
+            }
+        }
+    }
+    block_min_pair(bd, bk, red);
+    if (bk < 0) return false;
+    pi = (int)(bk / nj);
+    pj = (int)(bk - (long long)pi * nj);
+    return true;
+}
+
+// GHM::joinClusters (GHM.cpp:392-404)
+__device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red)
+{
+    int pi, pj;
+    while (closest_clusters(g, gap, o, o, q, pi, pj, red)) {
+        if (threadIdx.x == 0) {
+            ClusterRec& A = g.cl[g.bc[o][pi]];
+            ClusterRec& B = g.cl[g.bc[o][pj]];
+            merge_clusters(g, A, B);
+            B.dead = 1;
+        }
+        __syncthreads();
+        if (g.status) return;
+        // erase position pj from the vector (order preserved)
+        const int n = g.nbc[o];
+        int v = 0;
+        const int chunk0 = pj;
+        for (int basei = chunk0; basei < n - 1; basei += NT) {
+            const int i = basei + threadIdx.x;
+            if (i < n - 1) v = g.bc[o][i + 1];
+            __syncthreads();
+            if (i < n - 1) g.bc[o][i] = v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) g.nbc[o] = n - 1;
+        __syncthreads();
+    }
+}
+
+// ---- probability filter ---------------------------------------------------------------------
+
+// BaseCluster::calculateProbability (BaseCluster.cpp:548-590)
+__device__ void calc_probability(Ghm& g, ClusterRec& c)
+{
+    const double density = (double)g.cnt[c.orient] / g.area;
+    double probability = 1.0;
+    int px = 0, py = 0;
+    bool have = false;
+    for (int i = 0; i < c.n; i++) {
+        if (!g.pflag[c.off + i]) continue;
+        const uint32_t k = g.pool[c.off + i];
+        const int x = KEY_X(k), y = KEY_Y(k);
+        if (have) {
+            const double distance = cm::dpd_d(px, py, x, y);
+            const int cc = (int)ceil(0.5 * distance * distance);
+            const double p_i = 1.0 - cm::pow_int(1.0 - density, cc);
+            probability *= p_i;
+        }
+        have = true;
+        px = x;
+        py = y;
+    }
+    c.p = probability;
+    // duplicates of the first AP are erased without touching the statistics
+    const uint32_t f = g.pool[c.off];
+    int w = 1;
+    for (int i = 1; i < c.n; i++) {
+        const uint32_t k = g.pool[c.off + i];
+        if (k == f) continue;
+        g.pool[c.off + w] = k;
+        g.pflag[c.off + w] = g.pflag[c.off + i];
+        w++;
+    }
+    if (w != c.n) {
+        c.n = w;
+        cm::recompute_sums(c, g.pool);
+    }
+}
+
+// libstdc++ std::sort (introsort + final insertion sort) restated on cluster ids ordered by p,
+// so that ties come out in exactly the reference's order (GHM.cpp:527).
+struct PLess {
+    const ClusterRec* cl;
+    __device__ bool operator()(int l, int r) const { return cl[l].p < cl[r].p; }
+};
+__device__ void adjust_heap(int* first, int hole, int len, int value, PLess comp)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (comp(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && comp(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+__device__ void heap_sort(int* first, int len, PLess comp)
+{
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            const int value = first[parent];
+            adjust_heap(first, parent, len, value, comp);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int last = len;
+    while (last > 1) {
+        --last;
+        const int value = first[last];
+        first[last] = first[0];
+        adjust_heap(first, 0, last, value, comp);
+    }
+}
+__device__ void unguarded_linear_insert(int* last, PLess comp)
+{
+    const int val = *last;
+    int* next = last - 1;
+    while (comp(val, *next)) {
+        *last = *next;
+        last = next;
+        --next;
+    }
+    *last = val;
+}
+__device__ void insertion_sort(int* first, int* last, PLess comp)
+{
+    if (first == last) return;
+    for (int* i = first + 1; i != last; ++i) {
+        if (comp(*i, *first)) {
+            const int val = *i;
+            for (int* p = i; p != first; --p) *p = *(p - 1);
+            *first = val;
+        } else
+            unguarded_linear_insert(i, comp);
+    }
+}
+__device__ void std_sort(int* first, int n, PLess comp)
+{
+    if (n <= 0) return;
+    // __introsort_loop, recursion on the right part unrolled with an explicit stack
+    int depth0 = 0;
+    for (int t = n; t > 1; t >>= 1) depth0++;
+    depth0 *= 2;
+    struct Frame {
+        int lo, hi, depth;
+    } stack[64];
+    int sp = 0;
+    stack[sp++] = {0, n, depth0};
+    while (sp > 0) {
+        Frame f = stack[--sp];
+        int lo = f.lo, hi = f.hi, depth = f.depth;
+        while (hi - lo > 16) {
+            if (depth == 0) {
+                heap_sort(first + lo, hi - lo, comp);
+                break;
+            }
+            --depth;
+            // __move_median_to_first(lo, lo+1, mid, hi-1)
+            int* a = first + lo + 1;
+            int* b = first + lo + (hi - lo) / 2;
+            int* c = first + hi - 1;
+            int* r = first + lo;
+            int t;
+            if (comp(*a, *b)) {
+                if (comp(*b, *c)) { t = *r; *r = *b; *b = t; }
+                else if (comp(*a, *c)) { t = *r; *r = *c; *c = t; }
+                else { t = *r; *r = *a; *a = t; }
+            } else if (comp(*a, *c)) { t = *r; *r = *a; *a = t; }
+            else if (comp(*b, *c)) { t = *r; *r = *c; *c = t; }
+            else { t = *r; *r = *b; *b = t; }
+            // __unguarded_partition(lo+1, hi, pivot = lo)
+            int* pf = first + lo + 1;
+            int* pl = first + hi;
+            const int* pivot = first + lo;
+            while (true) {
+                while (comp(*pf, *pivot)) ++pf;
+                --pl;
+                while (comp(*pivot, *pl)) --pl;
+                if (!(pf < pl)) break;
+                t = *pf; *pf = *pl; *pl = t;
+                ++pf;
+            }
+            const int cut = (int)(pf - first);
+            // recurse on [cut, hi) first (the reference does), then loop on [lo, cut)
+            // order of processing does not change the result: the two ranges are disjoint
+            if (sp < 64) stack[sp++] = {cut, hi, depth};
+            hi = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        insertion_sort(first, first + 16, comp);
+        for (int* i = first + 16; i != first + n; ++i) unguarded_linear_insert(i, comp);
+    } else
+        insertion_sort(first, first + n, comp);
+}
+
+// bitonic sort of g.tmp[0..m) (m power of two) by the whole CTA
+__device__ void block_bitonic(uint32_t* a, int m)
+{
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += NT) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint32_t x = a[i], y = a[l];
+                    const bool up = ((i & k) == 0);
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[l] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// GHM::filterBaseClusters / BF / FDR (GHM.cpp:446-540)
+__device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
+{
+    const int tid = threadIdx.x;
+    for (int o = 0; o < 2; o++)
+        for (int i = tid; i < g.nbc[o]; i += NT) calc_probability(g, g.cl[g.bc[o][i]]);
+    __syncthreads();
+    for (int o = 0; o < 2; o++) {
+        if (prm.mult_hyp == 2) {
+            if (tid == 0) {
+                PLess comp{g.cl};
+                std_sort(g.bc[o], g.nbc[o], comp);
+                int k;
+                for (k = 0; k < g.nbc[o]; k++)
+                    if (g.cl[g.bc[o][k]].p > (k + 1) * prm.prob_cutoff / g.cnt[o]) break;
+                for (int i = k; i < g.nbc[o]; i++) g.cl[g.bc[o][i]].dead = 1;
+                g.nbc[o] = k;  // filtered APs are NOT returned to the matrix
+            }
+            __syncthreads();
+            continue;
+        }
+        // none / Bonferroni: failing clusters give their APs back to matrix[o]
+        if (tid == 0) {
+            const double thr = (prm.mult_hyp == 1) ? (prm.prob_cutoff / g.cnt[o]) : prm.prob_cutoff;
+            int w = 0, removed = 0;
+            for (int i = 0; i < g.nbc[o]; i++) {
+                const int id = g.bc[o][i];
+                if (g.cl[id].p > thr) {
+                    g.cl[id].dead = 2;  // to be re-inserted
+                    removed++;
+                } else
+                    g.bc[o][w++] = id;
+            }
+            g.nbc[o] = w;
+            sh_s[0] = removed;
+            sh_s[1] = 0;
+        }
+        __syncthreads();
+        if (sh_s[0] == 0) continue;
+        // gather: alive dots of matrix[o] + APs of the removed clusters, then sort + unique
+        {
+            const uint32_t* key = g.key[o];
+            const uint8_t* alive = g.alive[o];
+            const int n = g.nk[o];
+            for (int i = tid; i < n; i += NT)
+                if (alive[i]) g.tmp[atomicAdd(&sh_s[1], 1)] = key[i];
+            for (int c = 0; c < g.ncl; c++) {
+                const ClusterRec& cr = g.cl[c];
+                if (cr.dead != 2 || cr.orient != o) continue;
+                for (int i = tid; i < cr.n; i += NT) g.tmp[atomicAdd(&sh_s[1], 1)] = g.pool[cr.off + i];
+            }
+            __syncthreads();
+            for (int c = tid; c < g.ncl; c += NT)
+                if (g.cl[c].dead == 2 && g.cl[c].orient == o) g.cl[c].dead = 1;
+            const int m = sh_s[1];
+            int mp = 1;
+            while (mp < m) mp <<= 1;
+            for (int i = m + tid; i < mp; i += NT) g.tmp[i] = 0xffffffffu;
+            __syncthreads();
+            block_bitonic(g.tmp, mp);
+            // unique-compact back into key[o] (single pass by thread 0 is O(m); use a parallel
+            // flag + scan-free approach: position = number of distinct predecessors)
+            if (tid == 0) sh_s[1] = 0;
+            __syncthreads();
+            // chunked ordered compaction
+            for (int base = 0; base < m; base += NT) {
+                const int i = base + tid;
+                const bool keep = (i < m) && (i == 0 || g.tmp[i] != g.tmp[i - 1]);
+                // block exclusive scan of keep via ballot
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                const int lane = tid & 31, w = tid >> 5;
+                __shared__ int wsum[NW];
+                if (lane == 0) wsum[w] = __popc(bal);
+                __syncthreads();
+                int off = sh_s[1];
+                for (int ww = 0; ww < w; ww++) off += wsum[ww];
+                off += __popc(bal & ((1u << lane) - 1u));
+                if (keep) {
+                    g.key[o][off] = g.tmp[i];
+                    g.alive[o][off] = 1;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int s = 0;
+                    for (int ww = 0; ww < NW; ww++) s += wsum[ww];
+                    sh_s[1] += s;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) g.nk[o] = sh_s[1];
+            __syncthreads();
+        }
+    }
+}
+
+// ---- metaclustering ---------------------------------------------------------------------------
+
+// BaseCluster::twistCluster (BaseCluster.cpp:700-719); one thread per cluster
+__device__ void twist_all(Ghm& g, int o)
+{
+    for (int i = threadIdx.x; i < g.nbc[o]; i += NT) {
+        ClusterRec& c = g.cl[g.bc[o][i]];
+        int mx = KEY_Y(g.pool[c.off]), mn = mx;
+        for (int k = 1; k < c.n; k++) {
+            const int y = KEY_Y(g.pool[c.off + k]);
+            mx = max(mx, y);
+            mn = min(mn, y);
+        }
+        for (int k = 0; k < c.n; k++) {
+            const uint32_t key = g.pool[c.off + k];
+            g.pool[c.off + k] = MAKE_KEY(KEY_X(key), mx + mn - KEY_Y(key));
+        }
+        cm::recompute_sums(c, g.pool);
+        cm::update_stats(c, g.pool);
+    }
+    __syncthreads();
+}
+
+// GHM::clusterClusters (GHM.cpp:542-625)
+__device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh_s)
+{
+    const int tid = threadIdx.x;
+    bool join_flag = true;
+    while (join_flag) {
+        join_flag = false;
+        for (int k = 0; k < 4; k++) {
+            const int ox = (k < 2) ? 1 : 0;
+            const int oy = (k % 2 == 0) ? 1 : 0;
+            const bool twisted = (ox != oy);
+            if (twisted) twist_all(g, oy);
+            int pi = -1, pj = -1;
+            const bool found = closest_clusters(g, prm.cluster_gap, ox, oy, prm.q_value, pi, pj, red);
+            if (twisted) twist_all(g, oy);
+            if (tid == 0) {
+                sh_s[0] = 0;
+                if (found) {
+                    int cI = g.bc[ox][pi], cJ = g.bc[oy][pj];
+                    if (!twisted || !g.cl[cI].was_twisted) {
+                        g.cl[cJ].was_twisted = twisted ? 1 : 0;
+                        sh_s[0] = 1;
+                        const int mi = g.cl[cI].mult, mj = g.cl[cJ].mult;
+                        if (mi >= 0 && mj >= 0) {
+                            // move every cluster of mj to the end of mi (Multiplicon.cpp:104-111)
+                            for (int c = g.mult[mj].head; c >= 0; c = g.cl[c].mnext) g.cl[c].mult = mi;
+                            g.cl[g.mult[mi].tail].mnext = g.mult[mj].head;
+                            g.mult[mi].tail = g.mult[mj].tail;
+                            g.mult[mi].count += g.mult[mj].count;
+                            g.mult[mj].head = g.mult[mj].tail = -1;
+                            g.mult[mj].count = 0;
+                        } else if (mi >= 0 || mj >= 0) {
+                            if (mi < 0) {
+                                const int t = cI;
+                                cI = cJ;
+                                cJ = t;
+                            }
+                            const int m = g.cl[cI].mult;
+                            g.cl[cJ].mult = m;
+                            g.cl[cJ].mnext = -1;
+                            g.cl[g.mult[m].tail].mnext = cJ;
+                            g.mult[m].tail = cJ;
+                            g.mult[m].count++;
+                        } else {
+                            const int m = g.nmult++;
+                            g.mult[m].head = cI;
+                            g.mult[m].tail = cJ;
+                            g.mult[m].count = 2;
+                            g.mult[m].alive = 1;
+                            g.cl[cI].mult = m;
+                            g.cl[cI].mnext = cJ;
+                            g.cl[cJ].mult = m;
+                            g.cl[cJ].mnext = -1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (sh_s[0]) join_flag = true;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        // singletons (GHM.cpp:600-611), then drop empty / too small multiplicons (613-624)
+        for (int o = 0; o < 2; o++)
+            for (int i = 0; i < g.nbc[o]; i++) {
+                ClusterRec& c = g.cl[g.bc[o][i]];
+                if (c.mult < 0) {
+                    const int m = g.nmult++;
+                    c.was_twisted = 0;
+                    c.mult = m;
+                    c.mnext = -1;
+                    g.mult[m].head = g.mult[m].tail = g.bc[o][i];
+                    g.mult[m].count = 1;
+                    g.mult[m].alive = 1;
+                }
+            }
+        int kept = 0;
+        for (int m = 0; m < g.nmult; m++) {
+            unsigned aps = 0;
+            for (int c = g.mult[m].head; c >= 0; c = g.cl[c].mnext) aps += (unsigned)g.cl[c].n;
+            if (g.mult[m].count == 0 || aps < (unsigned)prm.anchor_points) {
+                g.mult[m].alive = 0;
+                continue;
+            }
+            g.out_mults[kept++] = m;
+        }
+        sh_s[0] = kept;
+    }
+    __syncthreads();
+}
+
+// ---- kernel -----------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* __restrict__ order,
+                                                     int n_tasks, int* next_task,
+                                                     const uint32_t* __restrict__ dots, uint8_t* ws,
+                                                     DevParams prm, int pool_factor)
+{
+    __shared__ Ghm g;
+    __shared__ Red red;
+    __shared__ int sh_i[NW];
+    __shared__ int sh_s[4];
+    __shared__ int sh_task;
+    const int tid = threadIdx.x;
+    while (true) {
+        if (tid == 0) sh_task = atomicAdd(next_task, 1);
+        __syncthreads();
+        const int ti = sh_task;
+        if (ti >= n_tasks) break;
+        GhmTask& task = tasks[order[ti]];
+        const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1], D = D0 + D1;
+        if (tid == 0) {
+            WsLayout L = ws_layout(D, pool_factor);
+            uint8_t* base = ws + task.ws_off;
+            g.key[0] = (uint32_t*)(base + L.key0);
+            g.key[1] = (uint32_t*)(base + L.key1);
+            g.alive[0] = base + L.alive0;
+            g.alive[1] = base + L.alive1;
+            g.nxt = (int*)(base + L.nxt);
+            g.pool = (uint32_t*)(base + L.pool);
+            g.pflag = base + L.pflag;
+            g.pool_cap = L.pool_cap;
+            g.pool_used = 0;
+            g.cl = (ClusterRec*)(base + L.cl);
+            g.cl_cap = L.cl_cap;
+            g.ncl = 0;
+            g.bc[0] = (int*)(base + L.bc0);
+            g.bc[1] = (int*)(base + L.bc1);
+            g.nbc[0] = g.nbc[1] = 0;
+            g.act = (int*)(base + L.act);
+            g.act_next = (int*)(base + L.act_next);
+            g.changed = base + L.changed;
+            g.mult = (MultRec*)(base + L.mult);
+            g.nmult = 0;
+            g.out_mults = (int*)(base + L.out_mults);
+            g.tmp = (uint32_t*)(base + L.tmp);
+            g.tmp_cap = L.tmp_cap;
+            g.status = 0;
+            g.nk[0] = D0;
+            g.nk[1] = D1;
+            g.cnt[0] = task.cnt[0];
+            g.cnt[1] = task.cnt[1];
+            g.area = (double)task.area;
+            g.level = task.level;
+        }
+        __syncthreads();
+        // stage the dots (written once by K1) into the mutable per-GHM matrix
+        {
+            const uint32_t* src = dots + task.dot_off;
+            for (int i = tid; i < D0; i += NT) {
+                g.key[0][i] = src[i];
+                g.alive[0][i] = 1;
+            }
+            for (int i = tid; i < D1; i += NT) {
+                g.key[1][i] = src[D0 + i];
+                g.alive[1][i] = 1;
+            }
+        }
+        __syncthreads();
+        const double q = prm.q_value;
+        bool ok = true;
+#define CHECK_STATUS()        \
+    __syncthreads();          \
+    if (g.status) ok = false; \
+    if (!ok) break;
+        do {
+            for (int gi = 0; gi < prm.n_gaps && gi < 10 && prm.gaps[gi] > 0 && ok; gi++) {
+                const int gap = prm.gaps[gi];
+                for (int o = 0; o < 2; o++) {
+                    seed_pass(g, gap, o, q, sh_i, sh_s);
+                    __syncthreads();
+                    if (g.status) { ok = false; break; }
+                    enrich_pass(g, gap, o, o, q, sh_i, sh_s);
+                    __syncthreads();
+                    if (g.status) { ok = false; break; }
+                    join_pass(g, gap, o, q, &red);
+                    __syncthreads();
+                    if (g.status) { ok = false; break; }
+                }
+            }
+            if (!ok) break;
+            for (int rep = 0; rep < 2 && ok; rep++) {
+                for (int e = 0; e < 4; e++) {
+                    // GHM.cpp:186-189: (cluster, matrix) orientations (0,0) (1,1) (1,0) (0,1)
+                    const int oc = (e == 1 || e == 2) ? 1 : 0;
+                    const int om = (e == 1 || e == 3) ? 1 : 0;
+                    enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
+                    __syncthreads();
+                    if (g.status) { ok = false; break; }
+                }
+                if (!ok) break;
+                if (rep == 0) {
+                    filter_pass(g, prm, sh_s);
+                    CHECK_STATUS();
+                }
+            }
+            if (!ok) break;
+            cluster_clusters(g, prm, &red, sh_s);
+        } while (false);
+#undef CHECK_STATUS
+        __syncthreads();
+        if (tid == 0) {
+            task.status = ok ? 0 : 1;
+            task.n_mult = ok ? sh_s[0] : 0;
+            task.n_clusters = g.ncl;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+                    const DevParams& prm, int pool_factor, int grid, cudaStream_t st)
+{
+    if (n_tasks == 0) return;
+    cluster_kernel<<<grid, NT, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor);
+}

@@ -1,0 +1,110 @@
+// Shared host/device definitions of the B200 collinearity engine.
+//
+// Vocabulary follows the reference: GHM (gene homology matrix), dots (homologous
+// gene pairs, GHM.cpp:34-85), base clusters, anchor points (AP), multiplicons.
+// Orientation index: 0 = OPP_ORIENT, 1 = SAME_ORIENT (GHM.h:27).
+#pragma once
+#include <stdint.h>
+
+#define IADH_MAX_COORD 46340  // BaseCluster.cpp:156-158: x*y is a 32-bit product
+
+// A dot / anchor point is packed as (x << 16) | y; both coordinates < 65536.
+#define KEY_X(k) ((int)((k) >> 16))
+#define KEY_Y(k) ((int)((k)&0xffffu))
+#define MAKE_KEY(x, y) ((((uint32_t)(x)) << 16) | ((uint32_t)(y)))
+
+struct DevParams {
+    int n_gaps;
+    int gaps[10];
+    int gap_size;
+    int cluster_gap;
+    int anchor_points;
+    int mult_hyp;  // 0 none, 1 Bonferroni, 2 FDR
+    double q_value;
+    double prob_cutoff;
+};
+
+// One GHM to cluster: either list x list (level 2) or profile x list.
+struct GhmTask {
+    int32_t x_list;       // L2: x list index; HL: -1
+    int32_t y_list;
+    int32_t x_object_id;  // Multiplicon x_objectID (GHM.cpp:588 / GHMProfile.cpp:13)
+    int32_t y_object_id;
+    int32_t level;        // 2 for L2, S+1 for HL
+    uint32_t cnt[2];      // count_points[o] after the build (static afterwards)
+    uint32_t pad0;
+    uint64_t area;        // GHM.cpp:221-236 (32-bit arithmetic, widened)
+    int64_t dot_off;      // offset (in keys) of this GHM's dots: [o=0 block][o=1 block]
+    int64_t ws_off;       // byte offset of this GHM's clustering workspace
+    int64_t ws_bytes;
+    int32_t seq;          // position in the caller's GHM sequence
+    int32_t status;       // out: 0 ok, 1 AP pool exhausted (host retries with a larger pool)
+    int64_t out_bytes;    // out: packed size of this GHM's multiplicons
+    int32_t n_mult;       // out
+    int32_t n_clusters;   // out
+    int32_t n_aps;        // out
+    int32_t pad1;
+};
+
+// Base cluster record (BaseCluster.h:316-331).  Anchor points live in the GHM's AP
+// pool at [off, off+n): keys in multiset order (x ascending, insertion order on ties,
+// AnchorPoint.h:144-156) with a parallel backbone flag byte.
+struct ClusterRec {
+    double a, b, avg_x, var_x, mrss, x_end1, x_end2, y_end1, y_end2;
+    double p;                          // random_probability
+    long long sx, sy, sxy, sxx, syy;   // exact integer sums over the APs (r_squared, regression)
+    int n;                             // anchor points
+    int off, cap;                      // pool block
+    int mult;                          // multiplicon index, -1 = none
+    int mnext;                         // next cluster in the multiplicon's list
+    unsigned char orient, was_twisted, dead, has_false;
+    // filled by the pack stage (K3)
+    int min_y, max_y;                  // Cluster::setBounds (Cluster.h:27-33)
+    int n_false;                       // false anchor points added by GHMProfile::setMultiplicons
+    int out_off;                       // byte offset of this cluster inside the GHM's packed block
+};
+
+struct MultRec {
+    int head, tail, count;  // cluster list, join order
+    int alive;
+    int out_off;            // byte offset of the 33-byte header inside the GHM's packed block
+    int pad[3];
+};
+
+// Profile column groups for the HL build (GHMProfile.cpp:17-59): per aligned column the
+// distinct (family, strand) combinations of its non-gap segment elements; gid = the single
+// gene id of the group or -1 when the group holds >= 2 different genes (then every y passes
+// the ID != test of Gene.cpp:20).
+struct ProfileDev {
+    int S, L;
+    const int32_t* col_ptr;    // L+1
+    const int32_t* grp_fam;
+    const int32_t* grp_gid;
+    const uint8_t* grp_strand;
+    // raw S*L arrays, for anchor-point gene ids (GHMProfile.cpp:86-112)
+    const int32_t* fam;
+    const int32_t* gid;
+    const int32_t* num_id;
+    const uint8_t* flags;
+};
+
+struct DatasetDev {
+    int n_lists;
+    const int64_t* list_off;
+    const int32_t* fam;
+    const int32_t* gid;
+    const int32_t* num_id;
+    uint8_t* flags;             // bit0 strand, bit2 masked
+    const int32_t* fam_ptr;     // CSR over families: members = global element indices, ascending
+    const int32_t* fam_members;
+};
+
+// Build tiles: <=256 consecutive columns of one GHM.
+struct BuildTile {
+    int32_t ghm;   // index into the task array
+    int32_t x0;    // first column
+    int32_t nx;    // columns in this tile
+    int32_t pad;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

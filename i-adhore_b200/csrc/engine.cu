@@ -1,0 +1,831 @@
+// Host engine + C-ABI (include/iadhore_b200.h) of the B200 collinearity engine.
+//
+// Replaces the scheduling half of DataSet::parallelLevel2ADHoReDyn (levelTwo.cpp:177-292) and
+// DataSet::parallelProfileSearch (higherLevel.cpp:252-326): instead of a pthread pool pulling
+// weight-balanced packets, every GHM of a call is batched into three device stages
+//   K1 build (count -> per-GHM tile scan -> fill)      build_kernels.cu
+//   K2 cluster (persistent CTAs, heaviest GHM first)   cluster_kernel.cu
+//   K3 pack (measure -> host size scan -> write)       pack_kernel.cu
+// with persistent, growable device buffers and pinned staging.  No CPU fallback exists: every
+// entry point fails if CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/iadhore_b200.h"
+#include "cluster_math.cuh"
+#include "common.h"
+#include "workspace.h"
+
+// kernels (other translation units)
+void launch_build_count(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmTask* tasks, int n_ghm,
+                        const int64_t* tile_prefix, int64_t n_tiles, uint32_t* tile_cnt, int sm_count, cudaStream_t st);
+void launch_tile_scan(const int64_t* tile_prefix, int n_ghm, const uint32_t* tile_cnt, uint32_t* tile_off,
+                      cudaStream_t st);
+void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmTask* tasks, int n_ghm,
+                       const int64_t* tile_prefix, int64_t n_tiles, const uint32_t* tile_off, uint32_t* keys,
+                       int sm_count, cudaStream_t st);
+void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
+void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+                    const DevParams& prm, int pool_factor, int grid, cudaStream_t st);
+void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
+                         const ProfileDev& pf, int pool_factor, cudaStream_t st);
+void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
+                       const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st);
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(IADH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// growable device buffer
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() { return (T*)p; }
+};
+// growable pinned host buffer
+struct HBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() { return (T*)p; }
+};
+
+struct iadh_result {
+    std::vector<uint8_t> bytes;
+    std::vector<int32_t> ghm_index;
+    iadh_stats stats;
+};
+
+struct iadh_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // dataset (host mirror + device)
+    int n_lists = 0;
+    std::vector<int64_t> list_off;
+    std::vector<uint8_t> flags;       // host mirror incl. mask bits
+    std::vector<int32_t> masked_cnt;  // per list
+    std::vector<int32_t> index_to_list;
+    int n_fam = 0;
+    DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members;
+    DatasetDev ds;
+    DevParams prm;
+    // per-call buffers
+    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_sel, d_out_off, d_out, d_counter;
+    DBuf d_pf_col, d_pf_gfam, d_pf_ggid, d_pf_gstrand, d_pf_fam, d_pf_gid, d_pf_num, d_pf_flags;
+    HBuf h_tasks, h_misc, h_out, h_pf;
+    // build_dots scratch
+    std::vector<int64_t> bd_cnt;
+    std::vector<int32_t> bd_dots;
+    int pool_factor = 8;
+    int ctas_per_sm = 4;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host-side scheduling (mirrors of the reference's 1-thread orders)
+
+// DataSet::sortGeneLists (DataSet.cpp:1088-1105): size descending; equal sizes come out in
+// descending list index because the multimap is walked in reverse
+static void sort_lists(iadh_ctx* c)
+{
+    std::vector<int32_t>& v = c->index_to_list;
+    v.resize(c->n_lists);
+    std::iota(v.begin(), v.end(), 0);
+    const std::vector<int64_t>& off = c->list_off;
+    std::stable_sort(v.begin(), v.end(), [&off](int a, int b) {
+        const int64_t sa = off[a + 1] - off[a], sb = off[b + 1] - off[b];
+        if (sa != sb) return sa > sb;
+        return a > b;
+    });
+}
+
+// DataSet::getSomeWorkL2 (levelTwo.cpp:113-175): anti-diagonal walk over the size-sorted lower
+// triangle, each pair assigned to the least-loaded rank (getProcForPackage, :98-111)
+static void pair_sequence(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& xs, std::vector<int32_t>& ys)
+{
+    const unsigned n = (unsigned)c->n_lists;
+    std::vector<uint64_t> load(n_ranks, 0);
+    unsigned cX = 0, cY = 0;
+    while (cX < n) {
+        const unsigned lX = c->index_to_list[cX], lY = c->index_to_list[cY];
+        const unsigned sx = (unsigned)(c->list_off[lX + 1] - c->list_off[lX]);
+        const unsigned sy = (unsigned)(c->list_off[lY + 1] - c->list_off[lY]);
+        const uint64_t weight = (unsigned)(sx * sy);  // 32-bit product, as the reference
+        unsigned sp = 0;
+        for (unsigned p = 1; p < load.size(); p++)
+            if (load[p] < load[sp]) sp = p;
+        load[sp] += weight;
+        if ((int)sp == rank) {
+            xs.push_back((int32_t)lX);
+            ys.push_back((int32_t)lY);
+        }
+        if ((cX - cY) < 2) {
+            if (cX == cY && cX == n - 1) break;
+            const unsigned d = cX + cY + 1;
+            cX = (d < n) ? d : n - 1;
+            cY = (d < n) ? 0 : d - n + 1;
+        } else {
+            cX--;
+            cY++;
+        }
+    }
+}
+
+// ParToolBox::statPartWorklSort (parallel.cpp:96-156): size-sorted lists dealt to the lightest package
+static void list_partition(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& out)
+{
+    std::vector<uint64_t> load(n_ranks, 0);
+    for (int32_t l : c->index_to_list) {
+        unsigned sp = 0;
+        for (unsigned p = 1; p < load.size(); p++)
+            if (load[p] < load[sp]) sp = p;
+        load[sp] += (uint64_t)(c->list_off[l + 1] - c->list_off[l]);
+        if ((int)sp == rank) out.push_back(l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static int upload(DBuf& d, const void* src, size_t bytes, cudaStream_t st)
+{
+    CU(d.ensure(bytes ? bytes : 16));
+    if (bytes) CU(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return IADH_OK;
+}
+
+struct ProfileHost {
+    ProfileDev dev;
+    bool valid = false;
+};
+
+// groups per profile column (see ProfileDev in common.h) + raw arrays -> device
+static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& out, int64_t& h2d)
+{
+    const int S = p->n_segments, L = p->length;
+    if (S < 1 || L < 0) return fail(IADH_ERR_ARG, "bad profile shape S=%d L=%d", S, L);
+    if (L > IADH_MAX_COORD) return fail(IADH_ERR_CAPACITY, "profile longer than %d columns", IADH_MAX_COORD);
+    std::vector<int32_t> col_ptr(L + 1, 0), gfam, ggid;
+    std::vector<uint8_t> gstrand;
+    for (int x = 0; x < L; x++) {
+        const size_t g0 = gfam.size();
+        for (int s = 0; s < S; s++) {
+            const size_t k = (size_t)s * L + x;
+            if (p->flags[k] & IADH_F_GAP) continue;
+            const int f = p->fam[k], gid = p->gid[k];
+            const uint8_t st = p->flags[k] & IADH_F_STRAND;
+            if (f < 0 || f >= c->n_fam) continue;  // family absent from the dataset: no partner possible
+            size_t g = g0;
+            for (; g < gfam.size(); g++)
+                if (gfam[g] == f && gstrand[g] == st) break;
+            if (g == gfam.size()) {
+                gfam.push_back(f);
+                ggid.push_back(gid);
+                gstrand.push_back(st);
+            } else if (ggid[g] != gid)
+                ggid[g] = -1;
+        }
+        col_ptr[x + 1] = (int32_t)gfam.size();
+    }
+    const size_t n = (size_t)S * L;
+    int rc;
+    if ((rc = upload(c->d_pf_col, col_ptr.data(), 4 * col_ptr.size(), c->st))) return rc;
+    if ((rc = upload(c->d_pf_gfam, gfam.data(), 4 * gfam.size(), c->st))) return rc;
+    if ((rc = upload(c->d_pf_ggid, ggid.data(), 4 * ggid.size(), c->st))) return rc;
+    if ((rc = upload(c->d_pf_gstrand, gstrand.data(), gstrand.size(), c->st))) return rc;
+    if ((rc = upload(c->d_pf_fam, p->fam, 4 * n, c->st))) return rc;
+    if ((rc = upload(c->d_pf_gid, p->gid, 4 * n, c->st))) return rc;
+    if ((rc = upload(c->d_pf_num, p->num_id, 4 * n, c->st))) return rc;
+    if ((rc = upload(c->d_pf_flags, p->flags, n, c->st))) return rc;
+    CU(cudaStreamSynchronize(c->st));  // the host vectors above die at return
+    h2d += 4 * (col_ptr.size() + 2 * gfam.size()) + gstrand.size() + 13 * n;
+    out.dev.S = S;
+    out.dev.L = L;
+    out.dev.col_ptr = c->d_pf_col.as<int32_t>();
+    out.dev.grp_fam = c->d_pf_gfam.as<int32_t>();
+    out.dev.grp_gid = c->d_pf_ggid.as<int32_t>();
+    out.dev.grp_strand = c->d_pf_gstrand.as<uint8_t>();
+    out.dev.fam = c->d_pf_fam.as<int32_t>();
+    out.dev.gid = c->d_pf_gid.as<int32_t>();
+    out.dev.num_id = c->d_pf_num.as<int32_t>();
+    out.dev.flags = c->d_pf_flags.as<uint8_t>();
+    out.valid = true;
+    return IADH_OK;
+}
+
+struct BatchOut {
+    std::vector<GhmTask> tasks;  // final state (cnt, n_mult, out_bytes ...)
+    std::vector<uint8_t> packed; // concatenated per-GHM blocks in seq order (no leading count)
+    std::vector<int32_t> ghm_index;
+    iadh_stats st;
+};
+
+// stages 1..4: build the dots of every task; on return tasks hold cnt/dot_off and d_dots the keys
+static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<GhmTask>& tasks, int64_t& total_dots,
+                       iadh_stats& st)
+{
+    const int n = (int)tasks.size();
+    std::vector<int64_t> tile_prefix(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        const int64_t nx = hl ? pf.L : (c->list_off[tasks[i].x_list + 1] - c->list_off[tasks[i].x_list]);
+        tile_prefix[i + 1] = tile_prefix[i] + (nx + 31) / 32;
+    }
+    const int64_t n_tiles = tile_prefix[n];
+    int rc;
+    if ((rc = upload(c->d_tasks, tasks.data(), sizeof(GhmTask) * (size_t)n, c->st))) return rc;
+    if ((rc = upload(c->d_tile_prefix, tile_prefix.data(), 8 * (size_t)(n + 1), c->st))) return rc;
+    st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 8 * (n + 1);
+    CU(c->d_tile_cnt.ensure(8 * (size_t)n_tiles + 16));
+    CU(c->d_tile_off.ensure(8 * (size_t)n_tiles + 16));
+    CU(cudaEventRecord(c->ev[1], c->st));
+    launch_build_count(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
+                       c->d_tile_cnt.as<uint32_t>(), c->sm_count, c->st);
+    launch_tile_scan(c->d_tile_prefix.as<int64_t>(), n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
+    CU(cudaEventRecord(c->ev[2], c->st));
+    st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
+    CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; tasks are read next)
+    st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
+    total_dots = 0;
+    for (int i = 0; i < n; i++) {
+        tasks[i].dot_off = total_dots;
+        total_dots += (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
+    }
+    if (total_dots > 0x7fffffff00ll) return fail(IADH_ERR_CAPACITY, "too many dots in one call");
+    CU(c->d_dots.ensure(4 * (size_t)total_dots + 16));
+    CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+    st.h2d_bytes += (int64_t)sizeof(GhmTask) * n;
+    CU(cudaEventRecord(c->ev[3], c->st));
+    launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
+                      c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
+    CU(cudaEventRecord(c->ev[4], c->st));
+    st.kernel_launches += n_tiles ? 1 : 0;
+    st.n_dots = total_dots;
+    return IADH_OK;
+}
+
+// the whole pipeline for a batch of GHMs (tasks[i].seq == i on entry)
+static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<GhmTask>& tasks, BatchOut& out)
+{
+    iadh_stats& st = out.st;
+    const int n = (int)tasks.size();
+    CU(cudaEventRecord(c->ev[0], c->st));
+    int64_t total_dots = 0;
+    int rc;
+    if (n == 0) {
+        out.tasks.clear();
+        return IADH_OK;
+    }
+    if ((rc = build_stage(c, hl, pf, tasks, total_dots, st))) return rc;
+
+    int pool_factor = c->pool_factor;
+    std::vector<int> order;
+    for (int attempt = 0;; attempt++) {
+        // active GHMs: at least anchor_points dots (GHM.cpp:159), heaviest first
+        order.clear();
+        size_t ws_total = 0;
+        for (int i = 0; i < n; i++) {
+            GhmTask& t = tasks[i];
+            const int64_t D = (int64_t)t.cnt[0] + t.cnt[1];
+            t.status = 0;
+            t.n_mult = t.n_clusters = t.n_aps = 0;
+            t.out_bytes = 0;
+            t.ws_off = 0;
+            t.ws_bytes = 0;
+            if (D < (int64_t)c->prm.anchor_points || D == 0) continue;
+            if (D > 0x0fffffff) return fail(IADH_ERR_CAPACITY, "GHM with %lld dots exceeds the per-GHM limit", (long long)D);
+            const WsLayout L = ws_layout((int)D, pool_factor);
+            t.ws_off = (int64_t)ws_total;
+            t.ws_bytes = (int64_t)L.total;
+            ws_total += L.total;
+            order.push_back(i);
+        }
+        std::stable_sort(order.begin(), order.end(), [&tasks](int a, int b) {
+            return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1] > (uint64_t)tasks[b].cnt[0] + tasks[b].cnt[1];
+        });
+        const int n_act = (int)order.size();
+        CU(c->d_ws.ensure(ws_total + 256));
+        if ((rc = upload(c->d_order, order.data(), 4 * (size_t)n_act, c->st))) return rc;
+        CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+        st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act;
+        CU(c->d_counter.ensure(16));
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 16, c->st));
+        CU(cudaEventRecord(c->ev[5], c->st));
+        const int grid = std::max(1, std::min(n_act, c->sm_count * c->ctas_per_sm));
+        launch_cluster(c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_counter.as<int>(),
+                       c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, grid, c->st);
+        CU(cudaEventRecord(c->ev[6], c->st));
+        // measure runs over every active GHM (those without multiplicons return at once)
+        launch_pack_measure(hl, c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_ws.as<uint8_t>(), c->ds, pf,
+                            pool_factor, c->st);
+        st.kernel_launches += n_act ? 2 : 0;
+        CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
+        bool retry = false;
+        for (int i : order)
+            if (tasks[i].status != 0) retry = true;
+        if (!retry) break;
+        if (attempt >= 3) return fail(IADH_ERR_CAPACITY, "anchor-point pool exhausted even at factor %d", pool_factor);
+        pool_factor *= 4;  // rare: rerun the clustering stage with a larger AP pool
+    }
+
+    // pack: sizes -> offsets -> write
+    std::vector<int> sel;
+    std::vector<int64_t> out_off;
+    int64_t total_bytes = 0;
+    for (int i = 0; i < n; i++)
+        if (tasks[i].n_mult > 0) {
+            sel.push_back(i);
+            out_off.push_back(total_bytes);
+            total_bytes += tasks[i].out_bytes;
+        }
+    out.packed.resize((size_t)total_bytes);
+    if (!sel.empty()) {
+        if ((rc = upload(c->d_sel, sel.data(), 4 * sel.size(), c->st))) return rc;
+        if ((rc = upload(c->d_out_off, out_off.data(), 8 * out_off.size(), c->st))) return rc;
+        CU(c->d_out.ensure((size_t)total_bytes + 16));
+        launch_pack_write(hl, c->d_tasks.as<GhmTask>(), c->d_sel.as<int>(), c->d_out_off.as<int64_t>(), (int)sel.size(),
+                          c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
+        st.kernel_launches += 1;
+        CU(c->h_out.ensure((size_t)total_bytes));
+        CU(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st));
+        st.h2d_bytes += 12 * (int64_t)sel.size();
+        st.d2h_bytes += total_bytes;
+    }
+    CU(cudaStreamSynchronize(c->st));
+    if (total_bytes) memcpy(out.packed.data(), c->h_out.p, (size_t)total_bytes);
+    for (int i : sel)
+        for (int k = 0; k < tasks[i].n_mult; k++) out.ghm_index.push_back(tasks[i].seq);
+    st.n_ghm = n;
+    for (int i = 0; i < n; i++) {
+        st.n_multiplicons += tasks[i].n_mult;
+        if (tasks[i].n_mult > 0) {
+            st.n_baseclusters += tasks[i].n_clusters;
+            st.n_anchorpoints += tasks[i].n_aps;
+        }
+    }
+    out.tasks = tasks;
+    return IADH_OK;
+}
+
+static iadh_result* make_result(BatchOut& b)
+{
+    iadh_result* r = new iadh_result();
+    const int32_t total = (int32_t)b.st.n_multiplicons;
+    r->bytes.resize(4 + b.packed.size());
+    memcpy(r->bytes.data(), &total, 4);
+    if (!b.packed.empty()) memcpy(r->bytes.data() + 4, b.packed.data(), b.packed.size());
+    r->ghm_index.swap(b.ghm_index);
+    r->stats = b.st;
+    return r;
+}
+
+static void init_task(GhmTask& t)
+{
+    memset(&t, 0, sizeof t);
+}
+
+// timing wrapper: total / build / cluster device times from CUDA events on the engine's stream
+struct Timer {
+    cudaEvent_t a, b;
+};
+
+static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, iadh_result** out)
+{
+    if (n < 0 || n > 0x3fffffff) return fail(IADH_ERR_ARG, "bad pair count");
+    std::vector<GhmTask> tasks((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        GhmTask& t = tasks[i];
+        init_task(t);
+        if (xs[i] < 0 || xs[i] >= c->n_lists || ys[i] < 0 || ys[i] >= c->n_lists)
+            return fail(IADH_ERR_ARG, "pair %lld names list %d/%d of %d", (long long)i, xs[i], ys[i], c->n_lists);
+        t.x_list = xs[i];
+        t.y_list = ys[i];
+        t.x_object_id = xs[i];
+        t.y_object_id = ys[i];
+        t.level = 2;
+        // GHM::prepareForStatisticalValidation (GHM.cpp:221-236): 32-bit unsigned arithmetic
+        const unsigned nx = (unsigned)(c->list_off[xs[i] + 1] - c->list_off[xs[i]]);
+        const unsigned ny = (unsigned)(c->list_off[ys[i] + 1] - c->list_off[ys[i]]);
+        t.area = (xs[i] == ys[i]) ? (unsigned)(nx * (nx - 1) / 2) : (unsigned)(nx * ny);
+        t.seq = (int32_t)i;
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->st));
+    BatchOut b;
+    memset(&b.st, 0, sizeof b.st);
+    ProfileDev nopf;
+    memset(&nopf, 0, sizeof nopf);
+    int rc = run_batch(c, false, nopf, tasks, b);
+    cudaEventRecord(e1, c->st);
+    cudaEventSynchronize(e1);
+    if (rc == IADH_OK) {
+        float ms = 0, m1 = 0, m2 = 0, m3 = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        b.st.total_ms = ms;
+        if (n > 0) {
+            cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
+            b.st.build_ms = m1 + m2;
+            cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
+            b.st.cluster_ms = m3;
+        }
+        *out = make_result(b);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+__global__ void omxn_kernel(const double* x, const int* n, long long count, double* out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = cm::omxn(x[i], n[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* iadh_last_error(void) { return g_err.c_str(); }
+const char* iadh_version(void) { return "iadhore_b200 0.1 (sm_100a)"; }
+
+int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
+{
+    if (!d || !out || d->n_lists < 0 || (d->n_lists > 0 && (!d->list_off || !d->fam || !d->gid || !d->num_id || !d->flags)))
+        return fail(IADH_ERR_ARG, "iadh_create: bad dataset descriptor");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(IADH_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    iadh_ctx* c = new iadh_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+    c->n_lists = d->n_lists;
+    c->list_off.assign(d->list_off, d->list_off + d->n_lists + 1);
+    const int64_t total = d->n_lists ? c->list_off[d->n_lists] : 0;
+    if (total >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 elements"); }
+    int max_fam = -1;
+    for (int l = 0; l < d->n_lists; l++) {
+        const int64_t sz = c->list_off[l + 1] - c->list_off[l];
+        if (sz < 0) { delete c; return fail(IADH_ERR_ARG, "list %d has negative size", l); }
+        if (sz > IADH_MAX_COORD) {
+            delete c;
+            return fail(IADH_ERR_CAPACITY,
+                        "list %d has %lld remapped elements (> %d): the reference's 32-bit x*y sums overflow there "
+                        "(BaseCluster.cpp:156-158), parity is undefined",
+                        l, (long long)sz, IADH_MAX_COORD);
+        }
+    }
+    for (int64_t i = 0; i < total; i++) {
+        if (d->fam[i] < 0) { delete c; return fail(IADH_ERR_ARG, "element %lld has a negative family id", (long long)i); }
+        max_fam = std::max(max_fam, d->fam[i]);
+    }
+    c->n_fam = max_fam + 1;
+    c->flags.resize((size_t)total);
+    c->masked_cnt.assign(d->n_lists, 0);
+    for (int l = 0; l < d->n_lists; l++)
+        for (int64_t i = c->list_off[l]; i < c->list_off[l + 1]; i++) {
+            uint8_t f = (d->flags[i] & IADH_F_STRAND) ? 1 : 0;
+            if (d->flags[i] & IADH_F_MASKED) {
+                f |= 4;
+                c->masked_cnt[l]++;
+            }
+            c->flags[i] = f;
+        }
+    // family CSR: members ascending by global element index
+    std::vector<int32_t> fam_ptr(c->n_fam + 1, 0), members((size_t)total);
+    for (int64_t i = 0; i < total; i++) fam_ptr[d->fam[i] + 1]++;
+    for (int f = 0; f < c->n_fam; f++) fam_ptr[f + 1] += fam_ptr[f];
+    {
+        std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
+        for (int64_t i = 0; i < total; i++) members[cur[d->fam[i]]++] = (int32_t)i;
+    }
+    int rc = IADH_OK;
+    if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
+    if (!rc) rc = upload(c->d_fam, d->fam, 4 * (size_t)total, c->st);
+    if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
+    if (!rc) rc = upload(c->d_num_id, d->num_id, 4 * (size_t)total, c->st);
+    if (!rc) rc = upload(c->d_flags, c->flags.data(), (size_t)total, c->st);
+    if (!rc) rc = upload(c->d_fam_ptr, fam_ptr.data(), 4 * fam_ptr.size(), c->st);
+    if (!rc) rc = upload(c->d_fam_members, members.data(), 4 * members.size(), c->st);
+    if (!rc && cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "dataset upload failed");
+    if (rc) { iadh_destroy(c); return rc; }
+    c->ds.n_lists = c->n_lists;
+    c->ds.list_off = c->d_list_off.as<int64_t>();
+    c->ds.fam = c->d_fam.as<int32_t>();
+    c->ds.gid = c->d_gid.as<int32_t>();
+    c->ds.num_id = c->d_num_id.as<int32_t>();
+    c->ds.flags = c->d_flags.as<uint8_t>();
+    c->ds.fam_ptr = c->d_fam_ptr.as<int32_t>();
+    c->ds.fam_members = c->d_fam_members.as<int32_t>();
+    sort_lists(c);
+    // defaults = shipped datasetI/II settings, Bonferroni (Settings.cpp:4-9)
+    memset(&c->prm, 0, sizeof c->prm);
+    const int g30[10] = {3, 4, 5, 6, 8, 11, 14, 18, 23, 30};
+    c->prm.n_gaps = 10;
+    memcpy(c->prm.gaps, g30, sizeof g30);
+    c->prm.gap_size = 30;
+    c->prm.cluster_gap = 35;
+    c->prm.anchor_points = 3;
+    c->prm.mult_hyp = IADH_MH_BONFERRONI;
+    c->prm.q_value = 0.75;
+    c->prm.prob_cutoff = 0.01;
+    *out = c;
+    return IADH_OK;
+}
+
+void iadh_destroy(iadh_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order,
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
+                    &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
+    for (DBuf* b : bufs) b->release();
+    c->h_tasks.release();
+    c->h_misc.release();
+    c->h_out.release();
+    c->h_pf.release();
+    for (int i = 0; i < 8; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int iadh_set_params(iadh_ctx* c, const iadh_params* p)
+{
+    if (!c || !p) return fail(IADH_ERR_ARG, "iadh_set_params: null argument");
+    if (p->n_gaps < 0 || p->n_gaps > 10) return fail(IADH_ERR_ARG, "n_gaps must be 0..10");
+    if (p->mult_hyp < 0 || p->mult_hyp > 2) return fail(IADH_ERR_ARG, "mult_hyp must be 0, 1 or 2");
+    if (p->gap_size < 1 || p->cluster_gap < 1 || p->anchor_points < 3)
+        return fail(IADH_ERR_ARG, "gap_size/cluster_gap must be >= 1 and anchor_points >= 3 (Settings.cpp:298-368)");
+    c->prm.n_gaps = p->n_gaps;
+    for (int i = 0; i < 10; i++) c->prm.gaps[i] = i < p->n_gaps ? p->gaps[i] : 0;
+    c->prm.gap_size = p->gap_size;
+    c->prm.cluster_gap = p->cluster_gap;
+    c->prm.anchor_points = p->anchor_points;
+    c->prm.mult_hyp = p->mult_hyp;
+    c->prm.q_value = p->q_value;
+    c->prm.prob_cutoff = p->prob_cutoff;
+    return IADH_OK;
+}
+
+int iadh_level2_pairs(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, iadh_result** out)
+{
+    if (!c || !out || (n > 0 && (!xs || !ys))) return fail(IADH_ERR_ARG, "iadh_level2_pairs: null argument");
+    CU(cudaSetDevice(c->device));
+    return run_l2(c, xs, ys, n, out);
+}
+
+int iadh_level2_all_pairs(iadh_ctx* c, int rank, int n_ranks, iadh_result** out)
+{
+    if (!c || !out) return fail(IADH_ERR_ARG, "iadh_level2_all_pairs: null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
+    CU(cudaSetDevice(c->device));
+    std::vector<int32_t> xs, ys;
+    pair_sequence(c, rank, n_ranks, xs, ys);
+    return run_l2(c, xs.data(), ys.data(), (int64_t)xs.size(), out);
+}
+
+int iadh_mask_range(iadh_ctx* c, int32_t list, int32_t begin, int32_t end)
+{
+    if (!c) return fail(IADH_ERR_ARG, "null ctx");
+    if (list < 0 || list >= c->n_lists) return fail(IADH_ERR_ARG, "mask_range: list %d out of range", list);
+    const int64_t sz = c->list_off[list + 1] - c->list_off[list];
+    if (begin < 0 || end >= sz) return fail(IADH_ERR_ARG, "mask_range: [%d,%d] outside list of %lld", begin, end, (long long)sz);
+    if (end < begin) return IADH_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t o = c->list_off[list];
+    for (int64_t i = o + begin; i <= o + end; i++)
+        if (!(c->flags[i] & 4)) {
+            c->flags[i] |= 4;
+            c->masked_cnt[list]++;
+        }
+    launch_mask(c->d_flags.as<uint8_t>(), o + begin, o + end, 1, c->st);
+    CU(cudaGetLastError());
+    return IADH_OK;
+}
+
+int iadh_clear_masks(iadh_ctx* c)
+{
+    if (!c) return fail(IADH_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    for (uint8_t& f : c->flags) f &= ~4;
+    std::fill(c->masked_cnt.begin(), c->masked_cnt.end(), 0);
+    if (!c->flags.empty()) {
+        launch_mask(c->d_flags.as<uint8_t>(), 0, (int64_t)c->flags.size() - 1, 0, c->st);
+        CU(cudaGetLastError());
+    }
+    return IADH_OK;
+}
+
+int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out)
+{
+    if (!c || !p || !out) return fail(IADH_ERR_ARG, "iadh_profile_search: null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
+    CU(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->st));
+    BatchOut b;
+    memset(&b.st, 0, sizeof b.st);
+    ProfileHost ph;
+    int rc = upload_profile(c, p, ph, b.st.h2d_bytes);
+    std::vector<GhmTask> tasks;
+    if (rc == IADH_OK) {
+        std::vector<int32_t> part;
+        list_partition(c, rank, n_ranks, part);
+        for (int32_t l : part) {
+            const unsigned sz = (unsigned)(c->list_off[l + 1] - c->list_off[l]);
+            const unsigned masked = (unsigned)c->masked_cnt[l];
+            if (sz - masked < (unsigned)c->prm.anchor_points) continue;  // higherLevel.cpp:40-41
+            GhmTask t;
+            init_task(t);
+            t.x_list = -1;
+            t.y_list = l;
+            t.x_object_id = p->x_object_id;
+            t.y_object_id = l;
+            t.level = p->n_segments + 1;  // GHMProfile.cpp:14
+            t.area = (unsigned)((unsigned)p->length * (sz - masked));  // GHM.cpp:228-234, level > 2
+            t.seq = (int32_t)tasks.size();
+            tasks.push_back(t);
+        }
+        rc = run_batch(c, true, ph.dev, tasks, b);
+    }
+    cudaEventRecord(e1, c->st);
+    cudaEventSynchronize(e1);
+    if (rc == IADH_OK) {
+        float ms = 0, m1 = 0, m2 = 0, m3 = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        b.st.total_ms = ms;
+        if (!tasks.empty()) {
+            cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
+            b.st.build_ms = m1 + m2;
+            cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
+            b.st.cluster_ms = m3;
+        }
+        *out = make_result(b);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n)
+{
+    if (n) *n = r ? r->bytes.size() : 0;
+    return r ? r->bytes.data() : nullptr;
+}
+const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n)
+{
+    if (n) *n = r ? r->ghm_index.size() : 0;
+    return r ? r->ghm_index.data() : nullptr;
+}
+int iadh_result_stats(const iadh_result* r, iadh_stats* s)
+{
+    if (!r || !s) return fail(IADH_ERR_ARG, "null argument");
+    *s = r->stats;
+    return IADH_OK;
+}
+void iadh_free_result(iadh_result* r) { delete r; }
+
+int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)
+{
+    if (!c || !ys || !cnt_out || !dots_out || !n_dots_out || (!p && !xs)) return fail(IADH_ERR_ARG, "iadh_build_dots: null argument");
+    CU(cudaSetDevice(c->device));
+    ProfileHost ph;
+    memset(&ph.dev, 0, sizeof ph.dev);
+    int64_t h2d = 0;
+    int rc;
+    if (p && (rc = upload_profile(c, p, ph, h2d))) return rc;
+    std::vector<GhmTask> tasks((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        init_task(tasks[i]);
+        tasks[i].x_list = p ? -1 : xs[i];
+        tasks[i].y_list = ys[i];
+        if (ys[i] < 0 || ys[i] >= c->n_lists || (!p && (xs[i] < 0 || xs[i] >= c->n_lists)))
+            return fail(IADH_ERR_ARG, "build_dots: list out of range");
+        tasks[i].seq = (int32_t)i;
+    }
+    iadh_stats st;
+    memset(&st, 0, sizeof st);
+    int64_t total = 0;
+    if (n > 0 && (rc = build_stage(c, p != nullptr, ph.dev, tasks, total, st))) return rc;
+    std::vector<uint32_t> keys((size_t)total);
+    if (total) CU(cudaMemcpyAsync(keys.data(), c->d_dots.p, 4 * (size_t)total, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    c->bd_cnt.resize(2 * (size_t)n);
+    c->bd_dots.resize(2 * (size_t)total);
+    for (int64_t i = 0; i < n; i++) {
+        c->bd_cnt[2 * i] = tasks[i].cnt[0];
+        c->bd_cnt[2 * i + 1] = tasks[i].cnt[1];
+    }
+    for (int64_t i = 0; i < total; i++) {
+        c->bd_dots[2 * i] = KEY_X(keys[i]);
+        c->bd_dots[2 * i + 1] = KEY_Y(keys[i]);
+    }
+    *cnt_out = c->bd_cnt.data();
+    *dots_out = c->bd_dots.data();
+    *n_dots_out = total;
+    return IADH_OK;
+}
+
+int iadh_omxn(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, double* out)
+{
+    if (!c || !x || !n || !out || count < 0) return fail(IADH_ERR_ARG, "iadh_omxn: bad argument");
+    if (count == 0) return IADH_OK;
+    CU(cudaSetDevice(c->device));
+    double *dx, *dout;
+    int* dn;
+    CU(cudaMalloc(&dx, 8 * count));
+    CU(cudaMalloc(&dout, 8 * count));
+    CU(cudaMalloc(&dn, 4 * count));
+    CU(cudaMemcpyAsync(dx, x, 8 * count, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(dn, n, 4 * count, cudaMemcpyHostToDevice, c->st));
+    omxn_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(dx, dn, count, dout);
+    CU(cudaMemcpyAsync(out, dout, 8 * count, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    cudaFree(dx);
+    cudaFree(dout);
+    cudaFree(dn);
+    return IADH_OK;
+}
+
+}  // extern "C"
