@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- GHM list-pair comparisons/s of the B200 collinearity engine.
+
+Workload (config.workload): BASELINE.json config 3 -- synthetic 10 genomes x 30k genes as
+100 gene lists x 3000 (20k families, planted segmental duplications; gap_size=30,
+cluster_gap=35, q=0.75, prob_cutoff=0.01, Bonferroni).  One step = one pass of the hot path:
+  * level 2 : GHM build + collinear clustering of all 5,050 list pairs, then
+  * profile search: P two-segment profiles (made from the P largest level-2 multiplicons)
+    against every list, with the masks accumulating as in higherLevel.cpp:165-171.
+metric = GHMs (list x list and profile x list comparisons) per second.
+
+  value : context resident in HBM (dataset uploaded once), device-resident throughput
+  e2e   : a fresh context per step from HOST buffers (dataset H2D inside the timed region),
+          results read back to the host -- the call a user of the C-ABI makes
+  N > 1 : one process per GPU (torchrun); the pair sequence / list partition is sharded with
+          the reference's own rules (levelTwo.cpp:98-148, parallel.cpp:96-156) and the packed
+          results are all-gathered over NCCL each call (levelTwo.cpp:225-269,
+          higherLevel.cpp:279-314).  Fixed total work => "strong" scaling.
+
+--impl reference times the UNMODIFIED reference objects (oracle/_ref/ref_harness, all host
+threads) on the same C3 files; falls back to the oracle port when oracle/_ref is absent.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "i-adhore_b200", "python"))
+
+from iadhore_b200 import capi, ingest, profiles, synth  # noqa: E402
+
+METRIC = "GHM list-pair comparisons/s"
+UNIT = "GHM/s"
+REF_HARNESS = os.path.join(REPO, "oracle", "_ref", "ref_harness")
+
+
+def workload_config(name: str):
+    if name == "c3":
+        return synth.config_c3(1.0)
+    if name == "c4":
+        return synth.config_c4(1.0)
+    if name.startswith("c3s"):
+        return synth.config_c3(float(name[3:]))
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(ds, res_stats, xs, ys):
+    """clustering stage reads each dot once (8 B as an (x,y) pair) and writes the
+    packed result once (17 B/AP + 102 B/cluster + 33 B/multiplicon); build stage reads 5 B per
+    element of both lists and writes each dot once (4 B packed key in this implementation)."""
+    sizes = np.diff(ds.list_off)
+    build = 5 * int(sizes[xs].sum() + sizes[ys].sum()) + 4 * res_stats["n_dots"]
+    cluster = 8 * res_stats["n_dots"] + 17 * res_stats["n_anchorpoints"] + 102 * res_stats["n_baseclusters"] + \
+        33 * res_stats["n_multiplicons"]
+    return build, cluster
+
+
+def make_profiles(ds, l2_bytes, n_profiles):
+    ms = capi.parse_packed(l2_bytes)
+    order = sorted(range(len(ms)), key=lambda i: (-sum(len(c.aps) for c in ms[i].clusters), i))[:n_profiles]
+    out = []
+    for i in order:
+        m = ms[i]
+        out.append((m, profiles.simple_profile(ds, m.x_object_id, m.y_object_id, m)))
+    return out
+
+
+def hot_path_step(eng, profs, rank, n_ranks, gather=None):
+    """One pass of the hot path; returns (units, stats list, launches)."""
+    eng.clear_masks()
+    launches = 1
+    r = eng.level2_all_pairs(rank, n_ranks)
+    if gather:
+        gather(r.bytes)
+    stats = [r.stats]
+    units = r.stats["n_ghm"]
+    for m, p in profs:
+        eng.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
+        eng.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
+        launches += 2
+        pr = eng.profile_search(p, rank, n_ranks)
+        if gather:
+            gather(pr.bytes)
+        stats.append(pr.stats)
+        units += pr.stats["n_ghm"]
+    launches += sum(s["kernel_launches"] for s in stats)
+    return units, stats, launches
+
+
+def run_reference(cfg, n_profiles, threads, tmpdir):
+    """The unmodified reference objects on the same workload files (bounded: L2 + n_profiles)."""
+    if os.path.exists(REF_HARNESS):
+        ini = synth.write_reference_inputs(cfg, tmpdir, n_threads=threads)
+        t0 = time.time()
+        p = subprocess.run([REF_HARNESS, ini, "-", "--time", "--threads", str(threads), "--max-profiles", str(n_profiles)],
+                           capture_output=True, text=True)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            raise RuntimeError("ref_harness failed: " + p.stderr[-400:])
+        l2 = re.search(r"L2: pairs=(\d+) dots=(\d+) build=([\d.]+)s run=([\d.]+)s wall=([\d.]+)s", p.stderr)
+        hl = re.search(r"HL: profiles=(\d+) ghmprofiles=(\d+) build=([\d.]+)s run=([\d.]+)s wall=([\d.]+)s", p.stderr)
+        units = int(l2.group(1)) + int(hl.group(2))
+        t = float(l2.group(5)) + float(hl.group(5))
+        return dict(kind="reference", units=units, seconds=t, l2_pairs=int(l2.group(1)), l2_s=float(l2.group(5)),
+                    hl_ghm=int(hl.group(2)), hl_s=float(hl.group(5)), dots=int(l2.group(2)), process_wall_s=wall)
+    # oracle port, multi-threaded
+    ds = ingest.dataset_from_synth(cfg)
+    eng = capi.Engine(capi.ORACLE_LIB, "oracle_", ds)
+    import ctypes as C
+    eng.lib.oracle_set_threads(eng.ctx, C.c_int(threads))
+    eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    t0 = time.time()
+    r = eng.level2_all_pairs()
+    t1 = time.time()
+    profs = make_profiles(ds, r.bytes, n_profiles)
+    t2 = time.time()
+    units, stats, _ = hot_path_step(eng, profs, 0, 1)
+    t3 = time.time()
+    hl_units = units - r.stats["n_ghm"]
+    hl_s = (t3 - t2) - (t1 - t0)  # the step re-ran L2; subtract its earlier time as estimate
+    return dict(kind="port", units=units, seconds=(t1 - t0) + max(hl_s, 0.0), l2_pairs=r.stats["n_ghm"], l2_s=t1 - t0,
+                hl_ghm=hl_units, hl_s=max(hl_s, 0.0), dots=r.stats["n_dots"], process_wall_s=t3 - t0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--profiles", type=int, default=32, help="profile searches per step")
+    ap.add_argument("--ref-profiles", type=int, default=4, help="profile searches in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = workload_config(a.workload)
+    ncores = os.cpu_count() or 1
+    config = {"workload": f"{a.workload}: synthetic {len(cfg.genomes)} genomes x {cfg.genomes[0].n_lists} lists x "
+                          f"{cfg.genomes[0].genes_per_list} genes, {cfg.n_families} families; L2 all pairs + "
+                          f"{a.profiles} profile searches per step",
+              "gap_size": cfg.gap_size, "cluster_gap": cfg.cluster_gap, "q_value": cfg.q_value,
+              "prob_cutoff": cfg.prob_cutoff, "anchor_points": cfg.anchor_points, "mult_hyp": "bonferroni",
+              "l2_flush": "working set per step (dots + per-GHM workspaces, >300 MB) exceeds the 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        last = None
+        with tempfile.TemporaryDirectory(prefix="iadh_ref_") as td:
+            for i in range(a.warmup + a.steps):
+                # the CPU path has no warm-up effects worth W extra minutes: run at most one warm-up
+                if i < a.warmup - 1:
+                    continue
+                last = run_reference(cfg, a.ref_profiles, ncores, td)
+                if i >= a.warmup:
+                    vals.append(last)
+        units = sum(v["units"] for v in vals)
+        secs = sum(v["seconds"] for v in vals)
+        value = units / secs
+        sample = (f"L2 all {last['l2_pairs']} pairs ({last['l2_s']:.2f}s) + first {a.ref_profiles} profiles of the "
+                  f"reference's own queue x all lists = {last['hl_ghm']} GHMProfiles ({last['hl_s']:.2f}s) per step")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": last["kind"], "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "l2_pairs_per_s": last["l2_pairs"] / last["l2_s"],
+                "hl_ghm_per_s": last["hl_ghm"] / last["hl_s"] if last["hl_s"] > 0 else None}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(payload: bytes):
+        """levelTwo.cpp:225-269 / higherLevel.cpp:279-314: all ranks end with every rank's packed
+        multiplicons in rank order (sizes, then padded bytes, over NCCL)."""
+        n = torch.tensor([len(payload)], dtype=torch.int64, device="cuda")
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        mx = int(max(int(s.item()) for s in sizes))
+        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf)
+        return [o[:int(s.item())] for o, s in zip(outs, sizes)]
+
+    t_setup = time.time()
+    ds = ingest.dataset_from_synth(cfg)
+    eng = capi.load_product(ds, device=local_rank)
+    eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    r0 = eng.level2_all_pairs()          # untimed: provides the multiplicons the profiles are made from
+    profs = make_profiles(ds, r0.bytes, a.profiles)
+    setup_s = time.time() - t_setup
+    g = gather if dist else None
+
+    for _ in range(a.warmup):
+        hot_path_step(eng, profs, rank, world, g)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = time.perf_counter()
+    units = 0
+    launches = 0
+    all_stats = []
+    for _ in range(a.steps):
+        u, st, ln = hot_path_step(eng, profs, rank, world, g)
+        units += u
+        launches += ln
+        all_stats.append(st)
+    barrier()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    # max over ranks of the time, sum of the units
+    if dist:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        u = torch.tensor([units, launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        units, launches = int(u[0].item()), int(u[1].item())
+    value = units / dt
+
+    # e2e: fresh context from host buffers every step (dataset H2D + results D2H in the timed region)
+    barrier()
+    e0 = time.perf_counter()
+    e_units = 0
+    h2d = d2h = 0
+    ds_bytes = ds.list_off.nbytes + ds.fam.nbytes + ds.gid.nbytes + ds.num_id.nbytes + ds.flags.nbytes
+    fam_csr_bytes = 4 * (int(ds.fam.max()) + 2) + ds.fam.nbytes
+    e_steps = max(1, min(a.steps, 3))
+    for _ in range(e_steps):
+        e2 = capi.load_product(ds, device=local_rank)
+        e2.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+        u, st, _ = hot_path_step(e2, profs, rank, world, g)
+        e2.close()
+        e_units += u
+        h2d += ds_bytes + fam_csr_bytes + sum(s["h2d_bytes"] for s in st)
+        d2h += sum(s["d2h_bytes"] for s in st)
+    barrier()
+    edt = time.perf_counter() - e0
+    if dist:
+        t = torch.tensor([edt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        edt = float(t.item())
+        u = torch.tensor([e_units], dtype=torch.int64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        e_units = int(u.item())
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (K2, clustering) and of the build kernels (K1), L2 launch
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    xs, ys = capi.plan_pairs(np.diff(ds.list_off), rank, world)
+    l2s = [st[0] for st in all_stats]
+    b_build, b_cluster = algorithmic_bytes(ds, l2s[0], xs, ys)
+    cl_ms = float(np.mean([s["cluster_ms"] for s in l2s]))
+    bd_ms = float(np.mean([s["build_ms"] for s in l2s]))
+    ach = b_cluster / (cl_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "cluster_kernel (K2, level-2 launch)", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_cluster,
+            "launch_ms": cl_ms,
+            "note": "latency/dependency-bound greedy clustering: its figure of merit is GHM/s, not GB/s (SURVEY 8d)"}
+    ach_b = b_build / (bd_ms * 1e-3) / 1e9 if bd_ms > 0 else None
+    roof_build = {"bound": "hbm", "kernel": "build_kernel count+fill (K1, level-2 launch)", "achieved": ach_b, "peak": peak,
+                  "unit": "GB/s", "frac": (ach_b / peak) if ach_b else None, "traffic": None,
+                  "algorithmic_bytes_per_launch": b_build, "launch_ms": bd_ms}
+    hl_stats = [s for st in all_stats for s in st[1:]]
+    l2_ms = float(np.mean([s["total_ms"] for s in l2s]))
+    hl_ms = float(np.mean([s["total_ms"] for s in hl_stats])) if hl_stats else None
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        with tempfile.TemporaryDirectory(prefix="iadh_cpu_") as td:
+            try:
+                rr = run_reference(cfg, a.ref_profiles, ncores, td)
+                cpu = {"value": rr["units"] / rr["seconds"], "unit": UNIT, "cores": ncores, "kind": rr["kind"],
+                       "sample": f"L2 all {rr['l2_pairs']} pairs ({rr['l2_s']:.2f}s) + {a.ref_profiles} profiles x all "
+                                 f"lists = {rr['hl_ghm']} GHMProfiles ({rr['hl_s']:.2f}s), {ncores} threads",
+                       "l2_pairs_per_s": rr["l2_pairs"] / rr["l2_s"],
+                       "hl_ghm_per_s": rr["hl_ghm"] / rr["hl_s"] if rr["hl_s"] > 0 else None}
+            except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+                cpu = {"value": None, "unit": UNIT, "cores": ncores, "kind": "unavailable", "sample": str(e)[:200]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64+int32", "data": "synthetic", "config": config, "clocks": clk,
+            "e2e": {"value": e_units / edt, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
+                    "d2h_bytes_per_step": d2h // e_steps, "ms_per_step": 1e3 * edt / e_steps},
+            "gpu_launches": launches, "roofline": roof, "roofline_build": roof_build, "cpu_baseline": cpu,
+            "units_per_step": units // a.steps, "l2_pairs_per_s": l2s[0]["n_ghm"] * (world if world > 1 else 1) / (l2_ms * 1e-3),
+            "hl_ghm_per_s": (hl_stats[0]["n_ghm"] * world / (hl_ms * 1e-3)) if hl_ms else None,
+            "anchor_points_per_s_build": l2s[0]["n_dots"] / (bd_ms * 1e-3) if bd_ms > 0 else None,
+            "l2_call_ms": l2_ms, "hl_call_ms": hl_ms, "setup_s": setup_s}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

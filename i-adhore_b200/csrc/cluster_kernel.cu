@@ -499,7 +499,7 @@ __device__ void calc_probability(Ghm& g, ClusterRec& c)
         if (have) {
             const double distance = cm::dpd_d(px, py, x, y);
             const int cc = (int)ceil(0.5 * distance * distance);
-            const double p_i = 1.0 - cm::pow_int(1.0 - density, cc);
+            const double p_i = 1.0 - cm::pow_ref(1.0 - density, cc);
             probability *= p_i;
         }
         have = true;

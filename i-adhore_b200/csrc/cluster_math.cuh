@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "common.h"
+#include "glibc_pow.cuh"
 
 namespace cm {
 
@@ -188,9 +189,8 @@ __device__ inline bool partial_overlap(const ClusterRec& A, const ClusterRec& B,
 }
 
 // ---------------------------------------------------------------------------------------
-// pow(b, n) for 0 < b <= 1, integer n >= 0, correctly rounded from a double-double
-// square-and-multiply: the reference calls glibc pow(double,double)
-// (BaseCluster.cpp:567), which is within 1 ulp of this.
+// Fallback power for bases outside glibc_pow_pos()'s domain (only reachable through the omxn
+// hook): correctly rounded double-double square-and-multiply.
 struct dd {
     double hi, lo;
 };
@@ -224,10 +224,19 @@ __device__ inline double pow_int(double base, int n)
     return r.hi + r.lo;
 }
 
+// pow(base, n) as the reference's libm computes it (BaseCluster.cpp:567, hpmath.cpp:21)
+__device__ inline double pow_ref(double base, int n)
+{
+    if (n == 0) return 1.0;
+    if (base > 0.0 && base < 1e300 && n > 0 && base >= 2.2250738585072014e-308) return glibc_pow_pos(base, (double)n);
+    if (base == 0.0 && n > 0) return 0.0;
+    return pow_int(base, n);
+}
+
 // hpmath.cpp:18-36
 __device__ inline double omxn(double x, int n)
 {
-    if (fabs(x) > 0.1) return pow_int(1.0 - x, n);
+    if (fabs(x) > 0.1) return pow_ref(1.0 - x, n);
     const double epsilon = fabs(x * 2.2204460492503131e-16);
     double term = 1.0, result = term;
     int i = 0;

@@ -149,30 +149,27 @@ struct iadh_ctx {
 
 // DataSet::sortGeneLists (DataSet.cpp:1088-1105): size descending; equal sizes come out in
 // descending list index because the multimap is walked in reverse
-static void sort_lists(iadh_ctx* c)
+static void sort_by_size(const std::vector<int64_t>& sizes, std::vector<int32_t>& v)
 {
-    std::vector<int32_t>& v = c->index_to_list;
-    v.resize(c->n_lists);
+    v.resize(sizes.size());
     std::iota(v.begin(), v.end(), 0);
-    const std::vector<int64_t>& off = c->list_off;
-    std::stable_sort(v.begin(), v.end(), [&off](int a, int b) {
-        const int64_t sa = off[a + 1] - off[a], sb = off[b + 1] - off[b];
-        if (sa != sb) return sa > sb;
+    std::stable_sort(v.begin(), v.end(), [&sizes](int a, int b) {
+        if (sizes[a] != sizes[b]) return sizes[a] > sizes[b];
         return a > b;
     });
 }
 
 // DataSet::getSomeWorkL2 (levelTwo.cpp:113-175): anti-diagonal walk over the size-sorted lower
 // triangle, each pair assigned to the least-loaded rank (getProcForPackage, :98-111)
-static void pair_sequence(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& xs, std::vector<int32_t>& ys)
+static void plan_pairs(const std::vector<int64_t>& sizes, const std::vector<int32_t>& index_to_list, int rank,
+                       int n_ranks, std::vector<int32_t>& xs, std::vector<int32_t>& ys)
 {
-    const unsigned n = (unsigned)c->n_lists;
+    const unsigned n = (unsigned)sizes.size();
     std::vector<uint64_t> load(n_ranks, 0);
     unsigned cX = 0, cY = 0;
     while (cX < n) {
-        const unsigned lX = c->index_to_list[cX], lY = c->index_to_list[cY];
-        const unsigned sx = (unsigned)(c->list_off[lX + 1] - c->list_off[lX]);
-        const unsigned sy = (unsigned)(c->list_off[lY + 1] - c->list_off[lY]);
+        const unsigned lX = index_to_list[cX], lY = index_to_list[cY];
+        const unsigned sx = (unsigned)sizes[lX], sy = (unsigned)sizes[lY];
         const uint64_t weight = (unsigned)(sx * sy);  // 32-bit product, as the reference
         unsigned sp = 0;
         for (unsigned p = 1; p < load.size(); p++)
@@ -195,16 +192,33 @@ static void pair_sequence(const iadh_ctx* c, int rank, int n_ranks, std::vector<
 }
 
 // ParToolBox::statPartWorklSort (parallel.cpp:96-156): size-sorted lists dealt to the lightest package
-static void list_partition(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& out)
+static void plan_lists(const std::vector<int64_t>& sizes, const std::vector<int32_t>& index_to_list, int rank,
+                       int n_ranks, std::vector<int32_t>& out)
 {
     std::vector<uint64_t> load(n_ranks, 0);
-    for (int32_t l : c->index_to_list) {
+    for (int32_t l : index_to_list) {
         unsigned sp = 0;
         for (unsigned p = 1; p < load.size(); p++)
             if (load[p] < load[sp]) sp = p;
-        load[sp] += (uint64_t)(c->list_off[l + 1] - c->list_off[l]);
+        load[sp] += (uint64_t)sizes[l];
         if ((int)sp == rank) out.push_back(l);
     }
+}
+
+static std::vector<int64_t> ctx_sizes(const iadh_ctx* c)
+{
+    std::vector<int64_t> s(c->n_lists);
+    for (int l = 0; l < c->n_lists; l++) s[l] = c->list_off[l + 1] - c->list_off[l];
+    return s;
+}
+static void sort_lists(iadh_ctx* c) { sort_by_size(ctx_sizes(c), c->index_to_list); }
+static void pair_sequence(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& xs, std::vector<int32_t>& ys)
+{
+    plan_pairs(ctx_sizes(c), c->index_to_list, rank, n_ranks, xs, ys);
+}
+static void list_partition(const iadh_ctx* c, int rank, int n_ranks, std::vector<int32_t>& out)
+{
+    plan_lists(ctx_sizes(c), c->index_to_list, rank, n_ranks, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -502,10 +516,10 @@ static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, 
     return rc;
 }
 
-__global__ void omxn_kernel(const double* x, const int* n, long long count, double* out)
+__global__ void omxn_kernel(const double* x, const int* n, long long count, double* out, int mode)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = cm::omxn(x[i], n[i]);
+    if (i < count) out[i] = mode ? cm::pow_ref(x[i], n[i]) : cm::omxn(x[i], n[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,6 +616,9 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->prm.mult_hyp = IADH_MH_BONFERRONI;
     c->prm.q_value = 0.75;
     c->prm.prob_cutoff = 0.01;
+    // tuning / test knobs (the anchor-point pool grows automatically when too small)
+    if (const char* e = getenv("IADH_POOL_FACTOR")) c->pool_factor = std::max(1, atoi(e));
+    if (const char* e = getenv("IADH_CTAS_PER_SM")) c->ctas_per_sm = std::max(1, atoi(e));
     *out = c;
     return IADH_OK;
 }
@@ -807,9 +824,46 @@ int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, 
     return IADH_OK;
 }
 
+int iadh_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out)
+{
+    if (!sizes || !out || !n_out || n_lists < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(IADH_ERR_ARG, "iadh_plan_lists: bad argument");
+    std::vector<int64_t> sz(sizes, sizes + n_lists);
+    std::vector<int32_t> itl, res;
+    sort_by_size(sz, itl);
+    plan_lists(sz, itl, rank, n_ranks, res);
+    std::copy(res.begin(), res.end(), out);
+    *n_out = (int64_t)res.size();
+    return IADH_OK;
+}
+
+int iadh_plan_pairs(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x, int32_t* out_y,
+                    int64_t* n_out)
+{
+    if (!sizes || !out_x || !out_y || !n_out || n_lists < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(IADH_ERR_ARG, "iadh_plan_pairs: bad argument");
+    std::vector<int64_t> sz(sizes, sizes + n_lists);
+    std::vector<int32_t> itl, xs, ys;
+    sort_by_size(sz, itl);
+    plan_pairs(sz, itl, rank, n_ranks, xs, ys);
+    std::copy(xs.begin(), xs.end(), out_x);
+    std::copy(ys.begin(), ys.end(), out_y);
+    *n_out = (int64_t)xs.size();
+    return IADH_OK;
+}
+
+static int math_hook(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, double* out, int mode);
 int iadh_omxn(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, double* out)
 {
-    if (!c || !x || !n || !out || count < 0) return fail(IADH_ERR_ARG, "iadh_omxn: bad argument");
+    return math_hook(c, x, n, count, out, 0);
+}
+int iadh_pow(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, double* out)
+{
+    return math_hook(c, x, n, count, out, 1);
+}
+static int math_hook(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, double* out, int mode)
+{
+    if (!c || !x || !n || !out || count < 0) return fail(IADH_ERR_ARG, "iadh_omxn/iadh_pow: bad argument");
     if (count == 0) return IADH_OK;
     CU(cudaSetDevice(c->device));
     double *dx, *dout;
@@ -819,7 +873,7 @@ int iadh_omxn(iadh_ctx* c, const double* x, const int32_t* n, int64_t count, dou
     CU(cudaMalloc(&dn, 4 * count));
     CU(cudaMemcpyAsync(dx, x, 8 * count, cudaMemcpyHostToDevice, c->st));
     CU(cudaMemcpyAsync(dn, n, 4 * count, cudaMemcpyHostToDevice, c->st));
-    omxn_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(dx, dn, count, dout);
+    omxn_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(dx, dn, count, dout, mode);
     CU(cudaMemcpyAsync(out, dout, 8 * count, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     cudaFree(dx);

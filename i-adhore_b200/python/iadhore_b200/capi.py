@@ -54,7 +54,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
-           "free_result", "build_dots", "omxn", "last_error", "version"]
+           "free_result", "build_dots", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
 def gap_sizes(gap_size: int) -> List[int]:
@@ -244,8 +244,45 @@ class Engine:
         self._chk(self._f("omxn")(self.ctx, _p(xa, C.c_double), _p(na, C.c_int32), C.c_int64(len(xa)), _p(out, C.c_double)))
         return out
 
+    def pow(self, base: np.ndarray, n: np.ndarray) -> np.ndarray:
+        xa = np.ascontiguousarray(base, dtype=np.float64)
+        na = np.ascontiguousarray(n, dtype=np.int32)
+        out = np.zeros_like(xa)
+        self._chk(self._f("pow")(self.ctx, _p(xa, C.c_double), _p(na, C.c_int32), C.c_int64(len(xa)), _p(out, C.c_double)))
+        return out
+
     def version(self) -> str:
         return self._f("version")().decode()
+
+
+def plan_pairs(sizes: Sequence[int], rank: int = 0, n_ranks: int = 1, lib_path: str = PRODUCT_LIB,
+               prefix: str = "iadh_") -> Tuple[np.ndarray, np.ndarray]:
+    """Host-only: the L2 pair sequence of (rank, n_ranks) (levelTwo.cpp:98-175)."""
+    lib = C.CDLL(lib_path)
+    sz = np.ascontiguousarray(sizes, dtype=np.int64)
+    n = len(sz)
+    xs = np.zeros(n * (n + 1) // 2 + 1, np.int32)
+    ys = np.zeros_like(xs)
+    cnt = C.c_int64()
+    rc = getattr(lib, prefix + "plan_pairs")(_p(sz, C.c_int64), C.c_int32(n), C.c_int(rank), C.c_int(n_ranks),
+                                             _p(xs, C.c_int32), _p(ys, C.c_int32), C.byref(cnt))
+    if rc:
+        raise RuntimeError("plan_pairs failed")
+    return xs[:cnt.value].copy(), ys[:cnt.value].copy()
+
+
+def plan_lists(sizes: Sequence[int], rank: int = 0, n_ranks: int = 1, lib_path: str = PRODUCT_LIB,
+               prefix: str = "iadh_") -> np.ndarray:
+    """Host-only: this rank's y-lists for a profile search (parallel.cpp:96-156)."""
+    lib = C.CDLL(lib_path)
+    sz = np.ascontiguousarray(sizes, dtype=np.int64)
+    out = np.zeros(len(sz) + 1, np.int32)
+    cnt = C.c_int64()
+    rc = getattr(lib, prefix + "plan_lists")(_p(sz, C.c_int64), C.c_int32(len(sz)), C.c_int(rank), C.c_int(n_ranks),
+                                             _p(out, C.c_int32), C.byref(cnt))
+    if rc:
+        raise RuntimeError("plan_lists failed")
+    return out[:cnt.value].copy()
 
 
 def load_product(ds: Dataset, device: int = 0) -> Engine:

@@ -151,8 +151,23 @@ int iadh_build_dots(iadh_ctx* ctx, const iadh_profile_desc* profile, const int32
                     const int32_t* y_list, int64_t n, const int64_t** cnt_out,
                     const int32_t** dots_out, int64_t* n_dots_out);
 
+/* Host-only scheduling helpers (no GPU needed; what the two drivers above use internally).
+ * sizes[l] = remapped length of list l.
+ * iadh_plan_lists: DataSet::sortGeneLists order (DataSet.cpp:1088-1105) dealt to n_ranks
+ *   packages as ParToolBox::statPartWorklSort does (parallel.cpp:96-156); writes this rank's
+ *   lists (big -> small) to out[0..*n_out), out must hold n_lists entries.
+ * iadh_plan_pairs: the pair walk of DataSet::getSomeWorkL2 (levelTwo.cpp:113-175) with the
+ *   least-loaded-rank rule (levelTwo.cpp:98-111); out_x/out_y must hold n(n+1)/2 entries. */
+int iadh_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out,
+                    int64_t* n_out);
+int iadh_plan_pairs(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x,
+                    int32_t* out_y, int64_t* n_out);
+
 /* hpmath::omxn (hpmath.cpp:18-36) evaluated on the device for n inputs (KAT hook). */
 int iadh_omxn(iadh_ctx* ctx, const double* x, const int32_t* n, int64_t count, double* out);
+/* pow(base, (double)n) as the reference's libm evaluates it inside
+ * BaseCluster::calculateProbability (BaseCluster.cpp:567), on the device (KAT hook). */
+int iadh_pow(iadh_ctx* ctx, const double* base, const int32_t* n, int64_t count, double* out);
 
 const char* iadh_last_error(void);
 const char* iadh_version(void);

@@ -3,6 +3,7 @@
 // The oracle behind the same C interface as include/iadhore_b200.h (prefix oracle_
 // instead of iadh_), so a parity test drives both with identical calls.
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -320,7 +321,51 @@ int oracle_omxn(oracle_ctx*, const double* x, const int32_t* n, int64_t count, d
     return IADH_OK;
 }
 
+int oracle_pow(oracle_ctx*, const double* x, const int32_t* n, int64_t count, double* out)
+{
+    for (int64_t i = 0; i < count; i++) out[i] = std::pow(x[i], n[i]);  // BaseCluster.cpp:567
+    return IADH_OK;
+}
+
 int oracle_gap_sizes(int gap_size, int32_t* gaps) { return gap_sizes(gap_size, gaps); }
+
+static oracle_ctx* sizes_ctx(const int64_t* sizes, int32_t n)
+{
+    oracle_ctx* c = new oracle_ctx();
+    c->lists.resize(n);
+    for (int l = 0; l < n; l++) {
+        c->lists[l].id = l;
+        c->lists[l].fam.assign((size_t)sizes[l], 0);
+    }
+    sort_lists(c);
+    return c;
+}
+
+int oracle_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out)
+{
+    oracle_ctx* c = sizes_ctx(sizes, n_lists);
+    std::vector<int> part;
+    list_partition(c, rank, n_ranks, part);
+    for (size_t i = 0; i < part.size(); i++) out[i] = part[i];
+    *n_out = (int64_t)part.size();
+    delete c;
+    return IADH_OK;
+}
+
+int oracle_plan_pairs(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x, int32_t* out_y,
+                      int64_t* n_out)
+{
+    oracle_ctx* c = sizes_ctx(sizes, n_lists);
+    std::vector<std::pair<int, int>> seq;
+    pair_sequence(c, rank, n_ranks, seq);
+    for (size_t i = 0; i < seq.size(); i++) {
+        out_x[i] = seq[i].first;
+        out_y[i] = seq[i].second;
+    }
+    *n_out = (int64_t)seq.size();
+    delete c;
+    return IADH_OK;
+}
 
 const char* oracle_last_error(void) { return g_err.c_str(); }
 const char* oracle_version(void) { return "oracle-port-1"; }

@@ -8,7 +8,12 @@
 // (Multiplicon.cpp:210-264).  The dump ("trace") is what pins oracle_core.cpp and
 // the CUDA path.  Trace layout: see tests/trace_io.py.
 //
-// usage: ref_harness <ini> <trace.bin> [--no-hl] [--max-profiles N] [--time]
+// usage: ref_harness <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--time]
+//                    [--threads T] [--no-dump]
+// With --threads the GHMs of a stage are evaluated concurrently (each thread owns its GHM,
+// exactly like the reference's work functions, DataSet.h:79,204); results are consumed in
+// sequence order, so the trace is identical to the 1-thread one.  --no-dump (or "-" as the
+// trace path) turns the harness into the CPU timing baseline used by bench.py.
 //
 // Private members of the reference classes are reached with the macro below;
 // this TU is the only one compiled that way (object layout is unaffected).
@@ -31,6 +36,9 @@
 #include <stdexcept>
 #include <cmath>
 #include <cassert>
+#include <atomic>
+#include <thread>
+#include <functional>
 #include <ext/hash_map>
 #include <ext/hash_set>
 #include <pthread.h>
@@ -52,21 +60,12 @@
 #undef private
 #undef protected
 
-#include <cstdio>
-#include <cstdint>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
-#include <deque>
-#include <chrono>
-
 using namespace std;
 
-static FILE* out = NULL;
-static void w32(int32_t v) { fwrite(&v, 4, 1, out); }
-static void w8(uint8_t v) { fwrite(&v, 1, 1, out); }
-static void wf64(double v) { fwrite(&v, 8, 1, out); }
+typedef std::string Blob;
+static void w32(Blob& b, int32_t v) { b.append((const char*)&v, 4); }
+static void w8(Blob& b, uint8_t v) { b.append((const char*)&v, 1); }
+static void wf64(Blob& b, double v) { b.append((const char*)&v, 8); }
 
 static map<string, int> famIds, geneIds;
 static int intern(map<string, int>& m, const string& s)
@@ -83,28 +82,28 @@ static double now()
     return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static void dumpDots(const GHM& ghm)
+static void dumpDots(Blob& b, const GHM& ghm)
 {
     for (int o = 0; o < 2; o++) {
         int n = 0;
         for (map<int, set<int> >::const_iterator ix = ghm.matrix[o].begin(); ix != ghm.matrix[o].end(); ix++)
             n += ix->second.size();
-        w32(n);
+        w32(b, n);
         for (map<int, set<int> >::const_iterator ix = ghm.matrix[o].begin(); ix != ghm.matrix[o].end(); ix++)
             for (set<int>::const_iterator iy = ix->second.begin(); iy != ix->second.end(); iy++) {
-                w32(ix->first);
-                w32(*iy);
+                w32(b, ix->first);
+                w32(b, *iy);
             }
     }
 }
 
-static void dumpPacked(const vector<Multiplicon*>& mps)
+static void dumpPacked(Blob& b, const vector<Multiplicon*>& mps)
 {
     int sz = Multiplicon::getPackSize(mps);
     vector<char> buf(sz);
     Multiplicon::packMultiplicons(mps, buf.data());
-    w32(sz);
-    fwrite(buf.data(), 1, sz, out);
+    w32(b, sz);
+    b.append(buf.data(), sz);
 }
 
 // GHMProfile whose setMultiplicons never drops a multiplicon (minHomologs = 0):
@@ -119,18 +118,48 @@ protected:
     }
 };
 
+struct ItemOut {
+    Blob blob;
+    vector<Multiplicon*> mps;
+    double tBuild, tRun;
+    long dots;
+    ItemOut() : tBuild(0), tRun(0), dots(0) {}
+};
+
+static void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
+{
+    if (threads <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&]() {
+            while (true) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                fn(i);
+            }
+        });
+    for (size_t t = 0; t < th.size(); t++) th[t].join();
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) {
-        fprintf(stderr, "usage: %s <ini> <trace.bin> [--no-hl] [--max-profiles N] [--time]\n", argv[0]);
+        fprintf(stderr, "usage: %s <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--time] [--threads T] [--no-dump]\n", argv[0]);
         return 2;
     }
-    bool doHL = true, timing = false;
+    bool doHL = true, timing = false, dump = strcmp(argv[2], "-") != 0;
     long maxProfiles = -1;
+    int threads = 1;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--no-hl")) doHL = false;
         else if (!strcmp(argv[i], "--time")) timing = true;
+        else if (!strcmp(argv[i], "--no-dump")) dump = false;
         else if (!strcmp(argv[i], "--max-profiles") && i + 1 < argc) maxProfiles = atol(argv[++i]);
+        else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
     }
 
     ParToolBox::init(&argc, &argv);
@@ -144,9 +173,13 @@ int main(int argc, char** argv)
     ds.sortGeneLists();
     cout.rdbuf(coutbuf);
 
-    out = fopen(argv[2], "wb");
-    if (!out) { perror("trace"); return 1; }
-    fwrite("IADHTRC1", 1, 8, out);
+    FILE* out = NULL;
+    if (dump) {
+        out = fopen(argv[2], "wb");
+        if (!out) { perror("trace"); return 1; }
+    }
+    Blob hdr;
+    hdr.append("IADHTRC1", 8);
 
     // ---- params -----------------------------------------------------------------
     int gaps[10];
@@ -154,91 +187,108 @@ int main(int argc, char** argv)
     settings.getGapSizes(gaps);
     int ngaps = 0;
     while (ngaps < 10 && gaps[ngaps] > 0) ngaps++;
-    w32(ngaps);
-    for (int i = 0; i < 10; i++) w32(i < ngaps ? gaps[i] : 0);
-    w32(settings.getGapSize());
-    w32(settings.getClusterGap());
-    w32(settings.getTandemGap());
-    w32(settings.getAnchorPoints());
-    w32((int)settings.getMultHypCorMethod()); // None=0, Bonferroni=1, FDR=2 (Settings.h)
-    w32(settings.level2Only() ? 1 : 0);
-    wf64(settings.getQValue());
-    wf64(settings.getProbCutoff());
+    w32(hdr, ngaps);
+    for (int i = 0; i < 10; i++) w32(hdr, i < ngaps ? gaps[i] : 0);
+    w32(hdr, settings.getGapSize());
+    w32(hdr, settings.getClusterGap());
+    w32(hdr, settings.getTandemGap());
+    w32(hdr, settings.getAnchorPoints());
+    w32(hdr, (int)settings.getMultHypCorMethod()); // None=0, Bonferroni=1, FDR=2 (Settings.h)
+    w32(hdr, settings.level2Only() ? 1 : 0);
+    wf64(hdr, settings.getQValue());
+    wf64(hdr, settings.getProbCutoff());
 
     // ---- dataset ----------------------------------------------------------------
     const vector<GeneList*>& gl = ds.genelists;
-    w32((int)gl.size());
+    w32(hdr, (int)gl.size());
     for (size_t l = 0; l < gl.size(); l++) {
         const vector<ListElement*>& re = gl[l]->getRemappedElements();
         const vector<ListElement*>& all = gl[l]->getElements();
-        w32(gl[l]->getID());
-        w32(intern(famIds, "genome:" + gl[l]->getGenomeName())); // genome id (for `identical`)
+        w32(hdr, gl[l]->getID());
+        w32(hdr, intern(famIds, "genome:" + gl[l]->getGenomeName())); // genome id (for `identical`)
         // raw (pre tandem-remap) elements: lets the python ingest be checked too
-        w32((int)all.size());
+        w32(hdr, (int)all.size());
         for (size_t i = 0; i < all.size(); i++) {
             const Gene& g = all[i]->getGene();
-            w32(intern(famIds, g.getFamily()));
-            w32(intern(geneIds, g.getID()));
-            w32(all[i]->getNumID());
-            w8(all[i]->getOrientation() ? 1 : 0);
-            w8(g.isRemapped() ? 1 : 0);
+            w32(hdr, intern(famIds, g.getFamily()));
+            w32(hdr, intern(geneIds, g.getID()));
+            w32(hdr, all[i]->getNumID());
+            w8(hdr, all[i]->getOrientation() ? 1 : 0);
+            w8(hdr, g.isRemapped() ? 1 : 0);
         }
-        w32((int)re.size());
+        w32(hdr, (int)re.size());
         for (size_t i = 0; i < re.size(); i++) {
             const Gene& g = re[i]->getGene();
-            w32(intern(famIds, g.getFamily()));
-            w32(intern(geneIds, g.getID()));
-            w32(re[i]->getNumID());
-            w8(re[i]->getOrientation() ? 1 : 0);
+            w32(hdr, intern(famIds, g.getFamily()));
+            w32(hdr, intern(geneIds, g.getID()));
+            w32(hdr, re[i]->getNumID());
+            w8(hdr, re[i]->getOrientation() ? 1 : 0);
         }
     }
-    w32((int)ds.indexToList.size());
-    for (size_t i = 0; i < ds.indexToList.size(); i++) w32(ds.indexToList[i]);
+    w32(hdr, (int)ds.indexToList.size());
+    for (size_t i = 0; i < ds.indexToList.size(); i++) w32(hdr, ds.indexToList[i]);
+    if (dump) fwrite(hdr.data(), 1, hdr.size(), out);
 
     // ---- level 2: every list pair in the 1-thread order of getSomeWorkL2 ----------
-    double tBuild = 0, tRun = 0;
-    long nPairs = 0, nDots = 0;
-    vector<Multiplicon*> l2;
+    vector<pair<unsigned, unsigned> > pairs;
     {
         unsigned n = gl.size();
         unsigned cX = 0, cY = 0;
         while (cX < n) {
-            unsigned lX = ds.indexToList[cX], lY = ds.indexToList[cY];
-            double t0 = now();
-            GHM ghm(*gl[lX], *gl[lY], false);
-            ghm.buildMatrix(settings.useFamily());
-            double t1 = now();
-            w32(1);
-            w32(lX);
-            w32(lY);
-            dumpDots(ghm);
-            nDots += ghm.count_points[0] + ghm.count_points[1];
-            double t2 = now();
-            ghm.run(settings);
-            double t3 = now();
-            tBuild += t1 - t0;
-            tRun += t3 - t2;
-            nPairs++;
-            vector<Multiplicon*> mps;
-            ghm.getMultiplicons(mps);
-            dumpPacked(mps);
-            l2.insert(l2.end(), mps.begin(), mps.end());
+            pairs.push_back(make_pair(ds.indexToList[cX], ds.indexToList[cY]));
             // next pair (levelTwo.cpp:152-164)
             if ((cX - cY) < 2) {
-                if (cX == cY && cX == n - 1) { cX = n; break; }
+                if (cX == cY && cX == n - 1) break;
                 unsigned newD = cX + cY + 1;
                 cX = (newD < n) ? newD : n - 1;
                 cY = (newD < n) ? 0 : newD - n + 1;
             } else { cX--; cY++; }
         }
     }
+    vector<ItemOut> l2out(pairs.size());
+    const bool useFamily = settings.useFamily();
+    double wall0 = now();
+    parallel_for(pairs.size(), threads, [&](size_t i) {
+        ItemOut& o = l2out[i];
+        unsigned lX = pairs[i].first, lY = pairs[i].second;
+        double t0 = now();
+        GHM ghm(*gl[lX], *gl[lY], false);
+        ghm.buildMatrix(useFamily);
+        double t1 = now();
+        if (dump) {
+            w32(o.blob, 1);
+            w32(o.blob, lX);
+            w32(o.blob, lY);
+            dumpDots(o.blob, ghm);
+        }
+        o.dots = ghm.count_points[0] + ghm.count_points[1];
+        double t2 = now();
+        ghm.run(settings);
+        double t3 = now();
+        o.tBuild = t1 - t0;
+        o.tRun = t3 - t2;
+        ghm.getMultiplicons(o.mps);
+        if (dump) dumpPacked(o.blob, o.mps);
+    });
+    double wallL2 = now() - wall0;
+    double tBuild = 0, tRun = 0;
+    long nDots = 0;
+    vector<Multiplicon*> l2;
+    for (size_t i = 0; i < l2out.size(); i++) {
+        if (dump) fwrite(l2out[i].blob.data(), 1, l2out[i].blob.size(), out);
+        Blob().swap(l2out[i].blob);
+        tBuild += l2out[i].tBuild;
+        tRun += l2out[i].tRun;
+        nDots += l2out[i].dots;
+        l2.insert(l2.end(), l2out[i].mps.begin(), l2out[i].mps.end());
+    }
     if (timing)
-        fprintf(stderr, "L2: pairs=%ld dots=%ld build=%.6fs run=%.6fs multiplicons=%zu\n",
-                nPairs, nDots, tBuild, tRun, l2.size());
+        fprintf(stderr, "L2: pairs=%zu dots=%ld build=%.6fs run=%.6fs wall=%.6fs threads=%d multiplicons=%zu\n",
+                pairs.size(), nDots, tBuild, tRun, wallL2, threads, l2.size());
 
-    // ---- higher level: mirror of DataSet::profileDetection, 1 thread ----------------
-    long nProfiles = 0, nGhmp = 0;
-    double tHLbuild = 0, tHLrun = 0;
+    // ---- higher level: mirror of DataSet::profileDetection ------------------------------
+    long nProfiles = 0, nGhmp = 0, nFound = 0;
+    double tHLbuild = 0, tHLrun = 0, wallHL = 0;
     if (doHL && !settings.level2Only()) {
         cout.rdbuf(NULL);
         ds.sortByMultipliconSize(l2);
@@ -246,6 +296,7 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < l2.size(); i++) todo.push_front(l2[i]);
         unsigned profile_id = 1;
         unsigned mid = 1;
+        const unsigned minAP = (unsigned)settings.getAnchorPoints();
         while (!todo.empty()) {
             if (maxProfiles >= 0 && nProfiles >= maxProfiles) break;
             Multiplicon* m = todo.front();
@@ -264,54 +315,59 @@ int main(int argc, char** argv)
                     throw ProfileException("all elements masked");
                 m->align(settings.getAlignmentMethod(), settings.getMaxGapsInAlignment());
                 if (m->getLevel() > 2) m->checkAlignment(settings.getAnchorPoints());
+                Blob pb;
                 if (m->getLevel() == 2) {
                     GeneList& lX = *gl[m->getXObjectID()];
                     lX.mask(m->getBeginX(), m->getEndX());
-                    w32(2); w32(m->getXObjectID()); w32(m->getBeginX()); w32(m->getEndX());
+                    w32(pb, 2); w32(pb, m->getXObjectID()); w32(pb, m->getBeginX()); w32(pb, m->getEndX());
                 }
                 lY.mask(m->getBeginY(), m->getEndY());
-                w32(2); w32(m->getYObjectID()); w32(m->getBeginY()); w32(m->getEndY());
+                w32(pb, 2); w32(pb, m->getYObjectID()); w32(pb, m->getBeginY()); w32(pb, m->getEndY());
 
                 // profile descriptor
                 const vector<GeneList*>& segs = profile->getSegments();
                 int S = segs.size(), L = segs[0]->getRemappedElements().size();
-                w32(3); w32(S); w32(L); w32(segs[0]->getID());
-                for (int s = 0; s < S; s++) {
-                    const vector<ListElement*>& e = segs[s]->getRemappedElements();
-                    if ((int)e.size() != L) { fprintf(stderr, "ragged profile\n"); return 1; }
-                    for (int x = 0; x < L; x++) {
-                        if (e[x]->isGap()) { w32(-1); w32(-1); w32(-1); w8(2); continue; }
-                        const Gene& g = e[x]->getGene();
-                        w32(intern(famIds, g.getFamily()));
-                        w32(intern(geneIds, g.getID()));
-                        w32(e[x]->getNumID());
-                        w8(e[x]->getOrientation() ? 1 : 0);
+                w32(pb, 3); w32(pb, S); w32(pb, L); w32(pb, segs[0]->getID());
+                if (dump)
+                    for (int s = 0; s < S; s++) {
+                        const vector<ListElement*>& e = segs[s]->getRemappedElements();
+                        if ((int)e.size() != L) { fprintf(stderr, "ragged profile\n"); return 1; }
+                        for (int x = 0; x < L; x++) {
+                            if (e[x]->isGap()) { w32(pb, -1); w32(pb, -1); w32(pb, -1); w8(pb, 2); continue; }
+                            const Gene& g = e[x]->getGene();
+                            w32(pb, intern(famIds, g.getFamily()));
+                            w32(pb, intern(geneIds, g.getID()));
+                            w32(pb, e[x]->getNumID());
+                            w8(pb, e[x]->getOrientation() ? 1 : 0);
+                        }
                     }
-                }
+                if (dump) fwrite(pb.data(), 1, pb.size(), out);
                 nProfiles++;
 
-                vector<Multiplicon*> found;
+                // the lists searched for this profile (higherLevel.cpp:36-41)
+                vector<int> lists;
                 for (size_t yi = 0; yi < ds.indexToList.size(); yi++) {
                     int lst = ds.indexToList[yi];
                     GeneList& g = *gl[lst];
-                    if (g.getSize() - g.getNumberOfMaskedElements() < (unsigned)settings.getAnchorPoints())
-                        continue;
-                    // (a) unfiltered run: what the device path must reproduce
+                    if (g.getSize() - g.getNumberOfMaskedElements() >= minAP) lists.push_back(lst);
+                }
+                vector<ItemOut> hout(lists.size());
+                double w0 = now();
+                parallel_for(lists.size(), threads, [&](size_t i) {
+                    ItemOut& o = hout[i];
+                    GeneList& g = *gl[lists[i]];
                     vector<Multiplicon*> pre;
-                    {
-                        double t0 = now();
+                    if (dump) {
+                        // (a) unfiltered run: what the device path must reproduce
                         GHMProfileNoFilter ghm(*profile, g);
                         ghm.buildMatrix();
-                        double t1 = now();
-                        w32(4); w32(lst);
-                        dumpDots(ghm);
+                        w32(o.blob, 4); w32(o.blob, lists[i]);
+                        dumpDots(o.blob, ghm);
                         ghm.run(settings);
                         ghm.getMultiplicons(pre);
-                        dumpPacked(pre);
-                        (void)t0; (void)t1;
+                        dumpPacked(o.blob, pre);
                     }
                     // (b) the reference's own run (with the homolog filter)
-                    vector<Multiplicon*> post;
                     {
                         double t0 = now();
                         GHMProfile ghm(*profile, g);
@@ -319,28 +375,40 @@ int main(int argc, char** argv)
                         double t1 = now();
                         ghm.run(settings);
                         double t2 = now();
-                        tHLbuild += t1 - t0; tHLrun += t2 - t1; nGhmp++;
-                        ghm.getMultiplicons(post);
+                        o.tBuild = t1 - t0;
+                        o.tRun = t2 - t1;
+                        ghm.getMultiplicons(o.mps);
                     }
-                    // kept flags: post is an in-order subsequence of pre
-                    w32((int)pre.size());
-                    size_t k = 0;
-                    for (size_t i = 0; i < pre.size(); i++) {
-                        bool kept = false;
-                        if (k < post.size() && pre[i]->getPackSize() == post[k]->getPackSize()) {
-                            vector<char> a(pre[i]->getPackSize()), b(post[k]->getPackSize());
-                            pre[i]->pack(a.data()); post[k]->pack(b.data());
-                            kept = (a == b);
+                    if (dump) {
+                        // kept flags: the filtered result is an in-order subsequence of `pre`
+                        w32(o.blob, (int)pre.size());
+                        size_t k = 0;
+                        for (size_t j = 0; j < pre.size(); j++) {
+                            bool kept = false;
+                            if (k < o.mps.size() && pre[j]->getPackSize() == o.mps[k]->getPackSize()) {
+                                vector<char> a(pre[j]->getPackSize()), b(o.mps[k]->getPackSize());
+                                pre[j]->pack(a.data()); o.mps[k]->pack(b.data());
+                                kept = (a == b);
+                            }
+                            if (kept) k++;
+                            w8(o.blob, kept ? 1 : 0);
                         }
-                        if (kept) k++;
-                        w8(kept ? 1 : 0);
+                        if (k != o.mps.size()) { fprintf(stderr, "kept-matching failed\n"); exit(1); }
+                        for (size_t j = 0; j < pre.size(); j++) delete pre[j];
                     }
-                    if (k != post.size()) { fprintf(stderr, "kept-matching failed\n"); return 1; }
-                    for (size_t i = 0; i < pre.size(); i++) delete pre[i];
-                    found.insert(found.end(), post.begin(), post.end());
+                });
+                wallHL += now() - w0;
+                vector<Multiplicon*> found;
+                for (size_t i = 0; i < hout.size(); i++) {
+                    if (dump) fwrite(hout[i].blob.data(), 1, hout[i].blob.size(), out);
+                    tHLbuild += hout[i].tBuild;
+                    tHLrun += hout[i].tRun;
+                    nGhmp++;
+                    found.insert(found.end(), hout[i].mps.begin(), hout[i].mps.end());
                 }
                 ds.sortByMultipliconSize(found);
-                w32(5); w32((int)found.size());
+                nFound += found.size();
+                if (dump) { Blob e; w32(e, 5); w32(e, (int)found.size()); fwrite(e.data(), 1, e.size(), out); }
                 for (size_t i = 0; i < found.size(); i++) {
                     found[i]->setParentID(mid);
                     todo.push_front(found[i]);
@@ -355,10 +423,14 @@ int main(int argc, char** argv)
         }
         cout.rdbuf(coutbuf);
     }
-    w32(0);
-    fclose(out);
+    if (dump) {
+        Blob e;
+        w32(e, 0);
+        fwrite(e.data(), 1, e.size(), out);
+        fclose(out);
+    }
     if (timing)
-        fprintf(stderr, "HL: profiles=%ld ghmprofiles=%ld build=%.6fs run=%.6fs\n",
-                nProfiles, nGhmp, tHLbuild, tHLrun);
+        fprintf(stderr, "HL: profiles=%ld ghmprofiles=%ld build=%.6fs run=%.6fs wall=%.6fs threads=%d found=%ld\n",
+                nProfiles, nGhmp, tHLbuild, tHLrun, wallHL, threads, nFound);
     return 0;
 }

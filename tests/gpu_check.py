@@ -79,8 +79,21 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", default="small")
     ap.add_argument("--skip-golden", action="store_true")
+    ap.add_argument("--trace", default=None, help="replay one (large) reference trace")
     a = ap.parse_args()
     bad = 0
+    if a.trace:
+        tr = read_trace(a.trace)
+        eng = capi.load_product(tr.dataset)
+        t0 = time.time()
+        errs = pl.replay_trace(eng, tr, pl.P_RTOL)
+        print(f"{a.trace}: {'OK' if not errs else 'FAIL'} ({time.time() - t0:.2f}s), "
+              f"{sum(1 for e in tr.events if e[0] == 'l2')} L2 + {sum(1 for e in tr.events if e[0] == 'hl')} HL GHMs")
+        for e in errs[:10]:
+            print("   ", e)
+        errs0 = pl.replay_trace(eng, tr, 0.0, check_dots=False)
+        print("   p-values bit-exact too:", not errs0)
+        bad += len(errs)
     if not a.skip_golden:
         bad += check_golden()
     if a.size == "small":

@@ -89,56 +89,4 @@ def oracle_engine(ds: capi.Dataset) -> capi.Engine:
     return capi.Engine(capi.ORACLE_LIB, "oracle_", ds)
 
 
-def simple_profile(ds: capi.Dataset, xl: int, yl: int, m: capi.PMultiplicon) -> capi.Profile:
-    """A 2-segment profile from a level-2 multiplicon, aligned on its anchor points only (the
-    hot path does not care which aligner produced the profile; this one is ours: anchor
-    points of the first cluster in x order are matched column by column, everything between
-    two anchors is laid out x-segment first then y-segment, padded with gaps)."""
-    bx, ex, by, ey = m.bounds
-    c = m.clusters[0]
-    aps = c.aps[np.argsort(c.aps[:, 2], kind="stable")]
-    # strictly monotone sub-chain of anchors (in x and, given orientation, in y)
-    chain = []
-    for gx, gy, x, y, real in aps:
-        if not chain:
-            chain.append((x, y))
-            continue
-        px, py = chain[-1]
-        if x > px and ((c.orient and y > py) or ((not c.orient) and y < py)):
-            chain.append((x, y))
-    xo, yo = int(ds.list_off[xl]), int(ds.list_off[yl])
-    segx: List[int] = []
-    segy: List[int] = []
-    yflip = not c.orient
-
-    def emit(xa, xb, ya_list):
-        xs_ = list(range(xa, xb))
-        n = max(len(xs_), len(ya_list))
-        segx.extend(xs_ + [-1] * (n - len(xs_)))
-        segy.extend(ya_list + [-1] * (n - len(ya_list)))
-
-    x0, y0 = chain[0]
-    segx.append(x0)
-    segy.append(y0)
-    for (x1, y1) in chain[1:]:
-        ys_between = list(range(y0 + 1, y1)) if not yflip else list(range(y0 - 1, y1, -1))
-        emit(x0 + 1, x1, ys_between)
-        segx.append(x1)
-        segy.append(y1)
-        x0, y0 = x1, y1
-    L = len(segx)
-    fam = np.full(2 * L, -1, np.int32)
-    gid = np.full(2 * L, -1, np.int32)
-    nid = np.full(2 * L, -1, np.int32)
-    flg = np.full(2 * L, capi.F_GAP, np.uint8)
-    for s, (seg, off, flip) in enumerate(((segx, xo, False), (segy, yo, yflip))):
-        for i, e in enumerate(seg):
-            if e < 0:
-                continue
-            k = s * L + i
-            fam[k] = ds.fam[off + e]
-            gid[k] = ds.gid[off + e]
-            nid[k] = ds.num_id[off + e]
-            st = int(ds.flags[off + e] & 1)
-            flg[k] = (st ^ 1) if flip else st  # inverted y-segments carry flipped strands (GeneList.cpp:270-281)
-    return capi.Profile(2, L, xl, fam, gid, nid, flg)
+from iadhore_b200.profiles import simple_profile  # noqa: E402,F401

@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the C-ABI, libiadhore_b200.so) against
+ (1) golden traces of the unmodified reference, (2) the oracle on seeded synthetic genomes,
+ (3) size-independent properties at the full C3 shape.
+Bar (north_star): anchor points, cluster membership, bounds, levels, regression doubles
+bit-exact; p-values within 1e-12 relative (written in parity_lib.P_RTOL)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_lib as pl
+from iadhore_b200 import capi, ingest, synth
+from trace_io import read_trace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", pl.golden_traces(), ids=lambda p: p.split("/")[-1].split(".")[0])
+def test_cuda_replays_reference_trace(path):
+    tr = read_trace(path)
+    eng = capi.load_product(tr.dataset)
+    errs = pl.replay_trace(eng, tr, rtol_p=pl.P_RTOL)
+    eng.close()
+    assert not errs, errs[:5]
+
+
+def _pair(cfg, mult_hyp):
+    ds = ingest.dataset_from_synth(cfg)
+    gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+    for e in (gpu, cpu):
+        e.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, mult_hyp, cfg.q_value, cfg.prob_cutoff)
+    return ds, gpu, cpu
+
+
+@pytest.mark.parametrize("mode", [capi.MH_NONE, capi.MH_BONFERRONI, capi.MH_FDR])
+def test_cuda_matches_oracle_small(mode):
+    cfg = synth.config_small(seed=30 + mode)
+    ds, gpu, cpu = _pair(cfg, mode)
+    rg, rc = gpu.level2_all_pairs(), cpu.level2_all_pairs()
+    assert rg.n_multiplicons > 50
+    assert capi.compare_packed(rg.bytes, rc.bytes, pl.P_RTOL) is None
+    assert np.array_equal(rg.ghm_index, rc.ghm_index)
+    assert rg.stats["n_dots"] == rc.stats["n_dots"]
+    # profile searches with masks accumulating like higherLevel.cpp:165-171
+    ms = capi.parse_packed(rc.bytes)
+    order = sorted(range(len(ms)), key=lambda i: -sum(len(c.aps) for c in ms[i].clusters))[:25]
+    found = 0
+    for i in order:
+        m = ms[i]
+        prof = pl.simple_profile(ds, m.x_object_id, m.y_object_id, m)
+        for e in (gpu, cpu):
+            e.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
+            e.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
+        pg, pc = gpu.profile_search(prof), cpu.profile_search(prof)
+        assert capi.compare_packed(pg.bytes, pc.bytes, pl.P_RTOL) is None, f"profile {i}"
+        found += pg.n_multiplicons
+    assert found > 0
+
+
+def test_fdr_sort_with_many_tied_pvalues():
+    """> 16 clusters with equal p-values in one GHM: exercises the restated libstdc++
+    introsort (unstable on ties) on the device."""
+    n = 40
+    fam, gid, flg, off = [], [], [], [0]
+    nf = 0
+    # list 0: n blocks of 4 collinear genes separated by 60 fillers; list 1: same blocks, same spacing
+    for l in range(2):
+        f, g, s = [], [], []
+        for b in range(n):
+            for k in range(4):
+                f.append(b * 4 + k)
+            for k in range(60):
+                f.append(100000 + nf)
+                nf += 1
+        fam += f
+        gid += list(range(len(gid), len(gid) + len(f)))
+        flg += [1] * len(f)
+        off.append(len(fam))
+    # densify family ids
+    u = {v: i for i, v in enumerate(sorted(set(fam)))}
+    ds = capi.Dataset(np.array(off, np.int64), np.array([u[v] for v in fam], np.int32), np.array(gid, np.int32),
+                      np.arange(len(fam), dtype=np.int32), np.array(flg, np.uint8))
+    gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+    for e in (gpu, cpu):
+        e.set_params(mult_hyp=capi.MH_FDR, prob_cutoff=0.5)
+    rg, rc = gpu.level2_pairs([0], [1]), cpu.level2_pairs([0], [1])
+    ms = capi.parse_packed(rc.bytes)
+    assert sum(len(m.clusters) for m in ms) >= 17
+    ps = [c.p for m in ms for c in m.clusters]
+    assert len(set(ps)) < len(ps)  # ties present
+    assert capi.compare_packed(rg.bytes, rc.bytes, pl.P_RTOL) is None
+
+
+def test_edge_cases():
+    # empty dataset
+    ds0 = capi.Dataset(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                       np.zeros(0, np.uint8))
+    e = capi.load_product(ds0)
+    r = e.level2_all_pairs()
+    assert r.n_multiplicons == 0 and r.bytes == b"\x00\x00\x00\x00"
+    e.close()
+    # ragged: empty list, 1-gene list, lists without any homolog, self comparison only
+    off = np.array([0, 0, 1, 4, 9], np.int64)
+    fam = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8], np.int32)
+    ds1 = capi.Dataset(off, fam, np.arange(9, dtype=np.int32), np.arange(9, dtype=np.int32), np.ones(9, np.uint8))
+    gpu, cpu = capi.load_product(ds1), pl.oracle_engine(ds1)
+    rg, rc = gpu.level2_all_pairs(), cpu.level2_all_pairs()
+    assert rg.bytes == rc.bytes == b"\x00\x00\x00\x00"
+    assert rg.stats["n_ghm"] == 10
+    # bad arguments are errors, not crashes
+    with pytest.raises(RuntimeError):
+        gpu.level2_pairs([0], [7])
+    with pytest.raises(RuntimeError):
+        gpu.mask_range(3, 0, 99)
+    with pytest.raises(RuntimeError):
+        gpu.set_params(anchor_points=2)
+    gpu.close()
+
+
+def test_everything_masked_profile_search_is_empty():
+    tr = read_trace(pl.golden_traces()[0])
+    gpu = capi.load_product(tr.dataset)
+    pl.set_params_from(gpu, tr.params)
+    for l in range(tr.dataset.n_lists):
+        gpu.mask_range(l, 0, tr.dataset.size(l) - 1)
+    prof = [ev[1] for ev in tr.events if ev[0] == "profile"][0]
+    r = gpu.profile_search(prof)
+    assert r.n_multiplicons == 0 and r.stats["n_ghm"] == 0
+    gpu.clear_masks()
+    assert gpu.profile_search(prof).stats["n_ghm"] == tr.dataset.n_lists
+    gpu.close()
+
+
+def test_list_longer_than_reference_limit_is_rejected():
+    n = 46341
+    ds = capi.Dataset(np.array([0, n], np.int64), np.zeros(n, np.int32), np.arange(n, dtype=np.int32),
+                      np.arange(n, dtype=np.int32), np.ones(n, np.uint8))
+    with pytest.raises(RuntimeError, match="46340"):
+        capi.load_product(ds)
+
+
+def test_omxn_device_known_answers():
+    tr = read_trace(pl.golden_traces()[0])
+    gpu, cpu = capi.load_product(tr.dataset), pl.oracle_engine(tr.dataset)
+    x = np.concatenate([[1e-4, 0.3], np.linspace(1e-9, 0.6, 500)])
+    n = np.concatenate([[1800, 7], np.arange(1, 501)]).astype(np.int32)
+    a, b = gpu.omxn(x, n), cpu.omxn(x, n)
+    assert a[0].hex() == "0x1.aba78d4067e56p-1"
+    assert abs(a[1] - float.fromhex("0x1.5152be12f5a5ep-4")) <= 2 ** -56
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-15
+    gpu.close()
+
+
+def test_pow_matches_host_libm():
+    """The device pow of the probability kernel (glibc 2.39 FMA variant restated) against the
+    host libm of this box, bit for bit, over the (density, exponent) domain of
+    BaseCluster::calculateProbability."""
+    tr = read_trace(pl.golden_traces()[0])
+    gpu, cpu = capi.load_product(tr.dataset), pl.oracle_engine(tr.dataset)
+    rng = np.random.RandomState(7)
+    n = 2_000_000
+    dens = np.where(rng.rand(n) < 0.5, 10.0 ** (-9 + 8.7 * rng.rand(n)), rng.rand(n) * 0.999)
+    base = 1.0 - dens
+    c = np.maximum(1, (10.0 ** (5.3 * rng.rand(n))).astype(np.int32))
+    c[::7] = 1 + rng.randint(0, 3000, size=len(c[::7]))
+    a, b = gpu.pow(base, c), cpu.pow(base, c)
+    big = np.abs(c * np.log(base)) >= 512     # documented: only 1 - pow() has to agree there
+    assert np.array_equal(a[~big], b[~big])
+    assert np.array_equal(1.0 - a[big], 1.0 - b[big])
+    gpu.close()
+
+
+def test_pool_exhaustion_is_retried(monkeypatch):
+    """A deliberately tiny anchor-point pool must trigger the engine's rerun with a larger pool
+    and still give the reference's answer."""
+    tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
+    monkeypatch.setenv("IADH_POOL_FACTOR", "1")
+    gpu = capi.load_product(tr.dataset)
+    monkeypatch.delenv("IADH_POOL_FACTOR")
+    errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL, check_dots=False)
+    gpu.close()
+    assert not errs, errs[:3]
+
+
+@pytest.mark.parametrize("scale", [float(os.environ.get("IADH_TEST_C3_SCALE", "1.0"))])
+def test_c3_full_size_properties(scale):
+    """BASELINE config 3 (10 genomes x 30k genes, 100 lists, 5050 pairs) through the CUDA path
+    only; checked through size-independent properties."""
+    cfg = synth.config_c3(scale)
+    ds = ingest.dataset_from_synth(cfg)
+    gpu = capi.load_product(ds)
+    gpu.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    r = gpu.level2_all_pairs()
+    n = ds.n_lists
+    assert r.stats["n_ghm"] == n * (n + 1) // 2
+    # idempotence
+    r2 = gpu.level2_all_pairs()
+    assert r2.bytes == r.bytes
+    # sharding: the union of the ranks' streams is the whole stream, GHM by GHM
+    xs, ys = capi.plan_pairs(np.diff(ds.list_off))
+    key = {(int(x), int(y)): i for i, (x, y) in enumerate(zip(xs, ys))}
+    ms = capi.parse_packed(r.bytes)
+    per_ghm = {}
+    for m, g in zip(ms, r.ghm_index):
+        per_ghm.setdefault(int(g), []).append(m)
+    shard_total = 0
+    for rank in range(2):
+        rs = gpu.level2_all_pairs(rank, 2)
+        xr, yr = capi.plan_pairs(np.diff(ds.list_off), rank, 2)
+        msr = capi.parse_packed(rs.bytes)
+        shard_total += len(msr)
+        for m, g in zip(msr, rs.ghm_index):
+            full = per_ghm[key[(int(xr[g]), int(yr[g]))]]
+            assert any(np.array_equal(m.clusters[0].aps, f.clusters[0].aps) for f in full)
+    assert shard_total == len(ms)
+    # every anchor point is a homologous pair of different genes; clusters obey the thresholds
+    nap = 0
+    for m in ms:
+        xo, yo = ds.list_off[m.x_object_id], ds.list_off[m.y_object_id]
+        assert m.level == 2 and sum(len(c.aps) for c in m.clusters) >= cfg.anchor_points
+        for c in m.clusters:
+            a = c.aps
+            nap += len(a)
+            assert np.all(np.diff(a[:, 2]) >= 0)                       # multiset order: x ascending
+            assert np.all(ds.fam[xo + a[:, 2]] == ds.fam[yo + a[:, 3]])
+            assert np.all(ds.gid[xo + a[:, 2]] != ds.gid[yo + a[:, 3]])
+            assert np.all(ds.num_id[xo + a[:, 2]] == a[:, 0]) and np.all(ds.num_id[yo + a[:, 3]] == a[:, 1])
+            same = (ds.flags[xo + a[:, 2]] & 1) == (ds.flags[yo + a[:, 3]] & 1)
+            assert c.bounds == (a[:, 2].min(), a[:, 2].max(), a[:, 3].min(), a[:, 3].max())
+            assert 0.0 <= c.p <= cfg.prob_cutoff
+            x, y = a[:, 2].astype(float), a[:, 3].astype(float)
+            r2v = np.corrcoef(x, y)[0, 1] ** 2
+            assert r2v >= cfg.q_value - 1e-9
+            assert (np.corrcoef(x, y)[0, 1] > 0) == bool(c.orient)
+    assert nap == r.stats["n_anchorpoints"] and len(ms) == r.stats["n_multiplicons"]
+    gpu.close()
