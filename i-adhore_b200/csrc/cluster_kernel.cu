@@ -44,6 +44,10 @@ struct Ghm {
     MultRec* mult;
     int nmult;
     int* out_mults;
+    double* rb_d;   // join cache: best distance / partner id of every cluster, rank, redo list
+    int* rb_j;
+    int* rank;
+    int* redo;
     uint32_t* tmp;
     int tmp_cap;
     int status;
@@ -110,16 +114,57 @@ __device__ void block_min_pair(double& d, long long& k, Red* sh)
 
 // ---- AP pool ------------------------------------------------------------------------------
 
-__device__ int pool_alloc(Ghm& g, int n)
+__device__ __forceinline__ int next_cap(int n);
+
+// Anchor-point pool: bump allocation of self-describing blocks [owner cluster, capacity,
+// payload...].  Growth of a cluster abandons its old block; when the pool runs out, the live
+// blocks (those a live cluster still points at) are slid down in allocation order and trimmed
+// to the capacity class of their current size.  Live data is at most ~4.7 D entries, so with
+// pool_factor >= 8 an allocation can only fail after a collection if the host under-sized the
+// pool on purpose (then the GHM reports status 1 and the engine reruns it with a larger pool).
+__device__ void pool_gc(Ghm& g)
 {
-    // single-thread contexts only
-    if (g.pool_used + n > g.pool_cap) {
-        g.status = 1;
-        return -1;
+    int r = 0, w = 0;
+    while (r < g.pool_used) {
+        const int owner = (int)g.pool[r];
+        const int cap = (int)g.pool[r + 1];
+        const int payload = r + 2;
+        ClusterRec& c = g.cl[owner];
+        if (owner < g.ncl && !c.dead && c.off == payload) {
+            int ncap = 8;
+            while (ncap < c.n) ncap <<= 1;
+            if (ncap > cap) ncap = cap;
+            if (w != r)
+                for (int i = 0; i < c.n; i++) {
+                    g.pool[w + 2 + i] = g.pool[payload + i];
+                    g.pflag[w + 2 + i] = g.pflag[payload + i];
+                }
+            g.pool[w] = (uint32_t)owner;
+            g.pool[w + 1] = (uint32_t)ncap;
+            c.off = w + 2;
+            c.cap = ncap;
+            w += 2 + ncap;
+        }
+        r += 2 + cap;
+    }
+    g.pool_used = w;
+}
+
+// single-thread contexts only (the rest of the CTA waits at a barrier)
+__device__ int pool_alloc(Ghm& g, int n, int owner)
+{
+    if (g.pool_used + n + 2 > g.pool_cap) {
+        pool_gc(g);
+        if (g.pool_used + n + 2 > g.pool_cap) {
+            g.status = 1;
+            return -1;
+        }
     }
     const int off = g.pool_used;
-    g.pool_used += n;
-    return off;
+    g.pool[off] = (uint32_t)owner;
+    g.pool[off + 1] = (uint32_t)n;
+    g.pool_used += n + 2;
+    return off + 2;
 }
 
 __device__ __forceinline__ int next_cap(int n)
@@ -134,7 +179,7 @@ __device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
 {
     if (c.n == c.cap) {
         const int ncap = c.cap * 2;
-        const int noff = pool_alloc(g, ncap);
+        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl));
         if (noff < 0) return false;
         for (int i = 0; i < c.n; i++) {
             g.pool[noff + i] = g.pool[c.off + i];
@@ -170,7 +215,7 @@ __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B)
     const int n = A.n + B.n;
     if (n > A.cap) {
         const int ncap = next_cap(n);
-        const int noff = pool_alloc(g, ncap);
+        const int noff = pool_alloc(g, ncap, (int)(&A - g.cl));
         if (noff < 0) return false;
         for (int i = 0; i < A.n; i++) {
             g.pool[noff + i] = g.pool[A.off + i];
@@ -281,8 +326,8 @@ __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s
             int len = 0;
             for (int j = i; j >= 0; j = nxt[j]) len++;
             const int cap = next_cap(len + (len >> 1));
-            const int off = pool_alloc(g, cap);
-            if (off >= 0 && g.ncl < g.cl_cap) {
+            const int off = (g.ncl < g.cl_cap) ? pool_alloc(g, cap, g.ncl) : -1;
+            if (off >= 0) {
                 ClusterRec& c = g.cl[g.ncl];
                 c.off = off; c.cap = cap; c.n = len;
                 c.mult = -1; c.mnext = -1; c.orient = (unsigned char)o; c.was_twisted = 0; c.dead = 0;
@@ -301,7 +346,7 @@ __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s
                 g.ncl++;
                 sh_s[0] = lastj;
             } else {
-                g.status = 1;
+                if (!g.status) g.status = 2;  // cluster table full
                 sh_s[0] = -1;
             }
         }
@@ -454,31 +499,165 @@ __device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double q, int&
     return true;
 }
 
-// GHM::joinClusters (GHM.cpp:392-404)
-__device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red)
+// One candidate pair of getClosestClusters (GHM.cpp:420-438): distance, then the interval and
+// merged-r^2 tests.  `bd`/`brank` = best so far of the caller; a pair replaces it when closer,
+// or equally close and earlier in vector order (the reference scans pairs lexicographically
+// with a strict '<').  Rejections by x / y extent are exact: every candidate distance of
+// distanceToCluster is a dpd between a point of A's hull and one of B's, and dpd >= |dx|, |dy|.
+__device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q,
+                                            double bd, int brank, int rankJ, double& dout)
 {
-    int pi, pj;
-    while (closest_clusters(g, gap, o, o, q, pi, pj, red)) {
-        if (threadIdx.x == 0) {
-            ClusterRec& A = g.cl[g.bc[o][pi]];
-            ClusterRec& B = g.cl[g.bc[o][pj]];
-            merge_clusters(g, A, B);
-            B.dead = 1;
+    const double xgap = cm::maxd(cI.x_end1 - cJ.x_end2, cJ.x_end1 - cI.x_end2);
+    if (xgap > bd) return false;
+    const uint32_t s1 = g.pool[cI.off], e1 = g.pool[cI.off + cI.n - 1];
+    const uint32_t s2 = g.pool[cJ.off], e2 = g.pool[cJ.off + cJ.n - 1];
+    const double ilo = cm::mind(cm::mind(cI.y_end1, cI.y_end2), (double)min(KEY_Y(s1), KEY_Y(e1)));
+    const double ihi = cm::maxd(cm::maxd(cI.y_end1, cI.y_end2), (double)max(KEY_Y(s1), KEY_Y(e1)));
+    const double jlo = cm::mind(cm::mind(cJ.y_end1, cJ.y_end2), (double)min(KEY_Y(s2), KEY_Y(e2)));
+    const double jhi = cm::maxd(cm::maxd(cJ.y_end1, cJ.y_end2), (double)max(KEY_Y(s2), KEY_Y(e2)));
+    if (cm::maxd(ilo - jhi, jlo - ihi) > bd) return false;
+    const double d = cm::dist_to_cluster(cI, cJ, s1, e1, s2, e2);
+    if (!(d < bd || (d == bd && rankJ < brank))) return false;
+    if (!(cm::r2_merged(cI, cJ) >= q && cm::partial_overlap(cI, cJ, g.pool))) return false;
+    dout = d;
+    return true;
+}
+
+// best partner of the cluster at position `pos` among the later positions (one warp)
+__device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = g.nbc[o];
+    const int idI = g.bc[o][pos];
+    const ClusterRec& cI = g.cl[idI];
+    double bd = gap + 1;
+    int bj = -1, brank = 0x7fffffff;
+    for (int j = pos + 1 + lane; j < n; j += 32) {
+        const int idJ = g.bc[o][j];
+        double d;
+        if (pair_better(g, cI, g.cl[idJ], q, bd, brank, g.rank[idJ], d)) {
+            if (d < gap + 1) {
+                bd = d;
+                bj = idJ;
+                brank = g.rank[idJ];
+            }
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, sft);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, sft);
+        const int orank = __shfl_xor_sync(0xffffffffu, brank, sft);
+        if (oj >= 0 && (bj < 0 || od < bd || (od == bd && orank < brank))) {
+            bd = od;
+            bj = oj;
+            brank = orank;
+        }
+    }
+    if (lane == 0) {
+        g.rb_d[idI] = bd;
+        g.rb_j[idI] = bj;
+    }
+}
+
+// GHM::joinClusters (GHM.cpp:392-404).  The reference rescans all pairs after every merge
+// (O(n^3)); here every cluster caches its best later partner and only the rows touched by a
+// merge are recomputed.  Vector order is kept as a static rank per pass: erasing a merged
+// cluster never changes the relative order of the others.
+__device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
+{
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int n = g.nbc[o];
+    if (n < 2) return;
+    for (int i = tid; i < n; i += NT) g.rank[g.bc[o][i]] = i;
+    __syncthreads();
+    for (int row = warp; row < n - 1; row += NW) join_row(g, o, row, gap, q);
+    if (tid == 0) {
+        g.rb_d[g.bc[o][n - 1]] = gap + 1;
+        g.rb_j[g.bc[o][n - 1]] = -1;
+    }
+    __syncthreads();
+    while (true) {
+        // global minimum over the rows: (distance, rank of i, rank of j)
+        double bd = gap + 1;
+        long long bk = -1;
+        for (int i = tid; i < n; i += NT) {
+            const int id = g.bc[o][i];
+            const int j = g.rb_j[id];
+            if (j < 0) continue;
+            const double d = g.rb_d[id];
+            const long long k = ((long long)g.rank[id] << 32) | (unsigned)g.rank[j];
+            if (bk < 0 || d < bd || (d == bd && k < bk)) {
+                bd = d;
+                bk = k;
+            }
+        }
+        block_min_pair(bd, bk, red);
+        if (bk < 0) break;
+        // ranks -> current positions (ranks are sorted along the vector: binary search)
+        const int rankA = (int)(bk >> 32), rankB = (int)(bk & 0xffffffff);
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (g.rank[g.bc[o][mid]] < rankA) lo = mid + 1;
+            else hi = mid;
+        }
+        const int pA = lo;
+        hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (g.rank[g.bc[o][mid]] < rankB) lo = mid + 1;
+            else hi = mid;
+        }
+        const int pB = lo;
+        const int idA = g.bc[o][pA], idB = g.bc[o][pB];
+        __syncthreads();
+        if (tid == 0) {
+            merge_clusters(g, g.cl[idA], g.cl[idB]);
+            g.cl[idB].dead = 1;
+            sh_s[2] = 0;  // rows to recompute
         }
         __syncthreads();
         if (g.status) return;
-        // erase position pj from the vector (order preserved)
-        const int n = g.nbc[o];
-        int v = 0;
-        const int chunk0 = pj;
-        for (int basei = chunk0; basei < n - 1; basei += NT) {
-            const int i = basei + threadIdx.x;
-            if (i < n - 1) v = g.bc[o][i + 1];
-            __syncthreads();
-            if (i < n - 1) g.bc[o][i] = v;
+        // erase position pB from the vector (order preserved)
+        {
+            int v = 0;
+            for (int basei = pB; basei < n - 1; basei += NT) {
+                const int i = basei + tid;
+                if (i < n - 1) v = g.bc[o][i + 1];
+                __syncthreads();
+                if (i < n - 1) g.bc[o][i] = v;
+                __syncthreads();
+            }
+            n--;
+            if (tid == 0) g.nbc[o] = n;
             __syncthreads();
         }
-        if (threadIdx.x == 0) g.nbc[o] = n - 1;
+        // refresh the cache: rows that pointed at A or B (and A's own row) are recomputed in full,
+        // earlier rows only re-test their pair with the merged cluster
+        const ClusterRec& cA = g.cl[idA];
+        for (int i = tid; i < n; i += NT) {
+            const int id = g.bc[o][i];
+            const int j = g.rb_j[id];
+            if (id == idA || j == idA || j == idB) {
+                if (i < n - 1) g.redo[atomicAdd(&sh_s[2], 1)] = i;
+                else {
+                    g.rb_d[id] = gap + 1;
+                    g.rb_j[id] = -1;
+                }
+            } else if (i < pA) {
+                double d;
+                const double cur = (j >= 0) ? g.rb_d[id] : (double)(gap + 1);
+                const int crank = (j >= 0) ? g.rank[j] : 0x7fffffff;
+                if (pair_better(g, g.cl[id], cA, q, cur, crank, rankA, d) && d < gap + 1) {
+                    g.rb_d[id] = d;
+                    g.rb_j[id] = idA;
+                }
+            }
+        }
+        __syncthreads();
+        const int nredo = sh_s[2];
+        for (int r = warp; r < nredo; r += NW) join_row(g, o, g.redo[r], gap, q);
         __syncthreads();
     }
 }
@@ -897,7 +1076,15 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
     __shared__ int sh_i[NW];
     __shared__ int sh_s[4];
     __shared__ int sh_task;
+    __shared__ long long prof[8];
     const int tid = threadIdx.x;
+#define PROF_BEGIN() long long pt_ = clock64()
+#define PROF_END(k)                              \
+    do {                                         \
+        const long long pn_ = clock64();         \
+        if (tid == 0) prof[k] += pn_ - pt_;      \
+        pt_ = pn_;                               \
+    } while (0)
     while (true) {
         if (tid == 0) sh_task = atomicAdd(next_task, 1);
         __syncthreads();
@@ -929,6 +1116,10 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.mult = (MultRec*)(base + L.mult);
             g.nmult = 0;
             g.out_mults = (int*)(base + L.out_mults);
+            g.rb_d = (double*)(base + L.rb_d);
+            g.rb_j = (int*)(base + L.rb_j);
+            g.rank = (int*)(base + L.rank);
+            g.redo = (int*)(base + L.redo);
             g.tmp = (uint32_t*)(base + L.tmp);
             g.tmp_cap = L.tmp_cap;
             g.status = 0;
@@ -955,6 +1146,9 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
         __syncthreads();
         const double q = prm.q_value;
         bool ok = true;
+        if (tid < 8) prof[tid] = 0;
+        const long long t_begin = clock64();
+        PROF_BEGIN();
 #define CHECK_STATUS()        \
     __syncthreads();          \
     if (g.status) ok = false; \
@@ -965,12 +1159,15 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                 for (int o = 0; o < 2; o++) {
                     seed_pass(g, gap, o, q, sh_i, sh_s);
                     __syncthreads();
+                    PROF_END(0);
                     if (g.status) { ok = false; break; }
                     enrich_pass(g, gap, o, o, q, sh_i, sh_s);
                     __syncthreads();
+                    PROF_END(1);
                     if (g.status) { ok = false; break; }
-                    join_pass(g, gap, o, q, &red);
+                    join_pass(g, gap, o, q, &red, sh_s);
                     __syncthreads();
+                    PROF_END(2);
                     if (g.status) { ok = false; break; }
                 }
             }
@@ -982,23 +1179,28 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                     const int om = (e == 1 || e == 3) ? 1 : 0;
                     enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
                     __syncthreads();
+                    PROF_END(1);
                     if (g.status) { ok = false; break; }
                 }
                 if (!ok) break;
                 if (rep == 0) {
                     filter_pass(g, prm, sh_s);
                     CHECK_STATUS();
+                    PROF_END(3);
                 }
             }
             if (!ok) break;
             cluster_clusters(g, prm, &red, sh_s);
+            PROF_END(4);
         } while (false);
 #undef CHECK_STATUS
         __syncthreads();
         if (tid == 0) {
-            task.status = ok ? 0 : 1;
+            task.status = ok ? 0 : (g.status ? g.status : 1);
             task.n_mult = ok ? sh_s[0] : 0;
             task.n_clusters = g.ncl;
+            prof[5] = clock64() - t_begin;
+            for (int k = 0; k < 8; k++) task.prof[k] = prof[k];
         }
         __syncthreads();
     }

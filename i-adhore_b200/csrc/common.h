@@ -44,6 +44,7 @@ struct GhmTask {
     int32_t n_clusters;   // out
     int32_t n_aps;        // out
     int32_t pad1;
+    long long prof[8];    // out: SM cycles per phase (seed, enrich, join, filter, metacluster, total, -, -)
 };
 
 // Base cluster record (BaseCluster.h:316-331).  Anchor points live in the GHM's AP

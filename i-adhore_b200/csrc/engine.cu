@@ -58,6 +58,19 @@ static int fail(int code, const char* fmt, ...)
             return fail(IADH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// IADH_TRACE=1: print the wall time of every stage (synchronising after each; debugging aid)
+#include <chrono>
+static bool g_trace = getenv("IADH_TRACE") != nullptr;
+static double g_t_last = 0;
+static void trace_mark(cudaStream_t st, const char* label)
+{
+    if (!g_trace) return;
+    cudaStreamSynchronize(st);
+    const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (label) fprintf(stderr, "[iadh] %-28s %8.3f ms\n", label, (now - g_t_last) * 1e3);
+    g_t_last = now;
+}
+
 // growable device buffer
 struct DBuf {
     void* p = nullptr;
@@ -308,6 +321,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     }
     const int64_t n_tiles = tile_prefix[n];
     int rc;
+    trace_mark(c->st, "host: tile prefix");
     if ((rc = upload(c->d_tasks, tasks.data(), sizeof(GhmTask) * (size_t)n, c->st))) return rc;
     if ((rc = upload(c->d_tile_prefix, tile_prefix.data(), 8 * (size_t)(n + 1), c->st))) return rc;
     st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 8 * (n + 1);
@@ -318,6 +332,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
                        c->d_tile_cnt.as<uint32_t>(), c->sm_count, c->st);
     launch_tile_scan(c->d_tile_prefix.as<int64_t>(), n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
     CU(cudaEventRecord(c->ev[2], c->st));
+    trace_mark(c->st, "K1 count + tile scan");
     st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
     CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; tasks are read next)
@@ -335,6 +350,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
                       c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
     CU(cudaEventRecord(c->ev[4], c->st));
+    trace_mark(c->st, "K1 fill (+tasks D2H/H2D)");
     st.kernel_launches += n_tiles ? 1 : 0;
     st.n_dots = total_dots;
     return IADH_OK;
@@ -346,6 +362,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     iadh_stats& st = out.st;
     const int n = (int)tasks.size();
     CU(cudaEventRecord(c->ev[0], c->st));
+    trace_mark(c->st, nullptr);
     int64_t total_dots = 0;
     int rc;
     if (n == 0) {
@@ -386,26 +403,50 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act;
         CU(c->d_counter.ensure(16));
         CU(cudaMemsetAsync(c->d_counter.p, 0, 16, c->st));
+        trace_mark(c->st, "host: order/ws + uploads");
         CU(cudaEventRecord(c->ev[5], c->st));
         const int grid = std::max(1, std::min(n_act, c->sm_count * c->ctas_per_sm));
         launch_cluster(c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_counter.as<int>(),
                        c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, grid, c->st);
         CU(cudaEventRecord(c->ev[6], c->st));
+        trace_mark(c->st, "K2 cluster");
         // measure runs over every active GHM (those without multiplicons return at once)
         launch_pack_measure(hl, c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_ws.as<uint8_t>(), c->ds, pf,
                             pool_factor, c->st);
         st.kernel_launches += n_act ? 2 : 0;
+        trace_mark(c->st, "K3 measure");
         CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
+        if (g_trace) {
+            long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int hv = order.empty() ? -1 : order[0];
+            for (int i : order) {
+                for (int k = 0; k < 8; k++) tot[k] += tasks[i].prof[k];
+                if (tasks[i].prof[5] > tasks[hv].prof[5]) hv = i;
+            }
+            fprintf(stderr, "[iadh] K2 cycles (all GHMs): seed %.2fM enrich %.2fM join %.2fM filter %.2fM meta %.2fM total %.2fM\n",
+                    tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
+            if (hv >= 0)
+                fprintf(stderr, "[iadh] slowest GHM %d (D=%u+%u, %d clusters, %d mult): seed %.2fM enrich %.2fM join %.2fM filter %.2fM meta %.2fM total %.2fM\n",
+                        hv, tasks[hv].cnt[0], tasks[hv].cnt[1], tasks[hv].n_clusters, tasks[hv].n_mult, tasks[hv].prof[0] / 1e6,
+                        tasks[hv].prof[1] / 1e6, tasks[hv].prof[2] / 1e6, tasks[hv].prof[3] / 1e6, tasks[hv].prof[4] / 1e6,
+                        tasks[hv].prof[5] / 1e6);
+        }
         bool retry = false;
         for (int i : order)
-            if (tasks[i].status != 0) retry = true;
+            if (tasks[i].status != 0) {
+                if (g_trace && !retry)
+                    fprintf(stderr, "[iadh] retry: GHM %d (D=%u+%u) status=%d clusters=%d pool_factor=%d\n", i, tasks[i].cnt[0],
+                            tasks[i].cnt[1], tasks[i].status, tasks[i].n_clusters, pool_factor);
+                retry = true;
+            }
         if (!retry) break;
         if (attempt >= 3) return fail(IADH_ERR_CAPACITY, "anchor-point pool exhausted even at factor %d", pool_factor);
         pool_factor *= 4;  // rare: rerun the clustering stage with a larger AP pool
     }
 
+    trace_mark(c->st, "tasks D2H");
     // pack: sizes -> offsets -> write
     std::vector<int> sel;
     std::vector<int64_t> out_off;
@@ -424,12 +465,14 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         launch_pack_write(hl, c->d_tasks.as<GhmTask>(), c->d_sel.as<int>(), c->d_out_off.as<int64_t>(), (int)sel.size(),
                           c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
         st.kernel_launches += 1;
+        trace_mark(c->st, "K3 write");
         CU(c->h_out.ensure((size_t)total_bytes));
         CU(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st));
         st.h2d_bytes += 12 * (int64_t)sel.size();
         st.d2h_bytes += total_bytes;
     }
     CU(cudaStreamSynchronize(c->st));
+    trace_mark(c->st, "result D2H");
     if (total_bytes) memcpy(out.packed.data(), c->h_out.p, (size_t)total_bytes);
     for (int i : sel)
         for (int k = 0; k < tasks[i].n_mult; k++) out.ghm_index.push_back(tasks[i].seq);
@@ -442,6 +485,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         }
     }
     out.tasks = tasks;
+    trace_mark(c->st, "host: collect");
     return IADH_OK;
 }
 

@@ -10,7 +10,7 @@
 #include "common.h"
 
 struct WsLayout {
-    size_t key0, key1, alive0, alive1, nxt, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, tmp;
+    size_t key0, key1, alive0, alive1, nxt, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, rb_d, rb_j, rank, redo, tmp;
     size_t total;
     int pool_cap, cl_cap, tmp_cap;
 };
@@ -48,6 +48,10 @@ static inline WsLayout ws_layout(int D, int pool_factor)
     L.changed = take((size_t)L.cl_cap);
     L.mult = take(sizeof(MultRec) * (size_t)L.cl_cap);
     L.out_mults = take(4 * (size_t)L.cl_cap);
+    L.rb_d = take(8 * (size_t)L.cl_cap);
+    L.rb_j = take(4 * (size_t)L.cl_cap);
+    L.rank = take(4 * (size_t)L.cl_cap);
+    L.redo = take(4 * (size_t)L.cl_cap);
     L.tmp = take(4 * (size_t)L.tmp_cap);
     L.total = (o + 255) & ~(size_t)255;
     return L;

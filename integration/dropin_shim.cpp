@@ -1,0 +1,221 @@
+// Drop-in shim: the ONLY translation unit a maintainer adds to i-ADHoRe 3.0 to run its hot path
+// on a B200.  It supplies strong definitions of the two driver members
+//
+//     void DataSet::parallelLevel2ADHoReDyn()                          (levelTwo.cpp:177-292)
+//     void DataSet::parallelProfileSearch(const Profile*, vector<..>&)  (higherLevel.cpp:252-326)
+//
+// that replace the pthread/MPI work distribution by calls into the C-ABI of
+// include/iadhore_b200.h.  Everything else -- Settings, ingest, tandem remapping, the profile
+// loop with its aligners and masks, every output table -- is the unmodified reference, compiled
+// from its own sources.  Results cross the boundary in the reference's own wire format and are
+// rehydrated with its own unpack constructors (Multiplicon.cpp:266-297), exactly as the reference
+// does for multiplicons received from another MPI rank.
+//
+// This file includes the reference's headers; it contains none of the reference's code.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "DataSet.h"
+#include "GeneList.h"
+#include "Gene.h"
+#include "ListElement.h"
+#include "Multiplicon.h"
+#include "Profile.h"
+#include "Settings.h"
+#include "parallel.h"
+
+#include "iadhore_b200.h"
+
+namespace {
+
+struct Bridge {
+    iadh_ctx* ctx = nullptr;
+    std::map<std::string, int> fam_ids, gene_ids;
+    std::vector<std::vector<unsigned char> > masked;  // shadow of ListElement::isMasked per list
+    int rank = 0, n_ranks = 1;
+    double t_l2 = 0, t_hl = 0;
+    long n_hl = 0;
+};
+Bridge B;
+
+int intern(std::map<std::string, int>& m, const std::string& s)
+{
+    std::map<std::string, int>::iterator it = m.find(s);
+    if (it != m.end()) return it->second;
+    const int id = (int)m.size();
+    m[s] = id;
+    return id;
+}
+
+void check(int rc, const char* what)
+{
+    if (rc != IADH_OK) throw std::runtime_error(std::string(what) + ": " + iadh_last_error());
+}
+
+// Flatten the DataSet (after mapGenes + remapTandems + sortGeneLists) and create the device context.
+void ensure_context(const std::vector<GeneList*>& genelists, const Settings& settings)
+{
+    if (B.ctx) return;
+    std::vector<int64_t> off(1, 0);
+    std::vector<int32_t> fam, gid, num;
+    std::vector<uint8_t> flags;
+    B.masked.resize(genelists.size());
+    for (size_t l = 0; l < genelists.size(); l++) {
+        const std::vector<ListElement*>& re = genelists[l]->getRemappedElements();
+        for (size_t i = 0; i < re.size(); i++) {
+            const Gene& g = re[i]->getGene();
+            fam.push_back(intern(B.fam_ids, g.getFamily()));
+            gid.push_back(intern(B.gene_ids, g.getID()));
+            num.push_back(re[i]->getNumID());
+            flags.push_back((re[i]->getOrientation() ? IADH_F_STRAND : 0) | (re[i]->isMasked() ? IADH_F_MASKED : 0));
+        }
+        B.masked[l].assign(re.size(), 0);
+        for (size_t i = 0; i < re.size(); i++) B.masked[l][i] = re[i]->isMasked() ? 1 : 0;
+        off.push_back((int64_t)fam.size());
+    }
+    iadh_dataset_desc d;
+    d.n_lists = (int32_t)genelists.size();
+    d.list_off = off.data();
+    d.fam = fam.data();
+    d.gid = gid.data();
+    d.num_id = num.data();
+    d.flags = flags.data();
+    const char* dev = getenv("IADH_DEVICE");
+    check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
+
+    iadh_params p;
+    int gaps[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    settings.getGapSizes(gaps);
+    p.n_gaps = 0;
+    for (int i = 0; i < 10; i++) {
+        p.gaps[i] = gaps[i] > 0 && p.n_gaps == i ? gaps[i] : 0;
+        if (gaps[i] > 0 && p.n_gaps == i) p.n_gaps++;
+    }
+    p.gap_size = settings.getGapSize();
+    p.cluster_gap = settings.getClusterGap();
+    p.anchor_points = settings.getAnchorPoints();
+    p.mult_hyp = (int)settings.getMultHypCorMethod();
+    p.q_value = settings.getQValue();
+    p.prob_cutoff = settings.getProbCutoff();
+    check(iadh_set_params(B.ctx, &p), "iadh_set_params");
+}
+
+// masks are mutated by the reference between searches (higherLevel.cpp:165-171): forward the delta
+void sync_masks(const std::vector<GeneList*>& genelists)
+{
+    for (size_t l = 0; l < genelists.size(); l++) {
+        const std::vector<ListElement*>& re = genelists[l]->getRemappedElements();
+        std::vector<unsigned char>& sh = B.masked[l];
+        size_t i = 0;
+        while (i < re.size()) {
+            if (re[i]->isMasked() && !sh[i]) {
+                size_t j = i;
+                while (j + 1 < re.size() && re[j + 1]->isMasked() && !sh[j + 1]) j++;
+                check(iadh_mask_range(B.ctx, (int32_t)l, (int32_t)i, (int32_t)j), "iadh_mask_range");
+                for (size_t k = i; k <= j; k++) sh[k] = 1;
+                i = j + 1;
+            } else
+                i++;
+        }
+    }
+}
+
+// the return value of Multiplicon::createHomologs(useFamily, minHomologs) (Multiplicon.cpp:352-382),
+// read from the hasHomolog flags the unpack constructor's createHomologs(useFamily, 0) left behind
+bool enough_homologs(const Multiplicon& m, int minHomologs)
+{
+    const std::vector<GeneList*>& xs = m.getXSegments();
+    for (size_t i = 0; i < xs.size(); i++) {
+        int count = 0;
+        for (unsigned j = 0; j < xs[i]->getSize(); j++) {
+            if (xs[i]->getRemappedElements()[j]->hasHomolog) count++;
+            if (count >= minHomologs) break;
+        }
+        if (count < minHomologs) return false;
+    }
+    const GeneList* ys = m.getYSegment();
+    for (unsigned count = 0, j = 0; j < ys->getSize(); j++) {
+        if (ys->getRemappedElements()[j]->hasHomolog) count++;
+        if ((int)count >= minHomologs) return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+// ---- replaces levelTwo.cpp:177-292 --------------------------------------------------------------
+void DataSet::parallelLevel2ADHoReDyn()
+{
+    if (settings.getClusterType() != Collinear)
+        throw std::runtime_error("the B200 path implements collinear detection only (cluster_type=collinear)");
+    if (!settings.useFamily())
+        throw std::runtime_error("the B200 path implements table_type=family only");
+    ensure_context(genelists, settings);
+    iadh_result* res = NULL;
+    check(iadh_level2_all_pairs(B.ctx, B.rank, B.n_ranks, &res), "iadh_level2_all_pairs");
+    size_t nbytes = 0;
+    const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
+    std::vector<Multiplicon*> mplicons;
+    Multiplicon::unpackL2Multiplicons((const char*)bytes, mplicons, genelists, settings.useFamily());
+    iadh_stats st;
+    iadh_result_stats(res, &st);
+    B.t_l2 += st.total_ms;
+    iadh_free_result(res);
+    addMultiplicons(mplicons);
+    sortByMultipliconSize(multiplicons);
+    if (getenv("IADH_VERBOSE"))
+        fprintf(stderr, "[iadh] level 2: %lld GHMs, %lld dots, %lld multiplicons, device %.2f ms\n", (long long)st.n_ghm,
+                (long long)st.n_dots, (long long)st.n_multiplicons, st.total_ms);
+}
+
+// ---- replaces higherLevel.cpp:252-326 -------------------------------------------------------------
+void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multiplicon*>& target)
+{
+    profileUC = profile;
+    sync_masks(genelists);
+    const std::vector<GeneList*>& segs = profile->getSegments();
+    const int S = (int)segs.size();
+    const int L = S ? (int)segs[0]->getRemappedElements().size() : 0;
+    std::vector<int32_t> fam((size_t)S * L, -1), gid((size_t)S * L, -1), num((size_t)S * L, -1);
+    std::vector<uint8_t> flags((size_t)S * L, IADH_F_GAP);
+    for (int s = 0; s < S; s++) {
+        const std::vector<ListElement*>& e = segs[s]->getRemappedElements();
+        for (int x = 0; x < L; x++) {
+            if (e[x]->isGap()) continue;
+            const Gene& g = e[x]->getGene();
+            const size_t k = (size_t)s * L + x;
+            fam[k] = intern(B.fam_ids, g.getFamily());
+            gid[k] = intern(B.gene_ids, g.getID());
+            num[k] = e[x]->getNumID();
+            flags[k] = e[x]->getOrientation() ? IADH_F_STRAND : 0;
+        }
+    }
+    iadh_profile_desc pd;
+    pd.n_segments = S;
+    pd.length = L;
+    pd.x_object_id = segs[0]->getID();
+    pd.fam = fam.data();
+    pd.gid = gid.data();
+    pd.num_id = num.data();
+    pd.flags = flags.data();
+    iadh_result* res = NULL;
+    check(iadh_profile_search(B.ctx, &pd, B.rank, B.n_ranks, &res), "iadh_profile_search");
+    size_t nbytes = 0;
+    const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
+    std::vector<Multiplicon*> mplicons;
+    Multiplicon::unpackHLMultiplicons((const char*)bytes, mplicons, *profile, genelists, settings.useFamily());
+    iadh_stats st;
+    iadh_result_stats(res, &st);
+    B.t_hl += st.total_ms;
+    B.n_hl++;
+    iadh_free_result(res);
+    // the homolog-count filter of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132)
+    for (size_t i = 0; i < mplicons.size(); i++) {
+        if (enough_homologs(*mplicons[i], settings.getAnchorPoints())) target.push_back(mplicons[i]);
+        else delete mplicons[i];
+    }
+}
