@@ -7,7 +7,8 @@
 // Multiplicon::pack / BaseCluster::pack / AnchorPoint::pack (Multiplicon.cpp:210-240,
 // BaseCluster.cpp:751-797, AnchorPoint.h:103-118), byte for byte.
 // Two launches over the GHMs that produced multiplicons: measure (sizes + in-place
-// normalisation) and write; the host scans the per-GHM sizes in between.
+// normalisation) and write; the host scans the per-GHM sizes in between.  One CTA per GHM,
+// one warp per base cluster, one lane per anchor point.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -16,13 +17,15 @@
 namespace {
 
 constexpr int PT = 128;
+constexpr int PW = PT / 32;
 
 struct PGhm {
     uint32_t* pool;
     ClusterRec* cl;
     MultRec* mult;
     int* out_mults;
-    int* oc;      // output clusters in stream order (reuses the `act` array)
+    int* oc;       // output clusters in stream order (reuses the `act` array)
+    int* scratch;  // per anchor point: false APs before it (reuses the `nxt` array)
     int n_mult, n_oc;
 };
 
@@ -36,6 +39,7 @@ __device__ void pghm_init(PGhm& p, const GhmTask& task, uint8_t* ws, int pool_fa
     p.mult = (MultRec*)(base + L.mult);
     p.out_mults = (int*)(base + L.out_mults);
     p.oc = (int*)(base + L.act);
+    p.scratch = (int*)(base + L.nxt);
     p.n_mult = task.n_mult;
 }
 
@@ -52,6 +56,14 @@ __device__ __forceinline__ void put64(uint8_t* p, double d)
 #pragma unroll
     for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i));
 }
+__device__ __forceinline__ void put_ap(uint8_t* q, int gx, int gy, int x, int y, int real)
+{
+    put32(q, gx);
+    put32(q + 4, gy);
+    put32(q + 8, x);
+    put32(q + 12, y);
+    q[16] = (uint8_t)real;
+}
 
 // does profile element (segment n, column x) pair with dataset element yg?  (Gene.cpp:17-30)
 __device__ __forceinline__ bool seg_match(const ProfileDev& pf, int n, int x, int fy, int gy)
@@ -61,6 +73,13 @@ __device__ __forceinline__ bool seg_match(const ProfileDev& pf, int n, int x, in
     return pf.fam[idx] == fy && pf.gid[idx] != gy;
 }
 
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
 template <bool HL>
 __global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const int* __restrict__ sel, int n_sel,
                                                           uint8_t* ws, DatasetDev ds, ProfileDev pf, int pool_factor)
@@ -68,56 +87,93 @@ __global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const 
     __shared__ PGhm p;
     if (blockIdx.x >= n_sel) return;
     GhmTask& task = tasks[sel[blockIdx.x]];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (task.n_mult == 0 || task.status != 0) return;  // uniform: nothing to serialise
     if (tid == 0) {
         pghm_init(p, task, ws, pool_factor);
-        int n = 0;
+        int n = 0, sbase = 0;
         for (int m = 0; m < p.n_mult; m++)
-            for (int c = p.mult[p.out_mults[m]].head; c >= 0; c = p.cl[c].mnext) p.oc[n++] = c;
+            for (int c = p.mult[p.out_mults[m]].head; c >= 0; c = p.cl[c].mnext) {
+                p.oc[n++] = c;
+                p.cl[c].out_off = sbase;  // temporarily: base of this cluster's scratch segment
+                sbase += p.cl[c].n;
+            }
         p.n_oc = n;
     }
     __syncthreads();
     const int64_t yoff = ds.list_off[task.y_list];
-    for (int i = tid; i < p.n_oc; i += PT) {
+    for (int i = warp; i < p.n_oc; i += PW) {
         ClusterRec& c = p.cl[p.oc[i]];
         uint32_t* ap = p.pool + c.off;
-        int mn = KEY_Y(ap[0]), mx = mn;
-        for (int k = 1; k < c.n; k++) {
+        int n = c.n;
+        int mn = 0x7fffffff, mx = -1;
+        bool sorted = true;
+        for (int k = lane; k < n; k += 32) {
             const int y = KEY_Y(ap[k]);
             mn = min(mn, y);
             mx = max(mx, y);
+            if (HL && k > 0 && ap[k - 1] >= ap[k]) sorted = false;
         }
-        c.min_y = mn;
-        c.max_y = mx;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
         int nfalse = 0;
         if (HL) {
-            // filterDuplicates: unique (x,y), ordered by x then y.  The array is x-sorted, so a
-            // plain sort of the packed keys gives exactly that order.
-            for (int a = 1; a < c.n; a++) {
-                const uint32_t v = ap[a];
-                int b = a - 1;
-                while (b >= 0 && ap[b] > v) {
-                    ap[b + 1] = ap[b];
-                    b--;
+            // filterDuplicates: unique (x,y), ordered by x then y.  The array is x-sorted, so a plain
+            // sort of the packed keys gives exactly that order; usually it already is.
+            if (!__all_sync(0xffffffffu, sorted)) {
+                if (lane == 0) {
+                    for (int a = 1; a < n; a++) {
+                        const uint32_t v = ap[a];
+                        int b = a - 1;
+                        while (b >= 0 && ap[b] > v) {
+                            ap[b + 1] = ap[b];
+                            b--;
+                        }
+                        ap[b + 1] = v;
+                    }
+                    int w = 1;
+                    for (int a = 1; a < n; a++)
+                        if (ap[a] != ap[w - 1]) ap[w++] = ap[a];
+                    c.n = w;
                 }
-                ap[b + 1] = v;
+                __syncwarp();
+                n = c.n;
             }
-            int w = 1;
-            for (int a = 1; a < c.n; a++)
-                if (ap[a] != ap[w - 1]) ap[w++] = ap[a];
-            c.n = w;
-            for (int a = 0; a < c.n; a++) {
-                const int x = KEY_X(ap[a]);
-                const int yg = (int)(yoff + KEY_Y(ap[a]));
-                const int fy = ds.fam[yg], gy = ds.gid[yg];
-                int matches = 0;
-                for (int n = 0; n < pf.S; n++) matches += seg_match(pf, n, x, fy, gy) ? 1 : 0;
-                if (matches > 1) nfalse += matches - 1;
+            // false anchor points: every further matching segment of the profile column; the
+            // scratch array keeps, per AP, the number of false APs of all earlier APs
+            int* scr = p.scratch + c.out_off;
+            int run = 0;
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                int nf = 0;
+                if (k < n) {
+                    const int x = KEY_X(ap[k]);
+                    const int yg = (int)(yoff + KEY_Y(ap[k]));
+                    const int fy = ds.fam[yg], gy = ds.gid[yg];
+                    int matches = 0;
+                    for (int s = 0; s < pf.S; s++) matches += seg_match(pf, s, x, fy, gy) ? 1 : 0;
+                    nf = matches > 1 ? matches - 1 : 0;
+                }
+                int inc = nf;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                if (k < n) scr[k] = run + inc - nf;
+                run += __shfl_sync(0xffffffffu, inc, 31);
             }
+            nfalse = run;
         }
-        c.n_false = nfalse;
-        c.has_false = nfalse > 0;
+        if (lane == 0) {
+            c.min_y = mn;
+            c.max_y = mx;
+            c.n_false = nfalse;
+            c.has_false = nfalse > 0;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -127,6 +183,7 @@ __global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const 
             mr.out_off = off;
             off += 33;
             for (int c = mr.head; c >= 0; c = p.cl[c].mnext) {
+                p.cl[c].cap = p.cl[c].out_off;  // scratch base survives in `cap` (the pool is frozen now)
                 p.cl[c].out_off = off;
                 off += 102 + 17 * (p.cl[c].n + p.cl[c].n_false);
                 naps += p.cl[c].n + p.cl[c].n_false;
@@ -147,7 +204,7 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
     __shared__ PGhm p;
     if (blockIdx.x >= n_sel) return;
     const GhmTask& task = tasks[sel[blockIdx.x]];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         pghm_init(p, task, ws, pool_factor);
         int n = 0;
@@ -184,84 +241,61 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
         put32(q + 25, ey);
         put32(q + 29, mr.count);
     }
-    // clusters + anchor points
-    for (int i = tid; i < p.n_oc; i += PT) {
+    // clusters + anchor points: one warp per cluster, one lane per anchor point
+    for (int i = warp; i < p.n_oc; i += PW) {
         const ClusterRec& c = p.cl[p.oc[i]];
         const uint32_t* ap = p.pool + c.off;
         uint8_t* q = dst + c.out_off;
-        put64(q, c.p);
-        q[8] = c.orient;
-        put64(q + 9, c.a);
-        put64(q + 17, c.has_false ? 0.0 : c.b);  // addAnchorPoint(AnchorPoint&) resets b (BaseCluster.cpp:82-85)
-        put64(q + 25, c.avg_x);
-        put64(q + 33, c.var_x);
-        put64(q + 41, c.mrss);
-        put64(q + 49, c.x_end1);
-        put64(q + 57, c.x_end2);
-        put64(q + 65, c.y_end1);
-        put64(q + 73, c.y_end2);
-        q[81] = c.was_twisted;
-        put32(q + 82, KEY_X(ap[0]));
-        put32(q + 86, KEY_X(ap[c.n - 1]));
-        put32(q + 90, c.min_y);
-        put32(q + 94, c.max_y);
-        put32(q + 98, c.n + c.n_false);
+        if (lane == 0) {
+            put64(q, c.p);
+            q[8] = c.orient;
+            put64(q + 9, c.a);
+            put64(q + 17, c.has_false ? 0.0 : c.b);  // addAnchorPoint(AnchorPoint&) resets b (BaseCluster.cpp:82-85)
+            put64(q + 25, c.avg_x);
+            put64(q + 33, c.var_x);
+            put64(q + 41, c.mrss);
+            put64(q + 49, c.x_end1);
+            put64(q + 57, c.x_end2);
+            put64(q + 65, c.y_end1);
+            put64(q + 73, c.y_end2);
+            q[81] = c.was_twisted;
+            put32(q + 82, KEY_X(ap[0]));
+            put32(q + 86, KEY_X(ap[c.n - 1]));
+            put32(q + 90, c.min_y);
+            put32(q + 94, c.max_y);
+            put32(q + 98, c.n + c.n_false);
+        }
         q += 102;
         if (!HL) {
-            for (int a = 0; a < c.n; a++) {
+            for (int a = lane; a < c.n; a += 32) {
                 const int x = KEY_X(ap[a]), y = KEY_Y(ap[a]);
-                put32(q, ds.num_id[xoff + x]);
-                put32(q + 4, ds.num_id[yoff + y]);
-                put32(q + 8, x);
-                put32(q + 12, y);
-                q[16] = 1;
-                q += 17;
+                put_ap(q + 17 * a, ds.num_id[xoff + x], ds.num_id[yoff + y], x, y, 1);
             }
         } else {
-            // multiset order after the false anchor points were inserted at upper_bound(x): per run
-            // of equal x, the real APs (y ascending) then that run's false APs in discovery order
-            int a = 0;
-            while (a < c.n) {
-                int e = a;
-                const int x = KEY_X(ap[a]);
-                while (e < c.n && KEY_X(ap[e]) == x) e++;
-                for (int r = a; r < e; r++) {
-                    const int y = KEY_Y(ap[r]);
-                    const int yg = (int)(yoff + y);
-                    const int fy = ds.fam[yg], gy = ds.gid[yg];
-                    int gx = -1;
-                    for (int n = 0; n < pf.S; n++)
-                        if (seg_match(pf, n, x, fy, gy)) {
-                            gx = pf.num_id[n * pf.L + x];
-                            break;
-                        }
-                    put32(q, gx);
-                    put32(q + 4, gx < 0 ? -1 : ds.num_id[yg]);
-                    put32(q + 8, x);
-                    put32(q + 12, y);
-                    q[16] = 1;
-                    q += 17;
-                }
-                if (c.has_false)
-                    for (int r = a; r < e; r++) {
-                        const int y = KEY_Y(ap[r]);
-                        const int yg = (int)(yoff + y);
-                        const int fy = ds.fam[yg], gy = ds.gid[yg];
-                        bool seen = false;
-                        for (int n = 0; n < pf.S; n++)
-                            if (seg_match(pf, n, x, fy, gy)) {
-                                if (seen) {
-                                    put32(q, pf.num_id[n * pf.L + x]);
-                                    put32(q + 4, ds.num_id[yg]);
-                                    put32(q + 8, x);
-                                    put32(q + 12, y);
-                                    q[16] = 0;
-                                    q += 17;
-                                }
-                                seen = true;
-                            }
+            // multiset order after the false anchor points were inserted at upper_bound(x): per run of
+            // equal x, the real APs (y ascending) then that run's false APs in discovery order.
+            //   real AP a   -> a + F(run start)            F(k) = false APs of all APs before k
+            //   its falses  -> run end + F(a) + 0,1,...
+            const int* scr = p.scratch + c.cap;
+            for (int a = lane; a < c.n; a += 32) {
+                const int x = KEY_X(ap[a]), y = KEY_Y(ap[a]);
+                int rs = a, re = a + 1;
+                while (rs > 0 && KEY_X(ap[rs - 1]) == x) rs--;
+                while (re < c.n && KEY_X(ap[re]) == x) re++;
+                const int yg = (int)(yoff + y);
+                const int fy = ds.fam[yg], gy = ds.gid[yg];
+                const int gyn = ds.num_id[yg];
+                int pos_false = re + (c.has_false ? scr[a] : 0);
+                const int pos_real = a + (c.has_false ? scr[rs] : 0);
+                bool seen = false;
+                for (int s = 0; s < pf.S; s++)
+                    if (seg_match(pf, s, x, fy, gy)) {
+                        const int gx = pf.num_id[s * pf.L + x];
+                        if (!seen) put_ap(q + 17 * pos_real, gx, gyn, x, y, 1);
+                        else put_ap(q + 17 * (pos_false++), gx, gyn, x, y, 0);
+                        seen = true;
                     }
-                a = e;
+                if (!seen) put_ap(q + 17 * pos_real, -1, -1, x, y, 1);  // (the reference exits here)
             }
         }
     }

@@ -14,6 +14,7 @@
 // This file includes the reference's headers; it contains none of the reference's code.
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -36,11 +37,31 @@ struct Bridge {
     iadh_ctx* ctx = nullptr;
     std::map<std::string, int> fam_ids, gene_ids;
     std::vector<std::vector<unsigned char> > masked;  // shadow of ListElement::isMasked per list
+    std::vector<int32_t> fam_of, gid_of;               // by ListElement numID (profile elements are copies)
     int rank = 0, n_ranks = 1;
     double t_l2 = 0, t_hl = 0;
     long n_hl = 0;
+    // wall-clock split of the profile searches (IADH_VERBOSE=1 prints it at exit)
+    double w_mask = 0, w_desc = 0, w_call = 0, w_unpack = 0;
+    long long n_ghm = 0, n_found = 0;
 };
 Bridge B;
+
+double wall()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+void report()
+{
+    if (!getenv("IADH_VERBOSE")) return;
+    fprintf(stderr,
+            "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons kept; wall: masks %.3fs, descriptor %.3fs, "
+            "device call %.3fs (device time %.3fs), unpack+filter %.3fs\n",
+            B.n_hl, B.n_ghm, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
+}
 
 int intern(std::map<std::string, int>& m, const std::string& s)
 {
@@ -65,6 +86,16 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     std::vector<uint8_t> flags;
     B.masked.resize(genelists.size());
     for (size_t l = 0; l < genelists.size(); l++) {
+        const std::vector<ListElement*>& all = genelists[l]->getElements();
+        for (size_t i = 0; i < all.size(); i++) {
+            const int id = all[i]->getNumID();
+            if (id >= (int)B.fam_of.size()) {
+                B.fam_of.resize(id + 1, -1);
+                B.gid_of.resize(id + 1, -1);
+            }
+            B.fam_of[id] = intern(B.fam_ids, all[i]->getGene().getFamily());
+            B.gid_of[id] = intern(B.gene_ids, all[i]->getGene().getID());
+        }
         const std::vector<ListElement*>& re = genelists[l]->getRemappedElements();
         for (size_t i = 0; i < re.size(); i++) {
             const Gene& g = re[i]->getGene();
@@ -86,6 +117,7 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     d.flags = flags.data();
     const char* dev = getenv("IADH_DEVICE");
     check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
+    atexit(report);
 
     iadh_params p;
     int gaps[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -104,10 +136,13 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     check(iadh_set_params(B.ctx, &p), "iadh_set_params");
 }
 
-// masks are mutated by the reference between searches (higherLevel.cpp:165-171): forward the delta
-void sync_masks(const std::vector<GeneList*>& genelists)
+// masks are mutated by the reference between searches (higherLevel.cpp:165-171), only on the x- and
+// y-list of the multiplicon under evaluation: forward the delta of those two lists
+void sync_masks(const std::vector<GeneList*>& genelists, int lx, int ly)
 {
-    for (size_t l = 0; l < genelists.size(); l++) {
+    for (int pass = 0; pass < 2; pass++) {
+        const int l = pass ? ly : lx;
+        if (l < 0 || l >= (int)genelists.size() || (pass && ly == lx)) continue;
         const std::vector<ListElement*>& re = genelists[l]->getRemappedElements();
         std::vector<unsigned char>& sh = B.masked[l];
         size_t i = 0;
@@ -176,7 +211,9 @@ void DataSet::parallelLevel2ADHoReDyn()
 void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multiplicon*>& target)
 {
     profileUC = profile;
-    sync_masks(genelists);
+    const double w0 = wall();
+    sync_masks(genelists, profile->getMultiplicon().getXObjectID(), profile->getMultiplicon().getYObjectID());
+    const double w1 = wall();
     const std::vector<GeneList*>& segs = profile->getSegments();
     const int S = (int)segs.size();
     const int L = S ? (int)segs[0]->getRemappedElements().size() : 0;
@@ -188,9 +225,15 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
             if (e[x]->isGap()) continue;
             const Gene& g = e[x]->getGene();
             const size_t k = (size_t)s * L + x;
-            fam[k] = intern(B.fam_ids, g.getFamily());
-            gid[k] = intern(B.gene_ids, g.getID());
-            num[k] = e[x]->getNumID();
+            const int id = e[x]->getNumID();
+            if (id >= 0 && id < (int)B.fam_of.size() && B.fam_of[id] >= 0) {
+                fam[k] = B.fam_of[id];
+                gid[k] = B.gid_of[id];
+            } else {
+                fam[k] = intern(B.fam_ids, g.getFamily());
+                gid[k] = intern(B.gene_ids, g.getID());
+            }
+            num[k] = id;
             flags[k] = e[x]->getOrientation() ? IADH_F_STRAND : 0;
         }
     }
@@ -203,7 +246,9 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     pd.num_id = num.data();
     pd.flags = flags.data();
     iadh_result* res = NULL;
+    const double w2 = wall();
     check(iadh_profile_search(B.ctx, &pd, B.rank, B.n_ranks, &res), "iadh_profile_search");
+    const double w3 = wall();
     size_t nbytes = 0;
     const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
     std::vector<Multiplicon*> mplicons;
@@ -218,4 +263,10 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
         if (enough_homologs(*mplicons[i], settings.getAnchorPoints())) target.push_back(mplicons[i]);
         else delete mplicons[i];
     }
+    B.n_ghm += st.n_ghm;
+    B.n_found += (long long)target.size();
+    B.w_mask += w1 - w0;
+    B.w_desc += w2 - w1;
+    B.w_call += w3 - w2;
+    B.w_unpack += wall() - w3;
 }

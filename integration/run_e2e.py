@@ -49,7 +49,7 @@ def run(binary, ini, env=None):
     l2 = re.search(r"Level 2 multiplicon detection\.\.\.\s*done\. \(time: ([\d.e+-]+)s\)", p.stdout)
     hl = re.search(r"Profile detection\.\.\.\s*done\. \(time: ([\d.e+-]+)s\)", p.stdout)
     return dict(wall_s=wall, l2_s=float(l2.group(1)) if l2 else None, hl_s=float(hl.group(1)) if hl else None,
-                stderr=p.stderr[-400:])
+                stderr="\n".join(l for l in p.stderr.splitlines() if "[iadh]" in l))
 
 
 def main():
