@@ -16,6 +16,7 @@
 //   join   : all cluster pairs evaluated in parallel, lexicographic-first minimum reduced.
 // State lives in a per-GHM workspace in HBM (L2-resident for all but the densest GHMs).
 #include <cuda_runtime.h>
+#include <cstdio>
 
 #include "cluster_math.cuh"
 #include "common.h"
@@ -23,8 +24,7 @@
 
 namespace {
 
-constexpr int NT = 256;
-constexpr int NW = NT / 32;
+constexpr int MAXW = 16;  // warps per CTA, upper bound (block size is a template parameter)
 
 struct Ghm {
     uint32_t* key[2];
@@ -48,9 +48,11 @@ struct Ghm {
     int* rb_j;
     int* rank;
     int* redo;
+    double* dscr;   // 2 doubles per anchor point: terms of the ordered mrss / var_x sums
     uint32_t* tmp;
     int tmp_cap;
     int status;
+    int coop[4];
     // task constants
     uint32_t cnt[2];
     double area;
@@ -58,19 +60,24 @@ struct Ghm {
 };
 
 struct Red {
-    double d[NW];
-    long long k[NW];
-    int i[NW];
+    double d[MAXW];
+    long long k[MAXW];
+    int i[MAXW];
 };
+
+// Everything below is parameterised on the CTA size NT: small GHMs run on 32- or 128-thread CTAs
+// (more GHMs in flight per SM, barriers almost free), heavy ones on 256 threads.
+template <int NT>
+struct KT {
+static constexpr int NW = NT / 32;
 
 // ---- block reductions -------------------------------------------------------------------
 
 // minimum int over the block (INT_MAX = none); two barriers
-__device__ int block_min_int(int v, int* sh)
+static __device__ int block_min_int(int v, int* sh)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    v = __reduce_min_sync(0xffffffffu, v);  // REDUX: one instruction, signed min
     if (lane == 0) sh[w] = v;
     __syncthreads();
     int r = sh[0];
@@ -81,7 +88,7 @@ __device__ int block_min_int(int v, int* sh)
 }
 
 // lexicographic minimum of (dist, idx); idx < 0 = none
-__device__ void block_min_pair(double& d, long long& k, Red* sh)
+static __device__ void block_min_pair(double& d, long long& k, Red* sh)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -114,15 +121,13 @@ __device__ void block_min_pair(double& d, long long& k, Red* sh)
 
 // ---- AP pool ------------------------------------------------------------------------------
 
-__device__ __forceinline__ int next_cap(int n);
-
 // Anchor-point pool: bump allocation of self-describing blocks [owner cluster, capacity,
 // payload...].  Growth of a cluster abandons its old block; when the pool runs out, the live
 // blocks (those a live cluster still points at) are slid down in allocation order and trimmed
 // to the capacity class of their current size.  Live data is at most ~4.7 D entries, so with
 // pool_factor >= 8 an allocation can only fail after a collection if the host under-sized the
 // pool on purpose (then the GHM reports status 1 and the engine reruns it with a larger pool).
-__device__ void pool_gc(Ghm& g)
+static __device__ void pool_gc(Ghm& g)
 {
     int r = 0, w = 0;
     while (r < g.pool_used) {
@@ -151,7 +156,7 @@ __device__ void pool_gc(Ghm& g)
 }
 
 // single-thread contexts only (the rest of the CTA waits at a barrier)
-__device__ int pool_alloc(Ghm& g, int n, int owner)
+static __device__ int pool_alloc(Ghm& g, int n, int owner)
 {
     if (g.pool_used + n + 2 > g.pool_cap) {
         pool_gc(g);
@@ -167,7 +172,7 @@ __device__ int pool_alloc(Ghm& g, int n, int owner)
     return off + 2;
 }
 
-__device__ __forceinline__ int next_cap(int n)
+static __device__ __forceinline__ int next_cap(int n)
 {
     int c = 8;
     while (c < n) c <<= 1;
@@ -175,7 +180,7 @@ __device__ __forceinline__ int next_cap(int n)
 }
 
 // multiset<AnchorPoint>::insert (BaseCluster.cpp:58-61): after the last AP with x <= X
-__device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
+static __device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
 {
     if (c.n == c.cap) {
         const int ncap = c.cap * 2;
@@ -210,7 +215,7 @@ __device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
 // BaseCluster::mergeWith (BaseCluster.cpp:338-351): B's APs are inserted one by one, i.e. a
 // stable merge with A's APs first on equal x; B's backbone points are dropped where A already
 // has a backbone point with the same x (set<AnchorPoint> on x).
-__device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B)
+static __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B)
 {
     const int n = A.n + B.n;
     if (n > A.cap) {
@@ -252,9 +257,206 @@ __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B)
     return true;
 }
 
+// ---- cooperative (whole-CTA) cluster updates ----------------------------------------------------
+// The reference recomputes a cluster's statistics from scratch after every change, with mrss and
+// var_x accumulated sequentially in multiset order.  That order is kept: all threads compute the
+// per-AP terms, one thread adds them up in order (a pure dependent-add chain, no loads or
+// multiplies on it).  Short clusters stay on one thread.
+static constexpr int COOP_MIN = 48;
+#define COOP_T(k) (g.coop[k])
+
+static __device__ void stats_coop(Ghm& g, ClusterRec& c)
+{
+    const int tid = threadIdx.x;
+    const int n = c.n;
+    if (n < COOP_T(0)) {
+        if (tid == 0) cm::update_stats(c, g.pool);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) cm::regress(c);
+    __syncthreads();
+    {
+        const double a = c.a, b = c.b, avg_x = c.avg_x;
+        const uint32_t* ap = g.pool + c.off;
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t k = ap[i];
+            const int x = KEY_X(k), y = KEY_Y(k);
+            const double y_est = b * x + a;
+            g.dscr[2 * i] = (y - y_est) * (y - y_est);
+            g.dscr[2 * i + 1] = (x - avg_x) * (x - avg_x);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mrss = 0.0, var_x = 0.0;
+        const double2* t = reinterpret_cast<const double2*>(g.dscr);
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = t[i + u];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                mrss += v[u].x;
+                var_x += v[u].y;
+            }
+        }
+        for (; i < n; i++) {
+            mrss += t[i].x;
+            var_x += t[i].y;
+        }
+        cm::finish_stats(c, mrss, var_x, g.pool);
+    }
+    __syncthreads();
+}
+
+static __device__ __forceinline__ int lower_bound_x(const uint32_t* a, int n, int x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEY_X(a[mid]) < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+static __device__ __forceinline__ int upper_bound_x(const uint32_t* a, int n, int x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEY_X(a[mid]) <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// BaseCluster::mergeWith by the whole CTA: every element finds its final position by a binary
+// search into the other cluster (A's APs first on equal x), staged, then copied.
+static __device__ bool merge_coop(Ghm& g, int idA, int idB)
+{
+    const int tid = threadIdx.x;
+    ClusterRec& A = g.cl[idA];
+    const ClusterRec& B = g.cl[idB];
+    const int nA = A.n, nB = B.n, n = nA + nB;
+    if (n < COOP_T(1)) {
+        __syncthreads();
+        if (tid == 0) merge_clusters(g, A, B);
+        __syncthreads();
+        return g.status == 0;
+    }
+    uint32_t* skey = g.tmp;
+    uint8_t* sflag = reinterpret_cast<uint8_t*>(g.tmp + g.tmp_cap);
+    {
+        const uint32_t* pa = g.pool + A.off;
+        const uint32_t* pb = g.pool + B.off;
+        const uint8_t* fa = g.pflag + A.off;
+        const uint8_t* fb = g.pflag + B.off;
+        for (int i = tid; i < nA; i += NT) {
+            const int pos = i + lower_bound_x(pb, nB, KEY_X(pa[i]));
+            skey[pos] = pa[i];
+            sflag[pos] = fa[i];
+        }
+        for (int j = tid; j < nB; j += NT) {
+            const int x = KEY_X(pb[j]);
+            const int ub = upper_bound_x(pa, nA, x);
+            uint8_t fl = fb[j];
+            if (fl)
+                for (int k = ub - 1; k >= 0 && KEY_X(pa[k]) == x; k--)
+                    if (fa[k]) {
+                        fl = 0;
+                        break;
+                    }
+            skey[j + ub] = pb[j];
+            sflag[j + ub] = fl;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool ok = true;
+        if (n > A.cap) {
+            const int ncap = next_cap(n);
+            const int noff = pool_alloc(g, ncap, idA);  // may compact the pool: A/B blocks can move
+            if (noff >= 0) {
+                A.off = noff;
+                A.cap = ncap;
+            } else
+                ok = false;
+        }
+        if (ok) {
+            A.n = n;
+            A.sx += B.sx; A.sy += B.sy; A.sxy += B.sxy; A.sxx += B.sxx; A.syy += B.syy;
+        }
+    }
+    __syncthreads();
+    if (g.status) return false;
+    for (int i = tid; i < n; i += NT) {
+        g.pool[A.off + i] = skey[i];
+        g.pflag[A.off + i] = sflag[i];
+    }
+    __syncthreads();
+    stats_coop(g, A);
+    return true;
+}
+
+// BaseCluster::addAnchorPoint(x, y) + updateStatistics by the whole CTA
+static __device__ bool insert_coop(Ghm& g, ClusterRec& c, uint32_t key)
+{
+    const int tid = threadIdx.x;
+    const int n = c.n;
+    if (n < COOP_T(2)) {
+        if (tid == 0 && insert_ap(g, c, key)) cm::update_stats(c, g.pool);
+        __syncthreads();
+        return g.status == 0;
+    }
+    if (tid == 0 && n == c.cap) {
+        const int ncap = c.cap * 2;
+        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl));
+        if (noff >= 0) {
+            for (int i = 0; i < n; i++) {
+                g.pool[noff + i] = g.pool[c.off + i];
+                g.pflag[noff + i] = g.pflag[c.off + i];
+            }
+            c.off = noff;
+            c.cap = ncap;
+        }
+    }
+    __syncthreads();
+    if (g.status) return false;
+    uint32_t* ap = g.pool + c.off;
+    uint8_t* fl = g.pflag + c.off;
+    const int pos = upper_bound_x(ap, n, KEY_X(key));
+    for (int base = n - 1; base >= pos; base -= NT) {
+        const int i = base - tid;
+        uint32_t v = 0;
+        uint8_t f = 0;
+        if (i >= pos) {
+            v = ap[i];
+            f = fl[i];
+        }
+        __syncthreads();
+        if (i >= pos) {
+            ap[i + 1] = v;
+            fl[i + 1] = f;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ap[pos] = key;
+        fl[pos] = 0;
+        c.n = n + 1;
+        const long long X = KEY_X(key), Y = KEY_Y(key);
+        c.sx += X; c.sy += Y; c.sxy += X * Y; c.sxx += X * X; c.syy += Y * Y;
+    }
+    __syncthreads();
+    stats_coop(g, c);
+    return true;
+}
+
 // ---- seed ---------------------------------------------------------------------------------
 
-__device__ __forceinline__ int lower_bound_key(const uint32_t* a, int lo, int hi, uint32_t v)
+static __device__ __forceinline__ int lower_bound_key(const uint32_t* a, int lo, int hi, uint32_t v)
 {
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -266,7 +468,7 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* a, int lo, int hi
 
 // GHM::seedBaseCluster inner search (GHM.cpp:248-276): closest alive dot in the window, strict
 // '<' so the first in (x,y) order wins ties; only dpd <= gap qualifies.
-__device__ int window_next(const uint32_t* key, const uint8_t* alive, int n, int i,
+static __device__ int window_next(const uint32_t* key, const uint8_t* alive, int n, int i,
                            int gap, int orient)
 {
     const uint32_t k = key[i];
@@ -292,7 +494,7 @@ __device__ int window_next(const uint32_t* key, const uint8_t* alive, int n, int
 }
 
 // GHM::seedBaseClusters (GHM.cpp:287-324)
-__device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s)
+static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s)
 {
     const int tid = threadIdx.x;
     const uint32_t* key = g.key[o];
@@ -341,7 +543,6 @@ __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s
                     w++;
                 }
                 cm::recompute_sums(c, g.pool);
-                cm::update_stats(c, g.pool);
                 g.bc[o][g.nbc[o]++] = g.ncl;
                 g.ncl++;
                 sh_s[0] = lastj;
@@ -352,6 +553,7 @@ __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s
         }
         __syncthreads();
         if (g.status) return;
+        stats_coop(g, g.cl[g.ncl - 1]);
         {
             // repair successor pointers that point into the erased chain
             const int lastj = sh_s[0];
@@ -368,14 +570,14 @@ __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s
 // ---- enrich -------------------------------------------------------------------------------
 
 // one (dot, cluster) test of GHM::enrichClusters (GHM.cpp:352-365)
-__device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
+static __device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
 {
     dist = cm::dist_to_point(c, x, y);
     if (dist >= limit) return false;
     return cm::r2_with_point(c, x, y) >= q && cm::in_interval(c, x, y);
 }
 
-__device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i, int* sh_s)
+static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i, int* sh_s)
 {
     const int tid = threadIdx.x;
     const uint32_t* key = g.key[om];
@@ -412,22 +614,26 @@ __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i
                 const int first = block_min_int((bk >= 0 && tid >= from) ? tid : 0x7fffffff, sh_i);
                 if (first == 0x7fffffff) break;
                 if (tid == first) {
-                    ClusterRec& c = g.cl[act[bk]];
-                    if (insert_ap(g, c, key[i])) {
-                        cm::update_stats(c, g.pool);
-                        if (!g.changed[bk]) {
-                            g.changed[bk] = 1;
-                            act_next[sh_s[1]++] = act[bk];
-                        }
-                        alive[i] = 0;
-                    }
                     sh_s[0] = bk;
+                    sh_s[3] = i;
                     bk = -1;
                     mine = false;
                 }
                 __syncthreads();
-                if (g.status) return;
                 const int kc = sh_s[0];
+                {
+                    const int di = sh_s[3];
+                    const bool ok = insert_coop(g, g.cl[act[kc]], key[di]);
+                    if (tid == 0 && ok) {
+                        if (!g.changed[kc]) {
+                            g.changed[kc] = 1;
+                            act_next[sh_s[1]++] = act[kc];
+                        }
+                        alive[di] = 0;
+                    }
+                    __syncthreads();
+                }
+                if (g.status) return;
                 if (mine && tid > first) {
                     if (bk == kc) {
                         bd = gap + 1;
@@ -466,7 +672,7 @@ __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i
 
 // GHM::getClosestClusters (GHM.cpp:406-444): first (i,j) in lexicographic order attaining the
 // minimum distance < gap+1 among pairs passing the interval and r^2 tests.
-__device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double q, int& pi, int& pj, Red* red)
+static __device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double q, int& pi, int& pj, Red* red)
 {
     const int ni = g.nbc[oi], nj = g.nbc[oj];
     const bool same = (oi == oj);
@@ -504,7 +710,7 @@ __device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double q, int&
 // or equally close and earlier in vector order (the reference scans pairs lexicographically
 // with a strict '<').  Rejections by x / y extent are exact: every candidate distance of
 // distanceToCluster is a dpd between a point of A's hull and one of B's, and dpd >= |dx|, |dy|.
-__device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q,
+static __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q,
                                             double bd, int brank, int rankJ, double& dout)
 {
     const double xgap = cm::maxd(cI.x_end1 - cJ.x_end2, cJ.x_end1 - cI.x_end2);
@@ -524,7 +730,7 @@ __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, 
 }
 
 // best partner of the cluster at position `pos` among the later positions (one warp)
-__device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
+static __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
 {
     const int lane = threadIdx.x & 31;
     const int n = g.nbc[o];
@@ -564,8 +770,10 @@ __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
 // (O(n^3)); here every cluster caches its best later partner and only the rows touched by a
 // merge are recomputed.  Vector order is kept as a static rank per pass: erasing a merged
 // cluster never changes the relative order of the others.
-__device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
+static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s, long long* pf2)
 {
+#define JP(k) do { const long long t_ = clock64(); if (threadIdx.x == 0) pf2[k] += t_ - jt; jt = t_; } while (0)
+    long long jt = clock64();
     const int tid = threadIdx.x, warp = tid >> 5;
     int n = g.nbc[o];
     if (n < 2) return;
@@ -577,6 +785,7 @@ __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
         g.rb_j[g.bc[o][n - 1]] = -1;
     }
     __syncthreads();
+    JP(0);
     while (true) {
         // global minimum over the rows: (distance, rank of i, rank of j)
         double bd = gap + 1;
@@ -593,7 +802,9 @@ __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
             }
         }
         block_min_pair(bd, bk, red);
+        JP(1);
         if (bk < 0) break;
+        if (threadIdx.x == 0) pf2[7]++;
         // ranks -> current positions (ranks are sorted along the vector: binary search)
         const int rankA = (int)(bk >> 32), rankB = (int)(bk & 0xffffffff);
         int lo = 0, hi = n;
@@ -612,13 +823,14 @@ __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
         const int pB = lo;
         const int idA = g.bc[o][pA], idB = g.bc[o][pB];
         __syncthreads();
+        JP(2);
+        if (!merge_coop(g, idA, idB)) return;
+        JP(3);
         if (tid == 0) {
-            merge_clusters(g, g.cl[idA], g.cl[idB]);
             g.cl[idB].dead = 1;
             sh_s[2] = 0;  // rows to recompute
         }
         __syncthreads();
-        if (g.status) return;
         // erase position pB from the vector (order preserved)
         {
             int v = 0;
@@ -633,6 +845,7 @@ __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
             if (tid == 0) g.nbc[o] = n;
             __syncthreads();
         }
+        JP(4);
         // refresh the cache: rows that pointed at A or B (and A's own row) are recomputed in full,
         // earlier rows only re-test their pair with the merged cluster
         const ClusterRec& cA = g.cl[idA];
@@ -656,16 +869,19 @@ __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s)
             }
         }
         __syncthreads();
+        JP(5);
         const int nredo = sh_s[2];
         for (int r = warp; r < nredo; r += NW) join_row(g, o, g.redo[r], gap, q);
         __syncthreads();
+        JP(6);
     }
+#undef JP
 }
 
 // ---- probability filter ---------------------------------------------------------------------
 
 // BaseCluster::calculateProbability (BaseCluster.cpp:548-590)
-__device__ void calc_probability(Ghm& g, ClusterRec& c)
+static __device__ void calc_probability(Ghm& g, ClusterRec& c)
 {
     const double density = (double)g.cnt[c.orient] / g.area;
     double probability = 1.0;
@@ -708,7 +924,7 @@ struct PLess {
     const ClusterRec* cl;
     __device__ bool operator()(int l, int r) const { return cl[l].p < cl[r].p; }
 };
-__device__ void adjust_heap(int* first, int hole, int len, int value, PLess comp)
+static __device__ void adjust_heap(int* first, int hole, int len, int value, PLess comp)
 {
     const int top = hole;
     int child = hole;
@@ -731,7 +947,7 @@ __device__ void adjust_heap(int* first, int hole, int len, int value, PLess comp
     }
     first[hole] = value;
 }
-__device__ void heap_sort(int* first, int len, PLess comp)
+static __device__ void heap_sort(int* first, int len, PLess comp)
 {
     if (len >= 2) {
         int parent = (len - 2) / 2;
@@ -750,7 +966,7 @@ __device__ void heap_sort(int* first, int len, PLess comp)
         adjust_heap(first, 0, last, value, comp);
     }
 }
-__device__ void unguarded_linear_insert(int* last, PLess comp)
+static __device__ void unguarded_linear_insert(int* last, PLess comp)
 {
     const int val = *last;
     int* next = last - 1;
@@ -761,7 +977,7 @@ __device__ void unguarded_linear_insert(int* last, PLess comp)
     }
     *last = val;
 }
-__device__ void insertion_sort(int* first, int* last, PLess comp)
+static __device__ void insertion_sort(int* first, int* last, PLess comp)
 {
     if (first == last) return;
     for (int* i = first + 1; i != last; ++i) {
@@ -773,7 +989,7 @@ __device__ void insertion_sort(int* first, int* last, PLess comp)
             unguarded_linear_insert(i, comp);
     }
 }
-__device__ void std_sort(int* first, int n, PLess comp)
+static __device__ void std_sort(int* first, int n, PLess comp)
 {
     if (n <= 0) return;
     // __introsort_loop, recursion on the right part unrolled with an explicit stack
@@ -835,7 +1051,7 @@ __device__ void std_sort(int* first, int n, PLess comp)
 }
 
 // bitonic sort of g.tmp[0..m) (m power of two) by the whole CTA
-__device__ void block_bitonic(uint32_t* a, int m)
+static __device__ void block_bitonic(uint32_t* a, int m)
 {
     for (int k = 2; k <= m; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -855,7 +1071,7 @@ __device__ void block_bitonic(uint32_t* a, int m)
 }
 
 // GHM::filterBaseClusters / BF / FDR (GHM.cpp:446-540)
-__device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
+static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
 {
     const int tid = threadIdx.x;
     for (int o = 0; o < 2; o++)
@@ -951,11 +1167,20 @@ __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
 
 // ---- metaclustering ---------------------------------------------------------------------------
 
-// BaseCluster::twistCluster (BaseCluster.cpp:700-719); one thread per cluster
-__device__ void twist_all(Ghm& g, int o)
+// BaseCluster::twistCluster (BaseCluster.cpp:700-719): y -> max_y + min_y - y, statistics
+// recomputed.  Short clusters: one thread each; long ones: the whole CTA per cluster (the mirrored
+// integer sums follow in closed form: sy' = nM - sy, sxy' = M sx - sxy, syy' = nM^2 - 2M sy + syy).
+static __device__ void twist_all(Ghm& g, int o, int* sh_i, int* sh_s)
 {
-    for (int i = threadIdx.x; i < g.nbc[o]; i += NT) {
+    const int tid = threadIdx.x;
+    if (tid == 0) sh_s[4] = 0;
+    __syncthreads();
+    for (int i = tid; i < g.nbc[o]; i += NT) {
         ClusterRec& c = g.cl[g.bc[o][i]];
+        if (c.n >= COOP_T(3)) {
+            g.redo[atomicAdd(&sh_s[4], 1)] = g.bc[o][i];
+            continue;
+        }
         int mx = KEY_Y(g.pool[c.off]), mn = mx;
         for (int k = 1; k < c.n; k++) {
             const int y = KEY_Y(g.pool[c.off + k]);
@@ -970,10 +1195,38 @@ __device__ void twist_all(Ghm& g, int o)
         cm::update_stats(c, g.pool);
     }
     __syncthreads();
+    const int nbig = sh_s[4];
+    for (int r = 0; r < nbig; r++) {
+        ClusterRec& c = g.cl[g.redo[r]];
+        uint32_t* ap = g.pool + c.off;
+        const int n = c.n;
+        int mn = 0x7fffffff, mx = -1;
+        for (int k = tid; k < n; k += NT) {
+            const int y = KEY_Y(ap[k]);
+            mn = min(mn, y);
+            mx = max(mx, y);
+        }
+        mn = block_min_int(mn, sh_i);
+        mx = -block_min_int(-mx, sh_i);
+        const int M = mn + mx;  // max_y + min_y
+        for (int k = tid; k < n; k += NT) {
+            const uint32_t key = ap[k];
+            ap[k] = MAKE_KEY(KEY_X(key), M - KEY_Y(key));
+        }
+        if (tid == 0) {
+            const long long Ml = M, nl = n;
+            const long long sy = c.sy, sxy = c.sxy, syy = c.syy;
+            c.sy = nl * Ml - sy;
+            c.sxy = Ml * c.sx - sxy;
+            c.syy = nl * Ml * Ml - 2 * Ml * sy + syy;
+        }
+        __syncthreads();
+        stats_coop(g, c);
+    }
 }
 
 // GHM::clusterClusters (GHM.cpp:542-625)
-__device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh_s)
+static __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh_i, int* sh_s)
 {
     const int tid = threadIdx.x;
     bool join_flag = true;
@@ -983,10 +1236,10 @@ __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh
             const int ox = (k < 2) ? 1 : 0;
             const int oy = (k % 2 == 0) ? 1 : 0;
             const bool twisted = (ox != oy);
-            if (twisted) twist_all(g, oy);
+            if (twisted) twist_all(g, oy, sh_i, sh_s);
             int pi = -1, pj = -1;
             const bool found = closest_clusters(g, prm.cluster_gap, ox, oy, prm.q_value, pi, pj, red);
-            if (twisted) twist_all(g, oy);
+            if (twisted) twist_all(g, oy, sh_i, sh_s);
             if (tid == 0) {
                 sh_s[0] = 0;
                 if (found) {
@@ -1064,19 +1317,25 @@ __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh
     __syncthreads();
 }
 
+};  // struct KT
+
 // ---- kernel -----------------------------------------------------------------------------------
 
+template <int NT>
 __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* __restrict__ order,
                                                      int n_tasks, int* next_task,
                                                      const uint32_t* __restrict__ dots, uint8_t* ws,
                                                      DevParams prm, int pool_factor)
 {
+    using K = KT<NT>;
+    constexpr int NW = K::NW;
     __shared__ Ghm g;
     __shared__ Red red;
     __shared__ int sh_i[NW];
-    __shared__ int sh_s[4];
+    __shared__ int sh_s[8];
     __shared__ int sh_task;
     __shared__ long long prof[8];
+    __shared__ long long prof2[8];
     const int tid = threadIdx.x;
 #define PROF_BEGIN() long long pt_ = clock64()
 #define PROF_END(k)                              \
@@ -1120,9 +1379,11 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.rb_j = (int*)(base + L.rb_j);
             g.rank = (int*)(base + L.rank);
             g.redo = (int*)(base + L.redo);
+            g.dscr = (double*)(base + L.dscr);
             g.tmp = (uint32_t*)(base + L.tmp);
             g.tmp_cap = L.tmp_cap;
             g.status = 0;
+            for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
             g.nk[0] = D0;
             g.nk[1] = D1;
             g.cnt[0] = task.cnt[0];
@@ -1146,7 +1407,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
         __syncthreads();
         const double q = prm.q_value;
         bool ok = true;
-        if (tid < 8) prof[tid] = 0;
+        if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
         const long long t_begin = clock64();
         PROF_BEGIN();
 #define CHECK_STATUS()        \
@@ -1157,15 +1418,15 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             for (int gi = 0; gi < prm.n_gaps && gi < 10 && prm.gaps[gi] > 0 && ok; gi++) {
                 const int gap = prm.gaps[gi];
                 for (int o = 0; o < 2; o++) {
-                    seed_pass(g, gap, o, q, sh_i, sh_s);
+                    K::seed_pass(g, gap, o, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(0);
                     if (g.status) { ok = false; break; }
-                    enrich_pass(g, gap, o, o, q, sh_i, sh_s);
+                    K::enrich_pass(g, gap, o, o, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(1);
                     if (g.status) { ok = false; break; }
-                    join_pass(g, gap, o, q, &red, sh_s);
+                    K::join_pass(g, gap, o, q, &red, sh_s, prof2);
                     __syncthreads();
                     PROF_END(2);
                     if (g.status) { ok = false; break; }
@@ -1177,20 +1438,20 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                     // GHM.cpp:186-189: (cluster, matrix) orientations (0,0) (1,1) (1,0) (0,1)
                     const int oc = (e == 1 || e == 2) ? 1 : 0;
                     const int om = (e == 1 || e == 3) ? 1 : 0;
-                    enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
+                    K::enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(1);
                     if (g.status) { ok = false; break; }
                 }
                 if (!ok) break;
                 if (rep == 0) {
-                    filter_pass(g, prm, sh_s);
+                    K::filter_pass(g, prm, sh_s);
                     CHECK_STATUS();
                     PROF_END(3);
                 }
             }
             if (!ok) break;
-            cluster_clusters(g, prm, &red, sh_s);
+            K::cluster_clusters(g, prm, &red, sh_i, sh_s);
             PROF_END(4);
         } while (false);
 #undef CHECK_STATUS
@@ -1200,7 +1461,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             task.n_mult = ok ? sh_s[0] : 0;
             task.n_clusters = g.ncl;
             prof[5] = clock64() - t_begin;
-            for (int k = 0; k < 8; k++) task.prof[k] = prof[k];
+            for (int k = 0; k < 8; k++) { task.prof[k] = prof[k]; task.prof2[k] = prof2[k]; }
         }
         __syncthreads();
     }
@@ -1209,8 +1470,12 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
 }  // namespace
 
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int grid, cudaStream_t st)
+                    const DevParams& prm, int pool_factor, int grid, int nt, cudaStream_t st)
 {
     if (n_tasks == 0) return;
-    cluster_kernel<<<grid, NT, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor);
+    switch (nt) {
+    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
+    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
+    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
+    }
 }

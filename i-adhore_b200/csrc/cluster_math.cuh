@@ -63,13 +63,10 @@ __device__ inline void recompute_sums(ClusterRec& c, const uint32_t* pool)
     c.sx = sx; c.sy = sy; c.sxy = sxy; c.sxx = sxx; c.syy = syy;
 }
 
-// BaseCluster.cpp:238-291 (regression + updateStatistics), executed eagerly after every
-// modification (the reference's lazy `b == 0.0` flag yields the same values, see DESIGN.md).
-// mrss / var_x are accumulated sequentially in multiset order.
-__device__ inline void update_stats(ClusterRec& c, const uint32_t* pool)
+// BaseCluster::regression (BaseCluster.cpp:266-291) from the exact integer sums
+__device__ inline void regress(ClusterRec& c)
 {
-    const int Ni = c.n;
-    const double N = (double)Ni;
+    const double N = (double)c.n;
     if (N >= 3.0) {
         const double sum_x = (double)c.sx, sum_y = (double)c.sy, sum_xy = (double)c.sxy, sum_x2 = (double)c.sxx;
         c.avg_x = sum_x / N;
@@ -79,6 +76,27 @@ __device__ inline void update_stats(ClusterRec& c, const uint32_t* pool)
         c.b = cov_xy / c.var_x;
         c.a = avg_y - c.b * c.avg_x;
     }
+}
+
+// tail of BaseCluster::updateStatistics (BaseCluster.cpp:258-263) given the two ordered sums
+__device__ inline void finish_stats(ClusterRec& c, double mrss, double var_x, const uint32_t* pool)
+{
+    const int Ni = c.n;
+    c.mrss = mrss / (Ni - 2);
+    c.var_x = var_x / (Ni - 1);
+    c.x_end1 = (double)(unsigned)KEY_X(pool[c.off]);
+    c.x_end2 = (double)(unsigned)KEY_X(pool[c.off + Ni - 1]);
+    c.y_end1 = c.x_end1 * c.b + c.a;
+    c.y_end2 = c.x_end2 * c.b + c.a;
+}
+
+// BaseCluster.cpp:238-291 (regression + updateStatistics), executed eagerly after every
+// modification (the reference's lazy `b == 0.0` flag yields the same values, see DESIGN.md).
+// mrss / var_x are accumulated sequentially in multiset order.
+__device__ inline void update_stats(ClusterRec& c, const uint32_t* pool)
+{
+    regress(c);
+    const int Ni = c.n;
     double var_x = 0.0, mrss = 0.0;
     const double a = c.a, b = c.b, avg_x = c.avg_x;
     for (int i = 0; i < Ni; i++) {
@@ -88,12 +106,7 @@ __device__ inline void update_stats(ClusterRec& c, const uint32_t* pool)
         mrss += (y - y_est) * (y - y_est);
         var_x += (x - avg_x) * (x - avg_x);
     }
-    c.mrss = mrss / (Ni - 2);
-    c.var_x = var_x / (Ni - 1);
-    c.x_end1 = (double)(unsigned)KEY_X(pool[c.off]);
-    c.x_end2 = (double)(unsigned)KEY_X(pool[c.off + Ni - 1]);
-    c.y_end1 = c.x_end1 * b + a;
-    c.y_end2 = c.x_end2 * b + a;
+    finish_stats(c, mrss, var_x, pool);
 }
 
 // BaseCluster.cpp:293-304
@@ -168,22 +181,44 @@ __device__ inline double dist_to_cluster(const ClusterRec& A, const ClusterRec& 
     return lo;
 }
 
-// BaseCluster.cpp:491-546
+// first index in [0,n) whose x is >= x / > x (the AP array is x-sorted)
+__device__ __forceinline__ int ap_lower(const uint32_t* ap, int n, int x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEY_X(ap[mid]) < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int ap_upper(const uint32_t* ap, int n, int x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEY_X(ap[mid]) <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// BaseCluster.cpp:491-546: every AP of B inside A's x-range must lie in A's prediction interval and
+// vice versa.  The reference scans all APs and tests the x-range per AP; the arrays are x-sorted, so
+// the same APs are reached by two binary searches (same tests, same order, same result).
 __device__ inline bool partial_overlap(const ClusterRec& A, const ClusterRec& B, const uint32_t* pool)
 {
-    const int x1min = KEY_X(pool[A.off]), x1max = KEY_X(pool[A.off + A.n - 1]);
-    for (int i = 0; i < B.n; i++) {
-        const uint32_t k = pool[B.off + i];
-        const int x = KEY_X(k);
-        if (x >= x1min && x <= x1max)
-            if (!in_interval(A, x, KEY_Y(k))) return false;
-    }
-    const int x2min = KEY_X(pool[B.off]), x2max = KEY_X(pool[B.off + B.n - 1]);
-    for (int i = 0; i < A.n; i++) {
-        const uint32_t k = pool[A.off + i];
-        const int x = KEY_X(k);
-        if (x >= x2min && x <= x2max)
-            if (!in_interval(B, x, KEY_Y(k))) return false;
+    const uint32_t* pa = pool + A.off;
+    const uint32_t* pb = pool + B.off;
+    const int x1min = KEY_X(pa[0]), x1max = KEY_X(pa[A.n - 1]);
+    const int x2min = KEY_X(pb[0]), x2max = KEY_X(pb[B.n - 1]);
+    if (x2max >= x1min && x2min <= x1max) {
+        const int lo = ap_lower(pb, B.n, x1min), hi = ap_upper(pb, B.n, x1max);
+        for (int i = lo; i < hi; i++)
+            if (!in_interval(A, KEY_X(pb[i]), KEY_Y(pb[i]))) return false;
+        const int lo2 = ap_lower(pa, A.n, x2min), hi2 = ap_upper(pa, A.n, x2max);
+        for (int i = lo2; i < hi2; i++)
+            if (!in_interval(B, KEY_X(pa[i]), KEY_Y(pa[i]))) return false;
     }
     return true;
 }

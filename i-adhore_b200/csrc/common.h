@@ -22,6 +22,7 @@ struct DevParams {
     int mult_hyp;  // 0 none, 1 Bonferroni, 2 FDR
     double q_value;
     double prob_cutoff;
+    int coop[4];   // debug: thresholds of the cooperative stats / merge / insert / twist paths
 };
 
 // One GHM to cluster: either list x list (level 2) or profile x list.
@@ -44,6 +45,7 @@ struct GhmTask {
     int32_t n_clusters;   // out
     int32_t n_aps;        // out
     int32_t pad1;
+    long long prof2[8];   // out: join sub-phases (init, reduce, locate, merge, erase, refresh, redo, #merges)
     long long prof[8];    // out: SM cycles per phase (seed, enrich, join, filter, metacluster, total, -, -)
 };
 

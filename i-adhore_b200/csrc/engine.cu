@@ -34,7 +34,7 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
                        int sm_count, cudaStream_t st);
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int grid, cudaStream_t st);
+                    const DevParams& prm, int pool_factor, int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
                          const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -135,6 +135,9 @@ struct iadh_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t st = nullptr;
+    cudaStream_t st_side[2] = {nullptr, nullptr};  // K2 size classes run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int d_small = 192, d_mid = 1024;               // dots: <= d_small -> 32-thread CTAs, <= d_mid -> 128, else 256
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // dataset (host mirror + device)
     int n_lists = 0;
@@ -405,9 +408,39 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(cudaMemsetAsync(c->d_counter.p, 0, 16, c->st));
         trace_mark(c->st, "host: order/ws + uploads");
         CU(cudaEventRecord(c->ev[5], c->st));
-        const int grid = std::max(1, std::min(n_act, c->sm_count * c->ctas_per_sm));
-        launch_cluster(c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_counter.as<int>(),
-                       c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, grid, c->st);
+        {
+            // three size classes (order is sorted by dots, descending), launched concurrently:
+            // heavy GHMs get 256-thread CTAs and start first, small ones 32-thread CTAs
+            int n_big = 0, n_mid = 0;
+            for (int i : order) {
+                const int64_t D = (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
+                if (D > c->d_mid) n_big++;
+                else if (D > c->d_small) n_mid++;
+            }
+            const int n_small = n_act - n_big - n_mid;
+            const int sm = c->sm_count;
+            int* ctr = c->d_counter.as<int>();
+            const int* ord = c->d_order.as<int>();
+            CU(cudaEventRecord(c->ev_fork, c->st));
+            if (n_big)
+                launch_cluster(c->d_tasks.as<GhmTask>(), ord, n_big, ctr, c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(),
+                               c->prm, pool_factor, std::min(n_big, sm * 2), 256, c->st);
+            if (n_mid) {
+                CU(cudaStreamWaitEvent(c->st_side[0], c->ev_fork, 0));
+                launch_cluster(c->d_tasks.as<GhmTask>(), ord + n_big, n_mid, ctr + 1, c->d_dots.as<uint32_t>(),
+                               c->d_ws.as<uint8_t>(), c->prm, pool_factor, std::min(n_mid, sm * 4), 128, c->st_side[0]);
+                CU(cudaEventRecord(c->ev_join[0], c->st_side[0]));
+                CU(cudaStreamWaitEvent(c->st, c->ev_join[0], 0));
+            }
+            if (n_small) {
+                CU(cudaStreamWaitEvent(c->st_side[1], c->ev_fork, 0));
+                launch_cluster(c->d_tasks.as<GhmTask>(), ord + n_big + n_mid, n_small, ctr + 2, c->d_dots.as<uint32_t>(),
+                               c->d_ws.as<uint8_t>(), c->prm, pool_factor, std::min(n_small, sm * 16), 32, c->st_side[1]);
+                CU(cudaEventRecord(c->ev_join[1], c->st_side[1]));
+                CU(cudaStreamWaitEvent(c->st, c->ev_join[1], 0));
+            }
+            st.kernel_launches += (n_big ? 1 : 0) + (n_mid ? 1 : 0) + (n_small ? 1 : 0) - (n_act ? 1 : 0);
+        }
         CU(cudaEventRecord(c->ev[6], c->st));
         trace_mark(c->st, "K2 cluster");
         // measure runs over every active GHM (those without multiplicons return at once)
@@ -432,6 +465,10 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                         hv, tasks[hv].cnt[0], tasks[hv].cnt[1], tasks[hv].n_clusters, tasks[hv].n_mult, tasks[hv].prof[0] / 1e6,
                         tasks[hv].prof[1] / 1e6, tasks[hv].prof[2] / 1e6, tasks[hv].prof[3] / 1e6, tasks[hv].prof[4] / 1e6,
                         tasks[hv].prof[5] / 1e6);
+            if (hv >= 0)
+                fprintf(stderr, "[iadh]   join of it: init %.2fM reduce %.2fM locate %.2fM merge %.2fM erase %.2fM refresh %.2fM redo %.2fM, %lld merges\n",
+                        tasks[hv].prof2[0] / 1e6, tasks[hv].prof2[1] / 1e6, tasks[hv].prof2[2] / 1e6, tasks[hv].prof2[3] / 1e6,
+                        tasks[hv].prof2[4] / 1e6, tasks[hv].prof2[5] / 1e6, tasks[hv].prof2[6] / 1e6, tasks[hv].prof2[7]);
         }
         bool retry = false;
         for (int i : order)
@@ -590,6 +627,11 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     c->n_lists = d->n_lists;
     c->list_off.assign(d->list_off, d->list_off + d->n_lists + 1);
     const int64_t total = d->n_lists ? c->list_off[d->n_lists] : 0;
@@ -663,6 +705,10 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     // tuning / test knobs (the anchor-point pool grows automatically when too small)
     if (const char* e = getenv("IADH_POOL_FACTOR")) c->pool_factor = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_CTAS_PER_SM")) c->ctas_per_sm = std::max(1, atoi(e));
+    for (int k = 0; k < 4; k++) c->prm.coop[k] = 48;
+    if (const char* e = getenv("IADH_COOP")) sscanf(e, "%d,%d,%d,%d", &c->prm.coop[0], &c->prm.coop[1], &c->prm.coop[2], &c->prm.coop[3]);
+    if (const char* e = getenv("IADH_D_SMALL")) c->d_small = atoi(e);
+    if (const char* e = getenv("IADH_D_MID")) c->d_mid = atoi(e);
     *out = c;
     return IADH_OK;
 }
@@ -684,6 +730,11 @@ void iadh_destroy(iadh_ctx* c)
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
+    for (int i = 0; i < 2; i++) {
+        if (c->st_side[i]) cudaStreamDestroy(c->st_side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     delete c;
 }
 
