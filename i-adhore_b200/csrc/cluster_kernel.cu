@@ -26,6 +26,14 @@ namespace {
 
 constexpr int MAXW = 16;  // warps per CTA, upper bound (block size is a template parameter)
 
+// The clustering of one GHM is a dependent chain that keeps about ONE warp busy (the one holding
+// "thread 0" of the serial sections).  Warp w of every CTA lands on SM sub-partition w % 4, so with
+// several CTAs per SM all busy warps would share one scheduler (measured: 2x slowdown at 4 CTAs/SM).
+// Each CTA therefore rotates its thread numbering by whole warps: the k-th CTA to arrive on an SM
+// puts its virtual thread 0 in warp k % NW.  All code below uses the virtual id VTID.
+__shared__ int s_rot;
+#define VTID ((int)((threadIdx.x + (unsigned)s_rot) & (unsigned)(NT - 1)))
+
 struct Ghm {
     uint32_t* key[2];
     uint8_t* alive[2];
@@ -47,7 +55,9 @@ struct Ghm {
     double* rb_d;   // join cache: best distance / partner id of every cluster, rank, redo list
     int* rb_j;
     int* rank;
+    int* pos;       // join: current position of a cluster id in its orientation vector
     int* redo;
+    int2* xr;       // enrich: per active cluster [x_end1 - gap, x_end2 + gap] (exact prefilter, dpd >= |dx|)
     double* dscr;   // 2 doubles per anchor point: terms of the ordered mrss / var_x sums
     uint32_t* tmp;
     int tmp_cap;
@@ -76,7 +86,7 @@ static constexpr int NW = NT / 32;
 // minimum int over the block (INT_MAX = none); two barriers
 static __device__ int block_min_int(int v, int* sh)
 {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = VTID & 31, w = VTID >> 5;
     v = __reduce_min_sync(0xffffffffu, v);  // REDUX: one instruction, signed min
     if (lane == 0) sh[w] = v;
     __syncthreads();
@@ -90,7 +100,7 @@ static __device__ int block_min_int(int v, int* sh)
 // lexicographic minimum of (dist, idx); idx < 0 = none
 static __device__ void block_min_pair(double& d, long long& k, Red* sh)
 {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = VTID & 31, w = VTID >> 5;
 #pragma unroll
     for (int s = 16; s; s >>= 1) {
         const double od = __shfl_xor_sync(0xffffffffu, d, s);
@@ -267,7 +277,7 @@ static constexpr int COOP_MIN = 48;
 
 static __device__ void stats_coop(Ghm& g, ClusterRec& c)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     const int n = c.n;
     if (n < COOP_T(0)) {
         if (tid == 0) cm::update_stats(c, g.pool);
@@ -336,7 +346,7 @@ static __device__ __forceinline__ int upper_bound_x(const uint32_t* a, int n, in
 // search into the other cluster (A's APs first on equal x), staged, then copied.
 static __device__ bool merge_coop(Ghm& g, int idA, int idB)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     ClusterRec& A = g.cl[idA];
     const ClusterRec& B = g.cl[idB];
     const int nA = A.n, nB = B.n, n = nA + nB;
@@ -403,7 +413,7 @@ static __device__ bool merge_coop(Ghm& g, int idA, int idB)
 // BaseCluster::addAnchorPoint(x, y) + updateStatistics by the whole CTA
 static __device__ bool insert_coop(Ghm& g, ClusterRec& c, uint32_t key)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     const int n = c.n;
     if (n < COOP_T(2)) {
         if (tid == 0 && insert_ap(g, c, key)) cm::update_stats(c, g.pool);
@@ -477,7 +487,17 @@ static __device__ int window_next(const uint32_t* key, const uint8_t* alive, int
     const int hiY = orient ? ry + gap : ry - 1;
     const int hiX = rx + gap;
     int best = gap + 1, bj = -1;
-    int j = lower_bound_key(key, i + 1, n, MAKE_KEY(rx + 1, 0));
+    // first dot of column rx+1 or later: the rest of column rx is usually 0-2 dots, so step over it
+    // before falling back to a binary search (dense GHMs)
+    int j = i + 1;
+    {
+        int steps = 0;
+        while (j < n && KEY_X(key[j]) == rx && steps < 3) {
+            j++;
+            steps++;
+        }
+        if (j < n && KEY_X(key[j]) == rx) j = lower_bound_key(key, j + 1, n, MAKE_KEY(rx + 1, 0));
+    }
     for (; j < n; j++) {
         const uint32_t kj = key[j];
         const int x = KEY_X(kj);
@@ -496,7 +516,7 @@ static __device__ int window_next(const uint32_t* key, const uint8_t* alive, int
 // GHM::seedBaseClusters (GHM.cpp:287-324)
 static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     const uint32_t* key = g.key[o];
     uint8_t* alive = g.alive[o];
     const int n = g.nk[o];
@@ -577,9 +597,42 @@ static __device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, i
     return cm::r2_with_point(c, x, y) >= q && cm::in_interval(c, x, y);
 }
 
+// all active clusters against one dot, in vector order (GHM.cpp:352-365).  g.xr[k] holds the
+// cluster's x-range widened by the gap: outside it distanceToPoint >= |dx| >= gap+1 >= bd, i.e. the
+// reference's own `distance < closest` test fails -- the prefilter rejects exactly those pairs.
+static __device__ __forceinline__ void enrich_scan(const Ghm& g, const int* act, int nact, int x, int y, double q,
+                                                   double& bd, int& bk)
+{
+    const int2* xr = g.xr;
+    int k = 0;
+    for (; k + 4 <= nact; k += 4) {
+        const int2 r0 = xr[k], r1 = xr[k + 1], r2 = xr[k + 2], r3 = xr[k + 3];
+        unsigned m = (x >= r0.x && x <= r0.y ? 1u : 0u) | (x >= r1.x && x <= r1.y ? 2u : 0u) |
+                     (x >= r2.x && x <= r2.y ? 4u : 0u) | (x >= r3.x && x <= r3.y ? 8u : 0u);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            double d;
+            if (enrich_test(g.cl[act[k + b]], x, y, bd, q, d)) {
+                bd = d;
+                bk = k + b;
+            }
+        }
+    }
+    for (; k < nact; k++) {
+        const int2 r = xr[k];
+        if (x < r.x || x > r.y) continue;
+        double d;
+        if (enrich_test(g.cl[act[k]], x, y, bd, q, d)) {
+            bd = d;
+            bk = k;
+        }
+    }
+}
+
 static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i, int* sh_s)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     const uint32_t* key = g.key[om];
     uint8_t* alive = g.alive[om];
     const int n = g.nk[om];
@@ -589,7 +642,11 @@ static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, in
     int* act = g.act;
     int* act_next = g.act_next;
     while (nact > 0) {
-        for (int i = tid; i < nact; i += NT) g.changed[i] = 0;
+        for (int i = tid; i < nact; i += NT) {
+            g.changed[i] = 0;
+            const ClusterRec& c = g.cl[act[i]];
+            g.xr[i] = make_int2((int)c.x_end1 - gap, (int)c.x_end2 + gap);
+        }
         if (tid == 0) sh_s[1] = 0;  // number of clusters in the next round
         __syncthreads();
         for (int base = 0; base < n; base += NT) {
@@ -601,13 +658,7 @@ static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, in
             if (mine) {
                 x = KEY_X(key[i]);
                 y = KEY_Y(key[i]);
-                for (int k = 0; k < nact; k++) {
-                    double d;
-                    if (enrich_test(g.cl[act[k]], x, y, bd, q, d)) {
-                        bd = d;
-                        bk = k;
-                    }
-                }
+                enrich_scan(g, act, nact, x, y, q, bd, bk);
             }
             int from = 0;
             while (true) {
@@ -630,6 +681,8 @@ static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, in
                             act_next[sh_s[1]++] = act[kc];
                         }
                         alive[di] = 0;
+                        const ClusterRec& c = g.cl[act[kc]];
+                        g.xr[kc] = make_int2((int)c.x_end1 - gap, (int)c.x_end2 + gap);
                     }
                     __syncthreads();
                 }
@@ -638,13 +691,7 @@ static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, in
                     if (bk == kc) {
                         bd = gap + 1;
                         bk = -1;
-                        for (int k = 0; k < nact; k++) {
-                            double d;
-                            if (enrich_test(g.cl[act[k]], x, y, bd, q, d)) {
-                                bd = d;
-                                bk = k;
-                            }
-                        }
+                        enrich_scan(g, act, nact, x, y, q, bd, bk);
                     } else {
                         double d;
                         // the changed cluster wins if strictly closer, or equally close and earlier
@@ -679,7 +726,7 @@ static __device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double 
     const long long total = (long long)ni * nj;
     double bd = gap + 1;
     long long bk = -1;
-    for (long long idx = threadIdx.x; idx < total; idx += NT) {
+    for (long long idx = VTID; idx < total; idx += NT) {
         const int i = (int)(idx / nj), j = (int)(idx - (long long)i * nj);
         if (same && j <= i) continue;
         const ClusterRec& cI = g.cl[g.bc[oi][i]];
@@ -732,7 +779,7 @@ static __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRe
 // best partner of the cluster at position `pos` among the later positions (one warp)
 static __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = VTID & 31;
     const int n = g.nbc[o];
     const int idI = g.bc[o][pos];
     const ClusterRec& cI = g.cl[idI];
@@ -772,12 +819,15 @@ static __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
 // cluster never changes the relative order of the others.
 static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int* sh_s, long long* pf2)
 {
-#define JP(k) do { const long long t_ = clock64(); if (threadIdx.x == 0) pf2[k] += t_ - jt; jt = t_; } while (0)
+#define JP(k) do { const long long t_ = clock64(); if (VTID == 0) pf2[k] += t_ - jt; jt = t_; } while (0)
     long long jt = clock64();
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = VTID, warp = tid >> 5;
     int n = g.nbc[o];
     if (n < 2) return;
-    for (int i = tid; i < n; i += NT) g.rank[g.bc[o][i]] = i;
+    for (int i = tid; i < n; i += NT) {
+        g.rank[g.bc[o][i]] = i;
+        g.pos[g.bc[o][i]] = i;
+    }
     __syncthreads();
     for (int row = warp; row < n - 1; row += NW) join_row(g, o, row, gap, q);
     if (tid == 0) {
@@ -795,7 +845,8 @@ static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int
             const int j = g.rb_j[id];
             if (j < 0) continue;
             const double d = g.rb_d[id];
-            const long long k = ((long long)g.rank[id] << 32) | (unsigned)g.rank[j];
+            // positions are monotone in rank: the same lexicographic order, and no search afterwards
+            const long long k = ((long long)i << 32) | (unsigned)g.pos[j];
             if (bk < 0 || d < bd || (d == bd && k < bk)) {
                 bd = d;
                 bk = k;
@@ -804,24 +855,10 @@ static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int
         block_min_pair(bd, bk, red);
         JP(1);
         if (bk < 0) break;
-        if (threadIdx.x == 0) pf2[7]++;
-        // ranks -> current positions (ranks are sorted along the vector: binary search)
-        const int rankA = (int)(bk >> 32), rankB = (int)(bk & 0xffffffff);
-        int lo = 0, hi = n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (g.rank[g.bc[o][mid]] < rankA) lo = mid + 1;
-            else hi = mid;
-        }
-        const int pA = lo;
-        hi = n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (g.rank[g.bc[o][mid]] < rankB) lo = mid + 1;
-            else hi = mid;
-        }
-        const int pB = lo;
+        if (VTID == 0) pf2[7]++;
+        const int pA = (int)(bk >> 32), pB = (int)(bk & 0xffffffff);
         const int idA = g.bc[o][pA], idB = g.bc[o][pB];
+        const int rankA = g.rank[idA];
         __syncthreads();
         JP(2);
         if (!merge_coop(g, idA, idB)) return;
@@ -838,7 +875,10 @@ static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int
                 const int i = basei + tid;
                 if (i < n - 1) v = g.bc[o][i + 1];
                 __syncthreads();
-                if (i < n - 1) g.bc[o][i] = v;
+                if (i < n - 1) {
+                    g.bc[o][i] = v;
+                    g.pos[v] = i;
+                }
                 __syncthreads();
             }
             n--;
@@ -1055,7 +1095,7 @@ static __device__ void block_bitonic(uint32_t* a, int m)
 {
     for (int k = 2; k <= m; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += NT) {
+            for (int i = VTID; i < m; i += NT) {
                 const int l = i ^ j;
                 if (l > i) {
                     const uint32_t x = a[i], y = a[l];
@@ -1073,7 +1113,7 @@ static __device__ void block_bitonic(uint32_t* a, int m)
 // GHM::filterBaseClusters / BF / FDR (GHM.cpp:446-540)
 static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     for (int o = 0; o < 2; o++)
         for (int i = tid; i < g.nbc[o]; i += NT) calc_probability(g, g.cl[g.bc[o][i]]);
     __syncthreads();
@@ -1172,7 +1212,7 @@ static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
 // integer sums follow in closed form: sy' = nM - sy, sxy' = M sx - sxy, syy' = nM^2 - 2M sy + syy).
 static __device__ void twist_all(Ghm& g, int o, int* sh_i, int* sh_s)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     if (tid == 0) sh_s[4] = 0;
     __syncthreads();
     for (int i = tid; i < g.nbc[o]; i += NT) {
@@ -1228,7 +1268,7 @@ static __device__ void twist_all(Ghm& g, int o, int* sh_i, int* sh_s)
 // GHM::clusterClusters (GHM.cpp:542-625)
 static __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, int* sh_i, int* sh_s)
 {
-    const int tid = threadIdx.x;
+    const int tid = VTID;
     bool join_flag = true;
     while (join_flag) {
         join_flag = false;
@@ -1325,7 +1365,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* __restrict__ order,
                                                      int n_tasks, int* next_task,
                                                      const uint32_t* __restrict__ dots, uint8_t* ws,
-                                                     DevParams prm, int pool_factor)
+                                                     DevParams prm, int pool_factor, int* sm_slot)
 {
     using K = KT<NT>;
     constexpr int NW = K::NW;
@@ -1336,7 +1376,13 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
     __shared__ int sh_task;
     __shared__ long long prof[8];
     __shared__ long long prof2[8];
-    const int tid = threadIdx.x;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
+    }
+    __syncthreads();
+    const int tid = VTID;
 #define PROF_BEGIN() long long pt_ = clock64()
 #define PROF_END(k)                              \
     do {                                         \
@@ -1378,6 +1424,8 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.rb_d = (double*)(base + L.rb_d);
             g.rb_j = (int*)(base + L.rb_j);
             g.rank = (int*)(base + L.rank);
+            g.pos = (int*)(base + L.pos);
+            g.xr = (int2*)(base + L.xr);
             g.redo = (int*)(base + L.redo);
             g.dscr = (double*)(base + L.dscr);
             g.tmp = (uint32_t*)(base + L.tmp);
@@ -1470,12 +1518,13 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
 }  // namespace
 
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int grid, int nt, cudaStream_t st)
+                    const DevParams& prm, int pool_factor, int* sm_slot, int grid, int nt, cudaStream_t st)
 {
     if (n_tasks == 0) return;
     switch (nt) {
-    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
-    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
-    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor); break;
+    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
+    case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
+    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
+    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
     }
 }

@@ -34,7 +34,7 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
                        int sm_count, cudaStream_t st);
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int grid, int nt, cudaStream_t st);
+                    const DevParams& prm, int pool_factor, int* sm_slot, int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
                          const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -71,29 +71,87 @@ static void trace_mark(cudaStream_t st, const char* label)
     g_t_last = now;
 }
 
+// Process-wide block cache behind the growable buffers: contexts are cheap to create and destroy
+// (a drop-in caller may build one per run), cudaMalloc / cudaMallocHost / cudaFree are not (and
+// cudaFree synchronises the device).  Blocks return here instead of to the driver; iadh_trim()
+// gives them back.
+#include <mutex>
+struct BlockCache {
+    struct Blk {
+        void* p;
+        size_t cap;
+        int dev;  // -1 = pinned host
+    };
+    std::mutex mu;
+    std::vector<Blk> blocks;
+    void* take(size_t bytes, int dev, size_t* cap_out)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); i++)
+            if (blocks[i].dev == dev && blocks[i].cap >= bytes && (best < 0 || blocks[i].cap < blocks[best].cap)) best = i;
+        if (best < 0) return nullptr;
+        void* p = blocks[best].p;
+        *cap_out = blocks[best].cap;
+        blocks.erase(blocks.begin() + best);
+        return p;
+    }
+    void give(void* p, size_t cap, int dev)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        blocks.push_back({p, cap, dev});
+    }
+    void trim()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (Blk& b : blocks) {
+            if (b.dev < 0) cudaFreeHost(b.p);
+            else {
+                cudaSetDevice(b.dev);
+                cudaFree(b.p);
+            }
+        }
+        blocks.clear();
+        cudaSetDevice(cur);
+    }
+};
+static BlockCache g_cache;
+
 // growable device buffer
 struct DBuf {
     void* p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) {
+            // the old block may still be read by work in flight; it must be idle before another
+            // context can take it from the cache (growth is rare: sizes converge after the first call)
+            cudaDeviceSynchronize();
+            g_cache.give(p, cap, dev);
+        }
         p = nullptr;
         cap = 0;
+        cudaGetDevice(&dev);
+        if ((p = g_cache.take(bytes, dev, &cap))) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            g_cache.trim();
             want = bytes;
             e = cudaMalloc(&p, want);
         }
         if (e == cudaSuccess) cap = want;
+        else p = nullptr;
         return e;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) g_cache.give(p, cap, dev);
         p = nullptr;
         cap = 0;
     }
@@ -107,17 +165,17 @@ struct HBuf {
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
+        release();
+        if ((p = g_cache.take(bytes, -1, &cap))) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
+        else p = nullptr;
         return e;
     }
     void release()
     {
-        if (p) cudaFreeHost(p);
+        if (p) g_cache.give(p, cap, -1);
         p = nullptr;
         cap = 0;
     }
@@ -126,7 +184,8 @@ struct HBuf {
 };
 
 struct iadh_result {
-    std::vector<uint8_t> bytes;
+    HBuf bytes;            // pinned: the device writes the packed stream straight into it (offset 4)
+    size_t n_bytes = 0;
     std::vector<int32_t> ghm_index;
     iadh_stats stats;
 };
@@ -135,9 +194,13 @@ struct iadh_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t st = nullptr;
-    cudaStream_t st_side[2] = {nullptr, nullptr};  // K2 size classes run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    int d_small = 192, d_mid = 1024;               // dots: <= d_small -> 32-thread CTAs, <= d_mid -> 128, else 256
+    cudaStream_t st_side[3] = {nullptr, nullptr, nullptr};  // K2 size classes run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    // K2 size classes, heaviest first: GHMs with >= min_dots dots run on nt-thread CTAs, per_sm CTAs per SM
+    struct SizeClass {
+        int min_dots, nt, per_sm;
+    } cls[4] = {{1025, 256, 2}, {193, 128, 4}, {0, 32, 16}, {0, 32, 16}};
+    int n_classes = 3;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // dataset (host mirror + device)
     int n_lists = 0;
@@ -307,9 +370,11 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
 
 struct BatchOut {
     std::vector<GhmTask> tasks;  // final state (cnt, n_mult, out_bytes ...)
-    std::vector<uint8_t> packed; // concatenated per-GHM blocks in seq order (no leading count)
+    HBuf packed;                 // pinned: int32 count + concatenated per-GHM blocks in seq order
+    size_t packed_bytes = 0;     // incl. the 4-byte count
     std::vector<int32_t> ghm_index;
     iadh_stats st;
+    ~BatchOut() { packed.release(); }
 };
 
 // stages 1..4: build the dots of every task; on return tasks hold cnt/dot_off and d_dots the keys
@@ -370,6 +435,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     int rc;
     if (n == 0) {
         out.tasks.clear();
+        CU(out.packed.ensure(4));
+        out.packed_bytes = 4;
         return IADH_OK;
     }
     if ((rc = build_stage(c, hl, pf, tasks, total_dots, st))) return rc;
@@ -404,49 +471,46 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         if ((rc = upload(c->d_order, order.data(), 4 * (size_t)n_act, c->st))) return rc;
         CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
         st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act;
-        CU(c->d_counter.ensure(16));
-        CU(cudaMemsetAsync(c->d_counter.p, 0, 16, c->st));
+        CU(c->d_counter.ensure(16 + 4 * 1024));  // 4 class queues + per-SM arrival counters
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024, c->st));
         trace_mark(c->st, "host: order/ws + uploads");
         CU(cudaEventRecord(c->ev[5], c->st));
         {
-            // three size classes (order is sorted by dots, descending), launched concurrently:
-            // heavy GHMs get 256-thread CTAs and start first, small ones 32-thread CTAs
-            int n_big = 0, n_mid = 0;
-            for (int i : order) {
-                const int64_t D = (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
-                if (D > c->d_mid) n_big++;
-                else if (D > c->d_small) n_mid++;
-            }
-            const int n_small = n_act - n_big - n_mid;
-            const int sm = c->sm_count;
+            // size classes (order is sorted by dots, descending), launched concurrently: heavy GHMs get
+            // wide CTAs and start first, the bulk runs on narrow CTAs (many GHMs in flight per SM --
+            // the clustering of one GHM is a dependent chain that keeps about one warp busy)
             int* ctr = c->d_counter.as<int>();
             const int* ord = c->d_order.as<int>();
             CU(cudaEventRecord(c->ev_fork, c->st));
-            if (n_big)
-                launch_cluster(c->d_tasks.as<GhmTask>(), ord, n_big, ctr, c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(),
-                               c->prm, pool_factor, std::min(n_big, sm * 2), 256, c->st);
-            if (n_mid) {
-                CU(cudaStreamWaitEvent(c->st_side[0], c->ev_fork, 0));
-                launch_cluster(c->d_tasks.as<GhmTask>(), ord + n_big, n_mid, ctr + 1, c->d_dots.as<uint32_t>(),
-                               c->d_ws.as<uint8_t>(), c->prm, pool_factor, std::min(n_mid, sm * 4), 128, c->st_side[0]);
-                CU(cudaEventRecord(c->ev_join[0], c->st_side[0]));
-                CU(cudaStreamWaitEvent(c->st, c->ev_join[0], 0));
+            int begin = 0, launched = 0;
+            for (int k = 0; k < c->n_classes; k++) {
+                int end = begin;
+                while (end < n_act && ((int64_t)tasks[order[end]].cnt[0] + tasks[order[end]].cnt[1] >= c->cls[k].min_dots ||
+                                       k == c->n_classes - 1))
+                    end++;
+                const int cnt = end - begin;
+                if (cnt > 0) {
+                    cudaStream_t s = (launched == 0) ? c->st : c->st_side[launched - 1];
+                    if (launched) CU(cudaStreamWaitEvent(s, c->ev_fork, 0));
+                    launch_cluster(c->d_tasks.as<GhmTask>(), ord + begin, cnt, ctr + k, c->d_dots.as<uint32_t>(),
+                                   c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, std::min(cnt, c->sm_count * c->cls[k].per_sm),
+                                   c->cls[k].nt, s);
+                    if (launched) {
+                        CU(cudaEventRecord(c->ev_join[launched - 1], s));
+                        CU(cudaStreamWaitEvent(c->st, c->ev_join[launched - 1], 0));
+                    }
+                    launched++;
+                }
+                begin = end;
             }
-            if (n_small) {
-                CU(cudaStreamWaitEvent(c->st_side[1], c->ev_fork, 0));
-                launch_cluster(c->d_tasks.as<GhmTask>(), ord + n_big + n_mid, n_small, ctr + 2, c->d_dots.as<uint32_t>(),
-                               c->d_ws.as<uint8_t>(), c->prm, pool_factor, std::min(n_small, sm * 16), 32, c->st_side[1]);
-                CU(cudaEventRecord(c->ev_join[1], c->st_side[1]));
-                CU(cudaStreamWaitEvent(c->st, c->ev_join[1], 0));
-            }
-            st.kernel_launches += (n_big ? 1 : 0) + (n_mid ? 1 : 0) + (n_small ? 1 : 0) - (n_act ? 1 : 0);
+            st.kernel_launches += launched;
         }
         CU(cudaEventRecord(c->ev[6], c->st));
         trace_mark(c->st, "K2 cluster");
         // measure runs over every active GHM (those without multiplicons return at once)
         launch_pack_measure(hl, c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_ws.as<uint8_t>(), c->ds, pf,
                             pool_factor, c->st);
-        st.kernel_launches += n_act ? 2 : 0;
+        st.kernel_launches += n_act ? 1 : 0;
         trace_mark(c->st, "K3 measure");
         CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -494,7 +558,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             out_off.push_back(total_bytes);
             total_bytes += tasks[i].out_bytes;
         }
-    out.packed.resize((size_t)total_bytes);
+    CU(out.packed.ensure((size_t)total_bytes + 4));
+    out.packed_bytes = (size_t)total_bytes + 4;
     if (!sel.empty()) {
         if ((rc = upload(c->d_sel, sel.data(), 4 * sel.size(), c->st))) return rc;
         if ((rc = upload(c->d_out_off, out_off.data(), 8 * out_off.size(), c->st))) return rc;
@@ -503,14 +568,12 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                           c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
         st.kernel_launches += 1;
         trace_mark(c->st, "K3 write");
-        CU(c->h_out.ensure((size_t)total_bytes));
-        CU(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(out.packed.as<uint8_t>() + 4, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st));
         st.h2d_bytes += 12 * (int64_t)sel.size();
         st.d2h_bytes += total_bytes;
     }
     CU(cudaStreamSynchronize(c->st));
     trace_mark(c->st, "result D2H");
-    if (total_bytes) memcpy(out.packed.data(), c->h_out.p, (size_t)total_bytes);
     for (int i : sel)
         for (int k = 0; k < tasks[i].n_mult; k++) out.ghm_index.push_back(tasks[i].seq);
     st.n_ghm = n;
@@ -530,9 +593,9 @@ static iadh_result* make_result(BatchOut& b)
 {
     iadh_result* r = new iadh_result();
     const int32_t total = (int32_t)b.st.n_multiplicons;
-    r->bytes.resize(4 + b.packed.size());
-    memcpy(r->bytes.data(), &total, 4);
-    if (!b.packed.empty()) memcpy(r->bytes.data() + 4, b.packed.data(), b.packed.size());
+    memcpy(b.packed.p, &total, 4);
+    std::swap(r->bytes, b.packed);
+    r->n_bytes = b.packed_bytes;
     r->ghm_index.swap(b.ghm_index);
     r->stats = b.st;
     return r;
@@ -627,7 +690,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
@@ -707,8 +770,22 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     if (const char* e = getenv("IADH_CTAS_PER_SM")) c->ctas_per_sm = std::max(1, atoi(e));
     for (int k = 0; k < 4; k++) c->prm.coop[k] = 48;
     if (const char* e = getenv("IADH_COOP")) sscanf(e, "%d,%d,%d,%d", &c->prm.coop[0], &c->prm.coop[1], &c->prm.coop[2], &c->prm.coop[3]);
-    if (const char* e = getenv("IADH_D_SMALL")) c->d_small = atoi(e);
-    if (const char* e = getenv("IADH_D_MID")) c->d_mid = atoi(e);
+    if (const char* e = getenv("IADH_CLASSES")) {  // "min_dots:threads:ctas_per_sm,..." heaviest class first
+        int n = 0;
+        const char* q = e;
+        while (n < 4) {
+            int a = 0, b = 0, d = 0;
+            if (sscanf(q, "%d:%d:%d", &a, &b, &d) != 3) break;
+            c->cls[n].min_dots = a;
+            c->cls[n].nt = b;
+            c->cls[n].per_sm = std::max(1, d);
+            n++;
+            q = strchr(q, ',');
+            if (!q) break;
+            q++;
+        }
+        if (n > 0) c->n_classes = n;
+    }
     *out = c;
     return IADH_OK;
 }
@@ -730,7 +807,7 @@ void iadh_destroy(iadh_ctx* c)
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         if (c->st_side[i]) cudaStreamDestroy(c->st_side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
@@ -861,8 +938,8 @@ int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n
 
 const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n)
 {
-    if (n) *n = r ? r->bytes.size() : 0;
-    return r ? r->bytes.data() : nullptr;
+    if (n) *n = r ? r->n_bytes : 0;
+    return r ? (const uint8_t*)r->bytes.p : nullptr;
 }
 const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n)
 {
@@ -875,7 +952,13 @@ int iadh_result_stats(const iadh_result* r, iadh_stats* s)
     *s = r->stats;
     return IADH_OK;
 }
-void iadh_free_result(iadh_result* r) { delete r; }
+void iadh_free_result(iadh_result* r)
+{
+    if (!r) return;
+    r->bytes.release();
+    delete r;
+}
+void iadh_trim(void) { g_cache.trim(); }
 
 int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
                     const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)

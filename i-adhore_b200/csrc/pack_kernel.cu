@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
                                                         uint8_t* __restrict__ out)
 {
     __shared__ PGhm p;
+    __shared__ uint32_t stage[PW][140];  // per warp: 32 x 17 bytes + alignment slack
     if (blockIdx.x >= n_sel) return;
     const GhmTask& task = tasks[sel[blockIdx.x]];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -267,9 +268,29 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
         }
         q += 102;
         if (!HL) {
-            for (int a = lane; a < c.n; a += 32) {
-                const int x = KEY_X(ap[a]), y = KEY_Y(ap[a]);
-                put_ap(q + 17 * a, ds.num_id[xoff + x], ds.num_id[yoff + y], x, y, 1);
+            // 17-byte records at arbitrary alignment: a chunk of 32 anchor points (544 contiguous
+            // output bytes) is assembled in shared memory at the same alignment phase as its
+            // destination, then stored as aligned 32-bit words (byte stores only at the two edges)
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
+            for (int a0 = 0; a0 < c.n; a0 += 32) {
+                const int cnt = min(32, c.n - a0);
+                uint8_t* g0 = q + 17 * (size_t)a0;
+                const int ph = (int)(reinterpret_cast<uintptr_t>(g0) & 3);
+                if (lane < cnt) {
+                    const int x = KEY_X(ap[a0 + lane]), y = KEY_Y(ap[a0 + lane]);
+                    put_ap(sb + ph + 17 * lane, ds.num_id[xoff + x], ds.num_id[yoff + y], x, y, 1);
+                }
+                __syncwarp();
+                const int nb = 17 * cnt;
+                const int head = (4 - ph) & 3;                 // bytes before the first aligned word
+                const int nwords = (nb - min(head, nb)) >> 2;
+                const int tail0 = min(head, nb) + 4 * nwords;  // first byte after the last full word
+                if (lane < min(head, nb)) g0[lane] = sb[ph + lane];
+                uint32_t* gw = reinterpret_cast<uint32_t*>(g0 + head);
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb + ph + head);
+                for (int w = lane; w < nwords; w += 32) gw[w] = sw[w];
+                if (lane < nb - tail0) g0[tail0 + lane] = sb[ph + tail0 + lane];
+                __syncwarp();
             }
         } else {
             // multiset order after the false anchor points were inserted at upper_bound(x): per run of

@@ -10,7 +10,7 @@
 #include "common.h"
 
 struct WsLayout {
-    size_t key0, key1, alive0, alive1, nxt, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, rb_d, rb_j, rank, redo, dscr, tmp;
+    size_t key0, key1, alive0, alive1, nxt, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, rb_d, rb_j, rank, pos, redo, xr, dscr, tmp;
     size_t total;
     int pool_cap, cl_cap, tmp_cap;
 };
@@ -51,7 +51,9 @@ static inline WsLayout ws_layout(int D, int pool_factor)
     L.rb_d = take(8 * (size_t)L.cl_cap);
     L.rb_j = take(4 * (size_t)L.cl_cap);
     L.rank = take(4 * (size_t)L.cl_cap);
+    L.pos = take(4 * (size_t)L.cl_cap);
     L.redo = take(4 * (size_t)L.cl_cap);
+    L.xr = take(8 * (size_t)L.cl_cap);   // per active cluster: x-range widened by the gap (enrich / join prefilter)
     L.dscr = take(16 * d + 32);   // per-AP terms of the ordered statistics sums
     L.tmp = take(4 * (size_t)L.tmp_cap + d + 32);  // staging: keys + one flag byte per entry
     L.total = (o + 255) & ~(size_t)255;

@@ -54,7 +54,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
-           "free_result", "build_dots", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
+           "free_result", "trim", "build_dots", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
 def gap_sizes(gap_size: int) -> List[int]:
@@ -102,14 +102,40 @@ def _p(a: np.ndarray, t):
 
 
 class Result:
-    def __init__(self, bytes_: bytes, ghm_index: np.ndarray, stats: dict):
-        self.bytes = bytes_
+    """One call's packed multiplicon stream.  The stream stays in the library's (pinned) result
+    buffer until `.bytes` is first read; the C result is freed when this object dies."""
+
+    def __init__(self, owner, res, ptr, n: int, ghm_index: np.ndarray, stats: dict):
+        self._owner, self._res, self._ptr, self._n = owner, res, ptr, n
+        self._bytes = None
         self.ghm_index = ghm_index
         self.stats = stats
 
     @property
+    def bytes(self) -> bytes:
+        if self._bytes is None:
+            self._bytes = C.string_at(self._ptr, self._n)
+            self._release()
+        return self._bytes
+
+    @property
+    def nbytes(self) -> int:
+        return self._n
+
+    @property
     def n_multiplicons(self) -> int:
-        return struct.unpack_from("<i", self.bytes, 0)[0]
+        return int(self.stats["n_multiplicons"])
+
+    def _release(self):
+        if self._res is not None:
+            self._owner._f("free_result")(self._res)
+            self._res = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -128,6 +154,8 @@ class Engine:
         f("result_ghm_index").restype = C.POINTER(C.c_int32)
         f("destroy").restype = None
         f("free_result").restype = None
+        f("free_result").argtypes = [C.c_void_p]
+        f("trim").restype = None
         self.ds = ds
         self._keep = [np.ascontiguousarray(ds.list_off, dtype=np.int64),
                       np.ascontiguousarray(ds.fam, dtype=np.int32),
@@ -169,14 +197,12 @@ class Engine:
     def _take(self, res) -> Result:
         n = C.c_size_t()
         ptr = self._f("result_bytes")(res, C.byref(n))
-        b = C.string_at(ptr, n.value)
         m = C.c_size_t()
         gp = self._f("result_ghm_index")(res, C.byref(m))
         gi = np.ctypeslib.as_array(gp, shape=(m.value,)).copy() if m.value else np.zeros(0, np.int32)
         st = Stats()
         self._chk(self._f("result_stats")(res, C.byref(st)))
-        self._f("free_result")(res)
-        return Result(b, gi, st.as_dict())
+        return Result(self, res, ptr, n.value, gi, st.as_dict())
 
     def level2_all_pairs(self, rank: int = 0, n_ranks: int = 1) -> Result:
         res = C.c_void_p()

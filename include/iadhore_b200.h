@@ -141,6 +141,9 @@ const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n_bytes);
 const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n_multiplicons);
 int iadh_result_stats(const iadh_result* r, iadh_stats* out);
 void iadh_free_result(iadh_result* r);
+/* Device and pinned-host blocks of destroyed contexts / freed results are kept in a process-wide
+ * cache (contexts are cheap to re-create); iadh_trim returns them to the driver. */
+void iadh_trim(void);
 
 /* Test/measurement hook: the dot sets of the build kernels alone (GHM.cpp:34-85 /
  * GHMProfile.cpp:17-59) for explicit L2 pairs or, if profile != NULL, for profile x

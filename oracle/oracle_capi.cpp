@@ -288,6 +288,7 @@ const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
 }
 int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; return IADH_OK; }
 void oracle_free_result(oracle_result* r) { delete r; }
+void oracle_trim(void) {}
 
 static oracle_result g_scratch;
 int oracle_build_dots(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys,
