@@ -130,6 +130,147 @@ __device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// L2, second generation: no per-column walk.
+//  * the partners of column x inside list Y are the slot range [lo, hi) of its family bucket,
+//    read from the (family, list) table (or two binary searches when the table is too large);
+//  * for the self comparison the cut `y <= x` (GHM.cpp:64) and the exclusion of the element itself
+//    (GHM.cpp:68) together are "slots before the element's own slot";
+//  * the per-orientation counts of a range are differences of a strand prefix sum, so the count
+//    pass is O(1) per column, and a partner's rank inside its orientation block is a prefix
+//    difference too -- every candidate computes its output address independently;
+//  * the fill pass expands the candidates of 32 columns over the lanes (load balanced), reads the
+//    member records coalesced and writes each column's two key runs contiguously.
+// Columns whose gene ID occurs more than once in the dataset (flags bit 3; a shipped dataset has
+// none) keep the exact ID test of GHM.cpp:68 on a per-lane slow path.
+struct ColRange {
+    int lo, hi;   // candidate slots
+    int sx;       // strand of the x element
+    int slow;     // needs the gene-ID test
+    int c0, c1;   // dots per orientation
+};
+
+__device__ __forceinline__ ColRange l2_col_range(const DatasetDev& ds, int xg, int y_list, int64_t yoff, int ylen,
+                                                 bool identical)
+{
+    ColRange r;
+    const int f = ds.fam[xg];
+    const int fl = ds.flags[xg];
+    r.sx = fl & 1;
+    r.slow = (fl & 8) ? 1 : 0;
+    if (ds.fam_list) {
+        const int32_t* row = ds.fam_list + (size_t)f * (ds.n_lists + 1) + y_list;
+        r.lo = row[0];
+        r.hi = row[1];
+    } else {
+        const int b0 = ds.fam_ptr[f], b1 = ds.fam_ptr[f + 1];
+        r.lo = lower_bound_i32(ds.fam_members, b0, b1, (int)yoff);
+        r.hi = lower_bound_i32(ds.fam_members, r.lo, b1, (int)(yoff + ylen));
+    }
+    if (identical) r.hi = ds.self_slot[xg] + (r.slow ? 1 : 0);
+    if (!r.slow) {
+        const int n = r.hi - r.lo;
+        const int np = ds.plus_prefix[r.hi] - ds.plus_prefix[r.lo];
+        r.c1 = r.sx ? np : n - np;
+        r.c0 = n - r.c1;
+    } else {
+        const int gx = ds.gid[xg];
+        r.c0 = r.c1 = 0;
+        for (int m = r.lo; m < r.hi; m++) {
+            if (ds.gid[ds.fam_members[m]] == gx) continue;
+            if ((int)(ds.mem_y[m] & 1u) == r.sx) r.c1++;
+            else r.c0++;
+        }
+    }
+    return r;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) l2_build_kernel(DatasetDev ds, GhmTask* __restrict__ tasks, int n_ghm,
+                                                       const int64_t* __restrict__ tile_prefix, int64_t n_tiles,
+                                                       uint32_t* __restrict__ tile_cnt,
+                                                       const uint32_t* __restrict__ tile_off,
+                                                       uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
+        const int g = find_ghm(tile_prefix, n_ghm, t);
+        const int x_list = tasks[g].x_list, y_list = tasks[g].y_list;
+        const int x0 = (int)(t - tile_prefix[g]) * 32;
+        const int64_t yoff = ds.list_off[y_list];
+        const int ylen = (int)(ds.list_off[y_list + 1] - yoff);
+        const int64_t xoff = ds.list_off[x_list];
+        const int nx = (int)(ds.list_off[x_list + 1] - xoff);
+        const int x = x0 + lane;
+        ColRange r;
+        r.lo = r.hi = r.sx = r.slow = r.c0 = r.c1 = 0;
+        if (x < nx) r = l2_col_range(ds, (int)(xoff + x), y_list, yoff, ylen, x_list == y_list);
+        int t0, t1;
+        const int e0 = warp_excl_scan(r.c0, lane, t0);
+        const int e1 = warp_excl_scan(r.c1, lane, t1);
+        if (!FILL) {
+            if (lane == 0) {
+                tile_cnt[2 * t] = (uint32_t)t0;
+                tile_cnt[2 * t + 1] = (uint32_t)t1;
+                if (t0) atomicAdd(&tasks[g].cnt[0], (uint32_t)t0);
+                if (t1) atomicAdd(&tasks[g].cnt[1], (uint32_t)t1);
+            }
+            continue;
+        }
+        if (t0 + t1 == 0) continue;
+        const int64_t dot_off = tasks[g].dot_off;
+        const int64_t base0 = dot_off + tile_off[2 * t];
+        const int64_t base1 = dot_off + tasks[g].cnt[0] + tile_off[2 * t + 1];
+        // slow columns: the lane walks its own range
+        if (r.slow) {
+            const int gx = ds.gid[(int)(xoff + x)];
+            int64_t o0 = base0 + e0, o1 = base1 + e1;
+            for (int m = r.lo; m < r.hi; m++) {
+                if (ds.gid[ds.fam_members[m]] == gx) continue;
+                const uint32_t my = ds.mem_y[m];
+                const uint32_t key = MAKE_KEY(x, my >> 1);
+                if ((int)(my & 1u) == r.sx) keys[o1++] = key;
+                else keys[o0++] = key;
+            }
+        }
+        // fast columns: candidates of the whole tile, spread over the lanes
+        const int len = r.slow ? 0 : r.hi - r.lo;
+        int total;
+        const int ex = warp_excl_scan(len, lane, total);
+        const int incl = ex + len;
+        const int pp_lo = ds.plus_prefix[r.lo];
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            // column of candidate k = number of lanes whose inclusive prefix is <= k
+            int c = 0;
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) {
+                const int v = __shfl_sync(full, incl, (c + sft - 1) & 31);
+                if (v <= k) c += sft;
+            }
+            c &= 31;
+            const int c_ex = __shfl_sync(full, ex, c);
+            const int c_lo = __shfl_sync(full, r.lo, c);
+            const int c_pp = __shfl_sync(full, pp_lo, c);
+            const int c_sx = __shfl_sync(full, r.sx, c);
+            const int c_e0 = __shfl_sync(full, e0, c);
+            const int c_e1 = __shfl_sync(full, e1, c);
+            if (k < total) {
+                const int m = c_lo + (k - c_ex);
+                const uint32_t my = ds.mem_y[m];
+                const int plus_before = ds.plus_prefix[m] - c_pp;
+                const int sy = (int)(my & 1u);
+                const int rank = sy ? plus_before : (m - c_lo) - plus_before;
+                const uint32_t key = MAKE_KEY(x0 + c, my >> 1);
+                if (sy == c_sx) keys[base1 + c_e1 + rank] = key;
+                else keys[base0 + c_e0 + rank] = key;
+            }
+        }
+    }
+}
+
 template <bool HL, bool FILL>
 __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf, GhmTask* __restrict__ tasks,
                                                     int n_ghm, const int64_t* __restrict__ tile_prefix,
@@ -248,7 +389,7 @@ void launch_build_count(bool hl, const DatasetDev& ds, const ProfileDev& pf, Ghm
     if (n_tiles == 0) return;
     int grid = grid_for(n_tiles, sm_count);
     if (hl) build_kernel<true, false><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, tile_cnt, nullptr, nullptr);
-    else build_kernel<false, false><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, tile_cnt, nullptr, nullptr);
+    else l2_build_kernel<false><<<grid, 256, 0, st>>>(ds, tasks, n_ghm, tile_prefix, n_tiles, tile_cnt, nullptr, nullptr);
 }
 
 void launch_tile_scan(const int64_t* tile_prefix, int n_ghm, const uint32_t* tile_cnt, uint32_t* tile_off,
@@ -265,7 +406,7 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
     if (n_tiles == 0) return;
     int grid = grid_for(n_tiles, sm_count);
     if (hl) build_kernel<true, true><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
-    else build_kernel<false, true><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
+    else l2_build_kernel<true><<<grid, 256, 0, st>>>(ds, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
 }
 
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st)

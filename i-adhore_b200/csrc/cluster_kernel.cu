@@ -41,9 +41,12 @@ struct Ghm {
     int* nxt;
     uint32_t* pool;
     uint8_t* pflag;
-    int pool_cap, pool_used;
+    // The two orientations of a GHM are clustered independently up to the final enrichment
+    // (GHM.cpp:167-184 touches matrix[o] / baseclusters[o] only), so they run on two CTAs.  Each owns
+    // a region of the AP pool and of the cluster table; region r = orientation r.
+    int pool_lo[2], pool_used[2], pool_hi[2];   // absolute indices into pool
     ClusterRec* cl;
-    int ncl, cl_cap;
+    int cl_lo[2], ncl[2], cl_hi[2];             // cluster ids of region r: [cl_lo[r], ncl[r])
     int* bc[2];
     int nbc[2];
     int* act;
@@ -60,7 +63,7 @@ struct Ghm {
     int2* xr;       // enrich: per active cluster [x_end1 - gap, x_end2 + gap] (exact prefilter, dpd >= |dx|)
     double* dscr;   // 2 doubles per anchor point: terms of the ordered mrss / var_x sums
     uint32_t* tmp;
-    int tmp_cap;
+    uint8_t* tmpf;  // staging flags, parallel to tmp
     int status;
     int coop[4];
     // task constants
@@ -137,15 +140,20 @@ static __device__ void block_min_pair(double& d, long long& k, Red* sh)
 // to the capacity class of their current size.  Live data is at most ~4.7 D entries, so with
 // pool_factor >= 8 an allocation can only fail after a collection if the host under-sized the
 // pool on purpose (then the GHM reports status 1 and the engine reruns it with a larger pool).
-static __device__ void pool_gc(Ghm& g)
+static __device__ __forceinline__ bool valid_id(const Ghm& g, int id)
 {
-    int r = 0, w = 0;
-    while (r < g.pool_used) {
+    return (id >= g.cl_lo[0] && id < g.ncl[0]) || (id >= g.cl_lo[1] && id < g.ncl[1]);
+}
+
+static __device__ void pool_gc(Ghm& g, int rg)
+{
+    int r = g.pool_lo[rg], w = r;
+    while (r < g.pool_used[rg]) {
         const int owner = (int)g.pool[r];
         const int cap = (int)g.pool[r + 1];
         const int payload = r + 2;
         ClusterRec& c = g.cl[owner];
-        if (owner < g.ncl && !c.dead && c.off == payload) {
+        if (valid_id(g, owner) && !c.dead && c.off == payload) {
             int ncap = 8;
             while (ncap < c.n) ncap <<= 1;
             if (ncap > cap) ncap = cap;
@@ -162,24 +170,28 @@ static __device__ void pool_gc(Ghm& g)
         }
         r += 2 + cap;
     }
-    g.pool_used = w;
+    g.pool_used[rg] = w;
 }
 
-// single-thread contexts only (the rest of the CTA waits at a barrier)
-static __device__ int pool_alloc(Ghm& g, int n, int owner)
+// single-thread contexts only (the rest of the CTA waits at a barrier).  `rg` = preferred region
+// (the cluster's orientation); the other region is a fallback, empty while the other orientation
+// is still being clustered by its own CTA.
+static __device__ int pool_alloc(Ghm& g, int n, int owner, int rg)
 {
-    if (g.pool_used + n + 2 > g.pool_cap) {
-        pool_gc(g);
-        if (g.pool_used + n + 2 > g.pool_cap) {
-            g.status = 1;
-            return -1;
+    for (int t = 0; t < 2; t++, rg ^= 1) {
+        if (g.pool_used[rg] + n + 2 > g.pool_hi[rg]) {
+            if (g.pool_hi[rg] == g.pool_lo[rg]) continue;
+            pool_gc(g, rg);
+            if (g.pool_used[rg] + n + 2 > g.pool_hi[rg]) continue;
         }
+        const int off = g.pool_used[rg];
+        g.pool[off] = (uint32_t)owner;
+        g.pool[off + 1] = (uint32_t)n;
+        g.pool_used[rg] += n + 2;
+        return off + 2;
     }
-    const int off = g.pool_used;
-    g.pool[off] = (uint32_t)owner;
-    g.pool[off + 1] = (uint32_t)n;
-    g.pool_used += n + 2;
-    return off + 2;
+    g.status = 1;
+    return -1;
 }
 
 static __device__ __forceinline__ int next_cap(int n)
@@ -194,7 +206,7 @@ static __device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
 {
     if (c.n == c.cap) {
         const int ncap = c.cap * 2;
-        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl));
+        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl), c.orient);
         if (noff < 0) return false;
         for (int i = 0; i < c.n; i++) {
             g.pool[noff + i] = g.pool[c.off + i];
@@ -230,7 +242,7 @@ static __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B
     const int n = A.n + B.n;
     if (n > A.cap) {
         const int ncap = next_cap(n);
-        const int noff = pool_alloc(g, ncap, (int)(&A - g.cl));
+        const int noff = pool_alloc(g, ncap, (int)(&A - g.cl), A.orient);
         if (noff < 0) return false;
         for (int i = 0; i < A.n; i++) {
             g.pool[noff + i] = g.pool[A.off + i];
@@ -357,7 +369,7 @@ static __device__ bool merge_coop(Ghm& g, int idA, int idB)
         return g.status == 0;
     }
     uint32_t* skey = g.tmp;
-    uint8_t* sflag = reinterpret_cast<uint8_t*>(g.tmp + g.tmp_cap);
+    uint8_t* sflag = g.tmpf;
     {
         const uint32_t* pa = g.pool + A.off;
         const uint32_t* pb = g.pool + B.off;
@@ -387,7 +399,7 @@ static __device__ bool merge_coop(Ghm& g, int idA, int idB)
         bool ok = true;
         if (n > A.cap) {
             const int ncap = next_cap(n);
-            const int noff = pool_alloc(g, ncap, idA);  // may compact the pool: A/B blocks can move
+            const int noff = pool_alloc(g, ncap, idA, A.orient);  // may compact the pool: A/B blocks can move
             if (noff >= 0) {
                 A.off = noff;
                 A.cap = ncap;
@@ -422,7 +434,7 @@ static __device__ bool insert_coop(Ghm& g, ClusterRec& c, uint32_t key)
     }
     if (tid == 0 && n == c.cap) {
         const int ncap = c.cap * 2;
-        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl));
+        const int noff = pool_alloc(g, ncap, (int)(&c - g.cl), c.orient);
         if (noff >= 0) {
             for (int i = 0; i < n; i++) {
                 g.pool[noff + i] = g.pool[c.off + i];
@@ -548,9 +560,10 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
             int len = 0;
             for (int j = i; j >= 0; j = nxt[j]) len++;
             const int cap = next_cap(len + (len >> 1));
-            const int off = (g.ncl < g.cl_cap) ? pool_alloc(g, cap, g.ncl) : -1;
+            const int nid = g.ncl[o];
+            const int off = (nid < g.cl_hi[o]) ? pool_alloc(g, cap, nid, o) : -1;
             if (off >= 0) {
-                ClusterRec& c = g.cl[g.ncl];
+                ClusterRec& c = g.cl[nid];
                 c.off = off; c.cap = cap; c.n = len;
                 c.mult = -1; c.mnext = -1; c.orient = (unsigned char)o; c.was_twisted = 0; c.dead = 0;
                 c.a = 0; c.b = 0; c.avg_x = 0; c.p = 0;
@@ -563,8 +576,8 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
                     w++;
                 }
                 cm::recompute_sums(c, g.pool);
-                g.bc[o][g.nbc[o]++] = g.ncl;
-                g.ncl++;
+                g.bc[o][g.nbc[o]++] = nid;
+                g.ncl[o] = nid + 1;
                 sh_s[0] = lastj;
             } else {
                 if (!g.status) g.status = 2;  // cluster table full
@@ -573,7 +586,7 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
         }
         __syncthreads();
         if (g.status) return;
-        stats_coop(g, g.cl[g.ncl - 1]);
+        stats_coop(g, g.cl[g.ncl[o] - 1]);
         {
             // repair successor pointers that point into the erased chain
             const int lastj = sh_s[0];
@@ -1156,14 +1169,15 @@ static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
             const int n = g.nk[o];
             for (int i = tid; i < n; i += NT)
                 if (alive[i]) g.tmp[atomicAdd(&sh_s[1], 1)] = key[i];
-            for (int c = 0; c < g.ncl; c++) {
+            // (clusters of orientation o are exactly the ids of region o)
+            for (int c = g.cl_lo[o]; c < g.ncl[o]; c++) {
                 const ClusterRec& cr = g.cl[c];
-                if (cr.dead != 2 || cr.orient != o) continue;
+                if (cr.dead != 2) continue;
                 for (int i = tid; i < cr.n; i += NT) g.tmp[atomicAdd(&sh_s[1], 1)] = g.pool[cr.off + i];
             }
             __syncthreads();
-            for (int c = tid; c < g.ncl; c += NT)
-                if (g.cl[c].dead == 2 && g.cl[c].orient == o) g.cl[c].dead = 1;
+            for (int c = g.cl_lo[o] + tid; c < g.ncl[o]; c += NT)
+                if (g.cl[c].dead == 2) g.cl[c].dead = 1;
             const int m = sh_s[1];
             int mp = 1;
             while (mp < m) mp <<= 1;
@@ -1395,29 +1409,54 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
         __syncthreads();
         const int ti = sh_task;
         if (ti >= n_tasks) break;
-        GhmTask& task = tasks[order[ti]];
+        // queue item = GHM index * 4 + orientation mask: 1 or 2 = that orientation only (the GHM has a
+        // second item for the other one), 3 = both orientations one after the other, 0 = phase 2 only
+        const int item = order[ti];
+        const int my_mask = item & 3;
+        const int my_o = (my_mask == 2) ? 1 : 0;
+        GhmTask& task = tasks[item >> 2];
         const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1], D = D0 + D1;
-        if (tid == 0) {
+        const int half_mask = task.half_mask;
+        const bool run_p1 = my_mask != 0;
+        const double q = prm.q_value;
+        if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
+        // view: phase 1 = this CTA's orientation only (its regions of every shared array),
+        //       phase 2 = the whole GHM
+        auto setup = [&](bool whole, bool fresh) {
             WsLayout L = ws_layout(D, pool_factor);
             uint8_t* base = ws + task.ws_off;
+            const int cc0 = D0 / 3 + 2, pc0 = pool_factor * D0 + 32;
+            const int eo = whole ? 0 : (my_o ? D0 : 0);       // element (dot) offset of the region
+            const int co = whole ? 0 : (my_o ? cc0 : 0);      // cluster-slot offset of the region
             g.key[0] = (uint32_t*)(base + L.key0);
             g.key[1] = (uint32_t*)(base + L.key1);
             g.alive[0] = base + L.alive0;
             g.alive[1] = base + L.alive1;
-            g.nxt = (int*)(base + L.nxt);
+            g.nxt = (int*)(base + L.nxt) + eo;
             g.pool = (uint32_t*)(base + L.pool);
             g.pflag = base + L.pflag;
-            g.pool_cap = L.pool_cap;
-            g.pool_used = 0;
             g.cl = (ClusterRec*)(base + L.cl);
-            g.cl_cap = L.cl_cap;
-            g.ncl = 0;
+            g.cl_lo[0] = 0; g.cl_hi[0] = cc0;
+            g.cl_lo[1] = cc0; g.cl_hi[1] = cc0 + D1 / 3 + 2;
+            g.pool_lo[0] = 0; g.pool_hi[0] = pc0;
+            g.pool_lo[1] = pc0; g.pool_hi[1] = L.pool_cap;
+            for (int r = 0; r < 2; r++) {
+                const bool have = !fresh && ((half_mask >> r) & 1);
+                g.nbc[r] = have ? task.half_nbc[r] : 0;
+                g.ncl[r] = have ? task.half_ncl[r] : g.cl_lo[r];
+                g.pool_used[r] = have ? task.half_pool[r] : g.pool_lo[r];
+            }
+            if (!whole) {  // the other orientation's regions belong to another CTA
+                const int other = my_o ^ 1;
+                g.pool_lo[other] = g.pool_hi[other] = g.pool_used[other] = 0;
+                g.ncl[other] = g.cl_lo[other];
+                g.cl_hi[other] = g.cl_lo[other];
+            }
             g.bc[0] = (int*)(base + L.bc0);
             g.bc[1] = (int*)(base + L.bc1);
-            g.nbc[0] = g.nbc[1] = 0;
-            g.act = (int*)(base + L.act);
-            g.act_next = (int*)(base + L.act_next);
-            g.changed = base + L.changed;
+            g.act = (int*)(base + L.act) + co;
+            g.act_next = (int*)(base + L.act_next) + co;
+            g.changed = base + L.changed + co;
             g.mult = (MultRec*)(base + L.mult);
             g.nmult = 0;
             g.out_mults = (int*)(base + L.out_mults);
@@ -1425,12 +1464,12 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.rb_j = (int*)(base + L.rb_j);
             g.rank = (int*)(base + L.rank);
             g.pos = (int*)(base + L.pos);
-            g.xr = (int2*)(base + L.xr);
-            g.redo = (int*)(base + L.redo);
-            g.dscr = (double*)(base + L.dscr);
-            g.tmp = (uint32_t*)(base + L.tmp);
-            g.tmp_cap = L.tmp_cap;
-            g.status = 0;
+            g.xr = (int2*)(base + L.xr) + co;
+            g.redo = (int*)(base + L.redo) + co;
+            g.dscr = (double*)(base + L.dscr) + 2 * (size_t)eo;
+            g.tmp = (uint32_t*)(base + L.tmp) + eo;
+            g.tmpf = (uint8_t*)((uint32_t*)(base + L.tmp) + L.tmp_cap) + eo;
+            g.status = fresh ? 0 : max(task.half_status[0], task.half_status[1]);
             for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
             g.nk[0] = D0;
             g.nk[1] = D1;
@@ -1438,49 +1477,83 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.cnt[1] = task.cnt[1];
             g.area = (double)task.area;
             g.level = task.level;
-        }
-        __syncthreads();
-        // stage the dots (written once by K1) into the mutable per-GHM matrix
-        {
-            const uint32_t* src = dots + task.dot_off;
-            for (int i = tid; i < D0; i += NT) {
-                g.key[0][i] = src[i];
-                g.alive[0][i] = 1;
+        };
+        // the dots (written once by K1) become the mutable matrix of one orientation
+        auto stage = [&](int o) {
+            const uint32_t* src = dots + task.dot_off + (o ? D0 : 0);
+            const int n = o ? D1 : D0;
+            for (int i = tid; i < n; i += NT) {
+                g.key[o][i] = src[i];
+                g.alive[o][i] = 1;
             }
-            for (int i = tid; i < D1; i += NT) {
-                g.key[1][i] = src[D0 + i];
-                g.alive[1][i] = 1;
-            }
-        }
-        __syncthreads();
-        const double q = prm.q_value;
-        bool ok = true;
-        if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
-        const long long t_begin = clock64();
+        };
         PROF_BEGIN();
-#define CHECK_STATUS()        \
-    __syncthreads();          \
-    if (g.status) ok = false; \
-    if (!ok) break;
-        do {
-            for (int gi = 0; gi < prm.n_gaps && gi < 10 && prm.gaps[gi] > 0 && ok; gi++) {
+        const long long t_begin = clock64();
+        // ---- phase 1 (GHM.cpp:167-184): seed / enrich / join at growing gaps, this orientation
+        if (run_p1) {
+            if (tid == 0) setup(my_mask == 3, true);
+            __syncthreads();
+            for (int o = 0; o < 2; o++)
+                if ((my_mask >> o) & 1) stage(o);
+            __syncthreads();
+            for (int gi = 0; gi < prm.n_gaps && gi < 10 && prm.gaps[gi] > 0 && !g.status; gi++) {
                 const int gap = prm.gaps[gi];
                 for (int o = 0; o < 2; o++) {
+                    if (!((my_mask >> o) & 1)) continue;
                     K::seed_pass(g, gap, o, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(0);
-                    if (g.status) { ok = false; break; }
+                    if (g.status) break;
                     K::enrich_pass(g, gap, o, o, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(1);
-                    if (g.status) { ok = false; break; }
+                    if (g.status) break;
                     K::join_pass(g, gap, o, q, &red, sh_s, prof2);
                     __syncthreads();
                     PROF_END(2);
-                    if (g.status) { ok = false; break; }
+                    if (g.status) break;
                 }
             }
-            if (!ok) break;
+            __syncthreads();
+            if (tid == 0) {
+                for (int o = 0; o < 2; o++) {
+                    if (!((my_mask >> o) & 1)) continue;
+                    task.half_nbc[o] = g.nbc[o];
+                    task.half_ncl[o] = g.ncl[o];
+                    task.half_pool[o] = g.pool_used[o];
+                    task.half_status[o] = g.status;
+                    task.half_cycles[o] = clock64() - t_begin;
+                }
+            }
+        }
+        // ---- hand-over: the CTA that finishes the GHM's last orientation carries on
+        bool last = true;
+        if (task.half_needed > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sh_s[7] = atomicAdd(&task.half_done, 1);
+            __syncthreads();
+            last = (sh_s[7] + 1 == task.half_needed);
+            __threadfence();  // acquire: also drops this SM's L1 lines (the other CTA wrote the rest)
+        }
+        if (tid == 0)
+            for (int k = 0; k < 8; k++) {
+                if (k < 5 && prof[k]) atomicAdd((unsigned long long*)&task.prof[k], (unsigned long long)prof[k]);
+                if (prof2[k]) atomicAdd((unsigned long long*)&task.prof2[k], (unsigned long long)prof2[k]);
+            }
+        __syncthreads();
+        if (!last) continue;
+        // ---- phase 2 (GHM.cpp:186-217): cross-orientation enrichment, filter, metaclustering
+        if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
+        if (tid == 0) setup(true, false);
+        __syncthreads();
+        for (int o = 0; o < 2; o++)
+            if (!((half_mask >> o) & 1)) stage(o);
+        __syncthreads();
+        const long long t_p2 = clock64();
+        pt_ = t_p2;
+        bool ok = (g.status == 0);
+        if (ok) do {
             for (int rep = 0; rep < 2 && ok; rep++) {
                 for (int e = 0; e < 4; e++) {
                     // GHM.cpp:186-189: (cluster, matrix) orientations (0,0) (1,1) (1,0) (0,1)
@@ -1494,7 +1567,9 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                 if (!ok) break;
                 if (rep == 0) {
                     K::filter_pass(g, prm, sh_s);
-                    CHECK_STATUS();
+                    __syncthreads();
+                    if (g.status) ok = false;
+                    if (!ok) break;
                     PROF_END(3);
                 }
             }
@@ -1502,14 +1577,16 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             K::cluster_clusters(g, prm, &red, sh_i, sh_s);
             PROF_END(4);
         } while (false);
-#undef CHECK_STATUS
         __syncthreads();
         if (tid == 0) {
             task.status = ok ? 0 : (g.status ? g.status : 1);
             task.n_mult = ok ? sh_s[0] : 0;
-            task.n_clusters = g.ncl;
-            prof[5] = clock64() - t_begin;
-            for (int k = 0; k < 8; k++) { task.prof[k] = prof[k]; task.prof2[k] = prof2[k]; }
+            task.n_clusters = (g.ncl[0] - g.cl_lo[0]) + (g.ncl[1] - g.cl_lo[1]);
+            // critical path of this GHM: the slower orientation, then phase 2
+            const long long h0 = (half_mask & 1) ? task.half_cycles[0] : 0, h1 = (half_mask & 2) ? task.half_cycles[1] : 0;
+            task.prof[5] = (h0 > h1 ? h0 : h1) + (clock64() - t_p2);
+            for (int k = 0; k < 5; k++)
+                if (prof[k]) atomicAdd((unsigned long long*)&task.prof[k], (unsigned long long)prof[k]);
         }
         __syncthreads();
     }

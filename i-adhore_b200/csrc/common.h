@@ -45,6 +45,13 @@ struct GhmTask {
     int32_t n_clusters;   // out
     int32_t n_aps;        // out
     int32_t pad1;
+    // The two orientations are clustered by two CTAs up to the final enrichment (cluster_kernel.cu):
+    int32_t half_mask;    // in: bit o = orientation o has its own queue item (>= 3 dots)
+    int32_t half_needed;  // in: number of queue items of this GHM (1 or 2)
+    int32_t half_done;    // device: items finished
+    int32_t half_nbc[2], half_ncl[2], half_pool[2], half_status[2];  // device: state handed to phase 2
+    int32_t pad2;
+    long long half_cycles[2];
     long long prof2[8];   // out: join sub-phases (init, reduce, locate, merge, erase, refresh, redo, #merges)
     long long prof[8];    // out: SM cycles per phase (seed, enrich, join, filter, metacluster, total, -, -)
 };
@@ -97,9 +104,14 @@ struct DatasetDev {
     const int32_t* fam;
     const int32_t* gid;
     const int32_t* num_id;
-    uint8_t* flags;             // bit0 strand, bit2 masked
+    uint8_t* flags;             // bit0 strand, bit2 masked, bit3 gene ID occurs more than once in the dataset
     const int32_t* fam_ptr;     // CSR over families: members = global element indices, ascending
     const int32_t* fam_members;
+    // level-2 build (build_kernels.cu): per member slot (same order as fam_members)
+    const uint32_t* mem_y;      // (coordinate inside its list << 1) | strand
+    const int32_t* plus_prefix; // [slot] = members with strand 1 in slots [0, slot)  (n + 1 entries)
+    const int32_t* self_slot;   // per element: its slot in fam_members
+    const int32_t* fam_list;    // [f * (n_lists + 1) + l] = first slot of family f at or after list l; may be null
 };
 
 // Build tiles: <=256 consecutive columns of one GHM.

@@ -201,6 +201,7 @@ struct iadh_ctx {
         int min_dots, nt, per_sm;
     } cls[4] = {{1025, 256, 2}, {193, 128, 4}, {0, 32, 16}, {0, 32, 16}};
     int n_classes = 3;
+    int split_min = 1024;  // both orientations need this many dots to be clustered by separate CTAs
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // dataset (host mirror + device)
     int n_lists = 0;
@@ -209,11 +210,11 @@ struct iadh_ctx {
     std::vector<int32_t> masked_cnt;  // per list
     std::vector<int32_t> index_to_list;
     int n_fam = 0;
-    DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members;
+    DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members, d_mem_y, d_plus_prefix, d_self_slot, d_fam_list;
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
-    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_sel, d_out_off, d_out, d_counter;
+    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_sel, d_out_off, d_out, d_counter;
     DBuf d_pf_col, d_pf_gfam, d_pf_ggid, d_pf_gstrand, d_pf_fam, d_pf_gid, d_pf_num, d_pf_flags;
     HBuf h_tasks, h_misc, h_out, h_pf;
     // build_dots scratch
@@ -455,22 +456,49 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             t.out_bytes = 0;
             t.ws_off = 0;
             t.ws_bytes = 0;
+            t.half_done = 0;
+            t.half_mask = 0;
+            t.half_needed = 1;
+            memset(t.prof, 0, sizeof t.prof);
+            memset(t.prof2, 0, sizeof t.prof2);
             if (D < (int64_t)c->prm.anchor_points || D == 0) continue;
             if (D > 0x0fffffff) return fail(IADH_ERR_CAPACITY, "GHM with %lld dots exceeds the per-GHM limit", (long long)D);
             const WsLayout L = ws_layout((int)D, pool_factor);
             t.ws_off = (int64_t)ws_total;
             t.ws_bytes = (int64_t)L.total;
             ws_total += L.total;
+            // an orientation with fewer than 3 dots cannot seed a cluster: no queue item of its own
+            t.half_mask = (t.cnt[0] >= 3 ? 1 : 0) | (t.cnt[1] >= 3 ? 2 : 0);
+            t.half_needed = 1;
             order.push_back(i);
         }
         std::stable_sort(order.begin(), order.end(), [&tasks](int a, int b) {
             return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1] > (uint64_t)tasks[b].cnt[0] + tasks[b].cnt[1];
         });
         const int n_act = (int)order.size();
+        // queue items: GHM * 4 + orientation mask.  The two orientations of a GHM are independent up to
+        // the final enrichment; when both are heavy they get an item (a CTA) each, the heavier first --
+        // that shortens the critical path of the heaviest GHMs, which is what a call waits for.
+        std::vector<int> items;
+        items.reserve(2 * (size_t)n_act);
+        for (int k = 0; k < n_act; k++) {
+            GhmTask& t = tasks[order[k]];
+            if (t.half_mask == 3 && (int)std::min(t.cnt[0], t.cnt[1]) >= c->split_min) {
+                const int first = (t.cnt[1] > t.cnt[0]) ? 2 : 1;
+                items.push_back(order[k] * 4 + first);
+                items.push_back(order[k] * 4 + (first ^ 3));
+                t.half_needed = 2;
+            } else {
+                items.push_back(order[k] * 4 + t.half_mask);
+                t.half_needed = 1;
+            }
+        }
+        const int n_items = (int)items.size();
         CU(c->d_ws.ensure(ws_total + 256));
         if ((rc = upload(c->d_order, order.data(), 4 * (size_t)n_act, c->st))) return rc;
+        if ((rc = upload(c->d_items, items.data(), 4 * (size_t)n_items, c->st))) return rc;
         CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
-        st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act;
+        st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act + 4 * n_items;
         CU(c->d_counter.ensure(16 + 4 * 1024));  // 4 class queues + per-SM arrival counters
         CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024, c->st));
         trace_mark(c->st, "host: order/ws + uploads");
@@ -480,14 +508,17 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             // wide CTAs and start first, the bulk runs on narrow CTAs (many GHMs in flight per SM --
             // the clustering of one GHM is a dependent chain that keeps about one warp busy)
             int* ctr = c->d_counter.as<int>();
-            const int* ord = c->d_order.as<int>();
+            const int* ord = c->d_items.as<int>();
             CU(cudaEventRecord(c->ev_fork, c->st));
             int begin = 0, launched = 0;
             for (int k = 0; k < c->n_classes; k++) {
+                // classes are cut by the GHM's total dots, so both orientations of a GHM share a class
                 int end = begin;
-                while (end < n_act && ((int64_t)tasks[order[end]].cnt[0] + tasks[order[end]].cnt[1] >= c->cls[k].min_dots ||
-                                       k == c->n_classes - 1))
-                    end++;
+                while (end < n_items) {
+                    const GhmTask& t = tasks[items[end] >> 2];
+                    if ((int64_t)t.cnt[0] + t.cnt[1] >= c->cls[k].min_dots || k == c->n_classes - 1) end++;
+                    else break;
+                }
                 const int cnt = end - begin;
                 if (cnt > 0) {
                     cudaStream_t s = (launched == 0) ? c->st : c->st_side[launched - 1];
@@ -735,7 +766,51 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
         std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
         for (int64_t i = 0; i < total; i++) members[cur[d->fam[i]]++] = (int32_t)i;
     }
+    // level-2 build tables (build_kernels.cu): member records, strand prefix counts, own slot of
+    // every element, duplicate-gene-ID flag, and the (family, list) -> first slot table
+    std::vector<uint32_t> mem_y((size_t)total);
+    std::vector<int32_t> plus_prefix((size_t)total + 1, 0), self_slot((size_t)total);
+    {
+        int l = 0;
+        std::vector<int32_t> elem_list((size_t)total);
+        for (int64_t i = 0; i < total; i++) {
+            while (i >= c->list_off[l + 1]) l++;
+            elem_list[i] = l;
+        }
+        for (int64_t m = 0; m < total; m++) {
+            const int32_t e = members[m];
+            const int strand = c->flags[e] & 1;
+            mem_y[m] = ((uint32_t)(e - c->list_off[elem_list[e]]) << 1) | (uint32_t)strand;
+            plus_prefix[m + 1] = plus_prefix[m] + strand;
+            self_slot[e] = (int32_t)m;
+        }
+        int max_gid = -1;
+        for (int64_t i = 0; i < total; i++) max_gid = std::max(max_gid, d->gid[i]);
+        std::vector<uint8_t> seen((size_t)max_gid + 2, 0);
+        for (int64_t i = 0; i < total; i++)
+            if (d->gid[i] >= 0 && seen[d->gid[i]] < 2) seen[d->gid[i]]++;
+        for (int64_t i = 0; i < total; i++)
+            if (d->gid[i] < 0 || seen[d->gid[i]] > 1) c->flags[i] |= 8;
+    }
+    std::vector<int32_t> fam_list;
+    const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
+    if (tbl > 0 && tbl <= (int64_t)128 << 20) {
+        fam_list.resize((size_t)tbl);
+        for (int f = 0; f < c->n_fam; f++) {
+            int32_t m = fam_ptr[f];
+            int32_t* row = fam_list.data() + (size_t)f * (d->n_lists + 1);
+            for (int l = 0; l <= d->n_lists; l++) {
+                const int64_t lim = (l < d->n_lists) ? c->list_off[l] : total;
+                while (m < fam_ptr[f + 1] && members[m] < lim) m++;
+                row[l] = m;
+            }
+        }
+    }
     int rc = IADH_OK;
+    if (!rc) rc = upload(c->d_mem_y, mem_y.data(), 4 * mem_y.size(), c->st);
+    if (!rc) rc = upload(c->d_plus_prefix, plus_prefix.data(), 4 * plus_prefix.size(), c->st);
+    if (!rc) rc = upload(c->d_self_slot, self_slot.data(), 4 * self_slot.size(), c->st);
+    if (!rc && !fam_list.empty()) rc = upload(c->d_fam_list, fam_list.data(), 4 * fam_list.size(), c->st);
     if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
     if (!rc) rc = upload(c->d_fam, d->fam, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
@@ -753,6 +828,10 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->ds.flags = c->d_flags.as<uint8_t>();
     c->ds.fam_ptr = c->d_fam_ptr.as<int32_t>();
     c->ds.fam_members = c->d_fam_members.as<int32_t>();
+    c->ds.mem_y = c->d_mem_y.as<uint32_t>();
+    c->ds.plus_prefix = c->d_plus_prefix.as<int32_t>();
+    c->ds.self_slot = c->d_self_slot.as<int32_t>();
+    c->ds.fam_list = fam_list.empty() ? nullptr : c->d_fam_list.as<int32_t>();
     sort_lists(c);
     // defaults = shipped datasetI/II settings, Bonferroni (Settings.cpp:4-9)
     memset(&c->prm, 0, sizeof c->prm);
@@ -770,6 +849,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     if (const char* e = getenv("IADH_CTAS_PER_SM")) c->ctas_per_sm = std::max(1, atoi(e));
     for (int k = 0; k < 4; k++) c->prm.coop[k] = 48;
     if (const char* e = getenv("IADH_COOP")) sscanf(e, "%d,%d,%d,%d", &c->prm.coop[0], &c->prm.coop[1], &c->prm.coop[2], &c->prm.coop[3]);
+    if (const char* e = getenv("IADH_SPLIT_MIN")) c->split_min = std::max(3, atoi(e));
     if (const char* e = getenv("IADH_CLASSES")) {  // "min_dots:threads:ctas_per_sm,..." heaviest class first
         int n = 0;
         const char* q = e;
@@ -795,8 +875,8 @@ void iadh_destroy(iadh_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
-    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order,
+    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
                     &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
     for (DBuf* b : bufs) b->release();
@@ -999,6 +1079,40 @@ int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, 
     *cnt_out = c->bd_cnt.data();
     *dots_out = c->bd_dots.data();
     *n_dots_out = total;
+    return IADH_OK;
+}
+
+int iadh_build_only(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    iadh_stats* out)
+{
+    if (!c || !ys || !out || (!p && !xs) || n < 0) return fail(IADH_ERR_ARG, "iadh_build_only: bad argument");
+    CU(cudaSetDevice(c->device));
+    ProfileHost ph;
+    memset(&ph.dev, 0, sizeof ph.dev);
+    memset(out, 0, sizeof *out);
+    int rc;
+    if (p && (rc = upload_profile(c, p, ph, out->h2d_bytes))) return rc;
+    std::vector<GhmTask> tasks((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        init_task(tasks[i]);
+        tasks[i].x_list = p ? -1 : xs[i];
+        tasks[i].y_list = ys[i];
+        if (ys[i] < 0 || ys[i] >= c->n_lists || (!p && (xs[i] < 0 || xs[i] >= c->n_lists)))
+            return fail(IADH_ERR_ARG, "build_only: list out of range");
+        tasks[i].seq = (int32_t)i;
+    }
+    int64_t total = 0;
+    if (n > 0 && (rc = build_stage(c, p != nullptr, ph.dev, tasks, total, *out))) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    out->n_ghm = n;
+    if (n > 0) {
+        float m1 = 0, m2 = 0;
+        cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
+        out->build_ms = m1 + m2;
+        out->cluster_ms = m2;  // (fill pass alone)
+        out->total_ms = m1 + m2;
+    }
     return IADH_OK;
 }
 

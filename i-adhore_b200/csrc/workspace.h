@@ -28,7 +28,7 @@ static inline WsLayout ws_layout(int D, int pool_factor)
         return r;
     };
     const size_t d = (size_t)D;
-    L.cl_cap = D / 3 + 2;
+    L.cl_cap = D / 3 + 4;   // two regions of D_o / 3 + 2 slots (one per orientation)
     L.pool_cap = pool_factor * D + 64;
     int tc = 1;
     while (tc < D) tc <<= 1;
@@ -37,7 +37,7 @@ static inline WsLayout ws_layout(int D, int pool_factor)
     L.key1 = take(4 * d);
     L.alive0 = take(d);
     L.alive1 = take(d);
-    L.nxt = take(4 * d);
+    L.nxt = take(4 * d);      // seed successor pointers; region of orientation 1 starts at D0
     L.pool = take(4 * (size_t)L.pool_cap);
     L.pflag = take((size_t)L.pool_cap);
     L.cl = take(sizeof(ClusterRec) * (size_t)L.cl_cap);

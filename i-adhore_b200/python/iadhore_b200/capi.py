@@ -54,7 +54,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
-           "free_result", "trim", "build_dots", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
+           "free_result", "trim", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
 def gap_sizes(gap_size: int) -> List[int]:
@@ -262,6 +262,19 @@ class Engine:
             k += cn[2 * i + 1]
             out.append((a, b))
         return out
+
+    def build_only(self, xs: Sequence[int], ys: Sequence[int], profile: Optional[Profile] = None) -> dict:
+        """Build kernels alone (dots stay on the device): stats dict with n_dots / build_ms."""
+        xa = np.ascontiguousarray(xs, dtype=np.int32)
+        ya = np.ascontiguousarray(ys, dtype=np.int32)
+        if profile is not None:
+            d, keep = self._pdesc(profile)
+            pd = C.byref(d)
+        else:
+            pd = None
+        st = Stats()
+        self._chk(self._f("build_only")(self.ctx, pd, _p(xa, C.c_int32), _p(ya, C.c_int32), C.c_int64(len(ya)), C.byref(st)))
+        return st.as_dict()
 
     def omxn(self, x: np.ndarray, n: np.ndarray) -> np.ndarray:
         xa = np.ascontiguousarray(x, dtype=np.float64)

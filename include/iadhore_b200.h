@@ -154,6 +154,11 @@ int iadh_build_dots(iadh_ctx* ctx, const iadh_profile_desc* profile, const int32
                     const int32_t* y_list, int64_t n, const int64_t** cnt_out,
                     const int32_t** dots_out, int64_t* n_dots_out);
 
+/* Measurement hook: the build kernels alone for the same arguments, dots left on the device.
+ * out->n_dots, out->build_ms (count + scan + fill), out->cluster_ms = the fill pass alone. */
+int iadh_build_only(iadh_ctx* ctx, const iadh_profile_desc* profile, const int32_t* x_list,
+                    const int32_t* y_list, int64_t n, iadh_stats* out);
+
 /* Host-only scheduling helpers (no GPU needed; what the two drivers above use internally).
  * sizes[l] = remapped length of list l.
  * iadh_plan_lists: DataSet::sortGeneLists order (DataSet.cpp:1088-1105) dealt to n_ranks

@@ -316,6 +316,26 @@ int oracle_build_dots(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* 
     return IADH_OK;
 }
 
+// CPU counterpart of the build-only measurement hook: GHM::buildMatrix / GHMProfile::buildMatrix
+// restated (build_l2 / build_hl), timed on the host; build_ms = wall time of the builds.
+int oracle_build_only(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                      iadh_stats* out)
+{
+    Profile P;
+    if (p) to_profile(p, P);
+    memset(out, 0, sizeof *out);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int64_t i = 0; i < n; i++) {
+        GHMInput g;
+        if (p) build_hl(P, c->lists[ys[i]], g);
+        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g);
+        out->n_dots += (int64_t)(g.dots[0].size() + g.dots[1].size());
+    }
+    out->n_ghm = n;
+    out->build_ms = out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return IADH_OK;
+}
+
 int oracle_omxn(oracle_ctx*, const double* x, const int32_t* n, int64_t count, double* out)
 {
     for (int64_t i = 0; i < count; i++) out[i] = omxn(x[i], n[i]);
