@@ -47,9 +47,61 @@ def workload_config(name: str):
         return synth.config_c3(1.0)
     if name == "c4":
         return synth.config_c4(1.0)
+    if name == "c5":
+        return synth.config_c5(1.0)
+    if name == "d2":
+        return synth.config_d2(1.0)
     if name.startswith("c3s"):
         return synth.config_c3(float(name[3:]))
+    if name.startswith("d2s"):
+        return synth.config_d2(float(name[3:]))
     raise SystemExit(f"unknown workload {name}")
+
+
+def workload_label(name, cfg, n_profiles):
+    n_lists = sum(len(g.list_sizes) if g.list_sizes else g.n_lists for g in cfg.genomes)
+    n_genes = sum(sum(g.list_sizes) if g.list_sizes else g.n_lists * g.genes_per_list for g in cfg.genomes)
+    shape = ("ragged lists with the shipped datasetII list-length distribution" if cfg.genomes[0].list_sizes
+             else f"{cfg.genomes[0].n_lists} lists x {cfg.genomes[0].genes_per_list} genes per genome")
+    return (f"{name}: synthetic {len(cfg.genomes)} genomes, {n_lists} gene lists, {n_genes} genes ({shape}), "
+            f"{cfg.n_families} families; L2 all {n_lists * (n_lists + 1) // 2} pairs + {n_profiles} profile searches per step")
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read+write per launch of a kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py traffic ...); None if absent."""
+    path = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        for k, v in json.load(open(path)).items():
+            if kernel_substr in k:
+                return v
+    except Exception:
+        pass
+    return None
+
+
+def build_roofline_c5(device, peak):
+    """K1 alone on BASELINE config 5 (dense GHMs: 4 genomes x 100k genes, 2,000 families), the
+    shape on which the HBM target of the GHM build is testable."""
+    cfg = synth.config_c5(1.0)
+    ds = ingest.dataset_from_synth(cfg)
+    sizes = np.diff(ds.list_off)
+    xs, ys = capi.plan_pairs(sizes)
+    eng = capi.load_product(ds, device=device)
+    best = None
+    for _ in range(6):   # first calls size the buffers; the dot buffer (89 MB) + tables stream through L2
+        st = eng.build_only(xs, ys)
+        if best is None or st["build_ms"] < best["build_ms"]:
+            best = st
+    eng.close()
+    alg = 5 * int(sizes[xs].sum() + sizes[ys].sum()) + 4 * best["n_dots"]
+    ach = alg / (best["build_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "l2_build_kernel count + tile scan + fill (K1), config 5: 78 list pairs", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("l2_build_kernel<1>"),
+            "algorithmic_bytes_per_launch": alg, "launch_ms": best["build_ms"], "fill_ms": best["cluster_ms"],
+            "dots": best["n_dots"], "anchor_points_per_s": best["n_dots"] / (best["build_ms"] * 1e-3)}
 
 
 class ClockSampler:
@@ -183,6 +235,7 @@ def main():
     ap.add_argument("--profiles", type=int, default=32, help="profile searches per step")
     ap.add_argument("--ref-profiles", type=int, default=4, help="profile searches in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the K1 roofline measurement on config 5")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -190,12 +243,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = workload_config(a.workload)
     ncores = os.cpu_count() or 1
-    config = {"workload": f"{a.workload}: synthetic {len(cfg.genomes)} genomes x {cfg.genomes[0].n_lists} lists x "
-                          f"{cfg.genomes[0].genes_per_list} genes, {cfg.n_families} families; L2 all pairs + "
-                          f"{a.profiles} profile searches per step",
+    config = {"workload": workload_label(a.workload, cfg, a.profiles),
               "gap_size": cfg.gap_size, "cluster_gap": cfg.cluster_gap, "q_value": cfg.q_value,
               "prob_cutoff": cfg.prob_cutoff, "anchor_points": cfg.anchor_points, "mult_hyp": "bonferroni",
-              "l2_flush": "working set per step (dots + per-GHM workspaces, >300 MB) exceeds the 126 MB L2"}
+              "l2_flush": "inputs larger than L2: per-step working set (dot keys + per-GHM clustering workspaces, ~0.5 GB allocated, >126 MB touched) does not fit the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -268,6 +319,7 @@ def main():
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
+    eng.event_record(0)          # CUDA events on the engine's own stream bracket the K steps
     t0 = time.perf_counter()
     units = 0
     launches = 0
@@ -277,14 +329,16 @@ def main():
         units += u
         launches += ln
         all_stats.append(st)
+    eng.event_record(1)
     barrier()
-    dt = time.perf_counter() - t0
+    wall_dt = time.perf_counter() - t0
+    dt = eng.event_elapsed_ms(0, 1) * 1e-3
     clk = clocks.stop()
     # max over ranks of the time, sum of the units
     if dist:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, wall_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt, wall_dt = float(t[0].item()), float(t[1].item())
         u = torch.tensor([units, launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
         units, launches = int(u[0].item()), int(u[1].item())
@@ -335,16 +389,25 @@ def main():
     bd_ms = float(np.mean([s["build_ms"] for s in l2s]))
     ach = b_cluster / (cl_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "cluster_kernel (K2, level-2 launch)", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_cluster,
+            "frac": ach / peak, "traffic": ncu_traffic("cluster_kernel"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_cluster,
             "launch_ms": cl_ms,
             "note": "latency/dependency-bound greedy clustering: its figure of merit is GHM/s, not GB/s (SURVEY 8d)"}
     ach_b = b_build / (bd_ms * 1e-3) / 1e9 if bd_ms > 0 else None
-    roof_build = {"bound": "hbm", "kernel": "build_kernel count+fill (K1, level-2 launch)", "achieved": ach_b, "peak": peak,
+    roof_build = {"bound": "hbm", "kernel": "l2_build_kernel count + tile scan + fill (K1, level-2 launch)", "achieved": ach_b, "peak": peak,
                   "unit": "GB/s", "frac": (ach_b / peak) if ach_b else None, "traffic": None,
                   "algorithmic_bytes_per_launch": b_build, "launch_ms": bd_ms}
     hl_stats = [s for st in all_stats for s in st[1:]]
     l2_ms = float(np.mean([s["total_ms"] for s in l2s]))
     hl_ms = float(np.mean([s["total_ms"] for s in hl_stats])) if hl_stats else None
+
+    roof_c5 = None
+    if world == 1 and not a.no_c5:
+        try:
+            eng.close()
+            roof_c5 = build_roofline_c5(local_rank, peak)
+        except Exception as e:
+            roof_c5 = {"error": str(e)[:200]}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -364,7 +427,8 @@ def main():
             "dtype": "f64+int32", "data": "synthetic", "config": config, "clocks": clk,
             "e2e": {"value": e_units / edt, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
                     "d2h_bytes_per_step": d2h // e_steps, "ms_per_step": 1e3 * edt / e_steps},
-            "gpu_launches": launches, "roofline": roof, "roofline_build": roof_build, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roof, "roofline_build": roof_build, "roofline_build_c5": roof_c5,
+            "cpu_baseline": cpu, "wall_ms_per_step": 1e3 * wall_dt / a.steps,
             "units_per_step": units // a.steps, "l2_pairs_per_s": l2s[0]["n_ghm"] * (world if world > 1 else 1) / (l2_ms * 1e-3),
             "hl_ghm_per_s": (hl_stats[0]["n_ghm"] * world / (hl_ms * 1e-3)) if hl_ms else None,
             "anchor_points_per_s_build": l2s[0]["n_dots"] / (bd_ms * 1e-3) if bd_ms > 0 else None,

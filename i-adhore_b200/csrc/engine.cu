@@ -201,7 +201,8 @@ struct iadh_ctx {
         int min_dots, nt, per_sm;
     } cls[4] = {{1025, 256, 2}, {193, 128, 4}, {0, 32, 16}, {0, 32, 16}};
     int n_classes = 3;
-    int split_min = 1024;  // both orientations need this many dots to be clustered by separate CTAs
+    int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
+    cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // dataset (host mirror + device)
     int n_lists = 0;
@@ -721,6 +722,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&c->user_ev[i]));
     for (int i = 0; i < 3; i++) {
         CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
@@ -886,6 +888,8 @@ void iadh_destroy(iadh_ctx* c)
     c->h_pf.release();
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; i++)
+        if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
     for (int i = 0; i < 3; i++) {
         if (c->st_side[i]) cudaStreamDestroy(c->st_side[i]);
@@ -979,7 +983,9 @@ int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n
     if (rc == IADH_OK) {
         std::vector<int32_t> part;
         list_partition(c, rank, n_ranks, part);
+        static const char* only_list = getenv("IADH_ONLY_LIST");  // profiling aid: one GHMProfile per call
         for (int32_t l : part) {
+            if (only_list && l != atoi(only_list)) continue;
             const unsigned sz = (unsigned)(c->list_off[l + 1] - c->list_off[l]);
             const unsigned masked = (unsigned)c->masked_cnt[l];
             if (sz - masked < (unsigned)c->prm.anchor_points) continue;  // higherLevel.cpp:40-41
@@ -1039,6 +1045,25 @@ void iadh_free_result(iadh_result* r)
     delete r;
 }
 void iadh_trim(void) { g_cache.trim(); }
+
+int iadh_event_record(iadh_ctx* c, int slot)
+{
+    if (!c || slot < 0 || slot >= 4) return fail(IADH_ERR_ARG, "iadh_event_record: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->user_ev[slot], c->st));
+    return IADH_OK;
+}
+int iadh_event_elapsed_ms(iadh_ctx* c, int from_slot, int to_slot, double* ms)
+{
+    if (!c || !ms || from_slot < 0 || from_slot >= 4 || to_slot < 0 || to_slot >= 4)
+        return fail(IADH_ERR_ARG, "iadh_event_elapsed_ms: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->user_ev[to_slot]));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->user_ev[from_slot], c->user_ev[to_slot]));
+    *ms = f;
+    return IADH_OK;
+}
 
 int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
                     const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)

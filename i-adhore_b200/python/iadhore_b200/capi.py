@@ -54,7 +54,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
-           "free_result", "trim", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
+           "free_result", "trim", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
 def gap_sizes(gap_size: int) -> List[int]:
@@ -275,6 +275,14 @@ class Engine:
         st = Stats()
         self._chk(self._f("build_only")(self.ctx, pd, _p(xa, C.c_int32), _p(ya, C.c_int32), C.c_int64(len(ya)), C.byref(st)))
         return st.as_dict()
+
+    def event_record(self, slot: int):
+        self._chk(self._f("event_record")(self.ctx, C.c_int(slot)))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self._chk(self._f("event_elapsed_ms")(self.ctx, C.c_int(a), C.c_int(b), C.byref(ms)))
+        return ms.value
 
     def omxn(self, x: np.ndarray, n: np.ndarray) -> np.ndarray:
         xa = np.ascontiguousarray(x, dtype=np.float64)

@@ -46,6 +46,7 @@ class GenomeSpec:
     genes_per_list: int
     wgd: bool
     seed: int
+    list_sizes: List[int] | None = None  # ragged lists (overrides n_lists x genes_per_list)
 
 
 @dataclass
@@ -102,16 +103,17 @@ def make_genome(cfg: SynthConfig, spec: GenomeSpec) -> List[List[Gene]]:
                 out.append((f, s if rng.unit() < 0.8 else (not s)))
         if rng.unit() < cfg.noise:
             out.append((rng.below(cfg.n_families), bool(rng.next() & 1)))
-    target = spec.n_lists * spec.genes_per_list
+    sizes = list(spec.list_sizes) if spec.list_sizes else [spec.genes_per_list] * spec.n_lists
+    target = sum(sizes)
     while len(out) < target:  # pad with noise genes at random positions
         pos = rng.below(len(out) + 1)
         out.insert(pos, (rng.below(cfg.n_families), bool(rng.next() & 1)))
     out = out[:target]
     lists: List[List[Gene]] = []
     k = 0
-    for li in range(spec.n_lists):
+    for li in range(len(sizes)):
         lst = []
-        for _ in range(spec.genes_per_list):
+        for _ in range(sizes[li]):
             f, s = out[k]
             lst.append((f"{spec.name}g{k:06d}", s, f))
             k += 1
@@ -219,3 +221,33 @@ def config_c5(scale: float = 1.0) -> SynthConfig:
         name="c5" if scale == 1.0 else f"c5s{scale:g}", n_families=fam, n_anc=gpl * 3,
         genomes=[GenomeSpec(f"e{g}", 3, gpl, g % 2 == 0, 3000 + g) for g in range(4)],
         t_tandem=0.3, tandem_gap=10, level_2_only=True)
+
+
+# list lengths (genes per gene list) of the shipped testset/datasetII lists: A. thaliana 7 lists,
+# V. vinifera 35, P. trichocarpa 378 (chromosomes + scaffolds); 104,008 genes in 420 lists.  Only the
+# shape is taken from the reference data set -- its gene families (iADHoRe_PLAZA.table) are not
+# part of the reference tree, so the genes and families are synthetic.
+D2_ATH = [7006, 6306, 5398, 4210, 4105, 117, 86]
+D2_VVI = [10353, 1886, 1867, 1779, 1748, 1729, 1638, 1481, 1409, 1329, 1327, 1237, 1221, 1168, 1135, 1107, 1000, 647,
+          632, 561, 445, 356, 350, 312, 249, 193, 144, 127, 125, 112, 90, 85, 73, 58, 9]
+D2_PTR_HEAD = [3168, 2681, 2337, 1979, 1966, 1849, 1701, 1627, 1433, 1422, 1297, 1286, 1275, 1274, 1215, 1208, 1155,
+               933, 454, 410, 381, 347, 273, 271, 248, 242, 218, 213, 167, 128, 123, 110, 108, 106, 104, 101, 99, 98, 97,
+               96, 94, 88, 87, 84, 83, 80, 78, 76, 73, 72, 71, 70, 69, 68, 67, 65, 63, 62, 61, 59, 57, 57, 55, 54, 53, 51,
+               47, 42, 39, 39, 39, 38, 38, 38, 37, 36, 36, 34, 32, 32, 31, 29, 29, 27, 27, 27, 26, 24, 23, 23, 23, 23, 21,
+               21, 20, 20, 19, 19, 18, 18, 18, 18, 17, 17, 16, 16, 16, 15, 15, 15, 14, 14, 13, 13, 13, 13, 13]
+# (count, length) runs of the remaining scaffolds
+D2_PTR_TAIL = [(7, 12), (6, 11), (10, 10), (14, 9), (17, 8), (29, 7), (37, 6), (52, 5), (89, 4)]
+
+
+def config_d2(scale: float = 1.0) -> SynthConfig:
+    """datasetII-shaped: 3 genomes, 420 ragged lists with the shipped list-length distribution."""
+    ptr = list(D2_PTR_HEAD)
+    for cnt, ln in D2_PTR_TAIL:
+        ptr += [ln] * cnt
+    def sc(v):
+        return [max(3, int(x * scale)) for x in v] if scale != 1.0 else list(v)
+    fam = max(200, int(20000 * scale))
+    return SynthConfig(
+        name="d2" if scale == 1.0 else f"d2s{scale:g}", n_families=fam, n_anc=int(fam * 1.4),
+        genomes=[GenomeSpec("ath", 7, 0, True, 4000, sc(D2_ATH)), GenomeSpec("vvi", 35, 0, False, 4001, sc(D2_VVI)),
+                 GenomeSpec("ptr", 378, 0, True, 4002, sc(ptr))])

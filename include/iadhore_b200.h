@@ -145,6 +145,10 @@ void iadh_free_result(iadh_result* r);
  * cache (contexts are cheap to re-create); iadh_trim returns them to the driver. */
 void iadh_trim(void);
 
+/* Device-side timing for benchmarks: CUDA events on the context's own stream (slots 0..3). */
+int iadh_event_record(iadh_ctx* ctx, int slot);
+int iadh_event_elapsed_ms(iadh_ctx* ctx, int from_slot, int to_slot, double* ms);
+
 /* Test/measurement hook: the dot sets of the build kernels alone (GHM.cpp:34-85 /
  * GHMProfile.cpp:17-59) for explicit L2 pairs or, if profile != NULL, for profile x
  * y_list[i].  Writes per GHM counts cnt[2*i+o] and the concatenated (x,y) int32 pairs

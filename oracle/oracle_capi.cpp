@@ -289,6 +289,20 @@ const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
 int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; return IADH_OK; }
 void oracle_free_result(oracle_result* r) { delete r; }
 void oracle_trim(void) {}
+// host-clock stand-ins of the device event hooks
+static std::chrono::steady_clock::time_point g_ev[4];
+int oracle_event_record(oracle_ctx*, int slot)
+{
+    if (slot < 0 || slot >= 4) return IADH_ERR_ARG;
+    g_ev[slot] = std::chrono::steady_clock::now();
+    return IADH_OK;
+}
+int oracle_event_elapsed_ms(oracle_ctx*, int a, int b, double* ms)
+{
+    if (a < 0 || a >= 4 || b < 0 || b >= 4 || !ms) return IADH_ERR_ARG;
+    *ms = std::chrono::duration<double, std::milli>(g_ev[b] - g_ev[a]).count();
+    return IADH_OK;
+}
 
 static oracle_result g_scratch;
 int oracle_build_dots(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys,

@@ -59,5 +59,23 @@ def report(src, dst):
             fh.write("\n")
 
 
+def traffic(src, dst):
+    """Merge dram__bytes_read.sum + dram__bytes_write.sum per launch (max over the captured launches
+    of each kernel) of an `ncu --set full` report into the JSON bench.py reads (roofline.traffic)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cur = json.load(open(dst)) if os.path.exists(dst) else {}
+    for r in rows[2:]:
+        name = r[ik].replace("void <unnamed>::", "").split("(")[0]
+        b = float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+        cur[name] = max(cur.get(name, 0), int(b)) if os.environ.get("NCU_TRAFFIC_KEEP_MAX") else int(b)
+    json.dump(cur, open(dst, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
