@@ -796,7 +796,8 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     }
     std::vector<int32_t> fam_list;
     const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
-    if (tbl > 0 && tbl <= (int64_t)128 << 20) {
+    // (IADH_NO_FAM_TABLE: test knob for the binary-search fallback used when the table would be too large)
+    if (tbl > 0 && tbl <= (int64_t)128 << 20 && !getenv("IADH_NO_FAM_TABLE")) {
         fam_list.resize((size_t)tbl);
         for (int f = 0; f < c->n_fam; f++) {
             int32_t m = fam_ptr[f];

@@ -234,3 +234,80 @@ def test_c3_full_size_properties(scale):
             assert (np.corrcoef(x, y)[0, 1] > 0) == bool(c.orient)
     assert nap == r.stats["n_anchorpoints"] and len(ms) == r.stats["n_multiplicons"]
     gpu.close()
+
+
+def _dup_id_dataset(seed=5):
+    """Small lists where gene IDs repeat inside a list and across lists (the reference compares ID
+    strings, GHM.cpp:68 / Gene.cpp:20): exercises the per-lane slow path of the level-2 build."""
+    rng = np.random.RandomState(seed)
+    sizes = [180, 150, 1, 0, 120]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(off[-1])
+    fam = rng.randint(0, 25, n).astype(np.int32)          # high-copy families: dense GHMs
+    gid = np.arange(n, dtype=np.int32)
+    dup = rng.choice(n, 60, replace=False)
+    gid[dup] = gid[rng.choice(n, 60)]                      # same ID in several places (same or other family)
+    fam[dup[:30]] = fam[gid[dup[:30]]]                     # ... and half of them homologous to their namesake
+    flags = rng.randint(0, 2, n).astype(np.uint8)
+    return capi.Dataset(off, fam, gid, np.arange(n, dtype=np.int32) + 1000, flags)
+
+
+@pytest.mark.parametrize("no_table", [False, True])
+def test_build_with_duplicate_gene_ids(no_table, monkeypatch):
+    ds = _dup_id_dataset()
+    if no_table:
+        monkeypatch.setenv("IADH_NO_FAM_TABLE", "1")
+    gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+    xs, ys = capi.plan_pairs(np.diff(ds.list_off))
+    dg, dc = gpu.build_dots(xs, ys), cpu.build_dots(xs, ys)
+    assert sum(len(a) + len(b) for a, b in dc) > 2000
+    for (a0, a1), (b0, b1) in zip(dg, dc):
+        assert np.array_equal(a0, b0) and np.array_equal(a1, b1)
+    st = gpu.build_only(xs, ys)
+    assert st["n_dots"] == sum(len(a) + len(b) for a, b in dc) and st["build_ms"] > 0
+    for e in (gpu, cpu):
+        e.set_params(mult_hyp=capi.MH_NONE, prob_cutoff=0.9)
+    assert capi.compare_packed(gpu.level2_all_pairs().bytes, cpu.level2_all_pairs().bytes, pl.P_RTOL) is None
+    gpu.close()
+
+
+def test_dense_build_matches_oracle():
+    """BASELINE config 5 shape at 3 % scale (tandem-rich, >= 50 members per family): dots of every
+    list pair, both orientations, in the reference's (x, y) order."""
+    cfg = synth.config_c5(0.03)
+    ds = ingest.dataset_from_synth(cfg)
+    gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+    xs, ys = capi.plan_pairs(np.diff(ds.list_off))
+    dg, dc = gpu.build_dots(xs, ys), cpu.build_dots(xs, ys)
+    assert sum(len(a) + len(b) for a, b in dc) > 100000
+    for (a0, a1), (b0, b1) in zip(dg, dc):
+        assert np.array_equal(a0, b0) and np.array_equal(a1, b1)
+    gpu.close()
+
+
+@pytest.mark.parametrize("split_min", ["3", "1000000"])
+def test_orientation_split_is_invisible(split_min, monkeypatch):
+    """The two orientations of a GHM may be clustered by two CTAs (IADH_SPLIT_MIN): same bytes."""
+    tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
+    monkeypatch.setenv("IADH_SPLIT_MIN", split_min)
+    gpu = capi.load_product(tr.dataset)
+    errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL)
+    gpu.close()
+    assert not errs, errs[:3]
+    cfg = synth.config_small(seed=41)
+    ds, gpu, cpu = _pair(cfg, capi.MH_BONFERRONI)
+    assert gpu.level2_all_pairs().bytes == cpu.level2_all_pairs().bytes
+    gpu.close()
+
+
+def test_event_hooks_time_the_engine_stream():
+    tr = read_trace(pl.golden_traces()[0])
+    gpu = capi.load_product(tr.dataset)
+    gpu.event_record(0)
+    r = gpu.level2_all_pairs()
+    gpu.event_record(1)
+    ms = gpu.event_elapsed_ms(0, 1)
+    assert ms >= r.stats["cluster_ms"] > 0
+    with pytest.raises(RuntimeError):
+        gpu.event_record(9)
+    gpu.close()
