@@ -64,6 +64,7 @@ struct Ghm {
     double* dscr;   // 2 doubles per anchor point: terms of the ordered mrss / var_x sums
     uint32_t* tmp;
     uint8_t* tmpf;  // staging flags, parallel to tmp
+    int scratch_cap;  // entries of tmp / doubles of dscr usable as whole-GHM scratch (phase 2)
     int status;
     int coop[4];
     // task constants
@@ -1123,12 +1124,82 @@ static __device__ void block_bitonic(uint32_t* a, int m)
         }
 }
 
+// BaseCluster::calculateProbability by one warp: the factors 1 - pow(1 - density, ceil(dpd^2 / 2)) of
+// consecutive backbone points are independent (each a ~400-cycle libm-exact pow), only their product
+// is ordered.  Lanes compute the factors into `fac`, lane 0 multiplies them in backbone order --
+// the same sequence of roundings as the reference's running product.  `bb` / `fac` = this cluster's
+// scratch slices (c.n entries each).
+static __device__ void calc_probability_warp(Ghm& g, ClusterRec& c, uint32_t* bb, double* fac)
+{
+    const int lane = VTID & 31;
+    const double density = (double)g.cnt[c.orient] / g.area;
+    const uint32_t* ap = g.pool + c.off;
+    const uint8_t* fl = g.pflag + c.off;
+    int m = 0;  // backbone points, in multiset order
+    for (int i0 = 0; i0 < c.n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = (i < c.n) && fl[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) bb[m + __popc(bal & ((1u << lane) - 1u))] = ap[i];
+        m += __popc(bal);
+    }
+    __syncwarp();
+    for (int j = 1 + lane; j < m; j += 32) {
+        const uint32_t a = bb[j - 1], b = bb[j];
+        const double distance = cm::dpd_d(KEY_X(a), KEY_Y(a), KEY_X(b), KEY_Y(b));
+        const int cc = (int)ceil(0.5 * distance * distance);
+        fac[j] = 1.0 - cm::pow_ref(1.0 - density, cc);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double probability = 1.0;
+        for (int j = 1; j < m; j++) probability *= fac[j];
+        c.p = probability;
+        // duplicates of the first AP are erased without touching the statistics
+        const uint32_t f = g.pool[c.off];
+        int w = 1;
+        for (int i = 1; i < c.n; i++) {
+            const uint32_t k = g.pool[c.off + i];
+            if (k == f) continue;
+            if (w != i) {
+                g.pool[c.off + w] = k;
+                g.pflag[c.off + w] = g.pflag[c.off + i];
+            }
+            w++;
+        }
+        if (w != c.n) {
+            c.n = w;
+            cm::recompute_sums(c, g.pool);
+        }
+    }
+    __syncwarp();
+}
+
 // GHM::filterBaseClusters / BF / FDR (GHM.cpp:446-540)
 static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
 {
-    const int tid = VTID;
-    for (int o = 0; o < 2; o++)
-        for (int i = tid; i < g.nbc[o]; i += NT) calc_probability(g, g.cl[g.bc[o][i]]);
+    const int tid = VTID, warp = tid >> 5;
+    // scratch slice of every cluster: exclusive prefix of the cluster sizes (staged in `redo`)
+    if (tid == 0) {
+        int run = 0, k = 0;
+        for (int o = 0; o < 2; o++)
+            for (int i = 0; i < g.nbc[o]; i++) {
+                g.redo[k++] = run;
+                run += g.cl[g.bc[o][i]].n;
+            }
+        sh_s[5] = run;
+    }
+    __syncthreads();
+    if (sh_s[5] <= g.scratch_cap) {
+        const int n0 = g.nbc[0], nall = g.nbc[0] + g.nbc[1];
+        for (int k = warp; k < nall; k += NW) {
+            ClusterRec& c = g.cl[k < n0 ? g.bc[0][k] : g.bc[1][k - n0]];
+            calc_probability_warp(g, c, g.tmp + g.redo[k], g.dscr + g.redo[k]);
+        }
+    } else {  // (duplicated dots beyond the scratch capacity: one thread per cluster)
+        for (int o = 0; o < 2; o++)
+            for (int i = tid; i < g.nbc[o]; i += NT) calc_probability(g, g.cl[g.bc[o][i]]);
+    }
     __syncthreads();
     for (int o = 0; o < 2; o++) {
         if (prm.mult_hyp == 2) {
@@ -1469,6 +1540,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             g.dscr = (double*)(base + L.dscr) + 2 * (size_t)eo;
             g.tmp = (uint32_t*)(base + L.tmp) + eo;
             g.tmpf = (uint8_t*)((uint32_t*)(base + L.tmp) + L.tmp_cap) + eo;
+            g.scratch_cap = whole ? D : 0;
             g.status = fresh ? 0 : max(task.half_status[0], task.half_status[1]);
             for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
             g.nk[0] = D0;
