@@ -33,6 +33,8 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
                        const int64_t* tile_prefix, int64_t n_tiles, const uint32_t* tile_off, uint32_t* keys,
                        int sm_count, cudaStream_t st);
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
+void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
+                   const uint8_t* flags, int gap, int64_t total, uint8_t* remapped, int32_t* t3, cudaStream_t st);
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
                     const DevParams& prm, int pool_factor, int* sm_slot, int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
@@ -1140,6 +1142,48 @@ int iadh_build_only(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, 
         out->total_ms = m1 + m2;
     }
     return IADH_OK;
+}
+
+int iadh_remap_tandems(const iadh_dataset_desc* d, int32_t tandem_gap, int device, uint8_t* remapped_out)
+{
+    if (!d || !remapped_out || d->n_lists < 0 || tandem_gap < 0 || (d->n_lists > 0 && (!d->list_off || !d->fam || !d->gid || !d->flags)))
+        return fail(IADH_ERR_ARG, "iadh_remap_tandems: bad argument");
+    const int64_t total = d->n_lists ? d->list_off[d->n_lists] : 0;
+    if (total == 0) return IADH_OK;
+    if (total >= 0x7fffffff) return fail(IADH_ERR_CAPACITY, "more than 2^31 elements");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(IADH_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    std::vector<int32_t> elem_list((size_t)total);
+    for (int l = 0; l < d->n_lists; l++) {
+        if (d->list_off[l + 1] < d->list_off[l]) return fail(IADH_ERR_ARG, "list %d has negative size", l);
+        for (int64_t i = d->list_off[l]; i < d->list_off[l + 1]; i++) elem_list[i] = l;
+    }
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DBuf b_off, b_el, b_fam, b_gid, b_fl, b_rem, b_t3;
+    int rc = IADH_OK;
+    if (!rc) rc = upload(b_off, d->list_off, 8 * (size_t)(d->n_lists + 1), st);
+    if (!rc) rc = upload(b_el, elem_list.data(), 4 * (size_t)total, st);
+    if (!rc) rc = upload(b_fam, d->fam, 4 * (size_t)total, st);
+    if (!rc) rc = upload(b_gid, d->gid, 4 * (size_t)total, st);
+    if (!rc) rc = upload(b_fl, d->flags, (size_t)total, st);
+    if (!rc && b_rem.ensure((size_t)total) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
+    if (!rc && b_t3.ensure(4 * (size_t)total) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
+    if (!rc) {
+        launch_tandem(b_off.as<int64_t>(), d->n_lists, b_el.as<int32_t>(), b_fam.as<int32_t>(), b_gid.as<int32_t>(),
+                      b_fl.as<uint8_t>(), tandem_gap, total, b_rem.as<uint8_t>(), b_t3.as<int32_t>(), st);
+        if (cudaMemcpyAsync(remapped_out, b_rem.p, (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail(IADH_ERR_CUDA, "tandem remapping failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaStreamSynchronize(st);
+    DBuf* bufs[] = {&b_off, &b_el, &b_fam, &b_gid, &b_fl, &b_rem, &b_t3};
+    for (DBuf* b : bufs) b->release();
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 int iadh_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out)

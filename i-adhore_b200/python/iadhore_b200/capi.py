@@ -52,7 +52,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
+EXPORTS = ["remap_tandems", "create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
            "free_result", "trim", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
@@ -330,6 +330,27 @@ def plan_lists(sizes: Sequence[int], rank: int = 0, n_ranks: int = 1, lib_path: 
     if rc:
         raise RuntimeError("plan_lists failed")
     return out[:cnt.value].copy()
+
+
+def remap_tandems(list_off, fam, gid, strand, tandem_gap: int, device: int = 0, lib_path: str = PRODUCT_LIB,
+                  prefix: str = "iadh_") -> np.ndarray:
+    """GeneList::remapTandemsFamily for every list (elements BEFORE remapping): the `remapped` flag
+    per element.  Product library: on the device; oracle library: sequential restatement."""
+    if not os.path.exists(lib_path):
+        raise RuntimeError(f"{lib_path} is missing: build it first")
+    lib = C.CDLL(lib_path)
+    lo = np.ascontiguousarray(list_off, dtype=np.int64)
+    fa = np.ascontiguousarray(fam, dtype=np.int32)
+    gi = np.ascontiguousarray(gid, dtype=np.int32)
+    fl = np.ascontiguousarray(strand, dtype=np.uint8)
+    d = DatasetDesc(len(lo) - 1, _p(lo, C.c_int64), _p(fa, C.c_int32), _p(gi, C.c_int32), _p(gi, C.c_int32), _p(fl, C.c_uint8))
+    out = np.zeros(len(fa), np.uint8)
+    rc = getattr(lib, prefix + "remap_tandems")(C.byref(d), C.c_int32(tandem_gap), C.c_int(device), _p(out, C.c_uint8))
+    if rc:
+        f = getattr(lib, prefix + "last_error")
+        f.restype = C.c_char_p
+        raise RuntimeError(f"{prefix}remap_tandems failed ({rc}): {f().decode()}")
+    return out.astype(bool)
 
 
 def load_product(ds: Dataset, device: int = 0) -> Engine:

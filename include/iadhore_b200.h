@@ -101,6 +101,14 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
 } iadh_stats;
 
+/* Replaces: DataSet::remapTandems (DataSet.cpp:204-213) -> GeneList::remapTandemsFamily
+ * (GeneList.cpp:143-200) with Gene::remapTo (Gene.cpp:51-62), family mode, on the device.
+ * `lists` describes the gene lists BEFORE remapping (GeneList::getElements() in order; num_id is
+ * ignored, flags = IADH_F_STRAND).  remapped_out[i] = Gene::isRemapped() of element i afterwards;
+ * the remapped lists handed to iadh_create are the elements with remapped_out == 0, in order. */
+int iadh_remap_tandems(const iadh_dataset_desc* lists, int32_t tandem_gap, int device,
+                       uint8_t* remapped_out);
+
 /* Replaces: DataSet ownership of the flattened lists; called once after
  * DataSet::sortGeneLists() (iADHoRe.cpp:75).  `device` = CUDA ordinal. */
 int iadh_create(const iadh_dataset_desc* ds, int device, iadh_ctx** out);

@@ -289,6 +289,42 @@ const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
 int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; return IADH_OK; }
 void oracle_free_result(oracle_result* r) { delete r; }
 void oracle_trim(void) {}
+
+// GeneList::remapTandemsFamily (GeneList.cpp:143-200), restated sequentially: the three passes in
+// the reference's order, remapTo() (Gene.cpp:51-62) sets the gene's flag and clears the target's.
+int oracle_remap_tandems(const iadh_dataset_desc* d, int32_t gap, int, uint8_t* r)
+{
+    for (int l = 0; l < d->n_lists; l++) {
+        const int64_t b = d->list_off[l], e = d->list_off[l + 1];
+        const int n = (int)(e - b);
+        const int32_t* fam = d->fam + b;
+        const int32_t* gid = d->gid + b;
+        const uint8_t* fl = d->flags + b;
+        uint8_t* rem = r + b;
+        for (int i = 0; i < n; i++) rem[i] = 0;
+        auto pair = [&](int i, int j) { return fam[i] == fam[j] && gid[i] != gid[j]; };
+        for (int i = n - 1; i > 0; i--) {           // '+' onto earlier '+'
+            if (!(fl[i] & 1)) continue;
+            for (int j = i - 1; j >= 0 && i - j <= gap + 1; j--) {
+                if (!(fl[j] & 1)) continue;
+                if (pair(i, j)) { rem[i] = 1; rem[j] = 0; break; }
+            }
+        }
+        for (int i = 0; i < n - 1; i++) {           // '-' onto later '-'
+            if (fl[i] & 1) continue;
+            for (int j = i + 1; j < n && j - i <= gap + 1; j++) {
+                if (fl[j] & 1) continue;
+                if (pair(i, j)) { rem[i] = 1; rem[j] = 0; break; }
+            }
+        }
+        for (int i = n - 1; i > 0; i--) {           // anything still unremapped onto any earlier gene
+            if (rem[i]) continue;
+            for (int j = i - 1; j >= 0 && i - j <= gap + 1; j--)
+                if (pair(i, j)) { rem[i] = 1; rem[j] = 0; break; }
+        }
+    }
+    return IADH_OK;
+}
 // host-clock stand-ins of the device event hooks
 static std::chrono::steady_clock::time_point g_ev[4];
 int oracle_event_record(oracle_ctx*, int slot)

@@ -311,3 +311,28 @@ def test_event_hooks_time_the_engine_stream():
     with pytest.raises(RuntimeError):
         gpu.event_record(9)
     gpu.close()
+
+
+def test_device_tandem_remap_matches_reference_and_oracle():
+    """iadh_remap_tandems (GeneList.cpp:143-200 on the device) against the reference's own flags in
+    the golden traces, and against the oracle on tandem-rich lists (config 5 shape, tandem_gap 10)
+    plus ragged / empty / single-gene lists and repeated gene IDs."""
+    for path in pl.golden_traces():
+        tr = read_trace(path)
+        off = np.concatenate([[0], np.cumsum([len(r) for r in tr.raw_lists])]).astype(np.int64)
+        cat = lambda k: np.concatenate([r[k] for r in tr.raw_lists])
+        got = capi.remap_tandems(off, cat("fam"), cat("gid"), cat("strand"), tr.params["tandem_gap"])
+        assert np.array_equal(got, cat("remapped").astype(bool)), path
+    cfg = synth.config_c5(0.1)
+    data = synth.generate(cfg)
+    lists = [lst for g in cfg.genomes for lst in data[g.name]] + [[], [("solo", True, 0)]]
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    fam = np.array([g[2] for l in lists for g in l], np.int32)
+    strand = np.array([g[1] for l in lists for g in l], np.uint8)
+    gid = np.arange(len(fam), dtype=np.int32)
+    gid[5::97] = gid[4::97][:len(gid[5::97])]          # neighbours sharing one gene ID never pair
+    for gap in (0, 1, 10, 15):
+        got = capi.remap_tandems(off, fam, gid, strand, gap)
+        want = capi.remap_tandems(off, fam, gid, strand, gap, lib_path=capi.ORACLE_LIB, prefix="oracle_")
+        assert np.array_equal(got, want), gap
+    assert want.sum() > 1000

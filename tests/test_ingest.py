@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import parity_lib as pl
-from iadhore_b200 import ingest, synth
+from iadhore_b200 import capi, ingest, synth
 from trace_io import read_trace
 
 
@@ -39,3 +39,32 @@ def test_generator_is_deterministic():
     assert a == b
     r = synth.SplitMix64(1234567)
     assert [r.next() for _ in range(3)] == [6457827717110365317, 3203168211198807973, 9817491932198370423]
+
+
+def _raw(tr):
+    off = np.concatenate([[0], np.cumsum([len(r) for r in tr.raw_lists])]).astype(np.int64)
+    cat = lambda k: np.concatenate([r[k] for r in tr.raw_lists])
+    return off, cat("fam"), cat("gid"), cat("strand"), cat("remapped").astype(bool)
+
+
+@pytest.mark.parametrize("path", pl.golden_traces(), ids=lambda p: p.split("/")[-1].split(".")[0])
+def test_oracle_tandem_remap_matches_reference(path):
+    """oracle_remap_tandems (the checker of the device kernel) against the reference's own flags."""
+    tr = read_trace(path)
+    off, fam, gid, strand, ref = _raw(tr)
+    got = capi.remap_tandems(off, fam, gid, strand, tr.params["tandem_gap"], lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    assert np.array_equal(got, ref)
+
+
+def test_oracle_tandem_remap_matches_python_mirror_on_tandem_rich_lists():
+    cfg = synth.config_c5(0.02)
+    data = synth.generate(cfg)
+    lists = [lst for g in cfg.genomes for lst in data[g.name]]
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    fam = np.array([g[2] for l in lists for g in l], np.int32)
+    strand = np.array([g[1] for l in lists for g in l], np.uint8)
+    gid = np.arange(len(fam), dtype=np.int32)
+    got = capi.remap_tandems(off, fam, gid, strand, cfg.tandem_gap, lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    want = np.concatenate([ingest.remap_tandems_family(fam[a:b].tolist(), gid[a:b].tolist(), strand[a:b].astype(bool).tolist(),
+                                                        cfg.tandem_gap) for a, b in zip(off[:-1], off[1:])])
+    assert got.sum() > 100 and np.array_equal(got, want)
