@@ -194,9 +194,14 @@ __global__ void __launch_bounds__(256) l2_build_kernel(DatasetDev ds, GhmTask* _
 {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
+    // every warp owns a contiguous block of tiles: the owning GHM is searched once, then advanced
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
-        const int g = find_ghm(tile_prefix, n_ghm, t);
+    const int64_t per_warp = (n_tiles + warps_total - 1) / warps_total;
+    const int64_t t_begin = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * per_warp;
+    const int64_t t_end = (t_begin + per_warp < n_tiles) ? t_begin + per_warp : n_tiles;
+    int g = (t_begin < n_tiles) ? find_ghm(tile_prefix, n_ghm, t_begin) : 0;
+    for (int64_t t = t_begin; t < t_end; t++) {
+        while (t >= tile_prefix[g + 1]) g++;
         const int x_list = tasks[g].x_list, y_list = tasks[g].y_list;
         const int x0 = (int)(t - tile_prefix[g]) * 32;
         const int64_t yoff = ds.list_off[y_list];
@@ -220,52 +225,67 @@ __global__ void __launch_bounds__(256) l2_build_kernel(DatasetDev ds, GhmTask* _
             continue;
         }
         if (t0 + t1 == 0) continue;
-        const int64_t dot_off = tasks[g].dot_off;
-        const int64_t base0 = dot_off + tile_off[2 * t];
-        const int64_t base1 = dot_off + tasks[g].cnt[0] + tile_off[2 * t + 1];
+        // offsets inside this GHM's key block stay 32-bit (a GHM holds < 2^28 dots)
+        uint32_t* __restrict__ kb = keys + tasks[g].dot_off;
+        const int base0 = (int)tile_off[2 * t];
+        const int base1 = (int)(tasks[g].cnt[0] + tile_off[2 * t + 1]);
         // slow columns: the lane walks its own range
         if (r.slow) {
             const int gx = ds.gid[(int)(xoff + x)];
-            int64_t o0 = base0 + e0, o1 = base1 + e1;
+            int o0 = base0 + e0, o1 = base1 + e1;
             for (int m = r.lo; m < r.hi; m++) {
                 if (ds.gid[ds.fam_members[m]] == gx) continue;
                 const uint32_t my = ds.mem_y[m];
                 const uint32_t key = MAKE_KEY(x, my >> 1);
-                if ((int)(my & 1u) == r.sx) keys[o1++] = key;
-                else keys[o0++] = key;
+                if ((int)(my & 1u) == r.sx) kb[o1++] = key;
+                else kb[o0++] = key;
             }
         }
-        // fast columns: candidates of the whole tile, spread over the lanes
+        // fast columns: groups of W lanes take one column each (W = the power of two below the tile's
+        // mean candidates per column), so a group reads its column's member records coalesced and
+        // writes the column's two key runs in order; no per-candidate search.  W = 1 (sparse tiles)
+        // degenerates to one lane per column, W = 32 to the whole warp per column.
         const int len = r.slow ? 0 : r.hi - r.lo;
         int total;
-        const int ex = warp_excl_scan(len, lane, total);
-        const int incl = ex + len;
+        warp_excl_scan(len, lane, total);
+        if (total == 0) continue;
+        int W = 1;
+        while (W < 32 && 2 * W <= (total >> 5)) W <<= 1;
+        const int R = 32 / W;
+        const int sub = lane & (W - 1), grp = lane / W;
         const int pp_lo = ds.plus_prefix[r.lo];
-        for (int k0 = 0; k0 < total; k0 += 32) {
-            const int k = k0 + lane;
-            // column of candidate k = number of lanes whose inclusive prefix is <= k
-            int c = 0;
-#pragma unroll
-            for (int sft = 16; sft; sft >>= 1) {
-                const int v = __shfl_sync(full, incl, (c + sft - 1) & 31);
-                if (v <= k) c += sft;
-            }
-            c &= 31;
-            const int c_ex = __shfl_sync(full, ex, c);
+        for (int cb = 0; cb < 32; cb += R) {
+            const int c = cb + grp;
+            const int c_len = __shfl_sync(full, len, c);
+            const int maxlen = __reduce_max_sync(full, c_len);
+            if (maxlen == 0) continue;
             const int c_lo = __shfl_sync(full, r.lo, c);
             const int c_pp = __shfl_sync(full, pp_lo, c);
             const int c_sx = __shfl_sync(full, r.sx, c);
-            const int c_e0 = __shfl_sync(full, e0, c);
-            const int c_e1 = __shfl_sync(full, e1, c);
-            if (k < total) {
-                const int m = c_lo + (k - c_ex);
+            const int c_b0 = base0 + __shfl_sync(full, e0, c);
+            const int c_b1 = base1 + __shfl_sync(full, e1, c);
+            const uint32_t xkey = (uint32_t)(x0 + c) << 16;
+            // two candidates per lane and trip: both record loads are in flight before either is used
+            for (int k = sub; k < c_len; k += 2 * W) {
+                const int k2 = k + W;
+                const bool two = k2 < c_len;
+                const int m = c_lo + k;
                 const uint32_t my = ds.mem_y[m];
-                const int plus_before = ds.plus_prefix[m] - c_pp;
-                const int sy = (int)(my & 1u);
-                const int rank = sy ? plus_before : (m - c_lo) - plus_before;
-                const uint32_t key = MAKE_KEY(x0 + c, my >> 1);
-                if (sy == c_sx) keys[base1 + c_e1 + rank] = key;
-                else keys[base0 + c_e0 + rank] = key;
+                const int pp = ds.plus_prefix[m];
+                const uint32_t my2 = two ? ds.mem_y[m + W] : 0u;
+                const int pp2 = two ? ds.plus_prefix[m + W] : 0;
+                {
+                    const int plus_before = pp - c_pp;
+                    const int sy = (int)(my & 1u);
+                    const int rank = sy ? plus_before : k - plus_before;
+                    kb[((sy == c_sx) ? c_b1 : c_b0) + rank] = xkey | (my >> 1);
+                }
+                if (two) {
+                    const int plus_before = pp2 - c_pp;
+                    const int sy = (int)(my2 & 1u);
+                    const int rank = sy ? plus_before : k2 - plus_before;
+                    kb[((sy == c_sx) ? c_b1 : c_b0) + rank] = xkey | (my2 >> 1);
+                }
             }
         }
     }
@@ -361,6 +381,24 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const int64_t* __restric
     }
 }
 
+// (family, list) -> first slot of the family at or after the list (built once per dataset)
+__global__ void __launch_bounds__(128) fam_list_kernel(const int32_t* __restrict__ fam_ptr,
+                                                       const int32_t* __restrict__ members,
+                                                       const int64_t* __restrict__ list_off, int n_fam, int n_lists,
+                                                       int64_t total, int32_t* __restrict__ table)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_fam) return;
+    int m = fam_ptr[f];
+    const int end = fam_ptr[f + 1];
+    int32_t* row = table + (size_t)f * (n_lists + 1);
+    for (int l = 0; l <= n_lists; l++) {
+        const int64_t lim = (l < n_lists) ? list_off[l] : total;
+        while (m < end && members[m] < lim) m++;
+        row[l] = m;
+    }
+}
+
 // GeneList::mask (GeneList.cpp:283-287)
 __global__ void mask_kernel(uint8_t* flags, int64_t begin, int64_t end, int set)
 {
@@ -414,4 +452,11 @@ void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream
     int64_t n = end - begin + 1;
     if (n <= 0) return;
     mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, begin, end, set);
+}
+
+void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64_t* list_off, int n_fam, int n_lists,
+                     int64_t total, int32_t* table, cudaStream_t st)
+{
+    if (n_fam == 0) return;
+    fam_list_kernel<<<(n_fam + 127) / 128, 128, 0, st>>>(fam_ptr, members, list_off, n_fam, n_lists, total, table);
 }

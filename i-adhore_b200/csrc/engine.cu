@@ -33,6 +33,8 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
                        const int64_t* tile_prefix, int64_t n_tiles, const uint32_t* tile_off, uint32_t* keys,
                        int sm_count, cudaStream_t st);
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
+void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64_t* list_off, int n_fam, int n_lists,
+                     int64_t total, int32_t* table, cudaStream_t st);
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
                    const uint8_t* flags, int gap, int64_t total, uint8_t* remapped, int32_t* t3, cudaStream_t st);
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
@@ -796,26 +798,13 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
         for (int64_t i = 0; i < total; i++)
             if (d->gid[i] < 0 || seen[d->gid[i]] > 1) c->flags[i] |= 8;
     }
-    std::vector<int32_t> fam_list;
-    const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
     // (IADH_NO_FAM_TABLE: test knob for the binary-search fallback used when the table would be too large)
-    if (tbl > 0 && tbl <= (int64_t)128 << 20 && !getenv("IADH_NO_FAM_TABLE")) {
-        fam_list.resize((size_t)tbl);
-        for (int f = 0; f < c->n_fam; f++) {
-            int32_t m = fam_ptr[f];
-            int32_t* row = fam_list.data() + (size_t)f * (d->n_lists + 1);
-            for (int l = 0; l <= d->n_lists; l++) {
-                const int64_t lim = (l < d->n_lists) ? c->list_off[l] : total;
-                while (m < fam_ptr[f + 1] && members[m] < lim) m++;
-                row[l] = m;
-            }
-        }
-    }
+    const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
+    const bool have_table = tbl > 0 && tbl <= ((int64_t)128 << 20) && !getenv("IADH_NO_FAM_TABLE");
     int rc = IADH_OK;
     if (!rc) rc = upload(c->d_mem_y, mem_y.data(), 4 * mem_y.size(), c->st);
     if (!rc) rc = upload(c->d_plus_prefix, plus_prefix.data(), 4 * plus_prefix.size(), c->st);
     if (!rc) rc = upload(c->d_self_slot, self_slot.data(), 4 * self_slot.size(), c->st);
-    if (!rc && !fam_list.empty()) rc = upload(c->d_fam_list, fam_list.data(), 4 * fam_list.size(), c->st);
     if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
     if (!rc) rc = upload(c->d_fam, d->fam, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
@@ -823,6 +812,12 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     if (!rc) rc = upload(c->d_flags, c->flags.data(), (size_t)total, c->st);
     if (!rc) rc = upload(c->d_fam_ptr, fam_ptr.data(), 4 * fam_ptr.size(), c->st);
     if (!rc) rc = upload(c->d_fam_members, members.data(), 4 * members.size(), c->st);
+    if (!rc && have_table) {  // the (family, list) table is built on the device from the CSR just uploaded
+        if (c->d_fam_list.ensure(4 * (size_t)tbl) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
+        else
+            launch_fam_list(c->d_fam_ptr.as<int32_t>(), c->d_fam_members.as<int32_t>(), c->d_list_off.as<int64_t>(), c->n_fam,
+                            d->n_lists, total, c->d_fam_list.as<int32_t>(), c->st);
+    }
     if (!rc && cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "dataset upload failed");
     if (rc) { iadh_destroy(c); return rc; }
     c->ds.n_lists = c->n_lists;
@@ -836,7 +831,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->ds.mem_y = c->d_mem_y.as<uint32_t>();
     c->ds.plus_prefix = c->d_plus_prefix.as<int32_t>();
     c->ds.self_slot = c->d_self_slot.as<int32_t>();
-    c->ds.fam_list = fam_list.empty() ? nullptr : c->d_fam_list.as<int32_t>();
+    c->ds.fam_list = have_table ? c->d_fam_list.as<int32_t>() : nullptr;
     sort_lists(c);
     // defaults = shipped datasetI/II settings, Bonferroni (Settings.cpp:4-9)
     memset(&c->prm, 0, sizeof c->prm);
