@@ -20,6 +20,7 @@
 
 #include "cluster_math.cuh"
 #include "common.h"
+#include "pack_measure.cuh"
 #include "workspace.h"
 
 namespace {
@@ -1450,11 +1451,13 @@ template <int NT>
 __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* __restrict__ order,
                                                      int n_tasks, int* next_task,
                                                      const uint32_t* __restrict__ dots, uint8_t* ws,
-                                                     DevParams prm, int pool_factor, int* sm_slot)
+                                                     DevParams prm, int pool_factor, int* sm_slot, DatasetDev ds,
+                                                     ProfileDev pf, int hl)
 {
     using K = KT<NT>;
     constexpr int NW = K::NW;
     __shared__ Ghm g;
+    __shared__ pk::PGhm pg;
     __shared__ Red red;
     __shared__ int sh_i[NW];
     __shared__ int sh_s[8];
@@ -1661,19 +1664,26 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                 if (prof[k]) atomicAdd((unsigned long long*)&task.prof[k], (unsigned long long)prof[k]);
         }
         __syncthreads();
+        // K3 measure as the tail of the GHM (bounds, HL duplicate filter and false anchor points, sizes)
+        if (ok && task.n_mult > 0) {
+            if (hl) pk::measure_ghm<true>(pg, task, ws, ds, pf, pool_factor);
+            else pk::measure_ghm<false>(pg, task, ws, ds, pf, pool_factor);
+        }
+        __syncthreads();
     }
 }
 
 }  // namespace
 
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int* sm_slot, int grid, int nt, cudaStream_t st)
+                    const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
+                    int grid, int nt, cudaStream_t st)
 {
     if (n_tasks == 0) return;
     switch (nt) {
-    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
-    case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
-    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
-    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot); break;
+    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     }
 }

@@ -38,7 +38,8 @@ void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
                    const uint8_t* flags, int gap, int64_t total, uint8_t* remapped, int32_t* t3, cudaStream_t st);
 void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
-                    const DevParams& prm, int pool_factor, int* sm_slot, int grid, int nt, cudaStream_t st);
+                    const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
+                    int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
                          const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -349,27 +350,44 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
         col_ptr[x + 1] = (int32_t)gfam.size();
     }
     const size_t n = (size_t)S * L;
-    int rc;
-    if ((rc = upload(c->d_pf_col, col_ptr.data(), 4 * col_ptr.size(), c->st))) return rc;
-    if ((rc = upload(c->d_pf_gfam, gfam.data(), 4 * gfam.size(), c->st))) return rc;
-    if ((rc = upload(c->d_pf_ggid, ggid.data(), 4 * ggid.size(), c->st))) return rc;
-    if ((rc = upload(c->d_pf_gstrand, gstrand.data(), gstrand.size(), c->st))) return rc;
-    if ((rc = upload(c->d_pf_fam, p->fam, 4 * n, c->st))) return rc;
-    if ((rc = upload(c->d_pf_gid, p->gid, 4 * n, c->st))) return rc;
-    if ((rc = upload(c->d_pf_num, p->num_id, 4 * n, c->st))) return rc;
-    if ((rc = upload(c->d_pf_flags, p->flags, n, c->st))) return rc;
-    CU(cudaStreamSynchronize(c->st));  // the host vectors above die at return
-    h2d += 4 * (col_ptr.size() + 2 * gfam.size()) + gstrand.size() + 13 * n;
+    // one pinned staging buffer, one H2D copy (the profile is re-sent on every search)
+    const size_t G = gfam.size();
+    size_t o = 0;
+    auto take = [&o](size_t bytes) {
+        const size_t r = o;
+        o += (bytes + 15) & ~(size_t)15;
+        return r;
+    };
+    const size_t o_col = take(4 * col_ptr.size()), o_gfam = take(4 * G), o_ggid = take(4 * G), o_gstr = take(G),
+                 o_fam = take(4 * n), o_gid = take(4 * n), o_num = take(4 * n), o_flg = take(n);
+    CU(c->h_pf.ensure(o + 16));
+    CU(c->d_pf_col.ensure(o + 16));
+    uint8_t* h = c->h_pf.as<uint8_t>();
+    memcpy(h + o_col, col_ptr.data(), 4 * col_ptr.size());
+    if (G) {
+        memcpy(h + o_gfam, gfam.data(), 4 * G);
+        memcpy(h + o_ggid, ggid.data(), 4 * G);
+        memcpy(h + o_gstr, gstrand.data(), G);
+    }
+    if (n) {
+        memcpy(h + o_fam, p->fam, 4 * n);
+        memcpy(h + o_gid, p->gid, 4 * n);
+        memcpy(h + o_num, p->num_id, 4 * n);
+        memcpy(h + o_flg, p->flags, n);
+    }
+    CU(cudaMemcpyAsync(c->d_pf_col.p, h, o, cudaMemcpyHostToDevice, c->st));
+    h2d += (int64_t)o;
+    uint8_t* dv = c->d_pf_col.as<uint8_t>();
     out.dev.S = S;
     out.dev.L = L;
-    out.dev.col_ptr = c->d_pf_col.as<int32_t>();
-    out.dev.grp_fam = c->d_pf_gfam.as<int32_t>();
-    out.dev.grp_gid = c->d_pf_ggid.as<int32_t>();
-    out.dev.grp_strand = c->d_pf_gstrand.as<uint8_t>();
-    out.dev.fam = c->d_pf_fam.as<int32_t>();
-    out.dev.gid = c->d_pf_gid.as<int32_t>();
-    out.dev.num_id = c->d_pf_num.as<int32_t>();
-    out.dev.flags = c->d_pf_flags.as<uint8_t>();
+    out.dev.col_ptr = (const int32_t*)(dv + o_col);
+    out.dev.grp_fam = (const int32_t*)(dv + o_gfam);
+    out.dev.grp_gid = (const int32_t*)(dv + o_ggid);
+    out.dev.grp_strand = dv + o_gstr;
+    out.dev.fam = (const int32_t*)(dv + o_fam);
+    out.dev.gid = (const int32_t*)(dv + o_gid);
+    out.dev.num_id = (const int32_t*)(dv + o_num);
+    out.dev.flags = dv + o_flg;
     out.valid = true;
     return IADH_OK;
 }
@@ -529,7 +547,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                     cudaStream_t s = (launched == 0) ? c->st : c->st_side[launched - 1];
                     if (launched) CU(cudaStreamWaitEvent(s, c->ev_fork, 0));
                     launch_cluster(c->d_tasks.as<GhmTask>(), ord + begin, cnt, ctr + k, c->d_dots.as<uint32_t>(),
-                                   c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, std::min(cnt, c->sm_count * c->cls[k].per_sm),
+                                   c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, c->ds, pf, hl,
+                                   std::min(cnt, c->sm_count * c->cls[k].per_sm),
                                    c->cls[k].nt, s);
                     if (launched) {
                         CU(cudaEventRecord(c->ev_join[launched - 1], s));
@@ -543,11 +562,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         }
         CU(cudaEventRecord(c->ev[6], c->st));
         trace_mark(c->st, "K2 cluster");
-        // measure runs over every active GHM (those without multiplicons return at once)
-        launch_pack_measure(hl, c->d_tasks.as<GhmTask>(), c->d_order.as<int>(), n_act, c->d_ws.as<uint8_t>(), c->ds, pf,
-                            pool_factor, c->st);
-        st.kernel_launches += n_act ? 1 : 0;
-        trace_mark(c->st, "K3 measure");
+        // (K3's measuring pass ran as the tail of every GHM inside K2)
         CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;

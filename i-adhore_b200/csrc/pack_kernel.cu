@@ -14,34 +14,16 @@
 #include "common.h"
 #include "workspace.h"
 
+#include "pack_measure.cuh"
+
 namespace {
+
+using pk::PGhm;
+using pk::pghm_init;
+using pk::seg_match;
 
 constexpr int PT = 128;
 constexpr int PW = PT / 32;
-
-struct PGhm {
-    uint32_t* pool;
-    ClusterRec* cl;
-    MultRec* mult;
-    int* out_mults;
-    int* oc;       // output clusters in stream order (reuses the `act` array)
-    int* scratch;  // per anchor point: false APs before it (reuses the `nxt` array)
-    int n_mult, n_oc;
-};
-
-__device__ void pghm_init(PGhm& p, const GhmTask& task, uint8_t* ws, int pool_factor)
-{
-    const int D = (int)(task.cnt[0] + task.cnt[1]);
-    WsLayout L = ws_layout(D, pool_factor);
-    uint8_t* base = ws + task.ws_off;
-    p.pool = (uint32_t*)(base + L.pool);
-    p.cl = (ClusterRec*)(base + L.cl);
-    p.mult = (MultRec*)(base + L.mult);
-    p.out_mults = (int*)(base + L.out_mults);
-    p.oc = (int*)(base + L.act);
-    p.scratch = (int*)(base + L.nxt);
-    p.n_mult = task.n_mult;
-}
 
 __device__ __forceinline__ void put32(uint8_t* p, int32_t v)
 {
@@ -65,21 +47,6 @@ __device__ __forceinline__ void put_ap(uint8_t* q, int gx, int gy, int x, int y,
     q[16] = (uint8_t)real;
 }
 
-// does profile element (segment n, column x) pair with dataset element yg?  (Gene.cpp:17-30)
-__device__ __forceinline__ bool seg_match(const ProfileDev& pf, int n, int x, int fy, int gy)
-{
-    const int idx = n * pf.L + x;
-    if (pf.flags[idx] & 2) return false;
-    return pf.fam[idx] == fy && pf.gid[idx] != gy;
-}
-
-__device__ __forceinline__ int warp_sum(int v)
-{
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-
 template <bool HL>
 __global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const int* __restrict__ sel, int n_sel,
                                                           uint8_t* ws, DatasetDev ds, ProfileDev pf, int pool_factor)
@@ -87,112 +54,8 @@ __global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const 
     __shared__ PGhm p;
     if (blockIdx.x >= n_sel) return;
     GhmTask& task = tasks[sel[blockIdx.x]];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (task.n_mult == 0 || task.status != 0) return;  // uniform: nothing to serialise
-    if (tid == 0) {
-        pghm_init(p, task, ws, pool_factor);
-        int n = 0, sbase = 0;
-        for (int m = 0; m < p.n_mult; m++)
-            for (int c = p.mult[p.out_mults[m]].head; c >= 0; c = p.cl[c].mnext) {
-                p.oc[n++] = c;
-                p.cl[c].out_off = sbase;  // temporarily: base of this cluster's scratch segment
-                sbase += p.cl[c].n;
-            }
-        p.n_oc = n;
-    }
-    __syncthreads();
-    const int64_t yoff = ds.list_off[task.y_list];
-    for (int i = warp; i < p.n_oc; i += PW) {
-        ClusterRec& c = p.cl[p.oc[i]];
-        uint32_t* ap = p.pool + c.off;
-        int n = c.n;
-        int mn = 0x7fffffff, mx = -1;
-        bool sorted = true;
-        for (int k = lane; k < n; k += 32) {
-            const int y = KEY_Y(ap[k]);
-            mn = min(mn, y);
-            mx = max(mx, y);
-            if (HL && k > 0 && ap[k - 1] >= ap[k]) sorted = false;
-        }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        }
-        int nfalse = 0;
-        if (HL) {
-            // filterDuplicates: unique (x,y), ordered by x then y.  The array is x-sorted, so a plain
-            // sort of the packed keys gives exactly that order; usually it already is.
-            if (!__all_sync(0xffffffffu, sorted)) {
-                if (lane == 0) {
-                    for (int a = 1; a < n; a++) {
-                        const uint32_t v = ap[a];
-                        int b = a - 1;
-                        while (b >= 0 && ap[b] > v) {
-                            ap[b + 1] = ap[b];
-                            b--;
-                        }
-                        ap[b + 1] = v;
-                    }
-                    int w = 1;
-                    for (int a = 1; a < n; a++)
-                        if (ap[a] != ap[w - 1]) ap[w++] = ap[a];
-                    c.n = w;
-                }
-                __syncwarp();
-                n = c.n;
-            }
-            // false anchor points: every further matching segment of the profile column; the
-            // scratch array keeps, per AP, the number of false APs of all earlier APs
-            int* scr = p.scratch + c.out_off;
-            int run = 0;
-            for (int k0 = 0; k0 < n; k0 += 32) {
-                const int k = k0 + lane;
-                int nf = 0;
-                if (k < n) {
-                    const int x = KEY_X(ap[k]);
-                    const int yg = (int)(yoff + KEY_Y(ap[k]));
-                    const int fy = ds.fam[yg], gy = ds.gid[yg];
-                    int matches = 0;
-                    for (int s = 0; s < pf.S; s++) matches += seg_match(pf, s, x, fy, gy) ? 1 : 0;
-                    nf = matches > 1 ? matches - 1 : 0;
-                }
-                int inc = nf;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += t;
-                }
-                if (k < n) scr[k] = run + inc - nf;
-                run += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            nfalse = run;
-        }
-        if (lane == 0) {
-            c.min_y = mn;
-            c.max_y = mx;
-            c.n_false = nfalse;
-            c.has_false = nfalse > 0;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int off = 0, naps = 0;
-        for (int m = 0; m < p.n_mult; m++) {
-            MultRec& mr = p.mult[p.out_mults[m]];
-            mr.out_off = off;
-            off += 33;
-            for (int c = mr.head; c >= 0; c = p.cl[c].mnext) {
-                p.cl[c].cap = p.cl[c].out_off;  // scratch base survives in `cap` (the pool is frozen now)
-                p.cl[c].out_off = off;
-                off += 102 + 17 * (p.cl[c].n + p.cl[c].n_false);
-                naps += p.cl[c].n + p.cl[c].n_false;
-            }
-        }
-        task.out_bytes = off;
-        task.n_clusters = p.n_oc;
-        task.n_aps = naps;
-    }
+    pk::measure_ghm<HL>(p, task, ws, ds, pf, pool_factor);
 }
 
 template <bool HL>

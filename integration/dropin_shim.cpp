@@ -43,7 +43,7 @@ struct Bridge {
     long n_hl = 0;
     // wall-clock split of the profile searches (IADH_VERBOSE=1 prints it at exit)
     double w_mask = 0, w_desc = 0, w_call = 0, w_unpack = 0;
-    long long n_ghm = 0, n_found = 0;
+    long long n_ghm = 0, n_found = 0, n_returned = 0;
 };
 Bridge B;
 
@@ -58,9 +58,9 @@ void report()
 {
     if (!getenv("IADH_VERBOSE")) return;
     fprintf(stderr,
-            "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons kept; wall: masks %.3fs, descriptor %.3fs, "
+            "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons returned, %lld kept; wall: masks %.3fs, descriptor %.3fs, "
             "device call %.3fs (device time %.3fs), unpack+filter %.3fs\n",
-            B.n_hl, B.n_ghm, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
+            B.n_hl, B.n_ghm, B.n_returned, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
 }
 
 int intern(std::map<std::string, int>& m, const std::string& s)
@@ -265,6 +265,7 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     }
     B.n_ghm += st.n_ghm;
     B.n_found += (long long)target.size();
+    B.n_returned += (long long)st.n_multiplicons;
     B.w_mask += w1 - w0;
     B.w_desc += w2 - w1;
     B.w_call += w3 - w2;
