@@ -1448,7 +1448,7 @@ static __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, 
 // ---- kernel -----------------------------------------------------------------------------------
 
 template <int NT>
-__global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* __restrict__ order,
+__global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* profs, const int* __restrict__ order,
                                                      int n_tasks, int* next_task,
                                                      const uint32_t* __restrict__ dots, uint8_t* ws,
                                                      DevParams prm, int pool_factor, int* sm_slot, DatasetDev ds,
@@ -1489,6 +1489,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
         const int my_mask = item & 3;
         const int my_o = (my_mask == 2) ? 1 : 0;
         GhmTask& task = tasks[item >> 2];
+        GhmProf& tprof = profs[item >> 2];
         const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1], D = D0 + D1;
         const int half_mask = task.half_mask;
         const bool run_p1 = my_mask != 0;
@@ -1597,7 +1598,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
                     task.half_ncl[o] = g.ncl[o];
                     task.half_pool[o] = g.pool_used[o];
                     task.half_status[o] = g.status;
-                    task.half_cycles[o] = clock64() - t_begin;
+                    tprof.half_cycles[o] = clock64() - t_begin;
                 }
             }
         }
@@ -1613,8 +1614,8 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
         }
         if (tid == 0)
             for (int k = 0; k < 8; k++) {
-                if (k < 5 && prof[k]) atomicAdd((unsigned long long*)&task.prof[k], (unsigned long long)prof[k]);
-                if (prof2[k]) atomicAdd((unsigned long long*)&task.prof2[k], (unsigned long long)prof2[k]);
+                if (k < 5 && prof[k]) atomicAdd((unsigned long long*)&tprof.prof[k], (unsigned long long)prof[k]);
+                if (prof2[k]) atomicAdd((unsigned long long*)&tprof.prof2[k], (unsigned long long)prof2[k]);
             }
         __syncthreads();
         if (!last) continue;
@@ -1658,10 +1659,10 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
             task.n_mult = ok ? sh_s[0] : 0;
             task.n_clusters = (g.ncl[0] - g.cl_lo[0]) + (g.ncl[1] - g.cl_lo[1]);
             // critical path of this GHM: the slower orientation, then phase 2
-            const long long h0 = (half_mask & 1) ? task.half_cycles[0] : 0, h1 = (half_mask & 2) ? task.half_cycles[1] : 0;
-            task.prof[5] = (h0 > h1 ? h0 : h1) + (clock64() - t_p2);
+            const long long h0 = (half_mask & 1) ? tprof.half_cycles[0] : 0, h1 = (half_mask & 2) ? tprof.half_cycles[1] : 0;
+            tprof.prof[5] = (h0 > h1 ? h0 : h1) + (clock64() - t_p2);
             for (int k = 0; k < 5; k++)
-                if (prof[k]) atomicAdd((unsigned long long*)&task.prof[k], (unsigned long long)prof[k]);
+                if (prof[k]) atomicAdd((unsigned long long*)&tprof.prof[k], (unsigned long long)prof[k]);
         }
         __syncthreads();
         // K3 measure as the tail of the GHM (bounds, HL duplicate filter and false anchor points, sizes)
@@ -1675,15 +1676,15 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, const int* 
 
 }  // namespace
 
-void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
                     const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
                     int grid, int nt, cudaStream_t st)
 {
     if (n_tasks == 0) return;
     switch (nt) {
-    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
-    case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
-    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
-    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    case 32: cluster_kernel<32><<<grid, 32, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     }
 }

@@ -51,9 +51,14 @@ struct GhmTask {
     int32_t half_done;    // device: items finished
     int32_t half_nbc[2], half_ncl[2], half_pool[2], half_status[2];  // device: state handed to phase 2
     int32_t pad2;
+};
+
+// Per-GHM cycle counters of K2 (debugging / profiling aid; a separate array so that the task
+// records that travel between host and device stay small).
+struct GhmProf {
     long long half_cycles[2];
-    long long prof2[8];   // out: join sub-phases (init, reduce, locate, merge, erase, refresh, redo, #merges)
-    long long prof[8];    // out: SM cycles per phase (seed, enrich, join, filter, metacluster, total, -, -)
+    long long prof2[8];   // join sub-phases (init, reduce, locate, merge, erase, refresh, redo, #merges)
+    long long prof[8];    // SM cycles per phase (seed, enrich, join, filter, metacluster, critical path, -, -)
 };
 
 // Base cluster record (BaseCluster.h:316-331).  Anchor points live in the GHM's AP

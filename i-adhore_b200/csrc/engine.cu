@@ -37,7 +37,7 @@ void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64
                      int64_t total, int32_t* table, cudaStream_t st);
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
                    const uint8_t* flags, int gap, int64_t total, uint8_t* remapped, int32_t* t3, cudaStream_t st);
-void launch_cluster(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
                     const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
                     int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
@@ -220,7 +220,7 @@ struct iadh_ctx {
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
-    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_sel, d_out_off, d_out, d_counter;
+    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_prof, d_sel, d_out_off, d_out, d_counter;
     DBuf d_pf_col, d_pf_gfam, d_pf_ggid, d_pf_gstrand, d_pf_fam, d_pf_gid, d_pf_num, d_pf_flags;
     HBuf h_tasks, h_misc, h_out, h_pf;
     // build_dots scratch
@@ -482,8 +482,6 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             t.half_done = 0;
             t.half_mask = 0;
             t.half_needed = 1;
-            memset(t.prof, 0, sizeof t.prof);
-            memset(t.prof2, 0, sizeof t.prof2);
             if (D < (int64_t)c->prm.anchor_points || D == 0) continue;
             if (D > 0x0fffffff) return fail(IADH_ERR_CAPACITY, "GHM with %lld dots exceeds the per-GHM limit", (long long)D);
             const WsLayout L = ws_layout((int)D, pool_factor);
@@ -522,6 +520,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         if ((rc = upload(c->d_items, items.data(), 4 * (size_t)n_items, c->st))) return rc;
         CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
         st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act + 4 * n_items;
+        CU(c->d_prof.ensure(sizeof(GhmProf) * (size_t)n + 16));
+        CU(cudaMemsetAsync(c->d_prof.p, 0, sizeof(GhmProf) * (size_t)n, c->st));
         CU(c->d_counter.ensure(16 + 4 * 1024));  // 4 class queues + per-SM arrival counters
         CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024, c->st));
         trace_mark(c->st, "host: order/ws + uploads");
@@ -546,7 +546,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 if (cnt > 0) {
                     cudaStream_t s = (launched == 0) ? c->st : c->st_side[launched - 1];
                     if (launched) CU(cudaStreamWaitEvent(s, c->ev_fork, 0));
-                    launch_cluster(c->d_tasks.as<GhmTask>(), ord + begin, cnt, ctr + k, c->d_dots.as<uint32_t>(),
+                    launch_cluster(c->d_tasks.as<GhmTask>(), c->d_prof.as<GhmProf>(), ord + begin, cnt, ctr + k, c->d_dots.as<uint32_t>(),
                                    c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, c->ds, pf, hl,
                                    std::min(cnt, c->sm_count * c->cls[k].per_sm),
                                    c->cls[k].nt, s);
@@ -567,23 +567,24 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(cudaStreamSynchronize(c->st));
         st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
         if (g_trace) {
+            std::vector<GhmProf> pr((size_t)n);
+            cudaMemcpy(pr.data(), c->d_prof.p, sizeof(GhmProf) * (size_t)n, cudaMemcpyDeviceToHost);
             long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             int hv = order.empty() ? -1 : order[0];
             for (int i : order) {
-                for (int k = 0; k < 8; k++) tot[k] += tasks[i].prof[k];
-                if (tasks[i].prof[5] > tasks[hv].prof[5]) hv = i;
+                for (int k = 0; k < 8; k++) tot[k] += pr[i].prof[k];
+                if (pr[i].prof[5] > pr[hv].prof[5]) hv = i;
             }
             fprintf(stderr, "[iadh] K2 cycles (all GHMs): seed %.2fM enrich %.2fM join %.2fM filter %.2fM meta %.2fM total %.2fM\n",
                     tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
             if (hv >= 0)
                 fprintf(stderr, "[iadh] slowest GHM %d (D=%u+%u, %d clusters, %d mult): seed %.2fM enrich %.2fM join %.2fM filter %.2fM meta %.2fM total %.2fM\n",
-                        hv, tasks[hv].cnt[0], tasks[hv].cnt[1], tasks[hv].n_clusters, tasks[hv].n_mult, tasks[hv].prof[0] / 1e6,
-                        tasks[hv].prof[1] / 1e6, tasks[hv].prof[2] / 1e6, tasks[hv].prof[3] / 1e6, tasks[hv].prof[4] / 1e6,
-                        tasks[hv].prof[5] / 1e6);
+                        hv, tasks[hv].cnt[0], tasks[hv].cnt[1], tasks[hv].n_clusters, tasks[hv].n_mult, pr[hv].prof[0] / 1e6,
+                        pr[hv].prof[1] / 1e6, pr[hv].prof[2] / 1e6, pr[hv].prof[3] / 1e6, pr[hv].prof[4] / 1e6, pr[hv].prof[5] / 1e6);
             if (hv >= 0)
                 fprintf(stderr, "[iadh]   join of it: init %.2fM reduce %.2fM locate %.2fM merge %.2fM erase %.2fM refresh %.2fM redo %.2fM, %lld merges\n",
-                        tasks[hv].prof2[0] / 1e6, tasks[hv].prof2[1] / 1e6, tasks[hv].prof2[2] / 1e6, tasks[hv].prof2[3] / 1e6,
-                        tasks[hv].prof2[4] / 1e6, tasks[hv].prof2[5] / 1e6, tasks[hv].prof2[6] / 1e6, tasks[hv].prof2[7]);
+                        pr[hv].prof2[0] / 1e6, pr[hv].prof2[1] / 1e6, pr[hv].prof2[2] / 1e6, pr[hv].prof2[3] / 1e6,
+                        pr[hv].prof2[4] / 1e6, pr[hv].prof2[5] / 1e6, pr[hv].prof2[6] / 1e6, pr[hv].prof2[7]);
         }
         bool retry = false;
         for (int i : order)
@@ -891,7 +892,7 @@ void iadh_destroy(iadh_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_prof,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
                     &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
     for (DBuf* b : bufs) b->release();
