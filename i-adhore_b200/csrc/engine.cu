@@ -8,6 +8,7 @@
 //   K3 pack (measure -> host size scan -> write)       pack_kernel.cu
 // with persistent, growable device buffers and pinned staging.  No CPU fallback exists: every
 // entry point fails if CUDA is unavailable.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -70,7 +71,8 @@ static double g_t_last = 0;
 static void trace_mark(cudaStream_t st, const char* label)
 {
     if (!g_trace) return;
-    cudaStreamSynchronize(st);
+    const cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) fprintf(stderr, "[iadh] !! %s after stage '%s'\n", cudaGetErrorString(se), label ? label : "(start)");
     const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     if (label) fprintf(stderr, "[iadh] %-28s %8.3f ms\n", label, (now - g_t_last) * 1e3);
     g_t_last = now;
@@ -124,6 +126,54 @@ struct BlockCache {
 };
 static BlockCache g_cache;
 
+// IADH_EFENCE=1 (debugging aid; compute-sanitizer is not available on every pool): device buffers
+// come from the virtual-memory API, placed so that the buffer ENDS at the last mapped byte (up to the
+// 256-byte alignment of its start); the next page is reserved but unmapped, so any access past the
+// end of a buffer faults deterministically instead of silently touching a neighbour.  Blocks are
+// never recycled in this mode.
+#include <dlfcn.h>
+static void* efence_alloc(size_t bytes)
+{
+    // the driver API is looked up at run time: the library must load on machines without a driver
+    static void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!drv) return nullptr;
+    typedef CUresult (*gran_t)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+    typedef CUresult (*reserve_t)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+    typedef CUresult (*create_t)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+    typedef CUresult (*map_t)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    typedef CUresult (*access_t)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+    static gran_t f_gran = (gran_t)dlsym(drv, "cuMemGetAllocationGranularity");
+    static reserve_t f_reserve = (reserve_t)dlsym(drv, "cuMemAddressReserve");
+    static create_t f_create = (create_t)dlsym(drv, "cuMemCreate");
+    static map_t f_map = (map_t)dlsym(drv, "cuMemMap");
+    static access_t f_access = (access_t)dlsym(drv, "cuMemSetAccess");
+    if (!f_gran || !f_reserve || !f_create || !f_map || !f_access) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaFree(0);
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev;
+    size_t gran = 0;
+    if (f_gran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS) return nullptr;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    const size_t mapped = (need + gran - 1) / gran * gran;
+    CUdeviceptr va = 0;
+    if (f_reserve(&va, mapped + gran, gran, 0, 0) != CUDA_SUCCESS) return nullptr;
+    CUmemGenericAllocationHandle h;
+    if (f_create(&h, mapped, &prop, 0) != CUDA_SUCCESS) return nullptr;
+    // IADH_EFENCE=2: guard page BEFORE the buffer instead (catches negative indices)
+    static const bool before = atoi(getenv("IADH_EFENCE")) == 2;
+    const CUdeviceptr at = before ? va + gran : va;
+    if (f_map(at, mapped, 0, h, 0) != CUDA_SUCCESS) return nullptr;
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (f_access(at, mapped, &acc, 1) != CUDA_SUCCESS) return nullptr;
+    return (void*)(before ? at : va + (mapped - need));
+}
+
 // growable device buffer
 struct DBuf {
     void* p = nullptr;
@@ -136,27 +186,46 @@ struct DBuf {
             // the old block may still be read by work in flight; it must be idle before another
             // context can take it from the cache (growth is rare: sizes converge after the first call)
             cudaDeviceSynchronize();
-            g_cache.give(p, cap, dev);
+            if (!getenv("IADH_EFENCE")) g_cache.give(p, cap, dev);
         }
         p = nullptr;
         cap = 0;
         cudaGetDevice(&dev);
-        if ((p = g_cache.take(bytes, dev, &cap))) return cudaSuccess;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            g_cache.trim();
-            want = bytes;
-            e = cudaMalloc(&p, want);
+        cudaError_t e = cudaSuccess;
+        static const char* efence = getenv("IADH_EFENCE");
+        if (efence) {
+            p = efence_alloc(bytes);
+            cap = p ? bytes : 0;
+            return p ? cudaSuccess : cudaErrorMemoryAllocation;
         }
-        if (e == cudaSuccess) cap = want;
-        else p = nullptr;
+        if (!(p = g_cache.take(bytes, dev, &cap))) {
+            size_t want = bytes + bytes / 4 + 256;
+            // never change the device's address space under a running kernel: with peer access enabled
+            // (NCCL in the same process) cudaMalloc also edits the peers' page tables
+            cudaDeviceSynchronize();
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                g_cache.trim();
+                want = bytes;
+                e = cudaMalloc(&p, want);
+            }
+            if (e == cudaSuccess) cap = want;
+            else p = nullptr;
+        }
+        // IADH_POISON=<byte>: debugging aid, every block handed out is filled with that byte first, so a
+        // read of memory the kernels did not write shows up deterministically (fresh cudaMalloc pages
+        // are zero, recycled ones hold old data)
+        static const char* poison = getenv("IADH_POISON");
+        if (p && poison) {
+            cudaMemset(p, atoi(poison), cap);
+            cudaDeviceSynchronize();  // (the memset runs on the legacy stream, our streams are non-blocking)
+        }
         return e;
     }
     void release()
     {
-        if (p) g_cache.give(p, cap, dev);
+        if (p && !getenv("IADH_EFENCE")) g_cache.give(p, cap, dev);
         p = nullptr;
         cap = 0;
     }
