@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- GHM list-pair comparisons/s of the B200 collinearity engine.
 
-Workload (config.workload): BASELINE.json config 3 -- synthetic 10 genomes x 30k genes as
-100 gene lists x 3000 (20k families, planted segmental duplications; gap_size=30,
-cluster_gap=35, q=0.75, prob_cutoff=0.01, Bonferroni).  One step = one pass of the hot path:
-  * level 2 : GHM build + collinear clustering of all 5,050 list pairs, then
+Workload (config.workload): BASELINE.json config 4, the largest configuration that fits one GPU --
+synthetic 50 genomes x 25k genes as 500 gene lists x 2500 (20k families, planted segmental
+duplications; gap_size=30, cluster_gap=35, q=0.75, prob_cutoff=0.01, Bonferroni).  datasetI/II
+(configs 0/1) cannot be run: their family tables are stripped from the reference tree.  Other
+workloads: --workload c3 (10 x 30k genes), d2 (datasetII-shaped ragged lists), c5 (K1 only).
+One step = one pass of the hot path:
+  * level 2 : GHM build + collinear clustering of all 125,250 list pairs, then
   * profile search: P two-segment profiles (made from the P largest level-2 multiplicons)
     against every list, with the masks accumulating as in higherLevel.cpp:165-171.
 metric = GHMs (list x list and profile x list comparisons) per second.
 
-  value : context resident in HBM (dataset uploaded once), device-resident throughput
+  value : context resident in HBM (dataset uploaded once), timed with CUDA events on the engine's stream
   e2e   : a fresh context per step from HOST buffers (dataset H2D inside the timed region),
-          results read back to the host -- the call a user of the C-ABI makes
+          results read back to pinned host memory -- the call a user of the C-ABI makes
   N > 1 : one process per GPU (torchrun); the pair sequence / list partition is sharded with
           the reference's own rules (levelTwo.cpp:98-148, parallel.cpp:96-156) and the packed
           results are all-gathered over NCCL each call (levelTwo.cpp:225-269,
           higherLevel.cpp:279-314).  Fixed total work => "strong" scaling.
 
 --impl reference times the UNMODIFIED reference objects (oracle/_ref/ref_harness, all host
-threads) on the same C3 files; falls back to the oracle port when oracle/_ref is absent.
+threads) on the same files, on a bounded sample with the step's own mix of list pairs and
+profile searches; falls back to the oracle port when oracle/_ref is absent.
 """
 import argparse
 import json
@@ -172,7 +176,7 @@ def hot_path_step(eng, profs, rank, n_ranks, gather=None):
     launches = 1
     r = eng.level2_all_pairs(rank, n_ranks)
     if gather:
-        gather(r.bytes)
+        gather(r)
     stats = [r.stats]
     units = r.stats["n_ghm"]
     for m, p in profs:
@@ -181,20 +185,23 @@ def hot_path_step(eng, profs, rank, n_ranks, gather=None):
         launches += 2
         pr = eng.profile_search(p, rank, n_ranks)
         if gather:
-            gather(pr.bytes)
+            gather(pr)
         stats.append(pr.stats)
         units += pr.stats["n_ghm"]
     launches += sum(s["kernel_launches"] for s in stats)
     return units, stats, launches
 
 
-def run_reference(cfg, n_profiles, threads, tmpdir):
-    """The unmodified reference objects on the same workload files (bounded: L2 + n_profiles)."""
+def run_reference(cfg, n_profiles, threads, tmpdir, max_pairs=-1):
+    """The unmodified reference objects on the same workload files.  Bounded sample with the
+    step's own mix: the first `max_pairs` list pairs of the level-2 sequence and `n_profiles`
+    profile searches over all lists (a GHMProfile costs the CPU ~20x a list pair, so the
+    proportion of the two kinds of GHM is part of the workload)."""
     if os.path.exists(REF_HARNESS):
         ini = synth.write_reference_inputs(cfg, tmpdir, n_threads=threads)
         t0 = time.time()
-        p = subprocess.run([REF_HARNESS, ini, "-", "--time", "--threads", str(threads), "--max-profiles", str(n_profiles)],
-                           capture_output=True, text=True)
+        p = subprocess.run([REF_HARNESS, ini, "-", "--time", "--threads", str(threads), "--max-profiles", str(n_profiles),
+                            "--max-pairs", str(max_pairs)], capture_output=True, text=True)
         wall = time.time() - t0
         if p.returncode != 0:
             raise RuntimeError("ref_harness failed: " + p.stderr[-400:])
@@ -229,7 +236,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--workload", default="c4")
     ap.add_argument("--profiles", type=int, default=32, help="profile searches per step")
     ap.add_argument("--ref-profiles", type=int, default=4, help="profile searches in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -244,7 +251,12 @@ def main():
     config = {"workload": workload_label(a.workload, cfg, a.profiles),
               "gap_size": cfg.gap_size, "cluster_gap": cfg.cluster_gap, "q_value": cfg.q_value,
               "prob_cutoff": cfg.prob_cutoff, "anchor_points": cfg.anchor_points, "mult_hyp": "bonferroni",
-              "l2_flush": "inputs larger than L2: per-step working set (dot keys + per-GHM clustering workspaces, ~0.5 GB allocated, >126 MB touched) does not fit the 126 MB L2"}
+              "l2_flush": "inputs larger than L2: the per-step working set (dot keys + per-GHM clustering workspaces; 13 GB allocated for c4, 0.5 GB for c3) does not fit the 126 MB L2"}
+
+    # the CPU sample is the same fraction of both kinds of GHM of a step
+    n_lists_total = sum(len(g.list_sizes) if g.list_sizes else g.n_lists for g in cfg.genomes)
+    n_pairs_total = n_lists_total * (n_lists_total + 1) // 2
+    ref_pairs = max(1, -(-n_pairs_total * a.ref_profiles // max(1, a.profiles)))
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -257,14 +269,15 @@ def main():
                 # the CPU path has no warm-up effects worth W extra minutes: run at most one warm-up
                 if i < a.warmup - 1:
                     continue
-                last = run_reference(cfg, a.ref_profiles, ncores, td)
+                last = run_reference(cfg, a.ref_profiles, ncores, td, ref_pairs)
                 if i >= a.warmup:
                     vals.append(last)
         units = sum(v["units"] for v in vals)
         secs = sum(v["seconds"] for v in vals)
         value = units / secs
-        sample = (f"L2 all {last['l2_pairs']} pairs ({last['l2_s']:.2f}s) + first {a.ref_profiles} profiles of the "
-                  f"reference's own queue x all lists = {last['hl_ghm']} GHMProfiles ({last['hl_s']:.2f}s) per step")
+        sample = (f"{a.ref_profiles}/{a.profiles} of a step, same mix: first {last['l2_pairs']} of {n_pairs_total} list pairs "
+                  f"({last['l2_s']:.2f}s) + first {a.ref_profiles} profiles of the reference's own queue x all lists = "
+                  f"{last['hl_ghm']} GHMProfiles ({last['hl_s']:.2f}s)")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic", "config": config, "impl": "reference",
@@ -290,18 +303,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(payload: bytes):
+    def gather(res):
         """levelTwo.cpp:225-269 / higherLevel.cpp:279-314: all ranks end with every rank's packed
-        multiplicons in rank order (sizes, then padded bytes, over NCCL)."""
-        n = torch.tensor([len(payload)], dtype=torch.int64, device="cuda")
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        mx = int(max(int(s.item()) for s in sizes))
-        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
-        outs = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(outs, buf)
-        return [o[:int(s.item())] for o, s in zip(outs, sizes)]
+        multiplicons in rank order (sizes, then padded bytes, over NCCL).  The payload goes from the
+        library's pinned result buffer straight to the device (no host-side copies)."""
+        view = res.view()
+        n = torch.tensor([view.size], dtype=torch.int64, device="cuda")
+        sizes = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(sizes, n)
+        sizes = sizes.tolist()
+        mx = max(sizes)
+        buf = torch.empty(mx, dtype=torch.uint8, device="cuda")
+        buf[:view.size].copy_(torch.from_numpy(view), non_blocking=True)
+        outs = torch.empty(world * mx, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(outs, buf)
+        torch.cuda.current_stream().synchronize()   # the pinned buffer is released when `res` dies
+        return [outs[r * mx:r * mx + sizes[r]] for r in range(world)]
 
     t_setup = time.time()
     ds = ingest.dataset_from_synth(cfg)
@@ -411,10 +428,11 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         with tempfile.TemporaryDirectory(prefix="iadh_cpu_") as td:
             try:
-                rr = run_reference(cfg, a.ref_profiles, ncores, td)
+                rr = run_reference(cfg, a.ref_profiles, ncores, td, ref_pairs)
                 cpu = {"value": rr["units"] / rr["seconds"], "unit": UNIT, "cores": ncores, "kind": rr["kind"],
-                       "sample": f"L2 all {rr['l2_pairs']} pairs ({rr['l2_s']:.2f}s) + {a.ref_profiles} profiles x all "
-                                 f"lists = {rr['hl_ghm']} GHMProfiles ({rr['hl_s']:.2f}s), {ncores} threads",
+                       "sample": f"{a.ref_profiles}/{a.profiles} of a step, same mix: first {rr['l2_pairs']} of {n_pairs_total} "
+                                 f"list pairs ({rr['l2_s']:.2f}s) + {a.ref_profiles} profiles x all lists = {rr['hl_ghm']} "
+                                 f"GHMProfiles ({rr['hl_s']:.2f}s), {ncores} threads",
                        "l2_pairs_per_s": rr["l2_pairs"] / rr["l2_s"],
                        "hl_ghm_per_s": rr["hl_ghm"] / rr["hl_s"] if rr["hl_s"] > 0 else None}
             except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line

@@ -122,6 +122,13 @@ class Result:
     def nbytes(self) -> int:
         return self._n
 
+    def view(self) -> np.ndarray:
+        """Zero-copy uint8 view of the packed stream inside the library's pinned result buffer
+        (valid while this object is alive and `.bytes` has not been materialised)."""
+        if self._bytes is not None:
+            return np.frombuffer(self._bytes, dtype=np.uint8)
+        return np.ctypeslib.as_array(self._ptr, shape=(self._n,))
+
     @property
     def n_multiplicons(self) -> int:
         return int(self.stats["n_multiplicons"])

@@ -8,7 +8,7 @@
 // (Multiplicon.cpp:210-264).  The dump ("trace") is what pins oracle_core.cpp and
 // the CUDA path.  Trace layout: see tests/trace_io.py.
 //
-// usage: ref_harness <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--time]
+// usage: ref_harness <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--max-pairs N] [--time]
 //                    [--threads T] [--no-dump]
 // With --threads the GHMs of a stage are evaluated concurrently (each thread owns its GHM,
 // exactly like the reference's work functions, DataSet.h:79,204); results are consumed in
@@ -152,13 +152,14 @@ int main(int argc, char** argv)
         return 2;
     }
     bool doHL = true, timing = false, dump = strcmp(argv[2], "-") != 0;
-    long maxProfiles = -1;
+    long maxProfiles = -1, maxPairs = -1;
     int threads = 1;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--no-hl")) doHL = false;
         else if (!strcmp(argv[i], "--time")) timing = true;
         else if (!strcmp(argv[i], "--no-dump")) dump = false;
         else if (!strcmp(argv[i], "--max-profiles") && i + 1 < argc) maxProfiles = atol(argv[++i]);
+        else if (!strcmp(argv[i], "--max-pairs") && i + 1 < argc) maxPairs = atol(argv[++i]);
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
     }
 
@@ -245,6 +246,8 @@ int main(int argc, char** argv)
             } else { cX--; cY++; }
         }
     }
+    // bounded sample for benchmarks: only the first maxPairs pairs of the sequence
+    if (maxPairs >= 0 && (size_t)maxPairs < pairs.size()) pairs.resize((size_t)maxPairs);
     vector<ItemOut> l2out(pairs.size());
     const bool useFamily = settings.useFamily();
     double wall0 = now();
