@@ -1445,6 +1445,71 @@ static __device__ void cluster_clusters(Ghm& g, const DevParams& prm, Red* red, 
 
 };  // struct KT
 
+// View of one GHM's workspace.  whole = false: the regions of orientation my_o only (phase 1 on its own
+// CTA / in its own launch); fresh = true: counters start empty, otherwise they are reloaded from the
+// state an earlier CTA or launch left in the task record.
+static __device__ void setup_view(Ghm& g, const GhmTask& task, uint8_t* ws, const DevParams& prm, int pool_factor,
+                                  int my_o, bool whole, bool fresh)
+{
+    const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1], D = D0 + D1;
+    const int half_mask = task.half_mask;
+    WsLayout L = ws_layout(D, pool_factor);
+    uint8_t* base = ws + task.ws_off;
+    const int cc0 = D0 / 3 + 2, pc0 = pool_factor * D0 + 32;
+    const int eo = whole ? 0 : (my_o ? D0 : 0);       // element (dot) offset of the region
+    const int co = whole ? 0 : (my_o ? cc0 : 0);      // cluster-slot offset of the region
+    g.key[0] = (uint32_t*)(base + L.key0);
+    g.key[1] = (uint32_t*)(base + L.key1);
+    g.alive[0] = base + L.alive0;
+    g.alive[1] = base + L.alive1;
+    g.nxt = (int*)(base + L.nxt) + eo;
+    g.pool = (uint32_t*)(base + L.pool);
+    g.pflag = base + L.pflag;
+    g.cl = (ClusterRec*)(base + L.cl);
+    g.cl_lo[0] = 0; g.cl_hi[0] = cc0;
+    g.cl_lo[1] = cc0; g.cl_hi[1] = cc0 + D1 / 3 + 2;
+    g.pool_lo[0] = 0; g.pool_hi[0] = pc0;
+    g.pool_lo[1] = pc0; g.pool_hi[1] = L.pool_cap;
+    for (int r = 0; r < 2; r++) {
+        const bool have = !fresh && ((half_mask >> r) & 1) && (whole || r == my_o);
+        g.nbc[r] = have ? task.half_nbc[r] : 0;
+        g.ncl[r] = have ? task.half_ncl[r] : g.cl_lo[r];
+        g.pool_used[r] = have ? task.half_pool[r] : g.pool_lo[r];
+    }
+    if (!whole) {  // the other orientation's regions belong to another CTA
+        const int other = my_o ^ 1;
+        g.pool_lo[other] = g.pool_hi[other] = g.pool_used[other] = 0;
+        g.ncl[other] = g.cl_lo[other];
+        g.cl_hi[other] = g.cl_lo[other];
+    }
+    g.bc[0] = (int*)(base + L.bc0);
+    g.bc[1] = (int*)(base + L.bc1);
+    g.act = (int*)(base + L.act) + co;
+    g.act_next = (int*)(base + L.act_next) + co;
+    g.changed = base + L.changed + co;
+    g.mult = (MultRec*)(base + L.mult);
+    g.nmult = 0;
+    g.out_mults = (int*)(base + L.out_mults);
+    g.rb_d = (double*)(base + L.rb_d);
+    g.rb_j = (int*)(base + L.rb_j);
+    g.rank = (int*)(base + L.rank);
+    g.pos = (int*)(base + L.pos);
+    g.xr = (int2*)(base + L.xr) + co;
+    g.redo = (int*)(base + L.redo) + co;
+    g.dscr = (double*)(base + L.dscr) + 2 * (size_t)eo;
+    g.tmp = (uint32_t*)(base + L.tmp) + eo;
+    g.tmpf = (uint8_t*)((uint32_t*)(base + L.tmp) + L.tmp_cap) + eo;
+    g.scratch_cap = whole ? D : 0;
+    g.status = fresh ? 0 : max(task.half_status[0], task.half_status[1]);
+    for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
+    g.nk[0] = D0;
+    g.nk[1] = D1;
+    g.cnt[0] = task.cnt[0];
+    g.cnt[1] = task.cnt[1];
+    g.area = (double)task.area;
+    g.level = task.level;
+}
+
 // ---- kernel -----------------------------------------------------------------------------------
 
 template <int NT>
@@ -1497,63 +1562,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
         if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
         // view: phase 1 = this CTA's orientation only (its regions of every shared array),
         //       phase 2 = the whole GHM
-        auto setup = [&](bool whole, bool fresh) {
-            WsLayout L = ws_layout(D, pool_factor);
-            uint8_t* base = ws + task.ws_off;
-            const int cc0 = D0 / 3 + 2, pc0 = pool_factor * D0 + 32;
-            const int eo = whole ? 0 : (my_o ? D0 : 0);       // element (dot) offset of the region
-            const int co = whole ? 0 : (my_o ? cc0 : 0);      // cluster-slot offset of the region
-            g.key[0] = (uint32_t*)(base + L.key0);
-            g.key[1] = (uint32_t*)(base + L.key1);
-            g.alive[0] = base + L.alive0;
-            g.alive[1] = base + L.alive1;
-            g.nxt = (int*)(base + L.nxt) + eo;
-            g.pool = (uint32_t*)(base + L.pool);
-            g.pflag = base + L.pflag;
-            g.cl = (ClusterRec*)(base + L.cl);
-            g.cl_lo[0] = 0; g.cl_hi[0] = cc0;
-            g.cl_lo[1] = cc0; g.cl_hi[1] = cc0 + D1 / 3 + 2;
-            g.pool_lo[0] = 0; g.pool_hi[0] = pc0;
-            g.pool_lo[1] = pc0; g.pool_hi[1] = L.pool_cap;
-            for (int r = 0; r < 2; r++) {
-                const bool have = !fresh && ((half_mask >> r) & 1);
-                g.nbc[r] = have ? task.half_nbc[r] : 0;
-                g.ncl[r] = have ? task.half_ncl[r] : g.cl_lo[r];
-                g.pool_used[r] = have ? task.half_pool[r] : g.pool_lo[r];
-            }
-            if (!whole) {  // the other orientation's regions belong to another CTA
-                const int other = my_o ^ 1;
-                g.pool_lo[other] = g.pool_hi[other] = g.pool_used[other] = 0;
-                g.ncl[other] = g.cl_lo[other];
-                g.cl_hi[other] = g.cl_lo[other];
-            }
-            g.bc[0] = (int*)(base + L.bc0);
-            g.bc[1] = (int*)(base + L.bc1);
-            g.act = (int*)(base + L.act) + co;
-            g.act_next = (int*)(base + L.act_next) + co;
-            g.changed = base + L.changed + co;
-            g.mult = (MultRec*)(base + L.mult);
-            g.nmult = 0;
-            g.out_mults = (int*)(base + L.out_mults);
-            g.rb_d = (double*)(base + L.rb_d);
-            g.rb_j = (int*)(base + L.rb_j);
-            g.rank = (int*)(base + L.rank);
-            g.pos = (int*)(base + L.pos);
-            g.xr = (int2*)(base + L.xr) + co;
-            g.redo = (int*)(base + L.redo) + co;
-            g.dscr = (double*)(base + L.dscr) + 2 * (size_t)eo;
-            g.tmp = (uint32_t*)(base + L.tmp) + eo;
-            g.tmpf = (uint8_t*)((uint32_t*)(base + L.tmp) + L.tmp_cap) + eo;
-            g.scratch_cap = whole ? D : 0;
-            g.status = fresh ? 0 : max(task.half_status[0], task.half_status[1]);
-            for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
-            g.nk[0] = D0;
-            g.nk[1] = D1;
-            g.cnt[0] = task.cnt[0];
-            g.cnt[1] = task.cnt[1];
-            g.area = (double)task.area;
-            g.level = task.level;
-        };
+        auto setup = [&](bool whole, bool fresh) { setup_view(g, task, ws, prm, pool_factor, my_o, whole, fresh); };
         // the dots (written once by K1) become the mutable matrix of one orientation
         auto stage = [&](int o) {
             const uint32_t* src = dots + task.dot_off + (o ? D0 : 0);
@@ -1674,6 +1683,78 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
     }
 }
 
+// ---- phase 1, one pass per launch ---------------------------------------------------------------
+// For large batches (thousands of GHMs) the fused kernel above is throughput-bound by instruction
+// fetch: co-resident CTAs sit in different passes of a 430 KB image and per-SM progress saturates
+// at about two CTAs (profiles/README.md).  Here every launch runs ONE pass (seed, enrich or join at
+// one gap size) over all (GHM, orientation) items, so all CTAs of an SM execute the same few KB of
+// code and many more of them can be resident; the per-orientation state (cluster count, pool
+// level, status) travels between launches in the task record.  Phase 2 then runs through
+// cluster_kernel with "phase 2 only" items.  Decisions and their order are unchanged.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
+                                                         int* next_item, const uint32_t* __restrict__ dots, uint8_t* ws,
+                                                         DevParams prm, int pool_factor, int* sm_slot, int pass, int gi)
+{
+    using K = KT<NT>;
+    constexpr int NW = K::NW;
+    __shared__ Ghm g;
+    __shared__ Red red;
+    __shared__ int sh_i[NW];
+    __shared__ int sh_s[8];
+    __shared__ int sh_task;
+    __shared__ long long prof2[8];
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
+    }
+    __syncthreads();
+    const int tid = VTID;
+    const int gap = prm.gaps[gi];
+    const double q = prm.q_value;
+    const bool first = (pass == 0 && gi == 0);
+    while (true) {
+        if (tid == 0) sh_task = atomicAdd(next_item, 1);
+        __syncthreads();
+        const int ti = sh_task;
+        if (ti >= n_items) break;
+        const int item = items[ti];   // GHM index * 2 + orientation
+        const int o = item & 1;
+        GhmTask& task = tasks[item >> 1];
+        // failed earlier (pool exhausted): the host retries the GHM.  Only this item's CTA writes
+        // half_status[o], so the test is uniform.
+        if (!first && task.half_status[o]) continue;
+        if (tid < 8) prof2[tid] = 0;
+        if (tid == 0) setup_view(g, task, ws, prm, pool_factor, o, false, first);
+        __syncthreads();
+        if (first) {
+            const int D0 = (int)task.cnt[0];
+            const uint32_t* src = dots + task.dot_off + (o ? D0 : 0);
+            const int n = (int)task.cnt[o];
+            for (int i = tid; i < n; i += NT) {
+                g.key[o][i] = src[i];
+                g.alive[o][i] = 1;
+            }
+            __syncthreads();
+        }
+        if (pass == 0) K::seed_pass(g, gap, o, q, sh_i, sh_s);
+        else if (pass == 1) {
+            if (g.nbc[o] > 0) K::enrich_pass(g, gap, o, o, q, sh_i, sh_s);
+        } else {
+            if (g.nbc[o] > 1) K::join_pass(g, gap, o, q, &red, sh_s, prof2);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            task.half_nbc[o] = g.nbc[o];
+            task.half_ncl[o] = g.ncl[o];
+            task.half_pool[o] = g.pool_used[o];
+            task.half_status[o] = g.status;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
@@ -1686,5 +1767,23 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
     case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    }
+}
+
+void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
+                        const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
+                        cudaStream_t st)
+{
+    if (n_items == 0) return;
+    // (threads, minimum CTAs per SM): the second number caps the registers per thread
+    #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi)
+    switch (nt) {
+    case 32: PASS_LAUNCH(32, 16); break;
+    case 3224: PASS_LAUNCH(32, 24); break;
+    case 3232: PASS_LAUNCH(32, 32); break;
+    case 128: PASS_LAUNCH(128, 4); break;
+    case 6412: PASS_LAUNCH(64, 12); break;
+    case 6416: PASS_LAUNCH(64, 16); break;
+    default: PASS_LAUNCH(64, 8); break;
     }
 }

@@ -41,6 +41,9 @@ void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_lis
 void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
                     const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
                     int grid, int nt, cudaStream_t st);
+void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
+                        const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
+                        cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
                          const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -276,6 +279,10 @@ struct iadh_ctx {
     } cls[4] = {{1025, 256, 2}, {193, 128, 4}, {0, 32, 16}, {0, 32, 16}};
     int n_classes = 3;
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
+    // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
+    int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
+    int64_t pass_ratio = 4096;
+    DBuf d_items1;
     cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // dataset (host mirror + device)
@@ -569,9 +576,33 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         // queue items: GHM * 4 + orientation mask.  The two orientations of a GHM are independent up to
         // the final enrichment; when both are heavy they get an item (a CTA) each, the heavier first --
         // that shortens the critical path of the heaviest GHMs, which is what a call waits for.
-        std::vector<int> items;
+        std::vector<int> items, items1;
         items.reserve(2 * (size_t)n_act);
+        // one pass per launch pays when the batch is throughput-bound: many GHMs and no single GHM
+        // that would become the critical path on a 32-thread CTA (total dots >> heaviest GHM's dots)
+        int64_t sum_d = 0, max_d = 1;
         for (int k = 0; k < n_act; k++) {
+            const int64_t D = (int64_t)tasks[order[k]].cnt[0] + tasks[order[k]].cnt[1];
+            sum_d += D;
+            max_d = std::max(max_d, D);
+        }
+        const bool pass_mode = n_act >= c->pass_min && c->prm.n_gaps > 0 && sum_d / max_d >= c->pass_ratio;
+        if (pass_mode) {
+            // phase 1 runs one pass per launch over (GHM, orientation) items, heaviest orientation first;
+            // phase 2 through the fused kernel with "phase 2 only" items
+            items1.reserve(2 * (size_t)n_act);
+            for (int k = 0; k < n_act; k++)
+                for (int o = 0; o < 2; o++)
+                    if ((tasks[order[k]].half_mask >> o) & 1) items1.push_back(order[k] * 2 + o);
+            std::stable_sort(items1.begin(), items1.end(), [&tasks](int a, int b) {
+                return tasks[a >> 1].cnt[a & 1] > tasks[b >> 1].cnt[b & 1];
+            });
+            for (int k = 0; k < n_act; k++) {
+                items.push_back(order[k] * 4);
+                tasks[order[k]].half_needed = 1;
+            }
+        }
+        for (int k = 0; k < n_act && !pass_mode; k++) {
             GhmTask& t = tasks[order[k]];
             if (t.half_mask == 3 && (int)std::min(t.cnt[0], t.cnt[1]) >= c->split_min) {
                 const int first = (t.cnt[1] > t.cnt[0]) ? 2 : 1;
@@ -587,12 +618,13 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(c->d_ws.ensure(ws_total + 256));
         if ((rc = upload(c->d_order, order.data(), 4 * (size_t)n_act, c->st))) return rc;
         if ((rc = upload(c->d_items, items.data(), 4 * (size_t)n_items, c->st))) return rc;
+        if (pass_mode && (rc = upload(c->d_items1, items1.data(), 4 * items1.size(), c->st))) return rc;
         CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
         st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act + 4 * n_items;
         CU(c->d_prof.ensure(sizeof(GhmProf) * (size_t)n + 16));
         CU(cudaMemsetAsync(c->d_prof.p, 0, sizeof(GhmProf) * (size_t)n, c->st));
-        CU(c->d_counter.ensure(16 + 4 * 1024));  // 4 class queues + per-SM arrival counters
-        CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024, c->st));
+        CU(c->d_counter.ensure(16 + 4 * 1024 + 4 * 64));  // 4 class queues + per-SM arrival counters + pass queues
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024 + 4 * 64, c->st));
         trace_mark(c->st, "host: order/ws + uploads");
         CU(cudaEventRecord(c->ev[5], c->st));
         {
@@ -601,6 +633,18 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             // the clustering of one GHM is a dependent chain that keeps about one warp busy)
             int* ctr = c->d_counter.as<int>();
             const int* ord = c->d_items.as<int>();
+            if (pass_mode) {
+                const int n1 = (int)items1.size();
+                const int grid = std::min(n1, c->sm_count * c->pass_per_sm);
+                for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0; gi++)
+                    for (int pass = 0; pass < 3; pass++) {
+                        launch_phase1_pass(c->d_tasks.as<GhmTask>(), c->d_items1.as<int>(), n1, ctr + 4 + 1024 + gi * 3 + pass,
+                                           c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, pass, gi,
+                                           grid, c->pass_nt, c->st);
+                        st.kernel_launches += n1 ? 1 : 0;
+                    }
+                trace_mark(c->st, "K2 phase 1 (one pass per launch)");
+            }
             CU(cudaEventRecord(c->ev_fork, c->st));
             int begin = 0, launched = 0;
             for (int k = 0; k < c->n_classes; k++) {
@@ -935,6 +979,9 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     for (int k = 0; k < 4; k++) c->prm.coop[k] = 48;
     if (const char* e = getenv("IADH_COOP")) sscanf(e, "%d,%d,%d,%d", &c->prm.coop[0], &c->prm.coop[1], &c->prm.coop[2], &c->prm.coop[3]);
     if (const char* e = getenv("IADH_SPLIT_MIN")) c->split_min = std::max(3, atoi(e));
+    if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
+    if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
+    if (const char* e = getenv("IADH_PASS_CFG")) sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);
     if (const char* e = getenv("IADH_CLASSES")) {  // "min_dots:threads:ctas_per_sm,..." heaviest class first
         int n = 0;
         const char* q = e;
@@ -961,7 +1008,7 @@ void iadh_destroy(iadh_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_prof,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_prof,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
                     &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
     for (DBuf* b : bufs) b->release();
