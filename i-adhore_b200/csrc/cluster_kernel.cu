@@ -1755,6 +1755,107 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
     }
 }
 
+// ---- phase 2, one stage per launch (same idea; whole-GHM view) ---------------------------------
+// stage 0: the four cross-orientation enrichments (GHM.cpp:186-189); 1: probability filter
+// (GHM.cpp:198-208); 2: the four enrichments again (:210-213); 3: metaclustering (:215-217) + the
+// measuring pass of K3.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
+                                                                int* next_item, const uint32_t* __restrict__ dots,
+                                                                uint8_t* ws, DevParams prm, int pool_factor, int* sm_slot,
+                                                                DatasetDev ds, ProfileDev pf, int hl, int stage)
+{
+    using K = KT<NT>;
+    constexpr int NW = K::NW;
+    __shared__ Ghm g;
+    __shared__ pk::PGhm pg;
+    __shared__ Red red;
+    __shared__ int sh_i[NW];
+    __shared__ int sh_s[8];
+    __shared__ int sh_task;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
+    }
+    __syncthreads();
+    const int tid = VTID;
+    const double q = prm.q_value;
+    while (true) {
+        if (tid == 0) sh_task = atomicAdd(next_item, 1);
+        __syncthreads();
+        const int ti = sh_task;
+        if (ti >= n_items) break;
+        GhmTask& task = tasks[items[ti] >> 2];
+        if (tid == 0) {
+            setup_view(g, task, ws, prm, pool_factor, 0, true, false);
+            if (stage > 0) {
+                g.nk[0] = task.half_nk[0];
+                g.nk[1] = task.half_nk[1];
+            }
+        }
+        __syncthreads();
+        if (g.status) {  // pool exhausted in an earlier launch: report, the host retries
+            if (tid == 0 && stage == 3) {
+                task.status = g.status;
+                task.n_mult = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (stage == 0) {  // orientations too small for phase-1 items are staged here
+            const int D0 = (int)task.cnt[0];
+            for (int o = 0; o < 2; o++) {
+                if ((task.half_mask >> o) & 1) continue;
+                const uint32_t* src = dots + task.dot_off + (o ? D0 : 0);
+                const int n = (int)task.cnt[o];
+                for (int i = tid; i < n; i += NT) {
+                    g.key[o][i] = src[i];
+                    g.alive[o][i] = 1;
+                }
+            }
+            __syncthreads();
+        }
+        if (stage == 0 || stage == 2) {
+            for (int e = 0; e < 4 && !g.status; e++) {
+                const int oc = (e == 1 || e == 2) ? 1 : 0;
+                const int om = (e == 1 || e == 3) ? 1 : 0;
+                if (g.nbc[oc] > 0 && g.nk[om] > 0) K::enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
+                __syncthreads();
+            }
+        } else if (stage == 1) {
+            K::filter_pass(g, prm, sh_s);
+            __syncthreads();
+        } else {
+            K::cluster_clusters(g, prm, &red, sh_i, sh_s);
+            __syncthreads();
+            if (tid == 0) {
+                task.status = g.status;
+                task.n_mult = g.status ? 0 : sh_s[0];
+                task.n_clusters = (g.ncl[0] - g.cl_lo[0]) + (g.ncl[1] - g.cl_lo[1]);
+            }
+            __syncthreads();
+            if (!g.status && task.n_mult > 0) {
+                if (hl) pk::measure_ghm<true>(pg, task, ws, ds, pf, pool_factor);
+                else pk::measure_ghm<false>(pg, task, ws, ds, pf, pool_factor);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && stage < 3) {
+            // every orientation's state now lives in the task record
+            task.half_mask = 3;
+            for (int o = 0; o < 2; o++) {
+                task.half_nbc[o] = g.nbc[o];
+                task.half_ncl[o] = g.ncl[o];
+                task.half_pool[o] = g.pool_used[o];
+                task.half_nk[o] = g.nk[o];
+            }
+            task.half_status[0] = task.half_status[1] = g.status;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
@@ -1767,6 +1868,22 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
     case 64: cluster_kernel<64><<<grid, 64, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     case 128: cluster_kernel<128><<<grid, 128, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
     default: cluster_kernel<256><<<grid, 256, 0, st>>>(tasks, profs, order, n_tasks, next_task, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0); break;
+    }
+}
+
+void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
+                         const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
+                         bool hl, int stage, int grid, int nt, cudaStream_t st)
+{
+    if (n_items == 0) return;
+    #define P2_LAUNCH(NT_, MB_) phase2_stage_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0, stage)
+    switch (nt) {
+    case 32: P2_LAUNCH(32, 16); break;
+    case 3224: P2_LAUNCH(32, 24); break;
+    case 128: P2_LAUNCH(128, 4); break;
+    case 6412: P2_LAUNCH(64, 12); break;
+    case 64: P2_LAUNCH(64, 8); break;
+    default: P2_LAUNCH(32, 32); break;
     }
 }
 

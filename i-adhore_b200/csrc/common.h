@@ -50,6 +50,7 @@ struct GhmTask {
     int32_t half_needed;  // in: number of queue items of this GHM (1 or 2)
     int32_t half_done;    // device: items finished
     int32_t half_nbc[2], half_ncl[2], half_pool[2], half_status[2];  // device: state handed to phase 2
+    int32_t half_nk[2];   // device: matrix sizes between the phase-2 launches of the pass-per-launch path
     int32_t pad2;
 };
 

@@ -44,6 +44,9 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
                         cudaStream_t st);
+void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
+                         const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
+                         bool hl, int stage, int grid, int nt, cudaStream_t st);
 void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
                          const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -392,6 +395,25 @@ static int upload(DBuf& d, const void* src, size_t bytes, cudaStream_t st)
     return IADH_OK;
 }
 
+// stable sort of ids, descending by key(id): counting sort when the key range is small (dots per
+// GHM are a few thousand; the batch can be 10^5 GHMs), comparison sort otherwise
+template <typename KeyFn>
+static void sort_desc_stable(std::vector<int>& ids, KeyFn key)
+{
+    uint64_t mx = 0;
+    for (int id : ids) mx = std::max<uint64_t>(mx, key(id));
+    if (mx > ((uint64_t)1 << 22) || ids.size() < 64) {
+        std::stable_sort(ids.begin(), ids.end(), [&key](int a, int b) { return key(a) > key(b); });
+        return;
+    }
+    std::vector<uint32_t> start((size_t)mx + 2, 0);
+    for (int id : ids) start[mx - key(id) + 1]++;
+    for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+    std::vector<int> out(ids.size());
+    for (int id : ids) out[start[mx - key(id)]++] = id;
+    ids.swap(out);
+}
+
 struct ProfileHost {
     ProfileDev dev;
     bool valid = false;
@@ -569,9 +591,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             t.half_needed = 1;
             order.push_back(i);
         }
-        std::stable_sort(order.begin(), order.end(), [&tasks](int a, int b) {
-            return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1] > (uint64_t)tasks[b].cnt[0] + tasks[b].cnt[1];
-        });
+        sort_desc_stable(order, [&tasks](int a) { return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1]; });
         const int n_act = (int)order.size();
         // queue items: GHM * 4 + orientation mask.  The two orientations of a GHM are independent up to
         // the final enrichment; when both are heavy they get an item (a CTA) each, the heavier first --
@@ -594,9 +614,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             for (int k = 0; k < n_act; k++)
                 for (int o = 0; o < 2; o++)
                     if ((tasks[order[k]].half_mask >> o) & 1) items1.push_back(order[k] * 2 + o);
-            std::stable_sort(items1.begin(), items1.end(), [&tasks](int a, int b) {
-                return tasks[a >> 1].cnt[a & 1] > tasks[b >> 1].cnt[b & 1];
-            });
+            sort_desc_stable(items1, [&tasks](int a) { return (uint64_t)tasks[a >> 1].cnt[a & 1]; });
             for (int k = 0; k < n_act; k++) {
                 items.push_back(order[k] * 4);
                 tasks[order[k]].half_needed = 1;
@@ -644,10 +662,17 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                         st.kernel_launches += n1 ? 1 : 0;
                     }
                 trace_mark(c->st, "K2 phase 1 (one pass per launch)");
+                const int grid2 = std::min(n_items, c->sm_count * c->pass_per_sm);
+                for (int stage = 0; stage < 4; stage++) {
+                    launch_phase2_stage(c->d_tasks.as<GhmTask>(), ord, n_items, ctr + 4 + 1024 + 32 + stage, c->d_dots.as<uint32_t>(),
+                                        c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2, c->pass_nt,
+                                        c->st);
+                    st.kernel_launches += n_items ? 1 : 0;
+                }
             }
             CU(cudaEventRecord(c->ev_fork, c->st));
             int begin = 0, launched = 0;
-            for (int k = 0; k < c->n_classes; k++) {
+            for (int k = 0; k < c->n_classes && !pass_mode; k++) {
                 // classes are cut by the GHM's total dots, so both orientations of a GHM share a class
                 int end = begin;
                 while (end < n_items) {

@@ -336,3 +336,22 @@ def test_device_tandem_remap_matches_reference_and_oracle():
         want = capi.remap_tandems(off, fam, gid, strand, gap, lib_path=capi.ORACLE_LIB, prefix="oracle_")
         assert np.array_equal(got, want), gap
     assert want.sum() > 1000
+
+
+def test_pass_per_launch_mode_is_invisible(monkeypatch):
+    """Phase 1 as one pass per launch (the path of large throughput-bound batches) forced on small
+    inputs, level 2 and profile searches: same bytes as the fused kernel / the reference."""
+    monkeypatch.setenv("IADH_PASS_MIN", "1")
+    monkeypatch.setenv("IADH_PASS_RATIO", "0")
+    tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
+    gpu = capi.load_product(tr.dataset)
+    errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL)
+    gpu.close()
+    assert not errs, errs[:3]
+    for mode in (capi.MH_BONFERRONI, capi.MH_FDR):
+        cfg = synth.config_small(seed=50 + mode)
+        ds, gpu, cpu = _pair(cfg, mode)
+        rg = gpu.level2_all_pairs()
+        assert rg.stats["kernel_launches"] > 30          # 10 gaps x 3 passes + phase 2 + build + pack
+        assert rg.bytes == cpu.level2_all_pairs().bytes
+        gpu.close()
