@@ -82,7 +82,10 @@ struct Red {
 
 // Everything below is parameterised on the CTA size NT: small GHMs run on 32- or 128-thread CTAs
 // (more GHMs in flight per SM, barriers almost free), heavy ones on 256 threads.
-template <int NT>
+// CP ("compact"): the big inlined helpers become single out-of-line copies.  The pass-per-launch
+// kernels are instruction-fetch bound (32 single-warp CTAs per SM), so a smaller hot image is worth
+// the call overhead there; the fused kernel keeps everything inline (latency first).
+template <int NT, bool CP = false>
 struct KT {
 static constexpr int NW = NT / 32;
 
@@ -289,7 +292,7 @@ static __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B
 static constexpr int COOP_MIN = 48;
 #define COOP_T(k) (g.coop[k])
 
-static __device__ void stats_coop(Ghm& g, ClusterRec& c)
+static __device__ void stats_coop_il(Ghm& g, ClusterRec& c)
 {
     const int tid = VTID;
     const int n = c.n;
@@ -333,6 +336,12 @@ static __device__ void stats_coop(Ghm& g, ClusterRec& c)
         cm::finish_stats(c, mrss, var_x, g.pool);
     }
     __syncthreads();
+}
+static __device__ __noinline__ void stats_coop_ni(Ghm& g, ClusterRec& c) { stats_coop_il(g, c); }
+static __device__ __forceinline__ void stats_coop(Ghm& g, ClusterRec& c)
+{
+    if (CP) stats_coop_ni(g, c);
+    else stats_coop_il(g, c);
 }
 
 static __device__ __forceinline__ int lower_bound_x(const uint32_t* a, int n, int x)
@@ -605,17 +614,25 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
 // ---- enrich -------------------------------------------------------------------------------
 
 // one (dot, cluster) test of GHM::enrichClusters (GHM.cpp:352-365)
-static __device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
+static __device__ __forceinline__ bool enrich_test_il(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
 {
     dist = cm::dist_to_point(c, x, y);
     if (dist >= limit) return false;
     return cm::r2_with_point(c, x, y) >= q && cm::in_interval(c, x, y);
 }
+static __device__ __noinline__ bool enrich_test_ni(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
+{
+    return enrich_test_il(c, x, y, limit, q, dist);
+}
+static __device__ __forceinline__ bool enrich_test(const ClusterRec& c, int x, int y, double limit, double q, double& dist)
+{
+    return CP ? enrich_test_ni(c, x, y, limit, q, dist) : enrich_test_il(c, x, y, limit, q, dist);
+}
 
 // all active clusters against one dot, in vector order (GHM.cpp:352-365).  g.xr[k] holds the
 // cluster's x-range widened by the gap: outside it distanceToPoint >= |dx| >= gap+1 >= bd, i.e. the
 // reference's own `distance < closest` test fails -- the prefilter rejects exactly those pairs.
-static __device__ __forceinline__ void enrich_scan(const Ghm& g, const int* act, int nact, int x, int y, double q,
+static __device__ __forceinline__ void enrich_scan_il(const Ghm& g, const int* act, int nact, int x, int y, double q,
                                                    double& bd, int& bk)
 {
     const int2* xr = g.xr;
@@ -643,6 +660,15 @@ static __device__ __forceinline__ void enrich_scan(const Ghm& g, const int* act,
             bk = k;
         }
     }
+}
+static __device__ __noinline__ void enrich_scan_ni(const Ghm& g, const int* act, int nact, int x, int y, double q, double& bd, int& bk)
+{
+    enrich_scan_il(g, act, nact, x, y, q, bd, bk);
+}
+static __device__ __forceinline__ void enrich_scan(const Ghm& g, const int* act, int nact, int x, int y, double q, double& bd, int& bk)
+{
+    if (CP) enrich_scan_ni(g, act, nact, x, y, q, bd, bk);
+    else enrich_scan_il(g, act, nact, x, y, q, bd, bk);
 }
 
 static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, int* sh_i, int* sh_s)
@@ -772,7 +798,7 @@ static __device__ bool closest_clusters(Ghm& g, int gap, int oi, int oj, double 
 // or equally close and earlier in vector order (the reference scans pairs lexicographically
 // with a strict '<').  Rejections by x / y extent are exact: every candidate distance of
 // distanceToCluster is a dpd between a point of A's hull and one of B's, and dpd >= |dx|, |dy|.
-static __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q,
+static __device__ __forceinline__ bool pair_better_il(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q,
                                             double bd, int brank, int rankJ, double& dout)
 {
     const double xgap = cm::maxd(cI.x_end1 - cJ.x_end2, cJ.x_end1 - cI.x_end2);
@@ -790,9 +816,19 @@ static __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRe
     dout = d;
     return true;
 }
+static __device__ __noinline__ bool pair_better_ni(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q, double bd,
+                                                   int brank, int rankJ, double& dout)
+{
+    return pair_better_il(g, cI, cJ, q, bd, brank, rankJ, dout);
+}
+static __device__ __forceinline__ bool pair_better(const Ghm& g, const ClusterRec& cI, const ClusterRec& cJ, double q, double bd,
+                                                   int brank, int rankJ, double& dout)
+{
+    return CP ? pair_better_ni(g, cI, cJ, q, bd, brank, rankJ, dout) : pair_better_il(g, cI, cJ, q, bd, brank, rankJ, dout);
+}
 
 // best partner of the cluster at position `pos` among the later positions (one warp)
-static __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
+static __device__ void join_row_il(Ghm& g, int o, int pos, int gap, double q)
 {
     const int lane = VTID & 31;
     const int n = g.nbc[o];
@@ -826,6 +862,12 @@ static __device__ void join_row(Ghm& g, int o, int pos, int gap, double q)
         g.rb_d[idI] = bd;
         g.rb_j[idI] = bj;
     }
+}
+static __device__ __noinline__ void join_row_ni(Ghm& g, int o, int pos, int gap, double q) { join_row_il(g, o, pos, gap, q); }
+static __device__ __forceinline__ void join_row(Ghm& g, int o, int pos, int gap, double q)
+{
+    if (CP) join_row_ni(g, o, pos, gap, q);
+    else join_row_il(g, o, pos, gap, q);
 }
 
 // GHM::joinClusters (GHM.cpp:392-404).  The reference rescans all pairs after every merge
@@ -1696,7 +1738,7 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
                                                          int* next_item, const uint32_t* __restrict__ dots, uint8_t* ws,
                                                          DevParams prm, int pool_factor, int* sm_slot, int pass, int gi)
 {
-    using K = KT<NT>;
+    using K = KT<NT, true>;
     constexpr int NW = K::NW;
     __shared__ Ghm g;
     __shared__ Red red;
@@ -1765,7 +1807,7 @@ __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, 
                                                                 uint8_t* ws, DevParams prm, int pool_factor, int* sm_slot,
                                                                 DatasetDev ds, ProfileDev pf, int hl, int stage)
 {
-    using K = KT<NT>;
+    using K = KT<NT, true>;
     constexpr int NW = K::NW;
     __shared__ Ghm g;
     __shared__ pk::PGhm pg;
