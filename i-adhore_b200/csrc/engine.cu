@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <numeric>
 #include <string>
@@ -299,7 +300,7 @@ struct iadh_ctx {
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
-    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_prof, d_sel, d_out_off, d_out, d_counter;
+    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_prof, d_plan, d_cnt, d_outs, d_sel, d_out_off, d_out, d_counter;
     DBuf d_pf_col, d_pf_gfam, d_pf_ggid, d_pf_gstrand, d_pf_fam, d_pf_gid, d_pf_num, d_pf_flags;
     HBuf h_tasks, h_misc, h_out, h_pf;
     // build_dots scratch
@@ -499,9 +500,79 @@ struct BatchOut {
     ~BatchOut() { packed.release(); }
 };
 
+// The task records stay on the device; only the fields that change hands travel, packed:
+//   cnt (device -> host after the count pass), the plan (host -> device), the outcome (device -> host).
+struct TaskPlan {
+    int64_t dot_off, ws_off, ws_bytes;
+    int32_t half_mask, half_needed;
+};
+struct TaskOut {
+    int64_t out_bytes;
+    int32_t status, n_mult, n_clusters, n_aps;
+};
+__global__ void gather_cnt_kernel(const GhmTask* __restrict__ tasks, int n, uint32_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[2 * i] = tasks[i].cnt[0];
+        out[2 * i + 1] = tasks[i].cnt[1];
+    }
+}
+__global__ void scatter_plan_kernel(GhmTask* __restrict__ tasks, int n, const TaskPlan* __restrict__ plan)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GhmTask& t = tasks[i];
+    const TaskPlan p = plan[i];
+    t.dot_off = p.dot_off;
+    t.ws_off = p.ws_off;
+    t.ws_bytes = p.ws_bytes;
+    t.half_mask = p.half_mask;
+    t.half_needed = p.half_needed;
+    t.half_done = 0;
+    t.status = 0;
+    t.n_mult = t.n_clusters = t.n_aps = 0;
+    t.out_bytes = 0;
+    for (int o = 0; o < 2; o++) t.half_nbc[o] = t.half_ncl[o] = t.half_pool[o] = t.half_status[o] = t.half_nk[o] = 0;
+}
+__global__ void gather_out_kernel(const GhmTask* __restrict__ tasks, int n, TaskOut* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TaskOut o;
+    o.out_bytes = tasks[i].out_bytes;
+    o.status = tasks[i].status;
+    o.n_mult = tasks[i].n_mult;
+    o.n_clusters = tasks[i].n_clusters;
+    o.n_aps = tasks[i].n_aps;
+    out[i] = o;
+}
+
+// host plan -> device task records (pinned staging, one copy, one kernel)
+static int send_plan(iadh_ctx* c, const std::vector<GhmTask>& tasks, iadh_stats& st)
+{
+    const int n = (int)tasks.size();
+    if (n == 0) return IADH_OK;
+    CU(c->h_tasks.ensure(sizeof(TaskPlan) * (size_t)n));
+    CU(c->d_plan.ensure(sizeof(TaskPlan) * (size_t)n));
+    TaskPlan* h = c->h_tasks.as<TaskPlan>();
+    for (int i = 0; i < n; i++) {
+        h[i].dot_off = tasks[i].dot_off;
+        h[i].ws_off = tasks[i].ws_off;
+        h[i].ws_bytes = tasks[i].ws_bytes;
+        h[i].half_mask = tasks[i].half_mask;
+        h[i].half_needed = tasks[i].half_needed;
+    }
+    CU(cudaMemcpyAsync(c->d_plan.p, h, sizeof(TaskPlan) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+    scatter_plan_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_plan.as<TaskPlan>());
+    st.h2d_bytes += (int64_t)sizeof(TaskPlan) * n;
+    st.kernel_launches += 1;
+    return IADH_OK;
+}
+
 // stages 1..4: build the dots of every task; on return tasks hold cnt/dot_off and d_dots the keys
 static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<GhmTask>& tasks, int64_t& total_dots,
-                       iadh_stats& st)
+                       iadh_stats& st, const std::function<int(std::vector<GhmTask>&)>& plan = nullptr)
 {
     const int n = (int)tasks.size();
     std::vector<int64_t> tile_prefix(n + 1, 0);
@@ -524,18 +595,29 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     CU(cudaEventRecord(c->ev[2], c->st));
     trace_mark(c->st, "K1 count + tile scan");
     st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
-    CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; tasks are read next)
-    st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
+    CU(c->d_cnt.ensure(8 * (size_t)n + 16));
+    CU(c->h_misc.ensure(8 * (size_t)n + 16));
+    gather_cnt_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_cnt.as<uint32_t>());
+    CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; the counts are read next)
+    st.d2h_bytes += 8 * (int64_t)n;
+    st.kernel_launches += 1;
     total_dots = 0;
-    for (int i = 0; i < n; i++) {
-        tasks[i].dot_off = total_dots;
-        total_dots += (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
+    {
+        const uint32_t* hc = c->h_misc.as<uint32_t>();
+        for (int i = 0; i < n; i++) {
+            tasks[i].cnt[0] = hc[2 * i];
+            tasks[i].cnt[1] = hc[2 * i + 1];
+            tasks[i].dot_off = total_dots;
+            total_dots += (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
+        }
     }
     if (total_dots > 0x7fffffff00ll) return fail(IADH_ERR_CAPACITY, "too many dots in one call");
     CU(c->d_dots.ensure(4 * (size_t)total_dots + 16));
-    CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
-    st.h2d_bytes += (int64_t)sizeof(GhmTask) * n;
+    // the clustering plan depends on the counts only: it goes to the device together with dot_off,
+    // so the fill pass and the clustering follow each other without another host round trip
+    if (plan && (rc = plan(tasks))) return rc;
+    if ((rc = send_plan(c, tasks, st))) return rc;
     CU(cudaEventRecord(c->ev[3], c->st));
     launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
                       c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
@@ -561,14 +643,19 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         out.packed_bytes = 4;
         return IADH_OK;
     }
-    if ((rc = build_stage(c, hl, pf, tasks, total_dots, st))) return rc;
-
+    // host-side plan of the clustering stage: depends only on the dot counts, so it is made between
+    // the count pass and the fill pass (inside build_stage) and travels to the device with dot_off
     int pool_factor = c->pool_factor;
-    std::vector<int> order;
-    for (int attempt = 0;; attempt++) {
+    std::vector<int> order, items, items1;
+    size_t ws_total = 0;
+    bool pass_mode = false;
+    int n_act = 0;
+    auto make_plan = [&](std::vector<GhmTask>& tasks) -> int {
+        items.clear();
+        items1.clear();
+        ws_total = 0;
         // active GHMs: at least anchor_points dots (GHM.cpp:159), heaviest first
         order.clear();
-        size_t ws_total = 0;
         for (int i = 0; i < n; i++) {
             GhmTask& t = tasks[i];
             const int64_t D = (int64_t)t.cnt[0] + t.cnt[1];
@@ -592,11 +679,10 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             order.push_back(i);
         }
         sort_desc_stable(order, [&tasks](int a) { return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1]; });
-        const int n_act = (int)order.size();
+        n_act = (int)order.size();
         // queue items: GHM * 4 + orientation mask.  The two orientations of a GHM are independent up to
         // the final enrichment; when both are heavy they get an item (a CTA) each, the heavier first --
         // that shortens the critical path of the heaviest GHMs, which is what a call waits for.
-        std::vector<int> items, items1;
         items.reserve(2 * (size_t)n_act);
         // one pass per launch pays when the batch is throughput-bound: many GHMs and no single GHM
         // that would become the critical path on a 32-thread CTA (total dots >> heaviest GHM's dots)
@@ -606,7 +692,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             sum_d += D;
             max_d = std::max(max_d, D);
         }
-        const bool pass_mode = n_act >= c->pass_min && c->prm.n_gaps > 0 && sum_d / max_d >= c->pass_ratio;
+        pass_mode = n_act >= c->pass_min && c->prm.n_gaps > 0 && sum_d / max_d >= c->pass_ratio;
         if (pass_mode) {
             // phase 1 runs one pass per launch over (GHM, orientation) items, heaviest orientation first;
             // phase 2 through the fused kernel with "phase 2 only" items
@@ -632,13 +718,20 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 t.half_needed = 1;
             }
         }
-        const int n_items = (int)items.size();
         CU(c->d_ws.ensure(ws_total + 256));
-        if ((rc = upload(c->d_order, order.data(), 4 * (size_t)n_act, c->st))) return rc;
+        return IADH_OK;
+    };
+    if ((rc = build_stage(c, hl, pf, tasks, total_dots, st, make_plan))) return rc;
+
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 0) {  // rare: the clustering stage is rerun with a larger anchor-point pool
+            if ((rc = make_plan(tasks))) return rc;
+            if ((rc = send_plan(c, tasks, st))) return rc;
+        }
+        const int n_items = (int)items.size();
         if ((rc = upload(c->d_items, items.data(), 4 * (size_t)n_items, c->st))) return rc;
         if (pass_mode && (rc = upload(c->d_items1, items1.data(), 4 * items1.size(), c->st))) return rc;
-        CU(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(GhmTask) * (size_t)n, cudaMemcpyHostToDevice, c->st));
-        st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 4 * n_act + 4 * n_items;
+        st.h2d_bytes += 4 * (int64_t)n_items + 4 * (int64_t)items1.size();
         CU(c->d_prof.ensure(sizeof(GhmProf) * (size_t)n + 16));
         CU(cudaMemsetAsync(c->d_prof.p, 0, sizeof(GhmProf) * (size_t)n, c->st));
         CU(c->d_counter.ensure(16 + 4 * 1024 + 4 * 64));  // 4 class queues + per-SM arrival counters + pass queues
@@ -701,9 +794,23 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(cudaEventRecord(c->ev[6], c->st));
         trace_mark(c->st, "K2 cluster");
         // (K3's measuring pass ran as the tail of every GHM inside K2)
-        CU(cudaMemcpyAsync(tasks.data(), c->d_tasks.p, sizeof(GhmTask) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(c->d_outs.ensure(sizeof(TaskOut) * (size_t)n));
+        CU(c->h_misc.ensure(sizeof(TaskOut) * (size_t)n));
+        gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
+        CU(cudaMemcpyAsync(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
-        st.d2h_bytes += (int64_t)sizeof(GhmTask) * n;
+        st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
+        st.kernel_launches += 1;
+        {
+            const TaskOut* ho = c->h_misc.as<TaskOut>();
+            for (int i = 0; i < n; i++) {
+                tasks[i].out_bytes = ho[i].out_bytes;
+                tasks[i].status = ho[i].status;
+                tasks[i].n_mult = ho[i].n_mult;
+                tasks[i].n_clusters = ho[i].n_clusters;
+                tasks[i].n_aps = ho[i].n_aps;
+            }
+        }
         if (g_trace) {
             std::vector<GhmProf> pr((size_t)n);
             cudaMemcpy(pr.data(), c->d_prof.p, sizeof(GhmProf) * (size_t)n, cudaMemcpyDeviceToHost);
@@ -734,7 +841,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             }
         if (!retry) break;
         if (attempt >= 3) return fail(IADH_ERR_CAPACITY, "anchor-point pool exhausted even at factor %d", pool_factor);
-        pool_factor *= 4;  // rare: rerun the clustering stage with a larger AP pool
+        pool_factor *= 4;
     }
 
     trace_mark(c->st, "tasks D2H");
@@ -1033,7 +1140,7 @@ void iadh_destroy(iadh_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_prof,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
                     &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
     for (DBuf* b : bufs) b->release();
