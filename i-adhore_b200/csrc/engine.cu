@@ -745,12 +745,17 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             int* ctr = c->d_counter.as<int>();
             const int* ord = c->d_items.as<int>();
             if (pass_mode) {
+                // single-warp CTAs: always the cooperative merge / insert / statistics paths (one code path,
+                // all 32 lanes busy) unless IADH_COOP says otherwise
+                DevParams pprm = c->prm;
+                if (!getenv("IADH_COOP"))
+                    for (int k = 0; k < 4; k++) pprm.coop[k] = 0;
                 const int n1 = (int)items1.size();
                 const int grid = std::min(n1, c->sm_count * c->pass_per_sm);
                 for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0; gi++)
                     for (int pass = 0; pass < 3; pass++) {
                         launch_phase1_pass(c->d_tasks.as<GhmTask>(), c->d_items1.as<int>(), n1, ctr + 4 + 1024 + gi * 3 + pass,
-                                           c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, pass, gi,
+                                           c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi,
                                            grid, c->pass_nt, c->st);
                         st.kernel_launches += n1 ? 1 : 0;
                     }
@@ -758,7 +763,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 const int grid2 = std::min(n_items, c->sm_count * c->pass_per_sm);
                 for (int stage = 0; stage < 4; stage++) {
                     launch_phase2_stage(c->d_tasks.as<GhmTask>(), ord, n_items, ctr + 4 + 1024 + 32 + stage, c->d_dots.as<uint32_t>(),
-                                        c->d_ws.as<uint8_t>(), c->prm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2, c->pass_nt,
+                                        c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2, c->pass_nt,
                                         c->st);
                     st.kernel_launches += n_items ? 1 : 0;
                 }
