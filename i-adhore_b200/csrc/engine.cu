@@ -286,6 +286,10 @@ struct iadh_ctx {
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
     int64_t pass_ratio = 4096;
+    // workspace bytes per chunk.  Default: one chunk.  Measured on config 4: chunks small enough for L2
+    // (256 MB of workspace) serialise 52 x 34 short launches and take 241 ms instead of 87 ms.
+    int64_t pass_chunk_bytes = (int64_t)1 << 60;
+    DBuf d_passctr;
     DBuf d_items1;
     cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -646,7 +650,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     // host-side plan of the clustering stage: depends only on the dot counts, so it is made between
     // the count pass and the fill pass (inside build_stage) and travels to the device with dot_off
     int pool_factor = c->pool_factor;
-    std::vector<int> order, items, items1;
+    std::vector<int> order, items, items1, chunk_k, chunk_i1;
     size_t ws_total = 0;
     bool pass_mode = false;
     int n_act = 0;
@@ -696,15 +700,28 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         if (pass_mode) {
             // phase 1 runs one pass per launch over (GHM, orientation) items, heaviest orientation first;
             // phase 2 through the fused kernel with "phase 2 only" items
+            // The batch can be cut into chunks of GHMs (contiguous in the heaviest-first order,
+            // IADH_PASS_CHUNK_MB of workspace each) whose 34 launches run before the next chunk starts, so
+            // that a GHM's state is re-read from L2 instead of HBM between its passes; off by default
+            // (see pass_chunk_bytes).
             items1.reserve(2 * (size_t)n_act);
-            for (int k = 0; k < n_act; k++)
+            chunk_k.clear();
+            chunk_i1.clear();
+            int64_t acc = 0;
+            for (int k = 0; k < n_act; k++) {
+                if (k == 0 || acc + tasks[order[k]].ws_bytes > c->pass_chunk_bytes) {
+                    chunk_k.push_back(k);
+                    chunk_i1.push_back((int)items1.size());
+                    acc = 0;
+                }
+                acc += tasks[order[k]].ws_bytes;
                 for (int o = 0; o < 2; o++)
                     if ((tasks[order[k]].half_mask >> o) & 1) items1.push_back(order[k] * 2 + o);
-            sort_desc_stable(items1, [&tasks](int a) { return (uint64_t)tasks[a >> 1].cnt[a & 1]; });
-            for (int k = 0; k < n_act; k++) {
                 items.push_back(order[k] * 4);
                 tasks[order[k]].half_needed = 1;
             }
+            chunk_k.push_back(n_act);
+            chunk_i1.push_back((int)items1.size());
         }
         for (int k = 0; k < n_act && !pass_mode; k++) {
             GhmTask& t = tasks[order[k]];
@@ -750,23 +767,31 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 DevParams pprm = c->prm;
                 if (!getenv("IADH_COOP"))
                     for (int k = 0; k < 4; k++) pprm.coop[k] = 0;
-                const int n1 = (int)items1.size();
-                const int grid = std::min(n1, c->sm_count * c->pass_per_sm);
-                for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0; gi++)
-                    for (int pass = 0; pass < 3; pass++) {
-                        launch_phase1_pass(c->d_tasks.as<GhmTask>(), c->d_items1.as<int>(), n1, ctr + 4 + 1024 + gi * 3 + pass,
-                                           c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi,
-                                           grid, c->pass_nt, c->st);
-                        st.kernel_launches += n1 ? 1 : 0;
+                const int n_chunks = (int)chunk_k.size() - 1;
+                CU(c->d_passctr.ensure(4 * 36 * (size_t)n_chunks + 16));
+                CU(cudaMemsetAsync(c->d_passctr.p, 0, 4 * 36 * (size_t)n_chunks, c->st));
+                for (int ch = 0; ch < n_chunks; ch++) {
+                    int* pc = c->d_passctr.as<int>() + 36 * ch;
+                    const int* it1 = c->d_items1.as<int>() + chunk_i1[ch];
+                    const int n1 = chunk_i1[ch + 1] - chunk_i1[ch];
+                    const int grid = std::min(n1, c->sm_count * c->pass_per_sm);
+                    for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0 && n1 > 0; gi++)
+                        for (int pass = 0; pass < 3; pass++) {
+                            launch_phase1_pass(c->d_tasks.as<GhmTask>(), it1, n1, pc + gi * 3 + pass, c->d_dots.as<uint32_t>(),
+                                               c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi, grid, c->pass_nt, c->st);
+                            st.kernel_launches += 1;
+                        }
+                    const int* it2 = ord + chunk_k[ch];
+                    const int n2 = chunk_k[ch + 1] - chunk_k[ch];
+                    const int grid2 = std::min(n2, c->sm_count * c->pass_per_sm);
+                    for (int stage = 0; stage < 4; stage++) {
+                        launch_phase2_stage(c->d_tasks.as<GhmTask>(), it2, n2, pc + 30 + stage, c->d_dots.as<uint32_t>(),
+                                            c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2,
+                                            c->pass_nt, c->st);
+                        st.kernel_launches += 1;
                     }
-                trace_mark(c->st, "K2 phase 1 (one pass per launch)");
-                const int grid2 = std::min(n_items, c->sm_count * c->pass_per_sm);
-                for (int stage = 0; stage < 4; stage++) {
-                    launch_phase2_stage(c->d_tasks.as<GhmTask>(), ord, n_items, ctr + 4 + 1024 + 32 + stage, c->d_dots.as<uint32_t>(),
-                                        c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2, c->pass_nt,
-                                        c->st);
-                    st.kernel_launches += n_items ? 1 : 0;
                 }
+                trace_mark(c->st, "K2 pass-per-launch (all chunks)");
             }
             CU(cudaEventRecord(c->ev_fork, c->st));
             int begin = 0, launched = 0;
@@ -1118,6 +1143,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     if (const char* e = getenv("IADH_SPLIT_MIN")) c->split_min = std::max(3, atoi(e));
     if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
+    if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char* e = getenv("IADH_PASS_CFG")) sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);
     if (const char* e = getenv("IADH_CLASSES")) {  // "min_dots:threads:ctas_per_sm,..." heaviest class first
         int n = 0;
@@ -1145,7 +1171,7 @@ void iadh_destroy(iadh_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
                     &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
     for (DBuf* b : bufs) b->release();
