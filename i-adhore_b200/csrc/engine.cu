@@ -722,6 +722,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             }
             chunk_k.push_back(n_act);
             chunk_i1.push_back((int)items1.size());
+            if (chunk_k.size() == 2)  // one chunk: heaviest orientation first over the whole batch
+                sort_desc_stable(items1, [&tasks](int a) { return (uint64_t)tasks[a >> 1].cnt[a & 1]; });
         }
         for (int k = 0; k < n_act && !pass_mode; k++) {
             GhmTask& t = tasks[order[k]];
