@@ -355,3 +355,15 @@ def test_pass_per_launch_mode_is_invisible(monkeypatch):
         assert rg.stats["kernel_launches"] > 30          # 10 gaps x 3 passes + phase 2 + build + pack
         assert rg.bytes == cpu.level2_all_pairs().bytes
         gpu.close()
+
+
+def test_pass_per_launch_mode_retries_pool_exhaustion(monkeypatch):
+    """The rerun with a larger anchor-point pool also works when the state travels between launches."""
+    monkeypatch.setenv("IADH_PASS_MIN", "1")
+    monkeypatch.setenv("IADH_PASS_RATIO", "0")
+    monkeypatch.setenv("IADH_POOL_FACTOR", "1")
+    tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
+    gpu = capi.load_product(tr.dataset)
+    errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL, check_dots=False)
+    gpu.close()
+    assert not errs, errs[:3]
