@@ -1736,7 +1736,8 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
                                                          int* next_item, const uint32_t* __restrict__ dots, uint8_t* ws,
-                                                         DevParams prm, int pool_factor, int* sm_slot, int pass, int gi)
+                                                         DevParams prm, int pool_factor, int* sm_slot, int pass, int gi,
+                                                         unsigned long long* dbg)
 {
     using K = KT<NT, true>;
     constexpr int NW = K::NW;
@@ -1792,6 +1793,9 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
             task.half_ncl[o] = g.ncl[o];
             task.half_pool[o] = g.pool_used[o];
             task.half_status[o] = g.status;
+            if (dbg && pass == 2)  // IADH_TRACE: join sub-phase cycles of the whole batch
+                for (int k = 0; k < 8; k++)
+                    if (prof2[k]) atomicAdd(&dbg[k], (unsigned long long)prof2[k]);
         }
         __syncthreads();
     }
@@ -1931,11 +1935,11 @@ void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* nex
 
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
-                        cudaStream_t st)
+                        cudaStream_t st, unsigned long long* dbg)
 {
     if (n_items == 0) return;
     // (threads, minimum CTAs per SM): the second number caps the registers per thread
-    #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi)
+    #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi, dbg)
     switch (nt) {
     case 32: PASS_LAUNCH(32, 16); break;
     case 3224: PASS_LAUNCH(32, 24); break;

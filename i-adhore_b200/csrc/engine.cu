@@ -44,7 +44,7 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
                     int grid, int nt, cudaStream_t st);
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
-                        cudaStream_t st);
+                        cudaStream_t st, unsigned long long* dbg = nullptr);
 void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                          const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
                          bool hl, int stage, int grid, int nt, cudaStream_t st);
@@ -770,8 +770,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 if (!getenv("IADH_COOP"))
                     for (int k = 0; k < 4; k++) pprm.coop[k] = 0;
                 const int n_chunks = (int)chunk_k.size() - 1;
-                CU(c->d_passctr.ensure(4 * 36 * (size_t)n_chunks + 16));
-                CU(cudaMemsetAsync(c->d_passctr.p, 0, 4 * 36 * (size_t)n_chunks, c->st));
+                CU(c->d_passctr.ensure(4 * 36 * (size_t)n_chunks + 80));
+                CU(cudaMemsetAsync(c->d_passctr.p, 0, 4 * 36 * (size_t)n_chunks + 80, c->st));
                 for (int ch = 0; ch < n_chunks; ch++) {
                     int* pc = c->d_passctr.as<int>() + 36 * ch;
                     const int* it1 = c->d_items1.as<int>() + chunk_i1[ch];
@@ -780,7 +780,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                     for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0 && n1 > 0; gi++)
                         for (int pass = 0; pass < 3; pass++) {
                             launch_phase1_pass(c->d_tasks.as<GhmTask>(), it1, n1, pc + gi * 3 + pass, c->d_dots.as<uint32_t>(),
-                                               c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi, grid, c->pass_nt, c->st);
+                                               c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi, grid, c->pass_nt, c->st,
+                                               g_trace ? (unsigned long long*)(c->d_passctr.as<int>() + 36 * n_chunks) : nullptr);
                             st.kernel_launches += 1;
                         }
                     const int* it2 = ord + chunk_k[ch];
@@ -794,6 +795,12 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                     }
                 }
                 trace_mark(c->st, "K2 pass-per-launch (all chunks)");
+                if (g_trace) {
+                    unsigned long long d[8];
+                    cudaMemcpy(d, c->d_passctr.as<int>() + 36 * n_chunks, sizeof d, cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "[iadh]   join passes, CTA-cycles of the batch: init %.1fM reduce %.1fM locate %.1fM merge %.1fM erase %.1fM refresh %.1fM redo %.1fM, %llu merges\n",
+                            d[0] / 1e6, d[1] / 1e6, d[2] / 1e6, d[3] / 1e6, d[4] / 1e6, d[5] / 1e6, d[6] / 1e6, d[7]);
+                }
             }
             CU(cudaEventRecord(c->ev_fork, c->st));
             int begin = 0, launched = 0;
