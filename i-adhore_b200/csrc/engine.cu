@@ -285,7 +285,7 @@ struct iadh_ctx {
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
-    int64_t pass_ratio = 4096;
+    int64_t pass_ratio = 1500;  // (config 3: 1,276 -> fused, tail-bound either way; 1/8 of config 4: 3,680 -> passes)
     // workspace bytes per chunk.  Default: one chunk.  Measured on config 4: chunks small enough for L2
     // (256 MB of workspace) serialise 52 x 34 short launches and take 241 ms instead of 87 ms.
     int64_t pass_chunk_bytes = (int64_t)1 << 60;
