@@ -285,6 +285,9 @@ struct iadh_ctx {
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
+    // a batch whose clustering workspace would exceed this is bisected (level-2 calls): set from the
+    // device's memory at create time, IADH_WS_BUDGET_MB overrides
+    int64_t ws_budget = (int64_t)1 << 62;
     int64_t pass_ratio = 1500;  // (config 3: 1,276 -> fused, tail-bound either way; 1/8 of config 4: 3,680 -> passes)
     // workspace bytes per chunk.  Default: one chunk.  Measured on config 4: chunks small enough for L2
     // (256 MB of workspace) serialise 52 x 34 short launches and take 241 ms instead of 87 ms.
@@ -494,6 +497,8 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
     out.valid = true;
     return IADH_OK;
 }
+
+static const int RC_SPLIT = 1000;  // internal: batch exceeds the workspace budget
 
 struct BatchOut {
     std::vector<GhmTask> tasks;  // final state (cnt, n_mult, out_bytes ...)
@@ -737,6 +742,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 t.half_needed = 1;
             }
         }
+        // too much for one go: the caller bisects the batch (the count pass that led here is cheap)
+        if ((int64_t)ws_total > c->ws_budget && n > 1 && !hl) return RC_SPLIT;
         CU(c->d_ws.ensure(ws_total + 256));
         return IADH_OK;
     };
@@ -976,13 +983,71 @@ static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, 
     ProfileDev nopf;
     memset(&nopf, 0, sizeof nopf);
     int rc = run_batch(c, false, nopf, tasks, b);
+    double acc_build = 0, acc_cluster = 0;
+    bool was_split = false;
+    if (rc == RC_SPLIT) {
+        // bisect until every part fits the workspace budget; parts are consecutive ranges of the pair
+        // sequence, so their packed streams simply follow each other
+        was_split = true;
+        std::vector<std::pair<int64_t, int64_t>> todo(1, std::make_pair((int64_t)0, n));
+        std::vector<uint8_t> bytes;
+        memset(&b.st, 0, sizeof b.st);
+        b.ghm_index.clear();
+        rc = IADH_OK;
+        while (!todo.empty() && rc == IADH_OK) {
+            const std::pair<int64_t, int64_t> r = todo.back();
+            todo.pop_back();
+            std::vector<GhmTask> part(tasks.begin() + r.first, tasks.begin() + r.second);
+            for (size_t i = 0; i < part.size(); i++) {
+                const GhmTask keep = tasks[r.first + i];
+                init_task(part[i]);
+                part[i].x_list = keep.x_list; part[i].y_list = keep.y_list;
+                part[i].x_object_id = keep.x_object_id; part[i].y_object_id = keep.y_object_id;
+                part[i].level = keep.level; part[i].area = keep.area;
+                part[i].seq = (int32_t)i;
+            }
+            BatchOut pb;
+            memset(&pb.st, 0, sizeof pb.st);
+            rc = run_batch(c, false, nopf, part, pb);
+            if (rc == RC_SPLIT) {
+                const int64_t mid = (r.first + r.second) / 2;
+                todo.push_back(std::make_pair(mid, r.second));   // (stack: the first half is done first)
+                todo.push_back(std::make_pair(r.first, mid));
+                rc = IADH_OK;
+                continue;
+            }
+            if (rc != IADH_OK) break;
+            cudaStreamSynchronize(c->st);
+            float m1 = 0, m2 = 0, m3 = 0;
+            cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
+            cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
+            acc_build += m1 + m2;
+            acc_cluster += m3;
+            bytes.insert(bytes.end(), pb.packed.as<uint8_t>() + 4, pb.packed.as<uint8_t>() + pb.packed_bytes);
+            for (int32_t gidx : pb.ghm_index) b.ghm_index.push_back(gidx + (int32_t)r.first);
+            b.st.n_ghm += pb.st.n_ghm; b.st.n_dots += pb.st.n_dots; b.st.n_multiplicons += pb.st.n_multiplicons;
+            b.st.n_baseclusters += pb.st.n_baseclusters; b.st.n_anchorpoints += pb.st.n_anchorpoints;
+            b.st.kernel_launches += pb.st.kernel_launches; b.st.h2d_bytes += pb.st.h2d_bytes; b.st.d2h_bytes += pb.st.d2h_bytes;
+        }
+        if (rc == IADH_OK) {
+            if (b.packed.ensure(bytes.size() + 4) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of pinned host memory");
+            else {
+                if (!bytes.empty()) memcpy(b.packed.as<uint8_t>() + 4, bytes.data(), bytes.size());
+                b.packed_bytes = bytes.size() + 4;
+            }
+        }
+    }
     cudaEventRecord(e1, c->st);
     cudaEventSynchronize(e1);
     if (rc == IADH_OK) {
         float ms = 0, m1 = 0, m2 = 0, m3 = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         b.st.total_ms = ms;
-        if (n > 0) {
+        if (was_split) {
+            b.st.build_ms = acc_build;
+            b.st.cluster_ms = acc_cluster;
+        } else if (n > 0) {
             cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
             cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
             b.st.build_ms = m1 + m2;
@@ -1150,6 +1215,11 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     for (int k = 0; k < 4; k++) c->prm.coop[k] = 48;
     if (const char* e = getenv("IADH_COOP")) sscanf(e, "%d,%d,%d,%d", &c->prm.coop[0], &c->prm.coop[1], &c->prm.coop[2], &c->prm.coop[3]);
     if (const char* e = getenv("IADH_SPLIT_MIN")) c->split_min = std::max(3, atoi(e));
+    {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) c->ws_budget = (int64_t)(tot / 2);
+    }
+    if (const char* e = getenv("IADH_WS_BUDGET_MB")) c->ws_budget = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;

@@ -367,3 +367,23 @@ def test_pass_per_launch_mode_retries_pool_exhaustion(monkeypatch):
     errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL, check_dots=False)
     gpu.close()
     assert not errs, errs[:3]
+
+
+def test_level2_batches_are_bisected_to_fit_memory(monkeypatch):
+    """A level-2 call whose clustering workspace exceeds the budget is bisected into consecutive
+    ranges of the pair sequence (IADH_WS_BUDGET_MB forces it here): same stream, same GHM indices."""
+    cfg = synth.config_small(seed=61)
+    ds, gpu, cpu = _pair(cfg, capi.MH_BONFERRONI)
+    want = cpu.level2_all_pairs()
+    whole = gpu.level2_all_pairs()
+    gpu.close()
+    monkeypatch.setenv("IADH_WS_BUDGET_MB", "1")
+    gpu2 = capi.load_product(ds)
+    gpu2.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    split = gpu2.level2_all_pairs()
+    assert split.stats["kernel_launches"] > 3 * whole.stats["kernel_launches"]     # really split
+    assert split.bytes == whole.bytes == want.bytes
+    assert np.array_equal(split.ghm_index, want.ghm_index)
+    for k in ("n_ghm", "n_dots", "n_multiplicons", "n_anchorpoints"):
+        assert split.stats[k] == whole.stats[k]
+    gpu2.close()
