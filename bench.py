@@ -409,11 +409,17 @@ def main():
     cl_ms = float(np.mean([s["cluster_ms"] for s in l2s]))
     bd_ms = float(np.mean([s["build_ms"] for s in l2s]))
     ach = b_cluster / (cl_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "cluster_kernel (K2, level-2 launch)", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": ncu_traffic("cluster_kernel"), "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": b_cluster,
+    pass_mode = l2s[0]["kernel_launches"] > 30     # K2 ran as 30 phase1_pass + 4 phase2_stage launches
+    roof = {"bound": "hbm",
+            "kernel": ("K2 of the level-2 call: phase1_pass_kernel x30 + phase2_stage_kernel x4 (one pass per launch), taken as "
+                       "one unit" if pass_mode else "K2 of the level-2 call: cluster_kernel (size-class launches, concurrent)"),
+            "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": ncu_traffic("K2 pass-per-launch" if pass_mode else "cluster_kernel"),
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": b_cluster,
             "launch_ms": cl_ms,
-            "note": "latency/dependency-bound greedy clustering: its figure of merit is GHM/s, not GB/s (SURVEY 8d)"}
+            "note": "latency/dependency-bound greedy clustering (issue-bound in the pass-per-launch form): its figure of merit "
+                    "is GHM/s, not GB/s (SURVEY 8d); traffic = dram bytes of the same launches under ncu, config 4 "
+                    "(40x the algorithmic bytes: every pass re-reads the live state of all GHMs, DESIGN.md 6)"}
     ach_b = b_build / (bd_ms * 1e-3) / 1e9 if bd_ms > 0 else None
     roof_build = {"bound": "hbm", "kernel": "l2_build_kernel count + tile scan + fill (K1, level-2 launch)", "achieved": ach_b, "peak": peak,
                   "unit": "GB/s", "frac": (ach_b / peak) if ach_b else None, "traffic": None,
