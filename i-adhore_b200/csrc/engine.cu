@@ -1418,6 +1418,17 @@ void iadh_free_result(iadh_result* r)
 }
 void iadh_trim(void) { g_cache.trim(); }
 
+int iadh_warmup(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(IADH_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));  // creates the primary context (0.5-1 s in a fresh process)
+    return IADH_OK;
+}
+
 int iadh_event_record(iadh_ctx* c, int slot)
 {
     if (!c || slot < 0 || slot >= 4) return fail(IADH_ERR_ARG, "iadh_event_record: bad argument");

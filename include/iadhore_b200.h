@@ -153,6 +153,11 @@ void iadh_free_result(iadh_result* r);
  * cache (contexts are cheap to re-create); iadh_trim returns them to the driver. */
 void iadh_trim(void);
 
+/* Creates the CUDA context of `device` (0.5-1 s in a fresh process).  Optional: a caller with host work
+ * to do first (the reference reads its gene lists and family table for about that long) can run it
+ * on a helper thread at start-up, so that iadh_create does not wait for it. */
+int iadh_warmup(int device);
+
 /* Device-side timing for benchmarks: CUDA events on the context's own stream (slots 0..3). */
 int iadh_event_record(iadh_ctx* ctx, int slot);
 int iadh_event_elapsed_ms(iadh_ctx* ctx, int from_slot, int to_slot, double* ms);

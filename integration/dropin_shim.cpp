@@ -18,6 +18,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "DataSet.h"
@@ -62,6 +63,24 @@ void report()
             "device call %.3fs (device time %.3fs), unpack+filter %.3fs\n",
             B.n_hl, B.n_ghm, B.n_returned, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
 }
+
+// The CUDA context is created on a helper thread while the reference's main() reads the gene lists
+// and the family table (same order of magnitude); ensure_context() joins it.
+struct Warmup {
+    std::thread th;
+    Warmup()
+    {
+        const char* dev = getenv("IADH_DEVICE");
+        const int d = dev ? atoi(dev) : 0;
+        th = std::thread([d]() { iadh_warmup(d); });
+    }
+    void join()
+    {
+        if (th.joinable()) th.join();
+    }
+    ~Warmup() { join(); }
+};
+Warmup g_warmup;
 
 int intern(std::map<std::string, int>& m, const std::string& s)
 {
@@ -116,6 +135,7 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     d.num_id = num.data();
     d.flags = flags.data();
     const char* dev = getenv("IADH_DEVICE");
+    g_warmup.join();
     check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
     atexit(report);
 

@@ -289,6 +289,7 @@ const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
 int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; return IADH_OK; }
 void oracle_free_result(oracle_result* r) { delete r; }
 void oracle_trim(void) {}
+int oracle_warmup(int) { return IADH_OK; }
 
 // GeneList::remapTandemsFamily (GeneList.cpp:143-200), restated sequentially: the three passes in
 // the reference's order, remapTo() (Gene.cpp:51-62) sets the gene's flag and clears the target's.
