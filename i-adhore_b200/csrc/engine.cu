@@ -280,8 +280,8 @@ struct iadh_ctx {
     // K2 size classes, heaviest first: GHMs with >= min_dots dots run on nt-thread CTAs, per_sm CTAs per SM
     struct SizeClass {
         int min_dots, nt, per_sm;
-    } cls[4] = {{1025, 256, 2}, {193, 128, 4}, {0, 32, 16}, {0, 32, 16}};
-    int n_classes = 3;
+    } cls[4] = {{257, 256, 2}, {0, 64, 4}, {0, 32, 16}, {0, 32, 16}};  // (measured on config 3 / 4 profile searches and config 3 level 2)
+    int n_classes = 2;
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
