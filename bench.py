@@ -197,7 +197,7 @@ def run_reference(cfg, n_profiles, threads, tmpdir, max_pairs=-1):
     step's own mix: the first `max_pairs` list pairs of the level-2 sequence and `n_profiles`
     profile searches over all lists (a GHMProfile costs the CPU ~20x a list pair, so the
     proportion of the two kinds of GHM is part of the workload)."""
-    if os.path.exists(REF_HARNESS):
+    if os.path.exists(REF_HARNESS) and not os.environ.get("IADH_BENCH_NO_REF"):
         ini = synth.write_reference_inputs(cfg, tmpdir, n_threads=threads)
         t0 = time.time()
         p = subprocess.run([REF_HARNESS, ini, "-", "--time", "--threads", str(threads), "--max-profiles", str(n_profiles),
@@ -211,23 +211,28 @@ def run_reference(cfg, n_profiles, threads, tmpdir, max_pairs=-1):
         t = float(l2.group(5)) + float(hl.group(5))
         return dict(kind="reference", units=units, seconds=t, l2_pairs=int(l2.group(1)), l2_s=float(l2.group(5)),
                     hl_ghm=int(hl.group(2)), hl_s=float(hl.group(5)), dots=int(l2.group(2)), process_wall_s=wall)
-    # oracle port, multi-threaded
+    # oracle port, multi-threaded (the reference binary is absent on this machine)
     ds = ingest.dataset_from_synth(cfg)
     eng = capi.Engine(capi.ORACLE_LIB, "oracle_", ds)
     import ctypes as C
     eng.lib.oracle_set_threads(eng.ctx, C.c_int(threads))
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    xs, ys = capi.plan_pairs(np.diff(ds.list_off), lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    if max_pairs >= 0:
+        xs, ys = xs[:max_pairs], ys[:max_pairs]
     t0 = time.time()
-    r = eng.level2_all_pairs()
+    r = eng.level2_pairs(xs, ys)
     t1 = time.time()
     profs = make_profiles(ds, r.bytes, n_profiles)
     t2 = time.time()
-    units, stats, _ = hot_path_step(eng, profs, 0, 1)
+    hl_units = 0
+    for m, p in profs:
+        eng.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
+        eng.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
+        hl_units += eng.profile_search(p).stats["n_ghm"]
     t3 = time.time()
-    hl_units = units - r.stats["n_ghm"]
-    hl_s = (t3 - t2) - (t1 - t0)  # the step re-ran L2; subtract its earlier time as estimate
-    return dict(kind="port", units=units, seconds=(t1 - t0) + max(hl_s, 0.0), l2_pairs=r.stats["n_ghm"], l2_s=t1 - t0,
-                hl_ghm=hl_units, hl_s=max(hl_s, 0.0), dots=r.stats["n_dots"], process_wall_s=t3 - t0)
+    return dict(kind="port", units=len(xs) + hl_units, seconds=(t1 - t0) + (t3 - t2), l2_pairs=len(xs), l2_s=t1 - t0,
+                hl_ghm=hl_units, hl_s=max(t3 - t2, 1e-9), dots=r.stats["n_dots"], process_wall_s=t3 - t0)
 
 
 def main():
