@@ -289,7 +289,6 @@ static __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B
 // var_x accumulated sequentially in multiset order.  That order is kept: all threads compute the
 // per-AP terms, one thread adds them up in order (a pure dependent-add chain, no loads or
 // multiplies on it).  Short clusters stay on one thread.
-static constexpr int COOP_MIN = 48;
 #define COOP_T(k) (g.coop[k])
 
 static __device__ void stats_coop_il(Ghm& g, ClusterRec& c)
@@ -1597,7 +1596,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
         const int my_o = (my_mask == 2) ? 1 : 0;
         GhmTask& task = tasks[item >> 2];
         GhmProf& tprof = profs[item >> 2];
-        const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1], D = D0 + D1;
+        const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1];
         const int half_mask = task.half_mask;
         const bool run_p1 = my_mask != 0;
         const double q = prm.q_value;

@@ -120,12 +120,5 @@ struct DatasetDev {
     const int32_t* fam_list;    // [f * (n_lists + 1) + l] = first slot of family f at or after list l; may be null
 };
 
-// Build tiles: <=256 consecutive columns of one GHM.
-struct BuildTile {
-    int32_t ghm;   // index into the task array
-    int32_t x0;    // first column
-    int32_t nx;    // columns in this tile
-    int32_t pad;
-};
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

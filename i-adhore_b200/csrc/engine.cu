@@ -48,8 +48,6 @@ void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next
 void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                          const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
                          bool hl, int stage, int grid, int nt, cudaStream_t st);
-void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
-                         const ProfileDev& pf, int pool_factor, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st);
 
@@ -307,9 +305,9 @@ struct iadh_ctx {
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
-    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_order, d_items, d_prof, d_plan, d_cnt, d_outs, d_sel, d_out_off, d_out, d_counter;
-    DBuf d_pf_col, d_pf_gfam, d_pf_ggid, d_pf_gstrand, d_pf_fam, d_pf_gid, d_pf_num, d_pf_flags;
-    HBuf h_tasks, h_misc, h_out, h_pf;
+    DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_items, d_prof, d_plan, d_cnt, d_outs, d_sel, d_out_off, d_out, d_counter;
+    DBuf d_pf_col;  // the profile descriptor (column groups + raw arrays), one block
+    HBuf h_tasks, h_misc, h_pf;
     // build_dots scratch
     std::vector<int64_t> bd_cnt;
     std::vector<int32_t> bd_dots;
@@ -1250,13 +1248,11 @@ void iadh_destroy(iadh_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
-                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_order, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
-                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_pf_gfam, &c->d_pf_ggid,
-                    &c->d_pf_gstrand, &c->d_pf_fam, &c->d_pf_gid, &c->d_pf_num, &c->d_pf_flags};
+                    &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col};
     for (DBuf* b : bufs) b->release();
     c->h_tasks.release();
     c->h_misc.release();
-    c->h_out.release();
     c->h_pf.release();
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -6,9 +6,9 @@
 // "false" anchor points of further matching profile segments; then
 // Multiplicon::pack / BaseCluster::pack / AnchorPoint::pack (Multiplicon.cpp:210-240,
 // BaseCluster.cpp:751-797, AnchorPoint.h:103-118), byte for byte.
-// Two launches over the GHMs that produced multiplicons: measure (sizes + in-place
-// normalisation) and write; the host scans the per-GHM sizes in between.  One CTA per GHM,
-// one warp per base cluster, one lane per anchor point.
+// The measuring pass (sizes + in-place normalisation, pack_measure.cuh) runs as the tail of each GHM
+// inside the clustering kernels; the host scans the per-GHM sizes; this file holds the writer.  One
+// CTA per GHM, one warp per base cluster, one lane per anchor point.
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -45,17 +45,6 @@ __device__ __forceinline__ void put_ap(uint8_t* q, int gx, int gy, int x, int y,
     put32(q + 8, x);
     put32(q + 12, y);
     q[16] = (uint8_t)real;
-}
-
-template <bool HL>
-__global__ void __launch_bounds__(PT) pack_measure_kernel(GhmTask* tasks, const int* __restrict__ sel, int n_sel,
-                                                          uint8_t* ws, DatasetDev ds, ProfileDev pf, int pool_factor)
-{
-    __shared__ PGhm p;
-    if (blockIdx.x >= n_sel) return;
-    GhmTask& task = tasks[sel[blockIdx.x]];
-    if (task.n_mult == 0 || task.status != 0) return;  // uniform: nothing to serialise
-    pk::measure_ghm<HL>(p, task, ws, ds, pf, pool_factor);
 }
 
 template <bool HL>
@@ -186,14 +175,6 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
 }
 
 }  // namespace
-
-void launch_pack_measure(bool hl, GhmTask* tasks, const int* sel, int n_sel, uint8_t* ws, const DatasetDev& ds,
-                         const ProfileDev& pf, int pool_factor, cudaStream_t st)
-{
-    if (n_sel == 0) return;
-    if (hl) pack_measure_kernel<true><<<n_sel, PT, 0, st>>>(tasks, sel, n_sel, ws, ds, pf, pool_factor);
-    else pack_measure_kernel<false><<<n_sel, PT, 0, st>>>(tasks, sel, n_sel, ws, ds, pf, pool_factor);
-}
 
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st)
