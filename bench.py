@@ -326,7 +326,7 @@ def main():
         return [outs[r * mx:r * mx + sizes[r]] for r in range(world)]
 
     t_setup = time.time()
-    ds = ingest.dataset_from_synth(cfg)
+    ds = ingest.dataset_from_synth(cfg, device=local_rank)   # tandem remapping on the device (iadh_remap_tandems)
     eng = capi.load_product(ds, device=local_rank)
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
     r0 = eng.level2_all_pairs()          # untimed: provides the multiplicons the profiles are made from

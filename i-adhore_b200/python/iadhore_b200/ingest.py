@@ -64,18 +64,30 @@ def remap_tandems_family(fam: Sequence[int], gid: Sequence[int], strand: Sequenc
     return remapped
 
 
-def build_dataset(lists: List[List[Gene]], tandem_gap: int) -> Dataset:
+def build_dataset(lists: List[List[Gene]], tandem_gap: int, device=None) -> Dataset:
     """lists in ini order (list index == GeneList::getID()).  numID counts every gene of
-    every list in order (DataSet.cpp:76-81); gene-ID strings are interned densely."""
+    every list in order (DataSet.cpp:76-81); gene-ID strings are interned densely.
+    device = CUDA ordinal: the tandem remapping runs on the GPU (iadh_remap_tandems, the product
+    path); None: the pure-Python mirror above (CPU tests)."""
     gid_map: Dict[str, int] = {}
     off = [0]
     fam_o, gid_o, num_o, flg_o = [], [], [], []
     cnt = 0
-    for lst in lists:
+    rem_all = None
+    if device is not None:
+        from . import capi
+        raw_off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+        gids = [gid_map.setdefault(g[0], len(gid_map)) for lst in lists for g in lst]
+        rem_all = capi.remap_tandems(raw_off, np.fromiter((g[2] for lst in lists for g in lst), np.int32, int(raw_off[-1])),
+                                     np.asarray(gids, np.int32),
+                                     np.fromiter((g[1] for lst in lists for g in lst), np.uint8, int(raw_off[-1])),
+                                     tandem_gap, device=device)
+    for li, lst in enumerate(lists):
         fam = [g[2] for g in lst]
         strand = [g[1] for g in lst]
         gid = [gid_map.setdefault(g[0], len(gid_map)) for g in lst]
-        rem = remap_tandems_family(fam, gid, strand, tandem_gap)
+        rem = (rem_all[raw_off[li]:raw_off[li + 1]] if rem_all is not None
+               else remap_tandems_family(fam, gid, strand, tandem_gap))
         keep = np.nonzero(~rem)[0]
         fam_o.append(np.asarray(fam, np.int32)[keep])
         gid_o.append(np.asarray(gid, np.int32)[keep])
@@ -88,10 +100,10 @@ def build_dataset(lists: List[List[Gene]], tandem_gap: int) -> Dataset:
                    cat(flg_o, np.uint8))
 
 
-def dataset_from_synth(cfg, data=None) -> Dataset:
+def dataset_from_synth(cfg, data=None, device=None) -> Dataset:
     from . import synth
     if data is None:
         data = synth.generate(cfg)
     lists = [lst for g in cfg.genomes for lst in data[g.name]]
     tg = cfg.tandem_gap if cfg.tandem_gap is not None else cfg.gap_size // 2  # Settings.cpp:337-343
-    return build_dataset(lists, tg)
+    return build_dataset(lists, tg, device=device)

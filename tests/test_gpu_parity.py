@@ -387,3 +387,12 @@ def test_level2_batches_are_bisected_to_fit_memory(monkeypatch):
     for k in ("n_ghm", "n_dots", "n_multiplicons", "n_anchorpoints"):
         assert split.stats[k] == whole.stats[k]
     gpu2.close()
+
+
+def test_ingest_with_device_tandem_remap_equals_the_host_mirror():
+    """The dataset bench.py builds (tandem remapping on the device) is the one the CPU tests build."""
+    for cfg in (synth.config_small(seed=71), synth.config_c5(0.02)):
+        a = ingest.dataset_from_synth(cfg)
+        b = ingest.dataset_from_synth(cfg, device=0)
+        for k in ("list_off", "fam", "gid", "num_id", "flags"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (cfg.name, k)
