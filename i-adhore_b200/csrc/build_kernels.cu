@@ -112,9 +112,18 @@ __device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev
         const int fy = ds.fam[best], gy = ds.gid[best], sy = fl & 1;
         bool e0 = false, e1 = false;
         for (int g = g0; g < g1; g++) {
-            if (pf.grp_fam[g] != fy) continue;
-            const int gg = pf.grp_gid[g];
-            if (gg >= 0 && gg == gy) continue;  // Gene.cpp:20: ID != other.ID
+            if (ds.pairs) {
+                // table_type=pairs: a group is one gene; it pairs with `best` iff best is in its bucket
+                // (Gene.cpp:24-27) -- buckets overlap, so family equality does not decide it
+                const int f = pf.grp_fam[g];
+                const int b0 = ds.fam_ptr[f], b1 = ds.fam_ptr[f + 1];
+                const int m = lower_bound_i32(ds.fam_members, b0, b1, best);
+                if (m >= b1 || ds.fam_members[m] != best) continue;
+            } else {
+                if (pf.grp_fam[g] != fy) continue;
+                const int gg = pf.grp_gid[g];
+                if (gg >= 0 && gg == gy) continue;  // Gene.cpp:20: ID != other.ID
+            }
             if (pf.grp_strand[g] == sy) e1 = true;
             else e0 = true;
         }

@@ -118,6 +118,10 @@ struct DatasetDev {
     const int32_t* plus_prefix; // [slot] = members with strand 1 in slots [0, slot)  (n + 1 entries)
     const int32_t* self_slot;   // per element: its slot in fam_members
     const int32_t* fam_list;    // [f * (n_lists + 1) + l] = first slot of family f at or after list l; may be null
+    // table_type=pairs (iadh_create_pairs): "family" = gene id and bucket f holds the positions of the
+    // partners of gene f (Gene.cpp:24-27), so buckets overlap and an element is not in its own bucket;
+    // fam[] = gid[], self_slot = first slot at or after the element, no gene-ID test anywhere
+    int pairs;
 };
 
 

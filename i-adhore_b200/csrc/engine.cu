@@ -301,6 +301,7 @@ struct iadh_ctx {
     std::vector<int32_t> masked_cnt;  // per list
     std::vector<int32_t> index_to_list;
     int n_fam = 0;
+    bool pairs = false;   // table_type=pairs (iadh_create_pairs): families are gene ids, buckets hold partners
     DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members, d_mem_y, d_plus_prefix, d_self_slot, d_fam_list;
     DatasetDev ds;
     DevParams prm;
@@ -438,7 +439,8 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
         for (int s = 0; s < S; s++) {
             const size_t k = (size_t)s * L + x;
             if (p->flags[k] & IADH_F_GAP) continue;
-            const int f = p->fam[k], gid = p->gid[k];
+            const int gid = p->gid[k];
+            const int f = c->pairs ? gid : p->fam[k];
             const uint8_t st = p->flags[k] & IADH_F_STRAND;
             if (f < 0 || f >= c->n_fam) continue;  // family absent from the dataset: no partner possible
             size_t g = g0;
@@ -474,7 +476,11 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
         memcpy(h + o_gstr, gstrand.data(), G);
     }
     if (n) {
-        memcpy(h + o_fam, p->fam, 4 * n);
+        if (c->pairs) {  // bucket key = gene id; ids outside the pair table have no bucket
+            int32_t* hf = (int32_t*)(h + o_fam);
+            for (size_t k = 0; k < n; k++) hf[k] = (p->gid[k] >= 0 && p->gid[k] < c->n_fam) ? p->gid[k] : -1;
+        } else
+            memcpy(h + o_fam, p->fam, 4 * n);
         memcpy(h + o_gid, p->gid, 4 * n);
         memcpy(h + o_num, p->num_id, 4 * n);
         memcpy(h + o_flg, p->flags, n);
@@ -955,6 +961,11 @@ struct Timer {
 static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, iadh_result** out)
 {
     if (n < 0 || n > 0x3fffffff) return fail(IADH_ERR_ARG, "bad pair count");
+    if (c->pairs)
+        for (int m : c->masked_cnt)
+            if (m)
+                return fail(IADH_ERR_STATE, "level-2 call in pairs mode while elements are masked: the reference's pairs-mode "
+                                          "build skips masked elements (ListElement.cpp:25), this one does not");
     std::vector<GhmTask> tasks((size_t)n);
     for (int64_t i = 0; i < n; i++) {
         GhmTask& t = tasks[i];
@@ -1071,9 +1082,35 @@ extern "C" {
 const char* iadh_last_error(void) { return g_err.c_str(); }
 const char* iadh_version(void) { return "iadhore_b200 0.1 (sm_100a)"; }
 
+static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                       int device, iadh_ctx** out);
+
 int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
 {
-    if (!d || !out || d->n_lists < 0 || (d->n_lists > 0 && (!d->list_off || !d->fam || !d->gid || !d->num_id || !d->flags)))
+    if (!d || (d->n_lists > 0 && !d->fam)) return fail(IADH_ERR_ARG, "iadh_create: bad dataset descriptor");
+    return create_impl(d, nullptr, nullptr, 0, device, out);
+}
+
+int iadh_create_pairs(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                      int device, iadh_ctx** out)
+{
+    if (!pair_ptr || n_genes < 0) return fail(IADH_ERR_ARG, "iadh_create_pairs: bad pair table");
+    for (int32_t g = 0; g < n_genes; g++)
+        if (pair_ptr[g + 1] < pair_ptr[g]) return fail(IADH_ERR_ARG, "iadh_create_pairs: pair_ptr is not ascending at gene %d", g);
+    if (pair_ptr[0] != 0 || (pair_ptr[n_genes] > 0 && !pair_ids)) return fail(IADH_ERR_ARG, "iadh_create_pairs: bad pair table");
+    for (int64_t k = 0; k < pair_ptr[n_genes]; k++)
+        if (pair_ids[k] < 0 || pair_ids[k] >= n_genes)
+            return fail(IADH_ERR_ARG, "iadh_create_pairs: partner id %d out of range (%d genes)", pair_ids[k], n_genes);
+    return create_impl(d, pair_ptr, pair_ids, n_genes, device, out);
+}
+
+}  // extern "C"
+
+static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                       int device, iadh_ctx** out)
+{
+    const bool pairs = pair_ptr != nullptr;
+    if (!d || !out || d->n_lists < 0 || (d->n_lists > 0 && (!d->list_off || !d->gid || !d->num_id || !d->flags)))
         return fail(IADH_ERR_ARG, "iadh_create: bad dataset descriptor");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1099,6 +1136,9 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->list_off.assign(d->list_off, d->list_off + d->n_lists + 1);
     const int64_t total = d->n_lists ? c->list_off[d->n_lists] : 0;
     if (total >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 elements"); }
+    c->pairs = pairs;
+    // the bucket key of an element: its family, or in pairs mode its gene id
+    const int32_t* key = pairs ? d->gid : d->fam;
     int max_fam = -1;
     for (int l = 0; l < d->n_lists; l++) {
         const int64_t sz = c->list_off[l + 1] - c->list_off[l];
@@ -1112,10 +1152,11 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
         }
     }
     for (int64_t i = 0; i < total; i++) {
-        if (d->fam[i] < 0) { delete c; return fail(IADH_ERR_ARG, "element %lld has a negative family id", (long long)i); }
-        max_fam = std::max(max_fam, d->fam[i]);
+        if (key[i] < 0) { delete c; return fail(IADH_ERR_ARG, "element %lld has a negative %s id", (long long)i, pairs ? "gene" : "family"); }
+        if (pairs && key[i] >= n_genes) { delete c; return fail(IADH_ERR_ARG, "element %lld: gene id %d outside the pair table (%d genes)", (long long)i, key[i], n_genes); }
+        max_fam = std::max(max_fam, key[i]);
     }
-    c->n_fam = max_fam + 1;
+    c->n_fam = pairs ? n_genes : max_fam + 1;
     c->flags.resize((size_t)total);
     c->masked_cnt.assign(d->n_lists, 0);
     for (int l = 0; l < d->n_lists; l++)
@@ -1128,17 +1169,51 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
             c->flags[i] = f;
         }
     // family CSR: members ascending by global element index
-    std::vector<int32_t> fam_ptr(c->n_fam + 1, 0), members((size_t)total);
-    for (int64_t i = 0; i < total; i++) fam_ptr[d->fam[i] + 1]++;
-    for (int f = 0; f < c->n_fam; f++) fam_ptr[f + 1] += fam_ptr[f];
-    {
+    std::vector<int32_t> fam_ptr(c->n_fam + 1, 0), members;
+    if (!pairs) {
+        members.resize((size_t)total);
+        for (int64_t i = 0; i < total; i++) fam_ptr[key[i] + 1]++;
+        for (int f = 0; f < c->n_fam; f++) fam_ptr[f + 1] += fam_ptr[f];
         std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
-        for (int64_t i = 0; i < total; i++) members[cur[d->fam[i]]++] = (int32_t)i;
+        for (int64_t i = 0; i < total; i++) members[cur[key[i]]++] = (int32_t)i;
+    } else {
+        // pairs mode: bucket g = positions of the partners of gene g, i.e. every y with
+        // Gene::isPairWith(g, y) (Gene.cpp:24-27).  occ = positions per gene id (ascending); only
+        // genes that occur in a list get a bucket.
+        std::vector<int32_t> occ_ptr((size_t)n_genes + 1, 0), occ((size_t)total);
+        for (int64_t i = 0; i < total; i++) occ_ptr[key[i] + 1]++;
+        for (int g = 0; g < n_genes; g++) occ_ptr[g + 1] += occ_ptr[g];
+        {
+            std::vector<int32_t> cur(occ_ptr.begin(), occ_ptr.end() - 1);
+            for (int64_t i = 0; i < total; i++) occ[cur[key[i]]++] = (int32_t)i;
+        }
+        int64_t m_total = 0;
+        for (int g = 0; g < n_genes; g++) {
+            int64_t n = 0;
+            if (occ_ptr[g + 1] > occ_ptr[g])
+                for (int64_t k = pair_ptr[g]; k < pair_ptr[g + 1]; k++) n += occ_ptr[pair_ids[k] + 1] - occ_ptr[pair_ids[k]];
+            m_total += n;
+            if (m_total >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 partner positions"); }
+            fam_ptr[g + 1] = (int32_t)m_total;
+        }
+        members.resize((size_t)m_total);
+        for (int g = 0; g < n_genes; g++) {
+            if (fam_ptr[g + 1] == fam_ptr[g]) continue;
+            int32_t* b = members.data() + fam_ptr[g];
+            int32_t* w = b;
+            for (int64_t k = pair_ptr[g]; k < pair_ptr[g + 1]; k++) {
+                const int p = pair_ids[k];
+                for (int32_t q = occ_ptr[p]; q < occ_ptr[p + 1]; q++) *w++ = occ[q];
+            }
+            std::sort(b, w);
+            if (std::adjacent_find(b, w) != w) { delete c; return fail(IADH_ERR_ARG, "pair table lists a partner of gene %d twice", g); }
+        }
     }
+    const int64_t n_mem = (int64_t)members.size();
     // level-2 build tables (build_kernels.cu): member records, strand prefix counts, own slot of
     // every element, duplicate-gene-ID flag, and the (family, list) -> first slot table
-    std::vector<uint32_t> mem_y((size_t)total);
-    std::vector<int32_t> plus_prefix((size_t)total + 1, 0), self_slot((size_t)total);
+    std::vector<uint32_t> mem_y((size_t)n_mem);
+    std::vector<int32_t> plus_prefix((size_t)n_mem + 1, 0), self_slot((size_t)total);
     {
         int l = 0;
         std::vector<int32_t> elem_list((size_t)total);
@@ -1146,20 +1221,25 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
             while (i >= c->list_off[l + 1]) l++;
             elem_list[i] = l;
         }
-        for (int64_t m = 0; m < total; m++) {
+        for (int64_t m = 0; m < n_mem; m++) {
             const int32_t e = members[m];
             const int strand = c->flags[e] & 1;
             mem_y[m] = ((uint32_t)(e - c->list_off[elem_list[e]]) << 1) | (uint32_t)strand;
             plus_prefix[m + 1] = plus_prefix[m] + strand;
-            self_slot[e] = (int32_t)m;
+            if (!pairs) self_slot[e] = (int32_t)m;
         }
+        if (pairs)  // the cut `y <= x` of the self comparison (GHM.cpp:125): partners before the element
+            for (int64_t i = 0; i < total; i++)
+                self_slot[i] = (int32_t)(std::lower_bound(members.begin() + fam_ptr[key[i]], members.begin() + fam_ptr[key[i] + 1],
+                                                          (int32_t)i) - members.begin());
         int max_gid = -1;
         for (int64_t i = 0; i < total; i++) max_gid = std::max(max_gid, d->gid[i]);
         std::vector<uint8_t> seen((size_t)max_gid + 2, 0);
         for (int64_t i = 0; i < total; i++)
             if (d->gid[i] >= 0 && seen[d->gid[i]] < 2) seen[d->gid[i]]++;
-        for (int64_t i = 0; i < total; i++)
-            if (d->gid[i] < 0 || seen[d->gid[i]] > 1) c->flags[i] |= 8;
+        if (!pairs)  // (pairs mode has no gene-ID test: a gene is never in its own pair set, GenePairs.cpp:25)
+            for (int64_t i = 0; i < total; i++)
+                if (d->gid[i] < 0 || seen[d->gid[i]] > 1) c->flags[i] |= 8;
     }
     // (IADH_NO_FAM_TABLE: test knob for the binary-search fallback used when the table would be too large)
     const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
@@ -1169,7 +1249,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     if (!rc) rc = upload(c->d_plus_prefix, plus_prefix.data(), 4 * plus_prefix.size(), c->st);
     if (!rc) rc = upload(c->d_self_slot, self_slot.data(), 4 * self_slot.size(), c->st);
     if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
-    if (!rc) rc = upload(c->d_fam, d->fam, 4 * (size_t)total, c->st);
+    if (!rc) rc = upload(c->d_fam, key, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_num_id, d->num_id, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_flags, c->flags.data(), (size_t)total, c->st);
@@ -1195,6 +1275,7 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     c->ds.plus_prefix = c->d_plus_prefix.as<int32_t>();
     c->ds.self_slot = c->d_self_slot.as<int32_t>();
     c->ds.fam_list = have_table ? c->d_fam_list.as<int32_t>() : nullptr;
+    c->ds.pairs = pairs ? 1 : 0;
     sort_lists(c);
     // defaults = shipped datasetI/II settings, Bonferroni (Settings.cpp:4-9)
     memset(&c->prm, 0, sizeof c->prm);
@@ -1241,6 +1322,8 @@ int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
     *out = c;
     return IADH_OK;
 }
+
+extern "C" {
 
 void iadh_destroy(iadh_ctx* c)
 {

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
                 const int pos_real = a + (c.has_false ? scr[rs] : 0);
                 bool seen = false;
                 for (int s = 0; s < pf.S; s++)
-                    if (seg_match(pf, s, x, fy, gy)) {
+                    if (pk::seg_match(ds, pf, s, x, yg, fy, gy)) {
                         const int gx = pf.num_id[s * pf.L + x];
                         if (!seen) put_ap(q + 17 * pos_real, gx, gyn, x, y, 1);
                         else put_ap(q + 17 * (pos_false++), gx, gyn, x, y, 0);

@@ -36,10 +36,24 @@ __device__ inline void pghm_init(PGhm& p, const GhmTask& task, uint8_t* ws, int 
 }
 
 // does profile element (segment n, column x) pair with dataset element yg?  (Gene.cpp:17-30)
-__device__ __forceinline__ bool seg_match(const ProfileDev& pf, int n, int x, int fy, int gy)
+// family mode: same family, different gene ID; pairs mode: yg is in the bucket of the element's gene
+__device__ __forceinline__ bool seg_match(const DatasetDev& ds, const ProfileDev& pf, int n, int x, int yg, int fy, int gy)
 {
     const int idx = n * pf.L + x;
     if (pf.flags[idx] & 2) return false;
+    if (ds.pairs) {
+        const int f = pf.fam[idx];   // = the element's gene id (upload_profile)
+        if (f < 0) return false;
+        int lo = ds.fam_ptr[f];
+        const int b1 = ds.fam_ptr[f + 1];
+        int hi = b1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ds.fam_members[mid] < yg) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo < b1 && ds.fam_members[lo] == yg;
+    }
     return pf.fam[idx] == fy && pf.gid[idx] != gy;
 }
 
@@ -114,7 +128,7 @@ __device__ void measure_ghm(PGhm& p, GhmTask& task, uint8_t* ws, const DatasetDe
                     const int yg = (int)(yoff + KEY_Y(ap[k]));
                     const int fy = ds.fam[yg], gy = ds.gid[yg];
                     int matches = 0;
-                    for (int s = 0; s < pf.S; s++) matches += seg_match(pf, s, x, fy, gy) ? 1 : 0;
+                    for (int s = 0; s < pf.S; s++) matches += seg_match(ds, pf, s, x, yg, fy, gy) ? 1 : 0;
                     nf = matches > 1 ? matches - 1 : 0;
                 }
                 int inc = nf;

@@ -52,7 +52,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["remap_tandems", "create", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
+EXPORTS = ["remap_tandems", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
@@ -77,6 +77,13 @@ class Dataset:
     gid: np.ndarray
     num_id: np.ndarray
     flags: np.ndarray
+    # table_type=pairs: CSR over gene ids (gid -> sorted partner gids); None = family mode
+    pair_ptr: Optional[np.ndarray] = None
+    pair_ids: Optional[np.ndarray] = None
+
+    @property
+    def pairs_mode(self) -> bool:
+        return self.pair_ptr is not None
 
     @property
     def n_lists(self) -> int:
@@ -173,7 +180,12 @@ class Engine:
                         _p(self._keep[2], C.c_int32), _p(self._keep[3], C.c_int32),
                         _p(self._keep[4], C.c_uint8))
         self.ctx = C.c_void_p()
-        self._chk(f("create")(C.byref(d), C.c_int(device), C.byref(self.ctx)))
+        if ds.pairs_mode:
+            self._keep += [np.ascontiguousarray(ds.pair_ptr, dtype=np.int64), np.ascontiguousarray(ds.pair_ids, dtype=np.int32)]
+            self._chk(f("create_pairs")(C.byref(d), _p(self._keep[5], C.c_int64), _p(self._keep[6], C.c_int32),
+                                        C.c_int32(len(self._keep[5]) - 1), C.c_int(device), C.byref(self.ctx)))
+        else:
+            self._chk(f("create")(C.byref(d), C.c_int(device), C.byref(self.ctx)))
 
     def _chk(self, rc: int):
         if rc != 0:

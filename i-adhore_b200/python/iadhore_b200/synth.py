@@ -70,6 +70,13 @@ class SynthConfig:
     tandem_gap: int | None = None
     level_2_only: bool = False
     mult_hyp: str | None = None  # None -> reference default (Bonferroni)
+    # table_type=pairs (GenePairs.cpp): the blast table lists gene pairs instead of families.  The
+    # pair relation is sampled from the families (each intra-family pair kept with pair_keep) plus
+    # pair_cross * N pairs across families, so it is neither transitive nor family-shaped.
+    table_type: str = "family"
+    pair_keep: float = 0.7
+    pair_cross: float = 0.03
+    pair_seed: int = 99
     extra: Dict[str, str] = field(default_factory=dict)
 
 
@@ -125,6 +132,39 @@ def generate(cfg: SynthConfig) -> Dict[str, List[List[Gene]]]:
     return {g.name: make_genome(cfg, g) for g in cfg.genomes}
 
 
+def pair_table(cfg: SynthConfig, data) -> List[Tuple[str, str]]:
+    """Gene pairs of a table_type=pairs configuration, deterministic in cfg.pair_seed.  Every gene gets at
+    least one partner: the reference dereferences the partner's pair set without a null check
+    (Gene.cpp:43-46 under GeneList.cpp:97-139), so a gene absent from the table crashes it."""
+    rng = SplitMix64(cfg.pair_seed)
+    genes = [(gid, f) for g in cfg.genomes for lst in data[g.name] for (gid, _s, f) in lst]
+    by_fam: Dict[int, List[str]] = {}
+    for gid, f in genes:
+        by_fam.setdefault(f, []).append(gid)
+    out: List[Tuple[str, str]] = []
+    has = set()
+    for f in sorted(by_fam):
+        m = by_fam[f]
+        for i in range(len(m)):
+            for j in range(i + 1, len(m)):
+                if m[i] != m[j] and rng.unit() < cfg.pair_keep:
+                    out.append((m[i], m[j]))
+                    has.add(m[i]); has.add(m[j])
+    n = len(genes)
+    for _ in range(int(cfg.pair_cross * n)):
+        a, b = genes[rng.below(n)][0], genes[rng.below(n)][0]
+        if a != b:
+            out.append((a, b))
+            has.add(a); has.add(b)
+    for i, (gid, _f) in enumerate(genes):
+        if gid not in has:
+            other = genes[(i + 1) % n][0]
+            if other != gid:
+                out.append((gid, other))
+                has.add(gid); has.add(other)
+    return out
+
+
 def write_reference_inputs(cfg: SynthConfig, outdir: str, data=None, n_threads: int = 1) -> str:
     """Write lists/, families.tsv and <name>.ini; returns the ini path."""
     if data is None:
@@ -145,13 +185,16 @@ def write_reference_inputs(cfg: SynthConfig, outdir: str, data=None, n_threads: 
             ini.append(f"l{li} {fn}")
         ini.append("")
     fam_fn = os.path.join(outdir, "families.tsv")
+    if cfg.table_type == "pairs":
+        fam_fn = os.path.join(outdir, "pairs.tsv")
+        fam_lines = [f"{a}\t{b}\n" for a, b in pair_table(cfg, data)]
     with open(fam_fn, "w") as fh:
         fh.writelines(fam_lines)
     os.makedirs(os.path.join(outdir, "out"), exist_ok=True)
     ini += [
         f"blast_table= {fam_fn}",
         f"output_path= {os.path.join(outdir, 'out')}/",
-        "table_type= family",
+        f"table_type= {cfg.table_type}",
         f"gap_size= {cfg.gap_size}",
         f"cluster_gap= {cfg.cluster_gap}",
         f"q_value= {cfg.q_value}",
@@ -186,6 +229,14 @@ def config_tiny(seed: int = 11, mult_hyp=None, n_genomes: int = 3) -> SynthConfi
         genomes=[GenomeSpec(f"t{g}", 2, 260 if g % 2 == 0 else 220, g % 2 == 0, seed * 100 + g)
                  for g in range(n_genomes)],
         k_inv=6, mult_hyp=mult_hyp)
+
+
+def config_tiny_pairs(seed: int = 15, mult_hyp=None) -> SynthConfig:
+    """config_tiny with a gene-pair blast table (table_type=pairs)."""
+    cfg = config_tiny(seed=seed, mult_hyp=mult_hyp)
+    cfg.name = f"tinyp{seed}"
+    cfg.table_type = "pairs"
+    return cfg
 
 
 def config_small(seed: int = 21, mult_hyp=None) -> SynthConfig:

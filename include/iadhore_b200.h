@@ -112,6 +112,18 @@ int iadh_remap_tandems(const iadh_dataset_desc* lists, int32_t tandem_gap, int d
 /* Replaces: DataSet ownership of the flattened lists; called once after
  * DataSet::sortGeneLists() (iADHoRe.cpp:75).  `device` = CUDA ordinal. */
 int iadh_create(const iadh_dataset_desc* ds, int device, iadh_ctx** out);
+/* table_type=pairs (Settings.cpp `table_type`, DataSet::getGenePairs DataSet.cpp:144-186): the same
+ * context for a dataset whose homology is a gene-pair relation instead of families.  Replaces the
+ * slow path of GHM::buildMatrix (GHM.cpp:105-147) and the pairs branch of Gene::isPairWith
+ * (Gene.cpp:24-27) inside GHMProfile::buildMatrix / setMultiplicons.  The pair sets are a CSR over
+ * the dense gene ids of ds->gid: partners of gene g = pair_ids[pair_ptr[g] .. pair_ptr[g+1]), ascending,
+ * symmetric, no self pairs -- i.e. Gene::pairs after getGenePairs.  ds->fam and the `fam` array of
+ * iadh_profile_desc are ignored (may be NULL).  Every other entry point behaves as in family mode;
+ * one difference inherited from the reference: the level-2 build honours masks in pairs mode
+ * (ListElement::matchingPositions, ListElement.cpp:20-30), so iadh_level2_* refuses to run while
+ * elements are masked (the reference never does that either: level 2 precedes all masking). */
+int iadh_create_pairs(const iadh_dataset_desc* ds, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                      int device, iadh_ctx** out);
 void iadh_destroy(iadh_ctx* ctx);
 
 /* Replaces: the Settings getters read inside GHM::runCollinear (GHM.cpp:157-219). */

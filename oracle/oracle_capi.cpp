@@ -20,6 +20,9 @@ struct oracle_ctx {
     std::vector<int> index_to_list;
     Params prm;
     int n_threads = 1;
+    PairTable pairs;       // table_type=pairs (oracle_create_pairs)
+    bool pairs_mode = false;
+    const PairTable* pt() const { return pairs_mode ? &pairs : nullptr; }
 };
 
 struct oracle_result {
@@ -109,6 +112,25 @@ int oracle_create(const iadh_dataset_desc* ds, int /*device*/, oracle_ctx** out)
     return IADH_OK;
 }
 
+// table_type=pairs counterpart of oracle_create: the family ids of the descriptor are ignored
+int oracle_create_pairs(const iadh_dataset_desc* ds, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                        int device, oracle_ctx** out)
+{
+    if (!pair_ptr || n_genes < 0 || (pair_ptr[n_genes] > 0 && !pair_ids)) { g_err = "bad pair table"; return IADH_ERR_ARG; }
+    iadh_dataset_desc d = *ds;
+    std::vector<int32_t> zero;
+    if (!d.fam) {
+        zero.assign((size_t)(d.n_lists ? d.list_off[d.n_lists] : 0), 0);
+        d.fam = zero.data();
+    }
+    int rc = oracle_create(&d, device, out);
+    if (rc) return rc;
+    (*out)->pairs.ptr.assign(pair_ptr, pair_ptr + n_genes + 1);
+    (*out)->pairs.ids.assign(pair_ids, pair_ids + pair_ptr[n_genes]);
+    (*out)->pairs_mode = true;
+    return IADH_OK;
+}
+
 void oracle_destroy(oracle_ctx* c) { delete c; }
 
 int oracle_set_threads(oracle_ctx* c, int n) { c->n_threads = n < 1 ? 1 : n; return IADH_OK; }
@@ -144,7 +166,7 @@ static void run_pair(const oracle_ctx* c, int lx, int ly, GhmOut& o)
 {
     GHMInput g;
     double t0 = now_s();
-    build_l2(c->lists[lx], c->lists[ly], lx == ly, g);
+    build_l2(c->lists[lx], c->lists[ly], lx == ly, g, c->pt());
     double t1 = now_s();
     o.dots = g.cnt[0] + g.cnt[1];
     std::vector<Cluster> cl;
@@ -164,13 +186,13 @@ static void run_profile(const oracle_ctx* c, const Profile& P, int ly, GhmOut& o
 {
     GHMInput g;
     double t0 = now_s();
-    build_hl(P, c->lists[ly], g);
+    build_hl(P, c->lists[ly], g, c->pt());
     double t1 = now_s();
     o.dots = g.cnt[0] + g.cnt[1];
     std::vector<Cluster> cl;
     std::vector<Multiplicon> ms;
     run_collinear(g, c->prm, cl, ms);
-    set_multiplicons_hl(P, c->lists[ly], cl, ms);
+    set_multiplicons_hl(P, c->lists[ly], cl, ms, c->pt());
     o.build_s = t1 - t0;
     o.run_s = now_s() - t1;
     pack(cl, ms, o.bytes, o.n_mult);
@@ -351,8 +373,8 @@ int oracle_build_dots(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* 
     g_scratch.dots.clear();
     for (int64_t i = 0; i < n; i++) {
         GHMInput g;
-        if (p) build_hl(P, c->lists[ys[i]], g);
-        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g);
+        if (p) build_hl(P, c->lists[ys[i]], g, c->pt());
+        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g, c->pt());
         for (int o = 0; o < 2; o++) {
             g_scratch.cnt.push_back((int64_t)g.dots[o].size());
             for (const std::pair<int, int>& d : g.dots[o]) {
@@ -378,8 +400,8 @@ int oracle_build_only(oracle_ctx* c, const iadh_profile_desc* p, const int32_t* 
     const auto t0 = std::chrono::steady_clock::now();
     for (int64_t i = 0; i < n; i++) {
         GHMInput g;
-        if (p) build_hl(P, c->lists[ys[i]], g);
-        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g);
+        if (p) build_hl(P, c->lists[ys[i]], g, c->pt());
+        else build_l2(c->lists[xs[i]], c->lists[ys[i]], xs[i] == ys[i], g, c->pt());
         out->n_dots += (int64_t)(g.dots[0].size() + g.dots[1].size());
     }
     out->n_ghm = n;

@@ -56,13 +56,32 @@ double omxn(double x, int n)
     return result;
 }
 
+bool PairTable::is_pair(int a, int b) const
+{
+    if (a < 0 || a + 1 >= (int)ptr.size()) return false;
+    return std::binary_search(ids.begin() + ptr[a], ids.begin() + ptr[a + 1], (int32_t)b);
+}
+
 // ---------------------------------------------------------------------------
 // GHM.cpp:34-85: family-hash join, family mode.  Masks are ignored (T11).
-void build_l2(const List& X, const List& Y, bool identical, GHMInput& g)
+// table_type=pairs (GHM.cpp:105-147): every x against every y that is neither a gap nor masked
+// (ListElement::matchingPositions, ListElement.cpp:20-30) and whose ID is in x's pair set.
+void build_l2(const List& X, const List& Y, bool identical, GHMInput& g, const PairTable* pt)
 {
     g.dots[0].clear();
     g.dots[1].clear();
     g.cnt[0] = g.cnt[1] = 0;
+    if (pt) {
+        for (int x = 0; x < X.size(); x++)
+            for (int y = 0; y < Y.size(); y++) {
+                if (Y.masked[y]) continue;
+                if (!pt->is_pair(X.gid[x], Y.gid[y])) continue;
+                if (identical && y > x) continue;  // GHM.cpp:125
+                int o = (X.strand[x] == Y.strand[y]) ? 1 : 0;
+                g.dots[o].insert(std::make_pair(x, y));
+                g.cnt[o]++;
+            }
+    } else {
     std::map<int, std::vector<int>> tree;  // family -> y positions, ascending
     for (int y = 0; y < Y.size(); y++) tree[Y.fam[y]].push_back(y);
     for (int x = 0; x < X.size(); x++) {
@@ -76,6 +95,7 @@ void build_l2(const List& X, const List& Y, bool identical, GHMInput& g)
             g.cnt[o]++;
         }
     }
+    }
     // GHM.cpp:221-236, 32-bit unsigned arithmetic (T8); level 2 => no masked rows
     unsigned int nx = (unsigned)X.size(), ny = (unsigned)Y.size();
     g.area = identical ? (unsigned int)(nx * (nx - 1) / 2) : (unsigned int)(nx * ny);
@@ -87,7 +107,7 @@ void build_l2(const List& X, const List& Y, bool identical, GHMInput& g)
 // GHMProfile.cpp:17-59: every segment, every non-gap position against every
 // non-gap, non-masked y element (ListElement.cpp:20-30), same family and a
 // different gene ID (Gene.cpp:17-30); counted on first insert only.
-void build_hl(const Profile& P, const List& Y, GHMInput& g)
+void build_hl(const Profile& P, const List& Y, GHMInput& g, const PairTable* pt)
 {
     g.dots[0].clear();
     g.dots[1].clear();
@@ -98,7 +118,7 @@ void build_hl(const Profile& P, const List& Y, GHMInput& g)
             if (P.flags[k] & 2) continue;
             for (int y = 0; y < Y.size(); y++) {
                 if (Y.masked[y]) continue;
-                if (P.fam[k] != Y.fam[y] || P.gid[k] == Y.gid[y]) continue;
+                if (pt ? !pt->is_pair(P.gid[k], Y.gid[y]) : (P.fam[k] != Y.fam[y] || P.gid[k] == Y.gid[y])) continue;
                 int o = ((P.flags[k] & 1) == Y.strand[y]) ? 1 : 0;
                 if (g.dots[o].insert(std::make_pair(x, y)).second) g.cnt[o]++;
             }
@@ -664,7 +684,7 @@ void set_multiplicons_l2(const List& X, const List& Y, std::vector<Cluster>& clu
 
 // GHMProfile.cpp:68-136 (without the createHomologs filter, which needs host state)
 void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& clusters,
-                         std::vector<Multiplicon>& mults)
+                         std::vector<Multiplicon>& mults, const PairTable* pt)
 {
     for (Multiplicon& m : mults) {
         set_bounds(clusters, m);
@@ -685,7 +705,7 @@ void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& 
                 for (int n = 0; n < P.S; n++) {
                     int k = n * P.L + e.x;
                     if (P.flags[k] & 2) continue;
-                    if (!(P.fam[k] == Y.fam[e.y] && P.gid[k] != Y.gid[e.y])) continue;
+                    if (!(pt ? pt->is_pair(P.gid[k], Y.gid[e.y]) : (P.fam[k] == Y.fam[e.y] && P.gid[k] != Y.gid[e.y]))) continue;
                     if (first_match) {
                         AP f;
                         f.gx = P.num_id[k]; f.gy = Y.num_id[e.y]; f.x = e.x; f.y = e.y; f.real = false;

@@ -39,6 +39,15 @@ struct Profile {  // S aligned segments of equal length L (gaps: flags bit1)
     std::vector<uint8_t> flags;             // bit0 strand, bit1 gap
 };
 
+// table_type=pairs: gene id -> ascending partner gene ids, i.e. GenePairs (GenePairs.cpp:3-48) after
+// DataSet::getGenePairs dropped the partners that are in no gene list (DataSet.cpp:144-186)
+struct PairTable {
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> ids;
+    // Gene::isPairWith, pairs branch (Gene.cpp:24-27): b's ID is in a's set
+    bool is_pair(int a, int b) const;
+};
+
 struct AP {
     int gx = -1, gy = -1, x = 0, y = 0;
     bool real = true;
@@ -72,10 +81,10 @@ struct GHMInput {
     int x_object_id = -1, y_object_id = -1;
 };
 
-// GHM.cpp:34-85 (family mode)
-void build_l2(const List& X, const List& Y, bool identical, GHMInput& g);
+// GHM.cpp:34-85 (family mode); with a pair table GHM.cpp:105-147 (table_type=pairs)
+void build_l2(const List& X, const List& Y, bool identical, GHMInput& g, const PairTable* pt = nullptr);
 // GHMProfile.cpp:17-59 + ListElement.cpp:20-30 + Gene.cpp:17-30
-void build_hl(const Profile& P, const List& Y, GHMInput& g);
+void build_hl(const Profile& P, const List& Y, GHMInput& g, const PairTable* pt = nullptr);
 // GHM.cpp:157-219 minus setMultiplicons; output = packed clusters / multiplicons
 void run_collinear(GHMInput& g, const Params& prm, std::vector<Cluster>& clusters,
                    std::vector<Multiplicon>& mults);
@@ -84,7 +93,7 @@ void set_multiplicons_l2(const List& X, const List& Y, std::vector<Cluster>& clu
                          std::vector<Multiplicon>& mults);
 // GHMProfile.cpp:68-136 up to (not including) createHomologs
 void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& clusters,
-                         std::vector<Multiplicon>& mults);
+                         std::vector<Multiplicon>& mults, const PairTable* pt = nullptr);
 // Multiplicon.cpp:210-240 / BaseCluster.cpp:751-797 / AnchorPoint.h:103-118, appended to `out`
 void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& mults,
           std::vector<uint8_t>& out, int& n_mult_total);

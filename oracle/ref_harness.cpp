@@ -180,7 +180,8 @@ int main(int argc, char** argv)
         if (!out) { perror("trace"); return 1; }
     }
     Blob hdr;
-    hdr.append("IADHTRC1", 8);
+    // "IADHTRC2" = table_type=pairs: the header carries the gene-pair sets after the dataset
+    hdr.append(settings.useFamily() ? "IADHTRC1" : "IADHTRC2", 8);
 
     // ---- params -----------------------------------------------------------------
     int gaps[10];
@@ -228,6 +229,27 @@ int main(int argc, char** argv)
     }
     w32(hdr, (int)ds.indexToList.size());
     for (size_t i = 0; i < ds.indexToList.size(); i++) w32(hdr, ds.indexToList[i]);
+    if (!settings.useFamily()) {
+        // pair sets as DataSet::getGenePairs left them (DataSet.cpp:144-186), by interned gene id
+        vector<vector<int> > ps(geneIds.size());
+        for (size_t l = 0; l < gl.size(); l++) {
+            const vector<ListElement*>& all = gl[l]->getElements();
+            for (size_t i = 0; i < all.size(); i++) {
+                const Gene& g = all[i]->getGene();
+                if (!g.pairs) continue;
+                vector<int>& v = ps[intern(geneIds, g.getID())];
+                if (!v.empty()) continue;  // (a repeated gene ID shares one set)
+                for (hash_set<string, stringhash>::const_iterator it = g.pairs->begin(); it != g.pairs->end(); it++)
+                    v.push_back(intern(geneIds, *it));
+                sort(v.begin(), v.end());
+            }
+        }
+        w32(hdr, (int)ps.size());
+        for (size_t g = 0; g < ps.size(); g++) {
+            w32(hdr, (int)ps[g].size());
+            for (size_t k = 0; k < ps[g].size(); k++) w32(hdr, ps[g][k]);
+        }
+    }
     if (dump) fwrite(hdr.data(), 1, hdr.size(), out);
 
     // ---- level 2: every list pair in the 1-thread order of getSomeWorkL2 ----------

@@ -25,6 +25,9 @@ CASES = {
     "tiny_fdr": (synth.config_tiny(seed=12, mult_hyp="FDR"), []),
     "tiny_none": (synth.config_tiny(seed=13, mult_hyp="none"), ["--max-profiles", "12"]),
     "tiny_4g": (synth.config_tiny(seed=14, n_genomes=4), ["--max-profiles", "25"]),
+    # table_type=pairs (trace magic IADHTRC2: carries the pair sets)
+    "tiny_pairs": (synth.config_tiny_pairs(seed=15), []),
+    "tiny_pairs_fdr": (synth.config_tiny_pairs(seed=16, mult_hyp="FDR"), ["--max-profiles", "15"]),
 }
 
 

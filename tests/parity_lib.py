@@ -81,8 +81,12 @@ def replay_trace(eng: capi.Engine, tr: Trace, rtol_p: float, check_dots: bool = 
     return errs
 
 
-def golden_traces() -> List[str]:
-    return sorted(os.path.join(GOLDEN, f) for f in os.listdir(GOLDEN) if f.endswith(".trace.gz"))
+def golden_traces(kind: Optional[str] = None) -> List[str]:
+    """kind: None = all, "family" / "pairs" = the traces of that table_type (pairs traces are named *pairs*)."""
+    out = sorted(os.path.join(GOLDEN, f) for f in os.listdir(GOLDEN) if f.endswith(".trace.gz"))
+    if kind is not None:
+        out = [p for p in out if ("pairs" in os.path.basename(p)) == (kind == "pairs")]
+    return out
 
 
 def oracle_engine(ds: capi.Dataset) -> capi.Engine:

@@ -317,7 +317,7 @@ def test_device_tandem_remap_matches_reference_and_oracle():
     """iadh_remap_tandems (GeneList.cpp:143-200 on the device) against the reference's own flags in
     the golden traces, and against the oracle on tandem-rich lists (config 5 shape, tandem_gap 10)
     plus ragged / empty / single-gene lists and repeated gene IDs."""
-    for path in pl.golden_traces():
+    for path in pl.golden_traces("family"):
         tr = read_trace(path)
         off = np.concatenate([[0], np.cumsum([len(r) for r in tr.raw_lists])]).astype(np.int64)
         cat = lambda k: np.concatenate([r[k] for r in tr.raw_lists])
@@ -396,3 +396,52 @@ def test_ingest_with_device_tandem_remap_equals_the_host_mirror():
         b = ingest.dataset_from_synth(cfg, device=0)
         for k in ("list_off", "fam", "gid", "num_id", "flags"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), (cfg.name, k)
+
+
+def test_pairs_mode_matches_oracle_and_refuses_masked_level2():
+    """table_type=pairs (iadh_create_pairs) beyond the golden traces: a larger set with the (gene, list)
+    table and with the binary-search fallback, all three filter modes, profile searches with masks; and
+    the one documented difference: a level-2 call with masked elements is refused."""
+    cfg = synth.config_small(seed=23)
+    cfg.table_type = "pairs"
+    ds = ingest.dataset_from_synth(cfg)
+    assert ds.pairs_mode
+    cpu = pl.oracle_engine(ds)
+    for no_table in (False, True):
+        if no_table:
+            os.environ["IADH_NO_FAM_TABLE"] = "1"
+        try:
+            gpu = capi.load_product(ds)
+        finally:
+            os.environ.pop("IADH_NO_FAM_TABLE", None)
+        for mode in (capi.MH_BONFERRONI, capi.MH_FDR, capi.MH_NONE):
+            for e in (gpu, cpu):
+                e.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, mode, cfg.q_value, cfg.prob_cutoff)
+                e.clear_masks()
+            xs, ys = [0, 1, 2, 3, 5, 7, 4], [0, 0, 1, 3, 2, 7, 9]
+            a, b = gpu.level2_pairs(xs, ys), cpu.level2_pairs(xs, ys)
+            assert a.n_multiplicons > 0 and not capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL)
+            da, db = gpu.build_dots(xs, ys), cpu.build_dots(xs, ys)
+            assert all(np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1]) for u, v in zip(da, db))
+            if no_table and mode != capi.MH_BONFERRONI:
+                continue
+            found = 0
+            ms = capi.parse_packed(b.bytes)
+            order = sorted(range(len(ms)), key=lambda i: -sum(len(c.aps) for c in ms[i].clusters))[:8]
+            for i in order:
+                m = ms[i]
+                prof = pl.simple_profile(ds, m.x_object_id, m.y_object_id, m)
+                for e in (gpu, cpu):
+                    e.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
+                    e.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
+                ra, rb = gpu.profile_search(prof), cpu.profile_search(prof)
+                assert not capi.compare_packed(ra.bytes, rb.bytes, pl.P_RTOL), i
+                da = gpu.build_dots([0] * ds.n_lists, list(range(ds.n_lists)), profile=prof)
+                db = cpu.build_dots([0] * ds.n_lists, list(range(ds.n_lists)), profile=prof)
+                assert all(np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1]) for u, v in zip(da, db))
+                found += ra.n_multiplicons
+            assert found > 0
+        gpu.mask_range(1, 0, 5)
+        with pytest.raises(RuntimeError, match="masked"):
+            gpu.level2_pairs([0], [1])
+        gpu.close()

@@ -12,9 +12,17 @@ from trace_io import read_trace
 def test_tandem_remap_matches_reference(path):
     tr = read_trace(path)
     n_remapped = 0
+    ds = tr.dataset
+    ps = None
+    if ds.pairs_mode:   # GeneList::remapTandemsPairs with indirect pairs (GeneList.cpp:83-141, Gene.cpp:33-49)
+        ps = {g: set(ds.pair_ids[ds.pair_ptr[g]:ds.pair_ptr[g + 1]].tolist()) for g in range(len(ds.pair_ptr) - 1)
+              if ds.pair_ptr[g + 1] > ds.pair_ptr[g]}
     for raw in tr.raw_lists:
-        r = ingest.remap_tandems_family(raw["fam"].tolist(), raw["gid"].tolist(), [bool(s) for s in raw["strand"]],
-                                        tr.params["tandem_gap"])
+        strand = [bool(s) for s in raw["strand"]]
+        if ps is not None:
+            r = ingest.remap_tandems_pairs(raw["gid"].tolist(), strand, tr.params["tandem_gap"], ps)
+        else:
+            r = ingest.remap_tandems_family(raw["fam"].tolist(), raw["gid"].tolist(), strand, tr.params["tandem_gap"])
         assert np.array_equal(r, raw["remapped"].astype(bool))
         n_remapped += int(r.sum())
     assert n_remapped > 0
@@ -47,7 +55,20 @@ def _raw(tr):
     return off, cat("fam"), cat("gid"), cat("strand"), cat("remapped").astype(bool)
 
 
-@pytest.mark.parametrize("path", pl.golden_traces(), ids=lambda p: p.split("/")[-1].split(".")[0])
+def test_pairs_ingest_matches_reference():
+    """table_type=pairs: pair sets (GenePairs + DataSet::getGenePairs), tandem remapping and numbering of
+    the ingest mirror against what the reference built for the same files."""
+    tr = read_trace([p for p in pl.golden_traces("pairs") if p.endswith("tiny_pairs.trace.gz")][0])
+    ds = ingest.dataset_from_synth(synth.config_tiny_pairs(seed=15))
+    for k in ("list_off", "gid", "num_id", "flags", "pair_ptr", "pair_ids"):
+        assert np.array_equal(getattr(ds, k), getattr(tr.dataset, k)), k
+    # the relation is not family-shaped: some gene has two partners that are not partners of each other
+    ps = {g: set(ds.pair_ids[ds.pair_ptr[g]:ds.pair_ptr[g + 1]].tolist()) for g in range(len(ds.pair_ptr) - 1)}
+    assert any(b not in ps[a] for g in ps for a in ps[g] for b in ps[g] if a != b)
+    assert all(g in ps[p] for g in ps for p in ps[g])   # symmetric
+
+
+@pytest.mark.parametrize("path", pl.golden_traces("family"), ids=lambda p: p.split("/")[-1].split(".")[0])
 def test_oracle_tandem_remap_matches_reference(path):
     """oracle_remap_tandems (the checker of the device kernel) against the reference's own flags."""
     tr = read_trace(path)

@@ -1,13 +1,14 @@
 """Reader for the traces written by oracle/ref_harness.cpp (the unmodified reference
 driven GHM by GHM).  Layout (little endian):
 
-  "IADHTRC1"
+  "IADHTRC1" (table_type=family) | "IADHTRC2" (table_type=pairs)
   params : i32 n_gaps, i32 gaps[10], i32 gap_size, cluster_gap, tandem_gap, anchor_points,
            mult_hyp, level2_only, f64 q_value, prob_cutoff
   dataset: i32 n_lists; per list: i32 id, i32 genome_id,
              i32 n_all,  n_all  x {i32 fam, gid, num_id, u8 strand, u8 remapped}
              i32 n,      n      x {i32 fam, gid, num_id, u8 strand}          (remapped elements)
            i32 n, i32 index_to_list[n]
+           IADHTRC2 only: i32 n_gene_ids; per gene id: i32 k, k x i32 partner gene id (ascending)
   records: i32 tag
      1 L2 GHM   : i32 x_list, y_list; dots; packed
      2 MASK     : i32 list, begin, end
@@ -102,7 +103,8 @@ def read_trace(path: str) -> Trace:
     import gzip
     with (gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")) as fh:
         r = _R(fh.read())
-    assert r.take(8) == b"IADHTRC1"
+    magic = r.take(8)
+    assert magic in (b"IADHTRC1", b"IADHTRC2")
     n_gaps = r.i32()
     gaps = [r.i32() for _ in range(10)][:n_gaps]
     prm = dict(gaps=gaps, gap_size=r.i32(), cluster_gap=r.i32(), tandem_gap=r.i32(),
@@ -121,6 +123,16 @@ def read_trace(path: str) -> Trace:
     ds = Dataset(np.array(off, np.int64), np.concatenate(fam).astype(np.int32), np.concatenate(gid).astype(np.int32),
                  np.concatenate(nid).astype(np.int32), np.concatenate(flg).astype(np.uint8))
     itl = r.rec("<i4", r.i32()).copy()
+    if magic == b"IADHTRC2":   # table_type=pairs: pair sets by gene id (DataSet::getGenePairs)
+        ng = r.i32()
+        ptr = np.zeros(ng + 1, np.int64)
+        ids = []
+        for g in range(ng):
+            k = r.i32()
+            ptr[g + 1] = ptr[g] + k
+            ids.append(r.rec("<i4", k))
+        ds.pair_ptr = ptr
+        ds.pair_ids = np.concatenate(ids).astype(np.int32) if ids else np.zeros(0, np.int32)
     tr = Trace(prm, ds, raw, genome, itl)
     pidx = -1
     while True:
