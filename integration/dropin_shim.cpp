@@ -12,6 +12,7 @@
 // does for multiplicons received from another MPI rank.
 //
 // This file includes the reference's headers; it contains none of the reference's code.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
@@ -23,6 +24,7 @@
 
 #include "DataSet.h"
 #include "GeneList.h"
+#include "GenePairs.h"
 #include "Gene.h"
 #include "ListElement.h"
 #include "Multiplicon.h"
@@ -97,7 +99,7 @@ void check(int rc, const char* what)
 }
 
 // Flatten the DataSet (after mapGenes + remapTandems + sortGeneLists) and create the device context.
-void ensure_context(const std::vector<GeneList*>& genelists, const Settings& settings)
+void ensure_context(const std::vector<GeneList*>& genelists, const Settings& settings, GenePairs* genepairs)
 {
     if (B.ctx) return;
     std::vector<int64_t> off(1, 0);
@@ -136,7 +138,31 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     d.flags = flags.data();
     const char* dev = getenv("IADH_DEVICE");
     g_warmup.join();
-    check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
+    if (settings.useFamily())
+        check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
+    else {
+        // table_type=pairs: the pair sets DataSet::getGenePairs left in `genepairs` (the very sets
+        // Gene::pairs points to, DataSet.cpp:165-183), as a CSR over the interned gene ids
+        const int n_genes = (int)B.gene_ids.size();
+        std::vector<std::vector<int32_t> > ps(n_genes);
+        for (std::map<std::string, int>::const_iterator it = B.gene_ids.begin(); it != B.gene_ids.end(); it++) {
+            hash_set<std::string, stringhash>* set = genepairs ? genepairs->getPairsOf(it->first) : NULL;
+            if (!set) continue;
+            std::vector<int32_t>& v = ps[it->second];
+            for (hash_set<std::string, stringhash>::const_iterator p = set->begin(); p != set->end(); p++) {
+                std::map<std::string, int>::const_iterator q = B.gene_ids.find(*p);
+                if (q != B.gene_ids.end()) v.push_back(q->second);
+            }
+            std::sort(v.begin(), v.end());
+        }
+        std::vector<int64_t> pptr(n_genes + 1, 0);
+        std::vector<int32_t> pids;
+        for (int g = 0; g < n_genes; g++) {
+            pids.insert(pids.end(), ps[g].begin(), ps[g].end());
+            pptr[g + 1] = (int64_t)pids.size();
+        }
+        check(iadh_create_pairs(&d, pptr.data(), pids.data(), n_genes, dev ? atoi(dev) : 0, &B.ctx), "iadh_create_pairs");
+    }
     atexit(report);
 
     iadh_params p;
@@ -207,9 +233,7 @@ void DataSet::parallelLevel2ADHoReDyn()
 {
     if (settings.getClusterType() != Collinear)
         throw std::runtime_error("the B200 path implements collinear detection only (cluster_type=collinear)");
-    if (!settings.useFamily())
-        throw std::runtime_error("the B200 path implements table_type=family only");
-    ensure_context(genelists, settings);
+    ensure_context(genelists, settings, genepairs);
     iadh_result* res = NULL;
     check(iadh_level2_all_pairs(B.ctx, B.rank, B.n_ranks, &res), "iadh_level2_all_pairs");
     size_t nbytes = 0;

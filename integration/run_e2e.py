@@ -3,7 +3,7 @@
 drop-in binary (build/dropin/i-adhore-b200 = the same reference host code + dropin_shim.cpp + the
 CUDA library) run the same .ini; every output table must be byte-identical.  Prints wall times.
 
-    python integration/run_e2e.py [--workload small|c3s0.3|c3] [--threads N] [--keep DIR]
+    python integration/run_e2e.py [--workload small|smallp|c3s0.3|c3] [--threads N] [--keep DIR]
 
 Test/measurement infrastructure: executes oracle/_ref as the checker and CPU baseline.
 """
@@ -33,6 +33,10 @@ def workload(name):
         return synth.config_small(seed=21)
     if name == "tiny":
         return synth.config_tiny(seed=11)
+    if name in ("tinyp", "smallp"):   # table_type=pairs
+        cfg = synth.config_tiny_pairs(seed=15) if name == "tinyp" else synth.config_small(seed=21)
+        cfg.table_type = "pairs"
+        return cfg
     if name == "c3":
         return synth.config_c3(1.0)
     if name.startswith("c3s"):
