@@ -55,6 +55,11 @@ def workload_config(name: str):
         return synth.config_c5(1.0)
     if name == "d2":
         return synth.config_d2(1.0)
+    if name.startswith("c3p"):   # config 3 with a gene-pair blast table (table_type=pairs), e.g. c3p, c3p0.5
+        cfg = synth.config_c3(float(name[3:] or 1.0))
+        cfg.table_type = "pairs"
+        cfg.name += "p"
+        return cfg
     if name.startswith("c3s"):
         return synth.config_c3(float(name[3:]))
     if name.startswith("d2s"):
@@ -68,7 +73,7 @@ def workload_label(name, cfg, n_profiles):
     shape = ("ragged lists with the shipped datasetII list-length distribution" if cfg.genomes[0].list_sizes
              else f"{cfg.genomes[0].n_lists} lists x {cfg.genomes[0].genes_per_list} genes per genome")
     return (f"{name}: synthetic {len(cfg.genomes)} genomes, {n_lists} gene lists, {n_genes} genes ({shape}), "
-            f"{cfg.n_families} families; L2 all {n_lists * (n_lists + 1) // 2} pairs + {n_profiles} profile searches per step")
+            f"{cfg.n_families} families{' sampled into a gene-pair table (table_type=pairs)' if cfg.table_type == 'pairs' else ''}; L2 all {n_lists * (n_lists + 1) // 2} pairs + {n_profiles} profile searches per step")
 
 
 def ncu_traffic(kernel_substr):

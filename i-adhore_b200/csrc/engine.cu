@@ -1177,37 +1177,40 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
         for (int64_t i = 0; i < total; i++) members[cur[key[i]]++] = (int32_t)i;
     } else {
-        // pairs mode: bucket g = positions of the partners of gene g, i.e. every y with
-        // Gene::isPairWith(g, y) (Gene.cpp:24-27).  occ = positions per gene id (ascending); only
-        // genes that occur in a list get a bucket.
-        std::vector<int32_t> occ_ptr((size_t)n_genes + 1, 0), occ((size_t)total);
-        for (int64_t i = 0; i < total; i++) occ_ptr[key[i] + 1]++;
-        for (int g = 0; g < n_genes; g++) occ_ptr[g + 1] += occ_ptr[g];
+        // pairs mode: bucket g = positions of the partners of gene g, i.e. every element e with
+        // gid[e] in pairs(g) (Gene::isPairWith(g, e), Gene.cpp:24-27).  Built through the transposed
+        // relation (rev[p] = genes that list p as a partner; equal to pairs for a symmetric table):
+        // walking the elements in ascending order and appending e to the bucket of every g in
+        // rev[gid[e]] leaves each bucket ascending without a sort.
+        const int64_t n_pairs = pair_ptr[n_genes];
+        std::vector<int64_t> rev_ptr((size_t)n_genes + 1, 0);
+        std::vector<int32_t> rev((size_t)n_pairs);
+        for (int64_t k = 0; k < n_pairs; k++) rev_ptr[pair_ids[k] + 1]++;
+        for (int g = 0; g < n_genes; g++) rev_ptr[g + 1] += rev_ptr[g];
         {
-            std::vector<int32_t> cur(occ_ptr.begin(), occ_ptr.end() - 1);
-            for (int64_t i = 0; i < total; i++) occ[cur[key[i]]++] = (int32_t)i;
+            std::vector<int64_t> cur(rev_ptr.begin(), rev_ptr.end() - 1);
+            for (int g = 0; g < n_genes; g++)
+                for (int64_t k = pair_ptr[g]; k < pair_ptr[g + 1]; k++) rev[cur[pair_ids[k]]++] = g;
         }
-        int64_t m_total = 0;
+        std::vector<int64_t> cnt((size_t)n_genes + 1, 0);
+        for (int64_t i = 0; i < total; i++)
+            for (int64_t k = rev_ptr[key[i]]; k < rev_ptr[key[i] + 1]; k++) cnt[rev[k] + 1]++;
         for (int g = 0; g < n_genes; g++) {
-            int64_t n = 0;
-            if (occ_ptr[g + 1] > occ_ptr[g])
-                for (int64_t k = pair_ptr[g]; k < pair_ptr[g + 1]; k++) n += occ_ptr[pair_ids[k] + 1] - occ_ptr[pair_ids[k]];
-            m_total += n;
-            if (m_total >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 partner positions"); }
-            fam_ptr[g + 1] = (int32_t)m_total;
+            cnt[g + 1] += cnt[g];
+            if (cnt[g + 1] >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 partner positions"); }
+            fam_ptr[g + 1] = (int32_t)cnt[g + 1];
         }
-        members.resize((size_t)m_total);
-        for (int g = 0; g < n_genes; g++) {
-            if (fam_ptr[g + 1] == fam_ptr[g]) continue;
-            int32_t* b = members.data() + fam_ptr[g];
-            int32_t* w = b;
-            for (int64_t k = pair_ptr[g]; k < pair_ptr[g + 1]; k++) {
-                const int p = pair_ids[k];
-                for (int32_t q = occ_ptr[p]; q < occ_ptr[p + 1]; q++) *w++ = occ[q];
+        members.resize((size_t)cnt[n_genes]);
+        {
+            std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
+            for (int64_t i = 0; i < total; i++)
+                for (int64_t k = rev_ptr[key[i]]; k < rev_ptr[key[i] + 1]; k++) members[cur[rev[k]]++] = (int32_t)i;
+        }
+        for (int g = 0; g < n_genes; g++)
+            if (std::adjacent_find(members.begin() + fam_ptr[g], members.begin() + fam_ptr[g + 1]) != members.begin() + fam_ptr[g + 1]) {
+                delete c;
+                return fail(IADH_ERR_ARG, "pair table lists a partner of gene %d twice", g);
             }
-            std::sort(b, w);
-            if (std::adjacent_find(b, w) != w) { delete c; return fail(IADH_ERR_ARG, "pair table lists a partner of gene %d twice", g); }
-        }
     }
     const int64_t n_mem = (int64_t)members.size();
     // level-2 build tables (build_kernels.cu): member records, strand prefix counts, own slot of
