@@ -8,6 +8,11 @@
 #include "oracle_core.h"
 
 #include <algorithm>
+#ifdef ORACLE_STUDY
+#include <atomic>
+#include <set>
+#include <tuple>
+#endif
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -503,11 +508,49 @@ static bool closest_clusters(GHMState& s, int gap, int orientI, int orientJ, int
     return closestDistance < gap + 1;
 }
 
+#ifdef ORACLE_STUDY
+#include "study/join_cache.inc"
+static void study_join_init(GHMState& s, int gap, int orient)
+{
+    using namespace study;
+    if (!cur) return;
+    const std::vector<int>& bc = s.BC[orient];
+    const int maxgap = s.prm.gaps[s.prm.n_gaps - 1];
+    std::vector<Hull> h;
+    for (int id : bc) h.push_back(hull(s.pool[id]));
+    C.calls++;
+    C.clusters += (long long)bc.size();
+    C.h_calls[bucket(bc.size())]++;
+    C.h_pairs[bucket(bc.size())] += (long long)bc.size() * ((long long)bc.size() - 1) / 2;
+    long long mx = C.max_clusters.load();
+    while ((long long)bc.size() > mx && !C.max_clusters.compare_exchange_weak(mx, (long long)bc.size())) {}
+    for (int id : bc)
+        if (cur->seen_clusters.insert(std::make_pair(id, (int)s.pool[id].aps.size())).second) C.changed++;
+    for (size_t i = 0; i < bc.size(); i++)
+        for (size_t j = i + 1; j < bc.size(); j++) {
+            C.pairs++;
+            const int d = apart(h[i], h[j]);
+            if (d <= gap + 1) C.near_gap++;
+            if (d <= maxgap + 1) {
+                C.near_max++;
+                if (cur->seen_pairs.insert(std::make_tuple(bc[i], (int)s.pool[bc[i]].aps.size(), bc[j], (int)s.pool[bc[j]].aps.size())).second)
+                    C.first_max++;
+            }
+        }
+}
+#endif
+
 // GHM.cpp:392-404
 static void join_clusters(GHMState& s, int gap, int orient)
 {
+#ifdef ORACLE_STUDY
+    study_join_init(s, gap, orient);
+#endif
     int i, j;
     while (closest_clusters(s, gap, orient, orient, i, j)) {
+#ifdef ORACLE_STUDY
+        study::C.merges++;
+#endif
         merge_with(s.pool[s.BC[orient][i]], s.pool[s.BC[orient][j]]);
         s.BC[orient].erase(s.BC[orient].begin() + j);
     }
@@ -619,6 +662,12 @@ static void cluster_clusters(GHMState& s)
 void run_collinear(GHMInput& g, const Params& prm, std::vector<Cluster>& clusters,
                    std::vector<Multiplicon>& mults)
 {
+#ifdef ORACLE_STUDY
+    study::PerGhm study_scope;
+    study::cur = &study_scope;
+    study::C.ghms++;
+    struct StudyEnd { ~StudyEnd() { study::cur = nullptr; } } study_end;
+#endif
     clusters.clear();
     mults.clear();
     if ((g.cnt[0] + g.cnt[1]) < (unsigned int)prm.anchor_points) return;
@@ -775,3 +824,14 @@ void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& 
 }
 
 }  // namespace oracle
+
+#ifdef ORACLE_STUDY
+extern "C" void oracle_study_counters(long long* out)
+{
+    using oracle::study::C;
+    out[0] = C.ghms; out[1] = C.calls; out[2] = C.pairs; out[3] = C.near_gap; out[4] = C.near_max;
+    out[5] = C.first_max; out[6] = C.clusters; out[7] = C.changed;
+    out[8] = C.merges; out[9] = C.max_clusters;
+    for (int b = 0; b < 6; b++) { out[10 + b] = C.h_calls[b]; out[16 + b] = C.h_pairs[b]; }
+}
+#endif
