@@ -10,6 +10,7 @@
 #include <algorithm>
 #ifdef ORACLE_STUDY
 #include <atomic>
+#include <mutex>
 #include <set>
 #include <tuple>
 #endif
@@ -387,6 +388,10 @@ struct GHMState {
         : g(g_), prm(p_), pool(pool_), mults(m_) {}
 };
 
+#ifdef ORACLE_STUDY
+#include "study/join_cache.inc"
+#endif
+
 // GHM.cpp:238-285
 static void seed_chain(const DotSet& mat, Cluster& c, int gap)
 {
@@ -454,6 +459,9 @@ static void enrich_clusters(GHMState& s, int gap, int clusterOrientation, int gh
             int x = it->first, y = it->second;
             double closestDistance = gap + 1;
             int closest = -1;
+#ifdef ORACLE_STUDY
+            if (study::cur) study::cur->enrich_tests += (long long)clusters.size();
+#endif
             for (size_t k = 0; k < clusters.size(); k++) {
                 Cluster& c = s.pool[clusters[k]];
                 update_stats(c);
@@ -509,7 +517,6 @@ static bool closest_clusters(GHMState& s, int gap, int orientI, int orientJ, int
 }
 
 #ifdef ORACLE_STUDY
-#include "study/join_cache.inc"
 static void study_join_init(GHMState& s, int gap, int orient)
 {
     using namespace study;
@@ -526,11 +533,13 @@ static void study_join_init(GHMState& s, int gap, int orient)
     while ((long long)bc.size() > mx && !C.max_clusters.compare_exchange_weak(mx, (long long)bc.size())) {}
     for (int id : bc)
         if (cur->seen_clusters.insert(std::make_pair(id, (int)s.pool[id].aps.size())).second) C.changed++;
+    cur->max_clusters = std::max(cur->max_clusters, (long long)bc.size());
     for (size_t i = 0; i < bc.size(); i++)
         for (size_t j = i + 1; j < bc.size(); j++) {
             C.pairs++;
+            cur->pairs++;
             const int d = apart(h[i], h[j]);
-            if (d <= gap + 1) C.near_gap++;
+            if (d <= gap + 1) { C.near_gap++; cur->near++; }
             if (d <= maxgap + 1) {
                 C.near_max++;
                 if (cur->seen_pairs.insert(std::make_tuple(bc[i], (int)s.pool[bc[i]].aps.size(), bc[j], (int)s.pool[bc[j]].aps.size())).second)
@@ -550,6 +559,7 @@ static void join_clusters(GHMState& s, int gap, int orient)
     while (closest_clusters(s, gap, orient, orient, i, j)) {
 #ifdef ORACLE_STUDY
         study::C.merges++;
+        if (study::cur) study::cur->merges++;
 #endif
         merge_with(s.pool[s.BC[orient][i]], s.pool[s.BC[orient][j]]);
         s.BC[orient].erase(s.BC[orient].begin() + j);
@@ -666,6 +676,8 @@ void run_collinear(GHMInput& g, const Params& prm, std::vector<Cluster>& cluster
     study::PerGhm study_scope;
     study::cur = &study_scope;
     study::C.ghms++;
+    study_scope.dots = (long long)(g.dots[0].size() + g.dots[1].size());
+    study_scope.level = g.level;
     struct StudyEnd { ~StudyEnd() { study::cur = nullptr; } } study_end;
 #endif
     clusters.clear();
@@ -826,6 +838,16 @@ void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& 
 }  // namespace oracle
 
 #ifdef ORACLE_STUDY
+// per-GHM records since the last call (7 values each); returns the count, copies at most `cap` records
+extern "C" long long oracle_study_records(long long* out, long long cap)
+{
+    std::lock_guard<std::mutex> lk(oracle::study::rec_mu);
+    long long n = (long long)oracle::study::recs.size();
+    for (long long i = 0; i < n && i < cap; i++)
+        for (int k = 0; k < 7; k++) out[7 * i + k] = oracle::study::recs[i].v[k];
+    oracle::study::recs.clear();
+    return n;
+}
 extern "C" void oracle_study_counters(long long* out)
 {
     using oracle::study::C;
