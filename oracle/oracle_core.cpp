@@ -556,6 +556,53 @@ static void join_clusters(GHMState& s, int gap, int orient)
     study_join_init(s, gap, orient);
 #endif
     int i, j;
+#ifdef ORACLE_STUDY
+    // Speculative batches: at a batch start list every valid pair, take up to K disjoint ones in the
+    // reference's order, then follow the reference's own sequence and count how long it agrees with the
+    // speculation (= the merges a device could have carried out concurrently and validated afterwards).
+    // The merges performed are always the reference's.
+    if (study::spec_k > 0) {
+        while (true) {
+            std::vector<int>& bc = s.BC[orient];
+            std::vector<std::tuple<double, int, int>> cand;
+            for (size_t a = 0; a < bc.size(); a++)
+                for (size_t b = a + 1; b < bc.size(); b++) {
+                    Cluster& cI = s.pool[bc[a]];
+                    Cluster& cJ = s.pool[bc[b]];
+                    const double d = dist_to_cluster(cI, cJ);
+                    if (d < gap + 1 && partial_overlap(cI, cJ) && r2_from(cI, &cJ, 0, 0) >= s.prm.q_value)
+                        cand.push_back(std::make_tuple(d, (int)a, (int)b));
+                }
+            if (cand.empty()) break;
+            std::sort(cand.begin(), cand.end());
+            std::vector<std::pair<int, int>> spec;
+            std::set<int> used;
+            for (const auto& c : cand) {
+                const int ia = bc[std::get<1>(c)], ib = bc[std::get<2>(c)];
+                if (used.count(ia) || used.count(ib)) continue;
+                used.insert(ia); used.insert(ib);
+                spec.push_back(std::make_pair(ia, ib));
+                if ((int)spec.size() >= study::spec_k) break;
+            }
+            int accepted = 0;
+            for (size_t t = 0; t < spec.size(); t++) {
+                if (!closest_clusters(s, gap, orient, orient, i, j)) break;
+                const bool same = (s.BC[orient][i] == spec[t].first && s.BC[orient][j] == spec[t].second);
+                study::C.merges++;
+                if (study::cur) study::cur->merges++;
+                merge_with(s.pool[s.BC[orient][i]], s.pool[s.BC[orient][j]]);
+                s.BC[orient].erase(s.BC[orient].begin() + j);
+                if (!same) break;
+                accepted++;
+            }
+            study::C.spec_batches++;
+            study::C.spec_offered += (long long)spec.size();
+            study::C.spec_accepted += accepted;
+            if (study::cur) study::cur->batches++;
+        }
+        return;
+    }
+#endif
     while (closest_clusters(s, gap, orient, orient, i, j)) {
 #ifdef ORACLE_STUDY
         study::C.merges++;
@@ -838,22 +885,24 @@ void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& 
 }  // namespace oracle
 
 #ifdef ORACLE_STUDY
-// per-GHM records since the last call (7 values each); returns the count, copies at most `cap` records
+// per-GHM records since the last call (8 values each); returns the count, copies at most `cap` records
 extern "C" long long oracle_study_records(long long* out, long long cap)
 {
     std::lock_guard<std::mutex> lk(oracle::study::rec_mu);
     long long n = (long long)oracle::study::recs.size();
     for (long long i = 0; i < n && i < cap; i++)
-        for (int k = 0; k < 7; k++) out[7 * i + k] = oracle::study::recs[i].v[k];
+        for (int k = 0; k < 8; k++) out[8 * i + k] = oracle::study::recs[i].v[k];
     oracle::study::recs.clear();
     return n;
 }
+extern "C" void oracle_study_set_spec(int k) { oracle::study::spec_k = k; }
 extern "C" void oracle_study_counters(long long* out)
 {
     using oracle::study::C;
     out[0] = C.ghms; out[1] = C.calls; out[2] = C.pairs; out[3] = C.near_gap; out[4] = C.near_max;
     out[5] = C.first_max; out[6] = C.clusters; out[7] = C.changed;
     out[8] = C.merges; out[9] = C.max_clusters;
+    out[22] = C.spec_batches; out[23] = C.spec_offered; out[24] = C.spec_accepted;
     for (int b = 0; b < 6; b++) { out[10 + b] = C.h_calls[b]; out[16 + b] = C.h_pairs[b]; }
 }
 #endif

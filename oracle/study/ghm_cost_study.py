@@ -20,20 +20,22 @@ from iadhore_b200 import capi, ingest, synth  # noqa: E402
 from iadhore_b200.profiles import simple_profile  # noqa: E402
 
 LIB = os.path.join(HERE, "liboracle_study.so")
-COLS = ["dots", "pairs_scanned", "near_pairs", "merges", "enrich_tests", "max_clusters", "level"]
+COLS = ["dots", "pairs_scanned", "near_pairs", "merges", "enrich_tests", "max_clusters", "level", "batches"]
 
 
 def records(eng):
     cap = 1 << 20
-    buf = (C.c_longlong * (7 * cap))()
+    buf = (C.c_longlong * (8 * cap))()
     eng.lib.oracle_study_records.restype = C.c_longlong
     n = eng.lib.oracle_study_records(buf, C.c_longlong(cap))
-    return np.ctypeslib.as_array(buf)[:7 * min(n, cap)].reshape(-1, 7).copy()
+    return np.ctypeslib.as_array(buf)[:8 * min(n, cap)].reshape(-1, 8).copy()
 
 
 def summary(r):
     out = {"ghms": int(len(r))}
-    for i, c in enumerate(COLS[:-1]):
+    for i, c in enumerate(COLS):
+        if c == 'level':
+            continue
         v = r[:, i]
         out[c] = dict(sum=int(v.sum()), mean=float(v.mean()), p50=float(np.percentile(v, 50)), p99=float(np.percentile(v, 99)),
                       max=int(v.max()))
@@ -45,11 +47,13 @@ def main():
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--pairs", type=int, default=300)
     ap.add_argument("--profiles", type=int, default=16)
+    ap.add_argument("--spec", type=int, default=0, help="speculative merge batches of up to K disjoint pairs (0 = off)")
     a = ap.parse_args()
     cfg = synth.config_c4(1.0) if a.workload == "c4" else synth.config_c3(1.0)
     cfg.genomes = cfg.genomes[:6]
     ds = ingest.dataset_from_synth(cfg)
     eng = capi.Engine(LIB, "oracle_", ds)
+    eng.lib.oracle_study_set_spec(C.c_int(a.spec))
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
     n = ds.n_lists
     allp = [(x, y) for x in range(n) for y in range(x + 1)]
