@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <set>
 #include <ctime>
 #include <map>
 #include <stdexcept>
@@ -46,7 +48,8 @@ struct Bridge {
     long n_hl = 0;
     // wall-clock split of the profile searches (IADH_VERBOSE=1 prints it at exit)
     double w_mask = 0, w_desc = 0, w_call = 0, w_unpack = 0;
-    long long n_ghm = 0, n_found = 0, n_returned = 0;
+    long long n_ghm = 0, n_found = 0, n_returned = 0, n_prefiltered = 0;
+    std::vector<std::vector<int32_t> > list_fam;       // family id per remapped element, per list
 };
 Bridge B;
 
@@ -61,9 +64,9 @@ void report()
 {
     if (!getenv("IADH_VERBOSE")) return;
     fprintf(stderr,
-            "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons returned, %lld kept; wall: masks %.3fs, descriptor %.3fs, "
-            "device call %.3fs (device time %.3fs), unpack+filter %.3fs\n",
-            B.n_hl, B.n_ghm, B.n_returned, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
+            "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons returned, %lld dropped before unpacking, %lld kept; "
+            "wall: masks %.3fs, descriptor %.3fs, device call %.3fs (device time %.3fs), unpack+filter %.3fs\n",
+            B.n_hl, B.n_ghm, B.n_returned, B.n_prefiltered, B.n_found, B.w_mask, B.w_desc, B.w_call, B.t_hl * 1e-3, B.w_unpack);
 }
 
 // The CUDA context is created on a helper thread while the reference's main() reads the gene lists
@@ -125,6 +128,8 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
             num.push_back(re[i]->getNumID());
             flags.push_back((re[i]->getOrientation() ? IADH_F_STRAND : 0) | (re[i]->isMasked() ? IADH_F_MASKED : 0));
         }
+        B.list_fam.resize(genelists.size());
+        B.list_fam[l].assign(fam.end() - re.size(), fam.end());
         B.masked[l].assign(re.size(), 0);
         for (size_t i = 0; i < re.size(); i++) B.masked[l][i] = re[i]->isMasked() ? 1 : 0;
         off.push_back((int64_t)fam.size());
@@ -226,6 +231,89 @@ bool enough_homologs(const Multiplicon& m, int minHomologs)
     return false;
 }
 
+// Cheap, conservative form of the homolog filter, applied to the packed stream BEFORE the unpack
+// constructors run (they copy S+1 segments and build Link sets per multiplicon, and 40 % of what a search
+// returns is then thrown away).  createHomologs (Multiplicon.cpp:352-382) marks an element of x-segment s
+// inside [begin_x, end_x] as "has homolog" only if (a) a Link inherited from the parent multiplicon
+// survives pruneLinks -- then the element is an end of an inherited Link of segment s -- or (b) addLinks
+// finds a same-family element in [begin_y, end_y] of the y-list.  Counting the elements that satisfy the
+// weaker "end of ANY inherited Link of segment s, or family present in the y-range" over-estimates the
+// count, so a segment that stays below minHomologs is certain to fail the exact test.  When the parent
+// has no Links, pruneLinks leaves the copied flags alone (Multiplicon.cpp:386-388): nothing is dropped.
+// Family mode only.  Returns the filtered stream (same layout) in `out`.
+struct ProfileLinks {
+    bool any = false;
+    std::vector<unsigned char> linked;  // S*L: element is an end of an inherited Link of its segment
+};
+
+void profile_links(const Profile* profile, int S, int L, const std::vector<int32_t>& num, ProfileLinks& pl)
+{
+    const std::set<Link>& hs = profile->getMultiplicon().getHomologs();
+    pl.any = !hs.empty();
+    pl.linked.assign((size_t)S * L, 0);
+    if (!pl.any) return;
+    std::vector<std::map<int, int> > col(S);   // numID -> column, per segment
+    for (int s = 0; s < S; s++)
+        for (int x = 0; x < L; x++)
+            if (num[(size_t)s * L + x] >= 0) col[s][num[(size_t)s * L + x]] = x;
+    for (std::set<Link>::const_iterator e = hs.begin(); e != hs.end(); e++) {
+        for (int end = 0; end < 2; end++) {
+            const int seg = end ? e->segmentY : e->segmentX;
+            const int id = end ? e->geneYID : e->geneXID;
+            if (seg < 0 || seg >= S) continue;
+            std::map<int, int>::const_iterator it = col[seg].find(id);
+            if (it != col[seg].end()) pl.linked[(size_t)seg * L + it->second] = 1;
+        }
+    }
+}
+
+long long prefilter_packed(const uint8_t* bytes, size_t nbytes, int S, int L, const std::vector<int32_t>& fam,
+                           const std::vector<uint8_t>& flags, const ProfileLinks& pl, int minHomologs,
+                           std::vector<char>& out)
+{
+    int32_t n = 0;
+    memcpy(&n, bytes, 4);
+    out.assign(4, 0);
+    int32_t kept = 0;
+    size_t o = 4;
+    std::vector<int32_t> yfam;
+    for (int32_t m = 0; m < n; m++) {
+        const size_t begin = o;
+        int32_t hdr[3], b[4], ncl;
+        memcpy(hdr, bytes + o, 12);          // x object, y object, level
+        memcpy(b, bytes + o + 13, 16);       // begin_x, end_x, begin_y, end_y (after the 1-byte redundant flag)
+        memcpy(&ncl, bytes + o + 29, 4);
+        o += 33;
+        for (int32_t c = 0; c < ncl; c++) {
+            int32_t nap;
+            memcpy(&nap, bytes + o + 98, 4);
+            o += 102 + (size_t)17 * nap;
+        }
+        bool drop = false;
+        const int yl = hdr[1];
+        if (pl.any && yl >= 0 && yl < (int)B.list_fam.size() && b[0] >= 0 && b[1] < L && b[2] >= 0 &&
+            b[3] < (int)B.list_fam[yl].size()) {
+            yfam.assign(B.list_fam[yl].begin() + b[2], B.list_fam[yl].begin() + b[3] + 1);
+            std::sort(yfam.begin(), yfam.end());
+            for (int s = 0; s < S && !drop; s++) {
+                int count = 0;
+                for (int x = b[0]; x <= b[1] && count < minHomologs; x++) {
+                    const size_t k = (size_t)s * L + x;
+                    if (flags[k] & IADH_F_GAP) continue;
+                    if (pl.linked[k] || std::binary_search(yfam.begin(), yfam.end(), fam[k])) count++;
+                }
+                if (count < minHomologs) drop = true;
+            }
+        }
+        if (drop) continue;
+        out.insert(out.end(), (const char*)bytes + begin, (const char*)bytes + o);
+        kept++;
+    }
+    memcpy(out.data(), &kept, 4);
+    (void)nbytes;
+    return n - kept;
+}
+
 }  // namespace
 
 // ---- replaces levelTwo.cpp:177-292 --------------------------------------------------------------
@@ -296,7 +384,15 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     size_t nbytes = 0;
     const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
     std::vector<Multiplicon*> mplicons;
-    Multiplicon::unpackHLMultiplicons((const char*)bytes, mplicons, *profile, genelists, settings.useFamily());
+    static const bool use_prefilter = !getenv("IADH_SHIM_NO_PREFILTER");
+    if (use_prefilter && settings.useFamily() && nbytes > 4) {
+        ProfileLinks pl;
+        profile_links(profile, S, L, num, pl);
+        std::vector<char> filtered;
+        B.n_prefiltered += prefilter_packed(bytes, nbytes, S, L, fam, flags, pl, settings.getAnchorPoints(), filtered);
+        Multiplicon::unpackHLMultiplicons(filtered.data(), mplicons, *profile, genelists, settings.useFamily());
+    } else
+        Multiplicon::unpackHLMultiplicons((const char*)bytes, mplicons, *profile, genelists, settings.useFamily());
     iadh_stats st;
     iadh_result_stats(res, &st);
     B.t_hl += st.total_ms;

@@ -35,11 +35,12 @@ def _cfg(name):
         return synth.config_tiny(seed=11)
     if name == "tiny_fdr":
         return synth.config_tiny(seed=12, mult_hyp="FDR")
-    cfg = synth.config_tiny_pairs(seed=15)
-    return cfg
+    if name == "small":    # 273 profile searches, levels up to 6: exercises the shim's homolog prefilter
+        return synth.config_small(seed=21)
+    return synth.config_tiny_pairs(seed=15)
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_fdr", "tiny_pairs"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_fdr", "tiny_pairs", "small"])
 def test_dropin_shim_tables_identical_with_oracle_backend(name):
     if not _binaries():
         pytest.skip("reference tree / prebuilt binaries not available")
