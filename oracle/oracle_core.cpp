@@ -584,6 +584,48 @@ static void join_clusters(GHMState& s, int gap, int orient)
                 spec.push_back(std::make_pair(ia, ib));
                 if ((int)spec.size() >= study::spec_k) break;
             }
+            // Validation criterion a device would use (no access to the reference's sequence): spec[t] is
+            // the smallest pair among the clusters no earlier merge of the batch touched, so the reference
+            // picks it at step t unless a pair involving one of the merged clusters A'_0..A'_{t-1} comes
+            // before it in (distance, position i, position j) order.  Computed on copies; compared below
+            // with what the reference really does.
+            int crit = (int)spec.size();
+            {
+                std::vector<int> rank(s.pool.size(), -1);
+                for (size_t a = 0; a < bc.size(); a++) rank[bc[a]] = (int)a;
+                std::vector<Cluster> merged;
+                std::vector<std::tuple<double, int, int>> key;  // (d, rank i, rank j) of every speculated pair
+                for (size_t t = 0; t < spec.size(); t++) {
+                    Cluster c = s.pool[spec[t].first];
+                    merge_with(c, s.pool[spec[t].second]);
+                    merged.push_back(c);
+                    Cluster& cI = s.pool[spec[t].first];
+                    Cluster& cJ = s.pool[spec[t].second];
+                    key.push_back(std::make_tuple(dist_to_cluster(cI, cJ), rank[spec[t].first], rank[spec[t].second]));
+                }
+                for (size_t t = 1; t < spec.size() && crit == (int)spec.size(); t++) {
+                    // the clusters present at step t: untouched ones and the members of spec[t..] as they
+                    // are, spec[0..t-1] in merged form at the position of their first member
+                    std::vector<std::pair<int, Cluster*>> cur_set;  // (rank, cluster)
+                    std::set<int> gone;
+                    for (size_t r = 0; r < t; r++) { gone.insert(spec[r].first); gone.insert(spec[r].second); }
+                    for (int id : bc) if (!gone.count(id)) cur_set.push_back(std::make_pair(rank[id], &s.pool[id]));
+                    for (size_t r = 0; r < t; r++) cur_set.push_back(std::make_pair(rank[spec[r].first], &merged[r]));
+                    for (size_t r = 0; r < t && crit == (int)spec.size(); r++)
+                        for (const auto& other : cur_set) {
+                            if (other.second == &merged[r]) continue;
+                            const bool first = rank[spec[r].first] < other.first;
+                            Cluster& cI = first ? merged[r] : *other.second;
+                            Cluster& cJ = first ? *other.second : merged[r];
+                            const double d = dist_to_cluster(cI, cJ);
+                            if (!(d < gap + 1)) continue;
+                            const std::tuple<double, int, int> k2 = std::make_tuple(d, std::min(rank[spec[r].first], other.first),
+                                                                                   std::max(rank[spec[r].first], other.first));
+                            if (!(k2 < key[t])) continue;
+                            if (partial_overlap(cI, cJ) && r2_from(cI, &cJ, 0, 0) >= s.prm.q_value) { crit = (int)t; break; }
+                        }
+                }
+            }
             int accepted = 0;
             for (size_t t = 0; t < spec.size(); t++) {
                 if (!closest_clusters(s, gap, orient, orient, i, j)) break;
@@ -598,6 +640,8 @@ static void join_clusters(GHMState& s, int gap, int orient)
             study::C.spec_batches++;
             study::C.spec_offered += (long long)spec.size();
             study::C.spec_accepted += accepted;
+            if (crit > accepted) study::C.crit_unsafe++;       // the criterion would have accepted a wrong merge
+            else if (crit < accepted) study::C.crit_lost += accepted - crit;   // safe, but accepted fewer
             if (study::cur) study::cur->batches++;
         }
         return;
@@ -903,6 +947,7 @@ extern "C" void oracle_study_counters(long long* out)
     out[5] = C.first_max; out[6] = C.clusters; out[7] = C.changed;
     out[8] = C.merges; out[9] = C.max_clusters;
     out[22] = C.spec_batches; out[23] = C.spec_offered; out[24] = C.spec_accepted;
+    out[25] = C.crit_unsafe; out[26] = C.crit_lost;
     for (int b = 0; b < 6; b++) { out[10 + b] = C.h_calls[b]; out[16 + b] = C.h_pairs[b]; }
 }
 #endif

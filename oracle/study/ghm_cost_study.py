@@ -79,6 +79,11 @@ def main():
                                heaviest_share_of_work=float(w.max() / max(w.sum(), 1))))
     out["profile_search"] = summary(np.concatenate(allr))
     out["per_search"] = per_search
+    if a.spec:
+        cnt = (C.c_longlong * 27)()
+        eng.lib.oracle_study_counters(cnt)
+        out["speculation"] = dict(k=a.spec, batches=cnt[22], offered=cnt[23], accepted=cnt[24],
+                                  criterion_unsafe_batches=cnt[25], criterion_lost_merges=cnt[26])
     print(json.dumps(out, indent=1))
 
 
