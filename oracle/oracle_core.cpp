@@ -534,6 +534,22 @@ static void study_join_init(GHMState& s, int gap, int orient)
     for (int id : bc)
         if (cur->seen_clusters.insert(std::make_pair(id, (int)s.pool[id].aps.size())).second) C.changed++;
     cur->max_clusters = std::max(cur->max_clusters, (long long)bc.size());
+    // warp-level view of the scan (32 lanes): today one warp takes a row and walks it in chunks of 32
+    // later positions, and a chunk runs the expensive evaluation if ANY of its pairs is near; a two-phase
+    // scan would first compact the near pairs of the whole call and evaluate them 32 at a time
+    {
+        long long near_call = 0;
+        for (size_t i = 0; i + 1 < bc.size(); i++)
+            for (size_t j0 = i + 1; j0 < bc.size(); j0 += 32) {
+                bool any = false;
+                for (size_t j = j0; j < std::min(bc.size(), j0 + 32); j++)
+                    if (apart(h[i], h[j]) <= gap + 1) { any = true; near_call++; }
+                C.warp_chunks++;
+                if (any) C.warp_heavy_now++;
+            }
+        C.warp_heavy_2phase += (near_call + 31) / 32;
+        C.warp_scan_2phase += ((long long)bc.size() * ((long long)bc.size() - 1) / 2 + 31) / 32;
+    }
     for (size_t i = 0; i < bc.size(); i++)
         for (size_t j = i + 1; j < bc.size(); j++) {
             C.pairs++;
@@ -948,6 +964,7 @@ extern "C" void oracle_study_counters(long long* out)
     out[8] = C.merges; out[9] = C.max_clusters;
     out[22] = C.spec_batches; out[23] = C.spec_offered; out[24] = C.spec_accepted;
     out[25] = C.crit_unsafe; out[26] = C.crit_lost;
+    out[27] = C.warp_chunks; out[28] = C.warp_heavy_now; out[29] = C.warp_heavy_2phase; out[30] = C.warp_scan_2phase;
     for (int b = 0; b < 6; b++) { out[10 + b] = C.h_calls[b]; out[16 + b] = C.h_pairs[b]; }
 }
 #endif

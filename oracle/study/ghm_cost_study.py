@@ -80,7 +80,7 @@ def main():
     out["profile_search"] = summary(np.concatenate(allr))
     out["per_search"] = per_search
     if a.spec:
-        cnt = (C.c_longlong * 27)()
+        cnt = (C.c_longlong * 31)()
         eng.lib.oracle_study_counters(cnt)
         out["speculation"] = dict(k=a.spec, batches=cnt[22], offered=cnt[23], accepted=cnt[24],
                                   criterion_unsafe_batches=cnt[25], criterion_lost_merges=cnt[26])

@@ -42,7 +42,7 @@ def main():
     step = max(1, len(allp) // a.pairs)
     sel = allp[::step][:a.pairs]
     r = eng.level2_pairs([p[0] for p in sel], [p[1] for p in sel])
-    out = (C.c_longlong * 27)()
+    out = (C.c_longlong * 31)()
     eng.lib.oracle_study_counters(out)
     ghms, calls, pairs, near_gap, near_max, first_max, clusters, changed = list(out)[:8]
     merges, max_clusters = out[8], out[9]
@@ -53,6 +53,8 @@ def main():
                           near_at_max_gap=near_max, first_time_at_max_gap=first_max,
                           repeat_factor_today=near_gap / max(first_max, 1),
                           scan_factor=pairs / max(first_max, 1), merges=merges, max_clusters=max_clusters,
+                          warp_view=dict(row_chunks_today=out[27], chunks_running_the_evaluation_today=out[28],
+                                         evaluation_steps_two_phase=out[29], scan_steps_two_phase=out[30]),
                           spec=dict(k=a.spec, batches=out[22], offered=out[23], accepted=out[24],
                                     merges_per_batch=merges / max(out[22], 1),
                                     criterion_unsafe_batches=out[25], criterion_lost_merges=out[26]) if a.spec else None,
