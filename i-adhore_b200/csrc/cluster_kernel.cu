@@ -17,6 +17,7 @@
 // State lives in a per-GHM workspace in HBM (L2-resident for all but the densest GHMs).
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "cluster_math.cuh"
 #include "common.h"
@@ -974,6 +975,240 @@ static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int
 #undef JP
 }
 
+// ---- two-phase join (EXPERIMENTAL, IADH_JOIN2=1, single-warp CTAs of the pass-per-launch path) ----
+// Same decisions as join_pass.  What changes is how the warp spends its lanes (of
+// the row chunks join_row walks, a third run the expensive pair evaluation for a single useful lane):
+//   scan     all lanes test pairs with the integer hull boxes only (exact rejections, see j2_box) and
+//            append the survivors, in row-major order, to a 64-entry queue in shared memory;
+//   evaluate whenever 32 survivors are queued every lane evaluates one of them (distance, merged r^2,
+//            interval test), a segmented minimum over equal rows folds them into rb_d / rb_j.
+// A row's result is the lexicographic minimum (distance, rank of the partner) over its valid pairs with
+// distance < gap + 1 -- the definition join_row implements -- whichever lane evaluates which pair.
+// The boxes live in arrays that are idle during the join: xr (x range), act (y low), act_next (y high).
+static __device__ __forceinline__ void j2_box(Ghm& g, int pos, const ClusterRec& c)
+{
+    // the extents pair_better tests before the distance, rounded outwards; non-finite or huge values
+    // (degenerate regressions) become "never apart"
+    const uint32_t s = g.pool[c.off], e = g.pool[c.off + c.n - 1];
+    const double ylo = cm::mind(cm::mind(c.y_end1, c.y_end2), (double)min(KEY_Y(s), KEY_Y(e)));
+    const double yhi = cm::maxd(cm::maxd(c.y_end1, c.y_end2), (double)max(KEY_Y(s), KEY_Y(e)));
+    const double lim = 1e9;
+    int2 x;
+    x.x = (c.x_end1 > -lim && c.x_end1 < lim) ? (int)floor(c.x_end1) : -(1 << 30);
+    x.y = (c.x_end2 > -lim && c.x_end2 < lim) ? (int)ceil(c.x_end2) : (1 << 30);
+    g.xr[pos] = x;
+    g.act[pos] = (ylo > -lim && ylo < lim) ? (int)floor(ylo) : -(1 << 30);
+    g.act_next[pos] = (yhi > -lim && yhi < lim) ? (int)ceil(yhi) : (1 << 30);
+}
+// hulls more than cap = gap + 1 apart in x or y: pair_better rejects such a pair (its bd <= gap + 1)
+static __device__ __forceinline__ bool j2_apart(const Ghm& g, int a, int b, int cap)
+{
+    const int2 ax = g.xr[a], bx = g.xr[b];
+    return (bx.x - ax.y > cap) | (ax.x - bx.y > cap) | (g.act[b] - g.act_next[a] > cap) | (g.act[a] - g.act_next[b] > cap);
+}
+
+// lanes 0..cnt-1 evaluate queue entries (row position, partner position); runs of equal rows are contiguous
+static __device__ __noinline__ void j2_drain(Ghm& g, int o, int gap, double q, const int* qrow, const int* qj, int cnt)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = VTID & 31;
+    int row = -1 - lane, idJ = -1, rk = 0x7fffffff;
+    double d = 1e300;
+    if (lane < cnt) {
+        row = qrow[lane];
+        const int id = g.bc[o][qj[lane]];
+        const ClusterRec& cI = g.cl[g.bc[o][row]];
+        const ClusterRec& cJ = g.cl[id];
+        const uint32_t s1 = g.pool[cI.off], e1 = g.pool[cI.off + cI.n - 1];
+        const uint32_t s2 = g.pool[cJ.off], e2 = g.pool[cJ.off + cJ.n - 1];
+        const double dd = cm::dist_to_cluster(cI, cJ, s1, e1, s2, e2);
+        if (dd < gap + 1 && cm::r2_merged(cI, cJ) >= q && cm::partial_overlap(cI, cJ, g.pool)) {
+            d = dd;
+            idJ = id;
+            rk = g.rank[id];
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double od = __shfl_down_sync(full, d, off);
+        const int orow = __shfl_down_sync(full, row, off);
+        const int oid = __shfl_down_sync(full, idJ, off);
+        const int ork = __shfl_down_sync(full, rk, off);
+        if (lane + off < 32 && orow == row && oid >= 0 && (idJ < 0 || od < d || (od == d && ork < rk))) {
+            d = od;
+            idJ = oid;
+            rk = ork;
+        }
+    }
+    const int prow = __shfl_up_sync(full, row, 1);
+    if (lane < cnt && (lane == 0 || prow != row) && idJ >= 0) {
+        const int idI = g.bc[o][row];
+        const int cj = g.rb_j[idI];
+        if (cj < 0 || d < g.rb_d[idI] || (d == g.rb_d[idI] && rk < g.rank[cj])) {
+            g.rb_d[idI] = d;
+            g.rb_j[idI] = idJ;
+        }
+    }
+    __syncwarp();
+}
+
+static __device__ void join_pass2(Ghm& g, int gap, int o, double q, Red* red, int* sh_s, long long* pf2)
+{
+    static_assert(NT == 32, "join_pass2 is written for single-warp CTAs");
+    __shared__ int qrow[64], qj[64];
+    const unsigned full = 0xffffffffu;
+    const int tid = VTID, lane = tid & 31;
+    int n = g.nbc[o];
+    if (n < 2) return;
+    const int cap = gap + 1;
+    int qn = 0;  // queued survivors (warp-uniform)
+    auto push = [&](bool pass, int row, int j) {
+        const unsigned m = __ballot_sync(full, pass);
+        if (m == 0) return;
+        if (pass) {
+            const int k = qn + __popc(m & ((1u << lane) - 1u));
+            qrow[k] = row;
+            qj[k] = j;
+        }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            j2_drain(g, o, gap, q, qrow, qj, 32);
+            const int rest = qn - 32;
+            int r0 = 0, j0 = 0;
+            if (lane < rest) {
+                r0 = qrow[32 + lane];
+                j0 = qj[32 + lane];
+            }
+            __syncwarp();
+            if (lane < rest) {
+                qrow[lane] = r0;
+                qj[lane] = j0;
+            }
+            qn = rest;
+            __syncwarp();
+        }
+    };
+    auto flush = [&]() {
+        if (qn) j2_drain(g, o, gap, q, qrow, qj, qn);
+        qn = 0;
+    };
+    for (int i = lane; i < n; i += 32) {
+        const int id = g.bc[o][i];
+        g.rank[id] = i;
+        g.pos[id] = i;
+        g.rb_d[id] = gap + 1;
+        g.rb_j[id] = -1;
+        j2_box(g, i, g.cl[id]);
+    }
+    __syncthreads();
+    {
+        // every pair (row < j), flattened: lane k of step t takes pair index 32 t + k in row-major order
+        const long long total = (long long)n * (n - 1) / 2;
+        int row = 0, j = 1 + lane;
+        while (row < n - 1 && j >= n) {
+            j = j - n + row + 2;
+            row++;
+        }
+        for (long long base = 0; base < total; base += 32) {
+            const bool in = row < n - 1;
+            push(in && !j2_apart(g, row, j, cap), row, j);
+            j += 32;
+            while (row < n - 1 && j >= n) {
+                j = j - n + row + 2;
+                row++;
+            }
+        }
+        flush();
+    }
+    __syncthreads();
+    while (true) {
+        // global minimum over the rows: (distance, position of i, position of j)
+        double bd = gap + 1;
+        long long bk = -1;
+        for (int i = tid; i < n; i += NT) {
+            const int id = g.bc[o][i];
+            const int j = g.rb_j[id];
+            if (j < 0) continue;
+            const double d = g.rb_d[id];
+            const long long k = ((long long)i << 32) | (unsigned)g.pos[j];
+            if (bk < 0 || d < bd || (d == bd && k < bk)) {
+                bd = d;
+                bk = k;
+            }
+        }
+        block_min_pair(bd, bk, red);
+        if (bk < 0) break;
+        if (VTID == 0) pf2[7]++;
+        const int pA = (int)(bk >> 32), pB = (int)(bk & 0xffffffff);
+        const int idA = g.bc[o][pA], idB = g.bc[o][pB];
+        __syncthreads();
+        if (!merge_coop(g, idA, idB)) return;
+        if (tid == 0) {
+            g.cl[idB].dead = 1;
+            sh_s[2] = 0;  // rows to recompute
+        }
+        __syncthreads();
+        // erase position pB from the vector (order preserved); the boxes move with their clusters
+        {
+            int v = 0, ylo = 0, yhi = 0;
+            int2 bx = make_int2(0, 0);
+            for (int basei = pB; basei < n - 1; basei += NT) {
+                const int i = basei + tid;
+                if (i < n - 1) {
+                    v = g.bc[o][i + 1];
+                    bx = g.xr[i + 1];
+                    ylo = g.act[i + 1];
+                    yhi = g.act_next[i + 1];
+                }
+                __syncthreads();
+                if (i < n - 1) {
+                    g.bc[o][i] = v;
+                    g.pos[v] = i;
+                    g.xr[i] = bx;
+                    g.act[i] = ylo;
+                    g.act_next[i] = yhi;
+                }
+                __syncthreads();
+            }
+            n--;
+            if (tid == 0) {
+                g.nbc[o] = n;
+                j2_box(g, pA, g.cl[idA]);
+            }
+            __syncthreads();
+        }
+        // rows that pointed at A or B, and A's own row, are recomputed in full (listed in redo);
+        // the other earlier rows only get the pair with the merged cluster as a new candidate
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            bool cand = false;
+            if (i < n) {
+                const int id = g.bc[o][i];
+                const int j = g.rb_j[id];
+                if (id == idA || j == idA || j == idB) {
+                    g.rb_d[id] = gap + 1;
+                    g.rb_j[id] = -1;
+                    if (i < n - 1) g.redo[atomicAdd(&sh_s[2], 1)] = i;
+                } else if (i < pA)
+                    cand = !j2_apart(g, i, pA, cap);
+            }
+            push(cand, i, pA);
+        }
+        __syncthreads();
+        const int nredo = sh_s[2];
+        for (int r = 0; r < nredo; r++) {
+            const int row = g.redo[r];
+            for (int base = row + 1; base < n; base += 32) {
+                const int j = base + lane;
+                push(j < n && !j2_apart(g, row, j, cap), row, j);
+            }
+        }
+        flush();
+        __syncthreads();
+    }
+}
+
 // ---- probability filter ---------------------------------------------------------------------
 
 // BaseCluster::calculateProbability (BaseCluster.cpp:548-590)
@@ -1800,6 +2035,52 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
     }
 }
 
+// The join pass with the two-phase scan (EXPERIMENTAL, IADH_JOIN2=1): a kernel of its own, so that the
+// default kernels above stay exactly as measured.  Same contract as phase1_pass_kernel with pass == 2.
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) phase1_join2_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
+                                                                int* next_item, uint8_t* ws, DevParams prm, int pool_factor,
+                                                                int gi, unsigned long long* dbg)
+{
+    constexpr int NT = 32;   // (VTID)
+    using K = KT<NT, true>;
+    __shared__ Ghm g;
+    __shared__ Red red;
+    __shared__ int sh_s[8];
+    __shared__ int sh_task;
+    __shared__ long long prof2[8];
+    if (threadIdx.x == 0) s_rot = 0;
+    __syncthreads();
+    const int tid = VTID;
+    const int gap = prm.gaps[gi];
+    const double q = prm.q_value;
+    while (true) {
+        if (tid == 0) sh_task = atomicAdd(next_item, 1);
+        __syncthreads();
+        const int ti = sh_task;
+        if (ti >= n_items) break;
+        const int item = items[ti];   // GHM index * 2 + orientation
+        const int o = item & 1;
+        GhmTask& task = tasks[item >> 1];
+        if (task.half_status[o]) continue;
+        if (tid < 8) prof2[tid] = 0;
+        if (tid == 0) setup_view(g, task, ws, prm, pool_factor, o, false, false);
+        __syncthreads();
+        if (g.nbc[o] > 1) K::join_pass2(g, gap, o, q, &red, sh_s, prof2);
+        __syncthreads();
+        if (tid == 0) {
+            task.half_nbc[o] = g.nbc[o];
+            task.half_ncl[o] = g.ncl[o];
+            task.half_pool[o] = g.pool_used[o];
+            task.half_status[o] = g.status;
+            if (dbg)
+                for (int k = 0; k < 8; k++)
+                    if (prof2[k]) atomicAdd(&dbg[k], (unsigned long long)prof2[k]);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- phase 2, one stage per launch (same idea; whole-GHM view) ---------------------------------
 // stage 0: the four cross-orientation enrichments (GHM.cpp:186-189); 1: probability filter
 // (GHM.cpp:198-208); 2: the four enrichments again (:210-213); 3: metaclustering (:215-217) + the
@@ -1932,11 +2213,27 @@ void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* nex
     }
 }
 
+// IADH_JOIN2=1: the join pass of the pass-per-launch path runs phase1_join2_kernel (two-phase scan).
+// Written at the end of round 1 without GPU time left: compiled, reviewed, NOT yet run on a device.
+// Off by default; read at every launch so a test can switch it per call.  To exercise it everywhere:
+//   IADH_JOIN2=1 IADH_PASS_MIN=1 IADH_PASS_RATIO=0 python -m pytest tests -m gpu
+static bool join2_enabled()
+{
+    const char* e = getenv("IADH_JOIN2");
+    return e != nullptr && atoi(e) != 0;
+}
+
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
                         cudaStream_t st, unsigned long long* dbg)
 {
     if (n_items == 0) return;
+    if (pass == 2 && (nt == 32 || nt == 3224 || nt == 3232) && join2_enabled()) {  // IADH_JOIN2=1 (experimental)
+        if (nt == 32) phase1_join2_kernel<16><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
+        else if (nt == 3224) phase1_join2_kernel<24><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
+        else phase1_join2_kernel<32><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
+        return;
+    }
     // (threads, minimum CTAs per SM): the second number caps the registers per thread
     #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi, dbg)
     switch (nt) {

@@ -10,6 +10,7 @@
 #include <algorithm>
 #ifdef ORACLE_STUDY
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <tuple>
@@ -565,6 +566,158 @@ static void study_join_init(GHMState& s, int gap, int orient)
 }
 #endif
 
+#ifdef ORACLE_STUDY
+// Lane-level CPU model of KT<32>::join_pass2 (i-adhore_b200/csrc/cluster_kernel.cu): the same flattened
+// scan, 64-entry queue, 32-wide evaluation with a segmented minimum, classification after a merge and redo
+// rows, with 32 "lanes" stepped in lock-step.  It proposes a merge sequence; join_clusters compares every
+// proposal with the reference's pick (study::C.j2_merges / j2_mismatch).
+struct J2Model {
+    GHMState& s;
+    int gap, o;
+    std::vector<int>& bc;
+    std::vector<double> rb_d;   // by pool id
+    std::vector<int> rb_j, rank, pos;
+    struct Box { int xlo, xhi, ylo, yhi; };
+    std::vector<Box> box;       // by position
+    std::vector<std::pair<int, int>> q;
+    J2Model(GHMState& s_, int gap_, int o_) : s(s_), gap(gap_), o(o_), bc(s_.BC[o_]) {}
+    Box make_box(Cluster& c)
+    {
+        update_stats(c);
+        const int ys = c.aps.front().y, ye = c.aps.back().y;
+        const double ylo = mind(mind(c.y_end1, c.y_end2), (double)std::min(ys, ye));
+        const double yhi = maxd(maxd(c.y_end1, c.y_end2), (double)std::max(ys, ye));
+        const double lim = 1e9;
+        Box b;
+        b.xlo = (c.x_end1 > -lim && c.x_end1 < lim) ? (int)std::floor(c.x_end1) : -(1 << 30);
+        b.xhi = (c.x_end2 > -lim && c.x_end2 < lim) ? (int)std::ceil(c.x_end2) : (1 << 30);
+        b.ylo = (ylo > -lim && ylo < lim) ? (int)std::floor(ylo) : -(1 << 30);
+        b.yhi = (yhi > -lim && yhi < lim) ? (int)std::ceil(yhi) : (1 << 30);
+        return b;
+    }
+    bool apart(int a, int b) const
+    {
+        const int cap = gap + 1;
+        return (box[b].xlo - box[a].xhi > cap) || (box[a].xlo - box[b].xhi > cap) || (box[b].ylo - box[a].yhi > cap) ||
+               (box[a].ylo - box[b].yhi > cap);
+    }
+    void drain(int cnt)
+    {
+        int row[32], idJ[32], rk[32];
+        double d[32];
+        for (int l = 0; l < 32; l++) {
+            row[l] = -1 - l; idJ[l] = -1; rk[l] = 0x7fffffff; d[l] = 1e300;
+            if (l < cnt) {
+                row[l] = q[l].first;
+                const int id = bc[q[l].second];
+                Cluster& cI = s.pool[bc[row[l]]];
+                Cluster& cJ = s.pool[id];
+                const double dd = dist_to_cluster(cI, cJ);
+                if (dd < gap + 1 && r2_from(cI, &cJ, 0, 0) >= s.prm.q_value && partial_overlap(cI, cJ)) {
+                    d[l] = dd; idJ[l] = id; rk[l] = rank[id];
+                }
+            }
+        }
+        for (int off = 1; off < 32; off <<= 1) {
+            int row2[32], id2[32], rk2[32];
+            double d2[32];
+            for (int l = 0; l < 32; l++) { const int m = (l + off < 32) ? l + off : l; row2[l] = row[m]; id2[l] = idJ[m]; rk2[l] = rk[m]; d2[l] = d[m]; }
+            for (int l = 0; l < 32; l++)
+                if (l + off < 32 && row2[l] == row[l] && id2[l] >= 0 && (idJ[l] < 0 || d2[l] < d[l] || (d2[l] == d[l] && rk2[l] < rk[l]))) {
+                    d[l] = d2[l]; idJ[l] = id2[l]; rk[l] = rk2[l];
+                }
+        }
+        for (int l = 0; l < cnt; l++) {
+            const bool head = (l == 0 || row[l - 1] != row[l]);
+            if (!head || idJ[l] < 0) continue;
+            const int idI = bc[row[l]];
+            const int cj = rb_j[idI];
+            if (cj < 0 || d[l] < rb_d[idI] || (d[l] == rb_d[idI] && rk[l] < rank[cj])) { rb_d[idI] = d[l]; rb_j[idI] = idJ[l]; }
+        }
+        q.erase(q.begin(), q.begin() + cnt);
+    }
+    // one warp step: lanes in order, survivors appended, 32 evaluated as soon as 32 are queued
+    void push(const bool* pass, const int* row, const int* j)
+    {
+        for (int l = 0; l < 32; l++)
+            if (pass[l]) q.push_back(std::make_pair(row[l], j[l]));
+        if (q.size() >= 32) drain(32);
+    }
+    void flush() { if (!q.empty()) drain((int)q.size()); }
+    void start()
+    {
+        const int n = (int)bc.size();
+        rb_d.assign(s.pool.size(), gap + 1); rb_j.assign(s.pool.size(), -1);
+        rank.assign(s.pool.size(), -1); pos.assign(s.pool.size(), -1);
+        box.resize(n);
+        for (int i = 0; i < n; i++) { rank[bc[i]] = i; pos[bc[i]] = i; box[i] = make_box(s.pool[bc[i]]); }
+        const long long total = (long long)n * (n - 1) / 2;
+        int row[32], j[32];
+        for (int l = 0; l < 32; l++) {
+            row[l] = 0; j[l] = 1 + l;
+            while (row[l] < n - 1 && j[l] >= n) { j[l] = j[l] - n + row[l] + 2; row[l]++; }
+        }
+        for (long long base = 0; base < total; base += 32) {
+            bool pass[32];
+            for (int l = 0; l < 32; l++) pass[l] = (row[l] < n - 1) && !apart(row[l], j[l]);
+            push(pass, row, j);
+            for (int l = 0; l < 32; l++) {
+                j[l] += 32;
+                while (row[l] < n - 1 && j[l] >= n) { j[l] = j[l] - n + row[l] + 2; row[l]++; }
+            }
+        }
+        flush();
+    }
+    bool pick(int& pA, int& pB) const
+    {
+        const int n = (int)bc.size();
+        double bd = gap + 1;
+        long long bk = -1;
+        for (int i = 0; i < n; i++) {
+            const int id = bc[i];
+            if (rb_j[id] < 0) continue;
+            const long long k = ((long long)i << 32) | (unsigned)pos[rb_j[id]];
+            if (bk < 0 || rb_d[id] < bd || (rb_d[id] == bd && k < bk)) { bd = rb_d[id]; bk = k; }
+        }
+        if (bk < 0) return false;
+        pA = (int)(bk >> 32); pB = (int)(bk & 0xffffffff);
+        return true;
+    }
+    // called after the caller merged position pB into pA and erased pB from bc
+    void merged(int pA, int idA, int idB)
+    {
+        const int n = (int)bc.size();
+        box.erase(box.begin() + pos[idB]);
+        for (int i = 0; i < n; i++) pos[bc[i]] = i;
+        box[pA] = make_box(s.pool[idA]);
+        std::vector<int> redo;
+        for (int base = 0; base < n; base += 32) {
+            bool pass[32]; int row[32], j[32];
+            for (int l = 0; l < 32; l++) {
+                const int i = base + l;
+                pass[l] = false; row[l] = i; j[l] = pA;
+                if (i >= n) continue;
+                const int id = bc[i];
+                const int jj = rb_j[id];
+                if (id == idA || jj == idA || jj == idB) {
+                    rb_d[id] = gap + 1; rb_j[id] = -1;
+                    if (i < n - 1) redo.push_back(i);
+                } else if (i < pA)
+                    pass[l] = !apart(i, pA);
+            }
+            push(pass, row, j);
+        }
+        for (int r : redo)
+            for (int base = r + 1; base < n; base += 32) {
+                bool pass[32]; int row[32], j[32];
+                for (int l = 0; l < 32; l++) { row[l] = r; j[l] = base + l; pass[l] = (j[l] < n) && !apart(r, j[l]); }
+                push(pass, row, j);
+            }
+        flush();
+    }
+};
+#endif
+
 // GHM.cpp:392-404
 static void join_clusters(GHMState& s, int gap, int orient)
 {
@@ -573,6 +726,30 @@ static void join_clusters(GHMState& s, int gap, int orient)
 #endif
     int i, j;
 #ifdef ORACLE_STUDY
+    if (study::j2_model && s.BC[orient].size() >= 2) {
+        std::unique_ptr<J2Model> mp(new J2Model(s, gap, orient));
+        mp->start();
+        while (true) {
+            J2Model& m = *mp;
+            int pA = -1, pB = -1;
+            const bool mine = m.pick(pA, pB);
+            const bool ref = closest_clusters(s, gap, orient, orient, i, j);
+            if (mine != ref || (ref && (pA != i || pB != j))) {
+                study::C.j2_mismatch++;
+                if (!ref) break;
+            }
+            if (!ref) break;
+            study::C.j2_merges++;
+            study::C.merges++;
+            if (study::cur) study::cur->merges++;
+            const int idA = s.BC[orient][i], idB = s.BC[orient][j];
+            merge_with(s.pool[idA], s.pool[idB]);
+            s.BC[orient].erase(s.BC[orient].begin() + j);
+            if (mine && pA == i && pB == j) m.merged(i, idA, idB);
+            else { mp.reset(new J2Model(s, gap, orient)); mp->start(); }   // resynchronise after a mismatch
+        }
+        return;
+    }
     // Speculative batches: at a batch start list every valid pair, take up to K disjoint ones in the
     // reference's order, then follow the reference's own sequence and count how long it agrees with the
     // speculation (= the merges a device could have carried out concurrently and validated afterwards).
@@ -956,6 +1133,7 @@ extern "C" long long oracle_study_records(long long* out, long long cap)
     return n;
 }
 extern "C" void oracle_study_set_spec(int k) { oracle::study::spec_k = k; }
+extern "C" void oracle_study_set_j2_model(int on) { oracle::study::j2_model = on; }
 extern "C" void oracle_study_counters(long long* out)
 {
     using oracle::study::C;
@@ -964,6 +1142,7 @@ extern "C" void oracle_study_counters(long long* out)
     out[8] = C.merges; out[9] = C.max_clusters;
     out[22] = C.spec_batches; out[23] = C.spec_offered; out[24] = C.spec_accepted;
     out[25] = C.crit_unsafe; out[26] = C.crit_lost;
+    out[31] = C.j2_merges; out[32] = C.j2_mismatch;
     out[27] = C.warp_chunks; out[28] = C.warp_heavy_now; out[29] = C.warp_heavy_2phase; out[30] = C.warp_scan_2phase;
     for (int b = 0; b < 6; b++) { out[10 + b] = C.h_calls[b]; out[16 + b] = C.h_pairs[b]; }
 }

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--pairs", type=int, default=300)
     ap.add_argument("--profiles", type=int, default=16)
+    ap.add_argument("--j2", action="store_true", help="run the lane-level model of KT<32>::join_pass2 against the reference's merges")
     ap.add_argument("--spec", type=int, default=0, help="speculative merge batches of up to K disjoint pairs (0 = off)")
     a = ap.parse_args()
     cfg = synth.config_c4(1.0) if a.workload == "c4" else synth.config_c3(1.0)
@@ -54,6 +55,7 @@ def main():
     ds = ingest.dataset_from_synth(cfg)
     eng = capi.Engine(LIB, "oracle_", ds)
     eng.lib.oracle_study_set_spec(C.c_int(a.spec))
+    eng.lib.oracle_study_set_j2_model(C.c_int(1 if a.j2 else 0))
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
     n = ds.n_lists
     allp = [(x, y) for x in range(n) for y in range(x + 1)]
@@ -80,10 +82,14 @@ def main():
     out["profile_search"] = summary(np.concatenate(allr))
     out["per_search"] = per_search
     if a.spec:
-        cnt = (C.c_longlong * 31)()
+        cnt = (C.c_longlong * 33)()
         eng.lib.oracle_study_counters(cnt)
         out["speculation"] = dict(k=a.spec, batches=cnt[22], offered=cnt[23], accepted=cnt[24],
                                   criterion_unsafe_batches=cnt[25], criterion_lost_merges=cnt[26])
+    if a.j2:
+        cnt = (C.c_longlong * 33)()
+        eng.lib.oracle_study_counters(cnt)
+        out["join_pass2_model"] = dict(merges_checked=cnt[31], mismatches=cnt[32])
     print(json.dumps(out, indent=1))
 
 

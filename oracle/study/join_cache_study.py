@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--pairs", type=int, default=400)
+    ap.add_argument("--j2", action="store_true", help="run the lane-level model of KT<32>::join_pass2 against the reference's merges")
     ap.add_argument("--spec", type=int, default=0, help="speculative merge batches of up to K disjoint pairs (0 = off)")
     a = ap.parse_args()
     if a.workload == "c4":      # config 4's per-GHM shape (2,500-gene lists, 20,000 families), fewer genomes
@@ -36,13 +37,14 @@ def main():
     ds = ingest.dataset_from_synth(cfg)
     eng = capi.Engine(LIB, "oracle_", ds)
     eng.lib.oracle_study_set_spec(C.c_int(a.spec))
+    eng.lib.oracle_study_set_j2_model(C.c_int(1 if a.j2 else 0))
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
     n = ds.n_lists
     allp = [(x, y) for x in range(n) for y in range(x + 1)]
     step = max(1, len(allp) // a.pairs)
     sel = allp[::step][:a.pairs]
     r = eng.level2_pairs([p[0] for p in sel], [p[1] for p in sel])
-    out = (C.c_longlong * 31)()
+    out = (C.c_longlong * 33)()
     eng.lib.oracle_study_counters(out)
     ghms, calls, pairs, near_gap, near_max, first_max, clusters, changed = list(out)[:8]
     merges, max_clusters = out[8], out[9]
@@ -53,6 +55,7 @@ def main():
                           near_at_max_gap=near_max, first_time_at_max_gap=first_max,
                           repeat_factor_today=near_gap / max(first_max, 1),
                           scan_factor=pairs / max(first_max, 1), merges=merges, max_clusters=max_clusters,
+                          join_pass2_model=dict(merges_checked=out[31], mismatches=out[32]) if a.j2 else None,
                           warp_view=dict(row_chunks_today=out[27], chunks_running_the_evaluation_today=out[28],
                                          evaluation_steps_two_phase=out[29], scan_steps_two_phase=out[30]),
                           spec=dict(k=a.spec, batches=out[22], offered=out[23], accepted=out[24],
