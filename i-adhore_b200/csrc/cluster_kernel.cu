@@ -34,6 +34,16 @@ constexpr int MAXW = 16;  // warps per CTA, upper bound (block size is a templat
 // Each CTA therefore rotates its thread numbering by whole warps: the k-th CTA to arrive on an SM
 // puts its virtual thread 0 in warp k % NW.  All code below uses the virtual id VTID.
 __shared__ int s_rot;
+static __device__ __forceinline__ unsigned read_smid()
+{
+#ifdef IADH_HOST_EMU   // tests/emu: the kernels compiled for the host, lanes as fibers
+    return 0;
+#else
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    return smid;
+#endif
+}
 #define VTID ((int)((threadIdx.x + (unsigned)s_rot) & (unsigned)(NT - 1)))
 
 struct Ghm {
@@ -1806,8 +1816,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
     __shared__ long long prof[8];
     __shared__ long long prof2[8];
     if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned smid = read_smid();
         s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
     }
     __syncthreads();
@@ -1982,8 +1991,7 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
     __shared__ int sh_task;
     __shared__ long long prof2[8];
     if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned smid = read_smid();
         s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
     }
     __syncthreads();
@@ -2100,8 +2108,7 @@ __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, 
     __shared__ int sh_s[8];
     __shared__ int sh_task;
     if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned smid = read_smid();
         s_rot = (NW > 1) ? 32 * (atomicAdd(&sm_slot[smid & 1023], 1) % NW) : 0;
     }
     __syncthreads();
@@ -2184,6 +2191,7 @@ __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, 
 
 }  // namespace
 
+#ifndef IADH_HOST_EMU   // (the host emulation of tests/emu calls the kernels directly)
 void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
                     const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf, bool hl,
                     int grid, int nt, cudaStream_t st)
@@ -2246,3 +2254,4 @@ void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next
     default: PASS_LAUNCH(64, 8); break;
     }
 }
+#endif  // IADH_HOST_EMU

@@ -976,6 +976,31 @@ void run_collinear(GHMInput& g, const Params& prm, std::vector<Cluster>& cluster
         enrich_clusters(s, prm.gaps[i], 1, 1);
         join_clusters(s, prm.gaps[i], 1);
     }
+#ifdef ORACLE_STUDY
+    // ORACLE_STUDY_DUMP=<file>: the state after the gap-size loop (per orientation the cluster vector with
+    // every cluster's anchor points in multiset order, then the dots left in the matrix) -- what
+    // tests/emu/emu_join2 dumps for the emulated device kernels
+    if (const char* path = getenv("ORACLE_STUDY_DUMP")) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        FILE* f = fopen(path, "a");
+        if (f) {
+            fprintf(f, "GHM %zu %zu\n", (size_t)g.cnt[0], (size_t)g.cnt[1]);
+            for (int o = 0; o < 2; o++) {
+                fprintf(f, " o%d clusters %zu\n", o, s.BC[o].size());
+                for (int id : s.BC[o]) {
+                    fprintf(f, "  c %zu:", s.pool[id].aps.size());
+                    for (const AP& e : s.pool[id].aps) fprintf(f, " %d,%d", e.x, e.y);
+                    fprintf(f, "\n");
+                }
+                fprintf(f, "  left %zu:", g.dots[o].size());
+                for (const std::pair<int, int>& d : g.dots[o]) fprintf(f, " %d,%d", d.first, d.second);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+#endif
     for (int rep = 0; rep < 2; rep++) {
         enrich_clusters(s, prm.gap_size, 0, 0);
         enrich_clusters(s, prm.gap_size, 1, 1);

@@ -1,0 +1,65 @@
+"""Writes the input of tests/emu/emu_join2 from a reference trace: the dot sets of its level-2 and
+profile GHMs (the reference's own buildMatrix output) and the gap-size schedule."""
+import struct
+import sys
+
+import numpy as np
+
+sys.path.insert(0, __file__.rsplit("/", 3)[0] + "/tests")
+from trace_io import read_trace  # noqa: E402
+
+
+def write_input(trace_path, out_path, max_ghms=None, min_dots=6, kinds=("l2", "hl")):
+    tr = read_trace(trace_path)
+    gaps = tr.params["gaps"]
+    recs = []
+    for ev in tr.events:
+        if ev[0] not in kinds:
+            continue
+        d0, d1 = ev[1].dots
+        if len(d0) + len(d1) < min_dots:
+            continue
+        keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+        recs.append((len(d0), len(d1), keys))
+        if max_ghms and len(recs) >= max_ghms:
+            break
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i10i", len(gaps), *(list(gaps) + [0] * (10 - len(gaps)))))
+        fh.write(struct.pack("<di", tr.params["q_value"], len(recs)))
+        for n0, n1, keys in recs:
+            fh.write(struct.pack("<IIQi", n0, n1, 1000000, 2))
+            fh.write(keys.tobytes())
+    return len(recs)
+
+
+def write_synth_input(out_path, workload="c3", n_pairs=12):
+    """Dot sets of the heaviest list pairs of a BASELINE-shaped synthetic set (dots from the oracle's build):
+    GHMs with 100+ clusters per orientation, which the tiny golden traces do not have."""
+    sys.path.insert(0, __file__.rsplit("/", 3)[0] + "/i-adhore_b200/python")
+    import parity_lib as pl
+    from iadhore_b200 import capi, ingest, synth
+    cfg = synth.config_c3(1.0) if workload == "c3" else synth.config_c4(1.0)
+    cfg.genomes = cfg.genomes[:4]
+    ds = ingest.dataset_from_synth(cfg)
+    eng = pl.oracle_engine(ds)
+    n = ds.n_lists
+    pairs = [(x, y) for x in range(n) for y in range(x + 1)][::7][:150]
+    dots = eng.build_dots([p[0] for p in pairs], [p[1] for p in pairs])
+    order = sorted(range(len(pairs)), key=lambda i: -(len(dots[i][0]) + len(dots[i][1])))[:n_pairs]
+    gaps = capi.gap_sizes(cfg.gap_size)
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i10i", len(gaps), *(list(gaps) + [0] * (10 - len(gaps)))))
+        fh.write(struct.pack("<di", cfg.q_value, len(order)))
+        for i in order:
+            d0, d1 = dots[i]
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            fh.write(struct.pack("<IIQi", len(d0), len(d1), 1000000, 2))
+            fh.write(keys.tobytes())
+    return len(order)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "--synth":
+        print(write_synth_input(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "c3", int(sys.argv[4]) if len(sys.argv) > 4 else 12))
+    else:
+        print(write_input(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None))

@@ -1,0 +1,79 @@
+"""The clustering kernels of cluster_kernel.cu compiled for the host and run under a one-warp emulation
+(tests/emu/: 32 lanes as fibers, every warp collective and barrier a rendezvous), in a container without a GPU.
+
+1. Fidelity of the emulation: the DEFAULT phase-1 kernels (seed / enrich / join per gap size), emulated, leave
+   exactly the state the oracle has after its gap-size loop -- cluster vectors, every cluster's anchor points
+   in order, the dots left in both matrices -- for all level-2 GHMs of a reference trace.
+2. The experimental two-phase join kernel (phase1_join2_kernel, IADH_JOIN2=1, written when no GPU time was
+   left) produces the same complete state as the default join, field by field, on the GHMs of reference
+   traces (family and pairs tables) and on heavy config-3-shaped GHMs (100+ clusters, 150+ merges each).
+"""
+import json
+import os
+import subprocess
+
+import pytest
+
+import parity_lib as pl
+from iadhore_b200 import capi
+from trace_io import read_trace
+
+EMU_DIR = os.path.join(pl.HERE, "emu")
+EMU = os.path.join(pl.REPO, "build", "emu", "emu_join2")
+STUDY_LIB = os.path.join(pl.REPO, "oracle", "study", "liboracle_study.so")
+CUDA_INC = "/usr/local/cuda/include/cuda_runtime.h"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CUDA_INC), reason="CUDA headers not installed")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-C", EMU_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    import sys
+    sys.path.insert(0, EMU_DIR)
+    import make_input
+    return make_input
+
+
+def _run(path, env=None):
+    p = subprocess.run([EMU, path], capture_output=True, text=True, env=dict(os.environ, **(env or {})), timeout=900)
+    assert p.returncode in (0, 1), p.stderr[-500:]
+    return json.loads(p.stdout.strip().splitlines()[-1]), p.stderr
+
+
+def test_emulated_default_kernels_match_the_oracle_state(emu, tmp_path):
+    subprocess.run(["make", "-C", os.path.join(pl.REPO, "oracle"), "study"], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    trace = [p for p in pl.golden_traces("family") if "tiny_4g" in p][0]
+    inp, d_emu, d_ora = str(tmp_path / "in.bin"), str(tmp_path / "emu.txt"), str(tmp_path / "ora.txt")
+    n = emu.write_input(trace, inp, min_dots=3, kinds=("l2",))
+    res, _ = _run(inp, {"EMU_DUMP": d_emu})
+    assert res["ghms"] == n and res["merges"] > 100
+    tr = read_trace(trace)
+    os.environ["ORACLE_STUDY_DUMP"] = d_ora
+    try:
+        eng = capi.Engine(STUDY_LIB, "oracle_", tr.dataset)
+        pl.set_params_from(eng, tr.params)
+        l2 = [e[1] for e in tr.events if e[0] == "l2"]
+        eng.level2_pairs([g.x_list for g in l2], [g.y_list for g in l2])
+    finally:
+        os.environ.pop("ORACLE_STUDY_DUMP", None)
+    assert open(d_emu).read() == open(d_ora).read()
+
+
+@pytest.mark.parametrize("name", ["tiny_bf", "tiny_pairs"])
+def test_two_phase_join_kernel_equals_default_join_on_reference_traces(emu, tmp_path, name):
+    trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
+    inp = str(tmp_path / "in.bin")
+    n = emu.write_input(trace, inp)          # level-2 and profile GHMs with at least 6 dots
+    res, err = _run(inp)
+    assert res["ghms"] == n > 50 and res["merges"] > 100
+    assert res["mismatching_ghms"] == 0, err[-800:]
+
+
+def test_two_phase_join_kernel_equals_default_join_on_heavy_ghms(emu, tmp_path):
+    inp = str(tmp_path / "in.bin")
+    assert emu.write_synth_input(inp, "c3", 8) == 8
+    res, err = _run(inp)
+    assert res["merges"] > 1000          # > 125 merges per GHM: queue drains of 32 and multi-chunk rows
+    assert res["mismatching_ghms"] == 0, err[-800:]
