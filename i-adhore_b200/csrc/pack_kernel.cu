@@ -22,7 +22,11 @@ using pk::PGhm;
 using pk::pghm_init;
 using pk::seg_match;
 
+#ifdef IADH_HOST_EMU   // tests/emu: one emulated warp per CTA
+constexpr int PT = 32;
+#else
 constexpr int PT = 128;
+#endif
 constexpr int PW = PT / 32;
 
 __device__ __forceinline__ void put32(uint8_t* p, int32_t v)
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, co
 
 }  // namespace
 
+#ifndef IADH_HOST_EMU
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st)
 {
@@ -183,3 +188,4 @@ void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int6
     if (hl) pack_write_kernel<true><<<n_sel, PT, 0, st>>>(tasks, sel, out_off, n_sel, ws, ds, pf, pool_factor, out);
     else pack_write_kernel<false><<<n_sel, PT, 0, st>>>(tasks, sel, out_off, n_sel, ws, ds, pf, pool_factor, out);
 }
+#endif  // IADH_HOST_EMU

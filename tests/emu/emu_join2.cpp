@@ -12,54 +12,7 @@
 
 #include "../../i-adhore_b200/csrc/cluster_kernel.cu"
 
-namespace emu {
-Fiber fibers[LANES];
-ucontext_t sched_ctx;
-int cur = 0, n_done = 0, arrived = 0;
-unsigned long long generation = 0, n_collectives = 0;
-unsigned block_id = 0;
-unsigned char xchg[2][LANES][16];
-static const std::function<void()>* g_body = nullptr;
-static void trampoline()
-{
-    (*g_body)();
-    fibers[cur].done = true;
-    n_done++;
-    swapcontext(&fibers[cur].ctx, &sched_ctx);
-}
-void run_block(unsigned block, const std::function<void()>& body)
-{
-    block_id = block;
-    g_body = &body;
-    n_done = 0;
-    arrived = 0;
-    for (int l = 0; l < LANES; l++) {
-        Fiber& f = fibers[l];
-        if (f.stack.empty()) f.stack.resize(1 << 20);
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
-        f.ctx.uc_link = &sched_ctx;
-        f.done = false;
-        makecontext(&f.ctx, trampoline, 0);
-    }
-    while (n_done < LANES) {
-        bool progressed = false;
-        for (int l = 0; l < LANES; l++) {
-            if (fibers[l].done) continue;
-            cur = l;
-            swapcontext(&sched_ctx, &fibers[l].ctx);
-            progressed = true;
-            // a lane that exited may complete a rendezvous the others are waiting in
-            if (arrived > 0 && arrived == LANES - n_done) {
-                arrived = 0;
-                generation++;
-            }
-        }
-        if (!progressed) break;
-    }
-}
-}  // namespace emu
+#include "emu_runtime.inc"
 
 struct GhmIn {
     uint32_t cnt[2];

@@ -1,0 +1,131 @@
+// TEST INFRASTRUCTURE: the fused clustering kernel (cluster_kernel<32>: phase 1, phase 2, K3 measuring pass)
+// and the K3 writer (pack_write_kernel) compiled for the host and run under the one-warp emulation of
+// cuda_emu.h, GHM by GHM, on the dot sets of a reference trace; the packed multiplicons must equal the
+// reference's bytes (Multiplicon::packMultiplicons of the same GHM), p-values included.
+//
+// input (little endian): i32 n_gaps, gaps[10], gap_size, cluster_gap, anchor_points, mult_hyp; f64 q, prob_cutoff;
+//   i32 n_lists; i64 list_off[n_lists+1]; i32 fam[T], gid[T], num_id[T]; u8 flags[T]   (T = list_off[n_lists])
+//   i32 n_profiles; per profile: i32 S, L; i32 fam[S*L], gid[S*L], num_id[S*L]; u8 flags[S*L]
+//   i32 n_ghm; per GHM: i32 profile (-1 = level 2), x_list, y_list, x_object_id, level; u64 area; u32 cnt0, cnt1;
+//                       u32 keys[cnt0+cnt1]; i32 n_expected; u8 expected[n_expected]
+//   (expected = the reference's packed blob of the GHM: i32 multiplicon count, then the multiplicons)
+#define IADH_HOST_EMU 1
+#include "cuda_emu.h"
+
+#include "../../i-adhore_b200/csrc/cluster_kernel.cu"
+#include "../../i-adhore_b200/csrc/pack_kernel.cu"
+
+#include "emu_runtime.inc"
+
+template <typename T>
+static bool rd(FILE* f, T* p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { fprintf(stderr, "usage: %s <trace_ghms.bin>\n", argv[0]); return 2; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror(argv[1]); return 2; }
+    DevParams prm;
+    memset(&prm, 0, sizeof prm);
+    if (!rd(f, &prm.n_gaps, 1) || !rd(f, prm.gaps, 10) || !rd(f, &prm.gap_size, 1) || !rd(f, &prm.cluster_gap, 1) ||
+        !rd(f, &prm.anchor_points, 1) || !rd(f, &prm.mult_hyp, 1) || !rd(f, &prm.q_value, 1) || !rd(f, &prm.prob_cutoff, 1)) return 2;
+    const int coop[4] = {16, 16, 16, 48};
+    memcpy(prm.coop, coop, sizeof coop);
+    int n_lists = 0;
+    if (!rd(f, &n_lists, 1)) return 2;
+    std::vector<int64_t> list_off(n_lists + 1);
+    if (!rd(f, list_off.data(), list_off.size())) return 2;
+    const size_t T = (size_t)list_off[n_lists];
+    std::vector<int32_t> fam(T), gid(T), num_id(T);
+    std::vector<uint8_t> flags(T);
+    if (!rd(f, fam.data(), T) || !rd(f, gid.data(), T) || !rd(f, num_id.data(), T) || !rd(f, flags.data(), T)) return 2;
+    DatasetDev ds;
+    memset(&ds, 0, sizeof ds);
+    ds.n_lists = n_lists;
+    ds.list_off = list_off.data();
+    ds.fam = fam.data();
+    ds.gid = gid.data();
+    ds.num_id = num_id.data();
+    ds.flags = flags.data();
+    struct Prof { int S, L; std::vector<int32_t> fam, gid, num_id; std::vector<uint8_t> flags; };
+    int n_prof = 0;
+    if (!rd(f, &n_prof, 1)) return 2;
+    std::vector<Prof> profs(n_prof);
+    for (Prof& p : profs) {
+        if (!rd(f, &p.S, 1) || !rd(f, &p.L, 1)) return 2;
+        const size_t n = (size_t)p.S * p.L;
+        p.fam.resize(n); p.gid.resize(n); p.num_id.resize(n); p.flags.resize(n);
+        if (!rd(f, p.fam.data(), n) || !rd(f, p.gid.data(), n) || !rd(f, p.num_id.data(), n) || !rd(f, p.flags.data(), n)) return 2;
+    }
+    int n_ghm = 0;
+    if (!rd(f, &n_ghm, 1)) return 2;
+    long long bad = 0, n_mult = 0, n_bytes = 0;
+    for (int gidx = 0; gidx < n_ghm; gidx++) {
+        int32_t pi, xl, yl, xobj, level, n_exp;
+        uint64_t area;
+        uint32_t cnt[2];
+        if (!rd(f, &pi, 1) || !rd(f, &xl, 1) || !rd(f, &yl, 1) || !rd(f, &xobj, 1) || !rd(f, &level, 1) || !rd(f, &area, 1) || !rd(f, cnt, 2)) return 2;
+        const bool hl = pi >= 0;
+        ProfileDev pf;
+        memset(&pf, 0, sizeof pf);
+        if (hl) {
+            const Prof& p = profs[pi];
+            pf.S = p.S; pf.L = p.L;
+            pf.fam = p.fam.data(); pf.gid = p.gid.data(); pf.num_id = p.num_id.data(); pf.flags = p.flags.data();
+        }
+        std::vector<uint32_t> keys(cnt[0] + cnt[1]);
+        if (!rd(f, keys.data(), keys.size()) || !rd(f, &n_exp, 1)) return 2;
+        std::vector<uint8_t> expected(n_exp);
+        if (!rd(f, expected.data(), expected.size())) return 2;
+        std::vector<uint8_t> got(4, 0);
+        const int D = (int)(cnt[0] + cnt[1]);
+        if (D >= prm.anchor_points && D > 0) {
+            for (int pool_factor = 8; pool_factor <= 2048; pool_factor *= 4) {
+                const WsLayout L = ws_layout(D, pool_factor);
+                std::vector<uint8_t> ws(L.total + 256, 0);
+                GhmTask task;
+                memset(&task, 0, sizeof task);
+                task.x_list = xl; task.y_list = yl; task.x_object_id = xobj; task.y_object_id = yl; task.level = level;
+                task.cnt[0] = cnt[0]; task.cnt[1] = cnt[1];
+                task.area = area;
+                task.half_mask = (cnt[0] >= 3 ? 1 : 0) | (cnt[1] >= 3 ? 2 : 0);
+                task.half_needed = 1;
+                GhmProf prof;
+                memset(&prof, 0, sizeof prof);
+                const int item = 0 * 4 + task.half_mask;
+                int next = 0;
+                std::vector<int> sm_slot(1024, 0);
+                emu::run_block(0, [&]() { cluster_kernel<32>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
+                if (task.status != 0) continue;   // anchor-point pool exhausted: retry with a larger pool, like the engine
+                int32_t nm = task.n_mult;
+                memcpy(got.data(), &nm, 4);
+                if (nm > 0) {
+                    got.resize(4 + (size_t)task.out_bytes);
+                    const int sel = 0;
+                    const int64_t off = 0;
+                    if (hl) emu::run_block(0, [&]() { pack_write_kernel<true>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
+                    else emu::run_block(0, [&]() { pack_write_kernel<false>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
+                }
+                break;
+            }
+        }
+        if (expected.size() < 4) expected.assign(4, 0);
+        int32_t nm;
+        memcpy(&nm, got.data(), 4);
+        n_mult += nm;
+        n_bytes += (long long)got.size() - 4;
+        if (got != expected) {
+            bad++;
+            int32_t ne;
+            memcpy(&ne, expected.data(), 4);
+            size_t k = 0;
+            while (k < got.size() && k < expected.size() && got[k] == expected[k]) k++;
+            fprintf(stderr, "GHM %d (%s %d x %d, D = %u + %u): %d multiplicons / %zu bytes, reference %d / %zu, first difference at byte %zu\n", gidx, hl ? "profile" : "level 2", xl,
+                    yl, cnt[0], cnt[1], nm, got.size(), ne, expected.size(), k);
+        }
+    }
+    fclose(f);
+    printf("{\"ghms\": %d, \"multiplicons\": %lld, \"bytes\": %lld, \"mismatching_ghms\": %lld, \"collectives\": %llu}\n", n_ghm, n_mult, n_bytes, bad,
+           emu::n_collectives);
+    return bad ? 1 : 0;
+}

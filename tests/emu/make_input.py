@@ -32,6 +32,56 @@ def write_input(trace_path, out_path, max_ghms=None, min_dots=6, kinds=("l2", "h
     return len(recs)
 
 
+def write_k2k3_input(trace_path, out_path, max_hl=None):
+    """Input of tests/emu/emu_k2k3: settings, the flattened dataset, the profiles and, per GHM of the trace
+    (level 2 and profile x list), its dot sets, area, level and the reference's packed multiplicons."""
+    tr = read_trace(trace_path)
+    p, ds = tr.params, tr.dataset
+    gaps = p["gaps"]
+    sizes = np.diff(ds.list_off).astype(np.int64)
+    masked = [np.zeros(int(n), bool) for n in sizes]
+    profiles, recs = [], []
+    n_hl = 0
+    for ev in tr.events:
+        if ev[0] == "l2":
+            g = ev[1]
+            nx, ny = int(sizes[g.x_list]), int(sizes[g.y_list])
+            area = (nx * (nx - 1) // 2 if g.x_list == g.y_list else nx * ny) & 0xffffffff   # GHM.cpp:221-236, 32-bit
+            recs.append((-1, g.x_list, g.y_list, g.x_list, 2, area, g))
+        elif ev[0] == "mask":
+            masked[ev[1]][ev[2]:ev[3] + 1] = True
+        elif ev[0] == "profile":
+            profiles.append(ev[1])
+        elif ev[0] == "hl" and (max_hl is None or n_hl < max_hl):
+            g, pr = ev[1], profiles[-1]
+            area = (pr.L * (int(sizes[g.y_list]) - int(masked[g.y_list].sum()))) & 0xffffffff
+            recs.append((len(profiles) - 1, -1, g.y_list, pr.x_object_id, pr.S + 1, area, g))
+            n_hl += 1
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i10i", len(gaps), *(list(gaps) + [0] * (10 - len(gaps)))))
+        fh.write(struct.pack("<iiiidd", p["gap_size"], p["cluster_gap"], p["anchor_points"], p["mult_hyp"], p["q_value"], p["prob_cutoff"]))
+        fh.write(struct.pack("<i", ds.n_lists))
+        fh.write(np.ascontiguousarray(ds.list_off, "<i8").tobytes())
+        for a in (ds.fam, ds.gid, ds.num_id):
+            fh.write(np.ascontiguousarray(a, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.flags, "u1").tobytes())
+        fh.write(struct.pack("<i", len(profiles)))
+        for pr in profiles:
+            fh.write(struct.pack("<ii", pr.S, pr.L))
+            for a in (pr.fam, pr.gid, pr.num_id):
+                fh.write(np.ascontiguousarray(a, "<i4").tobytes())
+            fh.write(np.ascontiguousarray(pr.flags, "u1").tobytes())
+        fh.write(struct.pack("<i", len(recs)))
+        for prof, xl, yl, xobj, level, area, g in recs:
+            d0, d1 = g.dots
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            fh.write(struct.pack("<iiiiiQII", prof, xl, yl, xobj, level, area, len(d0), len(d1)))
+            fh.write(keys.tobytes())
+            fh.write(struct.pack("<i", len(g.packed)))
+            fh.write(g.packed)
+    return len(recs)
+
+
 def write_synth_input(out_path, workload="c3", n_pairs=12):
     """Dot sets of the heaviest list pairs of a BASELINE-shaped synthetic set (dots from the oracle's build):
     GHMs with 100+ clusters per orientation, which the tiny golden traces do not have."""
@@ -59,7 +109,9 @@ def write_synth_input(out_path, workload="c3", n_pairs=12):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "--synth":
+    if sys.argv[1] == "--k2k3":
+        print(write_k2k3_input(sys.argv[2], sys.argv[3]))
+    elif sys.argv[1] == "--synth":
         print(write_synth_input(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "c3", int(sys.argv[4]) if len(sys.argv) > 4 else 12))
     else:
         print(write_input(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None))

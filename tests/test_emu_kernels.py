@@ -1,5 +1,9 @@
-"""The clustering kernels of cluster_kernel.cu compiled for the host and run under a one-warp emulation
+"""The kernels of cluster_kernel.cu and pack_kernel.cu compiled for the host and run under a one-warp emulation
 (tests/emu/: 32 lanes as fibers, every warp collective and barrier a rendezvous), in a container without a GPU.
+
+0. End to end: the fused clustering kernel (phase 1, phase 2, K3 measuring pass; the 32-thread instantiation) and
+   the K3 writer, emulated GHM by GHM on the dot sets of the reference traces, produce the reference's packed
+   multiplicons byte for byte -- level-2 and profile GHMs, all three multiple-hypothesis modes, p-values included.
 
 1. Fidelity of the emulation: the DEFAULT phase-1 kernels (seed / enrich / join per gap size), emulated, leave
    exactly the state the oracle has after its gap-size loop -- cluster vectors, every cluster's anchor points
@@ -20,6 +24,7 @@ from trace_io import read_trace
 
 EMU_DIR = os.path.join(pl.HERE, "emu")
 EMU = os.path.join(pl.REPO, "build", "emu", "emu_join2")
+EMU_K2K3 = os.path.join(pl.REPO, "build", "emu", "emu_k2k3")
 STUDY_LIB = os.path.join(pl.REPO, "oracle", "study", "liboracle_study.so")
 CUDA_INC = "/usr/local/cuda/include/cuda_runtime.h"
 
@@ -28,15 +33,15 @@ pytestmark = pytest.mark.skipif(not os.path.exists(CUDA_INC), reason="CUDA heade
 
 @pytest.fixture(scope="module")
 def emu():
-    subprocess.run(["make", "-C", EMU_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", EMU_DIR, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     import sys
     sys.path.insert(0, EMU_DIR)
     import make_input
     return make_input
 
 
-def _run(path, env=None):
-    p = subprocess.run([EMU, path], capture_output=True, text=True, env=dict(os.environ, **(env or {})), timeout=900)
+def _run(path, env=None, exe=None):
+    p = subprocess.run([exe or EMU, path], capture_output=True, text=True, env=dict(os.environ, **(env or {})), timeout=900)
     assert p.returncode in (0, 1), p.stderr[-500:]
     return json.loads(p.stdout.strip().splitlines()[-1]), p.stderr
 
@@ -76,4 +81,15 @@ def test_two_phase_join_kernel_equals_default_join_on_heavy_ghms(emu, tmp_path):
     assert emu.write_synth_input(inp, "c3", 8) == 8
     res, err = _run(inp)
     assert res["merges"] > 1000          # > 125 merges per GHM: queue drains of 32 and multi-chunk rows
+    assert res["mismatching_ghms"] == 0, err[-800:]
+
+
+@pytest.mark.parametrize("name", ["tiny_bf", "tiny_fdr", "tiny_none", "tiny_4g", "tiny_pairs"])
+def test_emulated_device_code_reproduces_the_reference_bytes(emu, tmp_path, name):
+    trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
+    inp = str(tmp_path / "in.bin")
+    # (profile GHMs of a pairs trace need the partner buckets of iadh_create_pairs: level 2 only there)
+    n = emu.write_k2k3_input(trace, inp, max_hl=0 if "pairs" in name else None)
+    res, err = _run(inp, exe=EMU_K2K3)
+    assert res["ghms"] == n and res["multiplicons"] > 30 and res["bytes"] > 15000
     assert res["mismatching_ghms"] == 0, err[-800:]
