@@ -22,8 +22,8 @@ using pk::PGhm;
 using pk::pghm_init;
 using pk::seg_match;
 
-#ifdef IADH_HOST_EMU   // tests/emu: one emulated warp per CTA
-constexpr int PT = 32;
+#if defined(IADH_HOST_EMU) && defined(IADH_EMU_PT)   // tests/emu: the emulated block size of the writer
+constexpr int PT = IADH_EMU_PT;
 #else
 constexpr int PT = 128;
 #endif

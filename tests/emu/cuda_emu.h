@@ -1,8 +1,9 @@
-// TEST INFRASTRUCTURE: a minimal host emulation of one CUDA thread block of ONE warp, enough to compile
+// TEST INFRASTRUCTURE: a minimal host emulation of one CUDA thread block (32 ... 256 threads), enough to compile
 // i-adhore_b200/csrc/cluster_kernel.cu with g++ and run its kernels on the CPU (GPU-less container).
-// The 32 lanes are fibers (ucontext) scheduled round-robin inside one OS thread; every warp collective and
-// barrier is a rendezvous of all 32, so divergent code paths between collectives behave as on the device as
-// long as the collectives themselves are reached by all lanes (true for these kernels).  Arithmetic is the
+// The threads are fibers (ucontext) scheduled round-robin inside one OS thread; a warp collective is a
+// rendezvous of the 32 lanes of the warp, __syncthreads of the whole block, so divergent code paths between
+// collectives behave as on the device as long as the collectives themselves are reached by all their
+// participants (true for these kernels).  Arithmetic is the
 // host's IEEE double arithmetic, compiled with -ffp-contract=off (the device code is built --fmad=false).
 // Not a performance model and not a race detector: lanes only interleave at collectives.
 #pragma once
@@ -29,69 +30,95 @@
 #endif
 
 namespace emu {
-constexpr int LANES = 32;
+constexpr int MAX_THREADS = 256, MAX_WARPS = MAX_THREADS / 32;
 struct Idx { unsigned x, y, z; };
 struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = true; };
-extern Fiber fibers[LANES];
+extern Fiber fibers[MAX_THREADS];
 extern ucontext_t sched_ctx;
-extern int cur, n_done, arrived;
-extern unsigned long long generation;
+extern int cur, n_threads, n_done, n_done_warp[MAX_WARPS];
+extern int arrived_block, arrived_warp[MAX_WARPS];
+extern unsigned long long block_gen, warp_gen[MAX_WARPS];
 extern unsigned block_id;
-extern unsigned char xchg[2][LANES][16];
+extern unsigned char xchg[2][MAX_THREADS][16];
 extern unsigned long long n_collectives;
 
 inline void yield() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
-// rendezvous of all lanes that have not exited
-inline void barrier()
+inline int blocked()
 {
-    const unsigned long long my = generation;
-    if (++arrived == LANES - n_done) {
-        arrived = 0;
-        generation++;
+    int b = arrived_block;
+    for (int w = 0; w < MAX_WARPS; w++) b += arrived_warp[w];
+    return b;
+}
+// Thread 0 leaves a rendezvous only after every other live thread is waiting in its next one.  The device
+// code has one pattern that depends on a warp being converged between two barriers: all lanes read a
+// value, then thread 0 (the serial sections are `if (tid == 0)`) updates it.  Running thread 0 strictly
+// last in every segment reproduces "reads first, then the write".
+inline void thread0_last()
+{
+    if (cur == 0)
+        while (blocked() < n_threads - n_done - 1) yield();
+}
+// __syncthreads: rendezvous of all threads of the block that have not exited
+inline void barrier_block()
+{
+    const unsigned long long my = block_gen;
+    if (++arrived_block == n_threads - n_done) {
+        arrived_block = 0;
+        block_gen++;
         n_collectives++;
     }
-    while (generation == my) yield();
-    // Lane 0 leaves a rendezvous only after every other live lane has reached the next one.  The device
-    // code has one pattern that depends on the warp being converged between two barriers: all lanes
-    // read a value, then lane 0 (the serial sections are `if (tid == 0)`) updates it.  Running lane 0
-    // strictly last in every segment reproduces "reads first, then the write".
-    if (cur == 0)
-        while (arrived < LANES - n_done - 1) yield();
+    while (block_gen == my) yield();
+    thread0_last();
+}
+// warp collectives: rendezvous of the 32 lanes of the calling thread's warp
+inline void barrier_warp()
+{
+    const int w = cur >> 5;
+    const unsigned long long my = warp_gen[w];
+    if (++arrived_warp[w] == 32 - n_done_warp[w]) {
+        arrived_warp[w] = 0;
+        warp_gen[w]++;
+        n_collectives++;
+    }
+    while (warp_gen[w] == my) yield();
+    thread0_last();
 }
 template <typename T>
 inline void publish(const T& v)
 {
     static_assert(sizeof(T) <= 16, "collective operand too large");
-    std::memcpy(xchg[generation & 1][cur], &v, sizeof(T));
+    std::memcpy(xchg[warp_gen[cur >> 5] & 1][cur], &v, sizeof(T));
 }
 template <typename T>
-inline T peek(unsigned long long gen, int lane)
+inline T peek(unsigned long long gen, int lane)   // lane of the calling thread's warp
 {
     T v;
-    std::memcpy(&v, xchg[gen & 1][lane], sizeof(T));
+    std::memcpy(&v, xchg[gen & 1][(cur & ~31) + lane], sizeof(T));
     return v;
 }
-void run_block(unsigned block, const std::function<void()>& body);
+inline bool lane_done(int lane) { return fibers[(cur & ~31) + lane].done; }
+inline unsigned long long wgen() { return warp_gen[cur >> 5]; }
+void run_block(unsigned block, int threads, const std::function<void()>& body);
 }  // namespace emu
 
 #define threadIdx (emu::Idx{(unsigned)emu::cur, 0u, 0u})
 #define blockIdx (emu::Idx{emu::block_id, 0u, 0u})
-#define blockDim (emu::Idx{32u, 1u, 1u})
+#define blockDim (emu::Idx{(unsigned)emu::n_threads, 1u, 1u})
 #define gridDim (emu::Idx{1u, 1u, 1u})
 
-inline void __syncthreads() { emu::barrier(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
+inline void __syncthreads() { emu::barrier_block(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_warp(); }
 inline void __threadfence() {}
 inline long long clock64() { return 0; }
 
 template <typename T>
 inline T emu_xchg(T v, const std::function<int(int)>& src)
 {
-    const unsigned long long gen = emu::generation;
+    const unsigned long long gen = emu::wgen();
     emu::publish(v);
-    emu::barrier();
-    const int s = src(emu::cur);
-    return (s >= 0 && s < emu::LANES) ? emu::peek<T>(gen, s) : v;
+    emu::barrier_warp();
+    const int s = src(emu::cur & 31);
+    return (s >= 0 && s < 32) ? emu::peek<T>(gen, s) : v;
 }
 template <typename T> inline T __shfl_sync(unsigned, T v, int lane, int = 32) { return emu_xchg<T>(v, [lane](int) { return lane & 31; }); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu_xchg<T>(v, [m](int l) { return l ^ m; }); }
@@ -99,22 +126,23 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int =
 template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) { return emu_xchg<T>(v, [d](int l) { return l - (int)d >= 0 ? l - (int)d : l; }); }
 inline unsigned __ballot_sync(unsigned, int pred)
 {
-    const unsigned long long gen = emu::generation;
+    const unsigned long long gen = emu::wgen();
     emu::publish<int>(pred != 0);
-    emu::barrier();
+    emu::barrier_warp();
     unsigned m = 0;
-    for (int l = 0; l < emu::LANES; l++)
-        if (!emu::fibers[l].done && emu::peek<int>(gen, l)) m |= 1u << l;
+    for (int l = 0; l < 32; l++)
+        if (!emu::lane_done(l) && emu::peek<int>(gen, l)) m |= 1u << l;
     return m;
 }
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
 inline int __reduce_min_sync(unsigned, int v)
 {
-    const unsigned long long gen = emu::generation;
+    const unsigned long long gen = emu::wgen();
     emu::publish<int>(v);
-    emu::barrier();
+    emu::barrier_warp();
     int r = v;
-    for (int l = 0; l < emu::LANES; l++) r = std::min(r, emu::peek<int>(gen, l));
+    for (int l = 0; l < 32; l++)
+        if (!emu::lane_done(l)) r = std::min(r, emu::peek<int>(gen, l));
     return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

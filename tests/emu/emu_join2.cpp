@@ -8,6 +8,7 @@
 // input (little endian): i32 n_gaps, i32 gaps[10], f64 q, i32 n_ghm; per GHM: u32 cnt0, cnt1, u64 area,
 // i32 level, u32 keys[cnt0 + cnt1] ((x << 16) | y, orientation 0 block first, each in (x, y) order)
 #define IADH_HOST_EMU 1
+#define EMU_NT 32
 #include "cuda_emu.h"
 
 #include "../../i-adhore_b200/csrc/cluster_kernel.cu"
@@ -72,9 +73,9 @@ static bool run_variant(const GhmIn& in, const DevParams& prm, int pool_factor, 
         for (int pass = 0; pass < 3; pass++) {
             int next_item = 0;
             if (pass == 2 && join2)
-                emu::run_block(0, [&]() { phase1_join2_kernel<32>(&task, items.data(), (int)items.size(), &next_item, ws.data(), prm, pool_factor, gi, dbg); });
+                emu::run_block(0, EMU_NT, [&]() { phase1_join2_kernel<32>(&task, items.data(), (int)items.size(), &next_item, ws.data(), prm, pool_factor, gi, dbg); });
             else
-                emu::run_block(0, [&]() { phase1_pass_kernel<32, 32>(&task, items.data(), (int)items.size(), &next_item, in.keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg); });
+                emu::run_block(0, EMU_NT, [&]() { phase1_pass_kernel<32, 32>(&task, items.data(), (int)items.size(), &next_item, in.keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg); });
             if (getenv("EMU_TRACE")) {
                 const ClusterRec* cl = (const ClusterRec*)(ws.data() + L.cl);
                 for (int o = 0; o < 2; o++) {

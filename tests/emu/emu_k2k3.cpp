@@ -10,6 +10,12 @@
 //                       u32 keys[cnt0+cnt1]; i32 n_expected; u8 expected[n_expected]
 //   (expected = the reference's packed blob of the GHM: i32 multiplicon count, then the multiplicons)
 #define IADH_HOST_EMU 1
+#ifndef EMU_NT
+#define EMU_NT 32        // block size of the emulated clustering kernel: 32, 64, 128 or 256
+#endif
+#if EMU_NT == 32
+#define IADH_EMU_PT 32   // (and a one-warp writer; the larger builds keep the writer's own 128 threads)
+#endif
 #include "cuda_emu.h"
 
 #include "../../i-adhore_b200/csrc/cluster_kernel.cu"
@@ -95,7 +101,7 @@ int main(int argc, char** argv)
                 const int item = 0 * 4 + task.half_mask;
                 int next = 0;
                 std::vector<int> sm_slot(1024, 0);
-                emu::run_block(0, [&]() { cluster_kernel<32>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
+                emu::run_block(0, EMU_NT, [&]() { cluster_kernel<EMU_NT>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
                 if (task.status != 0) continue;   // anchor-point pool exhausted: retry with a larger pool, like the engine
                 int32_t nm = task.n_mult;
                 memcpy(got.data(), &nm, 4);
@@ -103,8 +109,8 @@ int main(int argc, char** argv)
                     got.resize(4 + (size_t)task.out_bytes);
                     const int sel = 0;
                     const int64_t off = 0;
-                    if (hl) emu::run_block(0, [&]() { pack_write_kernel<true>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
-                    else emu::run_block(0, [&]() { pack_write_kernel<false>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
+                    if (hl) emu::run_block(0, PT, [&]() { pack_write_kernel<true>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
+                    else emu::run_block(0, PT, [&]() { pack_write_kernel<false>(&task, &sel, &off, 1, ws.data(), ds, pf, pool_factor, got.data() + 4); });
                 }
                 break;
             }

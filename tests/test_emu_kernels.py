@@ -1,7 +1,8 @@
 """The kernels of cluster_kernel.cu and pack_kernel.cu compiled for the host and run under a one-warp emulation
-(tests/emu/: 32 lanes as fibers, every warp collective and barrier a rendezvous), in a container without a GPU.
+(tests/emu/: the threads of a block as fibers, every warp collective and barrier a rendezvous), in a container without a GPU.
 
-0. End to end: the fused clustering kernel (phase 1, phase 2, K3 measuring pass; the 32-thread instantiation) and
+0. End to end: the fused clustering kernel (phase 1, phase 2, K3 measuring pass; 32-, 64-, 128- and 256-thread
+   instantiations, i.e. also the cooperative merge / insert / statistics paths and the cross-warp reductions) and
    the K3 writer, emulated GHM by GHM on the dot sets of the reference traces, produce the reference's packed
    multiplicons byte for byte -- level-2 and profile GHMs, all three multiple-hypothesis modes, p-values included.
 
@@ -24,7 +25,7 @@ from trace_io import read_trace
 
 EMU_DIR = os.path.join(pl.HERE, "emu")
 EMU = os.path.join(pl.REPO, "build", "emu", "emu_join2")
-EMU_K2K3 = os.path.join(pl.REPO, "build", "emu", "emu_k2k3")
+EMU_K2K3 = os.path.join(pl.REPO, "build", "emu", "emu_k2k3_%d")
 STUDY_LIB = os.path.join(pl.REPO, "oracle", "study", "liboracle_study.so")
 CUDA_INC = "/usr/local/cuda/include/cuda_runtime.h"
 
@@ -84,12 +85,14 @@ def test_two_phase_join_kernel_equals_default_join_on_heavy_ghms(emu, tmp_path):
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
-@pytest.mark.parametrize("name", ["tiny_bf", "tiny_fdr", "tiny_none", "tiny_4g", "tiny_pairs"])
-def test_emulated_device_code_reproduces_the_reference_bytes(emu, tmp_path, name):
+# block sizes of the fused kernel: 32 (single warp), 64 and 256 (the engine's default size classes), 128
+@pytest.mark.parametrize("name,nt", [("tiny_bf", 32), ("tiny_fdr", 32), ("tiny_none", 32), ("tiny_4g", 32), ("tiny_pairs", 32),
+                                     ("tiny_bf", 256), ("tiny_fdr", 64), ("tiny_none", 128), ("tiny_pairs", 256)])
+def test_emulated_device_code_reproduces_the_reference_bytes(emu, tmp_path, name, nt):
     trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
     inp = str(tmp_path / "in.bin")
     # (profile GHMs of a pairs trace need the partner buckets of iadh_create_pairs: level 2 only there)
     n = emu.write_k2k3_input(trace, inp, max_hl=0 if "pairs" in name else None)
-    res, err = _run(inp, exe=EMU_K2K3)
+    res, err = _run(inp, exe=EMU_K2K3 % nt)
     assert res["ghms"] == n and res["multiplicons"] > 30 and res["bytes"] > 15000
     assert res["mismatching_ghms"] == 0, err[-800:]
