@@ -96,3 +96,14 @@ def test_emulated_device_code_reproduces_the_reference_bytes(emu, tmp_path, name
     res, err = _run(inp, exe=EMU_K2K3 % nt)
     assert res["ghms"] == n and res["multiplicons"] > 30 and res["bytes"] > 15000
     assert res["mismatching_ghms"] == 0, err[-800:]
+
+
+@pytest.mark.parametrize("nt", [32, 256])
+def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_path, nt):
+    """GHMs with 100+ clusters (config-3-shaped list pairs): long cooperative merges, pool compaction, dozens of
+    multiplicons per GHM.  No reference trace at this size in the repo; the expected bytes are the oracle's."""
+    inp = str(tmp_path / "in.bin")
+    assert emu.write_k2k3_synth_input(inp, 4) == 4
+    res, err = _run(inp, exe=EMU_K2K3 % nt)
+    assert res["multiplicons"] > 20 and res["bytes"] > 50000
+    assert res["mismatching_ghms"] == 0, err[-800:]
