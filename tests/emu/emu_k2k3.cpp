@@ -101,6 +101,32 @@ int main(int argc, char** argv)
                 const int item = 0 * 4 + task.half_mask;
                 int next = 0;
                 std::vector<int> sm_slot(1024, 0);
+#if EMU_NT == 32
+                // EMU_PASS=1: the pass-per-launch path instead of the fused kernel (one launch per pass and gap
+                // size over the (GHM, orientation) items, then the four phase-2 stages); EMU_PASS=2: the same
+                // with the experimental two-phase join kernel (IADH_JOIN2)
+                const char* pm = getenv("EMU_PASS");
+                if (pm && atoi(pm) > 0) {
+                    const bool join2 = atoi(pm) == 2;
+                    std::vector<int> items1;
+                    for (int o = 0; o < 2; o++)
+                        if (cnt[o] >= 3) items1.push_back(o);
+                    unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int gi = 0; gi < prm.n_gaps && !items1.empty(); gi++)
+                        for (int pass = 0; pass < 3; pass++) {
+                            next = 0;
+                            if (pass == 2 && join2)
+                                emu::run_block(0, 32, [&]() { phase1_join2_kernel<32>(&task, items1.data(), (int)items1.size(), &next, ws.data(), prm, pool_factor, gi, dbg); });
+                            else
+                                emu::run_block(0, 32, [&]() { phase1_pass_kernel<32, 32>(&task, items1.data(), (int)items1.size(), &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg); });
+                        }
+                    const int item2 = 0;
+                    for (int stage = 0; stage < 4; stage++) {
+                        next = 0;
+                        emu::run_block(0, 32, [&]() { phase2_stage_kernel<32, 32>(&task, &item2, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0, stage); });
+                    }
+                } else
+#endif
                 emu::run_block(0, EMU_NT, [&]() { cluster_kernel<EMU_NT>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
                 if (task.status != 0) continue;   // anchor-point pool exhausted: retry with a larger pool, like the engine
                 int32_t nm = task.n_mult;

@@ -107,3 +107,15 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     res, err = _run(inp, exe=EMU_K2K3 % nt)
     assert res["multiplicons"] > 20 and res["bytes"] > 50000
     assert res["mismatching_ghms"] == 0, err[-800:]
+
+
+@pytest.mark.parametrize("mode,name", [("1", "tiny_bf"), ("1", "tiny_none"), ("2", "tiny_fdr"), ("2", "tiny_4g")])
+def test_emulated_pass_per_launch_path_reproduces_the_reference_bytes(emu, tmp_path, mode, name):
+    """The path of large batches: one launch per pass and gap size (phase1_pass_kernel), the four phase-2 stages
+    (phase2_stage_kernel), the writer.  mode 1 = default join, 2 = the experimental two-phase join kernel."""
+    trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
+    inp = str(tmp_path / "in.bin")
+    n = emu.write_k2k3_input(trace, inp)
+    res, err = _run(inp, env={"EMU_PASS": mode}, exe=EMU_K2K3 % 32)
+    assert res["ghms"] == n and res["multiplicons"] > 50
+    assert res["mismatching_ghms"] == 0, err[-800:]
