@@ -783,6 +783,17 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 const int n_chunks = (int)chunk_k.size() - 1;
                 CU(c->d_passctr.ensure(4 * 36 * (size_t)n_chunks + 80));
                 CU(cudaMemsetAsync(c->d_passctr.p, 0, 4 * 36 * (size_t)n_chunks + 80, c->st));
+                // IADH_PASS_TIMING=1 (measurement aid): device time of every pass / stage launch
+                static const bool pass_timing = getenv("IADH_PASS_TIMING") != nullptr;
+                std::vector<cudaEvent_t> pev;
+                auto pmark = [&]() {
+                    if (!pass_timing) return;
+                    cudaEvent_t e;
+                    cudaEventCreate(&e);
+                    cudaEventRecord(e, c->st);
+                    pev.push_back(e);
+                };
+                pmark();
                 for (int ch = 0; ch < n_chunks; ch++) {
                     int* pc = c->d_passctr.as<int>() + 36 * ch;
                     const int* it1 = c->d_items1.as<int>() + chunk_i1[ch];
@@ -794,6 +805,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                                                c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi, grid, c->pass_nt, c->st,
                                                g_trace ? (unsigned long long*)(c->d_passctr.as<int>() + 36 * n_chunks) : nullptr);
                             st.kernel_launches += 1;
+                            pmark();
                         }
                     const int* it2 = ord + chunk_k[ch];
                     const int n2 = chunk_k[ch + 1] - chunk_k[ch];
@@ -803,7 +815,19 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                                             c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2,
                                             c->pass_nt, c->st);
                         st.kernel_launches += 1;
+                        pmark();
                     }
+                }
+                if (pass_timing && !pev.empty()) {
+                    cudaEventSynchronize(pev.back());
+                    fprintf(stderr, "[iadh] pass timing (ms), %d items / %d GHMs:", (int)items1.size(), n_act);
+                    for (size_t k = 1; k < pev.size(); k++) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, pev[k - 1], pev[k]);
+                        fprintf(stderr, "%s%.2f", ((k - 1) % 3 == 0) ? " | " : " ", ms);
+                    }
+                    fprintf(stderr, "\n");
+                    for (cudaEvent_t e : pev) cudaEventDestroy(e);
                 }
                 trace_mark(c->st, "K2 pass-per-launch (all chunks)");
                 if (g_trace) {
