@@ -77,6 +77,19 @@ struct Ghm {
     uint32_t* tmp;
     uint8_t* tmpf;  // staging flags, parallel to tmp
     int scratch_cap;  // entries of tmp / doubles of dscr usable as whole-GHM scratch (phase 2)
+    // capacities of the view (the global workspace is sized by worst-case bounds, the shared-memory
+    // resident view by budgets: exceeding one sets `status`, the host re-runs the GHM on the global path)
+    int key_cap[2];   // entries of key[o] / alive[o]
+    int tmp_cap;      // entries of tmp / tmpf
+    int dscr_cap;     // anchor points per chunk of the ordered statistics sums (2 doubles each)
+    int tight;        // resident view: tight anchor-point block capacities, cluster slots recycled after merges
+    int free_head[2]; // recycled cluster slots per orientation (linked through ClusterRec::mnext), -1 = none
+    // seeding state per orientation (seed_pass): the successor pointers are gap-independent and persist
+    // across the gap sizes; g3 = smallest gap size at which some 3-dot chain exists (exact while no dot
+    // of the matrix was erased since it was computed: `dirty`), so seed passes below it are skipped
+    int nxt_off[2];   // start of orientation o's successor pointers inside nxt
+    int seeded[2], dirty[2], g3[2];
+    long long* ctr;   // measurement aid (resident kernel under IADH_PASS_TIMING): event counters, may be null
     int status;
     int coop[4];
     // task constants
@@ -156,12 +169,24 @@ static __device__ void block_min_pair(double& d, long long& k, Red* sh)
 // to the capacity class of their current size.  Live data is at most ~4.7 D entries, so with
 // pool_factor >= 8 an allocation can only fail after a collection if the host under-sized the
 // pool on purpose (then the GHM reports status 1 and the engine reruns it with a larger pool).
+static __device__ __forceinline__ int next_cap(int n)
+{
+    int c = 8;
+    while (c < n) c <<= 1;
+    return c;
+}
+// block capacity policies: the global pool (8 D entries) rounds to powers of two; the resident pool (2 D
+// entries in shared memory) allocates what is needed and grows by half
+static __device__ __forceinline__ int cap_for(const Ghm& g, int n) { return g.tight ? ((n + 3) & ~3) : next_cap(n); }
+static __device__ __forceinline__ int cap_grow(const Ghm& g, int cap) { return g.tight ? cap + max(4, (cap >> 1) & ~3) : cap * 2; }
+static __device__ __forceinline__ int cap_seed(const Ghm& g, int len) { return g.tight ? ((len + 2 + 3) & ~3) : next_cap(len + (len >> 1)); }
+
 static __device__ __forceinline__ bool valid_id(const Ghm& g, int id)
 {
     return (id >= g.cl_lo[0] && id < g.ncl[0]) || (id >= g.cl_lo[1] && id < g.ncl[1]);
 }
 
-static __device__ void pool_gc(Ghm& g, int rg)
+static __device__ void pool_gc_body(Ghm& g, int rg)
 {
     int r = g.pool_lo[rg], w = r;
     while (r < g.pool_used[rg]) {
@@ -170,8 +195,7 @@ static __device__ void pool_gc(Ghm& g, int rg)
         const int payload = r + 2;
         ClusterRec& c = g.cl[owner];
         if (valid_id(g, owner) && !c.dead && c.off == payload) {
-            int ncap = 8;
-            while (ncap < c.n) ncap <<= 1;
+            int ncap = cap_for(g, c.n);
             if (ncap > cap) ncap = cap;
             if (w != r)
                 for (int i = 0; i < c.n; i++) {
@@ -187,6 +211,17 @@ static __device__ void pool_gc(Ghm& g, int rg)
         r += 2 + cap;
     }
     g.pool_used[rg] = w;
+}
+
+#define CTR_ADD(k, v) do { if (g.ctr) g.ctr[k] += (v); } while (0)
+static __device__ void pool_gc(Ghm& g, int rg)
+{
+    const long long t0_ = g.ctr ? clock64() : 0;
+    pool_gc_body(g, rg);
+    if (g.ctr) {
+        g.ctr[8]++;
+        g.ctr[9] += clock64() - t0_;
+    }
 }
 
 // single-thread contexts only (the rest of the CTA waits at a barrier).  `rg` = preferred region
@@ -210,18 +245,12 @@ static __device__ int pool_alloc(Ghm& g, int n, int owner, int rg)
     return -1;
 }
 
-static __device__ __forceinline__ int next_cap(int n)
-{
-    int c = 8;
-    while (c < n) c <<= 1;
-    return c;
-}
 
 // multiset<AnchorPoint>::insert (BaseCluster.cpp:58-61): after the last AP with x <= X
 static __device__ bool insert_ap(Ghm& g, ClusterRec& c, uint32_t key)
 {
     if (c.n == c.cap) {
-        const int ncap = c.cap * 2;
+        const int ncap = cap_grow(g, c.cap);
         const int noff = pool_alloc(g, ncap, (int)(&c - g.cl), c.orient);
         if (noff < 0) return false;
         for (int i = 0; i < c.n; i++) {
@@ -257,7 +286,7 @@ static __device__ bool merge_clusters(Ghm& g, ClusterRec& A, const ClusterRec& B
 {
     const int n = A.n + B.n;
     if (n > A.cap) {
-        const int ncap = next_cap(n);
+        const int ncap = cap_for(g, n);
         const int noff = pool_alloc(g, ncap, (int)(&A - g.cl), A.orient);
         if (noff < 0) return false;
         for (int i = 0; i < A.n; i++) {
@@ -311,40 +340,50 @@ static __device__ void stats_coop_il(Ghm& g, ClusterRec& c)
         __syncthreads();
         return;
     }
-    if (tid == 0) cm::regress(c);
-    __syncthreads();
-    {
-        const double a = c.a, b = c.b, avg_x = c.avg_x;
-        const uint32_t* ap = g.pool + c.off;
-        for (int i = tid; i < n; i += NT) {
-            const uint32_t k = ap[i];
-            const int x = KEY_X(k), y = KEY_Y(k);
-            const double y_est = b * x + a;
-            g.dscr[2 * i] = (y - y_est) * (y - y_est);
-            g.dscr[2 * i + 1] = (x - avg_x) * (x - avg_x);
-        }
+    if (tid == 0) {
+        cm::regress(c);
+        CTR_ADD(14, n);
     }
     __syncthreads();
-    if (tid == 0) {
-        double mrss = 0.0, var_x = 0.0;
-        const double2* t = reinterpret_cast<const double2*>(g.dscr);
-        int i = 0;
-        for (; i + 8 <= n; i += 8) {
-            double2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = t[i + u];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                mrss += v[u].x;
-                var_x += v[u].y;
+    // the per-AP terms are staged chunk by chunk (the global view holds the whole cluster in one chunk, the
+    // resident view dscr_cap anchor points); thread 0 carries the two running sums across chunks
+    double mrss = 0.0, var_x = 0.0;
+    const int chunk = g.dscr_cap;
+    for (int base = 0; base < n; base += chunk) {
+        const int m = min(chunk, n - base);
+        {
+            const double a = c.a, b = c.b, avg_x = c.avg_x;
+            const uint32_t* ap = g.pool + c.off + base;
+            for (int i = tid; i < m; i += NT) {
+                const uint32_t k = ap[i];
+                const int x = KEY_X(k), y = KEY_Y(k);
+                const double y_est = b * x + a;
+                g.dscr[2 * i] = (y - y_est) * (y - y_est);
+                g.dscr[2 * i + 1] = (x - avg_x) * (x - avg_x);
             }
         }
-        for (; i < n; i++) {
-            mrss += t[i].x;
-            var_x += t[i].y;
+        __syncthreads();
+        if (tid == 0) {
+            const double2* t = reinterpret_cast<const double2*>(g.dscr);
+            int i = 0;
+            for (; i + 8 <= m; i += 8) {
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = t[i + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    mrss += v[u].x;
+                    var_x += v[u].y;
+                }
+            }
+            for (; i < m; i++) {
+                mrss += t[i].x;
+                var_x += t[i].y;
+            }
         }
-        cm::finish_stats(c, mrss, var_x, g.pool);
+        if (base + chunk < n) __syncthreads();   // the staging area is reused by the next chunk
     }
+    if (tid == 0) cm::finish_stats(c, mrss, var_x, g.pool);
     __syncthreads();
 }
 static __device__ __noinline__ void stats_coop_ni(Ghm& g, ClusterRec& c) { stats_coop_il(g, c); }
@@ -389,6 +428,12 @@ static __device__ bool merge_coop(Ghm& g, int idA, int idB)
         __syncthreads();
         return g.status == 0;
     }
+    if (n > g.tmp_cap) {   // (resident view only: the staging area is a budget)
+        __syncthreads();
+        if (tid == 0) g.status = 3;
+        __syncthreads();
+        return false;
+    }
     uint32_t* skey = g.tmp;
     uint8_t* sflag = g.tmpf;
     {
@@ -419,7 +464,7 @@ static __device__ bool merge_coop(Ghm& g, int idA, int idB)
     if (tid == 0) {
         bool ok = true;
         if (n > A.cap) {
-            const int ncap = next_cap(n);
+            const int ncap = cap_for(g, n);
             const int noff = pool_alloc(g, ncap, idA, A.orient);  // may compact the pool: A/B blocks can move
             if (noff >= 0) {
                 A.off = noff;
@@ -453,8 +498,10 @@ static __device__ bool insert_coop(Ghm& g, ClusterRec& c, uint32_t key)
         __syncthreads();
         return g.status == 0;
     }
+    if (tid == 0) CTR_ADD(12, 1);
     if (tid == 0 && n == c.cap) {
-        const int ncap = c.cap * 2;
+        CTR_ADD(10, n);
+        const int ncap = cap_grow(g, c.cap);
         const int noff = pool_alloc(g, ncap, (int)(&c - g.cl), c.orient);
         if (noff >= 0) {
             for (int i = 0; i < n; i++) {
@@ -546,30 +593,58 @@ static __device__ int window_next(const uint32_t* key, const uint8_t* alive, int
     return bj;
 }
 
-// GHM::seedBaseClusters (GHM.cpp:287-324)
-static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, int* sh_s)
+// GHM::seedBaseClusters (GHM.cpp:287-324).
+// The successor of a dot at gap size g -- the first dot of minimal dpd in its g x g window, if that
+// dpd <= g (GHM.cpp:248-276) -- does not depend on g: dpd >= max(dx, dy), so every dot with dpd <= g lies
+// inside the g-window, and the minimal-dpd dots of the largest window (ties included, same order) are the
+// minimal-dpd dots of every smaller window that holds one.  nxt[] therefore keeps the successor for the
+// largest gap size `gmax` for the whole gap-size loop; a pass at gap g follows a pointer only if its dpd
+// is <= g.  Pointers into dots erased since (by an accepted seed: repaired at once; by the enrichment:
+// checked at the start of the next pass) are recomputed.  g3 = the smallest g for which some alive dot has
+// two links <= g in a row; a pass with gap < g3 cannot build a 3-dot chain and is skipped by the callers
+// (exact as long as no dot was erased after g3 was computed: erasures can shorten a chain's links).
+static __device__ __forceinline__ int succ_at(const uint32_t* key, const int* nxt, int i, int gap)
+{
+    const int j = nxt[i];
+    if (j < 0) return -1;
+    const uint32_t a = key[i], b = key[j];
+    return cm::dpd_i(KEY_X(a), KEY_Y(a), KEY_X(b), KEY_Y(b)) <= gap ? j : -1;
+}
+
+static __device__ void seed_pass(Ghm& g, int gap, int gmax, int o, double q, int* sh_i, int* sh_s)
 {
     const int tid = VTID;
     const uint32_t* key = g.key[o];
     uint8_t* alive = g.alive[o];
     const int n = g.nk[o];
-    int* nxt = g.nxt;
-    for (int i = tid; i < n; i += NT) nxt[i] = alive[i] ? window_next(key, alive, n, i, gap, o) : -1;
+    int* nxt = g.nxt + g.nxt_off[o];
+    if (!g.seeded[o]) {
+        for (int i = tid; i < n; i += NT) nxt[i] = alive[i] ? window_next(key, alive, n, i, gmax, o) : -1;
+    } else {
+        for (int i = tid; i < n; i += NT)
+            if (alive[i]) {
+                const int j = nxt[i];
+                if (j >= 0 && !alive[j]) nxt[i] = window_next(key, alive, n, i, gmax, o);
+            }
+    }
     __syncthreads();
     int base = 0;
     while (base < n) {
         const int i = base + tid;
         bool acc = false;
-        if (i < n && alive[i] && nxt[i] >= 0 && nxt[nxt[i]] >= 0) {
-            long long sx = 0, sy = 0, sxy = 0, sxx = 0, syy = 0;
-            unsigned len = 0;
-            for (int j = i; j >= 0; j = nxt[j]) {
-                const uint32_t k = key[j];
-                const long long x = KEY_X(k), y = KEY_Y(k);
-                sx += x; sy += y; sxy += x * y; sxx += x * x; syy += y * y;
-                len++;
+        if (i < n && alive[i]) {
+            const int j1 = succ_at(key, nxt, i, gap);
+            if (j1 >= 0 && succ_at(key, nxt, j1, gap) >= 0) {
+                long long sx = 0, sy = 0, sxy = 0, sxx = 0, syy = 0;
+                unsigned len = 0;
+                for (int j = i; j >= 0; j = succ_at(key, nxt, j, gap)) {
+                    const uint32_t k = key[j];
+                    const long long x = KEY_X(k), y = KEY_Y(k);
+                    sx += x; sy += y; sxy += x * y; sxx += x * x; syy += y * y;
+                    len++;
+                }
+                acc = cm::r2_sums(sx, sy, sxy, sxx, syy, len) >= q;  // len > 2 by construction
             }
-            acc = cm::r2_sums(sx, sy, sxy, sxx, syy, len) >= q;  // len > 2 by construction
         }
         const int first = block_min_int(acc ? tid : 0x7fffffff, sh_i);
         if (first == 0x7fffffff) {
@@ -579,27 +654,34 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
         if (tid == first) {
             // commit: new base cluster from the chain (GHM.cpp:301-311)
             int len = 0;
-            for (int j = i; j >= 0; j = nxt[j]) len++;
-            const int cap = next_cap(len + (len >> 1));
-            const int nid = g.ncl[o];
+            for (int j = i; j >= 0; j = succ_at(key, nxt, j, gap)) len++;
+            const int cap = cap_seed(g, len);
+            // a slot freed by a merge (resident view) or the next fresh one
+            const bool reuse = g.free_head[o] >= 0;
+            const int nid = reuse ? g.free_head[o] : g.ncl[o];
             const int off = (nid < g.cl_hi[o]) ? pool_alloc(g, cap, nid, o) : -1;
             if (off >= 0) {
+                if (reuse) g.free_head[o] = g.cl[nid].mnext;
+                CTR_ADD(13, 1);
                 ClusterRec& c = g.cl[nid];
                 c.off = off; c.cap = cap; c.n = len;
                 c.mult = -1; c.mnext = -1; c.orient = (unsigned char)o; c.was_twisted = 0; c.dead = 0;
                 c.a = 0; c.b = 0; c.avg_x = 0; c.p = 0;
                 int w = 0, lastj = i;
-                for (int j = i; j >= 0; j = nxt[j]) {
+                for (int j = i; j >= 0;) {
+                    const int jn = succ_at(key, nxt, j, gap);   // (before the dot is erased: same pointer either way)
                     g.pool[off + w] = key[j];
                     g.pflag[off + w] = 1;
                     alive[j] = 0;
                     lastj = j;
                     w++;
+                    j = jn;
                 }
                 cm::recompute_sums(c, g.pool);
                 g.bc[o][g.nbc[o]++] = nid;
-                g.ncl[o] = nid + 1;
+                if (!reuse) g.ncl[o] = nid + 1;
                 sh_s[0] = lastj;
+                sh_s[6] = nid;
             } else {
                 if (!g.status) g.status = 2;  // cluster table full
                 sh_s[0] = -1;
@@ -607,18 +689,43 @@ static __device__ void seed_pass(Ghm& g, int gap, int o, double q, int* sh_i, in
         }
         __syncthreads();
         if (g.status) return;
-        stats_coop(g, g.cl[g.ncl[o] - 1]);
+        stats_coop(g, g.cl[sh_s[6]]);
         {
-            // repair successor pointers that point into the erased chain
+            // repair successor pointers that point into the erased chain (any dot within gmax columns before it)
             const int lastj = sh_s[0];
             const int cx = KEY_X(key[base + first]);
-            const int lo = lower_bound_key(key, 0, n, MAKE_KEY(max(cx - gap, 0), 0));
+            const int lo = lower_bound_key(key, 0, n, MAKE_KEY(max(cx - gmax, 0), 0));
             for (int j = lo + tid; j < lastj; j += NT)
-                if (alive[j] && nxt[j] >= 0 && !alive[nxt[j]]) nxt[j] = window_next(key, alive, n, j, gap, o);
+                if (alive[j] && nxt[j] >= 0 && !alive[nxt[j]]) nxt[j] = window_next(key, alive, n, j, gmax, o);
         }
         base = base + first + 1;
         __syncthreads();
     }
+    // smallest gap size with a 3-dot chain among the dots left (every pointer of an alive dot is current here)
+    int m = 0x7fffffff;
+    for (int i = tid; i < n; i += NT)
+        if (alive[i]) {
+            const int j = nxt[i];
+            if (j >= 0) {
+                const int k = nxt[j];
+                if (k >= 0) {
+                    const uint32_t a = key[i], b = key[j], c = key[k];
+                    m = min(m, max(cm::dpd_i(KEY_X(a), KEY_Y(a), KEY_X(b), KEY_Y(b)), cm::dpd_i(KEY_X(b), KEY_Y(b), KEY_X(c), KEY_Y(c))));
+                }
+            }
+        }
+    m = block_min_int(m, sh_i);
+    if (tid == 0) {
+        g.g3[o] = m;
+        g.seeded[o] = 1;
+        g.dirty[o] = 0;
+    }
+    __syncthreads();
+}
+// a seed pass at this gap size can be skipped: no 3-dot chain exists below g3 (see seed_pass)
+static __device__ __forceinline__ bool seed_skippable(const Ghm& g, int gap, int o)
+{
+    return g.seeded[o] && !g.dirty[o] && gap < g.g3[o];
 }
 
 // ---- enrich -------------------------------------------------------------------------------
@@ -732,6 +839,7 @@ static __device__ void enrich_pass(Ghm& g, int gap, int oc, int om, double q, in
                             act_next[sh_s[1]++] = act[kc];
                         }
                         alive[di] = 0;
+                        g.dirty[om] = 1;   // (seed_pass: the 3-dot-chain bound of this matrix is no longer exact)
                         const ClusterRec& c = g.cl[act[kc]];
                         g.xr[kc] = make_int2((int)c.x_end1 - gap, (int)c.x_end2 + gap);
                     }
@@ -932,6 +1040,10 @@ static __device__ void join_pass(Ghm& g, int gap, int o, double q, Red* red, int
         JP(3);
         if (tid == 0) {
             g.cl[idB].dead = 1;
+            if (g.tight) {   // the slot can hold a later seed of this orientation
+                g.cl[idB].mnext = g.free_head[o];
+                g.free_head[o] = idB;
+            }
             sh_s[2] = 0;  // rows to recompute
         }
         __syncthreads();
@@ -1156,6 +1268,10 @@ static __device__ void join_pass2(Ghm& g, int gap, int o, double q, Red* red, in
         if (!merge_coop(g, idA, idB)) return;
         if (tid == 0) {
             g.cl[idB].dead = 1;
+            if (g.tight) {   // the slot can hold a later seed of this orientation
+                g.cl[idB].mnext = g.free_head[o];
+                g.free_head[o] = idB;
+            }
             sh_s[2] = 0;  // rows to recompute
         }
         __syncthreads();
@@ -1411,6 +1527,100 @@ static __device__ void block_bitonic(uint32_t* a, int m)
         }
 }
 
+// the same network with every comparator ascending (first step of a merge block: partner i ^ (k - 1)) sorts
+// any m: elements at virtual positions >= m are +inf and never move, so their comparators are skipped
+static __device__ void block_sort_any(uint32_t* a, int m)
+{
+    for (int k = 2; (k >> 1) < m; k <<= 1) {
+        for (int i = VTID; i < m; i += NT) {
+            const int l = i ^ (k - 1);
+            if (l > i && l < m) {
+                const uint32_t x = a[i], y = a[l];
+                if (x > y) {
+                    a[i] = y;
+                    a[l] = x;
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = VTID; i < m; i += NT) {
+                const int l = i ^ j;
+                if (l > i && l < m) {
+                    const uint32_t x = a[i], y = a[l];
+                    if (x > y) {
+                        a[i] = y;
+                        a[l] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// BaseCluster::calculateProbability by one warp without scratch arrays (resident view): 32 anchor points at
+// a time; a backbone point's predecessor is the nearest flagged lane below it (or the last backbone point of
+// the previous chunk), the factors are multiplied by lane 0 in backbone order -- the reference's running product.
+static __device__ void calc_probability_regs(Ghm& g, ClusterRec& c)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = VTID & 31;
+    const double density = (double)g.cnt[c.orient] / g.area;
+    const uint32_t* ap = g.pool + c.off;
+    const uint8_t* fl = g.pflag + c.off;
+    double probability = 1.0;
+    uint32_t prev = 0;
+    bool have = false;
+    for (int i0 = 0; i0 < c.n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = (i < c.n) && fl[i];
+        const uint32_t k = f ? ap[i] : 0u;
+        const unsigned bal = __ballot_sync(full, f);
+        if (bal == 0) continue;
+        const unsigned below = bal & ((1u << lane) - 1u);
+        const int src = below ? 31 - __clz(below) : -1;
+        const uint32_t pk = __shfl_sync(full, k, src < 0 ? 0 : src);
+        const uint32_t a = src >= 0 ? pk : prev;
+        double fac = 1.0;
+        if (f && (src >= 0 || have)) {
+            const double distance = cm::dpd_d(KEY_X(a), KEY_Y(a), KEY_X(k), KEY_Y(k));
+            const int cc = (int)ceil(0.5 * distance * distance);
+            fac = 1.0 - cm::pow_ref(1.0 - density, cc);
+        }
+        unsigned m = bal;
+        if (!have) m &= m - 1;   // the first backbone point of the cluster has no factor
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const double v = __shfl_sync(full, fac, b);
+            if (lane == 0) probability *= v;
+        }
+        prev = __shfl_sync(full, k, 31 - __clz(bal));
+        have = true;
+    }
+    if (lane == 0) {
+        c.p = probability;
+        // duplicates of the first AP are erased without touching the statistics
+        const uint32_t f = g.pool[c.off];
+        int w = 1;
+        for (int i = 1; i < c.n; i++) {
+            const uint32_t k = g.pool[c.off + i];
+            if (k == f) continue;
+            if (w != i) {
+                g.pool[c.off + w] = k;
+                g.pflag[c.off + w] = g.pflag[c.off + i];
+            }
+            w++;
+        }
+        if (w != c.n) {
+            c.n = w;
+            cm::recompute_sums(c, g.pool);
+        }
+    }
+    __syncwarp();
+}
+
 // BaseCluster::calculateProbability by one warp: the factors 1 - pow(1 - density, ceil(dpd^2 / 2)) of
 // consecutive backbone points are independent (each a ~400-cycle libm-exact pow), only their product
 // is ordered.  Lanes compute the factors into `fac`, lane 0 multiplies them in backbone order --
@@ -1483,6 +1693,9 @@ static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
             ClusterRec& c = g.cl[k < n0 ? g.bc[0][k] : g.bc[1][k - n0]];
             calc_probability_warp(g, c, g.tmp + g.redo[k], g.dscr + g.redo[k]);
         }
+    } else if (g.tight) {  // resident view: no scratch slices, one warp per cluster on registers
+        const int n0 = g.nbc[0], nall = g.nbc[0] + g.nbc[1];
+        for (int k = warp; k < nall; k += NW) calc_probability_regs(g, g.cl[k < n0 ? g.bc[0][k] : g.bc[1][k - n0]]);
     } else {  // (duplicated dots beyond the scratch capacity: one thread per cluster)
         for (int o = 0; o < 2; o++)
             for (int i = tid; i < g.nbc[o]; i += NT) calc_probability(g, g.cl[g.bc[o][i]]);
@@ -1517,9 +1730,25 @@ static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
             g.nbc[o] = w;
             sh_s[0] = removed;
             sh_s[1] = 0;
+            sh_s[6] = 0;
         }
         __syncthreads();
         if (sh_s[0] == 0) continue;
+        if (g.tight) {
+            // resident view: the staging area and the matrix are budgets -- count first (alive dots + the
+            // anchor points coming back), give up (status 3: host re-runs the GHM on the global path) if over
+            int cntl = 0;
+            for (int i = tid; i < g.nk[o]; i += NT) cntl += g.alive[o][i] ? 1 : 0;
+            for (int c = g.cl_lo[o] + tid; c < g.ncl[o]; c += NT)
+                if (g.cl[c].dead == 2) cntl += g.cl[c].n;
+            if (cntl) atomicAdd(&sh_s[6], cntl);
+            __syncthreads();
+            if (sh_s[6] > g.tmp_cap || sh_s[6] > g.key_cap[o]) {
+                if (tid == 0) g.status = 3;
+                __syncthreads();
+                return;
+            }
+        }
         // gather: alive dots of matrix[o] + APs of the removed clusters, then sort + unique
         {
             const uint32_t* key = g.key[o];
@@ -1537,11 +1766,16 @@ static __device__ void filter_pass(Ghm& g, const DevParams& prm, int* sh_s)
             for (int c = g.cl_lo[o] + tid; c < g.ncl[o]; c += NT)
                 if (g.cl[c].dead == 2) g.cl[c].dead = 1;
             const int m = sh_s[1];
-            int mp = 1;
-            while (mp < m) mp <<= 1;
-            for (int i = m + tid; i < mp; i += NT) g.tmp[i] = 0xffffffffu;
-            __syncthreads();
-            block_bitonic(g.tmp, mp);
+            if (g.tight) {
+                __syncthreads();
+                block_sort_any(g.tmp, m);
+            } else {
+                int mp = 1;
+                while (mp < m) mp <<= 1;
+                for (int i = m + tid; i < mp; i += NT) g.tmp[i] = 0xffffffffu;
+                __syncthreads();
+                block_bitonic(g.tmp, mp);
+            }
             // unique-compact back into key[o] (single pass by thread 0 is O(m); use a parallel
             // flag + scan-free approach: position = number of distinct predecessors)
             if (tid == 0) sh_s[1] = 0;
@@ -1786,6 +2020,22 @@ static __device__ void setup_view(Ghm& g, const GhmTask& task, uint8_t* ws, cons
     g.tmp = (uint32_t*)(base + L.tmp) + eo;
     g.tmpf = (uint8_t*)((uint32_t*)(base + L.tmp) + L.tmp_cap) + eo;
     g.scratch_cap = whole ? D : 0;
+    g.key_cap[0] = g.key_cap[1] = 0x7fffffff;   // (worst-case sized: never the limit)
+    g.tmp_cap = 0x7fffffff;
+    g.dscr_cap = D > 0 ? D : 1;
+    g.tight = 0;
+    g.ctr = nullptr;
+    g.free_head[0] = g.free_head[1] = -1;
+    // successor pointers: orientation 1 follows orientation 0 inside the GHM's array (a view of one
+    // orientation already starts at its own region)
+    g.nxt_off[0] = 0;
+    g.nxt_off[1] = whole ? D0 : 0;
+    for (int r = 0; r < 2; r++) {
+        const bool have = !fresh && ((half_mask >> r) & 1) && (whole || r == my_o);
+        g.seeded[r] = have ? (task.half_seed[r] & 1) : 0;
+        g.dirty[r] = have ? ((task.half_seed[r] >> 1) & 1) : 0;
+        g.g3[r] = have ? task.half_g3[r] : 0;
+    }
     g.status = fresh ? 0 : max(task.half_status[0], task.half_status[1]);
     for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
     g.nk[0] = D0;
@@ -1844,6 +2094,8 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
         const int half_mask = task.half_mask;
         const bool run_p1 = my_mask != 0;
         const double q = prm.q_value;
+        int gmax = 1;   // largest gap size of the schedule (seed_pass)
+        for (int k = 0; k < prm.n_gaps && k < 10; k++) gmax = max(gmax, prm.gaps[k]);
         if (tid < 8) { prof[tid] = 0; prof2[tid] = 0; }
         // view: phase 1 = this CTA's orientation only (its regions of every shared array),
         //       phase 2 = the whole GHM
@@ -1870,7 +2122,7 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
                 const int gap = prm.gaps[gi];
                 for (int o = 0; o < 2; o++) {
                     if (!((my_mask >> o) & 1)) continue;
-                    K::seed_pass(g, gap, o, q, sh_i, sh_s);
+                    if (!K::seed_skippable(g, gap, o)) K::seed_pass(g, gap, gmax, o, q, sh_i, sh_s);
                     __syncthreads();
                     PROF_END(0);
                     if (g.status) break;
@@ -1968,6 +2220,301 @@ __global__ void __launch_bounds__(NT) cluster_kernel(GhmTask* tasks, GhmProf* pr
     }
 }
 
+// ---- resident kernel: the whole clustering state of a GHM in shared memory -----------------------
+// One CTA per GHM from the staged dots to the packed sizes (both orientations one after the other, phase 2,
+// K3 measuring pass); the state never travels to HBM between passes.  What leaves the SM at the end is what
+// the K3 writer reads: the anchor points and records of the clusters that made it into a multiplicon, copied
+// to the same positions of the GHM's global workspace (WsLayout), so the writer is unchanged.  A GHM that
+// outgrows a budget of RsLayout reports status != 0 and is re-run on the global path by the host.
+#ifdef IADH_HOST_EMU
+static uint8_t* rs_smem = nullptr;   // tests/emu: the "dynamic shared memory" of the emulated block
+#else
+extern __shared__ __align__(16) uint8_t rs_smem[];
+#endif
+
+static __device__ void setup_view_resident(Ghm& g, const GhmTask& task, uint8_t* base, const RsLayout& L, const DevParams& prm)
+{
+    g.key[0] = (uint32_t*)(base + L.key0);
+    g.key[1] = (uint32_t*)(base + L.key1);
+    g.alive[0] = base + L.alive0;
+    g.alive[1] = base + L.alive1;
+    g.nxt = (int*)(base + L.nxt);
+    g.pool = (uint32_t*)(base + L.pool);
+    g.pflag = base + L.pflag;
+    g.cl = (ClusterRec*)(base + L.cl);
+    g.cl_lo[0] = 0; g.cl_hi[0] = L.cl_cap0;
+    g.cl_lo[1] = L.cl_cap0; g.cl_hi[1] = L.cl_cap0 + L.cl_cap1;
+    // one pool region (the orientations are clustered one after the other by this CTA)
+    g.pool_lo[0] = 0; g.pool_hi[0] = L.pool_cap; g.pool_used[0] = 0;
+    g.pool_lo[1] = g.pool_hi[1] = g.pool_used[1] = L.pool_cap;
+    for (int r = 0; r < 2; r++) {
+        g.nbc[r] = 0;
+        g.ncl[r] = g.cl_lo[r];
+        g.free_head[r] = -1;
+    }
+    g.bc[0] = (int*)(base + L.bc0);
+    g.bc[1] = (int*)(base + L.bc1);
+    g.act = (int*)(base + L.act);
+    g.act_next = (int*)(base + L.act_next);
+    g.changed = base + L.changed;
+    g.mult = (MultRec*)(base + L.mult);
+    g.nmult = 0;
+    g.out_mults = (int*)(base + L.out_mults);
+    g.rb_d = (double*)(base + L.rb_d);
+    g.rb_j = (int*)(base + L.rb_j);
+    g.rank = (int*)(base + L.rank);
+    g.pos = (int*)(base + L.pos);
+    g.xr = (int2*)(base + L.xr);
+    g.redo = (int*)(base + L.redo);
+    g.dscr = (double*)(base + L.dscr);
+    g.tmp = (uint32_t*)(base + L.tmp);
+    g.tmpf = base + L.tmpf;
+    g.nxt_off[0] = 0;
+    g.nxt_off[1] = L.cap0;
+    for (int r = 0; r < 2; r++) g.seeded[r] = g.dirty[r] = g.g3[r] = 0;
+    g.scratch_cap = 0;
+    g.key_cap[0] = L.cap0;
+    g.key_cap[1] = L.cap1;
+    g.tmp_cap = L.tmp_cap;
+    g.dscr_cap = L.dscr_cap;
+    g.tight = 1;
+    g.status = 0;
+    for (int k = 0; k < 4; k++) g.coop[k] = prm.coop[k];
+    g.nk[0] = (int)task.cnt[0];
+    g.nk[1] = (int)task.cnt[1];
+    g.cnt[0] = task.cnt[0];
+    g.cnt[1] = task.cnt[1];
+    g.area = (double)task.area;
+    g.level = task.level;
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) resident_kernel(GhmTask* tasks, const int* __restrict__ order, int n_tasks, int* next_task,
+                                                            const uint32_t* __restrict__ dots, uint8_t* ws, DevParams prm,
+                                                            int pool_factor, int smem_bytes, DatasetDev ds, ProfileDev pf, int hl,
+                                                            unsigned long long* dbg)
+{
+    using K = KT<NT, true>;
+    constexpr int NW = K::NW;
+    __shared__ Ghm g;
+    __shared__ pk::PGhm pg;
+    __shared__ Red red;
+    __shared__ RsLayout lay;
+    __shared__ int sh_i[NW];
+    __shared__ int sh_s[8];
+    __shared__ int sh_task;
+    __shared__ long long prof2[8];
+    __shared__ long long rctr[16];
+    if (threadIdx.x == 0) s_rot = 0;
+    if (threadIdx.x < 16) rctr[threadIdx.x] = 0;
+    __syncthreads();
+    const int tid = VTID, lane = tid & 31, warp = tid >> 5;
+    const double q = prm.q_value;
+    int gmax = 1;   // largest gap size of the schedule (seed_pass)
+    for (int k = 0; k < prm.n_gaps && k < 10; k++) gmax = max(gmax, prm.gaps[k]);
+    long long rt_ = 0;
+#define RT(k) do { if (dbg) { const long long n_ = clock64(); if (tid == 0) rctr[k] += n_ - rt_; rt_ = n_; } } while (0)
+    while (true) {
+        if (tid == 0) sh_task = atomicAdd(next_task, 1);
+        __syncthreads();
+        const int ti = sh_task;
+        if (ti >= n_tasks) break;
+        if (dbg) rt_ = clock64();
+        GhmTask& task = tasks[order[ti]];
+        const int D0 = (int)task.cnt[0], D1 = (int)task.cnt[1];
+        if (tid == 0) {
+            lay = rs_layout(D0, D1, NT, prm.rs_squeeze);
+            setup_view_resident(g, task, rs_smem, lay, prm);
+            g.ctr = dbg ? rctr : nullptr;
+            if ((int)lay.total > smem_bytes) g.status = 4;   // (the host sizes the classes: never expected)
+        }
+        __syncthreads();
+        bool ok = (g.status == 0);
+        if (ok) {
+            // the dots (written once by K1) become the two mutable matrices
+            const uint32_t* src = dots + task.dot_off;
+            for (int i = tid; i < D0; i += NT) {
+                g.key[0][i] = src[i];
+                g.alive[0][i] = 1;
+            }
+            for (int i = tid; i < D1; i += NT) {
+                g.key[1][i] = src[D0 + i];
+                g.alive[1][i] = 1;
+            }
+            __syncthreads();
+            RT(0);
+            // ---- phase 1 (GHM.cpp:167-184): seed / enrich / join at growing gaps, per orientation
+            for (int gi = 0; gi < prm.n_gaps && gi < 10 && prm.gaps[gi] > 0 && !g.status; gi++) {
+                const int gap = prm.gaps[gi];
+                for (int o = 0; o < 2; o++) {
+                    if (g.nk[o] < 3) continue;   // cannot seed a cluster (an orientation's matrix only shrinks in phase 1)
+                    if (!K::seed_skippable(g, gap, o)) K::seed_pass(g, gap, gmax, o, q, sh_i, sh_s);
+                    __syncthreads();
+                    RT(1);
+                    if (g.status) break;
+                    if (g.nbc[o] > 0) {
+                        K::enrich_pass(g, gap, o, o, q, sh_i, sh_s);
+                        __syncthreads();
+                        RT(2);
+                        if (g.status) break;
+                    }
+                    if (g.nbc[o] > 1) {
+                        if constexpr (NT == 32) K::join_pass2(g, gap, o, q, &red, sh_s, prof2);
+                        else K::join_pass(g, gap, o, q, &red, sh_s, prof2);
+                        __syncthreads();
+                        RT(3);
+                        if (g.status) break;
+                    }
+                }
+            }
+            __syncthreads();
+            ok = (g.status == 0);
+        }
+        // ---- phase 2 (GHM.cpp:186-217): cross-orientation enrichment, filter, metaclustering
+        if (ok) do {
+            for (int rep = 0; rep < 2 && ok; rep++) {
+                for (int e = 0; e < 4; e++) {
+                    const int oc = (e == 1 || e == 2) ? 1 : 0;
+                    const int om = (e == 1 || e == 3) ? 1 : 0;
+                    if (g.nbc[oc] > 0 && g.nk[om] > 0) K::enrich_pass(g, prm.gap_size, oc, om, q, sh_i, sh_s);
+                    __syncthreads();
+                    if (g.status) { ok = false; break; }
+                }
+                RT(4);
+                if (!ok) break;
+                if (rep == 0) {
+                    K::filter_pass(g, prm, sh_s);
+                    __syncthreads();
+                    RT(5);
+                    if (g.status) ok = false;
+                }
+            }
+            if (!ok) break;
+            K::cluster_clusters(g, prm, &red, sh_i, sh_s);
+            RT(6);
+        } while (false);
+        __syncthreads();
+        const int n_mult = ok ? sh_s[0] : 0;
+        __syncthreads();
+        if (tid == 0) {
+            task.status = ok ? 0 : (g.status ? g.status : 1);
+            task.n_mult = n_mult;
+            task.n_clusters = 0;
+            task.n_aps = 0;
+            task.out_bytes = 0;
+        }
+        // K3 measure on the resident state (bounds, HL duplicate filter and false anchor points, sizes);
+        // its per-AP scratch (HL only) goes straight to the global workspace, where the writer reads it
+        if (ok && n_mult > 0) {
+            const WsLayout GL = ws_layout(D0 + D1, pool_factor);
+            uint8_t* gbase = ws + task.ws_off;
+            if (tid == 0) {
+                pg.pool = g.pool;
+                pg.cl = g.cl;
+                pg.mult = g.mult;
+                pg.out_mults = g.out_mults;
+                pg.oc = g.act;
+                pg.scratch = (int*)(gbase + GL.nxt);
+                pg.n_mult = n_mult;
+            }
+            __syncthreads();
+            if (hl) pk::measure_core<true>(pg, task, ds, pf);
+            else pk::measure_core<false>(pg, task, ds, pf);
+            __syncthreads();
+            // hand-over to the writer: same ids, same pool offsets, global arrays
+            {
+                uint32_t* gpool = (uint32_t*)(gbase + GL.pool);
+                ClusterRec* gcl = (ClusterRec*)(gbase + GL.cl);
+                MultRec* gmult = (MultRec*)(gbase + GL.mult);
+                int* gom = (int*)(gbase + GL.out_mults);
+                int* goc = (int*)(gbase + GL.act);
+                const int n_oc = pg.n_oc;
+                for (int i = warp; i < n_oc; i += NW) {
+                    const int id = g.act[i];
+                    const ClusterRec& c = g.cl[id];
+                    const uint32_t* ap = g.pool + c.off;
+                    for (int k = lane; k < c.n; k += 32) gpool[c.off + k] = ap[k];
+                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(&c);
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(&gcl[id]);
+                    for (int k = lane; k < (int)(sizeof(ClusterRec) / 4); k += 32) dw[k] = sw[k];
+                }
+                for (int m = tid; m < n_mult; m += NT) {
+                    const int mi = g.out_mults[m];
+                    gom[m] = mi;
+                    gmult[mi] = g.mult[mi];
+                }
+                for (int i = tid; i < n_oc; i += NT) goc[i] = g.act[i];
+            }
+        }
+        __syncthreads();
+        RT(7);
+        if (dbg && tid == 0) rctr[11] += prof2[7], prof2[7] = 0, rctr[15] += (ok ? 0 : 1);
+    }
+    if (dbg) {
+        __syncthreads();
+        if (tid < 16 && rctr[tid]) atomicAdd(&dbg[tid], (unsigned long long)rctr[tid]);
+    }
+#undef RT
+}
+
+// ---- work distribution of the pass-per-launch kernels ---------------------------------------------------
+// Most (GHM, orientation) items have nothing to do in most passes (config 4: half of the GHMs never form a
+// cluster; 72 % of the join calls see no cluster).  A visit used to cost a queue atomic plus a chain of
+// dependent loads into the 168-byte task record before the item could be dismissed.  Now a CTA takes up to 32
+// consecutive queue entries with one atomic; lane l reads entry l's packed state word (4 bytes per item,
+// coalesced, L2-resident) and only the entries with work in this pass are handed to the CTA.
+//   bits 0-7 smallest gap size with a 3-dot chain (saturated, seed_pass), 8 successors computed, 9 a dot was
+//   erased since, 10-11 base clusters (saturated at 3), 12 failed (pool exhausted: the host retries the GHM)
+struct Batch {
+    int item[32];
+    int n;
+    int more;
+};
+static __device__ __forceinline__ uint32_t pack_istate(const Ghm& g, int o)
+{
+    const uint32_t g3 = (uint32_t)(g.g3[o] < 0 ? 0 : (g.g3[o] > 255 ? 255 : g.g3[o]));
+    return g3 | (g.seeded[o] ? 0x100u : 0u) | (g.dirty[o] ? 0x200u : 0u) | ((uint32_t)min(g.nbc[o], 3) << 10) | (g.status ? 0x1000u : 0u);
+}
+// mode 0 seed, 1 enrich, 2 join (items = GHM * 2 + orientation); 3 = a phase-2 stage (items = GHM * 4)
+static __device__ void pop_batch(Batch& b, const int* __restrict__ items, int n_items, int* next, const uint32_t* __restrict__ istate,
+                                 int mode, int gap, bool first, int vtid)
+{
+    if (vtid < 32) {
+        // the queue is ordered heaviest item first: one entry at a time at its head (load balance), up to 32
+        // towards its tail (light items, mostly dismissed: fewer queue atomics)
+        int base = 0, cnt = 1;
+        if (vtid == 0) {
+            const float f = fminf(1.0f, (float)*(volatile int*)next / (float)(n_items > 0 ? n_items : 1));
+            cnt = 1 + (int)(31.0f * f * f * f);
+            base = atomicAdd(next, cnt);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        bool act = false;
+        int it = -1;
+        if (vtid < cnt && base + vtid < n_items) {
+            it = items[base + vtid];
+            if (mode == 3) {
+                const uint32_t st = istate[(it >> 2) * 2] | istate[(it >> 2) * 2 + 1];
+                act = (st & 0x1c00u) != 0;   // a cluster in either orientation, or a failure to report
+            } else {
+                const uint32_t st = istate[it];
+                if (first) act = true;
+                else if (st & 0x1000u) act = false;
+                else if (mode == 0) act = !((st & 0x300u) == 0x100u && gap < (int)(st & 0xffu));
+                else act = (int)((st >> 10) & 3u) >= mode;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (act) b.item[__popc(m & ((1u << vtid) - 1u))] = it;
+        if (vtid == 0) {
+            b.n = __popc(m);
+            b.more = base < n_items;
+        }
+    }
+    __syncthreads();
+}
+
 // ---- phase 1, one pass per launch ---------------------------------------------------------------
 // For large batches (thousands of GHMs) the fused kernel above is throughput-bound by instruction
 // fetch: co-resident CTAs sit in different passes of a 430 KB image and per-SM progress saturates
@@ -1980,7 +2527,7 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
                                                          int* next_item, const uint32_t* __restrict__ dots, uint8_t* ws,
                                                          DevParams prm, int pool_factor, int* sm_slot, int pass, int gi,
-                                                         unsigned long long* dbg)
+                                                         unsigned long long* dbg, uint32_t* istate)
 {
     using K = KT<NT, true>;
     constexpr int NW = K::NW;
@@ -1998,18 +2545,20 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
     const int tid = VTID;
     const int gap = prm.gaps[gi];
     const double q = prm.q_value;
+    int gmax = 1;   // largest gap size of the schedule (seed_pass)
+    for (int k = 0; k < prm.n_gaps && k < 10; k++) gmax = max(gmax, prm.gaps[k]);
     const bool first = (pass == 0 && gi == 0);
+    __shared__ Batch batch;
     while (true) {
-        if (tid == 0) sh_task = atomicAdd(next_item, 1);
-        __syncthreads();
-        const int ti = sh_task;
-        if (ti >= n_items) break;
-        const int item = items[ti];   // GHM index * 2 + orientation
+      // 32 queue entries at a time; items without work in this pass (failed earlier, no 3-dot chain at this
+      // gap size, no cluster to enrich, fewer than two clusters to join) are dismissed on their state word
+      pop_batch(batch, items, n_items, next_item, istate, pass, gap, first, tid);
+      if (!batch.more) break;
+      const int nb = batch.n;
+      for (int bi = 0; bi < nb; bi++) {
+        const int item = batch.item[bi];   // GHM index * 2 + orientation
         const int o = item & 1;
         GhmTask& task = tasks[item >> 1];
-        // failed earlier (pool exhausted): the host retries the GHM.  Only this item's CTA writes
-        // half_status[o], so the test is uniform.
-        if (!first && task.half_status[o]) continue;
         if (tid < 8) prof2[tid] = 0;
         if (tid == 0) setup_view(g, task, ws, prm, pool_factor, o, false, first);
         __syncthreads();
@@ -2023,7 +2572,9 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
             }
             __syncthreads();
         }
-        if (pass == 0) K::seed_pass(g, gap, o, q, sh_i, sh_s);
+        if (pass == 0) {
+            if (!K::seed_skippable(g, gap, o)) K::seed_pass(g, gap, gmax, o, q, sh_i, sh_s);
+        }
         else if (pass == 1) {
             if (g.nbc[o] > 0) K::enrich_pass(g, gap, o, o, q, sh_i, sh_s);
         } else {
@@ -2035,11 +2586,16 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
             task.half_ncl[o] = g.ncl[o];
             task.half_pool[o] = g.pool_used[o];
             task.half_status[o] = g.status;
+            task.half_g3[o] = g.g3[o];
+            task.half_seed[o] = (g.seeded[o] ? 1 : 0) | (g.dirty[o] ? 2 : 0);
+            istate[item] = pack_istate(g, o);
             if (dbg && pass == 2)  // IADH_TRACE: join sub-phase cycles of the whole batch
                 for (int k = 0; k < 8; k++)
                     if (prof2[k]) atomicAdd(&dbg[k], (unsigned long long)prof2[k]);
         }
         __syncthreads();
+      }
+      __syncthreads();   // (the batch is refilled by warp 0)
     }
 }
 
@@ -2048,7 +2604,7 @@ __global__ void __launch_bounds__(NT, MINB) phase1_pass_kernel(GhmTask* tasks, c
 template <int MINB>
 __global__ void __launch_bounds__(32, MINB) phase1_join2_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
                                                                 int* next_item, uint8_t* ws, DevParams prm, int pool_factor,
-                                                                int gi, unsigned long long* dbg)
+                                                                int gi, unsigned long long* dbg, uint32_t* istate)
 {
     constexpr int NT = 32;   // (VTID)
     using K = KT<NT, true>;
@@ -2062,15 +2618,15 @@ __global__ void __launch_bounds__(32, MINB) phase1_join2_kernel(GhmTask* tasks, 
     const int tid = VTID;
     const int gap = prm.gaps[gi];
     const double q = prm.q_value;
+    __shared__ Batch batch;
     while (true) {
-        if (tid == 0) sh_task = atomicAdd(next_item, 1);
-        __syncthreads();
-        const int ti = sh_task;
-        if (ti >= n_items) break;
-        const int item = items[ti];   // GHM index * 2 + orientation
+      pop_batch(batch, items, n_items, next_item, istate, 2, gap, false, tid);
+      if (!batch.more) break;
+      const int nb = batch.n;
+      for (int bi = 0; bi < nb; bi++) {
+        const int item = batch.item[bi];   // GHM index * 2 + orientation
         const int o = item & 1;
         GhmTask& task = tasks[item >> 1];
-        if (task.half_status[o]) continue;
         if (tid < 8) prof2[tid] = 0;
         if (tid == 0) setup_view(g, task, ws, prm, pool_factor, o, false, false);
         __syncthreads();
@@ -2081,11 +2637,14 @@ __global__ void __launch_bounds__(32, MINB) phase1_join2_kernel(GhmTask* tasks, 
             task.half_ncl[o] = g.ncl[o];
             task.half_pool[o] = g.pool_used[o];
             task.half_status[o] = g.status;
+            istate[item] = pack_istate(g, o);
             if (dbg)
                 for (int k = 0; k < 8; k++)
                     if (prof2[k]) atomicAdd(&dbg[k], (unsigned long long)prof2[k]);
         }
         __syncthreads();
+      }
+      __syncthreads();
     }
 }
 
@@ -2097,7 +2656,8 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, const int* __restrict__ items, int n_items,
                                                                 int* next_item, const uint32_t* __restrict__ dots,
                                                                 uint8_t* ws, DevParams prm, int pool_factor, int* sm_slot,
-                                                                DatasetDev ds, ProfileDev pf, int hl, int stage)
+                                                                DatasetDev ds, ProfileDev pf, int hl, int stage,
+                                                                const uint32_t* __restrict__ istate)
 {
     using K = KT<NT, true>;
     constexpr int NW = K::NW;
@@ -2114,12 +2674,15 @@ __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, 
     __syncthreads();
     const int tid = VTID;
     const double q = prm.q_value;
+    __shared__ Batch batch;
     while (true) {
-        if (tid == 0) sh_task = atomicAdd(next_item, 1);
-        __syncthreads();
-        const int ti = sh_task;
-        if (ti >= n_items) break;
-        GhmTask& task = tasks[items[ti] >> 2];
+      // GHMs without a base cluster in either orientation have nothing to do in phase 2 (their outcome
+      // fields were zeroed with the plan); the others are processed 32 queue entries at a time
+      pop_batch(batch, items, n_items, next_item, istate, 3, 0, false, tid);
+      if (!batch.more) break;
+      const int nb = batch.n;
+      for (int bi = 0; bi < nb; bi++) {
+        GhmTask& task = tasks[batch.item[bi] >> 2];
         if (tid == 0) {
             setup_view(g, task, ws, prm, pool_factor, 0, true, false);
             if (stage > 0) {
@@ -2186,6 +2749,8 @@ __global__ void __launch_bounds__(NT, MINB) phase2_stage_kernel(GhmTask* tasks, 
             task.half_status[0] = task.half_status[1] = g.status;
         }
         __syncthreads();
+      }
+      __syncthreads();
     }
 }
 
@@ -2205,12 +2770,70 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
     }
 }
 
+// resident kernel: `cfg` = threads per CTA, smem_bytes = dynamic shared memory per CTA (the size class)
+static int g_res_attr_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+template <int NT, int MINB>
+static cudaError_t launch_resident_t(int slot, GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots,
+                                     uint8_t* ws, const DevParams& prm, int pool_factor, int smem_bytes, const DatasetDev& ds,
+                                     const ProfileDev& pf, bool hl, int grid, cudaStream_t st, unsigned long long* dbg)
+{
+    if (!g_res_attr_done[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(resident_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e != cudaSuccess) return e;
+        g_res_attr_done[slot] = 1;
+    }
+    resident_kernel<NT, MINB><<<grid, NT, smem_bytes, st>>>(tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, smem_bytes, ds, pf, hl ? 1 : 0, dbg);
+    return cudaGetLastError();
+}
+// resident CTAs of this shape per SM (occupancy of the kernel with `smem_bytes` of dynamic shared memory)
+int resident_ctas_per_sm(int nt, int smem_bytes)
+{
+    int n = 0;
+    cudaError_t e;
+    switch (nt) {
+    case 32:
+        cudaFuncSetAttribute(resident_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resident_kernel<32, 8>, 32, (size_t)smem_bytes);
+        break;
+    case 64:
+        cudaFuncSetAttribute(resident_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resident_kernel<64, 4>, 64, (size_t)smem_bytes);
+        break;
+    case 128:
+        cudaFuncSetAttribute(resident_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resident_kernel<128, 2>, 128, (size_t)smem_bytes);
+        break;
+    default:
+        cudaFuncSetAttribute(resident_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resident_kernel<256, 1>, 256, (size_t)smem_bytes);
+        break;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return n;
+}
+
+cudaError_t launch_resident(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+                            const DevParams& prm, int pool_factor, int smem_bytes, const DatasetDev& ds, const ProfileDev& pf, bool hl,
+                            int grid, int nt, cudaStream_t st, unsigned long long* dbg)
+{
+    if (n_tasks == 0) return cudaSuccess;
+    switch (nt) {
+    case 32: return launch_resident_t<32, 8>(0, tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, smem_bytes, ds, pf, hl, grid, st, dbg);
+    case 64: return launch_resident_t<64, 4>(1, tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, smem_bytes, ds, pf, hl, grid, st, dbg);
+    case 128: return launch_resident_t<128, 2>(2, tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, smem_bytes, ds, pf, hl, grid, st, dbg);
+    default: return launch_resident_t<256, 1>(3, tasks, order, n_tasks, next_task, dots, ws, prm, pool_factor, smem_bytes, ds, pf, hl, grid, st, dbg);
+    }
+}
+
 void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                          const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
-                         bool hl, int stage, int grid, int nt, cudaStream_t st)
+                         bool hl, int stage, int grid, int nt, cudaStream_t st, const uint32_t* istate)
 {
     if (n_items == 0) return;
-    #define P2_LAUNCH(NT_, MB_) phase2_stage_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0, stage)
+    #define P2_LAUNCH(NT_, MB_) phase2_stage_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, ds, pf, hl ? 1 : 0, stage, istate)
     switch (nt) {
     case 32: P2_LAUNCH(32, 16); break;
     case 3224: P2_LAUNCH(32, 24); break;
@@ -2221,29 +2844,29 @@ void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* nex
     }
 }
 
-// IADH_JOIN2=1: the join pass of the pass-per-launch path runs phase1_join2_kernel (two-phase scan).
-// Written at the end of round 1 without GPU time left: compiled, reviewed, NOT yet run on a device.
-// Off by default; read at every launch so a test can switch it per call.  To exercise it everywhere:
-//   IADH_JOIN2=1 IADH_PASS_MIN=1 IADH_PASS_RATIO=0 python -m pytest tests -m gpu
+// The join pass of the pass-per-launch path runs phase1_join2_kernel (two-phase scan); IADH_JOIN2=0 selects the
+// row-by-row join of phase1_pass_kernel instead.  Round 2, on a B200: the whole GPU suite passes with either
+// (pass path forced), config 4's join passes take 22.8 ms instead of 49.6 ms (profiles/README.md).
+// Read at every launch so a test can switch it per call.
 static bool join2_enabled()
 {
     const char* e = getenv("IADH_JOIN2");
-    return e != nullptr && atoi(e) != 0;
+    return e == nullptr || atoi(e) != 0;
 }
 
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
-                        cudaStream_t st, unsigned long long* dbg)
+                        cudaStream_t st, unsigned long long* dbg, uint32_t* istate)
 {
     if (n_items == 0) return;
     if (pass == 2 && (nt == 32 || nt == 3224 || nt == 3232) && join2_enabled()) {  // IADH_JOIN2=1 (experimental)
-        if (nt == 32) phase1_join2_kernel<16><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
-        else if (nt == 3224) phase1_join2_kernel<24><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
-        else phase1_join2_kernel<32><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg);
+        if (nt == 32) phase1_join2_kernel<16><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg, istate);
+        else if (nt == 3224) phase1_join2_kernel<24><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg, istate);
+        else phase1_join2_kernel<32><<<grid, 32, 0, st>>>(tasks, items, n_items, next_item, ws, prm, pool_factor, gi, dbg, istate);
         return;
     }
     // (threads, minimum CTAs per SM): the second number caps the registers per thread
-    #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi, dbg)
+    #define PASS_LAUNCH(NT_, MB_) phase1_pass_kernel<NT_, MB_><<<grid, NT_, 0, st>>>(tasks, items, n_items, next_item, dots, ws, prm, pool_factor, sm_slot, pass, gi, dbg, istate)
     switch (nt) {
     case 32: PASS_LAUNCH(32, 16); break;
     case 3224: PASS_LAUNCH(32, 24); break;

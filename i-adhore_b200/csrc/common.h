@@ -23,6 +23,7 @@ struct DevParams {
     double q_value;
     double prob_cutoff;
     int coop[4];   // debug: thresholds of the cooperative stats / merge / insert / twist paths
+    int rs_squeeze; // test knob: resident budgets that real GHMs outgrow (exercises the fallback to the global path)
 };
 
 // One GHM to cluster: either list x list (level 2) or profile x list.
@@ -52,6 +53,9 @@ struct GhmTask {
     int32_t half_nbc[2], half_ncl[2], half_pool[2], half_status[2];  // device: state handed to phase 2
     int32_t half_nk[2];   // device: matrix sizes between the phase-2 launches of the pass-per-launch path
     int32_t pad2;
+    // device: seeding state between the launches of the pass-per-launch path (seed_pass in cluster_kernel.cu):
+    // smallest gap size with a 3-dot chain, and bit 0 = successor pointers computed, bit 1 = a dot was erased since
+    int32_t half_g3[2], half_seed[2];
 };
 
 // Per-GHM cycle counters of K2 (debugging / profiling aid; a separate array so that the task

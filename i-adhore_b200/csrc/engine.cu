@@ -44,10 +44,14 @@ void launch_cluster(GhmTask* tasks, GhmProf* profs, const int* order, int n_task
                     int grid, int nt, cudaStream_t st);
 void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                         const DevParams& prm, int pool_factor, int* sm_slot, int pass, int gi, int grid, int nt,
-                        cudaStream_t st, unsigned long long* dbg = nullptr);
+                        cudaStream_t st, unsigned long long* dbg, uint32_t* istate);
 void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* next_item, const uint32_t* dots, uint8_t* ws,
                          const DevParams& prm, int pool_factor, int* sm_slot, const DatasetDev& ds, const ProfileDev& pf,
-                         bool hl, int stage, int grid, int nt, cudaStream_t st);
+                         bool hl, int stage, int grid, int nt, cudaStream_t st, const uint32_t* istate);
+cudaError_t launch_resident(GhmTask* tasks, const int* order, int n_tasks, int* next_task, const uint32_t* dots, uint8_t* ws,
+                            const DevParams& prm, int pool_factor, int smem_bytes, const DatasetDev& ds, const ProfileDev& pf, bool hl,
+                            int grid, int nt, cudaStream_t st, unsigned long long* dbg = nullptr);
+int resident_ctas_per_sm(int nt, int smem_bytes);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st);
 
@@ -290,6 +294,14 @@ struct iadh_ctx {
     // workspace bytes per chunk.  Default: one chunk.  Measured on config 4: chunks small enough for L2
     // (256 MB of workspace) serialise 52 x 34 short launches and take 241 ms instead of 87 ms.
     int64_t pass_chunk_bytes = (int64_t)1 << 60;
+    // resident K2 (the GHM's clustering state in shared memory, one launch per size class): GHMs whose
+    // RsLayout fits res_max_bytes; the classes are shared-memory budgets per CTA
+    int resident = 0;               // IADH_RESIDENT=1 switches the path on (measured slower than the pass path: see DESIGN.md)
+    int res_max_bytes = 200 * 1024;
+    int res_wide_min = 600, res_wide_nt = 128;   // latency-bound calls: GHMs with >= res_wide_min dots get wide CTAs
+    cudaStream_t st_res[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_res[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DBuf d_items_res, d_items_fb, d_resdbg, d_istate;
     DBuf d_passctr;
     DBuf d_items1;
     cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
@@ -546,7 +558,20 @@ __global__ void scatter_plan_kernel(GhmTask* __restrict__ tasks, int n, const Ta
     t.status = 0;
     t.n_mult = t.n_clusters = t.n_aps = 0;
     t.out_bytes = 0;
-    for (int o = 0; o < 2; o++) t.half_nbc[o] = t.half_ncl[o] = t.half_pool[o] = t.half_status[o] = t.half_nk[o] = 0;
+    for (int o = 0; o < 2; o++) t.half_nbc[o] = t.half_ncl[o] = t.half_pool[o] = t.half_status[o] = t.half_nk[o] = t.half_g3[o] = t.half_seed[o] = 0;
+}
+// fallback of resident GHMs: fresh outcome fields before the fused kernel re-runs them (items = index * 4 + mask)
+__global__ void reset_subset_kernel(GhmTask* __restrict__ tasks, const int* __restrict__ items, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    GhmTask& t = tasks[items[k] >> 2];
+    t.half_done = 0;
+    t.half_needed = 1;
+    t.status = 0;
+    t.n_mult = t.n_clusters = t.n_aps = 0;
+    t.out_bytes = 0;
+    for (int o = 0; o < 2; o++) t.half_nbc[o] = t.half_ncl[o] = t.half_pool[o] = t.half_status[o] = t.half_nk[o] = t.half_g3[o] = t.half_seed[o] = 0;
 }
 __global__ void gather_out_kernel(const GhmTask* __restrict__ tasks, int n, TaskOut* __restrict__ out)
 {
@@ -663,6 +688,15 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     size_t ws_total = 0;
     bool pass_mode = false;
     int n_act = 0;
+    // resident K2: GHMs whose state fits the shared memory of one CTA (RsLayout), grouped into launches by
+    // (shared-memory budget, CTA width); force_global = outgrew a budget in an earlier attempt
+    struct ResLaunch {
+        int nt, smem, begin, count;
+    };
+    std::vector<ResLaunch> res_launches;
+    std::vector<int> res_items, order_all;
+    std::vector<uint8_t> is_res((size_t)n, 0), force_global((size_t)n, 0);
+    static const int res_buckets[] = {8 << 10, 12 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 96 << 10, 128 << 10, 200 << 10};
     auto make_plan = [&](std::vector<GhmTask>& tasks) -> int {
         items.clear();
         items1.clear();
@@ -692,6 +726,47 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             order.push_back(i);
         }
         sort_desc_stable(order, [&tasks](int a) { return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1]; });
+        order_all = order;
+        // split off the GHMs of the resident path; `order` keeps the rest (global-memory kernels below)
+        res_launches.clear();
+        res_items.clear();
+        std::fill(is_res.begin(), is_res.end(), 0);
+        if (c->resident && c->prm.n_gaps > 0) {
+            int64_t sum_d = 0, max_d = 1;
+            for (int i : order) {
+                const int64_t D = (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
+                sum_d += D;
+                max_d = std::max(max_d, D);
+            }
+            // a throughput-bound batch runs every GHM on one warp (most GHMs in flight per SM); a latency-bound
+            // call (a profile search: the heaviest GHM is the critical path) gives heavy GHMs wide CTAs
+            const bool throughput = (int)order.size() >= c->pass_min && sum_d / max_d >= c->pass_ratio;
+            std::map<std::pair<int, int>, std::vector<int>> classes;   // (-smem, nt) -> GHMs, heaviest first
+            std::vector<int> rest;
+            for (int i : order) {
+                const int D0 = (int)tasks[i].cnt[0], D1 = (int)tasks[i].cnt[1];
+                const int nt = (!throughput && D0 + D1 >= c->res_wide_min) ? c->res_wide_nt : 32;
+                const int64_t need = (int64_t)D0 + D1 > 100000 ? ((int64_t)1 << 40) : (int64_t)rs_layout(D0, D1, nt, c->prm.rs_squeeze).total;
+                if (force_global[i] || need > c->res_max_bytes) {
+                    rest.push_back(i);
+                    continue;
+                }
+                int b = 0;
+                while (res_buckets[b] < need) b++;
+                classes[std::make_pair(-std::min(res_buckets[b], c->res_max_bytes), nt)].push_back(i);
+                is_res[i] = 1;
+            }
+            for (auto& kv : classes) {
+                ResLaunch L;
+                L.nt = kv.first.second;
+                L.smem = -kv.first.first;
+                L.begin = (int)res_items.size();
+                L.count = (int)kv.second.size();
+                res_items.insert(res_items.end(), kv.second.begin(), kv.second.end());
+                res_launches.push_back(L);
+            }
+            order.swap(rest);
+        }
         n_act = (int)order.size();
         // queue items: GHM * 4 + orientation mask.  The two orientations of a GHM are independent up to
         // the final enrichment; when both are heavy they get an item (a CTA) each, the heavier first --
@@ -753,6 +828,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     };
     if ((rc = build_stage(c, hl, pf, tasks, total_dots, st, make_plan))) return rc;
 
+    int64_t st_fallbacks = 0;
     for (int attempt = 0;; attempt++) {
         if (attempt > 0) {  // rare: the clustering stage is rerun with a larger anchor-point pool
             if ((rc = make_plan(tasks))) return rc;
@@ -766,8 +842,71 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(cudaMemsetAsync(c->d_prof.p, 0, sizeof(GhmProf) * (size_t)n, c->st));
         CU(c->d_counter.ensure(16 + 4 * 1024 + 4 * 64));  // 4 class queues + per-SM arrival counters + pass queues
         CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024 + 4 * 64, c->st));
+        if (!res_items.empty() && (rc = upload(c->d_items_res, res_items.data(), 4 * res_items.size(), c->st))) return rc;
+        st.h2d_bytes += 4 * (int64_t)res_items.size();
         trace_mark(c->st, "host: order/ws + uploads");
         CU(cudaEventRecord(c->ev[5], c->st));
+        if (!res_launches.empty()) {
+            // resident K2: one launch per (shared-memory budget, CTA width), largest budget first, on side
+            // streams; each a persistent grid pulling its GHMs heaviest first
+            CU(cudaEventRecord(c->ev_fork, c->st));
+            int* rq = c->d_counter.as<int>() + 4 + 1024;   // queue heads (zeroed above)
+            // IADH_PASS_TIMING=1 (measurement aid): the launches run one after the other on the main stream, timed
+            static const bool res_timing = getenv("IADH_PASS_TIMING") != nullptr;
+            std::vector<cudaEvent_t> rev;
+            if (res_timing) {
+                CU(c->d_resdbg.ensure(8 * 16 * res_launches.size() + 16));
+                CU(cudaMemsetAsync(c->d_resdbg.p, 0, 8 * 16 * res_launches.size(), c->st));
+            }
+            for (size_t k = 0; k < res_launches.size(); k++) {
+                const ResLaunch& L = res_launches[k];
+                cudaStream_t s = res_timing ? c->st : c->st_res[k % 8];
+                if (res_timing) {
+                    cudaEvent_t e;
+                    cudaEventCreate(&e);
+                    cudaEventRecord(e, c->st);
+                    rev.push_back(e);
+                }
+                if (k < 8 && !res_timing) CU(cudaStreamWaitEvent(s, c->ev_fork, 0));
+                const int per_sm = std::max(1, resident_ctas_per_sm(L.nt, L.smem));
+                DevParams rprm = c->prm;
+                if (L.nt == 32 && !getenv("IADH_COOP"))   // one warp: always the all-lane merge / insert / statistics paths
+                    for (int q = 0; q < 4; q++) rprm.coop[q] = 0;
+                CU(launch_resident(c->d_tasks.as<GhmTask>(), c->d_items_res.as<int>() + L.begin, L.count, rq + (k % 60),
+                                   c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), rprm, pool_factor, L.smem, c->ds, pf, hl,
+                                   std::min(L.count, c->sm_count * per_sm), L.nt, s,
+                                   res_timing ? c->d_resdbg.as<unsigned long long>() + 16 * k : nullptr));
+                st.kernel_launches += 1;
+            }
+            for (size_t k = 0; k < std::min<size_t>(8, res_launches.size()) && !res_timing; k++) {
+                CU(cudaEventRecord(c->ev_res[k], c->st_res[k]));
+                CU(cudaStreamWaitEvent(c->st, c->ev_res[k], 0));
+            }
+            if (res_timing) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                cudaEventRecord(e, c->st);
+                rev.push_back(e);
+                cudaEventSynchronize(e);
+                for (size_t k = 0; k < res_launches.size(); k++) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, rev[k], rev[k + 1]);
+                    const ResLaunch& L = res_launches[k];
+                    int64_t dsum = 0;
+                    for (int q = 0; q < L.count; q++) dsum += (int64_t)tasks[res_items[L.begin + q]].cnt[0] + tasks[res_items[L.begin + q]].cnt[1];
+                    fprintf(stderr, "[iadh] resident launch %zu: %d threads, %d KB, %d CTAs/SM, %d GHMs, %lld dots (heaviest %u): %.3f ms\n", k, L.nt,
+                            L.smem >> 10, resident_ctas_per_sm(L.nt, L.smem), L.count, (long long)dsum,
+                            tasks[res_items[L.begin]].cnt[0] + tasks[res_items[L.begin]].cnt[1], ms);
+                    unsigned long long d[16];
+                    cudaMemcpy(d, c->d_resdbg.as<unsigned long long>() + 16 * k, sizeof d, cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "[iadh]   Mcycles: stage %.1f seed %.1f enrich %.1f join %.1f enrich2 %.1f filter %.1f meta %.1f pack %.1f | gc %llu (%.1f Mcyc) realloc-copied %llu merges %llu inserts %llu seeds %llu stat-sum entries %llu failed %llu\n",
+                            d[0] / 1e6, d[1] / 1e6, d[2] / 1e6, d[3] / 1e6, d[4] / 1e6, d[5] / 1e6, d[6] / 1e6, d[7] / 1e6, d[8], d[9] / 1e6, d[10],
+                            d[11], d[12], d[13], d[14], d[15]);
+                }
+                for (cudaEvent_t ev : rev) cudaEventDestroy(ev);
+            }
+            trace_mark(c->st, "K2 resident");
+        }
         {
             // size classes (order is sorted by dots, descending), launched concurrently: heavy GHMs get
             // wide CTAs and start first, the bulk runs on narrow CTAs (many GHMs in flight per SM --
@@ -781,6 +920,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 if (!getenv("IADH_COOP"))
                     for (int k = 0; k < 4; k++) pprm.coop[k] = 0;
                 const int n_chunks = (int)chunk_k.size() - 1;
+                CU(c->d_istate.ensure(8 * (size_t)n + 16));   // packed state word per (GHM, orientation) item (pop_batch)
+                CU(cudaMemsetAsync(c->d_istate.p, 0, 8 * (size_t)n, c->st));
                 CU(c->d_passctr.ensure(4 * 36 * (size_t)n_chunks + 80));
                 CU(cudaMemsetAsync(c->d_passctr.p, 0, 4 * 36 * (size_t)n_chunks + 80, c->st));
                 // IADH_PASS_TIMING=1 (measurement aid): device time of every pass / stage launch
@@ -803,7 +944,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                         for (int pass = 0; pass < 3; pass++) {
                             launch_phase1_pass(c->d_tasks.as<GhmTask>(), it1, n1, pc + gi * 3 + pass, c->d_dots.as<uint32_t>(),
                                                c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, pass, gi, grid, c->pass_nt, c->st,
-                                               g_trace ? (unsigned long long*)(c->d_passctr.as<int>() + 36 * n_chunks) : nullptr);
+                                               g_trace ? (unsigned long long*)(c->d_passctr.as<int>() + 36 * n_chunks) : nullptr,
+                                               c->d_istate.as<uint32_t>());
                             st.kernel_launches += 1;
                             pmark();
                         }
@@ -813,7 +955,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                     for (int stage = 0; stage < 4; stage++) {
                         launch_phase2_stage(c->d_tasks.as<GhmTask>(), it2, n2, pc + 30 + stage, c->d_dots.as<uint32_t>(),
                                             c->d_ws.as<uint8_t>(), pprm, pool_factor, ctr + 4, c->ds, pf, hl, stage, grid2,
-                                            c->pass_nt, c->st);
+                                            c->pass_nt, c->st, c->d_istate.as<uint32_t>());
                         st.kernel_launches += 1;
                         pmark();
                     }
@@ -905,8 +1047,48 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                         pr[hv].prof2[0] / 1e6, pr[hv].prof2[1] / 1e6, pr[hv].prof2[2] / 1e6, pr[hv].prof2[3] / 1e6,
                         pr[hv].prof2[4] / 1e6, pr[hv].prof2[5] / 1e6, pr[hv].prof2[6] / 1e6, pr[hv].prof2[7]);
         }
+        // resident GHMs that outgrew a shared-memory budget are re-run on the global path (fused kernel, wide
+        // CTAs), the others keep their results
+        {
+            std::vector<int> fb;
+            bool global_failed = false;
+            for (int i : order_all)
+                if (tasks[i].status != 0) {
+                    if (is_res[i]) fb.push_back(i);
+                    else global_failed = true;
+                }
+            for (int i : fb) force_global[i] = 1;
+            if (!fb.empty() && !global_failed) {
+                if (g_trace) fprintf(stderr, "[iadh] resident fallback: %d of %d GHMs (first: D=%u+%u status %d)\n", (int)fb.size(),
+                                     (int)res_items.size(), tasks[fb[0]].cnt[0], tasks[fb[0]].cnt[1], tasks[fb[0]].status);
+                std::vector<int> fitems;
+                for (int i : fb) fitems.push_back(i * 4 + tasks[i].half_mask);
+                if ((rc = upload(c->d_items_fb, fitems.data(), 4 * fitems.size(), c->st))) return rc;
+                CU(cudaMemsetAsync(c->d_counter.p, 0, 16 + 4 * 1024 + 4 * 64, c->st));
+                reset_subset_kernel<<<((int)fb.size() + 127) / 128, 128, 0, c->st>>>(c->d_tasks.as<GhmTask>(), c->d_items_fb.as<int>(), (int)fb.size());
+                launch_cluster(c->d_tasks.as<GhmTask>(), c->d_prof.as<GhmProf>(), c->d_items_fb.as<int>(), (int)fb.size(), c->d_counter.as<int>(),
+                               c->d_dots.as<uint32_t>(), c->d_ws.as<uint8_t>(), c->prm, pool_factor, c->d_counter.as<int>() + 4, c->ds, pf, hl,
+                               std::min((int)fb.size(), c->sm_count * 2), 256, c->st);
+                CU(cudaEventRecord(c->ev[6], c->st));
+                gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
+                CU(cudaMemcpyAsync(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+                CU(cudaStreamSynchronize(c->st));
+                st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
+                st.h2d_bytes += 4 * (int64_t)fitems.size();
+                st.kernel_launches += 3;
+                const TaskOut* ho = c->h_misc.as<TaskOut>();
+                for (int i : fb) {
+                    tasks[i].out_bytes = ho[i].out_bytes;
+                    tasks[i].status = ho[i].status;
+                    tasks[i].n_mult = ho[i].n_mult;
+                    tasks[i].n_clusters = ho[i].n_clusters;
+                    tasks[i].n_aps = ho[i].n_aps;
+                }
+                st_fallbacks += (int64_t)fb.size();
+            }
+        }
         bool retry = false;
-        for (int i : order)
+        for (int i : order_all)
             if (tasks[i].status != 0) {
                 if (g_trace && !retry)
                     fprintf(stderr, "[iadh] retry: GHM %d (D=%u+%u) status=%d clusters=%d pool_factor=%d\n", i, tasks[i].cnt[0],
@@ -1156,6 +1338,10 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 8; i++) {
+        CU(cudaStreamCreateWithFlags(&c->st_res[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_res[i], cudaEventDisableTiming));
+    }
     c->n_lists = d->n_lists;
     c->list_off.assign(d->list_off, d->list_off + d->n_lists + 1);
     const int64_t total = d->n_lists ? c->list_off[d->n_lists] : 0;
@@ -1326,6 +1512,10 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) c->ws_budget = (int64_t)(tot / 2);
     }
     if (const char* e = getenv("IADH_WS_BUDGET_MB")) c->ws_budget = (int64_t)std::max(1, atoi(e)) << 20;
+    if (const char* e = getenv("IADH_RESIDENT")) c->resident = atoi(e);
+    if (const char* e = getenv("IADH_RES_SQUEEZE")) c->prm.rs_squeeze = atoi(e);
+    if (const char* e = getenv("IADH_RES_MAX_KB")) c->res_max_bytes = std::min(222, std::max(4, atoi(e))) << 10;
+    if (const char* e = getenv("IADH_RES_WIDE")) sscanf(e, "%d:%d", &c->res_wide_min, &c->res_wide_nt);
     if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
@@ -1359,7 +1549,7 @@ void iadh_destroy(iadh_ctx* c)
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
-                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col};
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate};
     for (DBuf* b : bufs) b->release();
     c->h_tasks.release();
     c->h_misc.release();
@@ -1374,6 +1564,10 @@ void iadh_destroy(iadh_ctx* c)
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 8; i++) {
+        if (c->st_res[i]) cudaStreamDestroy(c->st_res[i]);
+        if (c->ev_res[i]) cudaEventDestroy(c->ev_res[i]);
+    }
     delete c;
 }
 

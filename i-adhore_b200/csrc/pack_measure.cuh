@@ -57,14 +57,13 @@ __device__ __forceinline__ bool seg_match(const DatasetDev& ds, const ProfileDev
     return pf.fam[idx] == fy && pf.gid[idx] != gy;
 }
 
-// whole CTA (any block size that is a multiple of 32); `p` = one shared PGhm of the CTA
+// whole CTA (any block size that is a multiple of 32); `p` = one shared PGhm of the CTA, its array
+// pointers and n_mult set by the caller (the GHM's global workspace, or the resident kernel's shared memory)
 template <bool HL>
-__device__ void measure_ghm(PGhm& p, GhmTask& task, uint8_t* ws, const DatasetDev& ds, const ProfileDev& pf,
-                            int pool_factor)
+__device__ void measure_core(PGhm& p, GhmTask& task, const DatasetDev& ds, const ProfileDev& pf)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, PW = blockDim.x >> 5;
     if (tid == 0) {
-        pghm_init(p, task, ws, pool_factor);
         int n = 0, sbase = 0;
         for (int m = 0; m < p.n_mult; m++)
             for (int c = p.mult[p.out_mults[m]].head; c >= 0; c = p.cl[c].mnext) {
@@ -167,6 +166,15 @@ __device__ void measure_ghm(PGhm& p, GhmTask& task, uint8_t* ws, const DatasetDe
         task.n_clusters = p.n_oc;
         task.n_aps = naps;
     }
+}
+
+template <bool HL>
+__device__ void measure_ghm(PGhm& p, GhmTask& task, uint8_t* ws, const DatasetDev& ds, const ProfileDev& pf,
+                            int pool_factor)
+{
+    if (threadIdx.x == 0) pghm_init(p, task, ws, pool_factor);
+    __syncthreads();
+    measure_core<HL>(p, task, ds, pf);
 }
 
 }  // namespace pk

@@ -59,3 +59,77 @@ static inline WsLayout ws_layout(int D, int pool_factor)
     L.total = (o + 255) & ~(size_t)255;
     return L;
 }
+
+// ---- shared-memory resident layout (resident_kernel, cluster_kernel.cu) ----------------------------
+// The same arrays as WsLayout, sized for a GHM whose whole clustering state lives in the shared memory
+// of ONE CTA from the first seed to the packed sizes: no workspace traffic to HBM between passes.
+// Capacities are budgets, not bounds -- a GHM that outgrows one (cluster slots, anchor-point pool, matrix
+// re-insertion) reports a status and is re-run by the host on the global-memory path; results never
+// depend on the budget.  Differences from WsLayout:
+//   * cluster slots are recycled after merges, so cl_cap bounds the LIVE clusters (config 3 / 4: at most
+//     D / 10 live against D / 4 ever created);
+//   * the pool is 2 D entries (tight block capacities + compaction) instead of 8 D;
+//   * dscr is a fixed chunk (the ordered sums are accumulated chunk by chunk);
+//   * the two orientations are clustered one after the other by the same CTA: act / xr / ... are shared.
+struct RsLayout {
+    uint32_t key0, key1, alive0, alive1, nxt, tmp, tmpf, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, rb_d, rb_j,
+        rank, pos, redo, xr, dscr;
+    uint32_t total;
+    int cap0, cap1, tmp_cap, pool_cap, cl_cap0, cl_cap1, dscr_cap;
+};
+
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline RsLayout rs_layout(int D0, int D1, int nt, int squeeze = 0)
+{
+    RsLayout L;
+    uint32_t o = 0;
+    auto take = [&o](uint32_t bytes) {
+        const uint32_t r = o;
+        o += (bytes + 15u) & ~15u;
+        return r;
+    };
+    const int D = D0 + D1;
+    L.cap0 = D0 + 32;   // matrix capacity: the dots + room for re-inserted anchor points of the other orientation
+    L.cap1 = D1 + 32;
+    L.tmp_cap = (L.cap0 > L.cap1 ? L.cap0 : L.cap1);
+    L.pool_cap = 2 * D + 64;
+    int c0 = D0 / 8 + 8, c1 = D1 / 8 + 8;
+    if (squeeze) {   // test knob (IADH_RES_SQUEEZE): budgets that real GHMs outgrow, to exercise the fallback
+        L.pool_cap = D / 2 + 16;
+        c0 = c1 = 3;
+        L.cap0 = D0;
+        L.cap1 = D1;
+    }
+    L.cl_cap0 = c0 < D0 / 3 + 2 ? c0 : D0 / 3 + 2;   // (never more slots than the global table has)
+    L.cl_cap1 = c1 < D1 / 3 + 2 ? c1 : D1 / 3 + 2;
+    const uint32_t cc = (uint32_t)(L.cl_cap0 + L.cl_cap1);
+    L.dscr_cap = nt > 64 ? nt : 64;
+    L.cl = take((uint32_t)sizeof(ClusterRec) * cc);
+    L.mult = take((uint32_t)sizeof(MultRec) * cc);
+    L.rb_d = take(8 * cc);
+    L.xr = take(8 * cc);
+    L.dscr = take(16 * (uint32_t)L.dscr_cap);
+    L.key0 = take(4 * (uint32_t)L.cap0);
+    L.key1 = take(4 * (uint32_t)L.cap1);
+    L.nxt = take(4 * (uint32_t)(L.cap0 + L.cap1));   // successor pointers persist across the gap sizes (seed_pass)
+    L.tmp = take(4 * (uint32_t)L.tmp_cap);
+    L.pool = take(4 * (uint32_t)L.pool_cap);
+    L.bc0 = take(4 * (uint32_t)L.cl_cap0);
+    L.bc1 = take(4 * (uint32_t)L.cl_cap1);
+    L.act = take(4 * cc);
+    L.act_next = take(4 * cc);
+    L.out_mults = take(4 * cc);
+    L.rb_j = take(4 * cc);
+    L.rank = take(4 * cc);
+    L.pos = take(4 * cc);
+    L.redo = take(4 * cc);
+    L.alive0 = take((uint32_t)L.cap0);
+    L.alive1 = take((uint32_t)L.cap1);
+    L.tmpf = take((uint32_t)L.tmp_cap);
+    L.pflag = take((uint32_t)L.pool_cap);
+    L.changed = take(cc);
+    L.total = o;
+    return L;
+}

@@ -146,6 +146,7 @@ inline int __reduce_min_sync(unsigned, int v)
     return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }

@@ -68,14 +68,15 @@ static bool run_variant(const GhmIn& in, const DevParams& prm, int pool_factor, 
     task.half_needed = (int)items.size();
     std::vector<int> sm_slot(1024, 0);
     unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t istate[2] = {0, 0};
     if (items.empty()) return true;
     for (int gi = 0; gi < prm.n_gaps; gi++)
         for (int pass = 0; pass < 3; pass++) {
             int next_item = 0;
             if (pass == 2 && join2)
-                emu::run_block(0, EMU_NT, [&]() { phase1_join2_kernel<32>(&task, items.data(), (int)items.size(), &next_item, ws.data(), prm, pool_factor, gi, dbg); });
+                emu::run_block(0, EMU_NT, [&]() { phase1_join2_kernel<32>(&task, items.data(), (int)items.size(), &next_item, ws.data(), prm, pool_factor, gi, dbg, istate); });
             else
-                emu::run_block(0, EMU_NT, [&]() { phase1_pass_kernel<32, 32>(&task, items.data(), (int)items.size(), &next_item, in.keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg); });
+                emu::run_block(0, EMU_NT, [&]() { phase1_pass_kernel<32, 32>(&task, items.data(), (int)items.size(), &next_item, in.keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg, istate); });
             if (getenv("EMU_TRACE")) {
                 const ClusterRec* cl = (const ClusterRec*)(ws.data() + L.cl);
                 for (int o = 0; o < 2; o++) {

@@ -65,7 +65,7 @@ int main(int argc, char** argv)
     }
     int n_ghm = 0;
     if (!rd(f, &n_ghm, 1)) return 2;
-    long long bad = 0, n_mult = 0, n_bytes = 0;
+    long long bad = 0, n_mult = 0, n_bytes = 0, n_resident = 0, n_fallback = 0;
     for (int gidx = 0; gidx < n_ghm; gidx++) {
         int32_t pi, xl, yl, xobj, level, n_exp;
         uint64_t area;
@@ -101,6 +101,28 @@ int main(int argc, char** argv)
                 const int item = 0 * 4 + task.half_mask;
                 int next = 0;
                 std::vector<int> sm_slot(1024, 0);
+                // EMU_RES=1: the resident kernel (the GHM's state in "shared memory": a host buffer of exactly
+                // RsLayout::total bytes, so an overrun of a budget shows up under a memory checker); a GHM that
+                // outgrows a budget (status != 0) falls through to the global-path kernel below, like the engine
+                const char* rm = getenv("EMU_RES");
+                bool done_resident = false;
+                if (rm && atoi(rm) > 0) {
+                    const RsLayout RL = rs_layout((int)cnt[0], (int)cnt[1], EMU_NT);
+                    std::vector<uint8_t> smem(RL.total + 16, 0xcd);
+                    rs_smem = smem.data();
+                    const int order0 = 0;
+                    constexpr int MB = EMU_NT == 32 ? 8 : EMU_NT == 64 ? 4 : EMU_NT == 128 ? 2 : 1;
+                    emu::run_block(0, EMU_NT, [&]() { resident_kernel<EMU_NT, MB>(&task, &order0, 1, &next, keys.data(), ws.data(), prm, pool_factor, (int)RL.total, ds, pf, hl ? 1 : 0, nullptr); });
+                    rs_smem = nullptr;
+                    n_resident++;
+                    if (task.status == 0) done_resident = true;
+                    else {
+                        n_fallback++;
+                        task.status = 0; task.n_mult = 0; task.out_bytes = 0; task.n_clusters = 0; task.n_aps = 0;
+                        next = 0;
+                    }
+                }
+                if (!done_resident) {
 #if EMU_NT == 32
                 // EMU_PASS=1: the pass-per-launch path instead of the fused kernel (one launch per pass and gap
                 // size over the (GHM, orientation) items, then the four phase-2 stages); EMU_PASS=2: the same
@@ -112,22 +134,24 @@ int main(int argc, char** argv)
                     for (int o = 0; o < 2; o++)
                         if (cnt[o] >= 3) items1.push_back(o);
                     unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t istate[2] = {0, 0};
                     for (int gi = 0; gi < prm.n_gaps && !items1.empty(); gi++)
                         for (int pass = 0; pass < 3; pass++) {
                             next = 0;
                             if (pass == 2 && join2)
-                                emu::run_block(0, 32, [&]() { phase1_join2_kernel<32>(&task, items1.data(), (int)items1.size(), &next, ws.data(), prm, pool_factor, gi, dbg); });
+                                emu::run_block(0, 32, [&]() { phase1_join2_kernel<32>(&task, items1.data(), (int)items1.size(), &next, ws.data(), prm, pool_factor, gi, dbg, istate); });
                             else
-                                emu::run_block(0, 32, [&]() { phase1_pass_kernel<32, 32>(&task, items1.data(), (int)items1.size(), &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg); });
+                                emu::run_block(0, 32, [&]() { phase1_pass_kernel<32, 32>(&task, items1.data(), (int)items1.size(), &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), pass, gi, dbg, istate); });
                         }
                     const int item2 = 0;
                     for (int stage = 0; stage < 4; stage++) {
                         next = 0;
-                        emu::run_block(0, 32, [&]() { phase2_stage_kernel<32, 32>(&task, &item2, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0, stage); });
+                        emu::run_block(0, 32, [&]() { phase2_stage_kernel<32, 32>(&task, &item2, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0, stage, istate); });
                     }
                 } else
 #endif
                 emu::run_block(0, EMU_NT, [&]() { cluster_kernel<EMU_NT>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
+                }
                 if (task.status != 0) continue;   // anchor-point pool exhausted: retry with a larger pool, like the engine
                 int32_t nm = task.n_mult;
                 memcpy(got.data(), &nm, 4);
@@ -157,7 +181,7 @@ int main(int argc, char** argv)
         }
     }
     fclose(f);
-    printf("{\"ghms\": %d, \"multiplicons\": %lld, \"bytes\": %lld, \"mismatching_ghms\": %lld, \"collectives\": %llu}\n", n_ghm, n_mult, n_bytes, bad,
-           emu::n_collectives);
+    printf("{\"ghms\": %d, \"multiplicons\": %lld, \"bytes\": %lld, \"mismatching_ghms\": %lld, \"collectives\": %llu, \"resident\": %lld, \"resident_fallbacks\": %lld}\n", n_ghm, n_mult, n_bytes, bad,
+           emu::n_collectives, n_resident, n_fallback);
     return bad ? 1 : 0;
 }

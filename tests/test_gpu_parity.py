@@ -175,6 +175,7 @@ def test_pool_exhaustion_is_retried(monkeypatch):
     and still give the reference's answer."""
     tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
     monkeypatch.setenv("IADH_POOL_FACTOR", "1")
+    monkeypatch.setenv("IADH_RESIDENT", "0")
     gpu = capi.load_product(tr.dataset)
     monkeypatch.delenv("IADH_POOL_FACTOR")
     errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL, check_dots=False)
@@ -289,6 +290,7 @@ def test_dense_build_matches_oracle():
 def test_orientation_split_is_invisible(split_min, monkeypatch):
     """The two orientations of a GHM may be clustered by two CTAs (IADH_SPLIT_MIN): same bytes."""
     tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
+    monkeypatch.setenv("IADH_RESIDENT", "0")     # (the split belongs to the global-memory kernels)
     monkeypatch.setenv("IADH_SPLIT_MIN", split_min)
     gpu = capi.load_product(tr.dataset)
     errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL)
@@ -343,6 +345,7 @@ def test_pass_per_launch_mode_is_invisible(monkeypatch):
     inputs, level 2 and profile searches: same bytes as the fused kernel / the reference."""
     monkeypatch.setenv("IADH_PASS_MIN", "1")
     monkeypatch.setenv("IADH_PASS_RATIO", "0")
+    monkeypatch.setenv("IADH_RESIDENT", "0")     # (the path of GHMs too large for the resident kernel)
     tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
     gpu = capi.load_product(tr.dataset)
     errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL)
@@ -361,6 +364,7 @@ def test_pass_per_launch_mode_retries_pool_exhaustion(monkeypatch):
     """The rerun with a larger anchor-point pool also works when the state travels between launches."""
     monkeypatch.setenv("IADH_PASS_MIN", "1")
     monkeypatch.setenv("IADH_PASS_RATIO", "0")
+    monkeypatch.setenv("IADH_RESIDENT", "0")
     monkeypatch.setenv("IADH_POOL_FACTOR", "1")
     tr = read_trace([p for p in pl.golden_traces() if "tiny_4g" in p][0])
     gpu = capi.load_product(tr.dataset)
@@ -445,3 +449,30 @@ def test_pairs_mode_matches_oracle_and_refuses_masked_level2():
         with pytest.raises(RuntimeError, match="masked"):
             gpu.level2_pairs([0], [1])
         gpu.close()
+
+
+@pytest.mark.parametrize("knobs", [{}, {"IADH_RES_WIDE": "1:64"}, {"IADH_RES_WIDE": "1:256"}, {"IADH_RES_SQUEEZE": "1"},
+                                   {"IADH_RES_SQUEEZE": "1", "IADH_POOL_FACTOR": "1"}, {"IADH_RESIDENT": "0"}, {"IADH_JOIN2": "0"}],
+                         ids=["resident", "wide64", "wide256", "squeezed", "squeezed_pool1", "global_only", "global_rowjoin"])
+def test_resident_kernel_variants_are_invisible(knobs, monkeypatch):
+    """The resident kernel (a GHM's clustering state in the shared memory of one CTA) on 32-, 64- and
+    256-thread CTAs, with budgets so small that most GHMs outgrow them and are re-run on the global path
+    (IADH_RES_SQUEEZE; with IADH_POOL_FACTOR=1 that re-run itself retries with a larger pool), and switched
+    off: the reference's bytes every time, level 2 and profile searches, all three filter modes."""
+    monkeypatch.setenv("IADH_RESIDENT", "1")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    if "IADH_JOIN2" in knobs:          # the row-by-row join of the pass-per-launch path (the two-phase join is the default)
+        monkeypatch.setenv("IADH_RESIDENT", "0")
+        monkeypatch.setenv("IADH_PASS_MIN", "1")
+        monkeypatch.setenv("IADH_PASS_RATIO", "0")
+    for name in ("tiny_4g", "tiny_fdr", "tiny_none", "tiny_pairs"):
+        tr = read_trace([p for p in pl.golden_traces() if name in p][0])
+        gpu = capi.load_product(tr.dataset)
+        errs = pl.replay_trace(gpu, tr, rtol_p=pl.P_RTOL, check_dots=False)
+        gpu.close()
+        assert not errs, (name, errs[:3])
+    cfg = synth.config_small(seed=77)
+    ds, gpu, cpu = _pair(cfg, capi.MH_BONFERRONI)
+    assert gpu.level2_all_pairs().bytes == cpu.level2_all_pairs().bytes
+    gpu.close()
