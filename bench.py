@@ -175,25 +175,54 @@ def make_profiles(ds, l2_bytes, n_profiles):
     return out
 
 
-def hot_path_step(eng, profs, rank, n_ranks, gather=None):
-    """One pass of the hot path; returns (units, stats list, launches)."""
+def ref_profiles_path(workload):
+    return os.path.join(REPO, "tests", "golden", f"bench_profiles_{workload}.bin.gz")
+
+
+def sample_pairs(n_pairs_total, ref_profiles, profiles):
+    """List pairs of the CPU sample: the same fraction of a step as its profile searches."""
+    return max(1, -(-n_pairs_total * ref_profiles // max(1, profiles)))
+
+
+def ref_profiles_meta(workload):
+    p = ref_profiles_path(workload).replace(".bin.gz", ".json")
+    return json.load(open(p)) if os.path.exists(p) and os.path.exists(ref_profiles_path(workload)) else None
+
+
+def bench_profiles(ds, workload, n_profiles, l2_bytes_fn):
+    """The profiles of a step as [(masks, Profile)], masks = (list, begin, end) ranges applied before the search
+    (higherLevel.cpp:165-171).  Preferred: the reference's OWN first aligned profiles on this workload, dumped by
+    oracle/_ref/ref_harness (tools/make_ref_profiles.py, committed under tests/golden/) -- the CPU arm searches
+    the first few of exactly these.  Otherwise 2-segment profiles made from the largest level-2 multiplicons."""
+    path = ref_profiles_path(workload)
+    meta = ref_profiles_meta(workload)
+    if meta and meta["profiles"] >= n_profiles:
+        ps = profiles.load_reference_profiles(ds, path, n_profiles)
+        if len(ps) == n_profiles:
+            return ps, (f"the reference's own first {n_profiles} aligned profiles on this workload (queue of the first {meta['max_pairs']} list "
+                        "pairs, as in the CPU sample; ref_harness --dump-profiles, committed under tests/golden)")
+    made = make_profiles(ds, l2_bytes_fn(), n_profiles)
+    return ([([(m.x_object_id, m.bounds[0], m.bounds[1]), (m.y_object_id, m.bounds[2], m.bounds[3])], p) for m, p in made],
+            "2-segment profiles from the largest level-2 multiplicons (no reference dump for this workload)")
+
+
+def hot_path_step(eng, profs, rank, n_ranks):
+    """One pass of the hot path: the level-2 call over this rank's share of the list pairs, then every profile
+    search of the step in one batched call (iadh_profile_search_batch; N > 1: whole profiles dealt round-robin
+    to the ranks); N > 1: each followed by the library's NCCL all-gather (iadh_allgather_results), after which
+    every rank holds all ranks' packed multiplicons on the host, as after the reference's MPI gathers.
+    Returns (units, stats of this rank's calls, launches)."""
     eng.clear_masks()
-    launches = 1
     r = eng.level2_all_pairs(rank, n_ranks)
-    if gather:
-        gather(r)
     stats = [r.stats]
-    units = r.stats["n_ghm"]
-    for m, p in profs:
-        eng.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
-        eng.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
-        launches += 2
-        pr = eng.profile_search(p, rank, n_ranks)
-        if gather:
-            gather(pr)
-        stats.append(pr.stats)
-        units += pr.stats["n_ghm"]
-    launches += sum(s["kernel_launches"] for s in stats)
+    if n_ranks > 1:
+        eng.allgather([r])
+    res = eng.profile_search_batch([p for _, p in profs], [m for m, _ in profs], rank, n_ranks, shard_profiles=n_ranks > 1)
+    if n_ranks > 1:
+        eng.allgather(res)
+    stats += [x.stats for x in res]
+    units = sum(s["n_ghm"] for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats)
     return units, stats, launches
 
 
@@ -251,6 +280,7 @@ def main():
     ap.add_argument("--ref-profiles", type=int, default=4, help="profile searches in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the K1 roofline measurement on config 5")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other named configurations")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -266,7 +296,10 @@ def main():
     # the CPU sample is the same fraction of both kinds of GHM of a step
     n_lists_total = sum(len(g.list_sizes) if g.list_sizes else g.n_lists for g in cfg.genomes)
     n_pairs_total = n_lists_total * (n_lists_total + 1) // 2
-    ref_pairs = max(1, -(-n_pairs_total * a.ref_profiles // max(1, a.profiles)))
+    ref_pairs = sample_pairs(n_pairs_total, a.ref_profiles, a.profiles)
+    meta = ref_profiles_meta(a.workload)
+    if meta and meta["profiles"] >= a.profiles and a.ref_profiles <= meta["profiles"]:
+        ref_pairs = meta["max_pairs"]     # the queue the committed profile dump was made from: same first profiles
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -313,34 +346,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(res):
-        """levelTwo.cpp:225-269 / higherLevel.cpp:279-314: all ranks end with every rank's packed
-        multiplicons in rank order (sizes, then padded bytes, over NCCL).  The payload goes from the
-        library's pinned result buffer straight to the device (no host-side copies)."""
-        view = res.view()
-        n = torch.tensor([view.size], dtype=torch.int64, device="cuda")
-        sizes = torch.empty(world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(sizes, n)
-        sizes = sizes.tolist()
-        mx = max(sizes)
-        buf = torch.empty(mx, dtype=torch.uint8, device="cuda")
-        buf[:view.size].copy_(torch.from_numpy(view), non_blocking=True)
-        outs = torch.empty(world * mx, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(outs, buf)
-        torch.cuda.current_stream().synchronize()   # the pinned buffer is released when `res` dies
-        return [outs[r * mx:r * mx + sizes[r]] for r in range(world)]
-
     t_setup = time.time()
     ds = ingest.dataset_from_synth(cfg, device=local_rank)   # tandem remapping on the device (iadh_remap_tandems)
     eng = capi.load_product(ds, device=local_rank)
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
-    r0 = eng.level2_all_pairs()          # untimed: provides the multiplicons the profiles are made from
-    profs = make_profiles(ds, r0.bytes, a.profiles)
+    profs, prof_src = bench_profiles(ds, a.workload, a.profiles, lambda: eng.level2_all_pairs().bytes)
+    config["profiles"] = prof_src
+    uid = None
+    if dist:   # the library's own communicator (NCCL): rank 0 makes the id, torch.distributed only carries it
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+        eng.comm_init(uid, rank, world)
     setup_s = time.time() - t_setup
-    g = gather if dist else None
 
     for _ in range(a.warmup):
-        hot_path_step(eng, profs, rank, world, g)
+        hot_path_step(eng, profs, rank, world)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -350,7 +373,7 @@ def main():
     launches = 0
     all_stats = []
     for _ in range(a.steps):
-        u, st, ln = hot_path_step(eng, profs, rank, world, g)
+        u, st, ln = hot_path_step(eng, profs, rank, world)
         units += u
         launches += ln
         all_stats.append(st)
@@ -369,10 +392,45 @@ def main():
         units, launches = int(u[0].item()), int(u[1].item())
     value = units / dt
 
+    # one profile search per call (the latency a sequential caller sees), outside the timed region
+    hl_single_ms = None
+    if world == 1 and a.profiles:
+        eng.clear_masks()
+        t_single = []
+        for masks, p in profs[:min(8, len(profs))]:
+            for (l, b, e) in masks:
+                eng.mask_range(l, b, e)
+            t_single.append(eng.profile_search(p).stats["total_ms"])
+        hl_single_ms = float(np.mean(t_single))
+    # other named configurations, short runs (N = 1 only): resident-context value of the same step
+    extra = {}
+    if world == 1 and not a.no_extra:
+        eng.close()
+        for wl in [w for w in ("c3", "d2") if w != a.workload]:
+            try:
+                xcfg = workload_config(wl)
+                xds = ingest.dataset_from_synth(xcfg, device=local_rank)
+                xe = capi.load_product(xds, device=local_rank)
+                xe.set_params(xcfg.gap_size, xcfg.cluster_gap, xcfg.anchor_points, capi.MH_BONFERRONI, xcfg.q_value, xcfg.prob_cutoff)
+                xp, xsrc = bench_profiles(xds, wl, a.profiles, lambda: xe.level2_all_pairs().bytes)
+                hot_path_step(xe, xp, 0, 1)
+                xe.event_record(0)
+                xu = 0
+                for _ in range(3):
+                    xu += hot_path_step(xe, xp, 0, 1)[0]
+                xe.event_record(1)
+                xms = xe.event_elapsed_ms(0, 1)
+                extra[wl] = {"workload": workload_label(wl, xcfg, a.profiles), "profiles": xsrc, "value": xu / (xms * 1e-3), "unit": UNIT,
+                             "ms_per_step": xms / 3, "steps": 3, "warmup": 1}
+                xe.close()
+            except Exception as e:
+                extra[wl] = {"error": str(e)[:200]}
+        eng = None
     # e2e: fresh context from host buffers every step (dataset H2D + results D2H in the timed region).
     # The resident context is closed first: its device blocks return to the library's cache, as they
     # would between two runs of a drop-in caller, instead of forcing a second 13 GB working set.
-    eng.close()
+    if eng is not None:
+        eng.close()
     barrier()
     e0 = time.perf_counter()
     e_units = 0
@@ -385,7 +443,9 @@ def main():
         te = time.perf_counter()
         e2 = capi.load_product(ds, device=local_rank)
         e2.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
-        u, st, _ = hot_path_step(e2, profs, rank, world, g)
+        if uid is not None:
+            e2.comm_init(uid, rank, world)     # (the communicator outlives contexts: no second ncclCommInitRank)
+        u, st, _ = hot_path_step(e2, profs, rank, world)
         e2.close()
         e_units += u
         h2d += ds_bytes + fam_csr_bytes + sum(s["h2d_bytes"] for s in st)
@@ -429,14 +489,17 @@ def main():
             "launch_ms": cl_ms,
             "note": "latency/dependency-bound greedy clustering (issue-bound in the pass-per-launch form): its figure of merit "
                     "is GHM/s, not GB/s (SURVEY 8d); traffic = dram bytes of the same launches under ncu, config 4 "
-                    "(40x the algorithmic bytes: every pass re-reads the live state of all GHMs, DESIGN.md 6)"}
+                    "(every pass re-reads the live state of the GHMs that still have work, DESIGN.md 6)"}
     ach_b = b_build / (bd_ms * 1e-3) / 1e9 if bd_ms > 0 else None
     roof_build = {"bound": "hbm", "kernel": "l2_build_kernel count + tile scan + fill (K1, level-2 launch)", "achieved": ach_b, "peak": peak,
                   "unit": "GB/s", "frac": (ach_b / peak) if ach_b else None, "traffic": None,
                   "algorithmic_bytes_per_launch": b_build, "launch_ms": bd_ms}
-    hl_stats = [s for st in all_stats for s in st[1:]]
     l2_ms = float(np.mean([s["total_ms"] for s in l2s]))
-    hl_ms = float(np.mean([s["total_ms"] for s in hl_stats])) if hl_stats else None
+    # the batched call: device time of the batch (spread over this rank's profiles in the stats), GHMs of this rank
+    hl_batch_ms = float(np.mean([sum(s["total_ms"] for s in st[1:]) for st in all_stats])) if a.profiles else None
+    hl_ghm_rank = int(np.mean([sum(s["n_ghm"] for s in st[1:]) for st in all_stats])) if a.profiles else 0
+    n_mine = len([k for k in range(a.profiles) if world == 1 or k % world == rank])
+    hl_ms = (hl_batch_ms / max(1, n_mine)) if hl_batch_ms is not None else None
 
     roof_c5 = None
     if world == 1 and not a.no_c5:
@@ -452,7 +515,7 @@ def main():
                 rr = run_reference(cfg, a.ref_profiles, ncores, td, ref_pairs)
                 cpu = {"value": rr["units"] / rr["seconds"], "unit": UNIT, "cores": ncores, "kind": rr["kind"],
                        "sample": f"{a.ref_profiles}/{a.profiles} of a step, same mix: first {rr['l2_pairs']} of {n_pairs_total} "
-                                 f"list pairs ({rr['l2_s']:.2f}s) + {a.ref_profiles} profiles x all lists = {rr['hl_ghm']} "
+                                 f"list pairs ({rr['l2_s']:.2f}s) + the first {a.ref_profiles} of the step's profiles x all lists = {rr['hl_ghm']} "
                                  f"GHMProfiles ({rr['hl_s']:.2f}s), {ncores} threads",
                        "l2_pairs_per_s": rr["l2_pairs"] / rr["l2_s"],
                        "hl_ghm_per_s": rr["hl_ghm"] / rr["hl_s"] if rr["hl_s"] > 0 else None}
@@ -468,9 +531,18 @@ def main():
             "gpu_launches": launches, "roofline": roof, "roofline_build": roof_build, "roofline_build_c5": roof_c5,
             "cpu_baseline": cpu, "wall_ms_per_step": 1e3 * wall_dt / a.steps,
             "units_per_step": units // a.steps, "l2_pairs_per_s": l2s[0]["n_ghm"] * (world if world > 1 else 1) / (l2_ms * 1e-3),
-            "hl_ghm_per_s": (hl_stats[0]["n_ghm"] * world / (hl_ms * 1e-3)) if hl_ms else None,
+            "hl_ghm_per_s": (hl_ghm_rank * (world if world > 1 else 1) / (hl_batch_ms * 1e-3)) if hl_batch_ms else None,
             "anchor_points_per_s_build": l2s[0]["n_dots"] / (bd_ms * 1e-3) if bd_ms > 0 else None,
-            "l2_call_ms": l2_ms, "hl_call_ms": hl_ms, "setup_s": setup_s}
+            "l2_call_ms": l2_ms, "hl_batch_ms": hl_batch_ms, "hl_call_ms": hl_ms, "hl_single_call_ms": hl_single_ms,
+            "hl_note": "hl_batch_ms = one iadh_profile_search_batch call over this rank's profiles of a step; hl_call_ms = "
+                       "that per profile; hl_single_call_ms = the same profiles one iadh_profile_search call at a time",
+            "setup_s": setup_s}
+    # the two kinds of GHM cost the CPU very differently (a GHMProfile ~30x a list pair): both ratios, not only the blend
+    if cpu and cpu.get("value"):
+        line["l2_ratio_vs_cpu"] = line["l2_pairs_per_s"] / cpu["l2_pairs_per_s"] if cpu.get("l2_pairs_per_s") else None
+        line["hl_ratio_vs_cpu"] = (line["hl_ghm_per_s"] / cpu["hl_ghm_per_s"]) if cpu.get("hl_ghm_per_s") and line["hl_ghm_per_s"] else None
+    if extra:
+        line["extra_configs"] = extra
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

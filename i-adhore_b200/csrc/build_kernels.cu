@@ -86,9 +86,9 @@ __device__ __forceinline__ void l2_column(const DatasetDev& ds, int xg, int x, i
 // non-masked elements of list Y (GHMProfile.cpp:25-57).  Emits every y once per orientation,
 // ascending.
 template <bool FILL>
-__device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev& pf, int x, int64_t yoff,
-                                          int ylen, int& c0, int& c1, uint32_t* __restrict__ keys, int64_t o0,
-                                          int64_t o1)
+__device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev& pf, const int16_t* __restrict__ vis, int kprof,
+                                          int x, int64_t yoff, int ylen, int& c0, int& c1, uint32_t* __restrict__ keys,
+                                          int64_t o0, int64_t o1)
 {
     const int g0 = pf.col_ptr[x], g1 = pf.col_ptr[x + 1];
     if (g0 == g1) return;
@@ -108,7 +108,8 @@ __device__ __forceinline__ void hl_column(const DatasetDev& ds, const ProfileDev
         if (best >= yend) break;
         last = best;
         const uint8_t fl = ds.flags[best];
-        if (fl & 4) continue;  // masked y elements are invisible (ListElement.cpp:25)
+        // masked y elements are invisible (ListElement.cpp:25); in a batch: masked when this profile is searched
+        if (vis ? (vis[best] <= kprof) : ((fl & 4) != 0)) continue;
         const int fy = ds.fam[best], gy = ds.gid[best], sy = fl & 1;
         bool e0 = false, e1 = false;
         for (int g = g0; g < g1; g++) {
@@ -312,12 +313,13 @@ __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf
     for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
         const int g = find_ghm(tile_prefix, n_ghm, t);
         const GhmTask task = tasks[g];
+        const ProfileDev& P = profile_of(pf, task.prof);
         const int x0 = (int)(t - tile_prefix[g]) * 32;
         const int64_t yoff = ds.list_off[task.y_list];
         const int ylen = (int)(ds.list_off[task.y_list + 1] - yoff);
         int nx;
         int64_t xoff = 0;
-        if (HL) nx = pf.L;
+        if (HL) nx = P.L;
         else {
             xoff = ds.list_off[task.x_list];
             nx = (int)(ds.list_off[task.x_list + 1] - xoff);
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf
         int c0 = 0, c1 = 0;
         if (!FILL) {
             if (x < nx) {
-                if (HL) hl_column<false>(ds, pf, x, yoff, ylen, c0, c1, nullptr, 0, 0);
+                if (HL) hl_column<false>(ds, P, pf.vis, task.prof, x, yoff, ylen, c0, c1, nullptr, 0, 0);
                 else l2_column<false>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, nullptr, 0, 0);
             }
             int t0, t1;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf
         } else {
             // pass 2: lane offsets = tile offset + exclusive scan of the recomputed lane counts
             if (x < nx) {
-                if (HL) hl_column<false>(ds, pf, x, yoff, ylen, c0, c1, nullptr, 0, 0);
+                if (HL) hl_column<false>(ds, P, pf.vis, task.prof, x, yoff, ylen, c0, c1, nullptr, 0, 0);
                 else l2_column<false>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, nullptr, 0, 0);
             }
             int t0, t1;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf
             const int64_t base1 = task.dot_off + task.cnt[0] + tile_off[2 * t + 1];
             c0 = c1 = 0;
             if (x < nx) {
-                if (HL) hl_column<true>(ds, pf, x, yoff, ylen, c0, c1, keys, base0 + e0, base1 + e1);
+                if (HL) hl_column<true>(ds, P, pf.vis, task.prof, x, yoff, ylen, c0, c1, keys, base0 + e0, base1 + e1);
                 else l2_column<true>(ds, (int)(xoff + x), x, yoff, ylen, task.x_list == task.y_list, c0, c1, keys, base0 + e0, base1 + e1);
             }
         }

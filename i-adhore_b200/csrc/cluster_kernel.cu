@@ -2839,8 +2839,19 @@ void launch_phase2_stage(GhmTask* tasks, const int* items, int n_items, int* nex
     case 3224: P2_LAUNCH(32, 24); break;
     case 128: P2_LAUNCH(128, 4); break;
     case 6412: P2_LAUNCH(64, 12); break;
+    case 6416: P2_LAUNCH(64, 16); break;
     case 64: P2_LAUNCH(64, 8); break;
-    default: P2_LAUNCH(32, 32); break;
+    default: P2_LAUNCH(32, 32); break;   // 3232 (pass_cfg_supported: nothing else gets here)
+    }
+}
+
+// the (threads, minimum CTAs per SM) pairs the pass-per-launch kernels are instantiated for, as IADH_PASS_CFG
+// codes; one table for phase 1 and phase 2 (the engine rejects anything else when the context is created)
+bool pass_cfg_supported(int code)
+{
+    switch (code) {
+    case 32: case 3224: case 3232: case 128: case 6412: case 6416: case 64: return true;
+    default: return false;
     }
 }
 
@@ -2874,7 +2885,8 @@ void launch_phase1_pass(GhmTask* tasks, const int* items, int n_items, int* next
     case 128: PASS_LAUNCH(128, 4); break;
     case 6412: PASS_LAUNCH(64, 12); break;
     case 6416: PASS_LAUNCH(64, 16); break;
-    default: PASS_LAUNCH(64, 8); break;
+    case 64: PASS_LAUNCH(64, 8); break;
+    default: PASS_LAUNCH(32, 32); break;   // 3232
     }
 }
 #endif  // IADH_HOST_EMU

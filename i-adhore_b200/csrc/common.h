@@ -45,7 +45,7 @@ struct GhmTask {
     int32_t n_mult;       // out
     int32_t n_clusters;   // out
     int32_t n_aps;        // out
-    int32_t pad1;
+    int32_t prof;         // HL batch (iadh_profile_search_batch): index of this GHM's profile; 0 otherwise
     // The two orientations are clustered by two CTAs up to the final enrichment (cluster_kernel.cu):
     int32_t half_mask;    // in: bit o = orientation o has its own queue item (>= 3 dots)
     int32_t half_needed;  // in: number of queue items of this GHM (1 or 2)
@@ -106,7 +106,19 @@ struct ProfileDev {
     const int32_t* gid;
     const int32_t* num_id;
     const uint8_t* flags;
+    // iadh_profile_search_batch: several profiles in one call.  batch[k] = descriptor of profile k (GhmTask::prof
+    // selects it; its own batch / vis fields are unused) and vis[e] = index of the first profile of the batch
+    // that sees dataset element e masked (0 = masked before the batch, 0x7fff = never): profile k sees e masked
+    // iff vis[e] <= k, which is what the same calls one after the other -- masks applied between them
+    // (higherLevel.cpp:165-171) -- would see.  Both null for a single-profile call.
+    const ProfileDev* batch;
+    const int16_t* vis;
 };
+// the profile a GHM belongs to
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline const ProfileDev& profile_of(const ProfileDev& pf, int prof) { return pf.batch ? pf.batch[prof] : pf; }
 
 struct DatasetDev {
     int n_lists;

@@ -52,6 +52,7 @@ cudaError_t launch_resident(GhmTask* tasks, const int* order, int n_tasks, int* 
                             const DevParams& prm, int pool_factor, int smem_bytes, const DatasetDev& ds, const ProfileDev& pf, bool hl,
                             int grid, int nt, cudaStream_t st, unsigned long long* dbg = nullptr);
 int resident_ctas_per_sm(int nt, int smem_bytes);
+bool pass_cfg_supported(int code);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st);
 
@@ -109,12 +110,35 @@ struct BlockCache {
         if (best < 0) return nullptr;
         void* p = blocks[best].p;
         *cap_out = blocks[best].cap;
+        (dev < 0 ? held_host : held_dev) -= blocks[best].cap;
         blocks.erase(blocks.begin() + best);
         return p;
+    }
+    // The cache is bounded (IADH_CACHE_MAX_MB, default 64 GB of device blocks and a quarter of that in pinned
+    // host blocks): a block that would push it over the bound goes back to the driver at once.
+    size_t held_dev = 0, held_host = 0;
+    static size_t limit_dev()
+    {
+        static const size_t v = getenv("IADH_CACHE_MAX_MB") ? (size_t)std::max(0, atoi(getenv("IADH_CACHE_MAX_MB"))) << 20 : (size_t)64 << 30;
+        return v;
     }
     void give(void* p, size_t cap, int dev)
     {
         std::lock_guard<std::mutex> lk(mu);
+        size_t& held = dev < 0 ? held_host : held_dev;
+        const size_t limit = dev < 0 ? limit_dev() / 4 : limit_dev();
+        if (held + cap > limit) {
+            if (dev < 0) cudaFreeHost(p);
+            else {
+                int cur = 0;
+                cudaGetDevice(&cur);
+                cudaSetDevice(dev);
+                cudaFree(p);
+                cudaSetDevice(cur);
+            }
+            return;
+        }
+        held += cap;
         blocks.push_back({p, cap, dev});
     }
     void trim()
@@ -130,6 +154,7 @@ struct BlockCache {
             }
         }
         blocks.clear();
+        held_dev = held_host = 0;
         cudaSetDevice(cur);
     }
 };
@@ -173,7 +198,7 @@ static void* efence_alloc(size_t bytes)
     CUmemGenericAllocationHandle h;
     if (f_create(&h, mapped, &prop, 0) != CUDA_SUCCESS) return nullptr;
     // IADH_EFENCE=2: guard page BEFORE the buffer instead (catches negative indices)
-    static const bool before = atoi(getenv("IADH_EFENCE")) == 2;
+    static const bool before = getenv("IADH_EFENCE") != nullptr && atoi(getenv("IADH_EFENCE")) == 2;
     const CUdeviceptr at = before ? va + gran : va;
     if (f_map(at, mapped, 0, h, 0) != CUDA_SUCCESS) return nullptr;
     CUmemAccessDesc acc = {};
@@ -268,6 +293,8 @@ struct HBuf {
 
 struct iadh_result {
     HBuf bytes;            // pinned: the device writes the packed stream straight into it (offset 4)
+    std::vector<uint8_t> owned;   // results cut out of a batch's stream (iadh_profile_search_batch) live here instead
+    iadh_ctx* owner = nullptr;    // set while the context may still hold this result's stream on the device
     size_t n_bytes = 0;
     std::vector<int32_t> ghm_index;
     iadh_stats stats;
@@ -306,6 +333,7 @@ struct iadh_ctx {
     DBuf d_items1;
     cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_call = nullptr;   // end of a call (ev[7] = its start)
     // dataset (host mirror + device)
     int n_lists = 0;
     std::vector<int64_t> list_off;
@@ -321,12 +349,31 @@ struct iadh_ctx {
     DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_items, d_prof, d_plan, d_cnt, d_outs, d_sel, d_out_off, d_out, d_counter;
     DBuf d_pf_col;  // the profile descriptor (column groups + raw arrays), one block
     HBuf h_tasks, h_misc, h_pf;
+    // multi-GPU (iadh_comm_*): NCCL communicator, loaded at run time
+    struct CommState* comm = nullptr;
+    // the packed stream of the most recent single-stream call still sits in d_out (iadh_allgather_results sends
+    // it from there instead of re-uploading the host copy)
+    const iadh_result* last_result = nullptr;
+    size_t last_result_body = 0;
+    // iadh_profile_search_batch: host copy of the profile lengths of the running batch, device staging
+    std::vector<int32_t> batch_L;
+    DBuf d_vis;
+    HBuf h_vis;
     // build_dots scratch
     std::vector<int64_t> bd_cnt;
     std::vector<int32_t> bd_dots;
     int pool_factor = 8;
     int ctas_per_sm = 4;
 };
+
+// the one result whose packed stream is still in d_out (only it carries a back pointer to the context)
+static void set_last_result(iadh_ctx* c, iadh_result* r, size_t body)
+{
+    if (c->last_result) const_cast<iadh_result*>(c->last_result)->owner = nullptr;
+    c->last_result = r;
+    c->last_result_body = body;
+    if (r) r->owner = c;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host-side scheduling (mirrors of the reference's 1-thread orders)
@@ -438,14 +485,18 @@ struct ProfileHost {
     bool valid = false;
 };
 
-// groups per profile column (see ProfileDev in common.h) + raw arrays -> device
-static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& out, int64_t& h2d)
+// column groups of a profile (see ProfileDev in common.h)
+static int profile_groups(const iadh_ctx* c, const iadh_profile_desc* p, std::vector<int32_t>& col_ptr, std::vector<int32_t>& gfam,
+                          std::vector<int32_t>& ggid, std::vector<uint8_t>& gstrand)
 {
     const int S = p->n_segments, L = p->length;
     if (S < 1 || L < 0) return fail(IADH_ERR_ARG, "bad profile shape S=%d L=%d", S, L);
     if (L > IADH_MAX_COORD) return fail(IADH_ERR_CAPACITY, "profile longer than %d columns", IADH_MAX_COORD);
-    std::vector<int32_t> col_ptr(L + 1, 0), gfam, ggid;
-    std::vector<uint8_t> gstrand;
+    if (L > 0 && (!p->gid || !p->num_id || !p->flags || (!c->pairs && !p->fam))) return fail(IADH_ERR_ARG, "profile descriptor with null arrays");
+    col_ptr.assign(L + 1, 0);
+    gfam.clear();
+    ggid.clear();
+    gstrand.clear();
     for (int x = 0; x < L; x++) {
         const size_t g0 = gfam.size();
         for (int s = 0; s < S; s++) {
@@ -467,9 +518,16 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
         }
         col_ptr[x + 1] = (int32_t)gfam.size();
     }
-    const size_t n = (size_t)S * L;
-    // one pinned staging buffer, one H2D copy (the profile is re-sent on every search)
-    const size_t G = gfam.size();
+    return IADH_OK;
+}
+
+// one profile laid out at h (host staging) / dv (the same bytes on the device); returns the bytes used
+static size_t place_profile(const iadh_ctx* c, const iadh_profile_desc* p, const std::vector<int32_t>& col_ptr,
+                            const std::vector<int32_t>& gfam, const std::vector<int32_t>& ggid, const std::vector<uint8_t>& gstrand,
+                            uint8_t* h, uint8_t* dv, ProfileDev& dev)
+{
+    const int S = p->n_segments, L = p->length;
+    const size_t n = (size_t)S * L, G = gfam.size();
     size_t o = 0;
     auto take = [&o](size_t bytes) {
         const size_t r = o;
@@ -478,38 +536,54 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
     };
     const size_t o_col = take(4 * col_ptr.size()), o_gfam = take(4 * G), o_ggid = take(4 * G), o_gstr = take(G),
                  o_fam = take(4 * n), o_gid = take(4 * n), o_num = take(4 * n), o_flg = take(n);
-    CU(c->h_pf.ensure(o + 16));
-    CU(c->d_pf_col.ensure(o + 16));
-    uint8_t* h = c->h_pf.as<uint8_t>();
-    memcpy(h + o_col, col_ptr.data(), 4 * col_ptr.size());
-    if (G) {
-        memcpy(h + o_gfam, gfam.data(), 4 * G);
-        memcpy(h + o_ggid, ggid.data(), 4 * G);
-        memcpy(h + o_gstr, gstrand.data(), G);
+    if (h) {
+        memcpy(h + o_col, col_ptr.data(), 4 * col_ptr.size());
+        if (G) {
+            memcpy(h + o_gfam, gfam.data(), 4 * G);
+            memcpy(h + o_ggid, ggid.data(), 4 * G);
+            memcpy(h + o_gstr, gstrand.data(), G);
+        }
+        if (n) {
+            if (c->pairs) {  // bucket key = gene id; ids outside the pair table have no bucket
+                int32_t* hf = (int32_t*)(h + o_fam);
+                for (size_t k = 0; k < n; k++) hf[k] = (p->gid[k] >= 0 && p->gid[k] < c->n_fam) ? p->gid[k] : -1;
+            } else
+                memcpy(h + o_fam, p->fam, 4 * n);
+            memcpy(h + o_gid, p->gid, 4 * n);
+            memcpy(h + o_num, p->num_id, 4 * n);
+            memcpy(h + o_flg, p->flags, n);
+        }
+        dev.S = S;
+        dev.L = L;
+        dev.col_ptr = (const int32_t*)(dv + o_col);
+        dev.grp_fam = (const int32_t*)(dv + o_gfam);
+        dev.grp_gid = (const int32_t*)(dv + o_ggid);
+        dev.grp_strand = dv + o_gstr;
+        dev.fam = (const int32_t*)(dv + o_fam);
+        dev.gid = (const int32_t*)(dv + o_gid);
+        dev.num_id = (const int32_t*)(dv + o_num);
+        dev.flags = dv + o_flg;
+        dev.batch = nullptr;
+        dev.vis = nullptr;
     }
-    if (n) {
-        if (c->pairs) {  // bucket key = gene id; ids outside the pair table have no bucket
-            int32_t* hf = (int32_t*)(h + o_fam);
-            for (size_t k = 0; k < n; k++) hf[k] = (p->gid[k] >= 0 && p->gid[k] < c->n_fam) ? p->gid[k] : -1;
-        } else
-            memcpy(h + o_fam, p->fam, 4 * n);
-        memcpy(h + o_gid, p->gid, 4 * n);
-        memcpy(h + o_num, p->num_id, 4 * n);
-        memcpy(h + o_flg, p->flags, n);
-    }
-    CU(cudaMemcpyAsync(c->d_pf_col.p, h, o, cudaMemcpyHostToDevice, c->st));
-    h2d += (int64_t)o;
-    uint8_t* dv = c->d_pf_col.as<uint8_t>();
-    out.dev.S = S;
-    out.dev.L = L;
-    out.dev.col_ptr = (const int32_t*)(dv + o_col);
-    out.dev.grp_fam = (const int32_t*)(dv + o_gfam);
-    out.dev.grp_gid = (const int32_t*)(dv + o_ggid);
-    out.dev.grp_strand = dv + o_gstr;
-    out.dev.fam = (const int32_t*)(dv + o_fam);
-    out.dev.gid = (const int32_t*)(dv + o_gid);
-    out.dev.num_id = (const int32_t*)(dv + o_num);
-    out.dev.flags = dv + o_flg;
+    return o;
+}
+
+// groups per profile column + raw arrays -> device (one pinned staging buffer, one H2D copy: the profile is
+// re-sent on every search)
+static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& out, int64_t& h2d)
+{
+    std::vector<int32_t> col_ptr, gfam, ggid;
+    std::vector<uint8_t> gstrand;
+    int rc = profile_groups(c, p, col_ptr, gfam, ggid, gstrand);
+    if (rc) return rc;
+    ProfileDev dummy;
+    const size_t bytes = place_profile(c, p, col_ptr, gfam, ggid, gstrand, nullptr, nullptr, dummy);
+    CU(c->h_pf.ensure(bytes + 16));
+    CU(c->d_pf_col.ensure(bytes + 16));
+    place_profile(c, p, col_ptr, gfam, ggid, gstrand, c->h_pf.as<uint8_t>(), c->d_pf_col.as<uint8_t>(), out.dev);
+    CU(cudaMemcpyAsync(c->d_pf_col.p, c->h_pf.p, bytes, cudaMemcpyHostToDevice, c->st));
+    h2d += (int64_t)bytes;
     out.valid = true;
     return IADH_OK;
 }
@@ -615,7 +689,8 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     const int n = (int)tasks.size();
     std::vector<int64_t> tile_prefix(n + 1, 0);
     for (int i = 0; i < n; i++) {
-        const int64_t nx = hl ? pf.L : (c->list_off[tasks[i].x_list + 1] - c->list_off[tasks[i].x_list]);
+        // (a batch of profiles: pf.batch is a device pointer, the lengths come from the host copy)
+        const int64_t nx = hl ? (pf.batch ? c->batch_L[tasks[i].prof] : pf.L) : (c->list_off[tasks[i].x_list + 1] - c->list_off[tasks[i].x_list]);
         tile_prefix[i + 1] = tile_prefix[i] + (nx + 31) / 32;
     }
     const int64_t n_tiles = tile_prefix[n];
@@ -669,6 +744,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
 // the whole pipeline for a batch of GHMs (tasks[i].seq == i on entry)
 static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<GhmTask>& tasks, BatchOut& out)
 {
+    set_last_result(c, nullptr, 0);   // (d_out is about to be overwritten)
     iadh_stats& st = out.st;
     const int n = (int)tasks.size();
     CU(cudaEventRecord(c->ev[0], c->st));
@@ -716,6 +792,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             t.half_needed = 1;
             if (D < (int64_t)c->prm.anchor_points || D == 0) continue;
             if (D > 0x0fffffff) return fail(IADH_ERR_CAPACITY, "GHM with %lld dots exceeds the per-GHM limit", (long long)D);
+            if (!ws_pool_fits(D, pool_factor))
+                return fail(IADH_ERR_CAPACITY, "GHM with %lld dots: anchor-point pool at factor %d exceeds 2^31 entries", (long long)D, pool_factor);
             const WsLayout L = ws_layout((int)D, pool_factor);
             t.ws_off = (int64_t)ws_total;
             t.ws_bytes = (int64_t)L.total;
@@ -949,6 +1027,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                             st.kernel_launches += 1;
                             pmark();
                         }
+                    CU(cudaGetLastError());
                     const int* it2 = ord + chunk_k[ch];
                     const int n2 = chunk_k[ch + 1] - chunk_k[ch];
                     const int grid2 = std::min(n2, c->sm_count * c->pass_per_sm);
@@ -959,6 +1038,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                         st.kernel_launches += 1;
                         pmark();
                     }
+                    CU(cudaGetLastError());
                 }
                 if (pass_timing && !pev.empty()) {
                     cudaEventSynchronize(pev.back());
@@ -1189,9 +1269,7 @@ static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, 
         t.area = (xs[i] == ys[i]) ? (unsigned)(nx * (nx - 1) / 2) : (unsigned)(nx * ny);
         t.seq = (int32_t)i;
     }
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    cudaEvent_t e0 = c->ev[7], e1 = c->ev_call;
     CU(cudaEventRecord(e0, c->st));
     BatchOut b;
     memset(&b.st, 0, sizeof b.st);
@@ -1270,9 +1348,8 @@ static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, 
             b.st.cluster_ms = m3;
         }
         *out = make_result(b);
+        set_last_result(c, was_split ? nullptr : *out, (*out)->n_bytes - 4);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return rc;
 }
 
@@ -1282,6 +1359,13 @@ __global__ void omxn_kernel(const double* x, const int* n, long long count, doub
     if (i < count) out[i] = mode ? cm::pow_ref(x[i], n[i]) : cm::omxn(x[i], n[i]);
 }
 
+// No exception crosses the C boundary: the host vectors of a call can throw (bad_alloc, length_error)
+#define IADH_TRY try {
+#define IADH_CATCH                                                                                   \
+    }                                                                                                \
+    catch (const std::bad_alloc&) { return fail(IADH_ERR_CAPACITY, "out of host memory"); }          \
+    catch (const std::exception& e_) { return fail(IADH_ERR_ARG, "exception: %s", e_.what()); }
+
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -1290,11 +1374,13 @@ const char* iadh_version(void) { return "iadhore_b200 0.1 (sm_100a)"; }
 
 static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
                        int device, iadh_ctx** out);
+void iadh_destroy(iadh_ctx* ctx);
 
 int iadh_create(const iadh_dataset_desc* d, int device, iadh_ctx** out)
 {
     if (!d || (d->n_lists > 0 && !d->fam)) return fail(IADH_ERR_ARG, "iadh_create: bad dataset descriptor");
-    return create_impl(d, nullptr, nullptr, 0, device, out);
+    IADH_TRY return create_impl(d, nullptr, nullptr, 0, device, out);
+    IADH_CATCH
 }
 
 int iadh_create_pairs(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
@@ -1307,7 +1393,8 @@ int iadh_create_pairs(const iadh_dataset_desc* d, const int64_t* pair_ptr, const
     for (int64_t k = 0; k < pair_ptr[n_genes]; k++)
         if (pair_ids[k] < 0 || pair_ids[k] >= n_genes)
             return fail(IADH_ERR_ARG, "iadh_create_pairs: partner id %d out of range (%d genes)", pair_ids[k], n_genes);
-    return create_impl(d, pair_ptr, pair_ids, n_genes, device, out);
+    IADH_TRY return create_impl(d, pair_ptr, pair_ids, n_genes, device, out);
+    IADH_CATCH
 }
 
 }  // extern "C"
@@ -1326,12 +1413,21 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
     iadh_ctx* c = new iadh_ctx();
+    // every early return below releases what was built so far (streams, events, device blocks)
+    struct Guard {
+        iadh_ctx* c;
+        ~Guard()
+        {
+            if (c) iadh_destroy(c);
+        }
+    } guard{c};
     c->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaEventCreate(&c->ev_call));
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&c->user_ev[i]));
     for (int i = 0; i < 3; i++) {
         CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
@@ -1345,16 +1441,15 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     c->n_lists = d->n_lists;
     c->list_off.assign(d->list_off, d->list_off + d->n_lists + 1);
     const int64_t total = d->n_lists ? c->list_off[d->n_lists] : 0;
-    if (total >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 elements"); }
+    if (total >= 0x7fffffff) { return fail(IADH_ERR_CAPACITY, "more than 2^31 elements"); }
     c->pairs = pairs;
     // the bucket key of an element: its family, or in pairs mode its gene id
     const int32_t* key = pairs ? d->gid : d->fam;
     int max_fam = -1;
     for (int l = 0; l < d->n_lists; l++) {
         const int64_t sz = c->list_off[l + 1] - c->list_off[l];
-        if (sz < 0) { delete c; return fail(IADH_ERR_ARG, "list %d has negative size", l); }
+        if (sz < 0) { return fail(IADH_ERR_ARG, "list %d has negative size", l); }
         if (sz > IADH_MAX_COORD) {
-            delete c;
             return fail(IADH_ERR_CAPACITY,
                         "list %d has %lld remapped elements (> %d): the reference's 32-bit x*y sums overflow there "
                         "(BaseCluster.cpp:156-158), parity is undefined",
@@ -1362,8 +1457,8 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         }
     }
     for (int64_t i = 0; i < total; i++) {
-        if (key[i] < 0) { delete c; return fail(IADH_ERR_ARG, "element %lld has a negative %s id", (long long)i, pairs ? "gene" : "family"); }
-        if (pairs && key[i] >= n_genes) { delete c; return fail(IADH_ERR_ARG, "element %lld: gene id %d outside the pair table (%d genes)", (long long)i, key[i], n_genes); }
+        if (key[i] < 0) { return fail(IADH_ERR_ARG, "element %lld has a negative %s id", (long long)i, pairs ? "gene" : "family"); }
+        if (pairs && key[i] >= n_genes) { return fail(IADH_ERR_ARG, "element %lld: gene id %d outside the pair table (%d genes)", (long long)i, key[i], n_genes); }
         max_fam = std::max(max_fam, key[i]);
     }
     c->n_fam = pairs ? n_genes : max_fam + 1;
@@ -1407,7 +1502,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
             for (int64_t k = rev_ptr[key[i]]; k < rev_ptr[key[i] + 1]; k++) cnt[rev[k] + 1]++;
         for (int g = 0; g < n_genes; g++) {
             cnt[g + 1] += cnt[g];
-            if (cnt[g + 1] >= 0x7fffffff) { delete c; return fail(IADH_ERR_CAPACITY, "more than 2^31 partner positions"); }
+            if (cnt[g + 1] >= 0x7fffffff) { return fail(IADH_ERR_CAPACITY, "more than 2^31 partner positions"); }
             fam_ptr[g + 1] = (int32_t)cnt[g + 1];
         }
         members.resize((size_t)cnt[n_genes]);
@@ -1418,7 +1513,6 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         }
         for (int g = 0; g < n_genes; g++)
             if (std::adjacent_find(members.begin() + fam_ptr[g], members.begin() + fam_ptr[g + 1]) != members.begin() + fam_ptr[g + 1]) {
-                delete c;
                 return fail(IADH_ERR_ARG, "pair table lists a partner of gene %d twice", g);
             }
     }
@@ -1475,7 +1569,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
                             d->n_lists, total, c->d_fam_list.as<int32_t>(), c->st);
     }
     if (!rc && cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "dataset upload failed");
-    if (rc) { iadh_destroy(c); return rc; }
+    if (rc) return rc;
     c->ds.n_lists = c->n_lists;
     c->ds.list_off = c->d_list_off.as<int64_t>();
     c->ds.fam = c->d_fam.as<int32_t>();
@@ -1519,7 +1613,11 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
-    if (const char* e = getenv("IADH_PASS_CFG")) sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);
+    if (const char* e = getenv("IADH_PASS_CFG")) {
+        sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);
+        if (!pass_cfg_supported(c->pass_nt) || c->pass_per_sm < 1)
+            return fail(IADH_ERR_ARG, "IADH_PASS_CFG=%s: unsupported launch configuration (codes: 32 3224 3232 64 6412 6416 128)", e);
+    }
     if (const char* e = getenv("IADH_CLASSES")) {  // "min_dots:threads:ctas_per_sm,..." heaviest class first
         int n = 0;
         const char* q = e;
@@ -1536,8 +1634,67 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
         }
         if (n > 0) c->n_classes = n;
     }
+    guard.c = nullptr;
     *out = c;
     return IADH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU exchange: NCCL, looked up at run time (the library must load where NCCL is absent; a process that
+// already loaded a libnccl.so.2 -- PyTorch's -- shares that copy)
+#include <nccl.h>
+struct CommState {
+    void* lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, n = 1;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    DBuf d_meta_send, d_meta_recv, d_send, d_recv;
+    HBuf h_meta, h_stage;
+};
+static void* nccl_lib()
+{
+    static void* lib = nullptr;
+    if (lib) return lib;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return lib;
+}
+static int nccl_bind(CommState& s)
+{
+    s.lib = nccl_lib();
+    if (!s.lib) return fail(IADH_ERR_STATE, "NCCL not found (libnccl.so.2): %s", dlerror());
+    s.GetUniqueId = (decltype(s.GetUniqueId))dlsym(s.lib, "ncclGetUniqueId");
+    s.CommInitRank = (decltype(s.CommInitRank))dlsym(s.lib, "ncclCommInitRank");
+    s.AllGather = (decltype(s.AllGather))dlsym(s.lib, "ncclAllGather");
+    s.CommDestroy = (decltype(s.CommDestroy))dlsym(s.lib, "ncclCommDestroy");
+    s.GetErrorString = (decltype(s.GetErrorString))dlsym(s.lib, "ncclGetErrorString");
+    if (!s.GetUniqueId || !s.CommInitRank || !s.AllGather || !s.CommDestroy || !s.GetErrorString)
+        return fail(IADH_ERR_STATE, "libnccl.so.2 lacks an expected symbol");
+    return IADH_OK;
+}
+#define NC(s, call)                                                                                              \
+    do {                                                                                                         \
+        ncclResult_t r_ = (call);                                                                                \
+        if (r_ != ncclSuccess) return fail(IADH_ERR_CUDA, "%s failed: %s", #call, (s).GetErrorString(r_));        \
+    } while (0)
+// Communicators outlive contexts: a host program that builds a fresh context per run (cheap) must not pay
+// ncclCommInitRank (hundreds of ms) again.  Keyed by the unique id; iadh_comm_destroy ends one explicitly.
+static std::mutex g_comm_mu;
+static std::map<std::string, CommState*> g_comms;
+static void comm_release(iadh_ctx* c) { c->comm = nullptr; }   // detach only
+static void comm_destroy(CommState* s)
+{
+    if (s->comm) s->CommDestroy(s->comm);
+    DBuf* bufs[] = {&s->d_meta_send, &s->d_meta_recv, &s->d_send, &s->d_recv};
+    for (DBuf* b : bufs) b->release();
+    s->h_meta.release();
+    s->h_stage.release();
+    delete s;
 }
 
 extern "C" {
@@ -1546,16 +1703,20 @@ void iadh_destroy(iadh_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    set_last_result(c, nullptr, 0);
+    comm_release(c);
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
-                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate};
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis};
     for (DBuf* b : bufs) b->release();
     c->h_tasks.release();
     c->h_misc.release();
     c->h_pf.release();
+    c->h_vis.release();
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_call) cudaEventDestroy(c->ev_call);
     for (int i = 0; i < 4; i++)
         if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
@@ -1571,7 +1732,13 @@ void iadh_destroy(iadh_ctx* c)
     delete c;
 }
 
+static int set_params_impl(iadh_ctx* c, const iadh_params* p);
 int iadh_set_params(iadh_ctx* c, const iadh_params* p)
+{
+    IADH_TRY return set_params_impl(c, p);
+    IADH_CATCH
+}
+static int set_params_impl(iadh_ctx* c, const iadh_params* p)
 {
     if (!c || !p) return fail(IADH_ERR_ARG, "iadh_set_params: null argument");
     if (p->n_gaps < 0 || p->n_gaps > 10) return fail(IADH_ERR_ARG, "n_gaps must be 0..10");
@@ -1593,7 +1760,8 @@ int iadh_level2_pairs(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t
 {
     if (!c || !out || (n > 0 && (!xs || !ys))) return fail(IADH_ERR_ARG, "iadh_level2_pairs: null argument");
     CU(cudaSetDevice(c->device));
-    return run_l2(c, xs, ys, n, out);
+    IADH_TRY return run_l2(c, xs, ys, n, out);
+    IADH_CATCH
 }
 
 int iadh_level2_all_pairs(iadh_ctx* c, int rank, int n_ranks, iadh_result** out)
@@ -1601,12 +1769,20 @@ int iadh_level2_all_pairs(iadh_ctx* c, int rank, int n_ranks, iadh_result** out)
     if (!c || !out) return fail(IADH_ERR_ARG, "iadh_level2_all_pairs: null argument");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
     CU(cudaSetDevice(c->device));
+    IADH_TRY
     std::vector<int32_t> xs, ys;
     pair_sequence(c, rank, n_ranks, xs, ys);
     return run_l2(c, xs.data(), ys.data(), (int64_t)xs.size(), out);
+    IADH_CATCH
 }
 
+static int mask_range_impl(iadh_ctx* c, int32_t list, int32_t begin, int32_t end);
 int iadh_mask_range(iadh_ctx* c, int32_t list, int32_t begin, int32_t end)
+{
+    IADH_TRY return mask_range_impl(c, list, begin, end);
+    IADH_CATCH
+}
+static int mask_range_impl(iadh_ctx* c, int32_t list, int32_t begin, int32_t end)
 {
     if (!c) return fail(IADH_ERR_ARG, "null ctx");
     if (list < 0 || list >= c->n_lists) return fail(IADH_ERR_ARG, "mask_range: list %d out of range", list);
@@ -1625,7 +1801,13 @@ int iadh_mask_range(iadh_ctx* c, int32_t list, int32_t begin, int32_t end)
     return IADH_OK;
 }
 
+static int clear_masks_impl(iadh_ctx* c);
 int iadh_clear_masks(iadh_ctx* c)
+{
+    IADH_TRY return clear_masks_impl(c);
+    IADH_CATCH
+}
+static int clear_masks_impl(iadh_ctx* c)
 {
     if (!c) return fail(IADH_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
@@ -1638,14 +1820,19 @@ int iadh_clear_masks(iadh_ctx* c)
     return IADH_OK;
 }
 
+static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out);
 int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out)
+{
+    IADH_TRY return profile_search_impl(c, p, rank, n_ranks, out);
+    IADH_CATCH
+}
+static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out)
 {
     if (!c || !p || !out) return fail(IADH_ERR_ARG, "iadh_profile_search: null argument");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
     CU(cudaSetDevice(c->device));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    // (the context's own events: nothing to create, destroy or leak per call)
+    cudaEvent_t e0 = c->ev[7], e1 = c->ev_call;
     CU(cudaEventRecord(e0, c->st));
     BatchOut b;
     memset(&b.st, 0, sizeof b.st);
@@ -1688,16 +1875,196 @@ int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n
             b.st.cluster_ms = m3;
         }
         *out = make_result(b);
+        set_last_result(c, *out, (*out)->n_bytes - 4);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return rc;
+}
+
+__global__ void apply_vis_kernel(uint8_t* __restrict__ flags, const int16_t* __restrict__ vis, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && vis[i] != 0x7fff) flags[i] |= 4;
+}
+
+static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+                              const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out);
+int iadh_profile_search_batch(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+                              const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out)
+{
+    IADH_TRY return profile_search_batch_impl(c, profiles, n_profiles, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
+    IADH_CATCH
+}
+static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+                              const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out)
+{
+    if (!c || !out || n_profiles < 0 || (n_profiles > 0 && (!profiles || !mask_ptr)))
+        return fail(IADH_ERR_ARG, "iadh_profile_search_batch: null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
+    if (n_profiles > 0x7ffe) return fail(IADH_ERR_CAPACITY, "at most 32766 profiles per batch");
+    if (n_profiles == 0) return IADH_OK;
+    if (mask_ptr[0] != 0) return fail(IADH_ERR_ARG, "iadh_profile_search_batch: mask_ptr[0] must be 0");
+    for (int k = 0; k < n_profiles; k++) {
+        out[k] = nullptr;
+        if (mask_ptr[k + 1] < mask_ptr[k] || (mask_ptr[k + 1] > 0 && !masks)) return fail(IADH_ERR_ARG, "iadh_profile_search_batch: bad mask_ptr");
+        for (int m = mask_ptr[k]; m < mask_ptr[k + 1]; m++) {
+            const iadh_mask_range_t& r = masks[m];
+            if (r.list < 0 || r.list >= c->n_lists) return fail(IADH_ERR_ARG, "batch mask %d: list %d out of range", m, r.list);
+            const int64_t sz = c->list_off[r.list + 1] - c->list_off[r.list];
+            if (r.begin < 0 || r.end >= sz) return fail(IADH_ERR_ARG, "batch mask %d: [%d,%d] outside list of %lld", m, r.begin, r.end, (long long)sz);
+        }
+    }
+    CU(cudaSetDevice(c->device));
+    cudaEvent_t e0 = c->ev[7], e1 = c->ev_call;
+    CU(cudaEventRecord(e0, c->st));
+    const int64_t total = c->n_lists ? c->list_off[c->n_lists] : 0;
+    BatchOut b;
+    memset(&b.st, 0, sizeof b.st);
+    // mask epochs + the GHMs of every profile, as the sequential calls would see them
+    CU(c->h_vis.ensure(2 * (size_t)total + 16));
+    CU(c->d_vis.ensure(2 * (size_t)total + 16));
+    int16_t* vis = c->h_vis.as<int16_t>();
+    for (int64_t i = 0; i < total; i++) vis[i] = (c->flags[i] & 4) ? 0 : 0x7fff;
+    std::vector<int32_t> mc = c->masked_cnt, part_lists;
+    if (shard_profiles) list_partition(c, 0, 1, part_lists);
+    else list_partition(c, rank, n_ranks, part_lists);
+    std::vector<GhmTask> tasks;
+    std::vector<int> t_begin((size_t)n_profiles + 1, 0);
+    std::vector<uint8_t> mine((size_t)n_profiles, 0);
+    int n_mine = 0;
+    for (int k = 0; k < n_profiles; k++) {
+        for (int m = mask_ptr[k]; m < mask_ptr[k + 1]; m++) {
+            const iadh_mask_range_t& r = masks[m];
+            const int64_t o = c->list_off[r.list];
+            for (int64_t i = o + r.begin; i <= o + r.end; i++)
+                if (vis[i] == 0x7fff) {
+                    vis[i] = (int16_t)k;
+                    mc[r.list]++;
+                }
+        }
+        t_begin[k] = (int)tasks.size();
+        mine[k] = (!shard_profiles || k % n_ranks == rank) ? 1 : 0;
+        if (!mine[k]) continue;
+        n_mine++;
+        const iadh_profile_desc& p = profiles[k];
+        for (int32_t l : part_lists) {
+            const unsigned sz = (unsigned)(c->list_off[l + 1] - c->list_off[l]);
+            const unsigned masked = (unsigned)mc[l];
+            if (sz - masked < (unsigned)c->prm.anchor_points) continue;  // higherLevel.cpp:40-41
+            GhmTask t;
+            init_task(t);
+            t.x_list = -1;
+            t.y_list = l;
+            t.x_object_id = p.x_object_id;
+            t.y_object_id = l;
+            t.level = p.n_segments + 1;
+            t.area = (unsigned)((unsigned)p.length * (sz - masked));
+            t.prof = k;
+            t.seq = (int32_t)tasks.size();
+            tasks.push_back(t);
+        }
+    }
+    t_begin[n_profiles] = (int)tasks.size();
+    // all profiles of this rank in one staging block, followed by their descriptors
+    int rc = IADH_OK;
+    std::vector<std::vector<int32_t>> col_ptr((size_t)n_profiles), gfam((size_t)n_profiles), ggid((size_t)n_profiles);
+    std::vector<std::vector<uint8_t>> gstrand((size_t)n_profiles);
+    std::vector<size_t> p_off((size_t)n_profiles + 1, 0);
+    ProfileDev dummy;
+    c->batch_L.assign((size_t)n_profiles, 0);
+    for (int k = 0; k < n_profiles && rc == IADH_OK; k++) {
+        p_off[k + 1] = p_off[k];
+        if ((rc = profile_groups(c, &profiles[k], col_ptr[k], gfam[k], ggid[k], gstrand[k]))) break;   // (validates every descriptor)
+        c->batch_L[k] = profiles[k].length;
+        if (mine[k]) p_off[k + 1] += place_profile(c, &profiles[k], col_ptr[k], gfam[k], ggid[k], gstrand[k], nullptr, nullptr, dummy);
+    }
+    if (rc) return rc;
+    const size_t desc_off = p_off[n_profiles], blob = desc_off + sizeof(ProfileDev) * (size_t)n_profiles;
+    CU(c->h_pf.ensure(blob + 16));
+    CU(c->d_pf_col.ensure(blob + 16));
+    {
+        uint8_t* h = c->h_pf.as<uint8_t>();
+        uint8_t* dv = c->d_pf_col.as<uint8_t>();
+        ProfileDev* hd = (ProfileDev*)(h + desc_off);
+        for (int k = 0; k < n_profiles; k++) {
+            memset(&hd[k], 0, sizeof(ProfileDev));
+            if (mine[k]) place_profile(c, &profiles[k], col_ptr[k], gfam[k], ggid[k], gstrand[k], h + p_off[k], dv + p_off[k], hd[k]);
+        }
+        CU(cudaMemcpyAsync(dv, h, blob, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(c->d_vis.p, vis, 2 * (size_t)total, cudaMemcpyHostToDevice, c->st));
+        b.st.h2d_bytes += (int64_t)blob + 2 * total;
+    }
+    ProfileDev pf;
+    memset(&pf, 0, sizeof pf);
+    pf.batch = (const ProfileDev*)(c->d_pf_col.as<uint8_t>() + desc_off);
+    pf.vis = c->d_vis.as<int16_t>();
+    set_last_result(c, nullptr, 0);
+    rc = run_batch(c, true, pf, tasks, b);
+    // the masks of the whole batch now hold, as after the sequential calls
+    if (rc == IADH_OK && total > 0 && mask_ptr[n_profiles] > 0) {
+        apply_vis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->st>>>(c->d_flags.as<uint8_t>(), c->d_vis.as<int16_t>(), total);
+        for (int64_t i = 0; i < total; i++)
+            if (vis[i] != 0x7fff) c->flags[i] |= 4;
+        c->masked_cnt = mc;
+    }
+    cudaEventRecord(e1, c->st);
+    cudaEventSynchronize(e1);
+    if (rc != IADH_OK) return rc;
+    float ms = 0, m1 = 0, m2 = 0, m3 = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (!tasks.empty()) {
+        cudaEventElapsedTime(&m1, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
+    }
+    // cut the packed stream (GHMs in task order) into one result per profile
+    const uint8_t* stream = b.packed.as<uint8_t>() + 4;
+    size_t pos = 0;
+    const double share = n_mine > 0 ? 1.0 / n_mine : 0.0;
+    for (int k = 0; k < n_profiles; k++) {
+        iadh_result* r = new iadh_result();
+        memset(&r->stats, 0, sizeof r->stats);
+        size_t bytes = 0;
+        for (int t = t_begin[k]; t < t_begin[k + 1]; t++) {
+            const GhmTask& tk = b.tasks[t];
+            bytes += (size_t)tk.out_bytes * (tk.n_mult > 0 ? 1 : 0);
+            r->stats.n_dots += (int64_t)tk.cnt[0] + tk.cnt[1];
+            r->stats.n_multiplicons += tk.n_mult;
+            if (tk.n_mult > 0) {
+                r->stats.n_baseclusters += tk.n_clusters;
+                r->stats.n_anchorpoints += tk.n_aps;
+            }
+            for (int q = 0; q < tk.n_mult; q++) r->ghm_index.push_back(t - t_begin[k]);
+        }
+        r->stats.n_ghm = t_begin[k + 1] - t_begin[k];
+        r->owned.resize(bytes + 4);
+        const int32_t nm = (int32_t)r->stats.n_multiplicons;
+        memcpy(r->owned.data(), &nm, 4);
+        if (bytes) memcpy(r->owned.data() + 4, stream + pos, bytes);
+        pos += bytes;
+        r->n_bytes = bytes + 4;
+        if (mine[k]) {   // device times of the batch, spread evenly over this rank's profiles
+            r->stats.total_ms = ms * share;
+            r->stats.build_ms = (m1 + m2) * share;
+            r->stats.cluster_ms = m3 * share;
+            r->stats.h2d_bytes = (int64_t)(b.st.h2d_bytes * share);
+            r->stats.d2h_bytes = (int64_t)(b.st.d2h_bytes * share);
+        }
+        out[k] = r;
+    }
+    // launches are counted once, on the first profile this rank searched
+    for (int k = 0; k < n_profiles; k++)
+        if (mine[k]) {
+            out[k]->stats.kernel_launches = b.st.kernel_launches + (mask_ptr[n_profiles] > 0 ? 1 : 0);
+            break;
+        }
+    return IADH_OK;
 }
 
 const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n)
 {
     if (n) *n = r ? r->n_bytes : 0;
-    return r ? (const uint8_t*)r->bytes.p : nullptr;
+    if (!r) return nullptr;
+    return r->owned.empty() ? (const uint8_t*)r->bytes.p : r->owned.data();
 }
 const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n)
 {
@@ -1713,6 +2080,7 @@ int iadh_result_stats(const iadh_result* r, iadh_stats* s)
 void iadh_free_result(iadh_result* r)
 {
     if (!r) return;
+    if (r->owner && r->owner->last_result == r) set_last_result(r->owner, nullptr, 0);
     r->bytes.release();
     delete r;
 }
@@ -1726,6 +2094,200 @@ int iadh_warmup(int device)
     if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
     CU(cudaFree(0));  // creates the primary context (0.5-1 s in a fresh process)
+    return IADH_OK;
+}
+
+int iadh_comm_unique_id(uint8_t* id_out, size_t n_bytes)
+{
+    if (!id_out || n_bytes < sizeof(ncclUniqueId)) return fail(IADH_ERR_ARG, "iadh_comm_unique_id: need %zu bytes", sizeof(ncclUniqueId));
+    CommState s;
+    int rc = nccl_bind(s);
+    if (rc) return rc;
+    ncclUniqueId id;
+    NC(s, s.GetUniqueId(&id));
+    memset(id_out, 0, n_bytes);
+    memcpy(id_out, &id, sizeof id);
+    return IADH_OK;
+}
+
+int iadh_comm_init(iadh_ctx* c, const uint8_t* id, size_t n_bytes, int rank, int n_ranks)
+{
+    if (!c || !id || n_bytes < sizeof(ncclUniqueId) || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(IADH_ERR_ARG, "iadh_comm_init: bad argument");
+    CU(cudaSetDevice(c->device));
+    comm_release(c);
+    const std::string key((const char*)id, sizeof(ncclUniqueId));
+    {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        auto it = g_comms.find(key);
+        if (it != g_comms.end()) {
+            if (it->second->rank != rank || it->second->n != n_ranks)
+                return fail(IADH_ERR_ARG, "iadh_comm_init: this id was joined as rank %d/%d", it->second->rank, it->second->n);
+            c->comm = it->second;
+            return IADH_OK;
+        }
+    }
+    CommState* s = new CommState();
+    int rc = nccl_bind(*s);
+    if (rc) {
+        delete s;
+        return rc;
+    }
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    const ncclResult_t r = s->CommInitRank(&s->comm, n_ranks, uid, rank);
+    if (r != ncclSuccess) {
+        rc = fail(IADH_ERR_CUDA, "ncclCommInitRank failed: %s", s->GetErrorString(r));
+        delete s;
+        return rc;
+    }
+    s->rank = rank;
+    s->n = n_ranks;
+    c->comm = s;
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    g_comms[key] = s;
+    return IADH_OK;
+}
+
+int iadh_comm_destroy(iadh_ctx* c)
+{
+    if (!c) return fail(IADH_ERR_ARG, "null ctx");
+    cudaSetDevice(c->device);
+    CommState* s = c->comm;
+    c->comm = nullptr;
+    if (s) {
+        cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        for (auto it = g_comms.begin(); it != g_comms.end(); ++it)
+            if (it->second == s) {
+                g_comms.erase(it);
+                break;
+            }
+        comm_destroy(s);
+    }
+    return IADH_OK;
+}
+
+// per result and rank: body bytes, multiplicons, GHMs, dots
+static const int META = 4;
+
+static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t n, iadh_result** all);
+int iadh_allgather_results(iadh_ctx* c, iadh_result* const* mine, int32_t n, iadh_result** all)
+{
+    IADH_TRY return allgather_results_impl(c, mine, n, all);
+    IADH_CATCH
+}
+static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t n, iadh_result** all)
+{
+    if (!c || !mine || !all || n < 0) return fail(IADH_ERR_ARG, "iadh_allgather_results: bad argument");
+    if (!c->comm) return fail(IADH_ERR_STATE, "iadh_allgather_results: no communicator (iadh_comm_init)");
+    if (n == 0) return IADH_OK;
+    for (int i = 0; i < n; i++) {
+        if (!mine[i]) return fail(IADH_ERR_ARG, "iadh_allgather_results: null result %d", i);
+        all[i] = nullptr;
+    }
+    CU(cudaSetDevice(c->device));
+    CommState& s = *c->comm;
+    const int N = s.n;
+    // 1. sizes of every rank's streams
+    CU(s.h_meta.ensure(8 * (size_t)META * n * (N + 1)));
+    CU(s.d_meta_send.ensure(8 * (size_t)META * n));
+    CU(s.d_meta_recv.ensure(8 * (size_t)META * n * N));
+    int64_t* hm = s.h_meta.as<int64_t>();
+    int64_t my_total = 0;
+    for (int i = 0; i < n; i++) {
+        hm[META * i] = (int64_t)mine[i]->n_bytes - 4;
+        hm[META * i + 1] = mine[i]->stats.n_multiplicons;
+        hm[META * i + 2] = mine[i]->stats.n_ghm;
+        hm[META * i + 3] = mine[i]->stats.n_dots;
+        my_total += hm[META * i];
+    }
+    CU(cudaMemcpyAsync(s.d_meta_send.p, hm, 8 * (size_t)META * n, cudaMemcpyHostToDevice, c->st));
+    NC(s, s.AllGather(s.d_meta_send.p, s.d_meta_recv.p, 8 * (size_t)META * n, ncclChar, s.comm, c->st));
+    int64_t* ha = hm + (size_t)META * n;
+    CU(cudaMemcpyAsync(ha, s.d_meta_recv.p, 8 * (size_t)META * n * N, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    std::vector<int64_t> tot((size_t)N, 0);
+    int64_t max_tot = 0;
+    for (int r = 0; r < N; r++) {
+        for (int i = 0; i < n; i++) tot[r] += ha[((size_t)r * n + i) * META];
+        max_tot = std::max(max_tot, tot[r]);
+    }
+    // 2. payload: this rank's bodies back to back, padded to the longest rank (NCCL gathers equal slots)
+    const size_t slot = (size_t)((max_tot + 15) & ~(int64_t)15);
+    if (slot > 0) {
+        const void* send = nullptr;
+        if (n == 1 && c->last_result == mine[0] && c->last_result_body == (size_t)my_total && c->d_out.cap >= slot)
+            send = c->d_out.p;   // still on the device: no re-upload (bytes past the body are padding)
+        else {
+            CU(s.d_send.ensure(slot));
+            size_t o = 0;
+            for (int i = 0; i < n; i++) {
+                size_t nb = 0;
+                const uint8_t* p = iadh_result_bytes(mine[i], &nb);
+                if (nb > 4) CU(cudaMemcpyAsync((uint8_t*)s.d_send.p + o, p + 4, nb - 4, cudaMemcpyHostToDevice, c->st));
+                o += nb - 4;
+            }
+            send = s.d_send.p;
+        }
+        CU(s.d_recv.ensure(slot * (size_t)N));
+        NC(s, s.AllGather(send, s.d_recv.p, slot, ncclChar, s.comm, c->st));
+    }
+    // 3. results: for every i the bodies of rank 0, 1, ... in rank order behind the summed count
+    if (n == 1) {
+        iadh_result* r = new iadh_result();
+        memset(&r->stats, 0, sizeof r->stats);
+        int64_t bytes = 0;
+        for (int k = 0; k < N; k++) bytes += tot[k];
+        if (r->bytes.ensure((size_t)bytes + 4) != cudaSuccess) {
+            delete r;
+            return fail(IADH_ERR_CUDA, "out of pinned host memory");
+        }
+        size_t o = 4;
+        for (int k = 0; k < N; k++) {
+            if (tot[k]) CU(cudaMemcpyAsync(r->bytes.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
+            o += (size_t)tot[k];
+            r->stats.n_multiplicons += ha[(size_t)k * META + 1];
+            r->stats.n_ghm += ha[(size_t)k * META + 2];
+            r->stats.n_dots += ha[(size_t)k * META + 3];
+        }
+        CU(cudaStreamSynchronize(c->st));
+        const int32_t nm = (int32_t)r->stats.n_multiplicons;
+        memcpy(r->bytes.p, &nm, 4);
+        r->n_bytes = (size_t)bytes + 4;
+        r->stats.d2h_bytes = bytes;
+        all[0] = r;
+        return IADH_OK;
+    }
+    if (slot > 0) {
+        CU(s.h_stage.ensure(slot * (size_t)N));
+        for (int k = 0; k < N; k++)
+            if (tot[k]) CU(cudaMemcpyAsync(s.h_stage.as<uint8_t>() + slot * (size_t)k, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    std::vector<size_t> cur((size_t)N, 0);
+    for (int i = 0; i < n; i++) {
+        iadh_result* r = new iadh_result();
+        memset(&r->stats, 0, sizeof r->stats);
+        size_t bytes = 0;
+        for (int k = 0; k < N; k++) bytes += (size_t)ha[((size_t)k * n + i) * META];
+        r->owned.resize(bytes + 4);
+        size_t o = 4;
+        for (int k = 0; k < N; k++) {
+            const int64_t* m = ha + ((size_t)k * n + i) * META;
+            if (m[0]) memcpy(r->owned.data() + o, s.h_stage.as<uint8_t>() + slot * (size_t)k + cur[k], (size_t)m[0]);
+            o += (size_t)m[0];
+            cur[k] += (size_t)m[0];
+            r->stats.n_multiplicons += m[1];
+            r->stats.n_ghm += m[2];
+            r->stats.n_dots += m[3];
+        }
+        const int32_t nm = (int32_t)r->stats.n_multiplicons;
+        memcpy(r->owned.data(), &nm, 4);
+        r->n_bytes = bytes + 4;
+        r->stats.d2h_bytes = (int64_t)bytes;
+        all[i] = r;
+    }
     return IADH_OK;
 }
 
@@ -1748,10 +2310,18 @@ int iadh_event_elapsed_ms(iadh_ctx* c, int from_slot, int to_slot, double* ms)
     return IADH_OK;
 }
 
+static int build_dots_impl(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out);
 int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
                     const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)
 {
-    if (!c || !ys || !cnt_out || !dots_out || !n_dots_out || (!p && !xs)) return fail(IADH_ERR_ARG, "iadh_build_dots: null argument");
+    IADH_TRY return build_dots_impl(c, p, xs, ys, n, cnt_out, dots_out, n_dots_out);
+    IADH_CATCH
+}
+static int build_dots_impl(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    const int64_t** cnt_out, const int32_t** dots_out, int64_t* n_dots_out)
+{
+    if (!c || !ys || !cnt_out || !dots_out || !n_dots_out || (!p && !xs) || n < 0) return fail(IADH_ERR_ARG, "iadh_build_dots: bad argument");
     CU(cudaSetDevice(c->device));
     ProfileHost ph;
     memset(&ph.dev, 0, sizeof ph.dev);
@@ -1790,7 +2360,15 @@ int iadh_build_dots(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, 
     return IADH_OK;
 }
 
+static int build_only_impl(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    iadh_stats* out);
 int iadh_build_only(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
+                    iadh_stats* out)
+{
+    IADH_TRY return build_only_impl(c, p, xs, ys, n, out);
+    IADH_CATCH
+}
+static int build_only_impl(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, const int32_t* ys, int64_t n,
                     iadh_stats* out)
 {
     if (!c || !ys || !out || (!p && !xs) || n < 0) return fail(IADH_ERR_ARG, "iadh_build_only: bad argument");
@@ -1824,7 +2402,13 @@ int iadh_build_only(iadh_ctx* c, const iadh_profile_desc* p, const int32_t* xs, 
     return IADH_OK;
 }
 
+static int remap_tandems_impl(const iadh_dataset_desc* d, int32_t tandem_gap, int device, uint8_t* remapped_out);
 int iadh_remap_tandems(const iadh_dataset_desc* d, int32_t tandem_gap, int device, uint8_t* remapped_out)
+{
+    IADH_TRY return remap_tandems_impl(d, tandem_gap, device, remapped_out);
+    IADH_CATCH
+}
+static int remap_tandems_impl(const iadh_dataset_desc* d, int32_t tandem_gap, int device, uint8_t* remapped_out)
 {
     if (!d || !remapped_out || d->n_lists < 0 || tandem_gap < 0 || (d->n_lists > 0 && (!d->list_off || !d->fam || !d->gid || !d->flags)))
         return fail(IADH_ERR_ARG, "iadh_remap_tandems: bad argument");
@@ -1866,7 +2450,13 @@ int iadh_remap_tandems(const iadh_dataset_desc* d, int32_t tandem_gap, int devic
     return rc;
 }
 
+static int plan_lists_impl(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out);
 int iadh_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out)
+{
+    IADH_TRY return plan_lists_impl(sizes, n_lists, rank, n_ranks, out, n_out);
+    IADH_CATCH
+}
+static int plan_lists_impl(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out, int64_t* n_out)
 {
     if (!sizes || !out || !n_out || n_lists < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
         return fail(IADH_ERR_ARG, "iadh_plan_lists: bad argument");
@@ -1879,7 +2469,15 @@ int iadh_plan_lists(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks
     return IADH_OK;
 }
 
+static int plan_pairs_impl(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x, int32_t* out_y,
+                    int64_t* n_out);
 int iadh_plan_pairs(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x, int32_t* out_y,
+                    int64_t* n_out)
+{
+    IADH_TRY return plan_pairs_impl(sizes, n_lists, rank, n_ranks, out_x, out_y, n_out);
+    IADH_CATCH
+}
+static int plan_pairs_impl(const int64_t* sizes, int32_t n_lists, int rank, int n_ranks, int32_t* out_x, int32_t* out_y,
                     int64_t* n_out)
 {
     if (!sizes || !out_x || !out_y || !n_out || n_lists < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
@@ -1908,19 +2506,25 @@ static int math_hook(iadh_ctx* c, const double* x, const int32_t* n, int64_t cou
     if (!c || !x || !n || !out || count < 0) return fail(IADH_ERR_ARG, "iadh_omxn/iadh_pow: bad argument");
     if (count == 0) return IADH_OK;
     CU(cudaSetDevice(c->device));
-    double *dx, *dout;
-    int* dn;
-    CU(cudaMalloc(&dx, 8 * count));
-    CU(cudaMalloc(&dout, 8 * count));
-    CU(cudaMalloc(&dn, 4 * count));
-    CU(cudaMemcpyAsync(dx, x, 8 * count, cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(dn, n, 4 * count, cudaMemcpyHostToDevice, c->st));
-    omxn_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(dx, dn, count, dout, mode);
-    CU(cudaMemcpyAsync(out, dout, 8 * count, cudaMemcpyDeviceToHost, c->st));
+    // (three cached blocks, released on every path)
+    struct Tmp {
+        DBuf x, out, n;
+        ~Tmp()
+        {
+            x.release();
+            out.release();
+            n.release();
+        }
+    } t;
+    CU(t.x.ensure(8 * (size_t)count));
+    CU(t.out.ensure(8 * (size_t)count));
+    CU(t.n.ensure(4 * (size_t)count));
+    CU(cudaMemcpyAsync(t.x.p, x, 8 * (size_t)count, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.n.p, n, 4 * (size_t)count, cudaMemcpyHostToDevice, c->st));
+    omxn_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->st>>>(t.x.as<double>(), t.n.as<int>(), count, t.out.as<double>(), mode);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, t.out.p, 8 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
-    cudaFree(dx);
-    cudaFree(dout);
-    cudaFree(dn);
     return IADH_OK;
 }
 

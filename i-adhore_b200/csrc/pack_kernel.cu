@@ -54,13 +54,14 @@ __device__ __forceinline__ void put_ap(uint8_t* q, int gx, int gy, int x, int y,
 template <bool HL>
 __global__ void __launch_bounds__(PT) pack_write_kernel(const GhmTask* tasks, const int* __restrict__ sel,
                                                         const int64_t* __restrict__ out_off, int n_sel, uint8_t* ws,
-                                                        DatasetDev ds, ProfileDev pf, int pool_factor,
+                                                        DatasetDev ds, ProfileDev pf_call, int pool_factor,
                                                         uint8_t* __restrict__ out)
 {
     __shared__ PGhm p;
     __shared__ uint32_t stage[PW][140];  // per warp: 32 x 17 bytes + alignment slack
     if (blockIdx.x >= n_sel) return;
     const GhmTask& task = tasks[sel[blockIdx.x]];
+    const ProfileDev& pf = profile_of(pf_call, task.prof);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         pghm_init(p, task, ws, pool_factor);

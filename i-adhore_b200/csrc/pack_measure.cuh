@@ -60,8 +60,9 @@ __device__ __forceinline__ bool seg_match(const DatasetDev& ds, const ProfileDev
 // whole CTA (any block size that is a multiple of 32); `p` = one shared PGhm of the CTA, its array
 // pointers and n_mult set by the caller (the GHM's global workspace, or the resident kernel's shared memory)
 template <bool HL>
-__device__ void measure_core(PGhm& p, GhmTask& task, const DatasetDev& ds, const ProfileDev& pf)
+__device__ void measure_core(PGhm& p, GhmTask& task, const DatasetDev& ds, const ProfileDev& pf_call)
 {
+    const ProfileDev& pf = profile_of(pf_call, task.prof);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, PW = blockDim.x >> 5;
     if (tid == 0) {
         int n = 0, sbase = 0;

@@ -29,7 +29,8 @@ static inline WsLayout ws_layout(int D, int pool_factor)
     };
     const size_t d = (size_t)D;
     L.cl_cap = D / 3 + 4;   // two regions of D_o / 3 + 2 slots (one per orientation)
-    L.pool_cap = pool_factor * D + 64;
+    // (callers reject GHMs whose pool would not fit an int: ws_pool_fits below)
+    L.pool_cap = (int)((long long)pool_factor * D + 64);
     int tc = 1;
     while (tc < D) tc <<= 1;
     L.tmp_cap = tc;
@@ -71,6 +72,9 @@ static inline WsLayout ws_layout(int D, int pool_factor)
 //   * the pool is 2 D entries (tight block capacities + compaction) instead of 8 D;
 //   * dscr is a fixed chunk (the ordered sums are accumulated chunk by chunk);
 //   * the two orientations are clustered one after the other by the same CTA: act / xr / ... are shared.
+// pool_cap, ClusterRec::off and ::cap are 32-bit: a (GHM, pool factor) pair is usable only below that
+static inline bool ws_pool_fits(long long D, int pool_factor) { return (long long)pool_factor * D + 64 <= 0x7fffffffll; }
+
 struct RsLayout {
     uint32_t key0, key1, alive0, alive1, nxt, tmp, tmpf, pool, pflag, cl, bc0, bc1, act, act_next, changed, mult, out_mults, rb_d, rb_j,
         rank, pos, redo, xr, dscr;

@@ -53,7 +53,8 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["remap_tandems", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
-           "clear_masks", "profile_search", "result_bytes", "result_ghm_index", "result_stats",
+           "clear_masks", "profile_search", "profile_search_batch", "comm_unique_id", "comm_init", "comm_destroy",
+           "allgather_results", "result_bytes", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
@@ -254,6 +255,44 @@ class Engine:
         res = C.c_void_p()
         self._chk(self._f("profile_search")(self.ctx, C.byref(d), C.c_int(rank), C.c_int(n_ranks), C.byref(res)))
         return self._take(res)
+
+    def profile_search_batch(self, profiles: Sequence[Profile], masks: Sequence[Sequence[Tuple[int, int, int]]],
+                             rank: int = 0, n_ranks: int = 1, shard_profiles: bool = False) -> List[Result]:
+        """iadh_profile_search_batch: masks[k] = (list, begin, end) ranges applied before profile k."""
+        n = len(profiles)
+        descs = (ProfileDesc * max(1, n))()
+        keep = []
+        for k, p in enumerate(profiles):
+            d, kp = self._pdesc(p)
+            descs[k] = d
+            keep.append(kp)
+        flat = [m for ms in masks for m in ms]
+        marr = np.ascontiguousarray(np.array(flat, dtype=np.int32).reshape(-1, 3))
+        mptr = np.zeros(n + 1, np.int32)
+        mptr[1:] = np.cumsum([len(ms) for ms in masks])
+        outs = (C.c_void_p * max(1, n))()
+        self._chk(self._f("profile_search_batch")(self.ctx, descs, C.c_int32(n), marr.ctypes.data_as(C.c_void_p),
+                                                   _p(mptr, C.c_int32), C.c_int(rank), C.c_int(n_ranks),
+                                                   C.c_int(1 if shard_profiles else 0), outs))
+        return [self._take(C.c_void_p(outs[k])) for k in range(n)]
+
+    # multi-GPU exchange (iadh_comm_*): rank 0 makes the id, every rank joins with the same id
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._chk(self._f("comm_unique_id")(buf, C.c_size_t(128)))
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._chk(self._f("comm_init")(self.ctx, buf, C.c_size_t(128), C.c_int(rank), C.c_int(n_ranks)))
+
+    def allgather(self, results: Sequence[Result]) -> List[Result]:
+        """iadh_allgather_results: every rank's streams in rank order, per result."""
+        n = len(results)
+        mine = (C.c_void_p * max(1, n))(*[r._res for r in results])
+        outs = (C.c_void_p * max(1, n))()
+        self._chk(self._f("allgather_results")(self.ctx, mine, C.c_int32(n), outs))
+        return [self._take(C.c_void_p(outs[k])) for k in range(n)]
 
     def build_dots(self, xs: Sequence[int], ys: Sequence[int], profile: Optional[Profile] = None):
         """-> list of (dots_o0 [n,2], dots_o1 [n,2]) per GHM."""

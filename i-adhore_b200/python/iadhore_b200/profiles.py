@@ -63,3 +63,39 @@ def simple_profile(ds: capi.Dataset, xl: int, yl: int, m: capi.PMultiplicon) -> 
             st = int(ds.flags[off + e] & 1)
             flg[k] = (st ^ 1) if flip else st  # inverted y-segments carry flipped strands (GeneList.cpp:270-281)
     return capi.Profile(2, L, xl, fam, gid, nid, flg)
+
+
+def load_reference_profiles(ds: capi.Dataset, path: str, limit: int = -1):
+    """The reference's own aligned profiles of a bench workload (tools/make_ref_profiles.py: dumped by
+    oracle/_ref/ref_harness --dump-profiles), in the order the reference searches them.
+    -> [(masks, Profile)], masks = [(list, begin, end)] applied before that profile (higherLevel.cpp:165-171).
+    Elements are identified by ListElement::getNumID(), which the ingest mirror reproduces."""
+    import gzip
+    import struct
+    raw = gzip.open(path, "rb").read()
+    by_num = np.full(int(ds.num_id.max()) + 1, -1, np.int64)
+    by_num[ds.num_id] = np.arange(len(ds.num_id))
+    out = []
+    off = 0
+    rec = np.dtype([("num", "<i4"), ("o", "u1")])
+    while off < len(raw) and (limit < 0 or len(out) < limit):
+        (nm,) = struct.unpack_from("<i", raw, off)
+        off += 4
+        masks = []
+        for _ in range(nm):
+            masks.append(struct.unpack_from("<iii", raw, off))
+            off += 12
+        S, L, xid = struct.unpack_from("<iii", raw, off)
+        off += 12
+        e = np.frombuffer(raw, dtype=rec, count=S * L, offset=off)
+        off += 5 * S * L
+        gap = e["num"] < 0
+        idx = by_num[np.where(gap, 0, e["num"])]
+        if np.any(idx[~gap] < 0):
+            raise ValueError("profile element not in the dataset (numID mismatch)")
+        fam = np.where(gap, -1, ds.fam[idx]).astype(np.int32)
+        gid = np.where(gap, -1, ds.gid[idx]).astype(np.int32)
+        nid = np.where(gap, -1, e["num"]).astype(np.int32)
+        flg = np.where(gap, capi.F_GAP, e["o"] & 1).astype(np.uint8)
+        out.append((masks, capi.Profile(S, L, xid, fam, gid, nid, flg)))
+    return out

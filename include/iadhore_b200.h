@@ -153,6 +153,41 @@ int iadh_clear_masks(iadh_ctx* ctx);
 int iadh_profile_search(iadh_ctx* ctx, const iadh_profile_desc* profile, int rank, int n_ranks,
                         iadh_result** out);
 
+/* Replaces: K consecutive iterations of the search half of DataSet::profileDetection (higherLevel.cpp:124-186:
+ * mask the multiplicon's segments :165-171, then profileSearch :178) in one call -- the batched / speculative
+ * path of SURVEY.md section 7 ("hard part 2").  Exactly equivalent to
+ *     for k in 0 .. n_profiles-1:
+ *         for m in mask_ptr[k] .. mask_ptr[k+1]-1:  iadh_mask_range(ctx, masks[m].list, masks[m].begin, masks[m].end)
+ *         iadh_profile_search(ctx, &profiles[k], rank, n_ranks, &out[k])
+ * (profile k sees the masks of sets 0..k and of earlier calls; afterwards all sets are applied to the context),
+ * but every profile x list GHM of the batch is built and clustered in the same kernel launches, so the fixed
+ * cost and the critical path of a search (one heavy GHM on one CTA) are paid once per batch, not per profile.
+ * shard_profiles != 0: instead of sharding the lists of every profile over the ranks (parallel.cpp:96-156),
+ * profile k is searched against ALL lists by rank k % n_ranks; the other ranks get an empty result for it.
+ * A caller that speculates (profiles built before the results of earlier searches are known) keeps out[k] only
+ * while the masks it assumed for k are the masks the reference's loop would have applied. */
+typedef struct {
+    int32_t list, begin, end;   /* GeneList::mask(begin, end) of list `list`, inclusive (GeneList.cpp:283-287) */
+} iadh_mask_range_t;
+int iadh_profile_search_batch(iadh_ctx* ctx, const iadh_profile_desc* profiles, int32_t n_profiles,
+                              const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank, int n_ranks,
+                              int shard_profiles, iadh_result** out);
+
+/* Multi-GPU exchange, one process (rank) per GPU.  Replaces the MPI plumbing of the two drivers: ParToolBox
+ * (parallel.cpp:13-31: rank / size) and the exchange step MPI_Allgather + MPI_Allgatherv of the packed
+ * multiplicons (levelTwo.cpp:225-269, higherLevel.cpp:279-314), here one NCCL all-gather of sizes and one of
+ * equal padded slots over NVLink.  iadh_comm_unique_id: rank 0 makes the id (128 bytes) and hands it to the other
+ * ranks by whatever the host program has (MPI_Bcast, a file, torch.distributed); iadh_comm_init: every rank, the
+ * same id.  iadh_allgather_results: for each i in [0, n), all[i] = the streams mine[i] of rank 0, 1, ..., n_ranks-1
+ * back to back behind their summed multiplicon count -- what unpackL2Multiplicons / unpackHLMultiplicons read on
+ * every rank after the reference's gather.  A single stream that is still on the device (the result of the call
+ * just made) is sent from there; the gathered stream goes straight into the new result's pinned buffer.
+ * iadh_result_ghm_index of a gathered result is empty (GHM positions are rank-local). */
+int iadh_comm_unique_id(uint8_t* id_out, size_t n_bytes);
+int iadh_comm_init(iadh_ctx* ctx, const uint8_t* id, size_t n_bytes, int rank, int n_ranks);
+int iadh_comm_destroy(iadh_ctx* ctx);
+int iadh_allgather_results(iadh_ctx* ctx, iadh_result* const* mine, int32_t n, iadh_result** all);
+
 /* Packed stream, byte-for-byte Multiplicon::packMultiplicons (Multiplicon.cpp:242-264):
  * int32 nMultiplicons, then per multiplicon the 33-byte header, per base cluster the
  * 102-byte header (BaseCluster.cpp:751-797), per anchor point 17 bytes (AnchorPoint.h:103). */

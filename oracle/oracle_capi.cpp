@@ -298,6 +298,50 @@ int oracle_profile_search(oracle_ctx* c, const iadh_profile_desc* p, int rank, i
     return IADH_OK;
 }
 
+// iadh_profile_search_batch restated: by definition the sequential calls (higherLevel.cpp:165-178 per iteration:
+// mask the segments, then search).  shard_profiles: profile k is searched against all lists by rank k % n_ranks.
+int oracle_profile_search_batch(oracle_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+                                const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, oracle_result** out)
+{
+    for (int k = 0; k < n_profiles; k++) {
+        for (int m = mask_ptr[k]; m < mask_ptr[k + 1]; m++) {
+            const int rc = oracle_mask_range(c, masks[m].list, masks[m].begin, masks[m].end);
+            if (rc) return rc;
+        }
+        if (shard_profiles && k % n_ranks != rank) {
+            *(out + k) = run_many(c, 0, [&](size_t, GhmOut&) {});
+            continue;
+        }
+        const int rc = shard_profiles ? oracle_profile_search(c, profiles + k, 0, 1, out + k) : oracle_profile_search(c, profiles + k, rank, n_ranks, out + k);
+        if (rc) return rc;
+    }
+    return IADH_OK;
+}
+
+// The exchange of the multi-GPU product (iadh_comm_*, iadh_allgather_results) has no CPU counterpart to check:
+// the oracle is a single process.  With one rank the gathered stream is the rank's own stream, which is all
+// these entry points provide (so that host code written against the interface links against either library).
+int oracle_comm_unique_id(uint8_t* id_out, size_t n_bytes)
+{
+    if (id_out) memset(id_out, 0, n_bytes);
+    return IADH_OK;
+}
+int oracle_comm_init(oracle_ctx*, const uint8_t*, size_t, int rank, int n_ranks)
+{
+    if (rank != 0 || n_ranks != 1) { g_err = "the oracle is a single process: one rank only"; return IADH_ERR_STATE; }
+    return IADH_OK;
+}
+int oracle_comm_destroy(oracle_ctx*) { return IADH_OK; }
+int oracle_allgather_results(oracle_ctx*, oracle_result* const* mine, int32_t n, oracle_result** all)
+{
+    for (int i = 0; i < n; i++) {
+        all[i] = new oracle_result();
+        all[i]->bytes = mine[i]->bytes;
+        all[i]->stats = mine[i]->stats;
+    }
+    return IADH_OK;
+}
+
 const uint8_t* oracle_result_bytes(const oracle_result* r, size_t* n)
 {
     *n = r->bytes.size();

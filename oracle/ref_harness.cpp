@@ -9,7 +9,7 @@
 // the CUDA path.  Trace layout: see tests/trace_io.py.
 //
 // usage: ref_harness <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--max-pairs N] [--time]
-//                    [--threads T] [--no-dump]
+//                    [--threads T] [--no-dump] [--dump-profiles file]
 // With --threads the GHMs of a stage are evaluated concurrently (each thread owns its GHM,
 // exactly like the reference's work functions, DataSet.h:79,204); results are consumed in
 // sequence order, so the trace is identical to the 1-thread one.  --no-dump (or "-" as the
@@ -152,6 +152,10 @@ int main(int argc, char** argv)
         return 2;
     }
     bool doHL = true, timing = false, dump = strcmp(argv[2], "-") != 0;
+    // --dump-profiles <file>: only the aligned profiles the reference searches, in order, each preceded by the
+    // masks applied before it (bench.py replays them on the device so that both arms search the same profiles):
+    //   i32 n_masks, n_masks x (i32 list, begin, end); i32 S, L, x_object_id; S*L x (i32 numID or -1 = gap, u8 orientation)
+    FILE* profOut = NULL;
     long maxProfiles = -1, maxPairs = -1;
     int threads = 1;
     for (int i = 3; i < argc; i++) {
@@ -161,6 +165,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--max-profiles") && i + 1 < argc) maxProfiles = atol(argv[++i]);
         else if (!strcmp(argv[i], "--max-pairs") && i + 1 < argc) maxPairs = atol(argv[++i]);
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--dump-profiles") && i + 1 < argc) profOut = fopen(argv[++i], "wb");
     }
 
     ParToolBox::init(&argc, &argv);
@@ -367,6 +372,23 @@ int main(int argc, char** argv)
                         }
                     }
                 if (dump) fwrite(pb.data(), 1, pb.size(), out);
+                if (profOut) {
+                    Blob q;
+                    const bool l2m = m->getLevel() == 2;
+                    w32(q, l2m ? 2 : 1);
+                    if (l2m) { w32(q, m->getXObjectID()); w32(q, m->getBeginX()); w32(q, m->getEndX()); }
+                    w32(q, m->getYObjectID()); w32(q, m->getBeginY()); w32(q, m->getEndY());
+                    w32(q, S); w32(q, L); w32(q, segs[0]->getID());
+                    for (int s = 0; s < S; s++) {
+                        const vector<ListElement*>& e = segs[s]->getRemappedElements();
+                        for (int x = 0; x < L; x++) {
+                            if (e[x]->isGap()) { w32(q, -1); w8(q, 0); continue; }
+                            w32(q, e[x]->getNumID());
+                            w8(q, e[x]->getOrientation() ? 1 : 0);
+                        }
+                    }
+                    fwrite(q.data(), 1, q.size(), profOut);
+                }
                 nProfiles++;
 
                 // the lists searched for this profile (higherLevel.cpp:36-41)
@@ -454,6 +476,7 @@ int main(int argc, char** argv)
         fwrite(e.data(), 1, e.size(), out);
         fclose(out);
     }
+    if (profOut) fclose(profOut);
     if (timing)
         fprintf(stderr, "HL: profiles=%ld ghmprofiles=%ld build=%.6fs run=%.6fs wall=%.6fs threads=%d found=%ld\n",
                 nProfiles, nGhmp, tHLbuild, tHLrun, wallHL, threads, nFound);

@@ -32,12 +32,22 @@ CASES = {
 
 
 def main():
+    only = sys.argv[1:]
     for name, (cfg, args) in CASES.items():
+        if only and name not in only:
+            continue
         tmp = tempfile.mkdtemp(prefix="golden_")
         try:
             ini = synth.write_reference_inputs(cfg, tmp)
             out = os.path.join(tmp, "trace.bin")
+            # tiny_4g also gets the profile-only dump bench.py replays on big workloads (pins profiles.load_reference_profiles)
+            prof = os.path.join(tmp, "profiles.bin")
+            if name == "tiny_4g":
+                args = args + ["--dump-profiles", prof]
             subprocess.run([HARNESS, ini, out] + args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            if name == "tiny_4g":
+                with open(prof, "rb") as fi, gzip.GzipFile(os.path.join(HERE, name + ".profiles.bin.gz"), "wb", mtime=0) as fo:
+                    shutil.copyfileobj(fi, fo)
             dst = os.path.join(HERE, name + ".trace.gz")
             with open(out, "rb") as fi, gzip.GzipFile(dst, "wb", mtime=0) as fo:
                 shutil.copyfileobj(fi, fo)

@@ -476,3 +476,56 @@ def test_resident_kernel_variants_are_invisible(knobs, monkeypatch):
     ds, gpu, cpu = _pair(cfg, capi.MH_BONFERRONI)
     assert gpu.level2_all_pairs().bytes == cpu.level2_all_pairs().bytes
     gpu.close()
+
+
+@pytest.mark.parametrize("table_type", ["family", "pairs"])
+def test_profile_search_batch_equals_sequential_calls(table_type):
+    """iadh_profile_search_batch (K profiles, the masks of set k applied before profile k, every GHM of the
+    batch in the same launches) against the same searches one call at a time on the device AND against the
+    oracle's sequential calls; then the list-sharded and the profile-sharded forms over 3 ranks; the masks
+    left in the context afterwards are those of the sequential calls."""
+    cfg = synth.config_small(seed=91)
+    cfg.table_type = table_type
+    ds, gpu, cpu = _pair(cfg, capi.MH_BONFERRONI)
+    ms = capi.parse_packed(cpu.level2_all_pairs().bytes)
+    order = sorted(range(len(ms)), key=lambda i: -sum(len(c.aps) for c in ms[i].clusters))[:12]
+    profs = [pl.simple_profile(ds, ms[i].x_object_id, ms[i].y_object_id, ms[i]) for i in order]
+    masks = [[(ms[i].x_object_id, ms[i].bounds[0], ms[i].bounds[1]), (ms[i].y_object_id, ms[i].bounds[2], ms[i].bounds[3])]
+             for i in order]
+    masks[3] = []                       # a profile without new masks
+    masks[5] = masks[5] + masks[5]      # overlapping ranges
+    want = []
+    for p, mk in zip(profs, masks):
+        for (l, b, e) in mk:
+            cpu.mask_range(l, b, e)
+        want.append(cpu.profile_search(p))
+    assert sum(w.n_multiplicons for w in want) > 0
+    # batch on the device, all lists, one rank
+    got = gpu.profile_search_batch(profs, masks)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert capi.compare_packed(g.bytes, w.bytes, pl.P_RTOL) is None, k
+        assert np.array_equal(g.ghm_index, w.ghm_index) and g.stats["n_ghm"] == w.stats["n_ghm"], k
+    assert got[0].stats["kernel_launches"] > 0
+    # the context now holds all masks: one more sequential search sees them
+    extra = pl.simple_profile(ds, ms[order[0]].x_object_id, ms[order[0]].y_object_id, ms[order[0]])
+    assert capi.compare_packed(gpu.profile_search(extra).bytes, cpu.profile_search(extra).bytes, pl.P_RTOL) is None
+    # sequential device calls from a clean context give the same bytes as the batch
+    gpu.clear_masks()
+    for k, (p, mk) in enumerate(zip(profs, masks)):
+        for (l, b, e) in mk:
+            gpu.mask_range(l, b, e)
+        assert gpu.profile_search(p).bytes == got[k].bytes, k
+    # sharded over 3 ranks: by lists (each rank's part of every profile) and by profiles (whole profiles round-robin)
+    for shard_profiles in (False, True):
+        for rank in range(3):
+            gpu.clear_masks()
+            cpu.clear_masks()
+            a = gpu.profile_search_batch(profs, masks, rank, 3, shard_profiles)
+            b = cpu.profile_search_batch(profs, masks, rank, 3, shard_profiles)
+            for k in range(len(profs)):
+                assert capi.compare_packed(a[k].bytes, b[k].bytes, pl.P_RTOL) is None, (shard_profiles, rank, k)
+                if shard_profiles:
+                    assert (a[k].stats["n_ghm"] > 0) == (k % 3 == rank)
+                    if k % 3 == rank:
+                        assert a[k].bytes == got[k].bytes
+    gpu.close()

@@ -89,3 +89,30 @@ def test_oracle_tandem_remap_matches_python_mirror_on_tandem_rich_lists():
     want = np.concatenate([ingest.remap_tandems_family(fam[a:b].tolist(), gid[a:b].tolist(), strand[a:b].astype(bool).tolist(),
                                                         cfg.tandem_gap) for a, b in zip(off[:-1], off[1:])])
     assert got.sum() > 100 and np.array_equal(got, want)
+
+
+def test_reference_profile_dump_loads_to_the_trace_profiles():
+    """profiles.load_reference_profiles (what bench.py replays on the device: the reference's own aligned
+    profiles, dumped by ref_harness --dump-profiles) against the profile / mask events of the full trace of
+    the same reference run."""
+    import os
+    import parity_lib as pl
+    from iadhore_b200 import profiles
+    from trace_io import read_trace
+    tr = read_trace(os.path.join(pl.GOLDEN, "tiny_4g.trace.gz"))
+    got = profiles.load_reference_profiles(tr.dataset, os.path.join(pl.GOLDEN, "tiny_4g.profiles.bin.gz"))
+    want, masks = [], []
+    for ev in tr.events:
+        if ev[0] == "mask":
+            masks.append((ev[1], ev[2], ev[3]))
+        elif ev[0] == "profile":
+            want.append((masks, ev[1]))
+            masks = []
+    assert len(got) == len(want) >= 20
+    for (gm, gp), (wm, wp) in zip(got, want):
+        assert [tuple(m) for m in gm] == wm
+        assert (gp.S, gp.L, gp.x_object_id) == (wp.S, wp.L, wp.x_object_id)
+        gap = (np.asarray(wp.flags) & 2) != 0
+        assert np.array_equal(np.asarray(gp.flags), np.asarray(wp.flags))
+        for k in ("fam", "gid", "num_id"):
+            assert np.array_equal(np.asarray(getattr(gp, k))[~gap], np.asarray(getattr(wp, k))[~gap]), k
