@@ -215,11 +215,13 @@ def hot_path_step(eng, profs, rank, n_ranks):
     eng.clear_masks()
     r = eng.level2_all_pairs(rank, n_ranks)
     stats = [r.stats]
+    final = [r]
     if n_ranks > 1:
-        eng.allgather([r])
+        final = eng.allgather([r])
     res = eng.profile_search_batch([p for _, p in profs], [m for m, _ in profs], rank, n_ranks, shard_profiles=n_ranks > 1)
-    if n_ranks > 1:
-        eng.allgather(res)
+    final += eng.allgather(res) if n_ranks > 1 else res
+    for x in final:      # every stream of the step on the host (the copies overlap the calls made after them)
+        x.wait()
     stats += [x.stats for x in res]
     units = sum(s["n_ghm"] for s in stats)
     launches = sum(s["kernel_launches"] for s in stats)

@@ -81,7 +81,7 @@ static double g_t_last = 0;
 static void trace_mark(cudaStream_t st, const char* label)
 {
     if (!g_trace) return;
-    const cudaError_t se = cudaStreamSynchronize(st);
+    const cudaError_t se = st ? cudaStreamSynchronize(st) : cudaSuccess;   // (null: host-only mark, the device keeps running)
     if (se != cudaSuccess) fprintf(stderr, "[iadh] !! %s after stage '%s'\n", cudaGetErrorString(se), label ? label : "(start)");
     const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     if (label) fprintf(stderr, "[iadh] %-28s %8.3f ms\n", label, (now - g_t_last) * 1e3);
@@ -295,6 +295,9 @@ struct iadh_result {
     HBuf bytes;            // pinned: the device writes the packed stream straight into it (offset 4)
     std::vector<uint8_t> owned;   // results cut out of a batch's stream (iadh_profile_search_batch) live here instead
     iadh_ctx* owner = nullptr;    // set while the context may still hold this result's stream on the device
+    // The device-to-host copy of the stream runs on the context's copy stream and overlaps whatever the caller does
+    // next (the next call's kernels included); iadh_result_bytes waits for it.  null = nothing in flight.
+    mutable cudaEvent_t ready = nullptr;
     size_t n_bytes = 0;
     std::vector<int32_t> ghm_index;
     iadh_stats stats;
@@ -334,6 +337,12 @@ struct iadh_ctx {
     cudaEvent_t user_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // iadh_event_record slots
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_call = nullptr;   // end of a call (ev[7] = its start)
+    // result copies: their own stream, so that a packed stream travels to the host while the next call computes;
+    // ev_packed = the writer finished (copy may start), ev_copied = the last copy finished (d_out / the gather's
+    // receive buffer may be overwritten)
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;
     // dataset (host mirror + device)
     int n_lists = 0;
     std::vector<int64_t> list_off;
@@ -348,13 +357,17 @@ struct iadh_ctx {
     // per-call buffers
     DBuf d_tasks, d_tile_prefix, d_tile_cnt, d_tile_off, d_dots, d_ws, d_items, d_prof, d_plan, d_cnt, d_outs, d_sel, d_out_off, d_out, d_counter;
     DBuf d_pf_col;  // the profile descriptor (column groups + raw arrays), one block
-    HBuf h_tasks, h_misc, h_pf;
+    HBuf h_tasks, h_misc, h_pf, h_init;
+    DBuf d_init;
     // multi-GPU (iadh_comm_*): NCCL communicator, loaded at run time
     struct CommState* comm = nullptr;
     // the packed stream of the most recent single-stream call still sits in d_out (iadh_allgather_results sends
     // it from there instead of re-uploading the host copy)
     const iadh_result* last_result = nullptr;
     size_t last_result_body = 0;
+    // same for a batch (iadh_profile_search_batch): its results' streams lie back to back in d_out
+    std::vector<const iadh_result*> last_batch;
+    size_t last_batch_body = 0;
     // iadh_profile_search_batch: host copy of the profile lengths of the running batch, device staging
     std::vector<int32_t> batch_L;
     DBuf d_vis;
@@ -370,6 +383,9 @@ struct iadh_ctx {
 static void set_last_result(iadh_ctx* c, iadh_result* r, size_t body)
 {
     if (c->last_result) const_cast<iadh_result*>(c->last_result)->owner = nullptr;
+    for (const iadh_result* b : c->last_batch) const_cast<iadh_result*>(b)->owner = nullptr;
+    c->last_batch.clear();
+    c->last_batch_body = 0;
     c->last_result = r;
     c->last_result_body = body;
     if (r) r->owner = c;
@@ -594,9 +610,22 @@ struct BatchOut {
     std::vector<GhmTask> tasks;  // final state (cnt, n_mult, out_bytes ...)
     HBuf packed;                 // pinned: int32 count + concatenated per-GHM blocks in seq order
     size_t packed_bytes = 0;     // incl. the 4-byte count
+    cudaEvent_t ready = nullptr; // the copy into `packed` runs on the context's copy stream; set when one is in flight
     std::vector<int32_t> ghm_index;
     iadh_stats st;
-    ~BatchOut() { packed.release(); }
+    void wait()
+    {
+        if (ready) {
+            cudaEventSynchronize(ready);
+            cudaEventDestroy(ready);
+            ready = nullptr;
+        }
+    }
+    ~BatchOut()
+    {
+        wait();
+        packed.release();
+    }
 };
 
 // The task records stay on the device; only the fields that change hands travel, packed:
@@ -647,6 +676,28 @@ __global__ void reset_subset_kernel(GhmTask* __restrict__ tasks, const int* __re
     t.out_bytes = 0;
     for (int o = 0; o < 2; o++) t.half_nbc[o] = t.half_ncl[o] = t.half_pool[o] = t.half_status[o] = t.half_nk[o] = t.half_g3[o] = t.half_seed[o] = 0;
 }
+// what the host knows about a GHM before the build (the rest of the device record starts as zero)
+struct TaskInit {
+    int32_t x_list, y_list, x_object_id, y_object_id, level, seq, prof, pad;
+    uint64_t area;
+};
+__global__ void init_tasks_kernel(GhmTask* __restrict__ tasks, int n, const TaskInit* __restrict__ init)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GhmTask t;
+    memset(&t, 0, sizeof t);
+    const TaskInit v = init[i];
+    t.x_list = v.x_list; t.y_list = v.y_list; t.x_object_id = v.x_object_id; t.y_object_id = v.y_object_id;
+    t.level = v.level; t.seq = v.seq; t.prof = v.prof;
+    t.area = v.area;
+    tasks[i] = t;
+}
+__global__ void scatter_dot_off_kernel(GhmTask* __restrict__ tasks, int n, const int64_t* __restrict__ dot_off)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tasks[i].dot_off = dot_off[i];
+}
 __global__ void gather_out_kernel(const GhmTask* __restrict__ tasks, int n, TaskOut* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -696,15 +747,32 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     const int64_t n_tiles = tile_prefix[n];
     int rc;
     trace_mark(c->st, "host: tile prefix");
-    if ((rc = upload(c->d_tasks, tasks.data(), sizeof(GhmTask) * (size_t)n, c->st))) return rc;
-    if ((rc = upload(c->d_tile_prefix, tile_prefix.data(), 8 * (size_t)(n + 1), c->st))) return rc;
-    st.h2d_bytes += (int64_t)sizeof(GhmTask) * n + 8 * (n + 1);
+    // the device task records are built from what the host knows (40 of their 184 bytes), through pinned staging
+    CU(c->d_tasks.ensure(sizeof(GhmTask) * (size_t)n + 16));
+    CU(c->h_init.ensure((sizeof(TaskInit) + 8) * (size_t)(n + 1)));
+    CU(c->d_init.ensure((sizeof(TaskInit) + 8) * (size_t)(n + 1)));
+    {
+        TaskInit* hi = c->h_init.as<TaskInit>();
+        for (int i = 0; i < n; i++) {
+            const GhmTask& t = tasks[i];
+            hi[i].x_list = t.x_list; hi[i].y_list = t.y_list; hi[i].x_object_id = t.x_object_id; hi[i].y_object_id = t.y_object_id;
+            hi[i].level = t.level; hi[i].seq = t.seq; hi[i].prof = t.prof; hi[i].pad = 0;
+            hi[i].area = t.area;
+        }
+        int64_t* hp = (int64_t*)(hi + n);
+        memcpy(hp, tile_prefix.data(), 8 * (size_t)(n + 1));
+        CU(cudaMemcpyAsync(c->d_init.p, hi, sizeof(TaskInit) * (size_t)n + 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
+        init_tasks_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_init.as<TaskInit>());
+        st.kernel_launches += 1;
+    }
+    const int64_t* d_tile_prefix = (const int64_t*)(c->d_init.as<TaskInit>() + n);
+    st.h2d_bytes += (int64_t)sizeof(TaskInit) * n + 8 * (n + 1);
     CU(c->d_tile_cnt.ensure(8 * (size_t)n_tiles + 16));
     CU(c->d_tile_off.ensure(8 * (size_t)n_tiles + 16));
     CU(cudaEventRecord(c->ev[1], c->st));
-    launch_build_count(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
+    launch_build_count(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
                        c->d_tile_cnt.as<uint32_t>(), c->sm_count, c->st);
-    launch_tile_scan(c->d_tile_prefix.as<int64_t>(), n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
+    launch_tile_scan(d_tile_prefix, n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
     CU(cudaEventRecord(c->ev[2], c->st));
     trace_mark(c->st, "K1 count + tile scan");
     st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
@@ -713,6 +781,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     gather_cnt_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_cnt.as<uint32_t>());
     CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; the counts are read next)
+    trace_mark(c->st, "counts D2H");
     st.d2h_bytes += 8 * (int64_t)n;
     st.kernel_launches += 1;
     total_dots = 0;
@@ -727,17 +796,33 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
     }
     if (total_dots > 0x7fffffff00ll) return fail(IADH_ERR_CAPACITY, "too many dots in one call");
     CU(c->d_dots.ensure(4 * (size_t)total_dots + 16));
-    // the clustering plan depends on the counts only: it goes to the device together with dot_off,
-    // so the fill pass and the clustering follow each other without another host round trip
-    if (plan && (rc = plan(tasks))) return rc;
-    if ((rc = send_plan(c, tasks, st))) return rc;
+    trace_mark(c->st, "host: dot offsets");
+    // the fill pass needs the dot offsets only: they go first, the fill kernel starts, and the host plans the
+    // clustering stage (orders, workspaces, queue items: milliseconds for 10^5 GHMs) while it runs
+    {
+        CU(c->h_tasks.ensure(sizeof(TaskPlan) * (size_t)n + 16));   // (sized for the plan that follows)
+        CU(c->d_plan.ensure(sizeof(TaskPlan) * (size_t)n + 16));
+        int64_t* h = c->h_tasks.as<int64_t>();
+        for (int i = 0; i < n; i++) h[i] = tasks[i].dot_off;
+        CU(cudaMemcpyAsync(c->d_plan.p, h, 8 * (size_t)n, cudaMemcpyHostToDevice, c->st));
+        scatter_dot_off_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_plan.as<int64_t>());
+        st.h2d_bytes += 8 * (int64_t)n;
+        st.kernel_launches += 1;
+    }
     CU(cudaEventRecord(c->ev[3], c->st));
-    launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, c->d_tile_prefix.as<int64_t>(), n_tiles,
+    launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
                       c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
     CU(cudaEventRecord(c->ev[4], c->st));
-    trace_mark(c->st, "K1 fill (+tasks D2H/H2D)");
     st.kernel_launches += n_tiles ? 1 : 0;
     st.n_dots = total_dots;
+    if (plan) {
+        // (the staging buffer of the offsets is reused by the plan: the copy above must have left it)
+        if ((rc = plan(tasks))) return rc;
+        trace_mark(nullptr, "host: plan (overlaps K1 fill)");
+        CU(cudaEventSynchronize(c->ev[3]));
+        if ((rc = send_plan(c, tasks, st))) return rc;
+    }
+    trace_mark(c->st, "K1 fill + plan H2D / scatter");
     return IADH_OK;
 }
 
@@ -761,6 +846,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     // the count pass and the fill pass (inside build_stage) and travels to the device with dot_off
     int pool_factor = c->pool_factor;
     std::vector<int> order, items, items1, chunk_k, chunk_i1;
+    std::vector<uint32_t> dcnt;
     size_t ws_total = 0;
     bool pass_mode = false;
     int n_act = 0;
@@ -779,8 +865,11 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         ws_total = 0;
         // active GHMs: at least anchor_points dots (GHM.cpp:159), heaviest first
         order.clear();
+        dcnt.resize(2 * (size_t)n);   // the sort keys, compact (the task records are 184 bytes apart)
         for (int i = 0; i < n; i++) {
             GhmTask& t = tasks[i];
+            dcnt[2 * (size_t)i] = t.cnt[0];
+            dcnt[2 * (size_t)i + 1] = t.cnt[1];
             const int64_t D = (int64_t)t.cnt[0] + t.cnt[1];
             t.status = 0;
             t.n_mult = t.n_clusters = t.n_aps = 0;
@@ -803,7 +892,9 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             t.half_needed = 1;
             order.push_back(i);
         }
-        sort_desc_stable(order, [&tasks](int a) { return (uint64_t)tasks[a].cnt[0] + tasks[a].cnt[1]; });
+        trace_mark(nullptr, "  plan: workspaces");
+        sort_desc_stable(order, [this_dcnt = dcnt.data()](int a) { return (uint64_t)this_dcnt[2 * (size_t)a] + this_dcnt[2 * (size_t)a + 1]; });
+        trace_mark(nullptr, "  plan: order");
         order_all = order;
         // split off the GHMs of the resident path; `order` keeps the rest (global-memory kernels below)
         res_launches.clear();
@@ -885,7 +976,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             chunk_k.push_back(n_act);
             chunk_i1.push_back((int)items1.size());
             if (chunk_k.size() == 2)  // one chunk: heaviest orientation first over the whole batch
-                sort_desc_stable(items1, [&tasks](int a) { return (uint64_t)tasks[a >> 1].cnt[a & 1]; });
+                sort_desc_stable(items1, [this_dcnt = dcnt.data()](int a) { return (uint64_t)this_dcnt[a]; });
         }
         for (int k = 0; k < n_act && !pass_mode; k++) {
             GhmTask& t = tasks[order[k]];
@@ -899,9 +990,11 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 t.half_needed = 1;
             }
         }
+        trace_mark(nullptr, "  plan: queue items");
         // too much for one go: the caller bisects the batch (the count pass that led here is cheap)
         if ((int64_t)ws_total > c->ws_budget && n > 1 && !hl) return RC_SPLIT;
         CU(c->d_ws.ensure(ws_total + 256));
+        trace_mark(nullptr, "  plan: workspace buffer");
         return IADH_OK;
     };
     if ((rc = build_stage(c, hl, pf, tasks, total_dots, st, make_plan))) return rc;
@@ -1095,6 +1188,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
         CU(cudaMemcpyAsync(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        trace_mark(c->st, "outcomes D2H");
         st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
         st.kernel_launches += 1;
         {
@@ -1191,22 +1285,37 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             out_off.push_back(total_bytes);
             total_bytes += tasks[i].out_bytes;
         }
+    trace_mark(c->st, "host: sizes -> offsets");
     CU(out.packed.ensure((size_t)total_bytes + 4));
+    trace_mark(c->st, "host: pinned result buffer");
     out.packed_bytes = (size_t)total_bytes + 4;
     if (!sel.empty()) {
         if ((rc = upload(c->d_sel, sel.data(), 4 * sel.size(), c->st))) return rc;
         if ((rc = upload(c->d_out_off, out_off.data(), 8 * out_off.size(), c->st))) return rc;
+        if (c->copy_pending) {   // the previous result may still be travelling out of d_out
+            if ((size_t)total_bytes + 16 > c->d_out.cap) CU(cudaEventSynchronize(c->ev_copied));   // (ensure() would hand the block on)
+            else CU(cudaStreamWaitEvent(c->st, c->ev_copied, 0));
+        }
         CU(c->d_out.ensure((size_t)total_bytes + 16));
         launch_pack_write(hl, c->d_tasks.as<GhmTask>(), c->d_sel.as<int>(), c->d_out_off.as<int64_t>(), (int)sel.size(),
                           c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
         st.kernel_launches += 1;
         trace_mark(c->st, "K3 write");
-        CU(cudaMemcpyAsync(out.packed.as<uint8_t>() + 4, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st));
+        // the copy to the host runs on the copy stream: the caller's next call computes meanwhile
+        CU(cudaEventRecord(c->ev_packed, c->st));
+        CU(cudaStreamWaitEvent(c->st_copy, c->ev_packed, 0));
+        CU(cudaMemcpyAsync(out.packed.as<uint8_t>() + 4, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st_copy));
+        CU(cudaEventRecord(c->ev_copied, c->st_copy));
+        CU(cudaEventCreateWithFlags(&out.ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(out.ready, c->st_copy));
+        c->copy_pending = true;
         st.h2d_bytes += 12 * (int64_t)sel.size();
         st.d2h_bytes += total_bytes;
     }
-    CU(cudaStreamSynchronize(c->st));
-    trace_mark(c->st, "result D2H");
+    if (g_trace) {
+        out.wait();
+        trace_mark(c->st, "result D2H");
+    }
     for (int i : sel)
         for (int k = 0; k < tasks[i].n_mult; k++) out.ghm_index.push_back(tasks[i].seq);
     st.n_ghm = n;
@@ -1217,7 +1326,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             st.n_anchorpoints += tasks[i].n_aps;
         }
     }
-    out.tasks = tasks;
+    out.tasks.swap(tasks);   // (the caller's vector is not used after the call)
     trace_mark(c->st, "host: collect");
     return IADH_OK;
 }
@@ -1228,6 +1337,8 @@ static iadh_result* make_result(BatchOut& b)
     const int32_t total = (int32_t)b.st.n_multiplicons;
     memcpy(b.packed.p, &total, 4);
     std::swap(r->bytes, b.packed);
+    r->ready = b.ready;
+    b.ready = nullptr;
     r->n_bytes = b.packed_bytes;
     r->ghm_index.swap(b.ghm_index);
     r->stats = b.st;
@@ -1317,6 +1428,7 @@ static int run_l2(iadh_ctx* c, const int32_t* xs, const int32_t* ys, int64_t n, 
             cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
             acc_build += m1 + m2;
             acc_cluster += m3;
+            pb.wait();
             bytes.insert(bytes.end(), pb.packed.as<uint8_t>() + 4, pb.packed.as<uint8_t>() + pb.packed_bytes);
             for (int32_t gidx : pb.ghm_index) b.ghm_index.push_back(gidx + (int32_t)r.first);
             b.st.n_ghm += pb.st.n_ghm; b.st.n_dots += pb.st.n_dots; b.st.n_multiplicons += pb.st.n_multiplicons;
@@ -1428,6 +1540,9 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
     CU(cudaEventCreate(&c->ev_call));
+    CU(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&c->user_ev[i]));
     for (int i = 0; i < 3; i++) {
         CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
@@ -1653,7 +1768,7 @@ struct CommState {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     DBuf d_meta_send, d_meta_recv, d_send, d_recv;
-    HBuf h_meta, h_stage;
+    HBuf h_meta, h_stage, h_recv;
 };
 static void* nccl_lib()
 {
@@ -1694,6 +1809,7 @@ static void comm_destroy(CommState* s)
     for (DBuf* b : bufs) b->release();
     s->h_meta.release();
     s->h_stage.release();
+    s->h_recv.release();
     delete s;
 }
 
@@ -1708,15 +1824,22 @@ void iadh_destroy(iadh_ctx* c)
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
-                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis};
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis, &c->d_init};
     for (DBuf* b : bufs) b->release();
     c->h_tasks.release();
     c->h_misc.release();
     c->h_pf.release();
     c->h_vis.release();
+    c->h_init.release();
     for (int i = 0; i < 8; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_call) cudaEventDestroy(c->ev_call);
+    if (c->st_copy) {
+        cudaStreamSynchronize(c->st_copy);
+        cudaStreamDestroy(c->st_copy);
+    }
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     for (int i = 0; i < 4; i++)
         if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
@@ -2017,6 +2140,7 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
         cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
     }
     // cut the packed stream (GHMs in task order) into one result per profile
+    b.wait();
     const uint8_t* stream = b.packed.as<uint8_t>() + 4;
     size_t pos = 0;
     const double share = n_mine > 0 ? 1.0 / n_mine : 0.0;
@@ -2051,6 +2175,12 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
         }
         out[k] = r;
     }
+    // the batch's stream is still in d_out, its results in order: iadh_allgather_results sends it from there
+    for (int k = 0; k < n_profiles; k++) {
+        c->last_batch.push_back(out[k]);
+        out[k]->owner = c;
+    }
+    c->last_batch_body = pos;
     // launches are counted once, on the first profile this rank searched
     for (int k = 0; k < n_profiles; k++)
         if (mine[k]) {
@@ -2064,8 +2194,14 @@ const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n)
 {
     if (n) *n = r ? r->n_bytes : 0;
     if (!r) return nullptr;
+    if (r->ready) {   // the stream may still be on its way to the host
+        cudaEventSynchronize(r->ready);
+        cudaEventDestroy(r->ready);
+        r->ready = nullptr;
+    }
     return r->owned.empty() ? (const uint8_t*)r->bytes.p : r->owned.data();
 }
+size_t iadh_result_size(const iadh_result* r) { return r ? r->n_bytes : 0; }
 const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n)
 {
     if (n) *n = r ? r->ghm_index.size() : 0;
@@ -2080,7 +2216,12 @@ int iadh_result_stats(const iadh_result* r, iadh_stats* s)
 void iadh_free_result(iadh_result* r)
 {
     if (!r) return;
-    if (r->owner && r->owner->last_result == r) set_last_result(r->owner, nullptr, 0);
+    if (r->owner) set_last_result(r->owner, nullptr, 0);   // (it, or the batch it belongs to, is no longer "the last one")
+    if (r->ready) {   // the pinned buffer goes back to the cache: the copy into it must be over
+        cudaEventSynchronize(r->ready);
+        cudaEventDestroy(r->ready);
+        r->ready = nullptr;
+    }
     r->bytes.release();
     delete r;
 }
@@ -2215,19 +2356,28 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
     }
     // 2. payload: this rank's bodies back to back, padded to the longest rank (NCCL gathers equal slots)
     const size_t slot = (size_t)((max_tot + 15) & ~(int64_t)15);
+    if (c->copy_pending) CU(cudaEventSynchronize(c->ev_copied));   // an earlier gather may still be reading the receive buffer
     if (slot > 0) {
         const void* send = nullptr;
-        if (n == 1 && c->last_result == mine[0] && c->last_result_body == (size_t)my_total && c->d_out.cap >= slot)
+        bool on_device = (n == 1 && c->last_result == mine[0] && c->last_result_body == (size_t)my_total);
+        if (!on_device && (size_t)n == c->last_batch.size() && c->last_batch_body == (size_t)my_total) {
+            on_device = true;
+            for (int i = 0; i < n; i++) on_device = on_device && c->last_batch[i] == mine[i];
+        }
+        if (on_device && c->d_out.cap >= slot)
             send = c->d_out.p;   // still on the device: no re-upload (bytes past the body are padding)
         else {
+            // one pinned staging block, one copy (the results' own buffers may be pageable)
             CU(s.d_send.ensure(slot));
+            CU(s.h_stage.ensure(slot));
             size_t o = 0;
             for (int i = 0; i < n; i++) {
                 size_t nb = 0;
                 const uint8_t* p = iadh_result_bytes(mine[i], &nb);
-                if (nb > 4) CU(cudaMemcpyAsync((uint8_t*)s.d_send.p + o, p + 4, nb - 4, cudaMemcpyHostToDevice, c->st));
+                if (nb > 4) memcpy(s.h_stage.as<uint8_t>() + o, p + 4, nb - 4);
                 o += nb - 4;
             }
+            if (o) CU(cudaMemcpyAsync(s.d_send.p, s.h_stage.p, o, cudaMemcpyHostToDevice, c->st));
             send = s.d_send.p;
         }
         CU(s.d_recv.ensure(slot * (size_t)N));
@@ -2244,14 +2394,20 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
             return fail(IADH_ERR_CUDA, "out of pinned host memory");
         }
         size_t o = 4;
+        CU(cudaEventRecord(c->ev_packed, c->st));
+        CU(cudaStreamWaitEvent(c->st_copy, c->ev_packed, 0));
         for (int k = 0; k < N; k++) {
-            if (tot[k]) CU(cudaMemcpyAsync(r->bytes.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
+            if (tot[k]) CU(cudaMemcpyAsync(r->bytes.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st_copy));
             o += (size_t)tot[k];
             r->stats.n_multiplicons += ha[(size_t)k * META + 1];
             r->stats.n_ghm += ha[(size_t)k * META + 2];
             r->stats.n_dots += ha[(size_t)k * META + 3];
         }
-        CU(cudaStreamSynchronize(c->st));
+        // (on the copy stream: the gathered stream reaches the host while the next call computes)
+        CU(cudaEventRecord(c->ev_copied, c->st_copy));
+        CU(cudaEventCreateWithFlags(&r->ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(r->ready, c->st_copy));
+        c->copy_pending = true;
         const int32_t nm = (int32_t)r->stats.n_multiplicons;
         memcpy(r->bytes.p, &nm, 4);
         r->n_bytes = (size_t)bytes + 4;
@@ -2260,9 +2416,9 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
         return IADH_OK;
     }
     if (slot > 0) {
-        CU(s.h_stage.ensure(slot * (size_t)N));
+        CU(s.h_recv.ensure(slot * (size_t)N));
         for (int k = 0; k < N; k++)
-            if (tot[k]) CU(cudaMemcpyAsync(s.h_stage.as<uint8_t>() + slot * (size_t)k, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
+            if (tot[k]) CU(cudaMemcpyAsync(s.h_recv.as<uint8_t>() + slot * (size_t)k, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
     }
     std::vector<size_t> cur((size_t)N, 0);
@@ -2275,7 +2431,7 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
         size_t o = 4;
         for (int k = 0; k < N; k++) {
             const int64_t* m = ha + ((size_t)k * n + i) * META;
-            if (m[0]) memcpy(r->owned.data() + o, s.h_stage.as<uint8_t>() + slot * (size_t)k + cur[k], (size_t)m[0]);
+            if (m[0]) memcpy(r->owned.data() + o, s.h_recv.as<uint8_t>() + slot * (size_t)k + cur[k], (size_t)m[0]);
             o += (size_t)m[0];
             cur[k] += (size_t)m[0];
             r->stats.n_multiplicons += m[1];

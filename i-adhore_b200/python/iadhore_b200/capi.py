@@ -54,7 +54,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["remap_tandems", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "profile_search_batch", "comm_unique_id", "comm_init", "comm_destroy",
-           "allgather_results", "result_bytes", "result_ghm_index", "result_stats",
+           "allgather_results", "result_bytes", "result_size", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
 
@@ -113,15 +113,23 @@ class Result:
     """One call's packed multiplicon stream.  The stream stays in the library's (pinned) result
     buffer until `.bytes` is first read; the C result is freed when this object dies."""
 
-    def __init__(self, owner, res, ptr, n: int, ghm_index: np.ndarray, stats: dict):
-        self._owner, self._res, self._ptr, self._n = owner, res, ptr, n
+    def __init__(self, owner, res, n: int, ghm_index: np.ndarray, stats: dict):
+        self._owner, self._res, self._ptr, self._n = owner, res, None, n
         self._bytes = None
         self.ghm_index = ghm_index
         self.stats = stats
 
+    def wait(self):
+        """Blocks until the stream is in the library's host buffer (the copy overlaps the calls made since)."""
+        if self._ptr is None and self._res is not None:
+            n = C.c_size_t()
+            self._ptr = self._owner._f("result_bytes")(self._res, C.byref(n))
+        return self
+
     @property
     def bytes(self) -> bytes:
         if self._bytes is None:
+            self.wait()
             self._bytes = C.string_at(self._ptr, self._n)
             self._release()
         return self._bytes
@@ -135,6 +143,7 @@ class Result:
         (valid while this object is alive and `.bytes` has not been materialised)."""
         if self._bytes is not None:
             return np.frombuffer(self._bytes, dtype=np.uint8)
+        self.wait()
         return np.ctypeslib.as_array(self._ptr, shape=(self._n,))
 
     @property
@@ -166,6 +175,8 @@ class Engine:
         f("last_error").restype = C.c_char_p
         f("version").restype = C.c_char_p
         f("result_bytes").restype = C.POINTER(C.c_uint8)
+        f("result_size").restype = C.c_size_t
+        f("result_size").argtypes = [C.c_void_p]
         f("result_ghm_index").restype = C.POINTER(C.c_int32)
         f("destroy").restype = None
         f("free_result").restype = None
@@ -215,14 +226,13 @@ class Engine:
         self._chk(self._f("set_params")(self.ctx, C.byref(p)))
 
     def _take(self, res) -> Result:
-        n = C.c_size_t()
-        ptr = self._f("result_bytes")(res, C.byref(n))
+        n = self._f("result_size")(res)      # (result_bytes would wait for the copy to the host)
         m = C.c_size_t()
         gp = self._f("result_ghm_index")(res, C.byref(m))
         gi = np.ctypeslib.as_array(gp, shape=(m.value,)).copy() if m.value else np.zeros(0, np.int32)
         st = Stats()
         self._chk(self._f("result_stats")(res, C.byref(st)))
-        return Result(self, res, ptr, n.value, gi, st.as_dict())
+        return Result(self, res, int(n), gi, st.as_dict())
 
     def level2_all_pairs(self, rank: int = 0, n_ranks: int = 1) -> Result:
         res = C.c_void_p()

@@ -192,6 +192,10 @@ int iadh_allgather_results(iadh_ctx* ctx, iadh_result* const* mine, int32_t n, i
  * int32 nMultiplicons, then per multiplicon the 33-byte header, per base cluster the
  * 102-byte header (BaseCluster.cpp:751-797), per anchor point 17 bytes (AnchorPoint.h:103). */
 const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n_bytes);
+/* A call returns as soon as its packed stream is complete on the DEVICE; the copy into the result's pinned host
+ * buffer runs on a copy stream of the context and overlaps whatever the caller does next (the next call's kernels
+ * included).  iadh_result_bytes waits for that copy; iadh_result_size (bytes of the stream) never waits. */
+size_t iadh_result_size(const iadh_result* r);
 /* Per multiplicon: index of the GHM (position in the pair / list sequence) it came from. */
 const int32_t* iadh_result_ghm_index(const iadh_result* r, size_t* n_multiplicons);
 int iadh_result_stats(const iadh_result* r, iadh_stats* out);

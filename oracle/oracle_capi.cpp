@@ -347,6 +347,7 @@ const uint8_t* oracle_result_bytes(const oracle_result* r, size_t* n)
     *n = r->bytes.size();
     return r->bytes.data();
 }
+size_t oracle_result_size(const oracle_result* r) { return r->bytes.size(); }
 const int32_t* oracle_result_ghm_index(const oracle_result* r, size_t* n)
 {
     *n = r->ghm_index.size();

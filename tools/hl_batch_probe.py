@@ -20,19 +20,23 @@ def main():
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--profiles", type=int, default=32)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-seq", action="store_true")
     a = ap.parse_args()
     cfg = bench.workload_config(a.workload)
     ds = ingest.dataset_from_synth(cfg)
     eng = capi.load_product(ds)
     eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
-    r = eng.level2_all_pairs()
-    profs = bench.make_profiles(ds, r.bytes, a.profiles)
-    masks = [[(m.x_object_id, m.bounds[0], m.bounds[1]), (m.y_object_id, m.bounds[2], m.bounds[3])] for m, _ in profs]
+    bp, src = bench.bench_profiles(ds, a.workload, a.profiles, lambda: eng.level2_all_pairs().bytes)
+    print(src, file=sys.stderr)
+    profs = [(None, p) for _, p in bp]
+    masks = [m for m, _ in bp]
     for rep in range(a.reps):
         eng.clear_masks()
         t0 = time.perf_counter()
         seq = []
         for (m, p), mk in zip(profs, masks):
+            if a.no_seq:
+                break
             for (l, b, e) in mk:
                 eng.mask_range(l, b, e)
             seq.append(eng.profile_search(p))
@@ -41,7 +45,7 @@ def main():
         t2 = time.perf_counter()
         bat = eng.profile_search_batch([p for _, p in profs], masks)
         t3 = time.perf_counter()
-        same = all(x.bytes == y.bytes for x, y in zip(seq, bat))
+        same = all(x.bytes == y.bytes for x, y in zip(seq, bat)) if seq else None
         print(f"rep {rep}: sequential {1e3 * (t1 - t0):.2f} ms wall ({sum(s.stats['total_ms'] for s in seq):.2f} device), "
               f"batch {1e3 * (t3 - t2):.2f} ms wall ({sum(s.stats['total_ms'] for s in bat):.2f} device, cluster "
               f"{sum(s.stats['cluster_ms'] for s in bat):.2f}, build {sum(s.stats['build_ms'] for s in bat):.2f}), "
