@@ -15,6 +15,8 @@
 // 5*(|X|+|Y|) element bytes read + 4*D key bytes written.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "common.h"
 
 namespace {
@@ -301,6 +303,272 @@ __global__ void __launch_bounds__(256) l2_build_kernel(DatasetDev ds, GhmTask* _
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// L2, third generation, for batches of many sparse GHMs (config 4: 125,250 list pairs, ~420 dots each,
+// 2,500 columns of which five in six are empty in any one GHM).  The tile kernels above visit every
+// (GHM, column) cell -- 313 M of them for 53 M dots.  Here the work is the dots themselves:
+//  * a column (element e of list X, family f) meets every member of f's bucket once: a member in list Y is
+//    a dot of the GHM (X, Y) if the call holds that pair (pair_idx, an n_lists x n_lists table of task
+//    indices, -1 = not in this call / this rank's share); the self comparison keeps the slots before the
+//    element's own (y < x, GHM.cpp:64-68), columns with a repeated gene ID keep the exact ID test;
+//  * pass 1 counts per (GHM, orientation) with one reduction per dot, the host turns the counts into
+//    offsets (it needs them anyway, for the clustering plan), pass 2 walks again and appends each key
+//    to its GHM's orientation block through an atomic cursor -- in arbitrary order;
+//  * pass 3 sorts every block ascending in shared memory: keys are (x << 16) | y and distinct, so the sorted
+//    block IS the reference's map<int, set<int>> order, independent of the order of arrival.
+// Member records are read coalesced (groups of W lanes per column, W adapted to the mean bucket length).
+template <bool FILL>
+__global__ void __launch_bounds__(256) l2_expand_kernel(DatasetDev ds, int64_t n_elems, const int32_t* __restrict__ pair_idx,
+                                                        const uint8_t* __restrict__ row_used,
+                                                        uint32_t* __restrict__ counter /* [2n]: counts (pass 1) or cursors (pass 2) */,
+                                                        const int64_t* __restrict__ dot_off, const uint32_t* __restrict__ cnt,
+                                                        uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_tiles = (n_elems + 31) >> 5;
+    const int nl = ds.n_lists;
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
+        const int64_t e = t * 32 + lane;
+        int len = 0, b0 = 0, X = 0, self = 0, meta = 0, gx = 0, x = 0;
+        if (e < n_elems) {
+            X = ds.elem_list[e];
+            if (row_used[X]) {   // (lists that are no GHM's x list in this call have nothing to do)
+                const int f = ds.fam[e];
+                const int fl = ds.flags[e];
+                b0 = ds.fam_ptr[f];
+                len = ds.fam_ptr[f + 1] - b0;
+                const int slow = (fl & 8) ? 1 : 0;
+                self = ds.self_slot[e] + slow;          // the self comparison keeps slots < self
+                meta = (fl & 1) | (slow << 1);
+                if (slow) gx = ds.gid[e];
+                x = (int)(e - ds.list_off[X]);
+            }
+        }
+        int total;
+        warp_excl_scan(len, lane, total);
+        if (total == 0) continue;
+        int W = 1;
+        while (W < 32 && 2 * W <= (total >> 5)) W <<= 1;
+        const int R = 32 / W;
+        const int sub = lane & (W - 1), grp = lane / W;
+        for (int cb = 0; cb < 32; cb += R) {
+            const int c = cb + grp;
+            const int c_len = __shfl_sync(full, len, c);
+            if (__reduce_max_sync(full, c_len) == 0) continue;
+            const int c_b0 = __shfl_sync(full, b0, c);
+            const int c_X = __shfl_sync(full, X, c);
+            const int c_self = __shfl_sync(full, self, c);
+            const int c_meta = __shfl_sync(full, meta, c);
+            const int c_gx = __shfl_sync(full, gx, c);
+            const uint32_t xkey = (uint32_t)__shfl_sync(full, x, c) << 16;
+            const int32_t* __restrict__ row = pair_idx + (size_t)c_X * nl;
+            // two members per lane and trip: both records are in flight before either is used
+            auto emit = [&](int m, int Y, int g, uint32_t my) {
+                if (g < 0) return;
+                if (Y == c_X && m >= c_self) return;
+                if ((c_meta & 2) && ds.gid[ds.fam_members[m]] == c_gx) return;   // GHM.cpp:68
+                const int o = ((int)(my & 1u) == (c_meta & 1)) ? 1 : 0;
+                if (!FILL) atomicAdd(&counter[2 * g + o], 1u);
+                else {
+                    const uint32_t pos = atomicAdd(&counter[2 * g + o], 1u);
+                    keys[dot_off[g] + (o ? cnt[2 * g] : 0u) + pos] = xkey | (my >> 1);
+                }
+            };
+            for (int k = sub; k < c_len; k += 2 * W) {
+                const int m = c_b0 + k;
+                const bool two = k + W < c_len;
+                const int Y = ds.mem_list[m];
+                const int Y2 = two ? ds.mem_list[m + W] : 0;
+                const uint32_t my = ds.mem_y[m];
+                const uint32_t my2 = two ? ds.mem_y[m + W] : 0u;
+                const int g = row[Y];
+                const int g2 = two ? row[Y2] : -1;
+                emit(m, Y, g, my);
+                emit(m + W, Y2, g2, my2);
+            }
+        }
+    }
+}
+
+// The same for profile GHMs (family mode): the work item is a column group of a profile -- one (family, strand) of
+// one aligned column, gid = its single gene or -1 (common.h) -- which meets every member of its family's bucket once:
+// a non-masked member in list Y, not the group's own gene (Gene.cpp:20), is the dot (column, y) of the GHM
+// (profile, Y), same orientation iff the strands agree.  A column's groups of one family differ in strand, so they
+// feed different orientation blocks of a GHM: no y is produced twice (the dedupe of GHMProfile.cpp:52-55).
+// Pairs mode keeps the tile kernel (buckets of different genes overlap there).
+template <bool FILL>
+__global__ void __launch_bounds__(256) hl_expand_kernel(DatasetDev ds, const HlGroup* __restrict__ items, int n_items,
+                                                        const int32_t* __restrict__ task_idx, const int16_t* __restrict__ vis,
+                                                        uint32_t* __restrict__ counter, const int64_t* __restrict__ dot_off,
+                                                        const uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int n_tiles = (n_items + 31) >> 5;
+    const int nl = ds.n_lists;
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
+        const int it = t * 32 + lane;
+        HlGroup G;
+        G.fam = G.gid = G.prof = 0;
+        G.x_strand = 0;
+        int len = 0, b0 = 0;
+        if (it < n_items) {
+            G = items[it];
+            b0 = ds.fam_ptr[G.fam];
+            len = ds.fam_ptr[G.fam + 1] - b0;
+        }
+        int total;
+        warp_excl_scan(len, lane, total);
+        if (total == 0) continue;
+        int W = 1;
+        while (W < 32 && 2 * W <= (total >> 5)) W <<= 1;
+        const int R = 32 / W;
+        const int sub = lane & (W - 1), grp = lane / W;
+        for (int cb = 0; cb < 32; cb += R) {
+            const int c = cb + grp;
+            const int c_len = __shfl_sync(full, len, c);
+            if (__reduce_max_sync(full, c_len) == 0) continue;
+            const int c_b0 = __shfl_sync(full, b0, c);
+            const int c_gid = __shfl_sync(full, G.gid, c);
+            const int c_prof = __shfl_sync(full, G.prof, c);
+            const uint32_t c_xs = __shfl_sync(full, G.x_strand, c);
+            const uint32_t xkey = (c_xs & 0xffffu) << 16;
+            const int c_strand = (int)(c_xs >> 31);
+            const int32_t* __restrict__ row = task_idx + (size_t)c_prof * nl;
+            for (int k = sub; k < c_len; k += W) {
+                const int m = c_b0 + k;
+                const int g = row[ds.mem_list[m]];
+                if (g < 0) continue;
+                const int e = ds.fam_members[m];
+                if (vis ? (vis[e] <= c_prof) : ((ds.flags[e] & 4) != 0)) continue;   // ListElement.cpp:25
+                if (c_gid >= 0 && ds.gid[e] == c_gid) continue;                       // Gene.cpp:20
+                const uint32_t my = ds.mem_y[m];
+                const int o = ((int)(my & 1u) == c_strand) ? 1 : 0;
+                if (!FILL) atomicAdd(&counter[2 * g + o], 1u);
+                else {
+                    const uint32_t pos = atomicAdd(&counter[2 * g + o], 1u);
+                    keys[dot_off[g] + (o ? cnt[2 * g] : 0u) + pos] = xkey | (my >> 1);
+                }
+            }
+        }
+    }
+}
+
+// Ascending sort of every (GHM, orientation) key block (the engine takes this path only when the largest block
+// fits SORT_MAX keys).  Blocks of up to 1,024 keys -- all but a handful on the sparse batches this path serves --
+// are sorted by ONE WARP IN REGISTERS: the block is padded with 0xffffffff to P = 32 R keys, lane l holds the keys at
+// positions l, l + 32, ... (coalesced loads and stores); a compare-exchange at distance j >= 32 pairs two registers
+// of the same lane, at distance j < 32 the same register of lanes l and l ^ j (one shuffle).  No shared memory, no
+// barrier; the eight warps of a CTA work on different blocks.  Larger blocks: one CTA, bitonic network in shared memory.
+#define SORT_MAX 8192
+#define SORT_WARP_MAX 1024
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(uint32_t* __restrict__ kb, int n, int lane)
+{
+    uint32_t v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int p = lane + 32 * r;
+        v[r] = p < n ? kb[p] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r & jr) continue;
+                    // positions p = lane + 32 r (bit j clear) and p + j; ascending where (p & k) == 0
+                    const bool up = (((lane + 32 * r) & k) == 0);
+                    const uint32_t a = v[r], b = v[r | jr];
+                    const uint32_t lo = min(a, b), hi = max(a, b);
+                    v[r] = up ? lo : hi;
+                    v[r | jr] = up ? hi : lo;
+                }
+            } else {
+                const bool lower = ((lane & j) == 0);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint32_t w = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (((lane + 32 * r) & k) == 0);
+                    v[r] = (lower == up) ? min(v[r], w) : max(v[r], w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int p = lane + 32 * r;
+        if (p < n) kb[p] = v[r];
+    }
+}
+
+__global__ void __launch_bounds__(256) seg_sort_warp_kernel(int n_seg, const int64_t* __restrict__ dot_off,
+                                                            const uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int sg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sg < n_seg; sg += warps_total) {
+        const int n = (int)cnt[sg];
+        if (n < 2 || n > SORT_WARP_MAX) continue;
+        uint32_t* __restrict__ kb = keys + dot_off[sg >> 1] + ((sg & 1) ? cnt[sg & ~1] : 0u);
+        if (n <= 32) warp_sort_regs<1>(kb, n, lane);
+        else if (n <= 64) warp_sort_regs<2>(kb, n, lane);
+        else if (n <= 128) warp_sort_regs<4>(kb, n, lane);
+        else if (n <= 256) warp_sort_regs<8>(kb, n, lane);
+        else if (n <= 512) warp_sort_regs<16>(kb, n, lane);
+        else warp_sort_regs<32>(kb, n, lane);
+    }
+}
+
+__global__ void __launch_bounds__(256) seg_sort_cta_kernel(int n_seg, const int64_t* __restrict__ dot_off,
+                                                           const uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys)
+{
+    __shared__ uint32_t s[SORT_MAX];
+    const int tid = threadIdx.x;
+    for (int sg = blockIdx.x; sg < n_seg; sg += gridDim.x) {
+        const int n = (int)cnt[sg];
+        if (n <= SORT_WARP_MAX) continue;
+        uint32_t* __restrict__ kb = keys + dot_off[sg >> 1] + ((sg & 1) ? cnt[sg & ~1] : 0u);
+        int P = 2048;
+        while (P < n) P <<= 1;
+        __syncthreads();   // (the previous block's readers are done with s)
+        for (int i = tid; i < P; i += 256) s[i] = i < n ? kb[i] : 0xffffffffu;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < (P >> 1); i += 256) {
+                    // the i-th compare-exchange of this step: positions a < b = a + j
+                    const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                    const int b = a | j;
+                    const uint32_t va = s[a], vb = s[b];
+                    const bool up = ((a & k) == 0);
+                    if ((va > vb) == up) {
+                        s[a] = vb;
+                        s[b] = va;
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = tid; i < n; i += 256) kb[i] = s[i];
+    }
+}
+
+// task records <- compact per-GHM arrays (family-expansion path: counts were taken outside the records)
+__global__ void scatter_cnt_kernel(GhmTask* __restrict__ tasks, int n, const uint32_t* __restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        tasks[i].cnt[0] = cnt[2 * i];
+        tasks[i].cnt[1] = cnt[2 * i + 1];
+    }
+}
+
 template <bool HL, bool FILL>
 __global__ void __launch_bounds__(256) build_kernel(DatasetDev ds, ProfileDev pf, GhmTask* __restrict__ tasks,
                                                     int n_ghm, const int64_t* __restrict__ tile_prefix,
@@ -457,6 +725,51 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
     if (hl) build_kernel<true, true><<<grid, 256, 0, st>>>(ds, pf, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
     else l2_build_kernel<true><<<grid, 256, 0, st>>>(ds, tasks, n_ghm, tile_prefix, n_tiles, nullptr, tile_off, keys);
 }
+
+static void launch_seg_sort(int n_seg, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, int sm_count, cudaStream_t st)
+{
+    seg_sort_warp_kernel<<<std::min((n_seg + 7) / 8, sm_count * 16), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
+    seg_sort_cta_kernel<<<std::min(n_seg, sm_count * 4), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
+}
+
+// family-expansion path (many sparse GHMs): count / fill / sort
+void launch_expand_count(const DatasetDev& ds, int64_t n_elems, const int32_t* pair_idx, const uint8_t* row_used, uint32_t* cnt,
+                         int sm_count, cudaStream_t st)
+{
+    if (n_elems == 0) return;
+    l2_expand_kernel<false><<<grid_for((n_elems + 31) / 32, sm_count), 256, 0, st>>>(ds, n_elems, pair_idx, row_used, cnt, nullptr, nullptr, nullptr);
+}
+
+void launch_expand_fill(const DatasetDev& ds, int64_t n_elems, const int32_t* pair_idx, const uint8_t* row_used, uint32_t* cursor,
+                        const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm, int sm_count,
+                        cudaStream_t st)
+{
+    if (n_ghm == 0) return;
+    scatter_cnt_kernel<<<(n_ghm + 255) / 256, 256, 0, st>>>(tasks, n_ghm, cnt);
+    if (n_elems == 0) return;
+    l2_expand_kernel<true><<<grid_for((n_elems + 31) / 32, sm_count), 256, 0, st>>>(ds, n_elems, pair_idx, row_used, cursor, dot_off, cnt, keys);
+    const int n_seg = 2 * n_ghm;
+    launch_seg_sort(n_seg, dot_off, cnt, keys, sm_count, st);
+}
+void launch_hl_expand_count(const DatasetDev& ds, const HlGroup* items, int n_items, const int32_t* task_idx, const int16_t* vis,
+                            uint32_t* cnt, int sm_count, cudaStream_t st)
+{
+    if (n_items == 0) return;
+    hl_expand_kernel<false><<<grid_for((n_items + 31) / 32, sm_count), 256, 0, st>>>(ds, items, n_items, task_idx, vis, cnt, nullptr, nullptr, nullptr);
+}
+
+void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_items, const int32_t* task_idx, const int16_t* vis,
+                           uint32_t* cursor, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm,
+                           int sm_count, cudaStream_t st)
+{
+    if (n_ghm == 0) return;
+    scatter_cnt_kernel<<<(n_ghm + 255) / 256, 256, 0, st>>>(tasks, n_ghm, cnt);
+    if (n_items == 0) return;
+    hl_expand_kernel<true><<<grid_for((n_items + 31) / 32, sm_count), 256, 0, st>>>(ds, items, n_items, task_idx, vis, cursor, dot_off, cnt, keys);
+    const int n_seg = 2 * n_ghm;
+    launch_seg_sort(n_seg, dot_off, cnt, keys, sm_count, st);
+}
+int expand_sort_max(void) { return SORT_MAX; }
 
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st)
 {

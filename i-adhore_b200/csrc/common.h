@@ -114,6 +114,12 @@ struct ProfileDev {
     const ProfileDev* batch;
     const int16_t* vis;
 };
+// Work item of the family-expansion build of profile GHMs (build_kernels.cu): one column group of one profile.
+struct HlGroup {
+    int32_t fam, gid;      // the group's family and its single gene id (-1: several genes)
+    uint32_t x_strand;     // column | strand << 31
+    int32_t prof;          // profile of the batch (0 for a single-profile call)
+};
 // the profile a GHM belongs to
 #ifdef __CUDACC__
 __host__ __device__
@@ -133,6 +139,8 @@ struct DatasetDev {
     const uint32_t* mem_y;      // (coordinate inside its list << 1) | strand
     const int32_t* plus_prefix; // [slot] = members with strand 1 in slots [0, slot)  (n + 1 entries)
     const int32_t* self_slot;   // per element: its slot in fam_members
+    const int32_t* mem_list;    // [slot] = list of the member (family-expansion build)
+    const int32_t* elem_list;   // per element: its list
     const int32_t* fam_list;    // [f * (n_lists + 1) + l] = first slot of family f at or after list l; may be null
     // table_type=pairs (iadh_create_pairs): "family" = gene id and bucket f holds the positions of the
     // partners of gene f (Gene.cpp:24-27), so buckets overlap and an element is not in its own bucket;

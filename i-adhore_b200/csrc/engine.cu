@@ -35,6 +35,17 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
                        const int64_t* tile_prefix, int64_t n_tiles, const uint32_t* tile_off, uint32_t* keys,
                        int sm_count, cudaStream_t st);
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st);
+void launch_expand_count(const DatasetDev& ds, int64_t n_elems, const int32_t* pair_idx, const uint8_t* row_used, uint32_t* cnt,
+                         int sm_count, cudaStream_t st);
+void launch_expand_fill(const DatasetDev& ds, int64_t n_elems, const int32_t* pair_idx, const uint8_t* row_used, uint32_t* cursor,
+                        const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm, int sm_count,
+                        cudaStream_t st);
+void launch_hl_expand_count(const DatasetDev& ds, const HlGroup* items, int n_items, const int32_t* task_idx, const int16_t* vis,
+                            uint32_t* cnt, int sm_count, cudaStream_t st);
+void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_items, const int32_t* task_idx, const int16_t* vis,
+                           uint32_t* cursor, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm,
+                           int sm_count, cudaStream_t st);
+int expand_sort_max(void);
 void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64_t* list_off, int n_fam, int n_lists,
                      int64_t total, int32_t* table, cudaStream_t st);
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
@@ -317,6 +328,13 @@ struct iadh_ctx {
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
+    // K1 family-expansion path (build_kernels.cu, third generation): level-2 batches of at least this many GHMs
+    int expand_min = 1024;
+    int hl_expand_min = 16;            // the same for profile GHMs (family mode): calls of at least this many GHMProfiles
+    std::vector<HlGroup> hl_items;     // column groups of the running call's profiles
+    int expand_sort_max = 0;   // 0 = the sort kernel's capacity (test knob: smaller values exercise the fall-back)
+    std::vector<int32_t> h_pair_idx;   // (x list, y list) -> task of the running call
+    std::vector<uint8_t> h_row_used;
     // a batch whose clustering workspace would exceed this is bisected (level-2 calls): set from the
     // device's memory at create time, IADH_WS_BUDGET_MB overrides
     int64_t ws_budget = (int64_t)1 << 62;
@@ -352,6 +370,7 @@ struct iadh_ctx {
     int n_fam = 0;
     bool pairs = false;   // table_type=pairs (iadh_create_pairs): families are gene ids, buckets hold partners
     DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members, d_mem_y, d_plus_prefix, d_self_slot, d_fam_list;
+    DBuf d_mem_list, d_elem_list, d_pair_idx, d_row_used, d_cur, d_hl_items;
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
@@ -537,6 +556,23 @@ static int profile_groups(const iadh_ctx* c, const iadh_profile_desc* p, std::ve
     return IADH_OK;
 }
 
+// the column groups of profile k as work items of the family-expansion build
+static void append_hl_items(iadh_ctx* c, int k, const std::vector<int32_t>& col_ptr, const std::vector<int32_t>& gfam,
+                            const std::vector<int32_t>& ggid, const std::vector<uint8_t>& gstrand)
+{
+    if (c->pairs) return;   // (pairs mode builds profile GHMs with the tile kernel)
+    const int L = (int)col_ptr.size() - 1;
+    for (int x = 0; x < L; x++)
+        for (int g = col_ptr[x]; g < col_ptr[x + 1]; g++) {
+            HlGroup it;
+            it.fam = gfam[g];
+            it.gid = ggid[g];
+            it.x_strand = (uint32_t)x | (gstrand[g] ? 0x80000000u : 0u);
+            it.prof = k;
+            c->hl_items.push_back(it);
+        }
+}
+
 // one profile laid out at h (host staging) / dv (the same bytes on the device); returns the bytes used
 static size_t place_profile(const iadh_ctx* c, const iadh_profile_desc* p, const std::vector<int32_t>& col_ptr,
                             const std::vector<int32_t>& gfam, const std::vector<int32_t>& ggid, const std::vector<uint8_t>& gstrand,
@@ -593,6 +629,8 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
     std::vector<uint8_t> gstrand;
     int rc = profile_groups(c, p, col_ptr, gfam, ggid, gstrand);
     if (rc) return rc;
+    c->hl_items.clear();
+    append_hl_items(c, 0, col_ptr, gfam, ggid, gstrand);
     ProfileDev dummy;
     const size_t bytes = place_profile(c, p, col_ptr, gfam, ggid, gstrand, nullptr, nullptr, dummy);
     CU(c->h_pf.ensure(bytes + 16));
@@ -738,14 +776,33 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
                        iadh_stats& st, const std::function<int(std::vector<GhmTask>&)>& plan = nullptr)
 {
     const int n = (int)tasks.size();
-    std::vector<int64_t> tile_prefix(n + 1, 0);
-    for (int i = 0; i < n; i++) {
-        // (a batch of profiles: pf.batch is a device pointer, the lengths come from the host copy)
-        const int64_t nx = hl ? (pf.batch ? c->batch_L[tasks[i].prof] : pf.L) : (c->list_off[tasks[i].x_list + 1] - c->list_off[tasks[i].x_list]);
-        tile_prefix[i + 1] = tile_prefix[i] + (nx + 31) / 32;
-    }
-    const int64_t n_tiles = tile_prefix[n];
     int rc;
+    // Path choice.  Many sparse level-2 GHMs: the family-expansion kernels (work = dots); otherwise (profile GHMs,
+    // small calls, dense GHMs, a pair named twice) the tile kernels (work = GHM columns).
+    const int nl = c->n_lists;
+    const int64_t n_prof = hl ? (pf.batch ? (int64_t)c->batch_L.size() : 1) : 0;
+    bool expand = hl ? (!c->pairs && n >= c->hl_expand_min && n_prof * nl <= ((int64_t)4 << 20))
+                     : (n >= c->expand_min && (int64_t)nl * nl <= ((int64_t)64 << 20));
+    if (expand) {
+        // (x list | profile, y list) -> task; a pair named twice sends the call to the tile kernels
+        c->h_pair_idx.assign((size_t)(hl ? n_prof : nl) * nl, -1);
+        c->h_row_used.assign((size_t)nl, 0);
+        for (int i = 0; i < n && expand; i++) {
+            int32_t& slot = c->h_pair_idx[(size_t)(hl ? tasks[i].prof : tasks[i].x_list) * nl + tasks[i].y_list];
+            if (slot >= 0) expand = false;
+            slot = i;
+            if (!hl) c->h_row_used[tasks[i].x_list] = 1;
+        }
+    }
+    std::vector<int64_t> tile_prefix(n + 1, 0);
+    auto make_tile_prefix = [&]() {
+        for (int i = 0; i < n; i++) {
+            // (a batch of profiles: pf.batch is a device pointer, the lengths come from the host copy)
+            const int64_t nx = hl ? (pf.batch ? c->batch_L[tasks[i].prof] : pf.L) : (c->list_off[tasks[i].x_list + 1] - c->list_off[tasks[i].x_list]);
+            tile_prefix[i + 1] = tile_prefix[i] + (nx + 31) / 32;
+        }
+    };
+    if (!expand) make_tile_prefix();
     trace_mark(c->st, "host: tile prefix");
     // the device task records are built from what the host knows (40 of their 184 bytes), through pinned staging
     CU(c->d_tasks.ensure(sizeof(GhmTask) * (size_t)n + 16));
@@ -765,25 +822,61 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
         init_tasks_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_init.as<TaskInit>());
         st.kernel_launches += 1;
     }
-    const int64_t* d_tile_prefix = (const int64_t*)(c->d_init.as<TaskInit>() + n);
+    int64_t* d_tile_prefix = (int64_t*)(c->d_init.as<TaskInit>() + n);
     st.h2d_bytes += (int64_t)sizeof(TaskInit) * n + 8 * (n + 1);
-    CU(c->d_tile_cnt.ensure(8 * (size_t)n_tiles + 16));
-    CU(c->d_tile_off.ensure(8 * (size_t)n_tiles + 16));
-    CU(cudaEventRecord(c->ev[1], c->st));
-    launch_build_count(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
-                       c->d_tile_cnt.as<uint32_t>(), c->sm_count, c->st);
-    launch_tile_scan(d_tile_prefix, n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
-    CU(cudaEventRecord(c->ev[2], c->st));
-    trace_mark(c->st, "K1 count + tile scan");
-    st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
     CU(c->d_cnt.ensure(8 * (size_t)n + 16));
     CU(c->h_misc.ensure(8 * (size_t)n + 16));
-    gather_cnt_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_cnt.as<uint32_t>());
-    CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; the counts are read next)
-    trace_mark(c->st, "counts D2H");
-    st.d2h_bytes += 8 * (int64_t)n;
-    st.kernel_launches += 1;
+    const int64_t n_elems = nl ? c->list_off[nl] : 0;
+    if (expand) {
+        if ((rc = upload(c->d_pair_idx, c->h_pair_idx.data(), 4 * c->h_pair_idx.size(), c->st))) return rc;
+        if ((rc = upload(c->d_row_used, c->h_row_used.data(), c->h_row_used.size(), c->st))) return rc;
+        st.h2d_bytes += 4 * (int64_t)c->h_pair_idx.size() + nl;
+        if (hl) {
+            if ((rc = upload(c->d_hl_items, c->hl_items.data(), sizeof(HlGroup) * c->hl_items.size(), c->st))) return rc;
+            st.h2d_bytes += (int64_t)(sizeof(HlGroup) * c->hl_items.size());
+        }
+        CU(cudaMemsetAsync(c->d_cnt.p, 0, 8 * (size_t)n, c->st));
+        CU(cudaEventRecord(c->ev[1], c->st));
+        if (hl)
+            launch_hl_expand_count(c->ds, c->d_hl_items.as<HlGroup>(), (int)c->hl_items.size(), c->d_pair_idx.as<int32_t>(), pf.vis,
+                                   c->d_cnt.as<uint32_t>(), c->sm_count, c->st);
+        else
+            launch_expand_count(c->ds, n_elems, c->d_pair_idx.as<int32_t>(), c->d_row_used.as<uint8_t>(), c->d_cnt.as<uint32_t>(), c->sm_count, c->st);
+        CU(cudaEventRecord(c->ev[2], c->st));
+        CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        trace_mark(c->st, "K1 expand count + counts D2H");
+        st.kernel_launches += 1;
+        st.d2h_bytes += 8 * (int64_t)n;
+        // the block sort of this path works in shared memory: a dense GHM sends the call to the tile kernels
+        const uint32_t* hc = c->h_misc.as<uint32_t>();
+        const uint32_t lim = (uint32_t)(c->expand_sort_max > 0 ? std::min(c->expand_sort_max, expand_sort_max()) : expand_sort_max());
+        for (int i = 0; i < 2 * n && expand; i++)
+            if (hc[i] > lim) expand = false;
+        if (!expand) {
+            make_tile_prefix();
+            CU(cudaMemcpyAsync(d_tile_prefix, tile_prefix.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
+            CU(cudaStreamSynchronize(c->st));   // (pageable source)
+        }
+    }
+    const int64_t n_tiles = tile_prefix[n];
+    if (!expand) {
+        CU(c->d_tile_cnt.ensure(8 * (size_t)n_tiles + 16));
+        CU(c->d_tile_off.ensure(8 * (size_t)n_tiles + 16));
+        CU(cudaEventRecord(c->ev[1], c->st));
+        launch_build_count(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
+                           c->d_tile_cnt.as<uint32_t>(), c->sm_count, c->st);
+        launch_tile_scan(d_tile_prefix, n, c->d_tile_cnt.as<uint32_t>(), c->d_tile_off.as<uint32_t>(), c->st);
+        CU(cudaEventRecord(c->ev[2], c->st));
+        trace_mark(c->st, "K1 count + tile scan");
+        st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
+        gather_cnt_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_cnt.as<uint32_t>());
+        CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; the counts are read next)
+        trace_mark(c->st, "counts D2H");
+        st.d2h_bytes += 8 * (int64_t)n;
+        st.kernel_launches += 1;
+    }
     total_dots = 0;
     {
         const uint32_t* hc = c->h_misc.as<uint32_t>();
@@ -809,11 +902,28 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
         st.h2d_bytes += 8 * (int64_t)n;
         st.kernel_launches += 1;
     }
+    if (expand) {
+        CU(c->d_cur.ensure(8 * (size_t)n + 16));
+        CU(cudaMemsetAsync(c->d_cur.p, 0, 8 * (size_t)n, c->st));
+    }
     CU(cudaEventRecord(c->ev[3], c->st));
-    launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
-                      c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
+    if (expand) {
+        // (d_plan holds the dot offsets until the plan is sent, which is stream-ordered after these kernels)
+        if (hl)
+            launch_hl_expand_fill(c->ds, c->d_hl_items.as<HlGroup>(), (int)c->hl_items.size(), c->d_pair_idx.as<int32_t>(), pf.vis,
+                                  c->d_cur.as<uint32_t>(), c->d_plan.as<int64_t>(), c->d_cnt.as<uint32_t>(), c->d_dots.as<uint32_t>(),
+                                  c->d_tasks.as<GhmTask>(), n, c->sm_count, c->st);
+        else
+            launch_expand_fill(c->ds, n_elems, c->d_pair_idx.as<int32_t>(), c->d_row_used.as<uint8_t>(), c->d_cur.as<uint32_t>(),
+                               c->d_plan.as<int64_t>(), c->d_cnt.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->d_tasks.as<GhmTask>(), n,
+                               c->sm_count, c->st);
+        st.kernel_launches += 3;
+    } else {
+        launch_build_fill(hl, c->ds, pf, c->d_tasks.as<GhmTask>(), n, d_tile_prefix, n_tiles,
+                          c->d_tile_off.as<uint32_t>(), c->d_dots.as<uint32_t>(), c->sm_count, c->st);
+        st.kernel_launches += n_tiles ? 1 : 0;
+    }
     CU(cudaEventRecord(c->ev[4], c->st));
-    st.kernel_launches += n_tiles ? 1 : 0;
     st.n_dots = total_dots;
     if (plan) {
         // (the staging buffer of the offsets is reused by the plan: the copy above must have left it)
@@ -847,6 +957,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     int pool_factor = c->pool_factor;
     std::vector<int> order, items, items1, chunk_k, chunk_i1;
     std::vector<uint32_t> dcnt;
+    std::vector<int64_t> wsb;       // per GHM: workspace bytes, orientation mask (compact copies: the task records are
+    std::vector<uint8_t> hmask;     // 184 bytes apart and the loops below visit them in heaviest-first order)
     size_t ws_total = 0;
     bool pass_mode = false;
     int n_act = 0;
@@ -866,6 +978,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         // active GHMs: at least anchor_points dots (GHM.cpp:159), heaviest first
         order.clear();
         dcnt.resize(2 * (size_t)n);   // the sort keys, compact (the task records are 184 bytes apart)
+        wsb.assign((size_t)n, 0);
+        hmask.assign((size_t)n, 0);
         for (int i = 0; i < n; i++) {
             GhmTask& t = tasks[i];
             dcnt[2 * (size_t)i] = t.cnt[0];
@@ -890,6 +1004,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             // an orientation with fewer than 3 dots cannot seed a cluster: no queue item of its own
             t.half_mask = (t.cnt[0] >= 3 ? 1 : 0) | (t.cnt[1] >= 3 ? 2 : 0);
             t.half_needed = 1;
+            wsb[i] = t.ws_bytes;
+            hmask[i] = (uint8_t)t.half_mask;
             order.push_back(i);
         }
         trace_mark(nullptr, "  plan: workspaces");
@@ -945,7 +1061,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         // that would become the critical path on a 32-thread CTA (total dots >> heaviest GHM's dots)
         int64_t sum_d = 0, max_d = 1;
         for (int k = 0; k < n_act; k++) {
-            const int64_t D = (int64_t)tasks[order[k]].cnt[0] + tasks[order[k]].cnt[1];
+            const int64_t D = (int64_t)dcnt[2 * (size_t)order[k]] + dcnt[2 * (size_t)order[k] + 1];
             sum_d += D;
             max_d = std::max(max_d, D);
         }
@@ -962,16 +1078,16 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             chunk_i1.clear();
             int64_t acc = 0;
             for (int k = 0; k < n_act; k++) {
-                if (k == 0 || acc + tasks[order[k]].ws_bytes > c->pass_chunk_bytes) {
+                const int i = order[k];
+                if (k == 0 || acc + wsb[i] > c->pass_chunk_bytes) {
                     chunk_k.push_back(k);
                     chunk_i1.push_back((int)items1.size());
                     acc = 0;
                 }
-                acc += tasks[order[k]].ws_bytes;
-                for (int o = 0; o < 2; o++)
-                    if ((tasks[order[k]].half_mask >> o) & 1) items1.push_back(order[k] * 2 + o);
-                items.push_back(order[k] * 4);
-                tasks[order[k]].half_needed = 1;
+                acc += wsb[i];
+                if (hmask[i] & 1) items1.push_back(i * 2);
+                if (hmask[i] & 2) items1.push_back(i * 2 + 1);
+                items.push_back(i * 4);   // (half_needed stays 1)
             }
             chunk_k.push_back(n_act);
             chunk_i1.push_back((int)items1.size());
@@ -979,16 +1095,15 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 sort_desc_stable(items1, [this_dcnt = dcnt.data()](int a) { return (uint64_t)this_dcnt[a]; });
         }
         for (int k = 0; k < n_act && !pass_mode; k++) {
-            GhmTask& t = tasks[order[k]];
-            if (t.half_mask == 3 && (int)std::min(t.cnt[0], t.cnt[1]) >= c->split_min) {
-                const int first = (t.cnt[1] > t.cnt[0]) ? 2 : 1;
-                items.push_back(order[k] * 4 + first);
-                items.push_back(order[k] * 4 + (first ^ 3));
-                t.half_needed = 2;
-            } else {
-                items.push_back(order[k] * 4 + t.half_mask);
-                t.half_needed = 1;
-            }
+            const int i = order[k];
+            const uint32_t c0 = dcnt[2 * (size_t)i], c1 = dcnt[2 * (size_t)i + 1];
+            if (hmask[i] == 3 && (int)std::min(c0, c1) >= c->split_min) {
+                const int first = (c1 > c0) ? 2 : 1;
+                items.push_back(i * 4 + first);
+                items.push_back(i * 4 + (first ^ 3));
+                tasks[i].half_needed = 2;
+            } else
+                items.push_back(i * 4 + hmask[i]);   // (half_needed stays 1)
         }
         trace_mark(nullptr, "  plan: queue items");
         // too much for one go: the caller bisects the batch (the count pass that led here is cheap)
@@ -1191,6 +1306,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         trace_mark(c->st, "outcomes D2H");
         st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
         st.kernel_launches += 1;
+        bool any_failed = false;
         {
             const TaskOut* ho = c->h_misc.as<TaskOut>();
             for (int i = 0; i < n; i++) {
@@ -1199,6 +1315,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                 tasks[i].n_mult = ho[i].n_mult;
                 tasks[i].n_clusters = ho[i].n_clusters;
                 tasks[i].n_aps = ho[i].n_aps;
+                any_failed = any_failed || ho[i].status != 0;
             }
         }
         if (g_trace) {
@@ -1227,7 +1344,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             std::vector<int> fb;
             bool global_failed = false;
             for (int i : order_all)
-                if (tasks[i].status != 0) {
+                if (any_failed && tasks[i].status != 0) {
                     if (is_res[i]) fb.push_back(i);
                     else global_failed = true;
                 }
@@ -1263,7 +1380,8 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         }
         bool retry = false;
         for (int i : order_all)
-            if (tasks[i].status != 0) {
+            if (!any_failed) break;
+            else if (tasks[i].status != 0) {
                 if (g_trace && !retry)
                     fprintf(stderr, "[iadh] retry: GHM %d (D=%u+%u) status=%d clusters=%d pool_factor=%d\n", i, tasks[i].cnt[0],
                             tasks[i].cnt[1], tasks[i].status, tasks[i].n_clusters, pool_factor);
@@ -1279,12 +1397,18 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     std::vector<int> sel;
     std::vector<int64_t> out_off;
     int64_t total_bytes = 0;
-    for (int i = 0; i < n; i++)
-        if (tasks[i].n_mult > 0) {
-            sel.push_back(i);
-            out_off.push_back(total_bytes);
-            total_bytes += tasks[i].out_bytes;
-        }
+    st.n_ghm = n;
+    for (int i = 0; i < n; i++) {   // one pass: what is packed and where, multiplicon -> GHM index, totals
+        const GhmTask& t = tasks[i];
+        if (t.n_mult <= 0) continue;
+        sel.push_back(i);
+        out_off.push_back(total_bytes);
+        total_bytes += t.out_bytes;
+        for (int k = 0; k < t.n_mult; k++) out.ghm_index.push_back(t.seq);
+        st.n_multiplicons += t.n_mult;
+        st.n_baseclusters += t.n_clusters;
+        st.n_anchorpoints += t.n_aps;
+    }
     trace_mark(c->st, "host: sizes -> offsets");
     CU(out.packed.ensure((size_t)total_bytes + 4));
     trace_mark(c->st, "host: pinned result buffer");
@@ -1315,16 +1439,6 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     if (g_trace) {
         out.wait();
         trace_mark(c->st, "result D2H");
-    }
-    for (int i : sel)
-        for (int k = 0; k < tasks[i].n_mult; k++) out.ghm_index.push_back(tasks[i].seq);
-    st.n_ghm = n;
-    for (int i = 0; i < n; i++) {
-        st.n_multiplicons += tasks[i].n_mult;
-        if (tasks[i].n_mult > 0) {
-            st.n_baseclusters += tasks[i].n_clusters;
-            st.n_anchorpoints += tasks[i].n_aps;
-        }
     }
     out.tasks.swap(tasks);   // (the caller's vector is not used after the call)
     trace_mark(c->st, "host: collect");
@@ -1635,10 +1749,9 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     // level-2 build tables (build_kernels.cu): member records, strand prefix counts, own slot of
     // every element, duplicate-gene-ID flag, and the (family, list) -> first slot table
     std::vector<uint32_t> mem_y((size_t)n_mem);
-    std::vector<int32_t> plus_prefix((size_t)n_mem + 1, 0), self_slot((size_t)total);
+    std::vector<int32_t> plus_prefix((size_t)n_mem + 1, 0), self_slot((size_t)total), mem_list((size_t)n_mem), elem_list((size_t)total);
     {
         int l = 0;
-        std::vector<int32_t> elem_list((size_t)total);
         for (int64_t i = 0; i < total; i++) {
             while (i >= c->list_off[l + 1]) l++;
             elem_list[i] = l;
@@ -1647,6 +1760,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
             const int32_t e = members[m];
             const int strand = c->flags[e] & 1;
             mem_y[m] = ((uint32_t)(e - c->list_off[elem_list[e]]) << 1) | (uint32_t)strand;
+            mem_list[m] = elem_list[e];
             plus_prefix[m + 1] = plus_prefix[m] + strand;
             if (!pairs) self_slot[e] = (int32_t)m;
         }
@@ -1670,6 +1784,8 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (!rc) rc = upload(c->d_mem_y, mem_y.data(), 4 * mem_y.size(), c->st);
     if (!rc) rc = upload(c->d_plus_prefix, plus_prefix.data(), 4 * plus_prefix.size(), c->st);
     if (!rc) rc = upload(c->d_self_slot, self_slot.data(), 4 * self_slot.size(), c->st);
+    if (!rc) rc = upload(c->d_mem_list, mem_list.data(), 4 * mem_list.size(), c->st);
+    if (!rc) rc = upload(c->d_elem_list, elem_list.data(), 4 * elem_list.size(), c->st);
     if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
     if (!rc) rc = upload(c->d_fam, key, 4 * (size_t)total, c->st);
     if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
@@ -1696,6 +1812,8 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     c->ds.mem_y = c->d_mem_y.as<uint32_t>();
     c->ds.plus_prefix = c->d_plus_prefix.as<int32_t>();
     c->ds.self_slot = c->d_self_slot.as<int32_t>();
+    c->ds.mem_list = c->d_mem_list.as<int32_t>();
+    c->ds.elem_list = c->d_elem_list.as<int32_t>();
     c->ds.fam_list = have_table ? c->d_fam_list.as<int32_t>() : nullptr;
     c->ds.pairs = pairs ? 1 : 0;
     sort_lists(c);
@@ -1726,6 +1844,9 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (const char* e = getenv("IADH_RES_MAX_KB")) c->res_max_bytes = std::min(222, std::max(4, atoi(e))) << 10;
     if (const char* e = getenv("IADH_RES_WIDE")) sscanf(e, "%d:%d", &c->res_wide_min, &c->res_wide_nt);
     if (const char* e = getenv("IADH_PASS_MIN")) c->pass_min = std::max(1, atoi(e));
+    if (const char* e = getenv("IADH_EXPAND_MIN")) c->expand_min = std::max(1, atoi(e));
+    if (const char* e = getenv("IADH_HL_EXPAND_MIN")) c->hl_expand_min = std::max(1, atoi(e));
+    if (const char* e = getenv("IADH_EXPAND_SORT_MAX")) c->expand_sort_max = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char* e = getenv("IADH_PASS_CFG")) {
@@ -1822,7 +1943,7 @@ void iadh_destroy(iadh_ctx* c)
     set_last_result(c, nullptr, 0);
     comm_release(c);
     if (c->st) cudaStreamSynchronize(c->st);
-    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list,
+    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list, &c->d_mem_list, &c->d_elem_list, &c->d_pair_idx, &c->d_row_used, &c->d_cur, &c->d_hl_items,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis, &c->d_init};
     for (DBuf* b : bufs) b->release();
@@ -2094,10 +2215,12 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
     std::vector<size_t> p_off((size_t)n_profiles + 1, 0);
     ProfileDev dummy;
     c->batch_L.assign((size_t)n_profiles, 0);
+    c->hl_items.clear();
     for (int k = 0; k < n_profiles && rc == IADH_OK; k++) {
         p_off[k + 1] = p_off[k];
         if ((rc = profile_groups(c, &profiles[k], col_ptr[k], gfam[k], ggid[k], gstrand[k]))) break;   // (validates every descriptor)
         c->batch_L[k] = profiles[k].length;
+        if (mine[k]) append_hl_items(c, k, col_ptr[k], gfam[k], ggid[k], gstrand[k]);
         if (mine[k]) p_off[k + 1] += place_profile(c, &profiles[k], col_ptr[k], gfam[k], ggid[k], gstrand[k], nullptr, nullptr, dummy);
     }
     if (rc) return rc;

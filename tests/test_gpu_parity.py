@@ -15,8 +15,13 @@ from trace_io import read_trace
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("k1", ["default", "tiles", "expansion"])
 @pytest.mark.parametrize("path", pl.golden_traces(), ids=lambda p: p.split("/")[-1].split(".")[0])
-def test_cuda_replays_reference_trace(path):
+def test_cuda_replays_reference_trace(path, k1, monkeypatch):
+    # K1 has two build paths (tile kernels / family expansion, chosen by batch size): the traces replay on both
+    if k1 != "default":
+        monkeypatch.setenv("IADH_EXPAND_MIN", "1" if k1 == "expansion" else "1000000000")
+        monkeypatch.setenv("IADH_HL_EXPAND_MIN", "1" if k1 == "expansion" else "1000000000")
     tr = read_trace(path)
     eng = capi.load_product(tr.dataset)
     errs = pl.replay_trace(eng, tr, rtol_p=pl.P_RTOL)
@@ -270,6 +275,52 @@ def test_build_with_duplicate_gene_ids(no_table, monkeypatch):
         e.set_params(mult_hyp=capi.MH_NONE, prob_cutoff=0.9)
     assert capi.compare_packed(gpu.level2_all_pairs().bytes, cpu.level2_all_pairs().bytes, pl.P_RTOL) is None
     gpu.close()
+
+
+@pytest.mark.parametrize("sort_max", [None, "64"])
+def test_family_expansion_build_is_invisible(sort_max, monkeypatch):
+    """K1's family-expansion path (count / append / block sort; taken by level-2 batches of >= 1,024 GHMs) forced on
+    small inputs: same dots in the same order as the oracle, same packed bytes -- family and pairs mode, repeated gene
+    IDs, pair lists in any orientation, a pair named twice (tile kernels), and blocks beyond the sort's capacity
+    (sort_max = 64: the call falls back to the tile kernels after the count pass)."""
+    monkeypatch.setenv("IADH_EXPAND_MIN", "1")
+    monkeypatch.setenv("IADH_HL_EXPAND_MIN", "1")
+    if sort_max:
+        monkeypatch.setenv("IADH_EXPAND_SORT_MAX", sort_max)
+    sets = [_dup_id_dataset(), ingest.dataset_from_synth(synth.config_small(seed=41)), ingest.dataset_from_synth(synth.config_c5(0.03))]
+    cfgp = synth.config_small(seed=23)
+    cfgp.table_type = "pairs"
+    sets.append(ingest.dataset_from_synth(cfgp))
+    for k, ds in enumerate(sets):
+        gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+        xs, ys = capi.plan_pairs(np.diff(ds.list_off))
+        lists = [(xs, ys), (list(ys[:40]) + [1, 0], list(xs[:40]) + [1, 0]), ([0, 2, 0], [1, 2, 1])]
+        for xa, ya in lists:
+            dg, dc = gpu.build_dots(xa, ya), cpu.build_dots(xa, ya)
+            assert len(dg) == len(dc) and sum(len(a) + len(b) for a, b in dc) > 100
+            for (a0, a1), (b0, b1) in zip(dg, dc):
+                assert np.array_equal(a0, b0) and np.array_equal(a1, b1), k
+        if k != 2:   # (the dense shape is a build-only workload)
+            for e in (gpu, cpu):
+                e.set_params(mult_hyp=capi.MH_BONFERRONI)
+            a, b = gpu.level2_all_pairs(), cpu.level2_all_pairs()
+            assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
+            a, b = gpu.level2_all_pairs(1, 3), cpu.level2_all_pairs(1, 3)     # one rank's share of the pairs
+            assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
+            # profile GHMs (family mode: expansion over the column groups; pairs mode: tile kernel), masks accumulating
+            ms = capi.parse_packed(cpu.level2_all_pairs().bytes)
+            order = sorted(range(len(ms)), key=lambda i: -sum(len(c.aps) for c in ms[i].clusters))[:6]
+            for i in order:
+                m = ms[i]
+                prof = pl.simple_profile(ds, m.x_object_id, m.y_object_id, m)
+                for e in (gpu, cpu):
+                    e.mask_range(m.x_object_id, m.bounds[0], m.bounds[1])
+                    e.mask_range(m.y_object_id, m.bounds[2], m.bounds[3])
+                ly = list(range(ds.n_lists))
+                da, db = gpu.build_dots([0] * ds.n_lists, ly, profile=prof), cpu.build_dots([0] * ds.n_lists, ly, profile=prof)
+                assert all(np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1]) for u, v in zip(da, db)), (k, i)
+                assert capi.compare_packed(gpu.profile_search(prof).bytes, cpu.profile_search(prof).bytes, pl.P_RTOL) is None
+        gpu.close()
 
 
 def test_dense_build_matches_oracle():
