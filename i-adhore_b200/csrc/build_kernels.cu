@@ -508,6 +508,9 @@ __device__ __forceinline__ void warp_sort_regs(uint32_t* __restrict__ kb, int n,
     }
 }
 
+// (two instantiations, launched one after the other: blocks of up to 256 keys -- 8 registers per lane, many warps
+// resident -- and blocks of 257 ... 1,024 keys)
+template <int RMAX>
 __global__ void __launch_bounds__(256) seg_sort_warp_kernel(int n_seg, const int64_t* __restrict__ dot_off,
                                                             const uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys)
 {
@@ -515,14 +518,17 @@ __global__ void __launch_bounds__(256) seg_sort_warp_kernel(int n_seg, const int
     const int warps_total = gridDim.x * (blockDim.x >> 5);
     for (int sg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sg < n_seg; sg += warps_total) {
         const int n = (int)cnt[sg];
-        if (n < 2 || n > SORT_WARP_MAX) continue;
+        if (RMAX == 8 ? (n < 2 || n > 256) : (n <= 256 || n > SORT_WARP_MAX)) continue;
         uint32_t* __restrict__ kb = keys + dot_off[sg >> 1] + ((sg & 1) ? cnt[sg & ~1] : 0u);
-        if (n <= 32) warp_sort_regs<1>(kb, n, lane);
-        else if (n <= 64) warp_sort_regs<2>(kb, n, lane);
-        else if (n <= 128) warp_sort_regs<4>(kb, n, lane);
-        else if (n <= 256) warp_sort_regs<8>(kb, n, lane);
-        else if (n <= 512) warp_sort_regs<16>(kb, n, lane);
-        else warp_sort_regs<32>(kb, n, lane);
+        if (RMAX == 8) {
+            if (n <= 32) warp_sort_regs<1>(kb, n, lane);
+            else if (n <= 64) warp_sort_regs<2>(kb, n, lane);
+            else if (n <= 128) warp_sort_regs<4>(kb, n, lane);
+            else warp_sort_regs<8>(kb, n, lane);
+        } else {
+            if (n <= 512) warp_sort_regs<16>(kb, n, lane);
+            else warp_sort_regs<32>(kb, n, lane);
+        }
     }
 }
 
@@ -728,7 +734,8 @@ void launch_build_fill(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmT
 
 static void launch_seg_sort(int n_seg, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, int sm_count, cudaStream_t st)
 {
-    seg_sort_warp_kernel<<<std::min((n_seg + 7) / 8, sm_count * 16), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
+    seg_sort_warp_kernel<8><<<std::min((n_seg + 7) / 8, sm_count * 16), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
+    seg_sort_warp_kernel<32><<<std::min((n_seg + 7) / 8, sm_count * 8), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
     seg_sort_cta_kernel<<<std::min(n_seg, sm_count * 4), 256, 0, st>>>(n_seg, dot_off, cnt, keys);
 }
 

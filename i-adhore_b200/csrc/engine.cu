@@ -46,6 +46,8 @@ void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_ite
                            uint32_t* cursor, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm,
                            int sm_count, cudaStream_t st);
 int expand_sort_max(void);
+void launch_intern(const char* blob, const int64_t* off, int64_t n, int32_t* table, uint32_t table_size, int32_t* rep, int32_t* cmin,
+                   int32_t* flag_scan, int32_t* block_sum, int32_t* total, int32_t* ids, cudaStream_t st);
 void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64_t* list_off, int n_fam, int n_lists,
                      int64_t total, int32_t* table, cudaStream_t st);
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
@@ -302,9 +304,27 @@ struct HBuf {
     T* as() { return (T*)p; }
 };
 
+// One pinned block holding the streams of several results (the profiles of a batch, the results of a gather): each
+// result is a slice of it -- no host copy per result -- and the block goes back to the cache with the last of them.
+struct SharedPinned {
+    HBuf buf;
+    int refs = 0;
+    cudaEvent_t ready = nullptr;   // the copy into buf on the context's copy stream; null = complete
+    void wait()
+    {
+        if (ready) {
+            cudaEventSynchronize(ready);
+            cudaEventDestroy(ready);
+            ready = nullptr;
+        }
+    }
+};
+
 struct iadh_result {
     HBuf bytes;            // pinned: the device writes the packed stream straight into it (offset 4)
-    std::vector<uint8_t> owned;   // results cut out of a batch's stream (iadh_profile_search_batch) live here instead
+    std::vector<uint8_t> owned;   // (host-assembled streams: the bisected level-2 call)
+    SharedPinned* shared = nullptr;   // or a slice [shared_off, shared_off + n_bytes) of a shared block
+    size_t shared_off = 0;
     iadh_ctx* owner = nullptr;    // set while the context may still hold this result's stream on the device
     // The device-to-host copy of the stream runs on the context's copy stream and overlaps whatever the caller does
     // next (the next call's kernels included); iadh_result_bytes waits for it.  null = nothing in flight.
@@ -359,8 +379,9 @@ struct iadh_ctx {
     // ev_packed = the writer finished (copy may start), ev_copied = the last copy finished (d_out / the gather's
     // receive buffer may be overwritten)
     cudaStream_t st_copy = nullptr;
-    cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
-    bool copy_pending = false;
+    cudaEvent_t ev_packed = nullptr, ev_copied = nullptr, ev_copied_recv = nullptr;
+    bool copy_pending = false;        // a copy out of d_out may be in flight (ev_copied)
+    bool copy_pending_recv = false;   // a copy out of the gather's receive buffer may be in flight (ev_copied_recv)
     // dataset (host mirror + device)
     int n_lists = 0;
     std::vector<int64_t> list_off;
@@ -370,7 +391,7 @@ struct iadh_ctx {
     int n_fam = 0;
     bool pairs = false;   // table_type=pairs (iadh_create_pairs): families are gene ids, buckets hold partners
     DBuf d_list_off, d_fam, d_gid, d_num_id, d_flags, d_fam_ptr, d_fam_members, d_mem_y, d_plus_prefix, d_self_slot, d_fam_list;
-    DBuf d_mem_list, d_elem_list, d_pair_idx, d_row_used, d_cur, d_hl_items;
+    DBuf d_mem_list, d_elem_list, d_pair_idx, d_row_used, d_cur, d_hl_items, d_ghdr;
     DatasetDev ds;
     DevParams prm;
     // per-call buffers
@@ -649,6 +670,10 @@ struct BatchOut {
     HBuf packed;                 // pinned: int32 count + concatenated per-GHM blocks in seq order
     size_t packed_bytes = 0;     // incl. the 4-byte count
     cudaEvent_t ready = nullptr; // the copy into `packed` runs on the context's copy stream; set when one is in flight
+    // groups of consecutive GHMs (the profiles of iadh_profile_search_batch) whose multiplicons form a stream of their
+    // own inside `packed`: [int32 count][blocks] per group, group k at group_off[k] (n_groups + 1 entries)
+    const std::vector<int>* group_begin = nullptr;   // in: first task of every group (+ the task count)
+    std::vector<size_t> group_off;
     std::vector<int32_t> ghm_index;
     iadh_stats st;
     void wait()
@@ -735,6 +760,15 @@ __global__ void scatter_dot_off_kernel(GhmTask* __restrict__ tasks, int n, const
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) tasks[i].dot_off = dot_off[i];
+}
+// the 4-byte multiplicon counts between the groups of a packed stream (run_batch): hdr = (byte offset, count) pairs
+__global__ void group_header_kernel(uint8_t* __restrict__ out, const int64_t* __restrict__ hdr, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = (int32_t)hdr[2 * i + 1];
+    uint8_t* p = out + hdr[2 * i];   // (unaligned: the blocks before it have odd sizes)
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 __global__ void gather_out_kernel(const GhmTask* __restrict__ tasks, int n, TaskOut* __restrict__ out)
 {
@@ -946,10 +980,14 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     trace_mark(c->st, nullptr);
     int64_t total_dots = 0;
     int rc;
-    if (n == 0) {
+    if (n == 0) {   // nothing to search: empty streams (count 0), one per group
+        const size_t ng = out.group_begin ? out.group_begin->size() - 1 : 1;
         out.tasks.clear();
-        CU(out.packed.ensure(4));
-        out.packed_bytes = 4;
+        CU(out.packed.ensure(4 * ng));
+        memset(out.packed.p, 0, 4 * ng);
+        out.packed_bytes = 4 * ng;
+        out.group_off.resize(ng + 1);
+        for (size_t k = 0; k <= ng; k++) out.group_off[k] = 4 * k;
         return IADH_OK;
     }
     // host-side plan of the clustering stage: depends only on the dot counts, so it is made between
@@ -1398,7 +1436,24 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     std::vector<int64_t> out_off;
     int64_t total_bytes = 0;
     st.n_ghm = n;
+    // Groups: the device stream is the host stream minus its first 4 bytes, so group 0's count is written by the host
+    // (make_result / the caller) and every later group starts with a 4-byte count written on the device.
+    const int n_groups = out.group_begin ? (int)out.group_begin->size() - 1 : 1;
+    std::vector<int64_t> ghdr;      // per later group: device offset of its header, and its count (pairs)
+    out.group_off.assign((size_t)n_groups + 1, 0);
+    int gk = 0;
+    int32_t gcount = 0;
+    auto next_group = [&]() {
+        if (gk > 0) ghdr[2 * (size_t)(gk - 1) + 1] = gcount;
+        gk++;
+        gcount = 0;
+        out.group_off[gk] = (size_t)total_bytes + 4;
+        ghdr.push_back(total_bytes);
+        ghdr.push_back(0);
+        total_bytes += 4;
+    };
     for (int i = 0; i < n; i++) {   // one pass: what is packed and where, multiplicon -> GHM index, totals
+        while (gk + 1 < n_groups && i >= (*out.group_begin)[gk + 1]) next_group();
         const GhmTask& t = tasks[i];
         if (t.n_mult <= 0) continue;
         sel.push_back(i);
@@ -1406,24 +1461,37 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         total_bytes += t.out_bytes;
         for (int k = 0; k < t.n_mult; k++) out.ghm_index.push_back(t.seq);
         st.n_multiplicons += t.n_mult;
+        gcount += t.n_mult;
         st.n_baseclusters += t.n_clusters;
         st.n_anchorpoints += t.n_aps;
     }
+    while (gk + 1 < n_groups) next_group();
+    if (gk > 0) ghdr[2 * (size_t)(gk - 1) + 1] = gcount;
+    out.group_off[n_groups] = (size_t)total_bytes + 4;
     trace_mark(c->st, "host: sizes -> offsets");
     CU(out.packed.ensure((size_t)total_bytes + 4));
     trace_mark(c->st, "host: pinned result buffer");
     out.packed_bytes = (size_t)total_bytes + 4;
-    if (!sel.empty()) {
-        if ((rc = upload(c->d_sel, sel.data(), 4 * sel.size(), c->st))) return rc;
-        if ((rc = upload(c->d_out_off, out_off.data(), 8 * out_off.size(), c->st))) return rc;
+    if (total_bytes > 0) {
         if (c->copy_pending) {   // the previous result may still be travelling out of d_out
             if ((size_t)total_bytes + 16 > c->d_out.cap) CU(cudaEventSynchronize(c->ev_copied));   // (ensure() would hand the block on)
             else CU(cudaStreamWaitEvent(c->st, c->ev_copied, 0));
         }
         CU(c->d_out.ensure((size_t)total_bytes + 16));
-        launch_pack_write(hl, c->d_tasks.as<GhmTask>(), c->d_sel.as<int>(), c->d_out_off.as<int64_t>(), (int)sel.size(),
-                          c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
-        st.kernel_launches += 1;
+        if (!sel.empty()) {
+            if ((rc = upload(c->d_sel, sel.data(), 4 * sel.size(), c->st))) return rc;
+            if ((rc = upload(c->d_out_off, out_off.data(), 8 * out_off.size(), c->st))) return rc;
+            launch_pack_write(hl, c->d_tasks.as<GhmTask>(), c->d_sel.as<int>(), c->d_out_off.as<int64_t>(), (int)sel.size(),
+                              c->d_ws.as<uint8_t>(), c->ds, pf, pool_factor, c->d_out.as<uint8_t>(), c->st);
+            st.kernel_launches += 1;
+        }
+        if (!ghdr.empty()) {
+            if ((rc = upload(c->d_ghdr, ghdr.data(), 8 * ghdr.size(), c->st))) return rc;
+            const int nh = (int)(ghdr.size() / 2);
+            group_header_kernel<<<(nh + 127) / 128, 128, 0, c->st>>>(c->d_out.as<uint8_t>(), c->d_ghdr.as<int64_t>(), nh);
+            st.kernel_launches += 1;
+            st.h2d_bytes += 8 * (int64_t)ghdr.size();
+        }
         trace_mark(c->st, "K3 write");
         // the copy to the host runs on the copy stream: the caller's next call computes meanwhile
         CU(cudaEventRecord(c->ev_packed, c->st));
@@ -1657,6 +1725,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     CU(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copied_recv, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&c->user_ev[i]));
     for (int i = 0; i < 3; i++) {
         CU(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
@@ -1943,7 +2012,7 @@ void iadh_destroy(iadh_ctx* c)
     set_last_result(c, nullptr, 0);
     comm_release(c);
     if (c->st) cudaStreamSynchronize(c->st);
-    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list, &c->d_mem_list, &c->d_elem_list, &c->d_pair_idx, &c->d_row_used, &c->d_cur, &c->d_hl_items,
+    DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list, &c->d_mem_list, &c->d_elem_list, &c->d_pair_idx, &c->d_row_used, &c->d_cur, &c->d_hl_items, &c->d_ghdr,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
                     &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis, &c->d_init};
     for (DBuf* b : bufs) b->release();
@@ -1961,6 +2030,7 @@ void iadh_destroy(iadh_ctx* c)
     }
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->ev_copied_recv) cudaEventDestroy(c->ev_copied_recv);
     for (int i = 0; i < 4; i++)
         if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
     if (c->st) cudaStreamDestroy(c->st);
@@ -2244,6 +2314,7 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
     pf.batch = (const ProfileDev*)(c->d_pf_col.as<uint8_t>() + desc_off);
     pf.vis = c->d_vis.as<int16_t>();
     set_last_result(c, nullptr, 0);
+    b.group_begin = &t_begin;
     rc = run_batch(c, true, pf, tasks, b);
     // the masks of the whole batch now hold, as after the sequential calls
     if (rc == IADH_OK && total > 0 && mask_ptr[n_profiles] > 0) {
@@ -2262,18 +2333,19 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
         cudaEventElapsedTime(&m2, c->ev[3], c->ev[4]);
         cudaEventElapsedTime(&m3, c->ev[5], c->ev[6]);
     }
-    // cut the packed stream (GHMs in task order) into one result per profile
-    b.wait();
-    const uint8_t* stream = b.packed.as<uint8_t>() + 4;
-    size_t pos = 0;
+    // one result per profile: slices of the batch's pinned stream (run_batch laid it out as one [count][blocks] stream
+    // per profile), still on its way to the host -- iadh_result_bytes waits for the copy
+    SharedPinned* sp = new SharedPinned();
+    std::swap(sp->buf, b.packed);
+    sp->ready = b.ready;
+    b.ready = nullptr;
+    sp->refs = n_profiles;
     const double share = n_mine > 0 ? 1.0 / n_mine : 0.0;
     for (int k = 0; k < n_profiles; k++) {
         iadh_result* r = new iadh_result();
         memset(&r->stats, 0, sizeof r->stats);
-        size_t bytes = 0;
         for (int t = t_begin[k]; t < t_begin[k + 1]; t++) {
             const GhmTask& tk = b.tasks[t];
-            bytes += (size_t)tk.out_bytes * (tk.n_mult > 0 ? 1 : 0);
             r->stats.n_dots += (int64_t)tk.cnt[0] + tk.cnt[1];
             r->stats.n_multiplicons += tk.n_mult;
             if (tk.n_mult > 0) {
@@ -2283,12 +2355,13 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
             for (int q = 0; q < tk.n_mult; q++) r->ghm_index.push_back(t - t_begin[k]);
         }
         r->stats.n_ghm = t_begin[k + 1] - t_begin[k];
-        r->owned.resize(bytes + 4);
-        const int32_t nm = (int32_t)r->stats.n_multiplicons;
-        memcpy(r->owned.data(), &nm, 4);
-        if (bytes) memcpy(r->owned.data() + 4, stream + pos, bytes);
-        pos += bytes;
-        r->n_bytes = bytes + 4;
+        r->shared = sp;
+        r->shared_off = b.group_off[k];
+        r->n_bytes = b.group_off[k + 1] - b.group_off[k];
+        if (k == 0) {   // (the first 4 bytes of the block are not part of the device stream)
+            const int32_t nm = (int32_t)r->stats.n_multiplicons;
+            memcpy(sp->buf.p, &nm, 4);
+        }
         if (mine[k]) {   // device times of the batch, spread evenly over this rank's profiles
             r->stats.total_ms = ms * share;
             r->stats.build_ms = (m1 + m2) * share;
@@ -2298,6 +2371,7 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
         }
         out[k] = r;
     }
+    const size_t pos = b.packed_bytes - 4;   // bytes of the device stream
     // the batch's stream is still in d_out, its results in order: iadh_allgather_results sends it from there
     for (int k = 0; k < n_profiles; k++) {
         c->last_batch.push_back(out[k]);
@@ -2321,6 +2395,10 @@ const uint8_t* iadh_result_bytes(const iadh_result* r, size_t* n)
         cudaEventSynchronize(r->ready);
         cudaEventDestroy(r->ready);
         r->ready = nullptr;
+    }
+    if (r->shared) {
+        r->shared->wait();
+        return r->shared->buf.as<uint8_t>() + r->shared_off;
     }
     return r->owned.empty() ? (const uint8_t*)r->bytes.p : r->owned.data();
 }
@@ -2346,6 +2424,11 @@ void iadh_free_result(iadh_result* r)
         r->ready = nullptr;
     }
     r->bytes.release();
+    if (r->shared && --r->shared->refs == 0) {
+        r->shared->wait();
+        r->shared->buf.release();
+        delete r->shared;
+    }
     delete r;
 }
 void iadh_trim(void) { g_cache.trim(); }
@@ -2471,15 +2554,17 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
     int64_t* ha = hm + (size_t)META * n;
     CU(cudaMemcpyAsync(ha, s.d_meta_recv.p, 8 * (size_t)META * n * N, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    // 2. payload: this rank's bodies in order, body i > 0 preceded by a 4-byte hole (the layout a batch leaves on the
+    //    device: run_batch writes the per-profile counts there), padded to the longest rank (NCCL gathers equal slots)
     std::vector<int64_t> tot((size_t)N, 0);
     int64_t max_tot = 0;
     for (int r = 0; r < N; r++) {
         for (int i = 0; i < n; i++) tot[r] += ha[((size_t)r * n + i) * META];
+        tot[r] += 4 * (int64_t)(n - 1);
         max_tot = std::max(max_tot, tot[r]);
     }
-    // 2. payload: this rank's bodies back to back, padded to the longest rank (NCCL gathers equal slots)
+    my_total += 4 * (int64_t)(n - 1);
     const size_t slot = (size_t)((max_tot + 15) & ~(int64_t)15);
-    if (c->copy_pending) CU(cudaEventSynchronize(c->ev_copied));   // an earlier gather may still be reading the receive buffer
     if (slot > 0) {
         const void* send = nullptr;
         bool on_device = (n == 1 && c->last_result == mine[0] && c->last_result_body == (size_t)my_total);
@@ -2488,7 +2573,7 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
             for (int i = 0; i < n; i++) on_device = on_device && c->last_batch[i] == mine[i];
         }
         if (on_device && c->d_out.cap >= slot)
-            send = c->d_out.p;   // still on the device: no re-upload (bytes past the body are padding)
+            send = c->d_out.p;   // still on the device: no re-upload (bytes past the stream are padding)
         else {
             // one pinned staging block, one copy (the results' own buffers may be pageable)
             CU(s.d_send.ensure(slot));
@@ -2497,76 +2582,83 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
             for (int i = 0; i < n; i++) {
                 size_t nb = 0;
                 const uint8_t* p = iadh_result_bytes(mine[i], &nb);
+                if (i) o += 4;
                 if (nb > 4) memcpy(s.h_stage.as<uint8_t>() + o, p + 4, nb - 4);
                 o += nb - 4;
             }
             if (o) CU(cudaMemcpyAsync(s.d_send.p, s.h_stage.p, o, cudaMemcpyHostToDevice, c->st));
             send = s.d_send.p;
         }
+        // an earlier gather's copy to the host may still be reading the receive buffer: the collective waits for it on
+        // the device (the host only when the buffer has to grow)
+        if (c->copy_pending_recv) {
+            if (slot * (size_t)N > s.d_recv.cap) CU(cudaEventSynchronize(c->ev_copied_recv));
+            else CU(cudaStreamWaitEvent(c->st, c->ev_copied_recv, 0));
+        }
         CU(s.d_recv.ensure(slot * (size_t)N));
         NC(s, s.AllGather(send, s.d_recv.p, slot, ncclChar, s.comm, c->st));
     }
-    // 3. results: for every i the bodies of rank 0, 1, ... in rank order behind the summed count
-    if (n == 1) {
-        iadh_result* r = new iadh_result();
-        memset(&r->stats, 0, sizeof r->stats);
-        int64_t bytes = 0;
-        for (int k = 0; k < N; k++) bytes += tot[k];
-        if (r->bytes.ensure((size_t)bytes + 4) != cudaSuccess) {
-            delete r;
-            return fail(IADH_ERR_CUDA, "out of pinned host memory");
-        }
-        size_t o = 4;
-        CU(cudaEventRecord(c->ev_packed, c->st));
-        CU(cudaStreamWaitEvent(c->st_copy, c->ev_packed, 0));
-        for (int k = 0; k < N; k++) {
-            if (tot[k]) CU(cudaMemcpyAsync(r->bytes.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st_copy));
-            o += (size_t)tot[k];
-            r->stats.n_multiplicons += ha[(size_t)k * META + 1];
-            r->stats.n_ghm += ha[(size_t)k * META + 2];
-            r->stats.n_dots += ha[(size_t)k * META + 3];
-        }
-        // (on the copy stream: the gathered stream reaches the host while the next call computes)
-        CU(cudaEventRecord(c->ev_copied, c->st_copy));
-        CU(cudaEventCreateWithFlags(&r->ready, cudaEventDisableTiming));
-        CU(cudaEventRecord(r->ready, c->st_copy));
-        c->copy_pending = true;
-        const int32_t nm = (int32_t)r->stats.n_multiplicons;
-        memcpy(r->bytes.p, &nm, 4);
-        r->n_bytes = (size_t)bytes + 4;
-        r->stats.d2h_bytes = bytes;
-        all[0] = r;
-        return IADH_OK;
+    // 3. results: for every i [summed count][body of rank 0][body of rank 1]..., all in one pinned block that the
+    //    results share as slices; every body travels from the receive buffer to its place on the copy stream (the
+    //    gathered streams reach the host while the next call computes), the counts are written by the host
+    SharedPinned* sp = new SharedPinned();
+    std::vector<size_t> res_off((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        size_t bytes = 4;
+        for (int k = 0; k < N; k++) bytes += (size_t)ha[((size_t)k * n + i) * META];
+        res_off[i + 1] = res_off[i] + bytes;
     }
-    if (slot > 0) {
-        CU(s.h_recv.ensure(slot * (size_t)N));
-        for (int k = 0; k < N; k++)
-            if (tot[k]) CU(cudaMemcpyAsync(s.h_recv.as<uint8_t>() + slot * (size_t)k, (uint8_t*)s.d_recv.p + slot * (size_t)k, (size_t)tot[k], cudaMemcpyDeviceToHost, c->st));
-        CU(cudaStreamSynchronize(c->st));
+    if (sp->buf.ensure(res_off[n] + 16) != cudaSuccess) {
+        delete sp;
+        return fail(IADH_ERR_CUDA, "out of pinned host memory");
     }
-    std::vector<size_t> cur((size_t)N, 0);
+    sp->refs = n;
+    CU(cudaEventRecord(c->ev_packed, c->st));
+    CU(cudaStreamWaitEvent(c->st_copy, c->ev_packed, 0));
+    std::vector<size_t> src_off((size_t)N, 0);   // position inside rank k's stream
     for (int i = 0; i < n; i++) {
         iadh_result* r = new iadh_result();
         memset(&r->stats, 0, sizeof r->stats);
-        size_t bytes = 0;
-        for (int k = 0; k < N; k++) bytes += (size_t)ha[((size_t)k * n + i) * META];
-        r->owned.resize(bytes + 4);
-        size_t o = 4;
+        size_t o = res_off[i] + 4;
         for (int k = 0; k < N; k++) {
             const int64_t* m = ha + ((size_t)k * n + i) * META;
-            if (m[0]) memcpy(r->owned.data() + o, s.h_recv.as<uint8_t>() + slot * (size_t)k + cur[k], (size_t)m[0]);
+            if (i) src_off[k] += 4;
+            if (m[0]) {
+                // (adjacent pieces -- every rank's body of a single result -- would merge into one copy; with n > 1
+                // the pieces of a rank are separated by the other results)
+                cudaError_t e = cudaMemcpyAsync(sp->buf.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k + src_off[k], (size_t)m[0],
+                                                cudaMemcpyDeviceToHost, c->st_copy);
+                if (e != cudaSuccess) {
+                    cudaStreamSynchronize(c->st_copy);
+                    sp->buf.release();
+                    delete sp;
+                    delete r;
+                    for (int q = 0; q < i; q++) {
+                        all[q]->shared = nullptr;
+                        delete all[q];
+                        all[q] = nullptr;
+                    }
+                    return fail(IADH_ERR_CUDA, "%s", cudaGetErrorString(e));
+                }
+            }
             o += (size_t)m[0];
-            cur[k] += (size_t)m[0];
+            src_off[k] += (size_t)m[0];
             r->stats.n_multiplicons += m[1];
             r->stats.n_ghm += m[2];
             r->stats.n_dots += m[3];
         }
         const int32_t nm = (int32_t)r->stats.n_multiplicons;
-        memcpy(r->owned.data(), &nm, 4);
-        r->n_bytes = bytes + 4;
-        r->stats.d2h_bytes = (int64_t)bytes;
+        memcpy(sp->buf.as<uint8_t>() + res_off[i], &nm, 4);
+        r->shared = sp;
+        r->shared_off = res_off[i];
+        r->n_bytes = res_off[i + 1] - res_off[i];
+        r->stats.d2h_bytes = (int64_t)r->n_bytes - 4;
         all[i] = r;
     }
+    CU(cudaEventRecord(c->ev_copied_recv, c->st_copy));
+    CU(cudaEventCreateWithFlags(&sp->ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(sp->ready, c->st_copy));
+    c->copy_pending_recv = true;
     return IADH_OK;
 }
 
@@ -2726,6 +2818,59 @@ static int remap_tandems_impl(const iadh_dataset_desc* d, int32_t tandem_gap, in
     DBuf* bufs[] = {&b_off, &b_el, &b_fam, &b_gid, &b_fl, &b_rem, &b_t3};
     for (DBuf* b : bufs) b->release();
     cudaStreamDestroy(st);
+    return rc;
+}
+
+static int intern_strings_impl(const char* blob, const int64_t* off, int64_t n, int device, int32_t* ids_out, int32_t* n_distinct_out);
+int iadh_intern_strings(const char* blob, const int64_t* off, int64_t n, int device, int32_t* ids_out, int32_t* n_distinct_out)
+{
+    IADH_TRY return intern_strings_impl(blob, off, n, device, ids_out, n_distinct_out);
+    IADH_CATCH
+}
+static int intern_strings_impl(const char* blob, const int64_t* off, int64_t n, int device, int32_t* ids_out, int32_t* n_distinct_out)
+{
+    if (n < 0 || (n > 0 && (!off || !ids_out)) || !n_distinct_out) return fail(IADH_ERR_ARG, "iadh_intern_strings: bad argument");
+    *n_distinct_out = 0;
+    if (n == 0) return IADH_OK;
+    if (n >= 0x3fffffff) return fail(IADH_ERR_CAPACITY, "more than 2^30 strings");
+    if (off[0] != 0) return fail(IADH_ERR_ARG, "iadh_intern_strings: off[0] must be 0");
+    for (int64_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return fail(IADH_ERR_ARG, "iadh_intern_strings: offsets are not ascending at string %lld", (long long)i);
+    if (off[n] > 0 && !blob) return fail(IADH_ERR_ARG, "iadh_intern_strings: null blob");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(IADH_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    uint32_t tsize = 1024;
+    while ((int64_t)tsize < 2 * n) tsize <<= 1;   // load factor <= 0.5
+    const size_t n_blocks = (size_t)((n + 1023) / 1024);
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DBuf b_blob, b_off, b_table, b_rep, b_cmin, b_scan, b_bsum, b_ids;
+    int rc = IADH_OK;
+    int32_t total = 0;
+    if (!rc) rc = upload(b_blob, blob, (size_t)off[n], st);
+    if (!rc) rc = upload(b_off, off, 8 * (size_t)(n + 1), st);
+    if (!rc && (b_table.ensure(4 * (size_t)tsize) != cudaSuccess || b_rep.ensure(4 * (size_t)n) != cudaSuccess ||
+                b_cmin.ensure(4 * (size_t)n) != cudaSuccess || b_scan.ensure(4 * (size_t)n) != cudaSuccess ||
+                b_bsum.ensure(4 * n_blocks + 16) != cudaSuccess || b_ids.ensure(4 * (size_t)n) != cudaSuccess))
+        rc = fail(IADH_ERR_CUDA, "out of device memory");
+    if (!rc) {
+        cudaMemsetAsync(b_table.p, 0xff, 4 * (size_t)tsize, st);   // -1: empty slot
+        cudaMemsetAsync(b_cmin.p, 0x7f, 4 * (size_t)n, st);        // 0x7f7f7f7f: above every index
+        int32_t* d_total = b_bsum.as<int32_t>() + n_blocks;
+        launch_intern(b_blob.as<char>(), b_off.as<int64_t>(), n, b_table.as<int32_t>(), tsize, b_rep.as<int32_t>(), b_cmin.as<int32_t>(),
+                      b_scan.as<int32_t>(), b_bsum.as<int32_t>(), d_total, b_ids.as<int32_t>(), st);
+        if (cudaMemcpyAsync(ids_out, b_ids.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail(IADH_ERR_CUDA, "string interning failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaStreamSynchronize(st);
+    DBuf* bufs[] = {&b_blob, &b_off, &b_table, &b_rep, &b_cmin, &b_scan, &b_bsum, &b_ids};
+    for (DBuf* b : bufs) b->release();
+    cudaStreamDestroy(st);
+    if (!rc) *n_distinct_out = total;
     return rc;
 }
 

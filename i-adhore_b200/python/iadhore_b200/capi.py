@@ -52,7 +52,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["remap_tandems", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
+EXPORTS = ["remap_tandems", "intern_strings", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "profile_search_batch", "comm_unique_id", "comm_init", "comm_destroy",
            "allgather_results", "result_bytes", "result_size", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
@@ -419,6 +419,28 @@ def remap_tandems(list_off, fam, gid, strand, tandem_gap: int, device: int = 0, 
         f.restype = C.c_char_p
         raise RuntimeError(f"{prefix}remap_tandems failed ({rc}): {f().decode()}")
     return out.astype(bool)
+
+
+def intern_strings(strings: Sequence[str], device: int = 0, lib_path: str = PRODUCT_LIB, prefix: str = "iadh_") -> Tuple[np.ndarray, int]:
+    """iadh_intern_strings: dense ids in order of first occurrence (equal strings, equal ids) and the number of
+    distinct strings.  Product library: hash table on the device; oracle library: std::unordered_map."""
+    if not os.path.exists(lib_path):
+        raise RuntimeError(f"{lib_path} is missing: build it first")
+    lib = C.CDLL(lib_path)
+    enc = [x.encode() for x in strings]
+    off = np.zeros(len(enc) + 1, np.int64)
+    if enc:
+        off[1:] = np.cumsum([len(b) for b in enc])
+    blob = b"".join(enc)
+    ids = np.zeros(len(enc), np.int32)
+    nd = C.c_int32(0)
+    rc = getattr(lib, prefix + "intern_strings")(C.c_char_p(blob), _p(off, C.c_int64), C.c_int64(len(enc)), C.c_int(device),
+                                                  _p(ids, C.c_int32), C.byref(nd))
+    if rc:
+        f = getattr(lib, prefix + "last_error")
+        f.restype = C.c_char_p
+        raise RuntimeError(f"{prefix}intern_strings failed ({rc}): {f().decode()}")
+    return ids, int(nd.value)
 
 
 def load_product(ds: Dataset, device: int = 0) -> Engine:

@@ -109,6 +109,16 @@ typedef struct {
 int iadh_remap_tandems(const iadh_dataset_desc* lists, int32_t tandem_gap, int device,
                        uint8_t* remapped_out);
 
+/* String interning on the device: dense ids for n byte strings (string i = blob[off[i] .. off[i+1]), off[0] = 0).
+ * Equal strings get equal ids; ids number the distinct strings in order of first occurrence, so the result does not
+ * depend on thread timing.  This is the hashing half of the reference's family join: DataSet::getGeneFamilies
+ * (DataSet.cpp:188-202) maps every gene through the blast table's map<string, string> (GeneFamily.cpp:12-16, 38-48)
+ * and GHM::buildMatrixFast hashes the family strings once more per list pair (GHM.cpp:34-50); a caller interns its
+ * family strings (-> iadh_dataset_desc.fam) and gene IDs (-> .gid) once with this call, and K1 joins on integers.
+ * No context needed; ids_out holds n entries. */
+int iadh_intern_strings(const char* blob, const int64_t* off, int64_t n, int device, int32_t* ids_out,
+                        int32_t* n_distinct_out);
+
 /* Replaces: DataSet ownership of the flattened lists; called once after
  * DataSet::sortGeneLists() (iADHoRe.cpp:75).  `device` = CUDA ordinal. */
 int iadh_create(const iadh_dataset_desc* ds, int device, iadh_ctx** out);

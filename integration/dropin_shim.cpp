@@ -108,24 +108,52 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     std::vector<int64_t> off(1, 0);
     std::vector<int32_t> fam, gid, num;
     std::vector<uint8_t> flags;
-    B.masked.resize(genelists.size());
-    for (size_t l = 0; l < genelists.size(); l++) {
-        const std::vector<ListElement*>& all = genelists[l]->getElements();
-        for (size_t i = 0; i < all.size(); i++) {
-            const int id = all[i]->getNumID();
+    const char* dev = getenv("IADH_DEVICE");
+    g_warmup.join();
+    // Strings -> dense ids on the device (iadh_intern_strings), once: the family and the gene ID of every element of
+    // every list, in list order.  Everything below -- and K1's join -- works on these integers; the reference would
+    // hash the same strings again for every list pair (GHM.cpp:34-50).
+    {
+        std::string fblob, gblob;
+        std::vector<int64_t> foff(1, 0), goff(1, 0);
+        std::vector<int> ids;
+        for (size_t l = 0; l < genelists.size(); l++) {
+            const std::vector<ListElement*>& all = genelists[l]->getElements();
+            for (size_t i = 0; i < all.size(); i++) {
+                fblob += all[i]->getGene().getFamily();
+                gblob += all[i]->getGene().getID();
+                foff.push_back((int64_t)fblob.size());
+                goff.push_back((int64_t)gblob.size());
+                ids.push_back(all[i]->getNumID());
+            }
+        }
+        const int64_t n = (int64_t)ids.size();
+        std::vector<int32_t> fid((size_t)n), gidv((size_t)n);
+        int32_t nf = 0, ng = 0;
+        check(iadh_intern_strings(fblob.data(), foff.data(), n, dev ? atoi(dev) : 0, fid.data(), &nf), "iadh_intern_strings (families)");
+        check(iadh_intern_strings(gblob.data(), goff.data(), n, dev ? atoi(dev) : 0, gidv.data(), &ng), "iadh_intern_strings (gene IDs)");
+        for (int64_t i = 0; i < n; i++) {
+            const int id = ids[i];
             if (id >= (int)B.fam_of.size()) {
                 B.fam_of.resize(id + 1, -1);
                 B.gid_of.resize(id + 1, -1);
             }
-            B.fam_of[id] = intern(B.fam_ids, all[i]->getGene().getFamily());
-            B.gid_of[id] = intern(B.gene_ids, all[i]->getGene().getID());
+            B.fam_of[id] = fid[i];
+            B.gid_of[id] = gidv[i];
+            // ids count the distinct strings in order of first occurrence: the string -> id maps of the host side
+            // (pairs tables, elements met later without a numID) are filled as new ids appear
+            if (fid[i] == (int32_t)B.fam_ids.size()) B.fam_ids[fblob.substr((size_t)foff[i], (size_t)(foff[i + 1] - foff[i]))] = fid[i];
+            if (gidv[i] == (int32_t)B.gene_ids.size()) B.gene_ids[gblob.substr((size_t)goff[i], (size_t)(goff[i + 1] - goff[i]))] = gidv[i];
         }
+    }
+    B.masked.resize(genelists.size());
+    for (size_t l = 0; l < genelists.size(); l++) {
         const std::vector<ListElement*>& re = genelists[l]->getRemappedElements();
         for (size_t i = 0; i < re.size(); i++) {
-            const Gene& g = re[i]->getGene();
-            fam.push_back(intern(B.fam_ids, g.getFamily()));
-            gid.push_back(intern(B.gene_ids, g.getID()));
-            num.push_back(re[i]->getNumID());
+            const int id = re[i]->getNumID();
+            fam.push_back(B.fam_of[id]);
+            gid.push_back(B.gid_of[id]);
+            num.push_back(id);
             flags.push_back((re[i]->getOrientation() ? IADH_F_STRAND : 0) | (re[i]->isMasked() ? IADH_F_MASKED : 0));
         }
         B.list_fam.resize(genelists.size());
@@ -141,8 +169,6 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
     d.gid = gid.data();
     d.num_id = num.data();
     d.flags = flags.data();
-    const char* dev = getenv("IADH_DEVICE");
-    g_warmup.join();
     if (settings.useFamily())
         check(iadh_create(&d, dev ? atoi(dev) : 0, &B.ctx), "iadh_create");
     else {

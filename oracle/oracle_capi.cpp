@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../include/iadhore_b200.h"
@@ -357,6 +358,21 @@ int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; 
 void oracle_free_result(oracle_result* r) { delete r; }
 void oracle_trim(void) {}
 int oracle_warmup(int) { return IADH_OK; }
+
+// Interning as the reference's string-keyed containers imply it (GeneFamily.cpp:12-16 map<string, string>,
+// GHM.cpp:34-50 family-string hash): equal strings, equal ids; ids in order of first occurrence.
+int oracle_intern_strings(const char* blob, const int64_t* off, int64_t n, int, int32_t* ids, int32_t* n_distinct)
+{
+    std::unordered_map<std::string, int32_t> seen;
+    for (int64_t i = 0; i < n; i++) {
+        const std::string s(blob + off[i], (size_t)(off[i + 1] - off[i]));
+        auto it = seen.find(s);
+        if (it == seen.end()) it = seen.emplace(s, (int32_t)seen.size()).first;
+        ids[i] = it->second;
+    }
+    *n_distinct = (int32_t)seen.size();
+    return IADH_OK;
+}
 
 // GeneList::remapTandemsFamily (GeneList.cpp:143-200), restated sequentially: the three passes in
 // the reference's order, remapTo() (Gene.cpp:51-62) sets the gene's flag and clears the target's.

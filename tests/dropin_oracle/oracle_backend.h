@@ -17,4 +17,5 @@
 #define iadh_result_stats oracle_result_stats
 #define iadh_free_result oracle_free_result
 #define iadh_warmup oracle_warmup
+#define iadh_intern_strings oracle_intern_strings
 #define iadh_last_error oracle_last_error

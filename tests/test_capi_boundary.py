@@ -86,3 +86,11 @@ def test_no_cpu_fallback():
     tr = read_trace(pl.golden_traces()[0])
     with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback|failed"):
         capi.load_product(tr.dataset)
+
+
+def test_oracle_interning_is_first_occurrence_order():
+    names = ["fam7", "fam2", "fam7", "", "fam2", "x" * 300, "", "fam7a", "fam7"]
+    ids, nd = capi.intern_strings(names, lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    assert ids.tolist() == [0, 1, 0, 2, 1, 3, 2, 4, 0] and nd == 5
+    ids, nd = capi.intern_strings([], lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    assert len(ids) == 0 and nd == 0

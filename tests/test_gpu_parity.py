@@ -323,6 +323,28 @@ def test_family_expansion_build_is_invisible(sort_max, monkeypatch):
         gpu.close()
 
 
+def test_device_string_interning_matches_oracle():
+    """iadh_intern_strings (the hashing half of the family join, on the device) against the oracle's unordered_map:
+    same dense ids in first-occurrence order -- gene and family names of a synthetic set, heavy duplication, empty and
+    long strings, strings that differ only in their last byte, and 300k strings over 50k distinct values."""
+    rng = np.random.RandomState(5)
+    cfg = synth.config_small(seed=9)
+    data = synth.generate(cfg)
+    genes = [g for gn in cfg.genomes for lst in data[gn.name] for g in lst]
+    cases = [[g[0] for g in genes] + [g[0] for g in genes[::3]],
+             ["F%d" % g[2] for g in genes],
+             ["", "a", "", "a" * 1000, "a" * 999 + "b", "a" * 1000, "b", "a"],
+             ["fam%d" % v for v in rng.randint(0, 50000, 300000)],
+             ["same"] * 5000]
+    for strings in cases:
+        a, na = capi.intern_strings(strings)
+        b, nb = capi.intern_strings(strings, lib_path=capi.ORACLE_LIB, prefix="oracle_")
+        assert na == nb == len(set(strings))
+        assert np.array_equal(a, b)
+    a, na = capi.intern_strings([])
+    assert len(a) == 0 and na == 0
+
+
 def test_dense_build_matches_oracle():
     """BASELINE config 5 shape at 3 % scale (tandem-rich, >= 50 members per family): dots of every
     list pair, both orientations, in the reference's (x, y) order."""
