@@ -565,6 +565,204 @@ __global__ void __launch_bounds__(256) seg_sort_cta_kernel(int n_seg, const int6
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Dataset tables on the device (family mode; iadh_create): the family CSR and everything K1 reads per member slot are
+// built from the flat element arrays by kernels -- the join side of DataSet::getGeneFamilies / GHM::buildMatrixFast
+// (the y-side map<family, vector<element>> of GHM.cpp:37-50, built once for the whole dataset instead of per pair).
+//   count    family histogram + gene-ID histogram (an ID seen twice switches K1 to its exact ID test, flags bit 3)
+//   scan     exclusive prefix sum -> fam_ptr
+//   scatter  element -> a slot of its family's bucket (atomic cursor, arbitrary order inside the bucket)
+//   sort     every bucket ascending (warp-register bitonic; shared-memory / global bitonic for large families):
+//            members ascending by global element index, as the tile kernels' binary searches and the (family, list)
+//            table expect
+//   records  per slot: (coordinate << 1 | strand), list; per element: own slot; strand prefix sum
+// exclusive scan of n int32 (out has n + 1 entries, out[n] = total): block-local scan, scan of the block sums, add
+__global__ void __launch_bounds__(1024) scan_block_kernel(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out,
+                                                          int32_t* __restrict__ block_sum)
+{
+    __shared__ int32_t warp_sum[32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t v = i < n ? in[i] : 0;
+    int total;
+    int32_t excl = warp_excl_scan(v, lane, total);
+    if (lane == 31) warp_sum[w] = total;
+    __syncthreads();
+    if (w == 0) {
+        int t2;
+        const int32_t x = warp_sum[lane];
+        const int32_t e = warp_excl_scan(x, lane, t2);
+        warp_sum[lane] = e;
+        if (lane == 31) block_sum[blockIdx.x] = t2;
+    }
+    __syncthreads();
+    if (i < n) out[i] = warp_sum[w] + excl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t* block_sum, int n_blocks)
+{
+    __shared__ int32_t warp_sum[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int32_t v = i < n_blocks ? block_sum[i] : 0;
+        int total;
+        const int32_t excl = warp_excl_scan(v, lane, total);
+        if (lane == 31) warp_sum[w] = total;
+        __syncthreads();
+        if (w == 0) {
+            int t2;
+            warp_sum[lane] = warp_excl_scan(warp_sum[lane], lane, t2);
+        }
+        __syncthreads();
+        const int32_t e = carry + warp_sum[w] + excl;
+        if (i < n_blocks) block_sum[i] = e;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = e + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sum[n_blocks] = carry;   // grand total
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(int32_t* __restrict__ out, int64_t n, const int32_t* __restrict__ block_sum, int n_blocks)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_sum[i >> 10];
+    if (i == n) out[n] = block_sum[n_blocks];
+}
+
+__global__ void __launch_bounds__(256) tab_count_kernel(const int32_t* __restrict__ fam, const int32_t* __restrict__ gid, int64_t n,
+                                                        int32_t* fam_cnt, int32_t* gid_cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&fam_cnt[fam[i]], 1);
+    const int g = gid[i];
+    if (g >= 0) atomicAdd(&gid_cnt[g], 1);
+}
+__global__ void __launch_bounds__(256) tab_scatter_kernel(const int32_t* __restrict__ fam, const int64_t* __restrict__ list_off, int n_lists,
+                                                          const int32_t* __restrict__ gid, const int32_t* __restrict__ gid_cnt, int64_t n,
+                                                          const int32_t* __restrict__ fam_ptr, int32_t* cursor, int32_t* __restrict__ members,
+                                                          int32_t* __restrict__ elem_list, uint8_t* __restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int f = fam[i];
+    members[fam_ptr[f] + atomicAdd(&cursor[f], 1)] = (int32_t)i;
+    int lo = 0, hi = n_lists;   // the list of element i: largest l with list_off[l] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (list_off[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    elem_list[i] = lo;
+    const int g = gid[i];
+    if (g < 0 || gid_cnt[g] > 1) flags[i] |= 8;   // the gene ID occurs more than once: exact ID test in K1
+}
+// segments of a CSR: bucket f = keys[ptr[f] .. ptr[f + 1])
+template <int RMAX>
+__global__ void __launch_bounds__(256) csr_sort_warp_kernel(int n_seg, const int32_t* __restrict__ ptr, uint32_t* __restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int sg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sg < n_seg; sg += warps_total) {
+        const int b = ptr[sg], n = ptr[sg + 1] - b;
+        if (RMAX == 8 ? (n < 2 || n > 256) : (n <= 256 || n > SORT_WARP_MAX)) continue;
+        uint32_t* __restrict__ kb = keys + b;
+        if (RMAX == 8) {
+            if (n <= 32) warp_sort_regs<1>(kb, n, lane);
+            else if (n <= 64) warp_sort_regs<2>(kb, n, lane);
+            else if (n <= 128) warp_sort_regs<4>(kb, n, lane);
+            else warp_sort_regs<8>(kb, n, lane);
+        } else {
+            if (n <= 512) warp_sort_regs<16>(kb, n, lane);
+            else warp_sort_regs<32>(kb, n, lane);
+        }
+    }
+}
+// buckets of more than 1,024 members: one CTA each; up to SORT_MAX keys in shared memory, beyond that on global memory
+// with the all-ascending form of the network (every merge starts with a "flip" stage, i against k - 1 - i, then plain
+// half-cleaners): every compare-exchange moves the smaller key down, so the +infinity padding above position n never
+// moves and stays virtual -- pairs that reach beyond n are skipped
+__global__ void __launch_bounds__(256) csr_sort_cta_kernel(int n_seg, const int32_t* __restrict__ ptr, uint32_t* __restrict__ keys)
+{
+    __shared__ uint32_t s[SORT_MAX];
+    const int tid = threadIdx.x;
+    for (int sg = blockIdx.x; sg < n_seg; sg += gridDim.x) {
+        const int b = ptr[sg], n = ptr[sg + 1] - b;
+        if (n <= SORT_WARP_MAX) continue;
+        uint32_t* __restrict__ kb = keys + b;
+        int64_t P = 2048;
+        while (P < n) P <<= 1;
+        __syncthreads();
+        if (P <= SORT_MAX) {
+            for (int i = tid; i < (int)P; i += 256) s[i] = i < n ? kb[i] : 0xffffffffu;
+            __syncthreads();
+            for (int k = 2; k <= (int)P; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < ((int)P >> 1); i += 256) {
+                        const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                        const int c = a | j;
+                        const uint32_t va = s[a], vb = s[c];
+                        const bool up = ((a & k) == 0);
+                        if ((va > vb) == up) {
+                            s[a] = vb;
+                            s[c] = va;
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int i = tid; i < n; i += 256) kb[i] = s[i];
+            continue;
+        }
+        for (int64_t k = 2; k <= P; k <<= 1) {
+            const int64_t h = k >> 1;
+            for (int64_t i = tid; i < (P >> 1); i += 256) {   // flip
+                const int64_t blk = i / h, off = i - blk * h;
+                const int64_t a = blk * k + off, c = blk * k + (k - 1 - off);
+                if (c < n) {
+                    const uint32_t va = kb[a], vb = kb[c];
+                    if (va > vb) {
+                        kb[a] = vb;
+                        kb[c] = va;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int64_t j = k >> 2; j > 0; j >>= 1) {
+                for (int64_t i = tid; i < (P >> 1); i += 256) {
+                    const int64_t a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                    const int64_t c = a | j;
+                    if (c < n) {
+                        const uint32_t va = kb[a], vb = kb[c];
+                        if (va > vb) {
+                            kb[a] = vb;
+                            kb[c] = va;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) tab_records_kernel(const int32_t* __restrict__ members, int64_t n_mem, const int32_t* __restrict__ elem_list,
+                                                          const int64_t* __restrict__ list_off, const uint8_t* __restrict__ flags,
+                                                          uint32_t* __restrict__ mem_y, int32_t* __restrict__ mem_list,
+                                                          int32_t* __restrict__ self_slot, int32_t* __restrict__ strand)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mem) return;
+    const int e = members[m];
+    const int l = elem_list[e];
+    const int st = flags[e] & 1;
+    mem_y[m] = ((uint32_t)(e - list_off[l]) << 1) | (uint32_t)st;
+    mem_list[m] = l;
+    self_slot[e] = (int32_t)m;
+    strand[m] = st;
+}
+
 // task records <- compact per-GHM arrays (family-expansion path: counts were taken outside the records)
 __global__ void scatter_cnt_kernel(GhmTask* __restrict__ tasks, int n, const uint32_t* __restrict__ cnt)
 {
@@ -777,6 +975,39 @@ void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_ite
     launch_seg_sort(n_seg, dot_off, cnt, keys, sm_count, st);
 }
 int expand_sort_max(void) { return SORT_MAX; }
+
+// exclusive scan, out[n] = total; block_sum holds n / 1024 + 2 entries
+void launch_scan_i32(const int32_t* in, int64_t n, int32_t* out, int32_t* block_sum, cudaStream_t st)
+{
+    const int n_blocks = (int)((n + 1023) / 1024);
+    if (n_blocks > 0) scan_block_kernel<<<n_blocks, 1024, 0, st>>>(in, n, out, block_sum);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(block_sum, n_blocks);
+    scan_add_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(out, n, block_sum, n_blocks);
+}
+
+// Dataset tables of iadh_create on the device (family mode).  In: fam / gid / flags (strand, mask bits) / list_off on
+// the device; zeroed fam_cnt[n_fam + 1], gid_cnt[n_gid + 1], cursor[n_fam + 1].  Out: fam_ptr, members, elem_list,
+// mem_y, mem_list, self_slot, plus_prefix, flags bit 3.  tmp = n ints, block_sum = n / 1024 + 2 ints.
+void launch_tables(const int32_t* fam, const int32_t* gid, uint8_t* flags, const int64_t* list_off, int n_lists, int64_t n, int n_fam,
+                   int32_t* fam_cnt, int32_t* gid_cnt, int32_t* cursor, int32_t* fam_ptr, int32_t* members, int32_t* elem_list,
+                   uint32_t* mem_y, int32_t* mem_list, int32_t* self_slot, int32_t* plus_prefix, int32_t* tmp, int32_t* block_sum,
+                   int sm_count, cudaStream_t st)
+{
+    if (n == 0) {
+        cudaMemsetAsync(fam_ptr, 0, 4 * (size_t)(n_fam + 1), st);
+        cudaMemsetAsync(plus_prefix, 0, 4, st);
+        return;
+    }
+    const unsigned g256 = (unsigned)((n + 255) / 256);
+    tab_count_kernel<<<g256, 256, 0, st>>>(fam, gid, n, fam_cnt, gid_cnt);
+    launch_scan_i32(fam_cnt, n_fam, fam_ptr, block_sum, st);
+    tab_scatter_kernel<<<g256, 256, 0, st>>>(fam, list_off, n_lists, gid, gid_cnt, n, fam_ptr, cursor, members, elem_list, flags);
+    csr_sort_warp_kernel<8><<<std::min((n_fam + 7) / 8, sm_count * 16), 256, 0, st>>>(n_fam, fam_ptr, (uint32_t*)members);
+    csr_sort_warp_kernel<32><<<std::min((n_fam + 7) / 8, sm_count * 8), 256, 0, st>>>(n_fam, fam_ptr, (uint32_t*)members);
+    csr_sort_cta_kernel<<<std::min(n_fam, sm_count * 4), 256, 0, st>>>(n_fam, fam_ptr, (uint32_t*)members);
+    tab_records_kernel<<<g256, 256, 0, st>>>(members, n, elem_list, list_off, flags, mem_y, mem_list, self_slot, tmp);
+    launch_scan_i32(tmp, n, plus_prefix, block_sum, st);
+}
 
 void launch_mask(uint8_t* flags, int64_t begin, int64_t end, int set, cudaStream_t st)
 {

@@ -46,6 +46,10 @@ void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_ite
                            uint32_t* cursor, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm,
                            int sm_count, cudaStream_t st);
 int expand_sort_max(void);
+void launch_tables(const int32_t* fam, const int32_t* gid, uint8_t* flags, const int64_t* list_off, int n_lists, int64_t n, int n_fam,
+                   int32_t* fam_cnt, int32_t* gid_cnt, int32_t* cursor, int32_t* fam_ptr, int32_t* members, int32_t* elem_list,
+                   uint32_t* mem_y, int32_t* mem_list, int32_t* self_slot, int32_t* plus_prefix, int32_t* tmp, int32_t* block_sum,
+                   int sm_count, cudaStream_t st);
 void launch_intern(const char* blob, const int64_t* off, int64_t n, int32_t* table, uint32_t table_size, int32_t* rep, int32_t* cmin,
                    int32_t* flag_scan, int32_t* block_sum, int32_t* total, int32_t* ids, cudaStream_t st);
 void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64_t* list_off, int n_fam, int n_lists,
@@ -1771,6 +1775,43 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
             }
             c->flags[i] = f;
         }
+    // (IADH_NO_FAM_TABLE: test knob for the binary-search fallback used when the table would be too large)
+    const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
+    const bool have_table = tbl > 0 && tbl <= ((int64_t)128 << 20) && !getenv("IADH_NO_FAM_TABLE");
+    int rc = IADH_OK;
+    // Family mode: the join tables (family CSR, member records, strand prefix, own slots, repeated-ID flags) are built
+    // on the device from the flat arrays (launch_tables, build_kernels.cu); IADH_HOST_TABLES=1 keeps the host
+    // construction below (test knob; pairs mode always: its buckets come from the pair table).
+    const bool device_tables = !pairs && !getenv("IADH_HOST_TABLES");
+    if (device_tables) {
+        int max_gid = -1;
+        for (int64_t i = 0; i < total; i++) max_gid = std::max(max_gid, d->gid[i]);
+        const size_t nf = (size_t)c->n_fam + 1, ng = (size_t)max_gid + 2, nb = (size_t)(std::max<int64_t>(total, (int64_t)nf) / 1024 + 4);
+        DBuf t_cnt, t_tmp;   // zeroed counters [fam_cnt | cursor | gid_cnt], then scratch [tmp | block sums]
+        if (!rc) rc = upload(c->d_list_off, c->list_off.data(), 8 * c->list_off.size(), c->st);
+        if (!rc) rc = upload(c->d_fam, key, 4 * (size_t)total, c->st);
+        if (!rc) rc = upload(c->d_gid, d->gid, 4 * (size_t)total, c->st);
+        if (!rc) rc = upload(c->d_num_id, d->num_id, 4 * (size_t)total, c->st);
+        if (!rc) rc = upload(c->d_flags, c->flags.data(), (size_t)total, c->st);
+        if (!rc && (t_cnt.ensure(4 * (2 * nf + ng) + 16) != cudaSuccess || t_tmp.ensure(4 * ((size_t)total + nb) + 16) != cudaSuccess ||
+                    c->d_fam_ptr.ensure(4 * nf + 16) != cudaSuccess || c->d_fam_members.ensure(4 * (size_t)total + 16) != cudaSuccess ||
+                    c->d_elem_list.ensure(4 * (size_t)total + 16) != cudaSuccess || c->d_mem_y.ensure(4 * (size_t)total + 16) != cudaSuccess ||
+                    c->d_mem_list.ensure(4 * (size_t)total + 16) != cudaSuccess || c->d_self_slot.ensure(4 * (size_t)total + 16) != cudaSuccess ||
+                    c->d_plus_prefix.ensure(4 * (size_t)total + 16) != cudaSuccess))
+            rc = fail(IADH_ERR_CUDA, "out of device memory");
+        if (!rc) {
+            cudaMemsetAsync(t_cnt.p, 0, 4 * (2 * nf + ng), c->st);
+            int32_t* fam_cnt = t_cnt.as<int32_t>();
+            launch_tables(c->d_fam.as<int32_t>(), c->d_gid.as<int32_t>(), c->d_flags.as<uint8_t>(), c->d_list_off.as<int64_t>(), d->n_lists, total,
+                          c->n_fam, fam_cnt, fam_cnt + 2 * nf, fam_cnt + nf, c->d_fam_ptr.as<int32_t>(), c->d_fam_members.as<int32_t>(),
+                          c->d_elem_list.as<int32_t>(), c->d_mem_y.as<uint32_t>(), c->d_mem_list.as<int32_t>(), c->d_self_slot.as<int32_t>(),
+                          c->d_plus_prefix.as<int32_t>(), t_tmp.as<int32_t>(), t_tmp.as<int32_t>() + total, c->sm_count, c->st);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(IADH_ERR_CUDA, "dataset table kernels failed to launch");
+        }
+        if (!rc && cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "dataset tables failed on the device");
+        t_cnt.release();
+        t_tmp.release();
+    } else {
     // family CSR: members ascending by global element index
     std::vector<int32_t> fam_ptr(c->n_fam + 1, 0), members;
     if (!pairs) {
@@ -1846,10 +1887,6 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
             for (int64_t i = 0; i < total; i++)
                 if (d->gid[i] < 0 || seen[d->gid[i]] > 1) c->flags[i] |= 8;
     }
-    // (IADH_NO_FAM_TABLE: test knob for the binary-search fallback used when the table would be too large)
-    const int64_t tbl = (int64_t)c->n_fam * (d->n_lists + 1);
-    const bool have_table = tbl > 0 && tbl <= ((int64_t)128 << 20) && !getenv("IADH_NO_FAM_TABLE");
-    int rc = IADH_OK;
     if (!rc) rc = upload(c->d_mem_y, mem_y.data(), 4 * mem_y.size(), c->st);
     if (!rc) rc = upload(c->d_plus_prefix, plus_prefix.data(), 4 * plus_prefix.size(), c->st);
     if (!rc) rc = upload(c->d_self_slot, self_slot.data(), 4 * self_slot.size(), c->st);
@@ -1862,6 +1899,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (!rc) rc = upload(c->d_flags, c->flags.data(), (size_t)total, c->st);
     if (!rc) rc = upload(c->d_fam_ptr, fam_ptr.data(), 4 * fam_ptr.size(), c->st);
     if (!rc) rc = upload(c->d_fam_members, members.data(), 4 * members.size(), c->st);
+    }
     if (!rc && have_table) {  // the (family, list) table is built on the device from the CSR just uploaded
         if (c->d_fam_list.ensure(4 * (size_t)tbl) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
         else

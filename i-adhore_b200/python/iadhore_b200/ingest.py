@@ -152,7 +152,12 @@ def build_dataset(lists: List[List[Gene]], tandem_gap: int, device=None, pairs=N
     if device is not None and ps is None:
         from . import capi
         raw_off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
-        gids = [gid_map.setdefault(g[0], len(gid_map)) for lst in lists for g in lst]
+        # gene-ID strings -> dense ids on the device (iadh_intern_strings: first-occurrence order, i.e. exactly the
+        # numbering the dict below would produce); the dict is then only a lookup table for the per-list loop
+        names = [g[0] for lst in lists for g in lst]
+        gid_arr, _ = capi.intern_strings(names, device=device)
+        gids = gid_arr.tolist()
+        gid_map.update(zip(names, gids))
         rem_all = capi.remap_tandems(raw_off, np.fromiter((g[2] for lst in lists for g in lst), np.int32, int(raw_off[-1])),
                                      np.asarray(gids, np.int32),
                                      np.fromiter((g[1] for lst in lists for g in lst), np.uint8, int(raw_off[-1])),

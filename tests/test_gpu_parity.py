@@ -258,11 +258,14 @@ def _dup_id_dataset(seed=5):
     return capi.Dataset(off, fam, gid, np.arange(n, dtype=np.int32) + 1000, flags)
 
 
+@pytest.mark.parametrize("host_tables", [False, True])
 @pytest.mark.parametrize("no_table", [False, True])
-def test_build_with_duplicate_gene_ids(no_table, monkeypatch):
+def test_build_with_duplicate_gene_ids(no_table, host_tables, monkeypatch):
     ds = _dup_id_dataset()
     if no_table:
         monkeypatch.setenv("IADH_NO_FAM_TABLE", "1")
+    if host_tables:   # iadh_create builds the join tables on the device by default; this is the host construction
+        monkeypatch.setenv("IADH_HOST_TABLES", "1")
     gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
     xs, ys = capi.plan_pairs(np.diff(ds.list_off))
     dg, dc = gpu.build_dots(xs, ys), cpu.build_dots(xs, ys)
@@ -343,6 +346,32 @@ def test_device_string_interning_matches_oracle():
         assert np.array_equal(a, b)
     a, na = capi.intern_strings([])
     assert len(a) == 0 and na == 0
+
+
+@pytest.mark.parametrize("host_tables", [False, True])
+def test_join_tables_with_giant_families(host_tables, monkeypatch):
+    """iadh_create's device-built join tables on family sizes that take every path of the bucket sort: 1 ... 32 members
+    (one register per lane), hundreds (8 / 32 registers), 3,000 (shared memory) and 10,000 (global-memory network with
+    virtual padding) -- dots of a few list pairs against the oracle, with the host construction as a second witness."""
+    if host_tables:
+        monkeypatch.setenv("IADH_HOST_TABLES", "1")
+    rng = np.random.RandomState(17)
+    sizes = [3000, 10000] + [700, 300, 150, 40] * 3 + list(rng.randint(1, 33, 400))
+    fam = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
+    rng.shuffle(fam)
+    n = len(fam)
+    n_lists = 12
+    off = np.linspace(0, n, n_lists + 1).astype(np.int64)
+    gid = np.arange(n, dtype=np.int32)
+    flags = rng.randint(0, 2, n).astype(np.uint8)
+    ds = capi.Dataset(off, fam, gid, np.arange(n, dtype=np.int32) + 7, flags)
+    gpu, cpu = capi.load_product(ds), pl.oracle_engine(ds)
+    xs, ys = [0, 3, 5, 11, 2], [0, 4, 5, 1, 9]
+    dg, dc = gpu.build_dots(xs, ys), cpu.build_dots(xs, ys)
+    assert sum(len(a) + len(b) for a, b in dc) > 10 ** 6
+    for (a0, a1), (b0, b1) in zip(dg, dc):
+        assert np.array_equal(a0, b0) and np.array_equal(a1, b1)
+    gpu.close()
 
 
 def test_dense_build_matches_oracle():
