@@ -362,13 +362,16 @@ struct iadh_ctx {
     // a batch whose clustering workspace would exceed this is bisected (level-2 calls): set from the
     // device's memory at create time, IADH_WS_BUDGET_MB overrides
     int64_t ws_budget = (int64_t)1 << 62;
+    int64_t pass_ratio_hl = 1500;   // the same threshold for profile GHMs (IADH_PASS_RATIO_HL)
     int64_t pass_ratio = 1500;  // (config 3: 1,276 -> fused, tail-bound either way; 1/8 of config 4: 3,680 -> passes)
     // workspace bytes per chunk.  Default: one chunk.  Measured on config 4: chunks small enough for L2
     // (256 MB of workspace) serialise 52 x 34 short launches and take 241 ms instead of 87 ms.
     int64_t pass_chunk_bytes = (int64_t)1 << 60;
     // resident K2 (the GHM's clustering state in shared memory, one launch per size class): GHMs whose
     // RsLayout fits res_max_bytes; the classes are shared-memory budgets per CTA
-    int resident = 0;               // IADH_RESIDENT=1 switches the path on (measured slower than the pass path: see DESIGN.md)
+    // shared-memory resident K2: 0 off, 1 on, 2 (default) = for batches of profile searches only -- measured on config 4,
+    // 32 searches: batch 25.6 -> 19.9 ms; level-2 call and single searches are faster on the global-memory paths
+    int resident = 2;
     int res_max_bytes = 200 * 1024;
     int res_wide_min = 600, res_wide_nt = 128;   // latency-bound calls: GHMs with >= res_wide_min dots get wide CTAs
     cudaStream_t st_res[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1058,7 +1061,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         res_launches.clear();
         res_items.clear();
         std::fill(is_res.begin(), is_res.end(), 0);
-        if (c->resident && c->prm.n_gaps > 0) {
+        if ((c->resident == 1 || (c->resident == 2 && hl && pf.batch)) && c->prm.n_gaps > 0) {
             int64_t sum_d = 0, max_d = 1;
             for (int i : order) {
                 const int64_t D = (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
@@ -1107,7 +1110,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
             sum_d += D;
             max_d = std::max(max_d, D);
         }
-        pass_mode = n_act >= c->pass_min && c->prm.n_gaps > 0 && sum_d / max_d >= c->pass_ratio;
+        pass_mode = n_act >= c->pass_min && c->prm.n_gaps > 0 && sum_d / max_d >= (hl ? c->pass_ratio_hl : c->pass_ratio);
         if (pass_mode) {
             // phase 1 runs one pass per launch over (GHM, orientation) items, heaviest orientation first;
             // phase 2 through the fused kernel with "phase 2 only" items
@@ -1954,7 +1957,8 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (const char* e = getenv("IADH_EXPAND_MIN")) c->expand_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_HL_EXPAND_MIN")) c->hl_expand_min = std::max(1, atoi(e));
     if (const char* e = getenv("IADH_EXPAND_SORT_MAX")) c->expand_sort_max = std::max(1, atoi(e));
-    if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = std::max(0, atoi(e));
+    if (const char* e = getenv("IADH_PASS_RATIO")) c->pass_ratio = c->pass_ratio_hl = std::max(0, atoi(e));
+    if (const char* e = getenv("IADH_PASS_RATIO_HL")) c->pass_ratio_hl = std::max(0, atoi(e));
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char* e = getenv("IADH_PASS_CFG")) {
         sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);

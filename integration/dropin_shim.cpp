@@ -40,6 +40,8 @@ namespace {
 
 struct Bridge {
     iadh_ctx* ctx = nullptr;
+    const void* owner = nullptr;   // the gene lists this context was made from (a second DataSet gets its own)
+    size_t owner_lists = 0;
     std::map<std::string, int> fam_ids, gene_ids;
     std::vector<std::vector<unsigned char> > masked;  // shadow of ListElement::isMasked per list
     std::vector<int32_t> fam_of, gid_of;               // by ListElement numID (profile elements are copies)
@@ -62,6 +64,10 @@ double wall()
 
 void report()
 {
+    if (B.ctx) {   // (atexit: streams, events and device blocks go back before the CUDA runtime shuts down)
+        iadh_destroy(B.ctx);
+        B.ctx = nullptr;
+    }
     if (!getenv("IADH_VERBOSE")) return;
     fprintf(stderr,
             "[iadh] profile searches: %ld calls, %lld GHMProfiles, %lld multiplicons returned, %lld dropped before unpacking, %lld kept; "
@@ -104,11 +110,19 @@ void check(int rc, const char* what)
 // Flatten the DataSet (after mapGenes + remapTandems + sortGeneLists) and create the device context.
 void ensure_context(const std::vector<GeneList*>& genelists, const Settings& settings, GenePairs* genepairs)
 {
-    if (B.ctx) return;
+    // one context per DataSet: a different set of gene lists (another DataSet in the same process) replaces it
+    const void* owner = genelists.empty() ? (const void*)&genelists : (const void*)genelists[0];
+    if (B.ctx && B.owner == owner && B.owner_lists == genelists.size()) return;
+    if (B.ctx) {
+        iadh_destroy(B.ctx);
+        B = Bridge();
+    }
+    B.owner = owner;
+    B.owner_lists = genelists.size();
     std::vector<int64_t> off(1, 0);
     std::vector<int32_t> fam, gid, num;
     std::vector<uint8_t> flags;
-    const char* dev = getenv("IADH_DEVICE");
+    const char* dev = getenv("IADH_DEVICE");   // (MPI build: one rank per GPU, e.g. IADH_DEVICE=$OMPI_COMM_WORLD_LOCAL_RANK)
     g_warmup.join();
     // Strings -> dense ids on the device (iadh_intern_strings), once: the family and the gene ID of every element of
     // every list, in list order.  Everything below -- and K1's join -- works on these integers; the reference would
@@ -194,7 +208,11 @@ void ensure_context(const std::vector<GeneList*>& genelists, const Settings& set
         }
         check(iadh_create_pairs(&d, pptr.data(), pids.data(), n_genes, dev ? atoi(dev) : 0, &B.ctx), "iadh_create_pairs");
     }
-    atexit(report);
+    static bool registered = false;
+    if (!registered) {
+        atexit(report);
+        registered = true;
+    }
 
     iadh_params p;
     int gaps[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -340,6 +358,39 @@ long long prefilter_packed(const uint8_t* bytes, size_t nbytes, int S, int L, co
     return n - kept;
 }
 
+// Multi-GPU (the reference's MPI build, one rank per GPU of the box): every rank searches its share
+// (rank / n_ranks arguments of the library calls: the reference's own partitions, levelTwo.cpp:98-111 and
+// parallel.cpp:96-156) and the packed multiplicons of all ranks are exchanged inside the library over NCCL
+// (iadh_allgather_results) -- the MPI_Allgather + MPI_Allgatherv of levelTwo.cpp:225-269 / higherLevel.cpp:279-314.
+// MPI is only used to hand rank 0's NCCL id to the others.  This block needs mpi.h: it is compiled in the
+// reference's HAVE_MPI configuration only (not available in the authoring image, where bench.py / tools/dist_check.py
+// drive the same library calls through torch.distributed instead).
+void join_ranks()
+{
+#ifdef HAVE_MPI
+    if (B.n_ranks > 1 || (int)ParToolBox::getNumProcesses() <= 1) return;
+    B.rank = ParToolBox::getProcID();
+    B.n_ranks = (int)ParToolBox::getNumProcesses();
+    uint8_t id[128];
+    if (B.rank == 0) check(iadh_comm_unique_id(id, sizeof id), "iadh_comm_unique_id");
+    MPI_Bcast(id, (int)sizeof id, MPI_BYTE, 0, MPI_COMM_WORLD);
+    check(iadh_comm_init(B.ctx, id, sizeof id, B.rank, B.n_ranks), "iadh_comm_init");
+#endif
+}
+// this rank's result -> all ranks' results in rank order (single rank: unchanged)
+iadh_result* gather(iadh_result* mine)
+{
+#ifdef HAVE_MPI
+    if (B.n_ranks > 1) {
+        iadh_result* all = NULL;
+        check(iadh_allgather_results(B.ctx, &mine, 1, &all), "iadh_allgather_results");
+        iadh_free_result(mine);
+        return all;
+    }
+#endif
+    return mine;
+}
+
 }  // namespace
 
 // ---- replaces levelTwo.cpp:177-292 --------------------------------------------------------------
@@ -348,8 +399,10 @@ void DataSet::parallelLevel2ADHoReDyn()
     if (settings.getClusterType() != Collinear)
         throw std::runtime_error("the B200 path implements collinear detection only (cluster_type=collinear)");
     ensure_context(genelists, settings, genepairs);
+    join_ranks();
     iadh_result* res = NULL;
     check(iadh_level2_all_pairs(B.ctx, B.rank, B.n_ranks, &res), "iadh_level2_all_pairs");
+    res = gather(res);
     size_t nbytes = 0;
     const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
     std::vector<Multiplicon*> mplicons;
@@ -406,6 +459,7 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     iadh_result* res = NULL;
     const double w2 = wall();
     check(iadh_profile_search(B.ctx, &pd, B.rank, B.n_ranks, &res), "iadh_profile_search");
+    res = gather(res);
     const double w3 = wall();
     size_t nbytes = 0;
     const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
