@@ -369,8 +369,9 @@ struct iadh_ctx {
     int64_t pass_chunk_bytes = (int64_t)1 << 60;
     // resident K2 (the GHM's clustering state in shared memory, one launch per size class): GHMs whose
     // RsLayout fits res_max_bytes; the classes are shared-memory budgets per CTA
-    // shared-memory resident K2: 0 off, 1 on, 2 (default) = for batches of profile searches only -- measured on config 4,
-    // 32 searches: batch 25.6 -> 19.9 ms; level-2 call and single searches are faster on the global-memory paths
+    // shared-memory resident K2: 0 off, 1 on, 2 (default) = for large batches of profile searches only (>= pass_min active
+    // GHMs) -- measured on config 4: 32 searches 25.6 -> 19.9 ms, 8 searches 11.9 -> 12.6 ms; the level-2 call and single
+    // searches are faster on the global-memory paths
     int resident = 2;
     int res_max_bytes = 200 * 1024;
     int res_wide_min = 600, res_wide_nt = 128;   // latency-bound calls: GHMs with >= res_wide_min dots get wide CTAs
@@ -516,6 +517,20 @@ static void list_partition(const iadh_ctx* c, int rank, int n_ranks, std::vector
 }
 
 // ---------------------------------------------------------------------------------------------
+
+// Result streams travel to the host on the copy stream in pieces of 2 MB: the calls that follow keep reading small
+// blocks back (dot counts, outcomes) through the same copy engine, and behind one 300 MB transfer -- 8 ranks pulling
+// the gathered level-2 result at once -- such a read-back waited tens of milliseconds (profile batch at 8 GPUs:
+// 39 ms, 10 ms of it work).  In pieces, and with the copy stream at the lowest priority, it slips in between.
+static cudaError_t copy_to_host_in_pieces(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+    const size_t piece = (size_t)2 << 20;
+    for (size_t o = 0; o < bytes; o += piece) {
+        const cudaError_t e = cudaMemcpyAsync((uint8_t*)dst + o, (const uint8_t*)src + o, std::min(piece, bytes - o), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 static int upload(DBuf& d, const void* src, size_t bytes, cudaStream_t st)
 {
@@ -708,6 +723,21 @@ struct TaskOut {
     int64_t out_bytes;
     int32_t status, n_mult, n_clusters, n_aps;
 };
+// Small read-backs (dot counts, outcomes, gather sizes) are written into pinned host memory BY A KERNEL (the pinned
+// block is mapped into the device's address space: unified addressing), not by the copy engine: the copy engine may be
+// busy for tens of milliseconds with a result stream on the copy stream (8 ranks pulling the gathered level-2 result
+// at once), and a 1 MB read-back queued behind it stalled the profile batch that followed (36 ms instead of 10).
+__global__ void readback_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_host, size_t n_words)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) dst_host[i] = src[i];
+}
+static cudaError_t readback(void* host_pinned, const void* dev, size_t bytes, cudaStream_t st)
+{
+    const size_t n_words = (bytes + 3) / 4;   // (blocks are allocated with slack: a rounded-up word is in range)
+    if (n_words == 0) return cudaSuccess;
+    readback_kernel<<<(unsigned)std::min<size_t>((n_words + 255) / 256, 592), 256, 0, st>>>((const uint32_t*)dev, (uint32_t*)host_pinned, n_words);
+    return cudaGetLastError();
+}
 __global__ void gather_cnt_kernel(const GhmTask* __restrict__ tasks, int n, uint32_t* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -884,7 +914,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
         else
             launch_expand_count(c->ds, n_elems, c->d_pair_idx.as<int32_t>(), c->d_row_used.as<uint8_t>(), c->d_cnt.as<uint32_t>(), c->sm_count, c->st);
         CU(cudaEventRecord(c->ev[2], c->st));
-        CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(readback(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, c->st));
         CU(cudaStreamSynchronize(c->st));
         trace_mark(c->st, "K1 expand count + counts D2H");
         st.kernel_launches += 1;
@@ -912,7 +942,7 @@ static int build_stage(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<G
         trace_mark(c->st, "K1 count + tile scan");
         st.kernel_launches += (n_tiles ? 1 : 0) + (n ? 1 : 0);
         gather_cnt_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_cnt.as<uint32_t>());
-        CU(cudaMemcpyAsync(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(readback(c->h_misc.p, c->d_cnt.p, 8 * (size_t)n, c->st));
         CU(cudaStreamSynchronize(c->st));  // (tile_prefix dies at return; the counts are read next)
         trace_mark(c->st, "counts D2H");
         st.d2h_bytes += 8 * (int64_t)n;
@@ -1061,7 +1091,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         res_launches.clear();
         res_items.clear();
         std::fill(is_res.begin(), is_res.end(), 0);
-        if ((c->resident == 1 || (c->resident == 2 && hl && pf.batch)) && c->prm.n_gaps > 0) {
+        if ((c->resident == 1 || (c->resident == 2 && hl && pf.batch && (int)order.size() >= c->pass_min)) && c->prm.n_gaps > 0) {
             int64_t sum_d = 0, max_d = 1;
             for (int i : order) {
                 const int64_t D = (int64_t)tasks[i].cnt[0] + tasks[i].cnt[1];
@@ -1346,7 +1376,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         CU(c->d_outs.ensure(sizeof(TaskOut) * (size_t)n));
         CU(c->h_misc.ensure(sizeof(TaskOut) * (size_t)n));
         gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
-        CU(cudaMemcpyAsync(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        CU(readback(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, c->st));
         CU(cudaStreamSynchronize(c->st));
         trace_mark(c->st, "outcomes D2H");
         st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
@@ -1407,7 +1437,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                                std::min((int)fb.size(), c->sm_count * 2), 256, c->st);
                 CU(cudaEventRecord(c->ev[6], c->st));
                 gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
-                CU(cudaMemcpyAsync(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+                CU(readback(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, c->st));
                 CU(cudaStreamSynchronize(c->st));
                 st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
                 st.h2d_bytes += 4 * (int64_t)fitems.size();
@@ -1503,7 +1533,7 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
         // the copy to the host runs on the copy stream: the caller's next call computes meanwhile
         CU(cudaEventRecord(c->ev_packed, c->st));
         CU(cudaStreamWaitEvent(c->st_copy, c->ev_packed, 0));
-        CU(cudaMemcpyAsync(out.packed.as<uint8_t>() + 4, c->d_out.p, (size_t)total_bytes, cudaMemcpyDeviceToHost, c->st_copy));
+        CU(copy_to_host_in_pieces(out.packed.as<uint8_t>() + 4, c->d_out.p, (size_t)total_bytes, c->st_copy));
         CU(cudaEventRecord(c->ev_copied, c->st_copy));
         CU(cudaEventCreateWithFlags(&out.ready, cudaEventDisableTiming));
         CU(cudaEventRecord(out.ready, c->st_copy));
@@ -1726,10 +1756,12 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;   // (numerically: lowest priority = largest value)
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
     CU(cudaEventCreate(&c->ev_call));
-    CU(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&c->st_copy, cudaStreamNonBlocking, prio_lo));
     CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_copied_recv, cudaEventDisableTiming));
@@ -2594,7 +2626,7 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
     CU(cudaMemcpyAsync(s.d_meta_send.p, hm, 8 * (size_t)META * n, cudaMemcpyHostToDevice, c->st));
     NC(s, s.AllGather(s.d_meta_send.p, s.d_meta_recv.p, 8 * (size_t)META * n, ncclChar, s.comm, c->st));
     int64_t* ha = hm + (size_t)META * n;
-    CU(cudaMemcpyAsync(ha, s.d_meta_recv.p, 8 * (size_t)META * n * N, cudaMemcpyDeviceToHost, c->st));
+    CU(readback(ha, s.d_meta_recv.p, 8 * (size_t)META * n * N, c->st));
     CU(cudaStreamSynchronize(c->st));
     // 2. payload: this rank's bodies in order, body i > 0 preceded by a 4-byte hole (the layout a batch leaves on the
     //    device: run_batch writes the per-profile counts there), padded to the longest rank (NCCL gathers equal slots)
@@ -2668,8 +2700,8 @@ static int allgather_results_impl(iadh_ctx* c, iadh_result* const* mine, int32_t
             if (m[0]) {
                 // (adjacent pieces -- every rank's body of a single result -- would merge into one copy; with n > 1
                 // the pieces of a rank are separated by the other results)
-                cudaError_t e = cudaMemcpyAsync(sp->buf.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k + src_off[k], (size_t)m[0],
-                                                cudaMemcpyDeviceToHost, c->st_copy);
+                cudaError_t e = copy_to_host_in_pieces(sp->buf.as<uint8_t>() + o, (uint8_t*)s.d_recv.p + slot * (size_t)k + src_off[k], (size_t)m[0],
+                                                       c->st_copy);
                 if (e != cudaSuccess) {
                     cudaStreamSynchronize(c->st_copy);
                     sp->buf.release();
