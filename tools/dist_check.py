@@ -65,6 +65,18 @@ def main():
         ok &= same
         print(f"[rank {rank}] 12 profile searches, {'whole profiles per rank' if shard_profiles else 'lists sharded'}: gathered == single-rank: {same}", flush=True)
     eng.clear_masks()
+    # slot reuse of the single-node shared-memory exchange: gathers whose results are still held make later gathers
+    # that map to the same slot take the NCCL route; every stream must come out the same either way
+    held, same = [], True
+    ref = blobs(full.bytes)
+    for it in range(10):
+        g = eng.allgather([eng.level2_all_pairs(rank, world)])[0]
+        same &= blobs(g.bytes) == ref
+        if it < 5:
+            held.append(g)
+    ok &= same
+    print(f"[rank {rank}] 10 more level-2 gathers, 5 results held: every gathered stream == single-rank stream: {same}", flush=True)
+    del held
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     eng.close()
