@@ -117,10 +117,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
+    def __init__(self, gpu_index):
+        self.idx = gpu_index          # one index or a comma-separated list
         self.rows = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Start of the timed region: earlier samples (taken while nvidia-smi initialised, during warm-up) are dropped."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -141,6 +146,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        self.rows = self.rows[self.first:]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -364,11 +370,17 @@ def main():
         eng.comm_init(uid, rank, world)
     setup_s = time.time() - t_setup
 
+    # clocks / throttle reasons of every GPU of the job, sampled by ONE nvidia-smi (rank 0) that is started before the
+    # warm-up: its start-up (NVML initialisation over all GPUs of the box holds driver locks for hundreds of
+    # milliseconds; one per rank stalled the CUDA calls of all ranks at 8 GPUs) is over when the timed region begins
+    clocks = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
     for _ in range(a.warmup):
         hot_path_step(eng, profs, rank, world)
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.mark()
     eng.event_record(0)          # CUDA events on the engine's own stream bracket the K steps
     t0 = time.perf_counter()
     units = 0
@@ -383,7 +395,7 @@ def main():
     barrier()
     wall_dt = time.perf_counter() - t0
     dt = eng.event_elapsed_ms(0, 1) * 1e-3
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     # max over ranks of the time, sum of the units
     if dist:
         t = torch.tensor([dt, wall_dt], dtype=torch.float64, device="cuda")

@@ -29,7 +29,7 @@ def main():
     dist.broadcast(t, 0)
     eng.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
     bp, _ = bench.bench_profiles(ds, wl, 32, lambda: eng.level2_all_pairs().bytes)
-    for rep in range(5):
+    for rep in range(8):
         eng.clear_masks()
         dist.barrier()
         torch.cuda.synchronize()
@@ -42,9 +42,16 @@ def main():
         t3 = time.perf_counter()
         gh = eng.allgather(res)
         t4 = time.perf_counter()
-        print(f"[rank {rank}] rep {rep}: L2 {1e3 * (t1 - t0):.1f} ms (device {r.stats['total_ms']:.1f}), gather {1e3 * (t2 - t1):.1f} ms "
-              f"({g[0].nbytes >> 20} MB), HL batch {1e3 * (t3 - t2):.1f} ms, gather {1e3 * (t4 - t3):.1f} ms", flush=True)
+        g[0].wait()
+        t5 = time.perf_counter()
+        for x in gh:
+            x.wait()
+        t6 = time.perf_counter()
         del r, g, res, gh
+        t7 = time.perf_counter()
+        print(f"[rank {rank}] rep {rep}: L2 {1e3 * (t1 - t0):.1f} ms (device {1e3 * 0:.0f}), gather {1e3 * (t2 - t1):.1f} ms, "
+              f"HL batch {1e3 * (t3 - t2):.1f} ms, gather {1e3 * (t4 - t3):.1f} ms, wait L2 stream {1e3 * (t5 - t4):.1f} ms, "
+              f"wait HL streams {1e3 * (t6 - t5):.1f} ms, free {1e3 * (t7 - t6):.1f} ms", flush=True)
     eng.close()
     dist.destroy_process_group()
 

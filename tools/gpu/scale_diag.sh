@@ -3,7 +3,5 @@ N=${1:-4}
 O=gpurun_out/scale
 mkdir -p $O
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/dist_timing.py c4 > $O/timing_n$N.log 2>&1
-grep "rep [34]" $O/timing_n$N.log | sort | head -16
-IADH_RESIDENT=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 tools/dist_timing.py c4 > $O/timing_n${N}_nores.log 2>&1
-grep "rep [34]" $O/timing_n${N}_nores.log | sort | head -16
+grep "rep [67]" $O/timing_n$N.log | tr '[' '\n' | grep "rep" | sort | head -16
 bash tools/gpu/scale.sh $N
