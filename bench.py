@@ -146,6 +146,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:     # gone before anything else is timed: its NVML shutdown holds driver locks that CUDA calls wait for
+            self.proc.wait(timeout=10)
+        except Exception:
+            self.proc.kill()
         self.rows = self.rows[self.first:]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]

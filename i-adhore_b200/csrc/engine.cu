@@ -46,6 +46,9 @@ void launch_hl_expand_fill(const DatasetDev& ds, const HlGroup* items, int n_ite
                            uint32_t* cursor, const int64_t* dot_off, const uint32_t* cnt, uint32_t* keys, GhmTask* tasks, int n_ghm,
                            int sm_count, cudaStream_t st);
 int expand_sort_max(void);
+void launch_tandem_pairs(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* gid, const uint8_t* flags,
+                         const int64_t* pair_ptr, const int32_t* pair_ids, int n_genes, int gap, int64_t total, uint8_t* remapped,
+                         int32_t* t3, cudaStream_t st);
 void launch_tables(const int32_t* fam, const int32_t* gid, uint8_t* flags, const int64_t* list_off, int n_lists, int64_t n, int n_fam,
                    int32_t* fam_cnt, int32_t* gid_cnt, int32_t* cursor, int32_t* fam_ptr, int32_t* members, int32_t* elem_list,
                    uint32_t* mem_y, int32_t* mem_list, int32_t* self_slot, int32_t* plus_prefix, int32_t* tmp, int32_t* block_sum,
@@ -251,6 +254,8 @@ struct DBuf {
         }
         if (!(p = g_cache.take(bytes, dev, &cap))) {
             size_t want = bytes + bytes / 4 + 256;
+            static const bool trace_alloc = getenv("IADH_TRACE_ALLOC") != nullptr;
+            if (trace_alloc) fprintf(stderr, "[iadh] cache miss: cudaMalloc(%zu MB) for a request of %zu MB\n", want >> 20, bytes >> 20);
             // never change the device's address space under a running kernel: with peer access enabled
             // (NCCL in the same process) cudaMalloc also edits the peers' page tables
             cudaDeviceSynchronize();
@@ -293,6 +298,8 @@ struct HBuf {
         release();
         if ((p = g_cache.take(bytes, -1, &cap))) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 256;
+        static const bool trace_alloc = getenv("IADH_TRACE_ALLOC") != nullptr;
+        if (trace_alloc) fprintf(stderr, "[iadh] cache miss: cudaMallocHost(%zu MB) for a request of %zu MB\n", want >> 20, bytes >> 20);
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         else p = nullptr;
@@ -3241,6 +3248,62 @@ static int intern_strings_impl(const char* blob, const int64_t* off, int64_t n, 
     for (DBuf* b : bufs) b->release();
     cudaStreamDestroy(st);
     if (!rc) *n_distinct_out = total;
+    return rc;
+}
+
+static int remap_tandems_pairs_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                                    int32_t tandem_gap, int device, uint8_t* remapped_out);
+int iadh_remap_tandems_pairs(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                             int32_t tandem_gap, int device, uint8_t* remapped_out)
+{
+    IADH_TRY return remap_tandems_pairs_impl(d, pair_ptr, pair_ids, n_genes, tandem_gap, device, remapped_out);
+    IADH_CATCH
+}
+static int remap_tandems_pairs_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, const int32_t* pair_ids, int32_t n_genes,
+                                    int32_t tandem_gap, int device, uint8_t* remapped_out)
+{
+    if (!d || !remapped_out || !pair_ptr || n_genes < 0 || d->n_lists < 0 || tandem_gap < 0 ||
+        (d->n_lists > 0 && (!d->list_off || !d->gid || !d->flags)))
+        return fail(IADH_ERR_ARG, "iadh_remap_tandems_pairs: bad argument");
+    if (pair_ptr[0] != 0 || (pair_ptr[n_genes] > 0 && !pair_ids)) return fail(IADH_ERR_ARG, "iadh_remap_tandems_pairs: bad pair table");
+    for (int32_t g = 0; g < n_genes; g++)
+        if (pair_ptr[g + 1] < pair_ptr[g]) return fail(IADH_ERR_ARG, "iadh_remap_tandems_pairs: pair_ptr is not ascending at gene %d", g);
+    const int64_t total = d->n_lists ? d->list_off[d->n_lists] : 0;
+    if (total == 0) return IADH_OK;
+    if (total >= 0x7fffffff) return fail(IADH_ERR_CAPACITY, "more than 2^31 elements");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(IADH_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(IADH_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    std::vector<int32_t> elem_list((size_t)total);
+    for (int l = 0; l < d->n_lists; l++) {
+        if (d->list_off[l + 1] < d->list_off[l]) return fail(IADH_ERR_ARG, "list %d has negative size", l);
+        for (int64_t i = d->list_off[l]; i < d->list_off[l + 1]; i++) elem_list[i] = l;
+    }
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DBuf b_off, b_el, b_gid, b_fl, b_pp, b_pi, b_rem, b_t3;
+    int rc = IADH_OK;
+    if (!rc) rc = upload(b_off, d->list_off, 8 * (size_t)(d->n_lists + 1), st);
+    if (!rc) rc = upload(b_el, elem_list.data(), 4 * (size_t)total, st);
+    if (!rc) rc = upload(b_gid, d->gid, 4 * (size_t)total, st);
+    if (!rc) rc = upload(b_fl, d->flags, (size_t)total, st);
+    if (!rc) rc = upload(b_pp, pair_ptr, 8 * (size_t)(n_genes + 1), st);
+    if (!rc) rc = upload(b_pi, pair_ids, 4 * (size_t)pair_ptr[n_genes], st);
+    if (!rc && b_rem.ensure((size_t)total) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
+    if (!rc && b_t3.ensure(4 * (size_t)total) != cudaSuccess) rc = fail(IADH_ERR_CUDA, "out of device memory");
+    if (!rc) {
+        launch_tandem_pairs(b_off.as<int64_t>(), d->n_lists, b_el.as<int32_t>(), b_gid.as<int32_t>(), b_fl.as<uint8_t>(), b_pp.as<int64_t>(),
+                            b_pi.as<int32_t>(), n_genes, tandem_gap, total, b_rem.as<uint8_t>(), b_t3.as<int32_t>(), st);
+        if (cudaMemcpyAsync(remapped_out, b_rem.p, (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail(IADH_ERR_CUDA, "tandem remapping failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaStreamSynchronize(st);
+    DBuf* bufs[] = {&b_off, &b_el, &b_gid, &b_fl, &b_pp, &b_pi, &b_rem, &b_t3};
+    for (DBuf* b : bufs) b->release();
+    cudaStreamDestroy(st);
     return rc;
 }
 

@@ -52,7 +52,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["remap_tandems", "intern_strings", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
+EXPORTS = ["remap_tandems", "remap_tandems_pairs", "intern_strings", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
            "clear_masks", "profile_search", "profile_search_batch", "comm_unique_id", "comm_init", "comm_destroy",
            "allgather_results", "result_bytes", "result_size", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
@@ -418,6 +418,29 @@ def remap_tandems(list_off, fam, gid, strand, tandem_gap: int, device: int = 0, 
         f = getattr(lib, prefix + "last_error")
         f.restype = C.c_char_p
         raise RuntimeError(f"{prefix}remap_tandems failed ({rc}): {f().decode()}")
+    return out.astype(bool)
+
+
+def remap_tandems_pairs(list_off, gid, strand, pair_ptr, pair_ids, tandem_gap: int, device: int = 0, lib_path: str = PRODUCT_LIB,
+                        prefix: str = "iadh_") -> np.ndarray:
+    """GeneList::remapTandemsPairs for every list (elements BEFORE remapping, pair sets as a CSR over the dense gene
+    ids): the `remapped` flag per element."""
+    if not os.path.exists(lib_path):
+        raise RuntimeError(f"{lib_path} is missing: build it first")
+    lib = C.CDLL(lib_path)
+    lo = np.ascontiguousarray(list_off, dtype=np.int64)
+    gi = np.ascontiguousarray(gid, dtype=np.int32)
+    fl = np.ascontiguousarray(strand, dtype=np.uint8)
+    pp = np.ascontiguousarray(pair_ptr, dtype=np.int64)
+    pi = np.ascontiguousarray(pair_ids, dtype=np.int32)
+    d = DatasetDesc(len(lo) - 1, _p(lo, C.c_int64), _p(gi, C.c_int32), _p(gi, C.c_int32), _p(gi, C.c_int32), _p(fl, C.c_uint8))
+    out = np.zeros(len(gi), np.uint8)
+    rc = getattr(lib, prefix + "remap_tandems_pairs")(C.byref(d), _p(pp, C.c_int64), _p(pi, C.c_int32), C.c_int32(len(pp) - 1),
+                                                       C.c_int32(tandem_gap), C.c_int(device), _p(out, C.c_uint8))
+    if rc:
+        f = getattr(lib, prefix + "last_error")
+        f.restype = C.c_char_p
+        raise RuntimeError(f"{prefix}remap_tandems_pairs failed ({rc}): {f().decode()}")
     return out.astype(bool)
 
 

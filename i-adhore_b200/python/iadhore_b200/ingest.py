@@ -162,14 +162,23 @@ def build_dataset(lists: List[List[Gene]], tandem_gap: int, device=None, pairs=N
                                      np.asarray(gids, np.int32),
                                      np.fromiter((g[1] for lst in lists for g in lst), np.uint8, int(raw_off[-1])),
                                      tandem_gap, device=device)
+    if device is not None and ps is not None:
+        # table_type=pairs: GeneList::remapTandemsPairs on the device (iadh_remap_tandems_pairs) over the CSR pair sets
+        from . import capi
+        raw_off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+        gids = [gid_map.setdefault(g[0], len(gid_map)) for lst in lists for g in lst]
+        pp, pi = pairs_csr(ps, len(gid_map))
+        rem_all = capi.remap_tandems_pairs(raw_off, np.asarray(gids, np.int32),
+                                           np.fromiter((g[1] for lst in lists for g in lst), np.uint8, int(raw_off[-1])),
+                                           pp, pi, tandem_gap, device=device)
     for li, lst in enumerate(lists):
         fam = [g[2] for g in lst]
         strand = [g[1] for g in lst]
         gid = [gid_map.setdefault(g[0], len(gid_map)) for g in lst]
-        if ps is not None:
-            rem = remap_tandems_pairs(gid, strand, tandem_gap, ps)
-        elif rem_all is not None:
+        if rem_all is not None:
             rem = rem_all[raw_off[li]:raw_off[li + 1]]
+        elif ps is not None:
+            rem = remap_tandems_pairs(gid, strand, tandem_gap, ps)
         else:
             rem = remap_tandems_family(fam, gid, strand, tandem_gap)
         keep = np.nonzero(~rem)[0]

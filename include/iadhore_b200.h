@@ -109,6 +109,12 @@ typedef struct {
 int iadh_remap_tandems(const iadh_dataset_desc* lists, int32_t tandem_gap, int device,
                        uint8_t* remapped_out);
 
+/* The same for table_type=pairs: GeneList::remapTandemsPairs (GeneList.cpp:84-141) with
+ * Gene::isIndirectPairWith (Gene.cpp:33-49: a partner, or a partner in common) and the hasPairs test.  Pair sets as
+ * for iadh_create_pairs: a CSR over the dense gene ids of lists->gid, partners ascending; lists->fam is ignored. */
+int iadh_remap_tandems_pairs(const iadh_dataset_desc* lists, const int64_t* pair_ptr, const int32_t* pair_ids,
+                             int32_t n_genes, int32_t tandem_gap, int device, uint8_t* remapped_out);
+
 /* String interning on the device: dense ids for n byte strings (string i = blob[off[i] .. off[i+1]), off[0] = 0).
  * Equal strings get equal ids; ids number the distinct strings in order of first occurrence, so the result does not
  * depend on thread timing.  This is the hashing half of the reference's family join: DataSet::getGeneFamilies

@@ -2,6 +2,7 @@
 //
 // The oracle behind the same C interface as include/iadhore_b200.h (prefix oracle_
 // instead of iadh_), so a parity test drives both with identical calls.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -358,6 +359,53 @@ int oracle_result_stats(const oracle_result* r, iadh_stats* s) { *s = r->stats; 
 void oracle_free_result(oracle_result* r) { delete r; }
 void oracle_trim(void) {}
 int oracle_warmup(int) { return IADH_OK; }
+
+// GeneList::remapTandemsPairs (GeneList.cpp:84-141), restated sequentially: the three passes in the reference's order
+// with Gene::isIndirectPairWith (Gene.cpp:33-49) over the CSR pair sets; a gene without pairs is never remapped.
+int oracle_remap_tandems_pairs(const iadh_dataset_desc* d, const int64_t* pp, const int32_t* pi, int32_t n_genes, int32_t gap, int,
+                               uint8_t* r)
+{
+    auto has = [&](int g) { return g >= 0 && g < n_genes && pp[g + 1] > pp[g]; };
+    auto indirect = [&](int ga, int gb) {
+        if (gb < 0 || gb >= n_genes) return false;
+        if (std::binary_search(pi + pp[ga], pi + pp[ga + 1], gb)) return true;
+        int64_t a = pp[ga], b = pp[gb];
+        while (a < pp[ga + 1] && b < pp[gb + 1]) {
+            if (pi[a] == pi[b]) return true;
+            if (pi[a] < pi[b]) a++;
+            else b++;
+        }
+        return false;
+    };
+    for (int l = 0; l < d->n_lists; l++) {
+        const int64_t b = d->list_off[l], e = d->list_off[l + 1];
+        const int n = (int)(e - b);
+        const int32_t* gid = d->gid + b;
+        const uint8_t* fl = d->flags + b;
+        uint8_t* rem = r + b;
+        for (int i = 0; i < n; i++) rem[i] = 0;
+        for (int i = n - 1; i > 0; i--) {           // '+' onto earlier '+'
+            if (!has(gid[i]) || !(fl[i] & 1)) continue;
+            for (int j = i - 1; j >= 0 && i - j <= gap + 1; j--) {
+                if (!(fl[j] & 1)) continue;
+                if (indirect(gid[i], gid[j])) { rem[i] = 1; rem[j] = 0; break; }
+            }
+        }
+        for (int i = 0; i < n - 1; i++) {           // '-' onto later '-'
+            if (!has(gid[i]) || (fl[i] & 1)) continue;
+            for (int j = i + 1; j < n && j - i <= gap + 1; j++) {
+                if (fl[j] & 1) continue;
+                if (indirect(gid[i], gid[j])) { rem[i] = 1; rem[j] = 0; break; }
+            }
+        }
+        for (int i = n - 1; i > 0; i--) {           // anything left onto any earlier gene
+            if (!has(gid[i]) || rem[i]) continue;
+            for (int j = i - 1; j >= 0 && i - j <= gap + 1; j--)
+                if (indirect(gid[i], gid[j])) { rem[i] = 1; rem[j] = 0; break; }
+        }
+    }
+    return IADH_OK;
+}
 
 // Interning as the reference's string-keyed containers imply it (GeneFamily.cpp:12-16 map<string, string>,
 // GHM.cpp:34-50 family-string hash): equal strings, equal ids; ids in order of first occurrence.

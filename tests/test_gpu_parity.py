@@ -326,6 +326,60 @@ def test_family_expansion_build_is_invisible(sort_max, monkeypatch):
         gpu.close()
 
 
+def test_result_exchange_with_a_single_rank_is_the_identity():
+    """iadh_comm_init / iadh_allgather_results with a communicator of one rank (what a 1-GPU box can run of the
+    multi-GPU exchange; 2-8 ranks: tools/dist_check.py under torchrun): the gathered streams equal the rank's own, for
+    a single result and for the results of a batch (slices of one pinned block, counts written on the device)."""
+    cfg = synth.config_small(seed=30)
+    ds = ingest.dataset_from_synth(cfg)
+    eng = capi.load_product(ds)
+    eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    eng.comm_init(eng.comm_unique_id(), 0, 1)
+    r = eng.level2_all_pairs()
+    g = eng.allgather([r])[0]
+    assert g.n_multiplicons == r.n_multiplicons > 50 and g.bytes == r.bytes
+    ms = capi.parse_packed(g.bytes)
+    order = sorted(range(len(ms)), key=lambda i: -sum(len(c.aps) for c in ms[i].clusters))[:6]
+    profs = [pl.simple_profile(ds, ms[i].x_object_id, ms[i].y_object_id, ms[i]) for i in order]
+    masks = [[(ms[i].x_object_id, ms[i].bounds[0], ms[i].bounds[1]), (ms[i].y_object_id, ms[i].bounds[2], ms[i].bounds[3])] for i in order]
+    res = eng.profile_search_batch(profs, masks)
+    got = eng.allgather(res)
+    assert sum(x.n_multiplicons for x in res) > 0
+    assert all(a.bytes == b.bytes for a, b in zip(got, res))
+    eng.close()
+
+
+def test_device_pairs_tandem_remap_matches_reference_and_oracle():
+    """iadh_remap_tandems_pairs (GeneList::remapTandemsPairs with indirect pairs, on the device) against the reference's
+    own flags in the table_type=pairs traces and against the oracle on a larger pairs-mode set."""
+    for path in pl.golden_traces("pairs"):
+        tr = read_trace(path)
+        off = np.concatenate([[0], np.cumsum([len(r) for r in tr.raw_lists])]).astype(np.int64)
+        gid = np.concatenate([r["gid"] for r in tr.raw_lists]).astype(np.int32)
+        strand = np.concatenate([r["strand"] for r in tr.raw_lists]).astype(np.uint8)
+        ref = np.concatenate([r["remapped"] for r in tr.raw_lists]).astype(bool)
+        got = capi.remap_tandems_pairs(off, gid, strand, tr.dataset.pair_ptr, tr.dataset.pair_ids, tr.params["tandem_gap"])
+        assert ref.sum() > 0 and np.array_equal(got, ref), path
+    cfg = synth.config_small(seed=23)
+    cfg.table_type = "pairs"
+    data = synth.generate(cfg)
+    lists = [lst for g in cfg.genomes for lst in data[g.name]]
+    gid_map = {}
+    ps = ingest.pair_sets(lists, synth.pair_table(cfg, data), gid_map)
+    pp, pi = ingest.pairs_csr(ps, len(gid_map))
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    gid = np.array([gid_map[g[0]] for l in lists for g in l], np.int32)
+    strand = np.array([g[1] for l in lists for g in l], np.uint8)
+    tg = cfg.tandem_gap if cfg.tandem_gap is not None else cfg.gap_size // 2
+    a = capi.remap_tandems_pairs(off, gid, strand, pp, pi, tg)
+    b = capi.remap_tandems_pairs(off, gid, strand, pp, pi, tg, lib_path=capi.ORACLE_LIB, prefix="oracle_")
+    assert b.sum() > 50 and np.array_equal(a, b)
+    # and the ingest mirror with the device path gives the dataset of the pure-Python path
+    d0, d1 = ingest.dataset_from_synth(cfg, data=data), ingest.dataset_from_synth(cfg, data=data, device=0)
+    for k in ("list_off", "gid", "num_id", "flags", "pair_ptr", "pair_ids"):
+        assert np.array_equal(getattr(d0, k), getattr(d1, k)), k
+
+
 def test_device_string_interning_matches_oracle():
     """iadh_intern_strings (the hashing half of the family join, on the device) against the oracle's unordered_map:
     same dense ids in first-occurrence order -- gene and family names of a synthetic set, heavy duplication, empty and

@@ -77,6 +77,18 @@ def test_oracle_tandem_remap_matches_reference(path):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("path", pl.golden_traces("pairs"), ids=lambda p: p.split("/")[-1].split(".")[0])
+def test_oracle_pairs_tandem_remap_matches_reference(path):
+    """oracle_remap_tandems_pairs (the checker of the device kernel) against the flags the reference's
+    GeneList::remapTandemsPairs left in the table_type=pairs traces."""
+    tr = read_trace(path)
+    off, fam, gid, strand, ref = _raw(tr)
+    ds = tr.dataset
+    got = capi.remap_tandems_pairs(off, gid, strand, ds.pair_ptr, ds.pair_ids, tr.params["tandem_gap"], lib_path=capi.ORACLE_LIB,
+                                   prefix="oracle_")
+    assert ref.sum() > 0 and np.array_equal(got, ref)
+
+
 def test_oracle_tandem_remap_matches_python_mirror_on_tandem_rich_lists():
     cfg = synth.config_c5(0.02)
     data = synth.generate(cfg)

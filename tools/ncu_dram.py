@@ -37,7 +37,7 @@ def main():
                  "every launch of one level-2 call on config 4 (bench workload), in launch order\n")
         fh.write("kernel,dram_read_bytes,dram_write_bytes,duration_ns\n")
         for d in call:
-            fh.write(f"{d['kernel']},{int(d.get('dram__bytes_read.sum', 0))},{int(d.get('dram__bytes_write.sum', 0))},"
+            fh.write(f"\"{d['kernel']}\",{int(d.get('dram__bytes_read.sum', 0))},{int(d.get('dram__bytes_write.sum', 0))},"
                      f"{int(d.get('gpu__time_duration.sum', 0))}\n")
     if len(sys.argv) > 3:
         tot = lambda pred: int(sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in call if pred(d["kernel"])))
