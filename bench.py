@@ -377,6 +377,13 @@ def main():
     # clocks / throttle reasons of every GPU of the job, sampled by ONE nvidia-smi (rank 0) that is started before the
     # warm-up: its start-up (NVML initialisation over all GPUs of the box holds driver locks for hundreds of
     # milliseconds; one per rank stalled the CUDA calls of all ranks at 8 GPUs) is over when the timed region begins
+    # the synthetic genome leaves millions of live Python objects behind: a full cyclic collection in the middle of a
+    # timed step costs hundreds of milliseconds (seen as 2-4x outliers of single e2e steps) -- collect now, then keep
+    # the collector out of the timed regions
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     clocks = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
