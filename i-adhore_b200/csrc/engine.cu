@@ -369,6 +369,7 @@ struct iadh_ctx {
     int split_min = 256;  // both orientations need this many dots to be clustered by separate CTAs
     // batches of at least pass_min GHMs run phase 1 one pass per launch (instruction-cache friendly, many CTAs per SM)
     int pass_min = 4096, pass_nt = 3232, pass_per_sm = 32;
+    bool pass_cfg_user = false;   // IADH_PASS_CFG given: no adaptation to the batch size
     // K1 family-expansion path (build_kernels.cu, third generation): level-2 batches of at least this many GHMs
     int expand_min = 1024;
     int hl_expand_min = 16;            // the same for profile GHMs (family mode): calls of at least this many GHMProfiles
@@ -1317,6 +1318,17 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
                     int* pc = c->d_passctr.as<int>() + 36 * ch;
                     const int* it1 = c->d_items1.as<int>() + chunk_i1[ch];
                     const int n1 = chunk_i1[ch + 1] - chunk_i1[ch];
+                    // Launch configuration by batch size (measured on shares of config 4, K2 ms at 250 k / 63 k / 31 k /
+                    // 16 k items: 32 CTAs per SM x 64 registers 60.7 / 23.3 / 18.5 / 15.6, 24 x 85 registers 67.5 / 22.0 / 17.0 /
+                    // 14.4, 16 x 128 registers 81.1 / 23.5 / 16.2 / 13.6): a big batch is throughput-bound and wants every
+                    // warp slot, a small one -- one rank's share at 4-8 GPUs -- is bound by its heaviest item in each of
+                    // the 34 launches and wants that item's warp to run without register spills.
+                    if (!c->pass_cfg_user) {
+                        const int per_sm_items = n1 / std::max(1, c->sm_count);
+                        if (per_sm_items >= 640) c->pass_nt = 3232, c->pass_per_sm = 32;
+                        else if (per_sm_items >= 320) c->pass_nt = 3224, c->pass_per_sm = 24;
+                        else c->pass_nt = 32, c->pass_per_sm = 16;
+                    }
                     const int grid = std::min(n1, c->sm_count * c->pass_per_sm);
                     for (int gi = 0; gi < c->prm.n_gaps && gi < 10 && c->prm.gaps[gi] > 0 && n1 > 0; gi++)
                         for (int pass = 0; pass < 3; pass++) {
@@ -2011,6 +2023,7 @@ static int create_impl(const iadh_dataset_desc* d, const int64_t* pair_ptr, cons
     if (const char* e = getenv("IADH_PASS_CHUNK_MB")) c->pass_chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char* e = getenv("IADH_PASS_CFG")) {
         sscanf(e, "%d:%d", &c->pass_nt, &c->pass_per_sm);
+        c->pass_cfg_user = true;
         if (!pass_cfg_supported(c->pass_nt) || c->pass_per_sm < 1)
             return fail(IADH_ERR_ARG, "IADH_PASS_CFG=%s: unsupported launch configuration (codes: 32 3224 3232 64 6412 6416 128)", e);
     }

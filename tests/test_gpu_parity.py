@@ -496,9 +496,13 @@ def test_device_tandem_remap_matches_reference_and_oracle():
     assert want.sum() > 1000
 
 
-def test_pass_per_launch_mode_is_invisible(monkeypatch):
+@pytest.mark.parametrize("cfg_code", [None, "3232:32", "3224:24", "32:16"])
+def test_pass_per_launch_mode_is_invisible(cfg_code, monkeypatch):
     """Phase 1 as one pass per launch (the path of large throughput-bound batches) forced on small
-    inputs, level 2 and profile searches: same bytes as the fused kernel / the reference."""
+    inputs, level 2 and profile searches: same bytes as the fused kernel / the reference -- with the launch
+    configuration the engine picks for the batch size and with each of the three it chooses from."""
+    if cfg_code:
+        monkeypatch.setenv("IADH_PASS_CFG", cfg_code)
     monkeypatch.setenv("IADH_PASS_MIN", "1")
     monkeypatch.setenv("IADH_PASS_RATIO", "0")
     monkeypatch.setenv("IADH_RESIDENT", "0")     # (the path of GHMs too large for the resident kernel)
