@@ -472,11 +472,16 @@ def main():
             e_times = []
         te = time.perf_counter()
         e2 = capi.load_product(ds, device=local_rank)
+        tc = time.perf_counter()
         e2.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
         if uid is not None:
             e2.comm_init(uid, rank, world)     # (the communicator outlives contexts: no second ncclCommInitRank)
         u, st, _ = hot_path_step(e2, profs, rank, world)
+        ts = time.perf_counter()
         e2.close()
+        if os.environ.get("BENCH_E2E_TRACE"):
+            print(f"[bench] e2e step {k}: create {1e3 * (tc - te):.1f} ms, calls {1e3 * (ts - tc):.1f} ms (level 2 device {st[0]['total_ms']:.1f}), "
+                  f"close {1e3 * (time.perf_counter() - ts):.1f} ms", file=sys.stderr, flush=True)
         e_units += u
         h2d += ds_bytes + fam_csr_bytes + sum(s["h2d_bytes"] for s in st)
         d2h += sum(s["d2h_bytes"] for s in st)

@@ -21,7 +21,18 @@ for masks, p in profs[:8]:
         eng.mask_range(l, b, e)
     eng.profile_search(p)
 eng.close()
-for step in range(8):
+if os.environ.get("E2E_EXTRAS"):   # as bench.py: short runs of two other workloads in between
+    for xwl in ("c3", "d2"):
+        xcfg = bench.workload_config(xwl)
+        xds = ingest.dataset_from_synth(xcfg, device=0)
+        xe = capi.load_product(xds)
+        xe.set_params(xcfg.gap_size, xcfg.cluster_gap, xcfg.anchor_points, capi.MH_BONFERRONI, xcfg.q_value, xcfg.prob_cutoff)
+        xp, _ = bench.bench_profiles(xds, xwl, 32, lambda: xe.level2_all_pairs().bytes)
+        for _ in range(4):
+            bench.hot_path_step(xe, xp, 0, 1)
+        xe.close()
+    print("---- extras done", file=sys.stderr, flush=True)
+for step in range(6):
     print(f"---- step {step}", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
     e2 = capi.load_product(ds)
