@@ -25,6 +25,7 @@
 #include "cluster_math.cuh"
 #include "common.h"
 #include "workspace.h"
+#include "homolog.h"
 
 // kernels (other translation units)
 void launch_build_count(bool hl, const DatasetDev& ds, const ProfileDev& pf, GhmTask* tasks, int n_ghm,
@@ -73,6 +74,10 @@ cudaError_t launch_resident(GhmTask* tasks, const int* order, int n_tasks, int* 
                             int grid, int nt, cudaStream_t st, unsigned long long* dbg = nullptr);
 int resident_ctas_per_sm(int nt, int smem_bytes);
 bool pass_cfg_supported(int code);
+void launch_link_tables(const LinkRec* links, int64_t n_links, int64_t n_elems, const ProfileDev& pf, int32_t* cols, int32_t* cnt,
+                        int32_t* lk_ptr, int32_t* lk_col, int32_t* block_sum, int sm_count, cudaStream_t st);
+void launch_homolog_filter(GhmTask* tasks, int n_tasks, uint8_t* ws, const DatasetDev& ds, int n_fam, const ProfileDev& pf,
+                           const HomologDev* hdev, int pool_factor, int min_homologs, int sm_count, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
                        const DatasetDev& ds, const ProfileDev& pf, int pool_factor, uint8_t* out, cudaStream_t st);
 
@@ -438,6 +443,13 @@ struct iadh_ctx {
     std::vector<int32_t> batch_L;
     DBuf d_vis;
     HBuf h_vis;
+    // homolog-count filter of the running profile search (iadh_profile_search_filtered, homolog_kernel.cu): per-profile
+    // CSR "element -> columns of its inherited Link partners" on the device; hf_active is set by the _filtered entry
+    // points around run_batch
+    bool hf_active = false;
+    int64_t hf_dropped = 0;   // multiplicons the filter removed in the last run_batch
+    DBuf d_links, d_lk_cols, d_lk_cnt, d_lk_ptr, d_lk_col, d_lk_bsum, d_hdev;
+    HBuf h_links;
     // build_dots scratch
     std::vector<int64_t> bd_cnt;
     std::vector<int32_t> bd_dots;
@@ -700,6 +712,63 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
     CU(cudaMemcpyAsync(c->d_pf_col.p, c->h_pf.p, bytes, cudaMemcpyHostToDevice, c->st));
     h2d += (int64_t)bytes;
     out.valid = true;
+    return IADH_OK;
+}
+
+// The inherited Link sets of a call's profiles (iadh_profile_search*_filtered) -> device tables of the homolog-count
+// filter (homolog_kernel.cu): one CSR "profile element -> columns of its Link partners" over the concatenated elements
+// of the profiles this rank searches, built by kernels from the raw (segment, numID) pairs.  link_ptr[k] .. link_ptr[k+1]
+// = Links of profile k; mine[k] == 0: not searched by this rank (no table).  The profiles must already be on their way
+// to the device (pf: the call's descriptor, as run_batch gets it).
+static int upload_links(iadh_ctx* c, const iadh_profile_desc* profiles, int n_profiles, const uint8_t* mine, const iadh_link_t* links,
+                        const int64_t* link_ptr, const ProfileDev& pf, iadh_stats& st)
+{
+    if (!links || !link_ptr) return fail(IADH_ERR_ARG, "homolog filter: null Link arrays");
+    if (link_ptr[0] < 0) return fail(IADH_ERR_ARG, "homolog filter: link_ptr[0] < 0");
+    std::vector<LinkRec> recs;
+    std::vector<int64_t> base((size_t)n_profiles, 0);
+    int64_t n_elems = 0;
+    for (int k = 0; k < n_profiles; k++) {
+        const int64_t b = link_ptr[k], e = link_ptr[k + 1];
+        if (e < b) return fail(IADH_ERR_ARG, "homolog filter: link_ptr not ascending at profile %d", k);
+        if (mine && !mine[k]) continue;
+        if (e == b)
+            return fail(IADH_ERR_ARG, "homolog filter: profile %d without Links (a profile's multiplicon owns the Links of its anchor points)", k);
+        const int S = profiles[k].n_segments, L = profiles[k].length;
+        base[k] = n_elems;
+        n_elems += (int64_t)S * L;
+        if (n_elems > 0x7ffffff0ll || (e - b) + (int64_t)recs.size() > 0x3ffffff0ll)
+            return fail(IADH_ERR_CAPACITY, "homolog filter: more than 2^31 profile elements or 2^30 Links in one call");
+        for (int64_t i = b; i < e; i++) {
+            const iadh_link_t& l = links[i];
+            if (l.segment_x < 0 || l.segment_x >= S || l.segment_y < 0 || l.segment_y >= S)
+                return fail(IADH_ERR_ARG, "homolog filter: Link %lld of profile %d names segment %d / %d of %d", (long long)(i - b), k, l.segment_x, l.segment_y, S);
+            LinkRec r;
+            r.seg_x = l.segment_x; r.seg_y = l.segment_y; r.gene_x = l.gene_x_id; r.gene_y = l.gene_y_id;
+            r.prof = k;
+            r.base = (int32_t)base[k];
+            recs.push_back(r);
+        }
+    }
+    const int64_t nl = (int64_t)recs.size();
+    int rc;
+    CU(c->d_lk_cols.ensure(8 * (size_t)nl + 16));
+    CU(c->d_lk_col.ensure(8 * (size_t)nl + 16));
+    CU(c->d_lk_cnt.ensure(4 * (size_t)n_elems + 16));
+    CU(c->d_lk_ptr.ensure(4 * (size_t)(n_elems + 1) + 16));
+    CU(c->d_lk_bsum.ensure(4 * (size_t)(n_elems / 1024 + 2) + 16));
+    if ((rc = upload(c->d_links, recs.data(), sizeof(LinkRec) * (size_t)nl, c->st))) return rc;
+    std::vector<HomologDev> hd((size_t)n_profiles);
+    for (int k = 0; k < n_profiles; k++) {
+        hd[k].lk_ptr = c->d_lk_ptr.as<int32_t>() + base[k];   // (profiles of other ranks: never dereferenced, no GHM names them)
+        hd[k].lk_col = c->d_lk_col.as<int32_t>();
+    }
+    if ((rc = upload(c->d_hdev, hd.data(), sizeof(HomologDev) * hd.size(), c->st))) return rc;
+    launch_link_tables(c->d_links.as<LinkRec>(), nl, n_elems, pf, c->d_lk_cols.as<int32_t>(), c->d_lk_cnt.as<int32_t>(), c->d_lk_ptr.as<int32_t>(),
+                       c->d_lk_col.as<int32_t>(), c->d_lk_bsum.as<int32_t>(), c->sm_count, c->st);
+    CU(cudaGetLastError());
+    st.h2d_bytes += (int64_t)(sizeof(LinkRec) * (size_t)nl + sizeof(HomologDev) * hd.size());
+    st.kernel_launches += nl > 0 ? 6 : 3;   // resolve, count, 3 x scan, fill
     return IADH_OK;
 }
 
@@ -1497,6 +1566,27 @@ static int run_batch(iadh_ctx* c, bool hl, const ProfileDev& pf, std::vector<Ghm
     }
 
     trace_mark(c->st, "tasks D2H");
+    // homolog-count filter (GHMProfile.cpp:129-132) on the clustered GHMs: dropped multiplicons leave the output lists,
+    // the sizes the measuring pass left in the task records are recomputed and read back once more
+    c->hf_dropped = 0;
+    if (hl && c->hf_active && n > 0) {
+        launch_homolog_filter(c->d_tasks.as<GhmTask>(), n, c->d_ws.as<uint8_t>(), c->ds, c->n_fam, pf, c->d_hdev.as<HomologDev>(), pool_factor,
+                              c->prm.anchor_points, c->sm_count, c->st);
+        gather_out_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(c->d_tasks.as<GhmTask>(), n, c->d_outs.as<TaskOut>());
+        CU(readback(c->h_misc.p, c->d_outs.p, sizeof(TaskOut) * (size_t)n, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        st.d2h_bytes += (int64_t)sizeof(TaskOut) * n;
+        st.kernel_launches += 3;
+        const TaskOut* ho = c->h_misc.as<TaskOut>();
+        for (int i = 0; i < n; i++) {
+            c->hf_dropped += tasks[i].n_mult - ho[i].n_mult;
+            tasks[i].out_bytes = ho[i].out_bytes;
+            tasks[i].n_mult = ho[i].n_mult;
+            tasks[i].n_clusters = ho[i].n_clusters;
+            tasks[i].n_aps = ho[i].n_aps;
+        }
+        trace_mark(c->st, "homolog filter");
+    }
     // pack: sizes -> offsets -> write
     std::vector<int> sel;
     std::vector<int64_t> out_off;
@@ -2323,13 +2413,26 @@ static int clear_masks_impl(iadh_ctx* c)
     return IADH_OK;
 }
 
-static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out);
+static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, const iadh_link_t* links, int64_t n_links, int rank, int n_ranks,
+                               iadh_result** out);
 int iadh_profile_search(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out)
 {
-    IADH_TRY return profile_search_impl(c, p, rank, n_ranks, out);
+    IADH_TRY return profile_search_impl(c, p, nullptr, -1, rank, n_ranks, out);
     IADH_CATCH
 }
-static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, iadh_result** out)
+int iadh_profile_search_filtered(iadh_ctx* c, const iadh_profile_desc* p, const iadh_link_t* links, int64_t n_links, int rank, int n_ranks,
+                                 iadh_result** out)
+{
+    IADH_TRY
+    if (!links || n_links <= 0) return fail(IADH_ERR_ARG, "iadh_profile_search_filtered: the Link set of the profile's multiplicon is required");
+    const int rc = profile_search_impl(c, p, links, n_links, rank, n_ranks, out);
+    if (c) c->hf_active = false;
+    return rc;
+    IADH_CATCH
+}
+// links == nullptr: no homolog filter
+static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, const iadh_link_t* links, int64_t n_links, int rank, int n_ranks,
+                               iadh_result** out)
 {
     if (!c || !p || !out) return fail(IADH_ERR_ARG, "iadh_profile_search: null argument");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(IADH_ERR_ARG, "bad rank %d/%d", rank, n_ranks);
@@ -2341,6 +2444,12 @@ static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank
     memset(&b.st, 0, sizeof b.st);
     ProfileHost ph;
     int rc = upload_profile(c, p, ph, b.st.h2d_bytes);
+    c->hf_active = false;
+    if (rc == IADH_OK && links) {
+        const int64_t lptr[2] = {0, n_links};
+        rc = upload_links(c, p, 1, nullptr, links, lptr, ph.dev, b.st);
+        c->hf_active = rc == IADH_OK;
+    }
     std::vector<GhmTask> tasks;
     if (rc == IADH_OK) {
         std::vector<int32_t> part;
@@ -2364,6 +2473,7 @@ static int profile_search_impl(iadh_ctx* c, const iadh_profile_desc* p, int rank
         }
         rc = run_batch(c, true, ph.dev, tasks, b);
     }
+    c->hf_active = false;
     cudaEventRecord(e1, c->st);
     cudaEventSynchronize(e1);
     if (rc == IADH_OK) {
@@ -2389,15 +2499,29 @@ __global__ void apply_vis_kernel(uint8_t* __restrict__ flags, const int16_t* __r
     if (i < n && vis[i] != 0x7fff) flags[i] |= 4;
 }
 
-static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                              const int64_t* link_ptr, const iadh_mask_range_t* masks,
                               const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out);
 int iadh_profile_search_batch(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
                               const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out)
 {
-    IADH_TRY return profile_search_batch_impl(c, profiles, n_profiles, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
+    IADH_TRY return profile_search_batch_impl(c, profiles, n_profiles, nullptr, nullptr, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
     IADH_CATCH
 }
-static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
+int iadh_profile_search_batch_filtered(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                                       const int64_t* link_ptr, const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank,
+                                       int n_ranks, int shard_profiles, iadh_result** out)
+{
+    IADH_TRY
+    if (n_profiles > 0 && (!links || !link_ptr)) return fail(IADH_ERR_ARG, "iadh_profile_search_batch_filtered: the Link sets are required");
+    const int rc = profile_search_batch_impl(c, profiles, n_profiles, links, link_ptr, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
+    if (c) c->hf_active = false;
+    return rc;
+    IADH_CATCH
+}
+// links == nullptr: no homolog filter
+static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                              const int64_t* link_ptr, const iadh_mask_range_t* masks,
                               const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out)
 {
     if (!c || !out || n_profiles < 0 || (n_profiles > 0 && (!profiles || !mask_ptr)))
@@ -2504,7 +2628,13 @@ static int profile_search_batch_impl(iadh_ctx* c, const iadh_profile_desc* profi
     pf.vis = c->d_vis.as<int16_t>();
     set_last_result(c, nullptr, 0);
     b.group_begin = &t_begin;
+    c->hf_active = false;
+    if (links) {
+        if ((rc = upload_links(c, profiles, n_profiles, mine.data(), links, link_ptr, pf, b.st))) return rc;
+        c->hf_active = true;
+    }
     rc = run_batch(c, true, pf, tasks, b);
+    c->hf_active = false;
     // the masks of the whole batch now hold, as after the sequential calls
     if (rc == IADH_OK && total > 0 && mask_ptr[n_profiles] > 0) {
         apply_vis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->st>>>(c->d_flags.as<uint8_t>(), c->d_vis.as<int16_t>(), total);

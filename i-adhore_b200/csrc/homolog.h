@@ -1,0 +1,18 @@
+// Device-side records of the homolog-count filter (homolog_kernel.cu), shared with the engine.
+#pragma once
+#include <stdint.h>
+
+// One Link of the profile's multiplicon (Multiplicon.h:22-52) as uploaded: segment indices and gene numIDs, the
+// profile of the batch it belongs to and that profile's first element in the concatenated element index space.
+struct LinkRec {
+    int32_t seg_x, seg_y, gene_x, gene_y;
+    int32_t prof;
+    int32_t base;
+};
+
+// Per profile: CSR over its S * L elements (segment-major, like ProfileDev::num_id) -> columns of the other ends of the
+// element's inherited Links.  lk_ptr points at the profile's first element; its values index lk_col.
+struct HomologDev {
+    const int32_t* lk_ptr;
+    const int32_t* lk_col;
+};

@@ -53,7 +53,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["remap_tandems", "remap_tandems_pairs", "intern_strings", "create", "create_pairs", "destroy", "set_params", "level2_all_pairs", "level2_pairs", "mask_range",
-           "clear_masks", "profile_search", "profile_search_batch", "comm_unique_id", "comm_init", "comm_destroy",
+           "clear_masks", "profile_search", "profile_search_batch", "profile_search_filtered", "profile_search_batch_filtered", "comm_unique_id", "comm_init", "comm_destroy",
            "allgather_results", "result_bytes", "result_size", "result_ghm_index", "result_stats",
            "free_result", "trim", "warmup", "event_record", "event_elapsed_ms", "build_dots", "build_only", "plan_lists", "plan_pairs", "omxn", "pow", "last_error", "version"]
 
@@ -103,6 +103,7 @@ class Profile:
     gid: np.ndarray
     num_id: np.ndarray
     flags: np.ndarray
+    links: np.ndarray = None   # (n, 4) int32: segment_x, segment_y, gene_x_id, gene_y_id of the parent multiplicon's Link set
 
 
 def _p(a: np.ndarray, t):
@@ -284,6 +285,41 @@ class Engine:
         self._chk(self._f("profile_search_batch")(self.ctx, descs, C.c_int32(n), marr.ctypes.data_as(C.c_void_p),
                                                    _p(mptr, C.c_int32), C.c_int(rank), C.c_int(n_ranks),
                                                    C.c_int(1 if shard_profiles else 0), outs))
+        return [self._take(C.c_void_p(outs[k])) for k in range(n)]
+
+    def profile_search_filtered(self, p: Profile, rank: int = 0, n_ranks: int = 1) -> Result:
+        """iadh_profile_search_filtered: the search with the homolog-count filter of GHMProfile.cpp:129-132 applied
+        (p.links = the Link set of the profile's multiplicon)."""
+        d, keep = self._pdesc(p)
+        lk = np.ascontiguousarray(p.links, dtype=np.int32).reshape(-1, 4)
+        res = C.c_void_p()
+        self._chk(self._f("profile_search_filtered")(self.ctx, C.byref(d), lk.ctypes.data_as(C.c_void_p), C.c_int64(len(lk)),
+                                                      C.c_int(rank), C.c_int(n_ranks), C.byref(res)))
+        return self._take(res)
+
+    def profile_search_batch_filtered(self, profiles: Sequence[Profile], masks: Sequence[Sequence[Tuple[int, int, int]]],
+                                      rank: int = 0, n_ranks: int = 1, shard_profiles: bool = False) -> List[Result]:
+        """iadh_profile_search_batch_filtered: the batch with every profile's homolog-count filter applied."""
+        n = len(profiles)
+        descs = (ProfileDesc * max(1, n))()
+        keep = []
+        for k, p in enumerate(profiles):
+            d, kp = self._pdesc(p)
+            descs[k] = d
+            keep.append(kp)
+        lks = [np.ascontiguousarray(p.links, dtype=np.int32).reshape(-1, 4) for p in profiles]
+        lk = np.ascontiguousarray(np.concatenate(lks)) if lks else np.zeros((0, 4), np.int32)
+        lptr = np.zeros(n + 1, np.int64)
+        lptr[1:] = np.cumsum([len(a) for a in lks])
+        flat = [m for ms in masks for m in ms]
+        marr = np.ascontiguousarray(np.array(flat, dtype=np.int32).reshape(-1, 3))
+        mptr = np.zeros(n + 1, np.int32)
+        mptr[1:] = np.cumsum([len(ms) for ms in masks])
+        outs = (C.c_void_p * max(1, n))()
+        self._chk(self._f("profile_search_batch_filtered")(self.ctx, descs, C.c_int32(n), lk.ctypes.data_as(C.c_void_p),
+                                                            _p(lptr, C.c_int64), marr.ctypes.data_as(C.c_void_p),
+                                                            _p(mptr, C.c_int32), C.c_int(rank), C.c_int(n_ranks),
+                                                            C.c_int(1 if shard_profiles else 0), outs))
         return [self._take(C.c_void_p(outs[k])) for k in range(n)]
 
     # multi-GPU exchange (iadh_comm_*): rank 0 makes the id, every rank joins with the same id

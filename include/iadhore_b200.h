@@ -189,6 +189,30 @@ int iadh_profile_search_batch(iadh_ctx* ctx, const iadh_profile_desc* profiles, 
                               const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank, int n_ranks,
                               int shard_profiles, iadh_result** out);
 
+/* Replaces: the homolog-count filter at the end of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132), i.e. the return
+ * value of Multiplicon::createHomologs(useFamily, minHomologs) (Multiplicon.cpp:352-382) with minHomologs =
+ * Settings::getAnchorPoints() (GHM.cpp:218), evaluated on the device for every multiplicon of the search BEFORE the
+ * stream is written: extractXObject / extractYObject (Multiplicon.cpp:331-350) slice the profile's segments to
+ * [begin_x, end_x] and the list to [begin_y, end_y]; pruneLinks (:384-421) keeps the inherited Links whose two genes are
+ * still inside the slices; addLinks (:423-494) adds the (x-segment element, y element) homologs; the multiplicon
+ * survives iff every x-segment and the y-segment hold at least minHomologs elements with a homolog.  The result holds
+ * exactly the multiplicons the reference's search returns (the `_filtered` entry points of the shim need no host-side
+ * filter); multiplicons that fail never cross PCIe (4 in 10 on the config-3 shape).
+ * links = profile->getMultiplicon().getHomologs() (Multiplicon.cpp:343-344: what extractXObject copies), any order;
+ * segment indices are profile segments, gene ids are ListElement numIDs.  n_links must be > 0: a profile's multiplicon
+ * always owns the Links of its anchor points (with an empty set the reference skips pruneLinks and keeps whatever
+ * flags the copied elements had, Multiplicon.cpp:386-388 -- not reproducible from this interface). */
+typedef struct {
+    int32_t segment_x, segment_y;   /* Link::segmentX < Link::segmentY (Multiplicon.h:22-41) */
+    int32_t gene_x_id, gene_y_id;   /* Link::geneXID, Link::geneYID                           */
+} iadh_link_t;
+int iadh_profile_search_filtered(iadh_ctx* ctx, const iadh_profile_desc* profile, const iadh_link_t* links, int64_t n_links,
+                                 int rank, int n_ranks, iadh_result** out);
+/* The batch with the same filter: links of profile k = links[link_ptr[k] .. link_ptr[k+1]). */
+int iadh_profile_search_batch_filtered(iadh_ctx* ctx, const iadh_profile_desc* profiles, int32_t n_profiles,
+                                       const iadh_link_t* links, const int64_t* link_ptr, const iadh_mask_range_t* masks,
+                                       const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, iadh_result** out);
+
 /* Multi-GPU exchange, one process (rank) per GPU.  Replaces the MPI plumbing of the two drivers: ParToolBox
  * (parallel.cpp:13-31: rank / size) and the exchange step MPI_Allgather + MPI_Allgatherv of the packed
  * multiplicons (levelTwo.cpp:225-269, higherLevel.cpp:279-314), here one NCCL all-gather of sizes and one of

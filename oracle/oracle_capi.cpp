@@ -184,7 +184,7 @@ static void run_pair(const oracle_ctx* c, int lx, int ly, GhmOut& o)
     }
 }
 
-static void run_profile(const oracle_ctx* c, const Profile& P, int ly, GhmOut& o)
+static void run_profile(const oracle_ctx* c, const Profile& P, int ly, GhmOut& o, const std::vector<Link>* links = nullptr)
 {
     GHMInput g;
     double t0 = now_s();
@@ -195,6 +195,7 @@ static void run_profile(const oracle_ctx* c, const Profile& P, int ly, GhmOut& o
     std::vector<Multiplicon> ms;
     run_collinear(g, c->prm, cl, ms);
     set_multiplicons_hl(P, c->lists[ly], cl, ms, c->pt());
+    if (links) filter_homologs(P, c->lists[ly], *links, c->prm.anchor_points, ms, c->pt());   // GHMProfile.cpp:129-132
     o.build_s = t1 - t0;
     o.run_s = now_s() - t1;
     pack(cl, ms, o.bytes, o.n_mult);
@@ -284,8 +285,8 @@ static void to_profile(const iadh_profile_desc* p, Profile& P)
     P.flags.assign(p->flags, p->flags + n);
 }
 
-extern "C" {
-int oracle_profile_search(oracle_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, oracle_result** out)
+static int profile_search(oracle_ctx* c, const iadh_profile_desc* p, const std::vector<Link>* links, int rank, int n_ranks,
+                          oracle_result** out)
 {
     Profile P;
     to_profile(p, P);
@@ -296,14 +297,55 @@ int oracle_profile_search(oracle_ctx* c, const iadh_profile_desc* p, int rank, i
         for (uint8_t m : c->lists[l].masked) masked += m;
         if ((unsigned)c->lists[l].size() - masked >= (unsigned)c->prm.anchor_points) lists.push_back(l);
     }
-    *out = run_many(c, lists.size(), [&](size_t i, GhmOut& o) { run_profile(c, P, lists[i], o); });
+    *out = run_many(c, lists.size(), [&](size_t i, GhmOut& o) { run_profile(c, P, lists[i], o, links); });
     return IADH_OK;
+}
+static int to_links(const iadh_link_t* links, int64_t n, std::vector<Link>& out)
+{
+    if (!links || n <= 0) { g_err = "the homolog filter needs the Link set of the profile's multiplicon"; return IADH_ERR_ARG; }
+    out.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        out[i].seg_x = links[i].segment_x; out[i].seg_y = links[i].segment_y;
+        out[i].gene_x = links[i].gene_x_id; out[i].gene_y = links[i].gene_y_id;
+    }
+    return IADH_OK;
+}
+
+extern "C" {
+int oracle_profile_search(oracle_ctx* c, const iadh_profile_desc* p, int rank, int n_ranks, oracle_result** out)
+{
+    return profile_search(c, p, nullptr, rank, n_ranks, out);
+}
+// iadh_profile_search_filtered restated: the search with the homolog-count filter of GHMProfile.cpp:129-132 applied
+int oracle_profile_search_filtered(oracle_ctx* c, const iadh_profile_desc* p, const iadh_link_t* links, int64_t n_links, int rank,
+                                   int n_ranks, oracle_result** out)
+{
+    std::vector<Link> lk;
+    if (int rc = to_links(links, n_links, lk)) return rc;
+    return profile_search(c, p, &lk, rank, n_ranks, out);
 }
 
 // iadh_profile_search_batch restated: by definition the sequential calls (higherLevel.cpp:165-178 per iteration:
 // mask the segments, then search).  shard_profiles: profile k is searched against all lists by rank k % n_ranks.
+static int profile_search_batch(oracle_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                                const int64_t* link_ptr, const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank,
+                                int n_ranks, int shard_profiles, oracle_result** out);
 int oracle_profile_search_batch(oracle_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_mask_range_t* masks,
                                 const int32_t* mask_ptr, int rank, int n_ranks, int shard_profiles, oracle_result** out)
+{
+    return profile_search_batch(c, profiles, n_profiles, nullptr, nullptr, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
+}
+int oracle_profile_search_batch_filtered(oracle_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                                         const int64_t* link_ptr, const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank,
+                                         int n_ranks, int shard_profiles, oracle_result** out)
+{
+    if (!links || !link_ptr) { g_err = "the homolog filter needs the Link sets"; return IADH_ERR_ARG; }
+    return profile_search_batch(c, profiles, n_profiles, links, link_ptr, masks, mask_ptr, rank, n_ranks, shard_profiles, out);
+}
+}  // extern "C"
+static int profile_search_batch(oracle_ctx* c, const iadh_profile_desc* profiles, int32_t n_profiles, const iadh_link_t* links,
+                                const int64_t* link_ptr, const iadh_mask_range_t* masks, const int32_t* mask_ptr, int rank,
+                                int n_ranks, int shard_profiles, oracle_result** out)
 {
     for (int k = 0; k < n_profiles; k++) {
         for (int m = mask_ptr[k]; m < mask_ptr[k + 1]; m++) {
@@ -314,11 +356,16 @@ int oracle_profile_search_batch(oracle_ctx* c, const iadh_profile_desc* profiles
             *(out + k) = run_many(c, 0, [&](size_t, GhmOut&) {});
             continue;
         }
-        const int rc = shard_profiles ? oracle_profile_search(c, profiles + k, 0, 1, out + k) : oracle_profile_search(c, profiles + k, rank, n_ranks, out + k);
+        std::vector<Link> lk;
+        if (links)
+            if (int rc = to_links(links + link_ptr[k], link_ptr[k + 1] - link_ptr[k], lk)) return rc;
+        const int rc = shard_profiles ? profile_search(c, profiles + k, links ? &lk : nullptr, 0, 1, out + k)
+                                      : profile_search(c, profiles + k, links ? &lk : nullptr, rank, n_ranks, out + k);
         if (rc) return rc;
     }
     return IADH_OK;
 }
+extern "C" {
 
 // The exchange of the multi-GPU product (iadh_comm_*, iadh_allgather_results) has no CPU counterpart to check:
 // the oracle is a single process.  With one rank the gathered stream is the rank's own stream, which is all

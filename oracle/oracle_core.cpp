@@ -1093,6 +1093,69 @@ void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& 
 }
 
 // ---------------------------------------------------------------------------
+// Multiplicon::createHomologs (Multiplicon.cpp:352-382) on the slices of extractXObject / extractYObject (:331-350)
+bool enough_homologs(const Profile& P, const List& Y, const std::vector<Link>& links, const Multiplicon& m, int min_homologs,
+                     const PairTable* pt)
+{
+    const int S = P.S, bx = m.begin_x, ex = m.end_x, by = m.begin_y, ey = m.end_y;
+    const int wx = ex >= bx ? ex - bx + 1 : 0, wy = ey >= by ? ey - by + 1 : 0;   // GeneList(const GeneList&, begin, end), GeneList.cpp:55-63
+    std::vector<std::vector<char>> hx(S, std::vector<char>(wx, 0));
+    std::vector<char> hy(wy, 0);
+    // pruneLinks (:384-421): numID -> element per x-segment slice; a Link stays while both ends are found
+    if (!links.empty()) {
+        std::vector<std::map<int, int>> le_map(S);
+        for (int i = 0; i < S; i++)
+            for (int j = 0; j < wx; j++) {
+                const int k = i * P.L + bx + j;
+                le_map[i][(P.flags[k] & 2) ? -1 : P.num_id[k]] = j;   // (a gap element carries numID -1, ListElement.cpp:5-9)
+            }
+        for (const Link& e : links) {
+            if (e.seg_x < 0 || e.seg_x >= S || e.seg_y < 0 || e.seg_y >= S) continue;
+            std::map<int, int>::const_iterator ix = le_map[e.seg_x].find(e.gene_x), iy = le_map[e.seg_y].find(e.gene_y);
+            if (ix == le_map[e.seg_x].end() || iy == le_map[e.seg_y].end()) continue;
+            hx[e.seg_x][ix->second] = 1;
+            hx[e.seg_y][iy->second] = 1;
+        }
+    }
+    // addLinks (:423-494)
+    for (int jy = 0; jy < wy; jy++) {
+        const int y = by + jy;
+        for (int i = 0; i < S; i++)
+            for (int j = 0; j < wx; j++) {
+                const int k = i * P.L + bx + j;
+                if (P.flags[k] & 2) continue;
+                // pairs (:425-447): the x element's pair set holds the y gene; families (:448-493): same family and
+                // not the same list element ("to have compatibility with the pairwise case", :484-485)
+                const bool hom = pt ? pt->is_pair(P.gid[k], Y.gid[y]) : (P.fam[k] == Y.fam[y] && P.num_id[k] != Y.num_id[y]);
+                if (!hom) continue;
+                hx[i][j] = 1;
+                hy[jy] = 1;
+            }
+    }
+    // counts (:360-381)
+    for (int i = 0; i < S; i++) {
+        int count = 0;
+        for (int j = 0; j < wx; j++) count += hx[i][j];
+        if (count < min_homologs) return false;
+    }
+    int count = 0;
+    for (int jy = 0; jy < wy; jy++) {
+        count += hy[jy];
+        if (count >= min_homologs) return true;
+    }
+    return false;
+}
+
+void filter_homologs(const Profile& P, const List& Y, const std::vector<Link>& links, int min_homologs,
+                     std::vector<Multiplicon>& mults, const PairTable* pt)
+{
+    std::vector<Multiplicon> kept;
+    for (const Multiplicon& m : mults)
+        if (enough_homologs(P, Y, links, m, min_homologs, pt)) kept.push_back(m);
+    mults.swap(kept);
+}
+
+// ---------------------------------------------------------------------------
 template <typename T>
 static void put(std::vector<uint8_t>& out, const T& v)
 {

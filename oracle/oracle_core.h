@@ -94,6 +94,22 @@ void set_multiplicons_l2(const List& X, const List& Y, std::vector<Cluster>& clu
 // GHMProfile.cpp:68-136 up to (not including) createHomologs
 void set_multiplicons_hl(const Profile& P, const List& Y, std::vector<Cluster>& clusters,
                          std::vector<Multiplicon>& mults, const PairTable* pt = nullptr);
+// One Link of a multiplicon's homolog set (Multiplicon.h:22-52): gene numIDs in two segments, segment_x < segment_y
+struct Link {
+    int seg_x = 0, seg_y = 0, gene_x = -1, gene_y = -1;
+};
+// Multiplicon::createHomologs(useFamily, minHomologs) (Multiplicon.cpp:352-382) for a multiplicon found by searching
+// profile P in list Y: extractXObject / extractYObject (:331-350) slice the S segments to [begin_x, end_x] and Y to
+// [begin_y, end_y], pruneLinks (:384-421) keeps the inherited Links whose two ends survive the slicing, addLinks
+// (:423-494) adds the x-segment x y-segment homologs; true iff every x-segment and the y-segment hold at least
+// min_homologs elements with a homolog.  This is the filter of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132).
+// `links` = the homologs of the profile's multiplicon (never empty for a real profile; for an empty set the reference
+// leaves the copied hasHomolog flags alone, :386-388 -- here they count as unset).
+bool enough_homologs(const Profile& P, const List& Y, const std::vector<Link>& links, const Multiplicon& m, int min_homologs,
+                     const PairTable* pt = nullptr);
+// the filter applied to a GHM's multiplicons: the survivors, in order (GHMProfile.cpp:129-135)
+void filter_homologs(const Profile& P, const List& Y, const std::vector<Link>& links, int min_homologs,
+                     std::vector<Multiplicon>& mults, const PairTable* pt = nullptr);
 // Multiplicon.cpp:210-240 / BaseCluster.cpp:751-797 / AnchorPoint.h:103-118, appended to `out`
 void pack(const std::vector<Cluster>& clusters, const std::vector<Multiplicon>& mults,
           std::vector<uint8_t>& out, int& n_mult_total);

@@ -371,6 +371,15 @@ int main(int argc, char** argv)
                             w8(pb, e[x]->getOrientation() ? 1 : 0);
                         }
                     }
+                if (dump) {
+                    // the Link set the search inherits from the profile's multiplicon (Multiplicon.cpp:343-344): input
+                    // of the homolog-count filter (createHomologs, Multiplicon.cpp:352-382)
+                    const set<Link>& hs = profile->getMultiplicon().getHomologs();
+                    w32(pb, 6); w32(pb, (int)hs.size());
+                    for (set<Link>::const_iterator e = hs.begin(); e != hs.end(); e++) {
+                        w32(pb, e->segmentX); w32(pb, e->segmentY); w32(pb, e->geneXID); w32(pb, e->geneYID);
+                    }
+                }
                 if (dump) fwrite(pb.data(), 1, pb.size(), out);
                 if (profOut) {
                     Blob q;

@@ -153,6 +153,7 @@ inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 // lanes interleave only at collectives, so a plain read-modify-write is atomic here
 template <typename T, typename U> inline T atomicAdd(T* p, U v) { const T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T, typename U> inline T atomicOr(T* p, U v) { const T old = *p; *p = (T)(old | (T)v); return old; }
 
 // CUDA's global min / max overload set
 template <class A, class B> inline typename std::common_type<A, B>::type min(A a, B b)

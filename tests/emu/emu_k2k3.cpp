@@ -9,6 +9,14 @@
 //   i32 n_ghm; per GHM: i32 profile (-1 = level 2), x_list, y_list, x_object_id, level; u64 area; u32 cnt0, cnt1;
 //                       u32 keys[cnt0+cnt1]; i32 n_expected; u8 expected[n_expected]
 //   (expected = the reference's packed blob of the GHM: i32 multiplicon count, then the multiplicons)
+// Format flags in bits 8+ of the first word (n_gaps):
+//   0x100  homolog-count filter (homolog_kernel.cu): every profile is followed by i32 n_links, n_links x {i32 segment_x,
+//          segment_y, gene_x_id, gene_y_id} (the Link set of its multiplicon) and `expected` of a profile GHM holds only
+//          the multiplicons the reference's own search kept (GHMProfile.cpp:129-132).  The link tables are built by the
+//          emulated link_resolve / link_count / link_fill kernels (the scan between them on the host), the filter
+//          kernel runs between the clustering kernel and the writer, as in the engine.
+//   0x200  table_type=pairs: the dataset is followed by i32 n_genes, i64 pair_ptr[n_genes + 1], i32 pair_ids[]; the
+//          partner buckets of iadh_create_pairs are rebuilt here (bucket g = positions of the partners of gene g)
 #define IADH_HOST_EMU 1
 #ifndef EMU_NT
 #define EMU_NT 32        // block size of the emulated clustering kernel: 32, 64, 128 or 256
@@ -17,9 +25,11 @@
 #define IADH_EMU_PT 32   // (and a one-warp writer; the larger builds keep the writer's own 128 threads)
 #endif
 #include "cuda_emu.h"
+#include <algorithm>
 
 #include "../../i-adhore_b200/csrc/cluster_kernel.cu"
 #include "../../i-adhore_b200/csrc/pack_kernel.cu"
+#include "../../i-adhore_b200/csrc/homolog_kernel.cu"
 
 #include "emu_runtime.inc"
 
@@ -35,6 +45,8 @@ int main(int argc, char** argv)
     memset(&prm, 0, sizeof prm);
     if (!rd(f, &prm.n_gaps, 1) || !rd(f, prm.gaps, 10) || !rd(f, &prm.gap_size, 1) || !rd(f, &prm.cluster_gap, 1) ||
         !rd(f, &prm.anchor_points, 1) || !rd(f, &prm.mult_hyp, 1) || !rd(f, &prm.q_value, 1) || !rd(f, &prm.prob_cutoff, 1)) return 2;
+    const int fmt = prm.n_gaps >> 8;
+    prm.n_gaps &= 0xff;
     const int coop[4] = {16, 16, 16, 48};
     memcpy(prm.coop, coop, sizeof coop);
     int n_lists = 0;
@@ -53,7 +65,49 @@ int main(int argc, char** argv)
     ds.gid = gid.data();
     ds.num_id = num_id.data();
     ds.flags = flags.data();
-    struct Prof { int S, L; std::vector<int32_t> fam, gid, num_id; std::vector<uint8_t> flags; };
+    // the dataset's bucket CSR: families (members ascending), or in pairs mode gene id -> positions of its partners
+    std::vector<int32_t> fam_ptr, fam_members, ds_fam_pairs;
+    int n_fam = 0;
+    if (fmt & 2) {
+        int n_genes = 0;
+        if (!rd(f, &n_genes, 1)) return 2;
+        std::vector<int64_t> pptr(n_genes + 1);
+        if (!rd(f, pptr.data(), pptr.size())) return 2;
+        std::vector<int32_t> pids((size_t)pptr[n_genes]);
+        if (!rd(f, pids.data(), pids.size())) return 2;
+        std::vector<std::vector<int32_t>> pos(n_genes);
+        for (size_t i = 0; i < T; i++)
+            if (gid[i] >= 0 && gid[i] < n_genes) pos[gid[i]].push_back((int32_t)i);
+        n_fam = n_genes;
+        fam_ptr.assign(n_genes + 1, 0);
+        for (int g = 0; g < n_genes; g++) {
+            std::vector<int32_t> b;
+            for (int64_t k = pptr[g]; k < pptr[g + 1]; k++) b.insert(b.end(), pos[pids[k]].begin(), pos[pids[k]].end());
+            std::sort(b.begin(), b.end());
+            fam_members.insert(fam_members.end(), b.begin(), b.end());
+            fam_ptr[g + 1] = (int32_t)fam_members.size();
+        }
+        ds_fam_pairs = gid;
+        ds.fam = ds_fam_pairs.data();   // "family" = gene id (iadh_create_pairs)
+        ds.pairs = 1;
+    } else {
+        for (size_t i = 0; i < T; i++) n_fam = std::max(n_fam, fam[i] + 1);
+        fam_ptr.assign(n_fam + 1, 0);
+        for (size_t i = 0; i < T; i++) fam_ptr[fam[i] + 1]++;
+        for (int k = 0; k < n_fam; k++) fam_ptr[k + 1] += fam_ptr[k];
+        fam_members.resize(T);
+        std::vector<int32_t> cur(fam_ptr.begin(), fam_ptr.end() - 1);
+        for (size_t i = 0; i < T; i++) fam_members[cur[fam[i]]++] = (int32_t)i;
+    }
+    ds.fam_ptr = fam_ptr.data();
+    ds.fam_members = fam_members.data();
+    struct Prof {
+        int S, L;
+        std::vector<int32_t> fam, gid, num_id;
+        std::vector<uint8_t> flags;
+        std::vector<LinkRec> links;
+        std::vector<int32_t> lk_ptr, lk_col;
+    };
     int n_prof = 0;
     if (!rd(f, &n_prof, 1)) return 2;
     std::vector<Prof> profs(n_prof);
@@ -62,10 +116,39 @@ int main(int argc, char** argv)
         const size_t n = (size_t)p.S * p.L;
         p.fam.resize(n); p.gid.resize(n); p.num_id.resize(n); p.flags.resize(n);
         if (!rd(f, p.fam.data(), n) || !rd(f, p.gid.data(), n) || !rd(f, p.num_id.data(), n) || !rd(f, p.flags.data(), n)) return 2;
+        if (fmt & 2)   // bucket key = gene id; ids outside the pair table have no bucket (place_profile, engine.cu)
+            for (size_t k = 0; k < n; k++) p.fam[k] = (p.gid[k] >= 0 && p.gid[k] < n_fam) ? p.gid[k] : -1;
+        if (fmt & 1) {
+            int nl = 0;
+            if (!rd(f, &nl, 1)) return 2;
+            std::vector<int32_t> raw(4 * (size_t)nl);
+            if (!rd(f, raw.data(), raw.size())) return 2;
+            p.links.resize(nl);
+            for (int i = 0; i < nl; i++) {
+                LinkRec& r = p.links[i];
+                r.seg_x = raw[4 * i]; r.seg_y = raw[4 * i + 1]; r.gene_x = raw[4 * i + 2]; r.gene_y = raw[4 * i + 3];
+                r.prof = 0;
+                r.base = 0;
+            }
+            // the link tables, as launch_link_tables builds them (homolog_kernel.cu): resolve, count, scan, fill
+            ProfileDev pf;
+            memset(&pf, 0, sizeof pf);
+            pf.S = p.S; pf.L = p.L;
+            pf.fam = p.fam.data(); pf.gid = p.gid.data(); pf.num_id = p.num_id.data(); pf.flags = p.flags.data();
+            std::vector<int32_t> cols(2 * (size_t)nl + 1, -7), cnt(n + 1, 0);
+            p.lk_ptr.assign(n + 1, 0);
+            p.lk_col.assign(2 * (size_t)nl + 1, -7);
+            emu::run_block(0, 256, [&]() { link_resolve_kernel(p.links.data(), nl, pf, cols.data()); });
+            for (int b = 0; b * 256 < nl; b++) emu::run_block(b, 256, [&]() { link_count_kernel(p.links.data(), nl, pf, cols.data(), cnt.data()); });
+            for (size_t k = 0; k < n; k++) p.lk_ptr[k + 1] = p.lk_ptr[k] + cnt[k];
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int b = 0; b * 256 < nl; b++)
+                emu::run_block(b, 256, [&]() { link_fill_kernel(p.links.data(), nl, pf, cols.data(), p.lk_ptr.data(), cnt.data(), p.lk_col.data()); });
+        }
     }
     int n_ghm = 0;
     if (!rd(f, &n_ghm, 1)) return 2;
-    long long bad = 0, n_mult = 0, n_bytes = 0, n_resident = 0, n_fallback = 0;
+    long long bad = 0, n_mult = 0, n_bytes = 0, n_resident = 0, n_fallback = 0, n_before = 0;
     for (int gidx = 0; gidx < n_ghm; gidx++) {
         int32_t pi, xl, yl, xobj, level, n_exp;
         uint64_t area;
@@ -153,6 +236,14 @@ int main(int argc, char** argv)
                 emu::run_block(0, EMU_NT, [&]() { cluster_kernel<EMU_NT>(&task, &prof, &item, 1, &next, keys.data(), ws.data(), prm, pool_factor, sm_slot.data(), ds, pf, hl ? 1 : 0); });
                 }
                 if (task.status != 0) continue;   // anchor-point pool exhausted: retry with a larger pool, like the engine
+                if ((fmt & 1) && hl) {   // homolog-count filter between clustering and writer, as in run_batch
+                    const Prof& p = profs[pi];
+                    HomologDev hd;
+                    hd.lk_ptr = p.lk_ptr.data();
+                    hd.lk_col = p.lk_col.data();
+                    n_before += task.n_mult;
+                    emu::run_block(0, HT, [&]() { homolog_filter_kernel(&task, 1, ws.data(), ds, n_fam, pf, &hd, pool_factor, prm.anchor_points); });
+                }
                 int32_t nm = task.n_mult;
                 memcpy(got.data(), &nm, 4);
                 if (nm > 0) {
@@ -181,7 +272,7 @@ int main(int argc, char** argv)
         }
     }
     fclose(f);
-    printf("{\"ghms\": %d, \"multiplicons\": %lld, \"bytes\": %lld, \"mismatching_ghms\": %lld, \"collectives\": %llu, \"resident\": %lld, \"resident_fallbacks\": %lld}\n", n_ghm, n_mult, n_bytes, bad,
-           emu::n_collectives, n_resident, n_fallback);
+    printf("{\"ghms\": %d, \"multiplicons\": %lld, \"bytes\": %lld, \"mismatching_ghms\": %lld, \"collectives\": %llu, \"resident\": %lld, \"resident_fallbacks\": %lld, \"before_homolog_filter\": %lld}\n", n_ghm, n_mult, n_bytes, bad,
+           emu::n_collectives, n_resident, n_fallback, n_before);
     return bad ? 1 : 0;
 }

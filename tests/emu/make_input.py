@@ -32,9 +32,13 @@ def write_input(trace_path, out_path, max_ghms=None, min_dots=6, kinds=("l2", "h
     return len(recs)
 
 
-def write_k2k3_input(trace_path, out_path, max_hl=None):
+def write_k2k3_input(trace_path, out_path, max_hl=None, filtered=False, pairs_table=False):
     """Input of tests/emu/emu_k2k3: settings, the flattened dataset, the profiles and, per GHM of the trace
-    (level 2 and profile x list), its dot sets, area, level and the reference's packed multiplicons."""
+    (level 2 and profile x list), its dot sets, area, level and the reference's packed multiplicons.
+    filtered: the profiles carry the Link sets of their multiplicons and a profile GHM expects only the multiplicons the
+    reference's search kept (homolog-count filter, format flag 0x100); pairs_table: a table_type=pairs trace with its
+    pair sets (flag 0x200), so that profile GHMs can be emulated there too."""
+    from trace_io import kept_packed
     tr = read_trace(trace_path)
     p, ds = tr.params, tr.dataset
     gaps = p["gaps"]
@@ -58,27 +62,36 @@ def write_k2k3_input(trace_path, out_path, max_hl=None):
             recs.append((len(profiles) - 1, -1, g.y_list, pr.x_object_id, pr.S + 1, area, g))
             n_hl += 1
     with open(out_path, "wb") as fh:
-        fh.write(struct.pack("<i10i", len(gaps), *(list(gaps) + [0] * (10 - len(gaps)))))
+        fmt = (0x100 if filtered else 0) | (0x200 if pairs_table else 0)
+        fh.write(struct.pack("<i10i", len(gaps) | fmt, *(list(gaps) + [0] * (10 - len(gaps)))))
         fh.write(struct.pack("<iiiidd", p["gap_size"], p["cluster_gap"], p["anchor_points"], p["mult_hyp"], p["q_value"], p["prob_cutoff"]))
         fh.write(struct.pack("<i", ds.n_lists))
         fh.write(np.ascontiguousarray(ds.list_off, "<i8").tobytes())
         for a in (ds.fam, ds.gid, ds.num_id):
             fh.write(np.ascontiguousarray(a, "<i4").tobytes())
         fh.write(np.ascontiguousarray(ds.flags, "u1").tobytes())
+        if pairs_table:
+            fh.write(struct.pack("<i", len(ds.pair_ptr) - 1))
+            fh.write(np.ascontiguousarray(ds.pair_ptr, "<i8").tobytes())
+            fh.write(np.ascontiguousarray(ds.pair_ids, "<i4").tobytes())
         fh.write(struct.pack("<i", len(profiles)))
         for pr in profiles:
             fh.write(struct.pack("<ii", pr.S, pr.L))
             for a in (pr.fam, pr.gid, pr.num_id):
                 fh.write(np.ascontiguousarray(a, "<i4").tobytes())
             fh.write(np.ascontiguousarray(pr.flags, "u1").tobytes())
+            if filtered:
+                fh.write(struct.pack("<i", len(pr.links)))
+                fh.write(np.ascontiguousarray(pr.links, "<i4").tobytes())
         fh.write(struct.pack("<i", len(recs)))
         for prof, xl, yl, xobj, level, area, g in recs:
             d0, d1 = g.dots
             keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
             fh.write(struct.pack("<iiiiiQII", prof, xl, yl, xobj, level, area, len(d0), len(d1)))
             fh.write(keys.tobytes())
-            fh.write(struct.pack("<i", len(g.packed)))
-            fh.write(g.packed)
+            expected = kept_packed([g]) if (filtered and prof >= 0) else g.packed
+            fh.write(struct.pack("<i", len(expected)))
+            fh.write(expected)
     return len(recs)
 
 

@@ -16,7 +16,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(REPO, "i-adhore_b200", "python"))
 
 from iadhore_b200 import capi  # noqa: E402
-from trace_io import Trace, concat_packed, read_trace  # noqa: E402
+from trace_io import Trace, concat_packed, kept_packed, read_trace  # noqa: E402
 
 GOLDEN = os.path.join(HERE, "golden")
 P_RTOL = 1e-12  # north_star: p-values within 1e-12 relative; everything else bit-exact
@@ -27,8 +27,10 @@ def set_params_from(eng: capi.Engine, p: dict):
                    p["prob_cutoff"], p["gaps"])
 
 
-def replay_trace(eng: capi.Engine, tr: Trace, rtol_p: float, check_dots: bool = True, batch_l2: bool = True) -> List[str]:
-    """Returns a list of mismatch descriptions (empty == parity)."""
+def replay_trace(eng: capi.Engine, tr: Trace, rtol_p: float, check_dots: bool = True, batch_l2: bool = True,
+                 filtered: bool = False) -> List[str]:
+    """Returns a list of mismatch descriptions (empty == parity).  filtered: every profile is also searched through
+    the `_filtered` entry point and compared with what the reference's own search kept (homolog-count filter)."""
     errs: List[str] = []
     set_params_from(eng, tr.params)
     eng.clear_masks()
@@ -76,9 +78,33 @@ def replay_trace(eng: capi.Engine, tr: Trace, rtol_p: float, check_dots: bool = 
             msg = capi.compare_packed(r.bytes, concat_packed([g.packed for g in cur]), rtol_p)
             if msg:
                 errs.append(f"HL profile {cur[0].profile_idx if cur else '?'}: {msg}")
+            if filtered and prof.links is not None and len(prof.links):
+                rf = eng.profile_search_filtered(prof)
+                msg = capi.compare_packed(rf.bytes, kept_packed(cur), rtol_p)
+                if msg:
+                    errs.append(f"HL profile {cur[0].profile_idx if cur else '?'}, homolog filter: {msg}")
+                n_kept = sum(int(g.kept.sum()) for g in cur)
+                if rf.n_multiplicons != n_kept:
+                    errs.append(f"HL profile {cur[0].profile_idx if cur else '?'}: {rf.n_multiplicons} multiplicons in the stats, {n_kept} kept by the reference")
             if len(errs) > 20:
                 break
     return errs
+
+
+def trace_searches(tr: Trace):
+    """The profile searches of a trace in order: (masks applied before the search, profile, its HL GHM records)."""
+    out, masks, prof, cur = [], [], None, []
+    for ev in tr.events:
+        if ev[0] == "mask":
+            masks.append((ev[1], ev[2], ev[3]))
+        elif ev[0] == "profile":
+            prof, cur = ev[1], []
+        elif ev[0] == "hl":
+            cur.append(ev[1])
+        elif ev[0] == "done":
+            out.append((masks, prof, cur))
+            masks = []
+    return out
 
 
 def golden_traces(kind: Optional[str] = None) -> List[str]:

@@ -15,6 +15,8 @@ driven GHM by GHM).  Layout (little endian):
      3 PROFILE  : i32 S, L, x_object_id; S*L x {i32 fam, gid, num_id, u8 flags(bit0 strand, bit1 gap)}
      4 HL GHM   : i32 y_list; dots; packed (before the homolog filter); i32 n, u8 kept[n]
      5 HL DONE  : i32 n_found
+     6 LINKS    : i32 n, n x {i32 segment_x, segment_y, gene_x_id, gene_y_id}  (after a PROFILE record: the Link set
+                  the search inherits from the profile's multiplicon, Multiplicon.cpp:343-344; set<Link> order)
      0 end
   dots  : per orientation o=0,1: i32 n, n x {i32 x, i32 y}
   packed: i32 n_bytes, bytes = Multiplicon::packMultiplicons
@@ -159,6 +161,11 @@ def read_trace(path: str) -> Trace:
             tr.events.append(("hl", GhmRec("hl", -1, y, d, pk, kept, pidx)))
         elif tag == 5:
             tr.events.append(("done", r.i32()))
+        elif tag == 6:
+            lk = r.rec("<i4", 4 * r.i32()).reshape(-1, 4).copy()
+            kind, prof = tr.events[-1][0], tr.events[-1][1]
+            assert kind == "profile"
+            prof.links = lk
         else:
             raise ValueError(f"bad tag {tag} at {r.o}")
     return tr
@@ -172,3 +179,29 @@ def concat_packed(chunks: List[bytes]) -> bytes:
         n += struct.unpack_from("<i", c, 0)[0]
         body.append(c[4:])
     return struct.pack("<i", n) + b"".join(body)
+
+
+def split_packed(b: bytes) -> List[bytes]:
+    """The byte range of every multiplicon of a packMultiplicons buffer (33-byte header, per cluster 102 + 17 * n_ap)."""
+    n = struct.unpack_from("<i", b, 0)[0]
+    o, out = 4, []
+    for _ in range(n):
+        begin = o
+        ncl = struct.unpack_from("<i", b, o + 29)[0]
+        o += 33
+        for _ in range(ncl):
+            o += 102 + 17 * struct.unpack_from("<i", b, o + 98)[0]
+        out.append(b[begin:o])
+    assert o == len(b)
+    return out
+
+
+def kept_packed(ghms) -> bytes:
+    """What the reference's own search returns for the HL GHMs of one profile: the multiplicons that passed the
+    homolog-count filter of GHMProfile.cpp:129-132 (`kept` flags of the trace), as one stream."""
+    body = []
+    for g in ghms:
+        ms = split_packed(g.packed)
+        assert len(ms) == len(g.kept)
+        body += [m for m, k in zip(ms, g.kept) if k]
+    return struct.pack("<i", len(body)) + b"".join(body)
