@@ -74,8 +74,9 @@ cudaError_t launch_resident(GhmTask* tasks, const int* order, int n_tasks, int* 
                             int grid, int nt, cudaStream_t st, unsigned long long* dbg = nullptr);
 int resident_ctas_per_sm(int nt, int smem_bytes);
 bool pass_cfg_supported(int code);
-void launch_link_tables(const LinkRec* links, int64_t n_links, int64_t n_elems, const ProfileDev& pf, int32_t* cols, int32_t* cnt,
-                        int32_t* lk_ptr, int32_t* lk_col, int32_t* block_sum, int sm_count, cudaStream_t st);
+void launch_link_tables(const LinkIn* links, const int64_t* link_ptr, int64_t n_links, const int32_t* elem_base, int n_prof, int64_t n_elems,
+                        const ProfileDev& pf, unsigned long long* keys, int32_t* vals, uint32_t mask, int32_t* cols, int32_t* cnt,
+                        int32_t* lk_ptr, int32_t* lk_col, int32_t* block_sum, cudaStream_t st);
 void launch_homolog_filter(GhmTask* tasks, int n_tasks, uint8_t* ws, const DatasetDev& ds, int n_fam, const ProfileDev& pf,
                            const HomologDev* hdev, int pool_factor, int min_homologs, int sm_count, cudaStream_t st);
 void launch_pack_write(bool hl, const GhmTask* tasks, const int* sel, const int64_t* out_off, int n_sel, uint8_t* ws,
@@ -448,8 +449,7 @@ struct iadh_ctx {
     // points around run_batch
     bool hf_active = false;
     int64_t hf_dropped = 0;   // multiplicons the filter removed in the last run_batch
-    DBuf d_links, d_lk_cols, d_lk_cnt, d_lk_ptr, d_lk_col, d_lk_bsum, d_hdev;
-    HBuf h_links;
+    DBuf d_links, d_link_ptr, d_elem_base, d_lk_keys, d_lk_vals, d_lk_cols, d_lk_cnt, d_lk_ptr, d_lk_col, d_lk_bsum, d_hdev;
     // build_dots scratch
     std::vector<int64_t> bd_cnt;
     std::vector<int32_t> bd_dots;
@@ -723,52 +723,62 @@ static int upload_profile(iadh_ctx* c, const iadh_profile_desc* p, ProfileHost& 
 static int upload_links(iadh_ctx* c, const iadh_profile_desc* profiles, int n_profiles, const uint8_t* mine, const iadh_link_t* links,
                         const int64_t* link_ptr, const ProfileDev& pf, iadh_stats& st)
 {
+    static_assert(sizeof(LinkIn) == sizeof(iadh_link_t), "Links are uploaded as the caller laid them out");
     if (!links || !link_ptr) return fail(IADH_ERR_ARG, "homolog filter: null Link arrays");
     if (link_ptr[0] < 0) return fail(IADH_ERR_ARG, "homolog filter: link_ptr[0] < 0");
-    std::vector<LinkRec> recs;
-    std::vector<int64_t> base((size_t)n_profiles, 0);
-    int64_t n_elems = 0;
+    // this rank's profiles: their Links back to back on the device, their elements numbered consecutively
+    std::vector<int64_t> lptr((size_t)n_profiles + 1, 0);
+    std::vector<int32_t> ebase((size_t)n_profiles + 1, 0);
+    int64_t n_elems = 0, nl = 0;
     for (int k = 0; k < n_profiles; k++) {
         const int64_t b = link_ptr[k], e = link_ptr[k + 1];
         if (e < b) return fail(IADH_ERR_ARG, "homolog filter: link_ptr not ascending at profile %d", k);
-        if (mine && !mine[k]) continue;
-        if (e == b)
-            return fail(IADH_ERR_ARG, "homolog filter: profile %d without Links (a profile's multiplicon owns the Links of its anchor points)", k);
-        const int S = profiles[k].n_segments, L = profiles[k].length;
-        base[k] = n_elems;
-        n_elems += (int64_t)S * L;
-        if (n_elems > 0x7ffffff0ll || (e - b) + (int64_t)recs.size() > 0x3ffffff0ll)
-            return fail(IADH_ERR_CAPACITY, "homolog filter: more than 2^31 profile elements or 2^30 Links in one call");
-        for (int64_t i = b; i < e; i++) {
-            const iadh_link_t& l = links[i];
-            if (l.segment_x < 0 || l.segment_x >= S || l.segment_y < 0 || l.segment_y >= S)
-                return fail(IADH_ERR_ARG, "homolog filter: Link %lld of profile %d names segment %d / %d of %d", (long long)(i - b), k, l.segment_x, l.segment_y, S);
-            LinkRec r;
-            r.seg_x = l.segment_x; r.seg_y = l.segment_y; r.gene_x = l.gene_x_id; r.gene_y = l.gene_y_id;
-            r.prof = k;
-            r.base = (int32_t)base[k];
-            recs.push_back(r);
+        if (!mine || mine[k]) {
+            if (e == b)
+                return fail(IADH_ERR_ARG, "homolog filter: profile %d without Links (a profile's multiplicon owns the Links of its anchor points)", k);
+            const int S = profiles[k].n_segments, L = profiles[k].length;
+            for (int64_t i = b; i < e; i++) {
+                const iadh_link_t& l = links[i];
+                if (l.segment_x < 0 || l.segment_x >= S || l.segment_y < 0 || l.segment_y >= S)
+                    return fail(IADH_ERR_ARG, "homolog filter: Link %lld of profile %d names segment %d / %d of %d", (long long)(i - b), k, l.segment_x, l.segment_y, S);
+            }
+            n_elems += (int64_t)S * L;
+            nl += e - b;
+            if (n_elems > 0x3ffffff0ll || nl > 0x3ffffff0ll)
+                return fail(IADH_ERR_CAPACITY, "homolog filter: more than 2^30 profile elements or Links in one call");
         }
+        lptr[k + 1] = nl;
+        ebase[k + 1] = (int32_t)n_elems;
     }
-    const int64_t nl = (int64_t)recs.size();
+    uint32_t slots = 16;
+    while ((int64_t)slots < 2 * n_elems) slots <<= 1;
     int rc;
+    CU(c->d_links.ensure(sizeof(LinkIn) * (size_t)nl + 16));
     CU(c->d_lk_cols.ensure(8 * (size_t)nl + 16));
     CU(c->d_lk_col.ensure(8 * (size_t)nl + 16));
     CU(c->d_lk_cnt.ensure(4 * (size_t)n_elems + 16));
     CU(c->d_lk_ptr.ensure(4 * (size_t)(n_elems + 1) + 16));
     CU(c->d_lk_bsum.ensure(4 * (size_t)(n_elems / 1024 + 2) + 16));
-    if ((rc = upload(c->d_links, recs.data(), sizeof(LinkRec) * (size_t)nl, c->st))) return rc;
+    CU(c->d_lk_keys.ensure(8 * (size_t)slots));
+    CU(c->d_lk_vals.ensure(4 * (size_t)slots));
+    for (int k = 0; k < n_profiles; k++)
+        if (lptr[k + 1] > lptr[k])
+            CU(cudaMemcpyAsync(c->d_links.as<LinkIn>() + lptr[k], links + link_ptr[k], sizeof(LinkIn) * (size_t)(lptr[k + 1] - lptr[k]),
+                               cudaMemcpyHostToDevice, c->st));
+    if ((rc = upload(c->d_link_ptr, lptr.data(), 8 * lptr.size(), c->st))) return rc;
+    if ((rc = upload(c->d_elem_base, ebase.data(), 4 * ebase.size(), c->st))) return rc;
     std::vector<HomologDev> hd((size_t)n_profiles);
     for (int k = 0; k < n_profiles; k++) {
-        hd[k].lk_ptr = c->d_lk_ptr.as<int32_t>() + base[k];   // (profiles of other ranks: never dereferenced, no GHM names them)
+        hd[k].lk_ptr = c->d_lk_ptr.as<int32_t>() + ebase[k];   // (profiles of other ranks: never dereferenced, no GHM names them)
         hd[k].lk_col = c->d_lk_col.as<int32_t>();
     }
     if ((rc = upload(c->d_hdev, hd.data(), sizeof(HomologDev) * hd.size(), c->st))) return rc;
-    launch_link_tables(c->d_links.as<LinkRec>(), nl, n_elems, pf, c->d_lk_cols.as<int32_t>(), c->d_lk_cnt.as<int32_t>(), c->d_lk_ptr.as<int32_t>(),
-                       c->d_lk_col.as<int32_t>(), c->d_lk_bsum.as<int32_t>(), c->sm_count, c->st);
+    launch_link_tables(c->d_links.as<LinkIn>(), c->d_link_ptr.as<int64_t>(), nl, c->d_elem_base.as<int32_t>(), n_profiles, n_elems, pf,
+                       c->d_lk_keys.as<unsigned long long>(), c->d_lk_vals.as<int32_t>(), slots - 1, c->d_lk_cols.as<int32_t>(),
+                       c->d_lk_cnt.as<int32_t>(), c->d_lk_ptr.as<int32_t>(), c->d_lk_col.as<int32_t>(), c->d_lk_bsum.as<int32_t>(), c->st);
     CU(cudaGetLastError());
-    st.h2d_bytes += (int64_t)(sizeof(LinkRec) * (size_t)nl + sizeof(HomologDev) * hd.size());
-    st.kernel_launches += nl > 0 ? 6 : 3;   // resolve, count, 3 x scan, fill
+    st.h2d_bytes += (int64_t)(sizeof(LinkIn) * (size_t)nl + 12 * (size_t)(n_profiles + 1) + sizeof(HomologDev) * hd.size());
+    st.kernel_launches += (n_elems > 0 ? 1 : 0) + (nl > 0 ? 3 : 0) + 3;   // hash, resolve, count, fill, 3 x scan
     return IADH_OK;
 }
 
@@ -2293,7 +2303,8 @@ void iadh_destroy(iadh_ctx* c)
     if (c->st) cudaStreamSynchronize(c->st);
     DBuf* bufs[] = {&c->d_list_off, &c->d_fam, &c->d_gid, &c->d_num_id, &c->d_flags, &c->d_fam_ptr, &c->d_fam_members, &c->d_mem_y, &c->d_plus_prefix, &c->d_self_slot, &c->d_fam_list, &c->d_mem_list, &c->d_elem_list, &c->d_pair_idx, &c->d_row_used, &c->d_cur, &c->d_hl_items, &c->d_ghdr,
                     &c->d_tasks, &c->d_tile_prefix, &c->d_tile_cnt, &c->d_tile_off, &c->d_dots, &c->d_ws, &c->d_items, &c->d_items1, &c->d_passctr, &c->d_prof, &c->d_plan, &c->d_cnt, &c->d_outs,
-                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis, &c->d_init};
+                    &c->d_sel, &c->d_out_off, &c->d_out, &c->d_counter, &c->d_pf_col, &c->d_items_res, &c->d_items_fb, &c->d_resdbg, &c->d_istate, &c->d_vis, &c->d_init,
+                    &c->d_links, &c->d_link_ptr, &c->d_elem_base, &c->d_lk_keys, &c->d_lk_vals, &c->d_lk_cols, &c->d_lk_cnt, &c->d_lk_ptr, &c->d_lk_col, &c->d_lk_bsum, &c->d_hdev};
     for (DBuf* b : bufs) b->release();
     c->h_tasks.release();
     c->h_misc.release();

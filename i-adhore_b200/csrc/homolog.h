@@ -2,12 +2,10 @@
 #pragma once
 #include <stdint.h>
 
-// One Link of the profile's multiplicon (Multiplicon.h:22-52) as uploaded: segment indices and gene numIDs, the
-// profile of the batch it belongs to and that profile's first element in the concatenated element index space.
-struct LinkRec {
+// One Link of a profile's multiplicon (Multiplicon.h:22-52) as the caller hands it over: layout of iadh_link_t
+// (include/iadhore_b200.h), uploaded as is.
+struct LinkIn {
     int32_t seg_x, seg_y, gene_x, gene_y;
-    int32_t prof;
-    int32_t base;
 };
 
 // Per profile: CSR over its S * L elements (segment-major, like ProfileDev::num_id) -> columns of the other ends of the

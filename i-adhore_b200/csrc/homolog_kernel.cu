@@ -9,8 +9,9 @@
 //       inside the cut (both ends are profile elements, i.e. both columns must lie in [begin_x, end_x]), or
 //   (b) addLinks (:423-494): an x-segment element and a y-segment element are homologous -- same family and not the
 //       same list element (:484-485) / in pairs mode the y gene is in the x gene's pair set (:437) -- which marks both.
-// Here: the inherited Links of a profile are resolved to columns once per search (link_resolve_kernel) and turned into
-// a CSR "element -> columns of its Link partners" (count, scan, fill); the filter kernel then evaluates (a) by a range
+// Here: the inherited Links of a profile are resolved to columns once per search (a hash table (segment, numID) -> column
+// over the profile elements, one probe per Link end) and turned into a CSR "element -> columns of its Link partners"
+// (count, scan, fill); the filter kernel then evaluates (a) by a range
 // test over an element's few partners and (b) by intersecting the element's family bucket (the dataset's CSR, members
 // ascending) with [begin_y, end_y], which marks the y side in a shared-memory bitmap at the same time.  A multiplicon
 // costs S * (end_x - begin_x + 1) bucket look-ups instead of the reference's S * |x| * |y| string compares.  Dropped
@@ -31,57 +32,120 @@ namespace {
 constexpr int HT = 128;                                  // threads of a filter CTA
 constexpr int YW = (IADH_MAX_COORD + 31) / 32 + 1;      // bitmap words for the longest possible y range
 
-// one warp per Link end: the column of gene `id` in segment `seg` of the Link's profile, or -1
-// (numIDs are unique per list element, DataSet.cpp:76-81, so a segment holds an id at most once;
-//  pruneLinks' map would keep the last occurrence, Multiplicon.cpp:397 -- so does the max below)
-__global__ void __launch_bounds__(256) link_resolve_kernel(const LinkRec* __restrict__ links, int64_t n_links, ProfileDev pf_call,
-                                                           int32_t* __restrict__ cols)
+// ---- link tables -----------------------------------------------------------------------------------------------
+// Links arrive as the caller's array (include/iadhore_b200.h: iadh_link_t = LinkIn), the Links of profile k at
+// [link_ptr[k], link_ptr[k+1]); the elements of the profiles this rank searches are numbered consecutively, profile k
+// from elem_base[k] (segment-major inside a profile, like ProfileDev::num_id).
+
+// the profile an index of a CSR-like prefix array belongs to: largest k with ptr[k] <= i (empty ranges are skipped)
+template <typename T>
+__device__ __forceinline__ int owner_of(const T* __restrict__ ptr, int n, int64_t i)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < 2 * n_links; w += n_warps) {
-        const LinkRec& lk = links[w >> 1];
-        const int end = (int)(w & 1);
-        const int seg = end ? lk.seg_y : lk.seg_x, id = end ? lk.gene_y : lk.gene_x;
-        const ProfileDev& pf = profile_of(pf_call, lk.prof);
-        const int32_t* num = pf.num_id + (size_t)seg * pf.L;
-        const uint8_t* flg = pf.flags + (size_t)seg * pf.L;
-        int found = -1;
-        for (int x = lane; x < pf.L; x += 32)
-            if (!(flg[x] & 2) && num[x] == id) found = x;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, d));
-        if (lane == 0) cols[w] = found;
+    int lo = 0, hi = n;   // invariant: ptr[lo] <= i < ptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)ptr[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+// (first element of the segment, numID) identifies a profile element: numIDs are unique per list element
+// (DataSet.cpp:76-81); should a segment ever hold an id twice, the later column wins, as in the map pruneLinks
+// builds (Multiplicon.cpp:397)
+__device__ __forceinline__ unsigned long long elem_key(int seg_first, int id) { return ((unsigned long long)(uint32_t)seg_first << 32) | (uint32_t)id; }
+
+// open-addressing table (key -> column) over all non-gap elements; keys start as ~0, vals as -1
+__global__ void __launch_bounds__(256) link_hash_kernel(const int32_t* __restrict__ elem_base, int n_prof, int64_t n_elems, ProfileDev pf_call,
+                                                        unsigned long long* keys, int32_t* vals, uint32_t mask)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    const int k = owner_of(elem_base, n_prof, e);
+    const ProfileDev& pf = profile_of(pf_call, k);
+    const int local = (int)(e - elem_base[k]);
+    if (pf.flags[local] & 2) return;   // gap
+    const int col = local % pf.L;
+    const unsigned long long key = elem_key(elem_base[k] + (local - col), pf.num_id[local]);
+    uint32_t slot = hash_key(key) & mask;
+    while (true) {
+        const unsigned long long old = atomicCAS(&keys[slot], ~0ull, key);
+        if (old == ~0ull || old == key) {
+            atomicMax(&vals[slot], col);
+            return;
+        }
+        slot = (slot + 1) & mask;
     }
 }
 
+// per Link end: the column of its gene in its segment, or -1 (gene not in the profile / segment index out of range)
+__global__ void __launch_bounds__(256) link_resolve_kernel(const LinkIn* __restrict__ links, const int64_t* __restrict__ link_ptr,
+                                                           const int32_t* __restrict__ elem_base, int n_prof, ProfileDev pf_call,
+                                                           const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                           uint32_t mask, int32_t* __restrict__ cols)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 2 * link_ptr[n_prof]) return;
+    const LinkIn lk = links[w >> 1];
+    const int k = owner_of(link_ptr, n_prof, w >> 1);
+    const ProfileDev& pf = profile_of(pf_call, k);
+    const int seg = (w & 1) ? lk.seg_y : lk.seg_x, id = (w & 1) ? lk.gene_y : lk.gene_x;
+    int found = -1;
+    if (seg >= 0 && seg < pf.S) {
+        const unsigned long long key = elem_key(elem_base[k] + seg * pf.L, id);
+        uint32_t slot = hash_key(key) & mask;
+        while (true) {
+            const unsigned long long cur = keys[slot];
+            if (cur == key) {
+                found = vals[slot];
+                break;
+            }
+            if (cur == ~0ull) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+    cols[w] = found;
+}
+
 // per profile element: number of inherited Links it is an end of (Links with an unresolved end never survive)
-__global__ void __launch_bounds__(256) link_count_kernel(const LinkRec* __restrict__ links, int64_t n_links, ProfileDev pf_call,
+__global__ void __launch_bounds__(256) link_count_kernel(const LinkIn* __restrict__ links, const int64_t* __restrict__ link_ptr,
+                                                         const int32_t* __restrict__ elem_base, int n_prof, ProfileDev pf_call,
                                                          const int32_t* __restrict__ cols, int32_t* cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_links) return;
+    if (i >= link_ptr[n_prof]) return;
     const int cx = cols[2 * i], cy = cols[2 * i + 1];
     if (cx < 0 || cy < 0) return;
-    const LinkRec& lk = links[i];
-    const int L = profile_of(pf_call, lk.prof).L;
-    atomicAdd(&cnt[(size_t)lk.base + (size_t)lk.seg_x * L + cx], 1);
-    atomicAdd(&cnt[(size_t)lk.base + (size_t)lk.seg_y * L + cy], 1);
+    const LinkIn lk = links[i];
+    const int k = owner_of(link_ptr, n_prof, i);
+    const int L = profile_of(pf_call, k).L;
+    atomicAdd(&cnt[(size_t)elem_base[k] + (size_t)lk.seg_x * L + cx], 1);
+    atomicAdd(&cnt[(size_t)elem_base[k] + (size_t)lk.seg_y * L + cy], 1);
 }
 
 // CSR fill: every element gets the columns of its partners (order inside an element's run is arbitrary: the filter
 // only asks whether ANY partner lies in a column range)
-__global__ void __launch_bounds__(256) link_fill_kernel(const LinkRec* __restrict__ links, int64_t n_links, ProfileDev pf_call,
+__global__ void __launch_bounds__(256) link_fill_kernel(const LinkIn* __restrict__ links, const int64_t* __restrict__ link_ptr,
+                                                        const int32_t* __restrict__ elem_base, int n_prof, ProfileDev pf_call,
                                                         const int32_t* __restrict__ cols, const int32_t* __restrict__ lk_ptr,
                                                         int32_t* cursor, int32_t* __restrict__ lk_col)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_links) return;
+    if (i >= link_ptr[n_prof]) return;
     const int cx = cols[2 * i], cy = cols[2 * i + 1];
     if (cx < 0 || cy < 0) return;
-    const LinkRec& lk = links[i];
-    const int L = profile_of(pf_call, lk.prof).L;
-    const size_t ex = (size_t)lk.base + (size_t)lk.seg_x * L + cx, ey = (size_t)lk.base + (size_t)lk.seg_y * L + cy;
+    const LinkIn lk = links[i];
+    const int k = owner_of(link_ptr, n_prof, i);
+    const int L = profile_of(pf_call, k).L;
+    const size_t ex = (size_t)elem_base[k] + (size_t)lk.seg_x * L + cx, ey = (size_t)elem_base[k] + (size_t)lk.seg_y * L + cy;
     lk_col[lk_ptr[ex] + atomicAdd(&cursor[ex], 1)] = cy;
     lk_col[lk_ptr[ey] + atomicAdd(&cursor[ey], 1)] = cx;
 }
@@ -222,23 +286,26 @@ __global__ void __launch_bounds__(HT) homolog_filter_kernel(GhmTask* tasks, int 
 #ifndef IADH_HOST_EMU
 void launch_scan_i32(const int32_t* in, int64_t n, int32_t* out, int32_t* block_sum, cudaStream_t st);
 
-// links -> per-element partner columns.  cols: 2 * n_links ints, cnt: n_elems ints (zeroed here, reused as the fill
-// cursor), lk_ptr: n_elems + 1, lk_col: 2 * n_links, block_sum: n_elems / 1024 + 2
-void launch_link_tables(const LinkRec* links, int64_t n_links, int64_t n_elems, const ProfileDev& pf, int32_t* cols, int32_t* cnt,
-                        int32_t* lk_ptr, int32_t* lk_col, int32_t* block_sum, int sm_count, cudaStream_t st)
+// links -> per-element partner columns.  keys / vals: hash table of `mask + 1` slots (a power of two >= 2 * n_elems),
+// cols: 2 * n_links ints, cnt: n_elems ints (zeroed here, reused as the fill cursor), lk_ptr: n_elems + 1,
+// lk_col: 2 * n_links, block_sum: n_elems / 1024 + 2
+void launch_link_tables(const LinkIn* links, const int64_t* link_ptr, int64_t n_links, const int32_t* elem_base, int n_prof, int64_t n_elems,
+                        const ProfileDev& pf, unsigned long long* keys, int32_t* vals, uint32_t mask, int32_t* cols, int32_t* cnt,
+                        int32_t* lk_ptr, int32_t* lk_col, int32_t* block_sum, cudaStream_t st)
 {
-    cudaMemsetAsync(cnt, 0, 4 * (size_t)n_elems, st);
+    cudaMemsetAsync(cnt, 0, 4 * (size_t)n_elems + 4, st);
+    cudaMemsetAsync(keys, 0xff, 8 * ((size_t)mask + 1), st);
+    cudaMemsetAsync(vals, 0xff, 4 * ((size_t)mask + 1), st);
+    const unsigned gl = (unsigned)((n_links + 255) / 256), ge = (unsigned)((n_elems + 255) / 256);
+    if (n_elems > 0) link_hash_kernel<<<ge, 256, 0, st>>>(elem_base, n_prof, n_elems, pf, keys, vals, mask);
     if (n_links > 0) {
-        const unsigned g = (unsigned)((n_links + 255) / 256);
-        const int64_t warps = 2 * n_links;
-        link_resolve_kernel<<<(unsigned)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count * 32), 256, 0, st>>>(links, n_links, pf, cols);
-        link_count_kernel<<<g, 256, 0, st>>>(links, n_links, pf, cols, cnt);
+        link_resolve_kernel<<<(unsigned)((2 * n_links + 255) / 256), 256, 0, st>>>(links, link_ptr, elem_base, n_prof, pf, keys, vals, mask, cols);
+        link_count_kernel<<<gl, 256, 0, st>>>(links, link_ptr, elem_base, n_prof, pf, cols, cnt);
     }
     launch_scan_i32(cnt, n_elems, lk_ptr, block_sum, st);
     if (n_links > 0) {
-        const unsigned g = (unsigned)((n_links + 255) / 256);
-        cudaMemsetAsync(cnt, 0, 4 * (size_t)n_elems, st);
-        link_fill_kernel<<<g, 256, 0, st>>>(links, n_links, pf, cols, lk_ptr, cnt, lk_col);
+        cudaMemsetAsync(cnt, 0, 4 * (size_t)n_elems + 4, st);
+        link_fill_kernel<<<gl, 256, 0, st>>>(links, link_ptr, elem_base, n_prof, pf, cols, lk_ptr, cnt, lk_col);
     }
 }
 

@@ -65,11 +65,13 @@ def simple_profile(ds: capi.Dataset, xl: int, yl: int, m: capi.PMultiplicon) -> 
     return capi.Profile(2, L, xl, fam, gid, nid, flg)
 
 
-def load_reference_profiles(ds: capi.Dataset, path: str, limit: int = -1):
+def load_reference_profiles(ds: capi.Dataset, path: str, limit: int = -1, links_path: str = None):
     """The reference's own aligned profiles of a bench workload (tools/make_ref_profiles.py: dumped by
     oracle/_ref/ref_harness --dump-profiles), in the order the reference searches them.
     -> [(masks, Profile)], masks = [(list, begin, end)] applied before that profile (higherLevel.cpp:165-171).
-    Elements are identified by ListElement::getNumID(), which the ingest mirror reproduces."""
+    Elements are identified by ListElement::getNumID(), which the ingest mirror reproduces.
+    links_path: the file written by --dump-profile-links beside it; every Profile then carries `.links`, the Link set
+    its search inherits (input of the homolog-count filter)."""
     import gzip
     import struct
     raw = gzip.open(path, "rb").read()
@@ -98,4 +100,11 @@ def load_reference_profiles(ds: capi.Dataset, path: str, limit: int = -1):
         nid = np.where(gap, -1, e["num"]).astype(np.int32)
         flg = np.where(gap, capi.F_GAP, e["o"] & 1).astype(np.uint8)
         out.append((masks, capi.Profile(S, L, xid, fam, gid, nid, flg)))
+    if links_path:
+        lraw = gzip.open(links_path, "rb").read()
+        lo = 0
+        for _, p in out:
+            (nl,) = struct.unpack_from("<i", lraw, lo)
+            p.links = np.frombuffer(lraw, dtype="<i4", count=4 * nl, offset=lo + 4).reshape(nl, 4).copy()
+            lo += 4 + 16 * nl
     return out

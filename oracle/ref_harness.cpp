@@ -9,7 +9,7 @@
 // the CUDA path.  Trace layout: see tests/trace_io.py.
 //
 // usage: ref_harness <ini> <trace.bin|-> [--no-hl] [--max-profiles N] [--max-pairs N] [--time]
-//                    [--threads T] [--no-dump] [--dump-profiles file]
+//                    [--threads T] [--no-dump] [--dump-profiles file] [--dump-profile-links file]
 // With --threads the GHMs of a stage are evaluated concurrently (each thread owns its GHM,
 // exactly like the reference's work functions, DataSet.h:79,204); results are consumed in
 // sequence order, so the trace is identical to the 1-thread one.  --no-dump (or "-" as the
@@ -156,6 +156,9 @@ int main(int argc, char** argv)
     // masks applied before it (bench.py replays them on the device so that both arms search the same profiles):
     //   i32 n_masks, n_masks x (i32 list, begin, end); i32 S, L, x_object_id; S*L x (i32 numID or -1 = gap, u8 orientation)
     FILE* profOut = NULL;
+    // --dump-profile-links <file>: beside --dump-profiles, per dumped profile the Link set its search inherits
+    // (Multiplicon.cpp:343-344): i32 n_links, n_links x (i32 segment_x, segment_y, gene_x_id, gene_y_id)
+    FILE* linkOut = NULL;
     long maxProfiles = -1, maxPairs = -1;
     int threads = 1;
     for (int i = 3; i < argc; i++) {
@@ -166,6 +169,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--max-pairs") && i + 1 < argc) maxPairs = atol(argv[++i]);
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--dump-profiles") && i + 1 < argc) profOut = fopen(argv[++i], "wb");
+        else if (!strcmp(argv[i], "--dump-profile-links") && i + 1 < argc) linkOut = fopen(argv[++i], "wb");
     }
 
     ParToolBox::init(&argc, &argv);
@@ -398,6 +402,15 @@ int main(int argc, char** argv)
                     }
                     fwrite(q.data(), 1, q.size(), profOut);
                 }
+                if (linkOut) {
+                    Blob q;
+                    const set<Link>& hs = profile->getMultiplicon().getHomologs();
+                    w32(q, (int)hs.size());
+                    for (set<Link>::const_iterator e = hs.begin(); e != hs.end(); e++) {
+                        w32(q, e->segmentX); w32(q, e->segmentY); w32(q, e->geneXID); w32(q, e->geneYID);
+                    }
+                    fwrite(q.data(), 1, q.size(), linkOut);
+                }
                 nProfiles++;
 
                 // the lists searched for this profile (higherLevel.cpp:36-41)
@@ -486,6 +499,7 @@ int main(int argc, char** argv)
         fclose(out);
     }
     if (profOut) fclose(profOut);
+    if (linkOut) fclose(linkOut);
     if (timing)
         fprintf(stderr, "HL: profiles=%ld ghmprofiles=%ld build=%.6fs run=%.6fs wall=%.6fs threads=%d found=%ld\n",
                 nProfiles, nGhmp, tHLbuild, tHLrun, wallHL, threads, nFound);

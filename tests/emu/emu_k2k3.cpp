@@ -105,9 +105,10 @@ int main(int argc, char** argv)
         int S, L;
         std::vector<int32_t> fam, gid, num_id;
         std::vector<uint8_t> flags;
-        std::vector<LinkRec> links;
-        std::vector<int32_t> lk_ptr, lk_col;
+        std::vector<LinkIn> links;
+        int32_t lk_base = 0;   // first element of the profile in the batch's link tables
     };
+    std::vector<int32_t> all_lk_ptr, all_lk_col;
     int n_prof = 0;
     if (!rd(f, &n_prof, 1)) return 2;
     std::vector<Prof> profs(n_prof);
@@ -125,26 +126,52 @@ int main(int argc, char** argv)
             if (!rd(f, raw.data(), raw.size())) return 2;
             p.links.resize(nl);
             for (int i = 0; i < nl; i++) {
-                LinkRec& r = p.links[i];
+                LinkIn& r = p.links[i];
                 r.seg_x = raw[4 * i]; r.seg_y = raw[4 * i + 1]; r.gene_x = raw[4 * i + 2]; r.gene_y = raw[4 * i + 3];
-                r.prof = 0;
-                r.base = 0;
             }
-            // the link tables, as launch_link_tables builds them (homolog_kernel.cu): resolve, count, scan, fill
-            ProfileDev pf;
+        }
+    }
+    if ((fmt & 1) && n_prof > 0) {
+        // the link tables of ALL profiles in one go, as launch_link_tables builds them for a batch (homolog_kernel.cu):
+        // hash, resolve, count, scan, fill over the concatenated Links / elements.  Every profile is followed by an
+        // empty slot (a profile of the batch that another rank searches: no Links, no elements here).
+        const int np2 = 2 * n_prof;
+        std::vector<ProfileDev> pdev(np2);
+        std::vector<int64_t> link_ptr(np2 + 1, 0);
+        std::vector<int32_t> elem_base(np2 + 1, 0);
+        std::vector<LinkIn> all;
+        for (int k = 0; k < n_prof; k++) {
+            Prof& p = profs[k];
+            ProfileDev& pf = pdev[2 * k];
             memset(&pf, 0, sizeof pf);
             pf.S = p.S; pf.L = p.L;
             pf.fam = p.fam.data(); pf.gid = p.gid.data(); pf.num_id = p.num_id.data(); pf.flags = p.flags.data();
-            std::vector<int32_t> cols(2 * (size_t)nl + 1, -7), cnt(n + 1, 0);
-            p.lk_ptr.assign(n + 1, 0);
-            p.lk_col.assign(2 * (size_t)nl + 1, -7);
-            emu::run_block(0, 256, [&]() { link_resolve_kernel(p.links.data(), nl, pf, cols.data()); });
-            for (int b = 0; b * 256 < nl; b++) emu::run_block(b, 256, [&]() { link_count_kernel(p.links.data(), nl, pf, cols.data(), cnt.data()); });
-            for (size_t k = 0; k < n; k++) p.lk_ptr[k + 1] = p.lk_ptr[k] + cnt[k];
-            std::fill(cnt.begin(), cnt.end(), 0);
-            for (int b = 0; b * 256 < nl; b++)
-                emu::run_block(b, 256, [&]() { link_fill_kernel(p.links.data(), nl, pf, cols.data(), p.lk_ptr.data(), cnt.data(), p.lk_col.data()); });
+            memset(&pdev[2 * k + 1], 0, sizeof(ProfileDev));
+            all.insert(all.end(), p.links.begin(), p.links.end());
+            link_ptr[2 * k + 1] = link_ptr[2 * k + 2] = (int64_t)all.size();
+            elem_base[2 * k + 1] = elem_base[2 * k + 2] = elem_base[2 * k] + p.S * p.L;
         }
+        const int64_t nl = (int64_t)all.size(), n = elem_base[np2];
+        ProfileDev pfc;
+        memset(&pfc, 0, sizeof pfc);
+        pfc.batch = pdev.data();
+        uint32_t slots = 16;
+        while ((int64_t)slots < 2 * n) slots <<= 1;
+        std::vector<unsigned long long> keys(slots, ~0ull);
+        std::vector<int32_t> vals(slots, -1);
+        std::vector<int32_t> cols(2 * (size_t)nl + 1, -7), cnt((size_t)n + 1, 0);
+        all_lk_ptr.assign((size_t)n + 1, 0);
+        all_lk_col.assign(2 * (size_t)nl + 1, -7);
+        for (int64_t b = 0; b * 256 < n; b++) emu::run_block((unsigned)b, 256, [&]() { link_hash_kernel(elem_base.data(), np2, n, pfc, keys.data(), vals.data(), slots - 1); });
+        for (int64_t b = 0; b * 256 < 2 * nl; b++)
+            emu::run_block((unsigned)b, 256, [&]() { link_resolve_kernel(all.data(), link_ptr.data(), elem_base.data(), np2, pfc, keys.data(), vals.data(), slots - 1, cols.data()); });
+        for (int64_t b = 0; b * 256 < nl; b++)
+            emu::run_block((unsigned)b, 256, [&]() { link_count_kernel(all.data(), link_ptr.data(), elem_base.data(), np2, pfc, cols.data(), cnt.data()); });
+        for (int64_t k = 0; k < n; k++) all_lk_ptr[k + 1] = all_lk_ptr[k] + cnt[k];
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int64_t b = 0; b * 256 < nl; b++)
+            emu::run_block((unsigned)b, 256, [&]() { link_fill_kernel(all.data(), link_ptr.data(), elem_base.data(), np2, pfc, cols.data(), all_lk_ptr.data(), cnt.data(), all_lk_col.data()); });
+        for (int k = 0; k < n_prof; k++) profs[k].lk_base = elem_base[2 * k];
     }
     int n_ghm = 0;
     if (!rd(f, &n_ghm, 1)) return 2;
@@ -239,8 +266,8 @@ int main(int argc, char** argv)
                 if ((fmt & 1) && hl) {   // homolog-count filter between clustering and writer, as in run_batch
                     const Prof& p = profs[pi];
                     HomologDev hd;
-                    hd.lk_ptr = p.lk_ptr.data();
-                    hd.lk_col = p.lk_col.data();
+                    hd.lk_ptr = all_lk_ptr.data() + p.lk_base;
+                    hd.lk_col = all_lk_col.data();
                     n_before += task.n_mult;
                     emu::run_block(0, HT, [&]() { homolog_filter_kernel(&task, 1, ws.data(), ds, n_fam, pf, &hd, pool_factor, prm.anchor_points); });
                 }

@@ -37,12 +37,16 @@ def main():
     with tempfile.TemporaryDirectory(prefix="iadh_prof_") as td:
         ini = synth.write_reference_inputs(cfg, td, n_threads=a.threads)
         raw = os.path.join(td, "profiles.bin")
+        raw_links = os.path.join(td, "links.bin")
         p = subprocess.run([bench.REF_HARNESS, ini, "-", "--time", "--threads", str(a.threads), "--max-profiles", str(a.profiles),
-                            "--max-pairs", str(max_pairs), "--dump-profiles", raw], capture_output=True, text=True)
+                            "--max-pairs", str(max_pairs), "--dump-profiles", raw, "--dump-profile-links", raw_links], capture_output=True, text=True)
         sys.stderr.write(p.stderr[-600:])
         if p.returncode != 0:
             raise SystemExit("ref_harness failed")
-        with open(raw, "rb") as f, gzip.open(out, "wb", compresslevel=9) as g:
+        with open(raw, "rb") as f, gzip.GzipFile(out, "wb", compresslevel=9, mtime=0) as g:
+            g.write(f.read())
+        # the Link sets the searches inherit (input of the homolog-count filter, iadh_profile_search_batch_filtered)
+        with open(raw_links, "rb") as f, gzip.GzipFile(out.replace("bench_profiles_", "bench_profile_links_"), "wb", compresslevel=9, mtime=0) as g:
             g.write(f.read())
     import json
     with open(out.replace(".bin.gz", ".json"), "w") as f:
