@@ -457,15 +457,45 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     pd.num_id = num.data();
     pd.flags = flags.data();
     iadh_result* res = NULL;
+    // The homolog-count filter of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132) runs on the device when the
+    // library gets the Link set the search inherits (Multiplicon.cpp:343-344): the stream then holds exactly the
+    // multiplicons the reference's search returns.  IADH_SHIM_HOST_FILTER=1 keeps the filter on the host (the
+    // unfiltered entry point + the code below), IADH_SHIM_VERIFY_FILTER=1 re-checks every returned multiplicon.
+    static const bool host_filter = getenv("IADH_SHIM_HOST_FILTER") != NULL;
+    static const bool verify_filter = getenv("IADH_SHIM_VERIFY_FILTER") != NULL;
+    const std::set<Link>& inherited = profile->getMultiplicon().getHomologs();
+    const bool device_filter = !host_filter && !inherited.empty();
+    std::vector<iadh_link_t> links;
+    if (device_filter) {
+        links.reserve(inherited.size());
+        for (std::set<Link>::const_iterator e = inherited.begin(); e != inherited.end(); e++) {
+            iadh_link_t l;
+            l.segment_x = e->segmentX;
+            l.segment_y = e->segmentY;
+            l.gene_x_id = e->geneXID;
+            l.gene_y_id = e->geneYID;
+            links.push_back(l);
+        }
+    }
     const double w2 = wall();
-    check(iadh_profile_search(B.ctx, &pd, B.rank, B.n_ranks, &res), "iadh_profile_search");
+    if (device_filter)
+        check(iadh_profile_search_filtered(B.ctx, &pd, links.data(), (int64_t)links.size(), B.rank, B.n_ranks, &res), "iadh_profile_search_filtered");
+    else
+        check(iadh_profile_search(B.ctx, &pd, B.rank, B.n_ranks, &res), "iadh_profile_search");
     res = gather(res);
     const double w3 = wall();
     size_t nbytes = 0;
     const uint8_t* bytes = iadh_result_bytes(res, &nbytes);
     std::vector<Multiplicon*> mplicons;
     static const bool use_prefilter = !getenv("IADH_SHIM_NO_PREFILTER");
-    if (use_prefilter && settings.useFamily() && nbytes > 4) {
+    if (device_filter) {
+        // (the unpack constructor's createHomologs(useFamily, 0) rebuilds the Link set of every kept multiplicon)
+        Multiplicon::unpackHLMultiplicons((const char*)bytes, mplicons, *profile, genelists, settings.useFamily());
+        if (verify_filter)
+            for (size_t i = 0; i < mplicons.size(); i++)
+                if (!enough_homologs(*mplicons[i], settings.getAnchorPoints()))
+                    throw std::runtime_error("IADH_SHIM_VERIFY_FILTER: the device kept a multiplicon the host filter drops");
+    } else if (use_prefilter && settings.useFamily() && nbytes > 4) {
         ProfileLinks pl;
         profile_links(profile, S, L, num, pl);
         std::vector<char> filtered;
@@ -478,9 +508,9 @@ void DataSet::parallelProfileSearch(const Profile* profile, std::vector<Multipli
     B.t_hl += st.total_ms;
     B.n_hl++;
     iadh_free_result(res);
-    // the homolog-count filter of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132)
+    // the homolog-count filter of GHMProfile::setMultiplicons (GHMProfile.cpp:129-132), unless the device applied it
     for (size_t i = 0; i < mplicons.size(); i++) {
-        if (enough_homologs(*mplicons[i], settings.getAnchorPoints())) target.push_back(mplicons[i]);
+        if (device_filter || enough_homologs(*mplicons[i], settings.getAnchorPoints())) target.push_back(mplicons[i]);
         else delete mplicons[i];
     }
     B.n_ghm += st.n_ghm;

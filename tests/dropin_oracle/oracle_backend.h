@@ -12,6 +12,7 @@
 #define iadh_mask_range oracle_mask_range
 #define iadh_clear_masks oracle_clear_masks
 #define iadh_profile_search oracle_profile_search
+#define iadh_profile_search_filtered oracle_profile_search_filtered
 #define iadh_result_bytes oracle_result_bytes
 #define iadh_result_ghm_index oracle_result_ghm_index
 #define iadh_result_stats oracle_result_stats

@@ -40,10 +40,15 @@ def _cfg(name):
     return synth.config_tiny_pairs(seed=15)
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_fdr", "tiny_pairs", "small"])
-def test_dropin_shim_tables_identical_with_oracle_backend(name):
+# filter: where the homolog-count filter of GHMProfile.cpp:129-132 runs -- "library" = inside the search call
+# (iadh_profile_search_filtered, the default; IADH_SHIM_VERIFY_FILTER re-checks every kept multiplicon on the host),
+# "host" = the shim's own filter after the unfiltered call (IADH_SHIM_HOST_FILTER)
+@pytest.mark.parametrize("name,filt", [("tiny", "library"), ("tiny_fdr", "library"), ("tiny_pairs", "library"), ("small", "library"),
+                                       ("tiny_pairs", "host"), ("small", "host")])
+def test_dropin_shim_tables_identical_with_oracle_backend(name, filt, monkeypatch):
     if not _binaries():
         pytest.skip("reference tree / prebuilt binaries not available")
+    monkeypatch.setenv("IADH_SHIM_VERIFY_FILTER" if filt == "library" else "IADH_SHIM_HOST_FILTER", "1")
     cfg = _cfg(name)
     data = synth.generate(cfg)
     td = tempfile.mkdtemp(prefix="shim_cpu_")
