@@ -19,6 +19,12 @@ from iadhore_b200 import synth  # noqa: E402
 
 HARNESS = os.path.join(REPO, "oracle", "_ref", "ref_harness")
 
+def _with(cfg, **kw):
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
 CASES = {
     # name: (config, harness args)
     "tiny_bf": (synth.config_tiny(seed=11), []),
@@ -28,6 +34,9 @@ CASES = {
     # table_type=pairs (trace magic IADHTRC2: carries the pair sets)
     "tiny_pairs": (synth.config_tiny_pairs(seed=15), []),
     "tiny_pairs_fdr": (synth.config_tiny_pairs(seed=16, mult_hyp="FDR"), ["--max-profiles", "15"]),
+    # non-default settings: 5 anchor points (= the minimum of the homolog-count filter, GHM.cpp:218), smaller gaps, q 0.8
+    "tiny_ap5": (_with(synth.config_tiny(seed=17, n_genomes=4), anchor_points=5, gap_size=20, cluster_gap=25, q_value=0.8),
+                 ["--max-profiles", "25"]),
 }
 
 

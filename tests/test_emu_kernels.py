@@ -87,7 +87,7 @@ def test_two_phase_join_kernel_equals_default_join_on_heavy_ghms(emu, tmp_path):
 
 # block sizes of the fused kernel: 32 (single warp), 64 and 256 (the engine's default size classes), 128
 @pytest.mark.parametrize("name,nt", [("tiny_bf", 32), ("tiny_fdr", 32), ("tiny_none", 32), ("tiny_4g", 32), ("tiny_pairs", 32),
-                                     ("tiny_bf", 256), ("tiny_fdr", 64), ("tiny_none", 128), ("tiny_pairs", 256)])
+                                     ("tiny_bf", 256), ("tiny_fdr", 64), ("tiny_none", 128), ("tiny_pairs", 256), ("tiny_ap5", 32), ("tiny_ap5", 256)])
 def test_emulated_device_code_reproduces_the_reference_bytes(emu, tmp_path, name, nt):
     trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
     inp = str(tmp_path / "in.bin")
@@ -109,7 +109,7 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
-@pytest.mark.parametrize("mode,name", [("1", "tiny_bf"), ("1", "tiny_none"), ("2", "tiny_fdr"), ("2", "tiny_4g")])
+@pytest.mark.parametrize("mode,name", [("1", "tiny_bf"), ("1", "tiny_none"), ("2", "tiny_fdr"), ("2", "tiny_4g"), ("2", "tiny_ap5")])
 def test_emulated_pass_per_launch_path_reproduces_the_reference_bytes(emu, tmp_path, mode, name):
     """The path of large batches: one launch per pass and gap size (phase1_pass_kernel), the four phase-2 stages
     (phase2_stage_kernel), the writer.  mode 1 = default join, 2 = the experimental two-phase join kernel."""

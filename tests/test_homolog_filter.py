@@ -104,7 +104,8 @@ def emu():
 @pytest.mark.parametrize("name,nt,env", [("tiny_bf", 32, {}), ("tiny_4g", 128, {}), ("tiny_none", 256, {}), ("tiny_fdr", 64, {}),
                                          ("tiny_pairs", 32, {}), ("tiny_pairs_fdr", 128, {}),
                                          ("tiny_4g", 128, {"EMU_RES": "1"}), ("tiny_none", 32, {"EMU_PASS": "2"}),
-                                         ("tiny_pairs", 32, {"EMU_PASS": "1"}), ("tiny_pairs_fdr", 64, {"EMU_RES": "1"})])
+                                         ("tiny_pairs", 32, {"EMU_PASS": "1"}), ("tiny_pairs_fdr", 64, {"EMU_RES": "1"}),
+                                         ("tiny_ap5", 256, {}), ("tiny_ap5", 64, {"EMU_RES": "1"})])   # (5 homologs per segment)
 def test_emulated_filter_kernels_reproduce_the_kept_bytes(emu, tmp_path, name, nt, env):
     trace = [p for p in TRACES if p.endswith(name + ".trace.gz")][0]
     inp = str(tmp_path / "in.bin")
