@@ -49,3 +49,10 @@ def level2_all_pairs(engine, device: torch.device) -> bytes:
 def profile_search(engine, profile, device: torch.device) -> bytes:
     r = engine.profile_search(profile, dist.get_rank(), dist.get_world_size())
     return merge_packed(all_gather_bytes(r.bytes, device))
+
+
+def profile_search_filtered(engine, profile, device: torch.device) -> bytes:
+    """The list-sharded search with the homolog-count filter applied by every rank to its own multiplicons (the filter
+    is local to a multiplicon: GHMProfile.cpp:129-132 runs inside each rank's work function in the reference too)."""
+    r = engine.profile_search_filtered(profile, dist.get_rank(), dist.get_world_size())
+    return merge_packed(all_gather_bytes(r.bytes, device))

@@ -35,6 +35,7 @@ def _worker(rank, world, port, path, q):
                 eng.mask_range(ev[1], ev[2], ev[3])
             elif ev[0] == "profile":
                 out.append(idist.profile_search(eng, ev[1], dev))
+                out.append(idist.profile_search_filtered(eng, ev[1], dev))   # + the homolog-count filter on every rank's share
                 n += 1
                 if n == 6:
                     break
@@ -74,10 +75,12 @@ def test_sharded_search_matches_single_rank(world):
             eng.mask_range(ev[1], ev[2], ev[3])
         elif ev[0] == "profile":
             single.append(eng.profile_search(ev[1]).bytes)
+            single.append(eng.profile_search_filtered(ev[1]).bytes)
             n += 1
             if n == 6:
                 break
     assert len(single) == len(res[0])
+    assert sum(len(capi.parse_packed(b)) for b in single[2::2]) < sum(len(capi.parse_packed(b)) for b in single[1::2])   # the filter dropped something
     for a, b in zip(res[0], single):
         ka = sorted(_key(m) for m in capi.parse_packed(a))
         kb = sorted(_key(m) for m in capi.parse_packed(b))
