@@ -101,7 +101,8 @@ def load_reference_profiles(ds: capi.Dataset, path: str, limit: int = -1, links_
         flg = np.where(gap, capi.F_GAP, e["o"] & 1).astype(np.uint8)
         out.append((masks, capi.Profile(S, L, xid, fam, gid, nid, flg)))
     if links_path:
-        lraw = gzip.open(links_path, "rb").read()
+        import lzma
+        lraw = (lzma.open if links_path.endswith(".xz") else gzip.open)(links_path, "rb").read()
         lo = 0
         for _, p in out:
             (nl,) = struct.unpack_from("<i", lraw, lo)

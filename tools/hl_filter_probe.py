@@ -28,7 +28,7 @@ def main():
     cfg = bench.workload_config(a.workload)
     ds = ingest.dataset_from_synth(cfg)
     path = bench.ref_profiles_path(a.workload)
-    bp = profiles.load_reference_profiles(ds, path, a.profiles, links_path=path.replace("bench_profiles_", "bench_profile_links_"))
+    bp = profiles.load_reference_profiles(ds, path, a.profiles, links_path=path.replace("bench_profiles_", "bench_profile_links_").replace(".bin.gz", ".bin.xz"))
     profs = [p for _, p in bp]
     masks = [m for m, _ in bp]
     n_links = sum(len(p.links) for p in profs)
