@@ -120,3 +120,52 @@ def oracle_engine(ds: capi.Dataset) -> capi.Engine:
 
 
 from iadhore_b200.profiles import simple_profile  # noqa: E402,F401
+
+
+def stream_digest(streams) -> dict:
+    """Known-answer digest of packed multiplicon streams (Multiplicon.cpp:210-264 layout): counts, total bytes, sha1 of the
+    bytes, sha1 of the bytes with every cluster's 8-byte random_probability zeroed (everything that must be bit-exact
+    under the north_star bar) and the sum of log p over all clusters (the one field with a tolerance)."""
+    import hashlib
+    import math
+    import struct
+    full, struct_h = hashlib.sha1(), hashlib.sha1()
+    n_mult = n_cl = n_bytes = 0
+    logs = []
+    for b in streams:
+        b = bytes(b)
+        full.update(b)
+        z = bytearray(b)
+        (n,) = struct.unpack_from("<i", b, 0)
+        o = 4
+        for _ in range(n):
+            (ncl,) = struct.unpack_from("<i", b, o + 29)
+            o += 33
+            for _ in range(ncl):
+                (pv,) = struct.unpack_from("<d", b, o)
+                logs.append(math.log(max(pv, 1e-300)))
+                z[o:o + 8] = b"\0" * 8
+                o += 102 + 17 * struct.unpack_from("<i", b, o + 98)[0]
+                n_cl += 1
+        assert o == len(b)
+        struct_h.update(bytes(z))
+        n_mult += n
+        n_bytes += len(b)
+    return dict(multiplicons=n_mult, clusters=n_cl, bytes=n_bytes, sha1=full.hexdigest(), struct_sha1=struct_h.hexdigest(),
+                p_log_sum=math.fsum(logs))   # (exactly rounded: no summation noise on top of the tolerance below)
+
+
+def digest_mismatch(got: dict, want: dict, rtol_p: float = P_RTOL) -> Optional[str]:
+    """None if `got` meets the parity bar against the known answer: the same bytes, or at least the same bytes outside
+    the p-values and a sum of log p that differs by no more than rtol_p per cluster (every p within rtol_p relative,
+    the north_star bar, moves its logarithm by at most rtol_p)."""
+    for k in ("multiplicons", "clusters", "bytes"):
+        if got[k] != want[k]:
+            return f"{k}: {got[k]} != {want[k]}"
+    if got["sha1"] == want["sha1"]:
+        return None
+    if got["struct_sha1"] != want["struct_sha1"]:
+        return "a field other than a p-value differs"
+    if abs(got["p_log_sum"] - want["p_log_sum"]) > rtol_p * want["clusters"] + 1e-9:
+        return f"p-values: sum of log p {got['p_log_sum']!r} vs {want['p_log_sum']!r}"
+    return None

@@ -136,6 +136,30 @@ def test_c4_profile_searches_match_oracle(c4):
     assert found > 0
 
 
+def test_c4_benched_profile_batch_matches_the_oracle_known_answers(c4):
+    """The profile batch bench.py times -- the reference's own first 32 aligned profiles of config 4 against all 500
+    lists in one iadh_profile_search_batch call -- against the oracle's digest of the same 32 searches
+    (tests/golden/bench_profiles_c4.kat.json, made on the CPU by tests/golden/make_bench_kat.py; the oracle needs
+    minutes for them, so the answers are committed instead of recomputed here).  Then the same batch through
+    iadh_profile_search_batch_filtered (homolog-count filter on the device, the Link sets of the 32 profiles)."""
+    import json
+    sys.path.insert(0, os.path.join(pl.REPO, "tests", "golden"))
+    import make_bench_kat
+    kat = json.load(open(os.path.join(pl.GOLDEN, "bench_profiles_c4.kat.json")))
+    ds, gpu = c4["ds"], c4["gpu"]
+    bp = make_bench_kat.load(ds)
+    assert len(bp) == kat["profiles"]
+    profs, masks = [p for _, p in bp], [m for m, _ in bp]
+    for kind in ("plain", "filtered"):
+        gpu.clear_masks()
+        res = gpu.profile_search_batch(profs, masks) if kind == "plain" else gpu.profile_search_batch_filtered(profs, masks)
+        msg = pl.digest_mismatch(pl.stream_digest([r.bytes for r in res]), kat[kind])
+        assert msg is None, (kind, msg)
+        assert sum(r.stats["n_ghm"] for r in res) == 32 * 500
+    gpu.clear_masks()
+    assert kat["filtered"]["multiplicons"] < kat["plain"]["multiplicons"]
+
+
 def test_c3_level2_and_20_profile_searches_match_oracle():
     cfg = synth.config_c3(1.0)
     ds, gpu, cpu = _engines(cfg)

@@ -70,3 +70,24 @@ def test_omxn_known_answers():
     out = eng.omxn(np.array([1e-4, 0.3]), np.array([1800, 7], np.int32))
     assert out[0].hex() == "0x1.aba78d4067e56p-1"
     assert out[1].hex() == "0x1.5152be12f5a5ep-4"
+
+
+def test_stream_digest_separates_p_values_from_the_rest():
+    """parity_lib.stream_digest / digest_mismatch (the known-answer form of the parity bar used at full bench size):
+    a last-bit change of a p-value is tolerated, any other byte is not."""
+    import struct
+    tr = read_trace(pl.golden_traces()[0])
+    streams = [ev[1].packed for ev in tr.events if ev[0] == "l2" and len(ev[1].packed) > 4][:5]
+    want = pl.stream_digest(streams)
+    assert want["multiplicons"] > 0 and want["clusters"] >= want["multiplicons"]
+    assert pl.digest_mismatch(pl.stream_digest(streams), want) is None
+    b = bytearray(streams[0])
+    o = 4 + 33                                   # first cluster of the first multiplicon: p-value at offset 0
+    (pv,) = struct.unpack_from("<d", b, o)
+    struct.pack_into("<d", b, o, np.nextafter(pv, 1.0))
+    assert pl.digest_mismatch(pl.stream_digest([bytes(b)] + streams[1:]), want) is None
+    struct.pack_into("<d", b, o, pv * (1 + 1e-6))
+    assert "p-values" in pl.digest_mismatch(pl.stream_digest([bytes(b)] + streams[1:]), want)
+    b = bytearray(streams[0])
+    b[4 + 33 + 9] ^= 1                           # a bit of the regression slope
+    assert "other than a p-value" in pl.digest_mismatch(pl.stream_digest([bytes(b)] + streams[1:]), want)

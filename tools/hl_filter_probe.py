@@ -52,6 +52,15 @@ def main():
                                   "multiplicons": sum(r.n_multiplicons for r in res), "bytes": sum(r._n for r in res),
                                   "ghms": sum(r.stats["n_ghm"] for r in res), "launches": sum(r.stats["kernel_launches"] for r in res),
                                   "h2d": sum(r.stats["h2d_bytes"] for r in res)})
+    # streams of the last repetition, for comparison with the oracle's (profiles/parity_r02.md)
+    import hashlib
+    for kind in ("plain", "filtered"):
+        eng.clear_masks()
+        res = eng.profile_search_batch(profs, masks) if kind == "plain" else eng.profile_search_batch_filtered(profs, masks)
+        h = hashlib.sha1()
+        for r in res:
+            h.update(r.bytes)
+        out[kind + "_sha1"] = h.hexdigest()
     eng.close()
     line = json.dumps(out)
     print(line)
