@@ -1,8 +1,9 @@
 """Known answers for the profile batch bench.py times on config 4: the reference's own first 32 aligned profiles
 (bench_profiles_c4.bin.gz, with the Link sets their searches inherit: bench_profile_links_c4.bin.xz) searched by the
 ORACLE against all 500 lists, without and with the homolog-count filter -> tests/golden/bench_profiles_c4.kat.json
-(digest of the 32 packed streams, parity_lib.stream_digest).  The GPU suite compares the device's batch with it
-(tests/test_gpu_bench_parity.py).  CPU only, about 3 minutes on 8 cores.
+(digest of the 32 packed streams, parity_lib.stream_digest), plus the digest of the whole level-2 call of a bench step
+(125,250 list pairs).  The GPU suite compares the device's batch with it
+(tests/test_gpu_bench_parity.py).  CPU only, about 10 minutes on 8 cores.
 
     python tests/golden/make_bench_kat.py
 """
@@ -40,6 +41,11 @@ def main():
         filtered.append(eng.profile_search_filtered(p).bytes)
         print(k, len(plain[-1]), len(filtered[-1]), flush=True)
     out = {"workload": "c4", "profiles": len(bp), "plain": pl.stream_digest(plain), "filtered": pl.stream_digest(filtered)}
+    # the level-2 call of a bench step: all 125,250 list pairs in the reference's pair order, one stream
+    eng.clear_masks()
+    l2 = eng.level2_all_pairs()
+    out["level2"] = pl.stream_digest([l2.bytes])
+    out["level2"]["ghms"] = int(l2.stats["n_ghm"])
     with open(os.path.join(HERE, "bench_profiles_c4.kat.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out))

@@ -7,6 +7,9 @@ calls under the oracle:
     of >= 3,000 GHMs (the 500 heaviest + 2,500 random ones) are cut out of its stream and compared
     with the oracle's bytes for the same list pairs; the same sample is also run as a call of its own
     on the fused path and with the throughput path forced (IADH_PASS_MIN=1 IADH_PASS_RATIO=0);
+  * the digest of the WHOLE config-4 level-2 stream and of the benched profile batch (the reference's own 32 profiles,
+    without and with the homolog-count filter) against known answers computed by the oracle on the CPU
+    (tests/golden/bench_profiles_c4.kat.json);
   * config 3: the full level-2 call against the oracle on a sample, then 20 profile searches with
     accumulating masks against the oracle;
   * 100 random small datasets with NON-default settings (tools/fuzz_parity.py as a test).
@@ -134,6 +137,18 @@ def test_c4_profile_searches_match_oracle(c4):
         found += a.n_multiplicons
     gpu.clear_masks()
     assert found > 0
+
+
+def test_c4_full_level2_stream_matches_the_oracle_known_answer(c4):
+    """The WHOLE level-2 call of a bench step (125,250 list pairs, one stream of ~320 MB) against the oracle's digest of
+    the same call (tests/golden/bench_profiles_c4.kat.json, "level2": made on the CPU by tests/golden/make_bench_kat.py --
+    minutes of oracle time, so the answer is committed): every multiplicon of the benched call, not a sample."""
+    import json
+    kat = json.load(open(os.path.join(pl.GOLDEN, "bench_profiles_c4.kat.json")))["level2"]
+    full = c4["full"]
+    assert full.stats["n_ghm"] == kat["ghms"] == 125250
+    msg = pl.digest_mismatch(pl.stream_digest([full.bytes]), kat)
+    assert msg is None, msg
 
 
 def test_c4_benched_profile_batch_matches_the_oracle_known_answers(c4):
