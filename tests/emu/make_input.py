@@ -136,6 +136,49 @@ def write_k2k3_synth_input(out_path, n_pairs=6):
     return len(order)
 
 
+def write_k2k3_workload_input(out_path, workload="d2", n_pairs=4):
+    """emu_k2k3 input from a bench workload (bench.workload_config): its n_pairs heaviest list pairs by dot count among
+    the pairs of the largest lists; dots and expected bytes from the oracle."""
+    repo = __file__.rsplit("/", 3)[0]
+    sys.path.insert(0, repo + "/i-adhore_b200/python")
+    sys.path.insert(0, repo)
+    import bench
+    import parity_lib as pl
+    from iadhore_b200 import capi, ingest
+    cfg = bench.workload_config(workload)
+    ds = ingest.dataset_from_synth(cfg)
+    eng = pl.oracle_engine(ds)
+    eng.set_params(cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff)
+    sizes = np.diff(ds.list_off).astype(np.int64)
+    xs, ys = capi.plan_pairs(sizes)
+    cand = np.argsort(-(sizes[xs] * sizes[ys]), kind="stable")[:60]
+    dots = eng.build_dots(xs[cand], ys[cand])
+    order = sorted(range(len(cand)), key=lambda i: -(len(dots[i][0]) + len(dots[i][1])))[:n_pairs]
+    gaps = capi.gap_sizes(cfg.gap_size)
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i10i", len(gaps), *(list(gaps) + [0] * (10 - len(gaps)))))
+        fh.write(struct.pack("<iiiidd", cfg.gap_size, cfg.cluster_gap, cfg.anchor_points, capi.MH_BONFERRONI, cfg.q_value, cfg.prob_cutoff))
+        fh.write(struct.pack("<i", ds.n_lists))
+        fh.write(np.ascontiguousarray(ds.list_off, "<i8").tobytes())
+        for a in (ds.fam, ds.gid, ds.num_id):
+            fh.write(np.ascontiguousarray(a, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.flags, "u1").tobytes())
+        fh.write(struct.pack("<i", 0))
+        fh.write(struct.pack("<i", len(order)))
+        for i in order:
+            x, y = int(xs[cand[i]]), int(ys[cand[i]])
+            d0, d1 = dots[i]
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            nx, ny = int(sizes[x]), int(sizes[y])
+            area = (nx * (nx - 1) // 2 if x == y else nx * ny) & 0xffffffff
+            expected = eng.level2_pairs([x], [y]).bytes
+            fh.write(struct.pack("<iiiiiQII", -1, x, y, x, 2, area, len(d0), len(d1)))
+            fh.write(keys.tobytes())
+            fh.write(struct.pack("<i", len(expected)))
+            fh.write(expected)
+    return [(int(xs[cand[i]]), int(ys[cand[i]]), len(dots[i][0]), len(dots[i][1])) for i in order]
+
+
 def write_synth_input(out_path, workload="c3", n_pairs=12):
     """Dot sets of the heaviest list pairs of a BASELINE-shaped synthetic set (dots from the oracle's build):
     GHMs with 100+ clusters per orientation, which the tiny golden traces do not have."""

@@ -109,6 +109,19 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
+@pytest.mark.parametrize("nt,env", [(32, {"EMU_PASS": "2"}), (128, {"EMU_RES": "1"})])
+def test_emulated_device_code_on_the_heaviest_d2_ghms(emu, tmp_path, nt, env):
+    """The four heaviest list pairs of the datasetII-shaped workload (lists of 4,000 ... 9,987 genes, up to 6,085 dots
+    per GHM: three times the heaviest GHM of config 3) on the pass-per-launch and the resident kernels; expected
+    bytes from the oracle.  (The fused 256-thread form passes too: 20 s, not in the suite.)"""
+    inp = str(tmp_path / "in.bin")
+    pairs = emu.write_k2k3_workload_input(inp, "d2", 4)
+    assert max(a + b for _, _, a, b in pairs) > 5000
+    res, err = _run(inp, env=env, exe=EMU_K2K3 % nt)
+    assert res["ghms"] == 4 and res["multiplicons"] > 50
+    assert res["mismatching_ghms"] == 0, err[-800:]
+
+
 @pytest.mark.parametrize("mode,name", [("1", "tiny_bf"), ("1", "tiny_none"), ("2", "tiny_fdr"), ("2", "tiny_4g"), ("2", "tiny_ap5")])
 def test_emulated_pass_per_launch_path_reproduces_the_reference_bytes(emu, tmp_path, mode, name):
     """The path of large batches: one launch per pass and gap size (phase1_pass_kernel), the four phase-2 stages

@@ -10,6 +10,7 @@ calls under the oracle:
   * the digest of the WHOLE config-4 level-2 stream and of the benched profile batch (the reference's own 32 profiles,
     without and with the homolog-count filter) against known answers computed by the oracle on the CPU
     (tests/golden/bench_profiles_c4.kat.json);
+  * the datasetII-shaped workload (d2): the whole level-2 call and 8 profile searches against the oracle;
   * config 3: the full level-2 call against the oracle on a sample, then 20 profile searches with
     accumulating masks against the oracle;
   * 100 random small datasets with NON-default settings (tools/fuzz_parity.py as a test).
@@ -195,6 +196,36 @@ def test_c3_level2_and_20_profile_searches_match_oracle():
         assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
         found += a.n_multiplicons
     assert found > 0
+    gpu.close()
+
+
+def test_d2_level2_and_profile_searches_match_oracle():
+    """The datasetII-shaped workload of the bench line (`--workload d2`: 420 ragged lists, 7 ... 9,987 genes, the shipped
+    list-length distribution with synthetic genes): the WHOLE level-2 call (88,410 list pairs, GHMs up to 6,000 dots)
+    byte for byte against the oracle, then 8 profile searches with accumulating masks one call at a time and the same 8
+    as one batch."""
+    import bench
+    cfg = bench.workload_config("d2")
+    ds, gpu, cpu = _engines(cfg)
+    full, want = gpu.level2_all_pairs(), cpu.level2_all_pairs()
+    assert full.stats["n_ghm"] == want.stats["n_ghm"] == 88410 and full.stats["n_dots"] == want.stats["n_dots"]
+    assert capi.compare_packed(full.bytes, want.bytes, pl.P_RTOL) is None
+    assert np.array_equal(full.ghm_index, want.ghm_index)
+    profs = bench.make_profiles(ds, want.bytes, 8)
+    masks = [[(m.x_object_id, m.bounds[0], m.bounds[1]), (m.y_object_id, m.bounds[2], m.bounds[3])] for m, _ in profs]
+    single, found = [], 0
+    for (m, p), mk in zip(profs, masks):
+        for e in (gpu, cpu):
+            for (l, b, e2) in mk:
+                e.mask_range(l, b, e2)
+        a, b = gpu.profile_search(p), cpu.profile_search(p)
+        assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
+        single.append(a.bytes)
+        found += a.n_multiplicons
+    assert found > 50
+    gpu.clear_masks()
+    for k, r in enumerate(gpu.profile_search_batch([p for _, p in profs], masks)):
+        assert r.bytes == single[k], k
     gpu.close()
 
 
