@@ -164,8 +164,9 @@ int iadh_clear_masks(iadh_ctx* ctx);
  * profile: lists big->small in the static partition of ParToolBox::statPartWorklSort
  * (parallel.cpp:96-156) for (rank, n_ranks); lists with fewer than anchor_points unmasked
  * elements are skipped (higherLevel.cpp:40-41).  Multiplicons are returned BEFORE the
- * homolog-count filter of GHMProfile.cpp:129-132 (it needs the parent's Link set, host
- * state); the shim re-applies it after unpacking. */
+ * homolog-count filter of GHMProfile.cpp:129-132, which needs the Link set of the profile's
+ * multiplicon: iadh_profile_search_filtered (below) takes that set and applies the filter on
+ * the device; with this entry point the caller applies it after unpacking. */
 int iadh_profile_search(iadh_ctx* ctx, const iadh_profile_desc* profile, int rank, int n_ranks,
                         iadh_result** out);
 
