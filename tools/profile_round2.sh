@@ -26,6 +26,10 @@ cap pass_g4 "phase1_" 42 3 python tools/trace_run.py --workload c4 --profiles 0 
 cap k1_expand "l2_expand|seg_sort" 5 5 python tools/trace_run.py --workload c4 --profiles 0 --reps 2
 cap k1_c5 "l2_build_kernel" 2 2 python tools/build_probe.py --workload c5 --reps 2
 cap hl_cluster "cluster_kernel|hl_expand" 0 4 python tools/hl_batch_probe.py --workload c4 --profiles 8 --reps 1 --no-seq
+# K4 (homolog-count filter): the probe first (plain vs filtered batch, sha1 of the streams), then the link-table kernels
+# and the filter kernel of the filtered batch (not captured in round 2: the GPU budget ended with the probe)
+python tools/hl_filter_probe.py --reps 3 --out $O/hl_filter_probe.json 2> $O/hl_filter_probe.err
+cap k4_filter "link_|homolog_filter" 0 5 python tools/hl_filter_probe.py --reps 0
 cuobjdump -sass i-adhore_b200/csrc/libiadhore_b200.so 2>/dev/null | grep -E "Function :|LDG\.E\.128|STG\.E\.128|ATOMG|RED\.|SHFL|LDGSTS|UTMA" | \
     awk '/Function :/ {f=$3} !/Function :/ {split($0,a," "); for(i in a) if (a[i] ~ /^(LDG|STG|ATOMG|RED|SHFL|LDGSTS|UTMA)/) c[f" "a[i]]++} END {for (k in c) print c[k], k}' | sort -k2,2 -k1,1nr > $O/sass_mnemonics.txt
 ls -la $O
