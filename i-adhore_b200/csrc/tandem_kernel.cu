@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(128) tandem_pass3_kernel(const int64_t* __rest
 
 }  // namespace
 
+#ifndef IADH_HOST_EMU   // (tests/emu compiles the kernels above for the host)
 void launch_tandem(const int64_t* list_off, int n_lists, const int32_t* elem_list, const int32_t* fam, const int32_t* gid,
                    const uint8_t* flags, int gap, int64_t total, uint8_t* remapped, int32_t* t3, cudaStream_t st)
 {
@@ -162,3 +163,4 @@ void launch_tandem_pairs(const int64_t* list_off, int n_lists, const int32_t* el
                                                                                 n_genes, gap, total, remapped, t3);
     tandem_pass3_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(list_off, n_lists, remapped, t3);
 }
+#endif  // IADH_HOST_EMU

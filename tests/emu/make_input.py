@@ -136,6 +136,29 @@ def write_k2k3_synth_input(out_path, n_pairs=6):
     return len(order)
 
 
+def write_tandem_input(trace_path, out_path):
+    """Input of tests/emu/emu_tandem: the gene lists of a trace BEFORE tandem remapping (every element: family, gene id,
+    strand) with the reference's own Gene::isRemapped() flags as the expected output; pairs traces add the pair sets."""
+    tr = read_trace(trace_path)
+    raw = tr.raw_lists
+    off = np.zeros(len(raw) + 1, np.int64)
+    off[1:] = np.cumsum([len(a) for a in raw])
+    cat = np.concatenate(raw)
+    pairs = hasattr(tr.dataset, "pair_ptr") and tr.dataset.pair_ptr is not None
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<iii", tr.params["tandem_gap"], 1 if pairs else 0, len(raw)))
+        fh.write(off.astype("<i8").tobytes())
+        fh.write(np.ascontiguousarray(cat["fam"], "<i4").tobytes())
+        fh.write(np.ascontiguousarray(cat["gid"], "<i4").tobytes())
+        fh.write(np.ascontiguousarray(cat["strand"], "u1").tobytes())
+        fh.write(np.ascontiguousarray(cat["remapped"], "u1").tobytes())
+        if pairs:
+            fh.write(struct.pack("<i", len(tr.dataset.pair_ptr) - 1))
+            fh.write(np.ascontiguousarray(tr.dataset.pair_ptr, "<i8").tobytes())
+            fh.write(np.ascontiguousarray(tr.dataset.pair_ids, "<i4").tobytes())
+    return int(off[-1]), int(cat["remapped"].sum())
+
+
 def write_k2k3_workload_input(out_path, workload="d2", n_pairs=4):
     """emu_k2k3 input from a bench workload (bench.workload_config): its n_pairs heaviest list pairs by dot count among
     the pairs of the largest lists; dots and expected bytes from the oracle."""

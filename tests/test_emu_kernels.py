@@ -109,6 +109,19 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
+@pytest.mark.parametrize("name", ["tiny_4g", "tiny_none", "tiny_ap5", "tiny_pairs", "tiny_pairs_fdr"])
+def test_emulated_tandem_kernels_reproduce_the_reference_flags(emu, tmp_path, name):
+    """tandem_kernel.cu (partners in parallel, passes 1-2 in closed form, pass 3 one thread per list; family mode and
+    table_type=pairs with Gene::isIndirectPairWith) on the gene lists of a trace before remapping: Gene::isRemapped()
+    of every gene as the unmodified reference left it."""
+    trace = [p for p in pl.golden_traces() if p.endswith(name + ".trace.gz")][0]
+    inp = str(tmp_path / "in.bin")
+    n, n_remapped = emu.write_tandem_input(trace, inp)
+    res, err = _run(inp, exe=os.path.join(pl.REPO, "build", "emu", "emu_tandem"))
+    assert res["elements"] == n and res["remapped"] == n_remapped > 50
+    assert res["mismatching"] == 0, err[-500:]
+
+
 @pytest.mark.parametrize("nt,env", [(32, {"EMU_PASS": "2"}), (128, {"EMU_RES": "1"})])
 def test_emulated_device_code_on_the_heaviest_d2_ghms(emu, tmp_path, nt, env):
     """The four heaviest list pairs of the datasetII-shaped workload (lists of 4,000 ... 9,987 genes, up to 6,085 dots
