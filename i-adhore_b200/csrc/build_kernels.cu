@@ -894,6 +894,7 @@ __global__ void mask_kernel(uint8_t* flags, int64_t begin, int64_t end, int set)
 // ---------------------------------------------------------------------------------------
 // host launchers
 
+#ifndef IADH_HOST_EMU   // (tests/emu compiles the kernels above for the host and launches them itself)
 static inline int grid_for(int64_t warps_needed, int sm_count)
 {
     int64_t blocks = (warps_needed + 7) / 8;
@@ -1022,3 +1023,4 @@ void launch_fam_list(const int32_t* fam_ptr, const int32_t* members, const int64
     if (n_fam == 0) return;
     fam_list_kernel<<<(n_fam + 127) / 128, 128, 0, st>>>(fam_ptr, members, list_off, n_fam, n_lists, total, table);
 }
+#endif  // IADH_HOST_EMU

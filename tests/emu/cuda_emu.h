@@ -30,7 +30,13 @@
 #endif
 
 namespace emu {
-constexpr int MAX_THREADS = 256, MAX_WARPS = MAX_THREADS / 32;
+#ifndef EMU_MAX_THREADS
+#define EMU_MAX_THREADS 256
+#endif
+#ifndef EMU_STACK_BYTES
+#define EMU_STACK_BYTES (1 << 20)
+#endif
+constexpr int MAX_THREADS = EMU_MAX_THREADS, MAX_WARPS = MAX_THREADS / 32;
 struct Idx { unsigned x, y, z; };
 struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = true; };
 extern Fiber fibers[MAX_THREADS];
@@ -38,7 +44,7 @@ extern ucontext_t sched_ctx;
 extern int cur, n_threads, n_done, n_done_warp[MAX_WARPS];
 extern int arrived_block, arrived_warp[MAX_WARPS];
 extern unsigned long long block_gen, warp_gen[MAX_WARPS];
-extern unsigned block_id;
+extern unsigned block_id, grid_dim;
 extern unsigned char xchg[2][MAX_THREADS][16];
 extern unsigned long long n_collectives;
 
@@ -99,12 +105,19 @@ inline T peek(unsigned long long gen, int lane)   // lane of the calling thread'
 inline bool lane_done(int lane) { return fibers[(cur & ~31) + lane].done; }
 inline unsigned long long wgen() { return warp_gen[cur >> 5]; }
 void run_block(unsigned block, int threads, const std::function<void()>& body);
+// a whole grid, block after block (kernels that do not wait for another block: all of K1)
+inline void launch(unsigned grid, int threads, const std::function<void()>& body)
+{
+    grid_dim = grid;
+    for (unsigned b = 0; b < grid; b++) run_block(b, threads, body);
+    grid_dim = 1;
+}
 }  // namespace emu
 
 #define threadIdx (emu::Idx{(unsigned)emu::cur, 0u, 0u})
 #define blockIdx (emu::Idx{emu::block_id, 0u, 0u})
 #define blockDim (emu::Idx{(unsigned)emu::n_threads, 1u, 1u})
-#define gridDim (emu::Idx{1u, 1u, 1u})
+#define gridDim (emu::Idx{emu::grid_dim, 1u, 1u})
 
 inline void __syncthreads() { emu::barrier_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_warp(); }
@@ -143,6 +156,16 @@ inline int __reduce_min_sync(unsigned, int v)
     int r = v;
     for (int l = 0; l < 32; l++)
         if (!emu::lane_done(l)) r = std::min(r, emu::peek<int>(gen, l));
+    return r;
+}
+inline int __reduce_max_sync(unsigned, int v)
+{
+    const unsigned long long gen = emu::wgen();
+    emu::publish<int>(v);
+    emu::barrier_warp();
+    int r = v;
+    for (int l = 0; l < 32; l++)
+        if (!emu::lane_done(l)) r = std::max(r, emu::peek<int>(gen, l));
     return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -136,6 +136,92 @@ def write_k2k3_synth_input(out_path, n_pairs=6):
     return len(order)
 
 
+def write_k1_input(trace_path, out_path):
+    """Input of tests/emu/emu_k1: the flat dataset of a (family-mode) trace and, per level-2 GHM, the dot sets the
+    reference's buildMatrix produced, as packed keys."""
+    tr = read_trace(trace_path)
+    ds = tr.dataset
+    l2 = [ev[1] for ev in tr.events if ev[0] == "l2"]
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i", ds.n_lists))
+        fh.write(np.ascontiguousarray(ds.list_off, "<i8").tobytes())
+        fh.write(np.ascontiguousarray(ds.fam, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.gid, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.flags & 1, "u1").tobytes())
+        fh.write(struct.pack("<i", len(l2)))
+        for g in l2:
+            d0, d1 = g.dots
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            fh.write(struct.pack("<iiII", g.x_list, g.y_list, len(d0), len(d1)))
+            fh.write(keys.tobytes())
+    return len(l2), sum(len(g.dots[0]) + len(g.dots[1]) for g in l2)
+
+
+def write_k1_workload_input(out_path, workload="d2", n_pairs=40, cfg=None):
+    """emu_k1 input from a bench workload (or a given config): the list pairs with the most dots among the pairs of the
+    largest lists; expected dots from the oracle's build (pinned on the reference's dot sets by the golden traces)."""
+    repo = __file__.rsplit("/", 3)[0]
+    sys.path.insert(0, repo + "/i-adhore_b200/python")
+    sys.path.insert(0, repo)
+    import bench
+    import parity_lib as pl
+    from iadhore_b200 import capi, ingest
+    cfg = cfg or bench.workload_config(workload)
+    ds = ingest.dataset_from_synth(cfg)
+    eng = pl.oracle_engine(ds)
+    sizes = np.diff(ds.list_off).astype(np.int64)
+    xs, ys = capi.plan_pairs(sizes)
+    cand = np.argsort(-(sizes[xs] * sizes[ys]), kind="stable")[:max(60, n_pairs)]
+    dots = eng.build_dots(xs[cand], ys[cand])
+    order = sorted(range(len(cand)), key=lambda i: -(len(dots[i][0]) + len(dots[i][1])))[:n_pairs]
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i", ds.n_lists))
+        fh.write(np.ascontiguousarray(ds.list_off, "<i8").tobytes())
+        fh.write(np.ascontiguousarray(ds.fam, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.gid, "<i4").tobytes())
+        fh.write(np.ascontiguousarray(ds.flags & 1, "u1").tobytes())
+        fh.write(struct.pack("<i", len(order)))
+        for i in order:
+            d0, d1 = dots[i]
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            fh.write(struct.pack("<iiII", int(xs[cand[i]]), int(ys[cand[i]]), len(d0), len(d1)))
+            fh.write(keys.tobytes())
+    return [(len(dots[i][0]), len(dots[i][1])) for i in order]
+
+
+def write_k1_giant_input(out_path):
+    """emu_k1 input with family sizes that take every path of the bucket sort of the join tables -- 1 ... 32 members (one
+    register per lane), hundreds (8 / 32 registers), 3,000 (shared memory), 10,000 (global-memory network) -- the
+    dataset of tests/test_gpu_parity.py::test_join_tables_with_giant_families; expected dots from the oracle."""
+    repo = __file__.rsplit("/", 3)[0]
+    sys.path.insert(0, repo + "/i-adhore_b200/python")
+    import parity_lib as pl
+    from iadhore_b200 import capi
+    rng = np.random.RandomState(17)
+    sizes = [3000, 10000] + [700, 300, 150, 40] * 3 + list(rng.randint(1, 33, 400))
+    fam = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
+    rng.shuffle(fam)
+    n, n_lists = len(fam), 12
+    off = np.linspace(0, n, n_lists + 1).astype(np.int64)
+    gid = np.arange(n, dtype=np.int32)
+    flags = rng.randint(0, 2, n).astype(np.uint8)
+    cpu = pl.oracle_engine(capi.Dataset(off, fam, gid, np.arange(n, dtype=np.int32) + 7, flags))
+    xs, ys = [0, 3, 11], [0, 4, 1]
+    dots = cpu.build_dots(xs, ys)
+    with open(out_path, "wb") as fh:
+        fh.write(struct.pack("<i", n_lists))
+        fh.write(off.astype("<i8").tobytes())
+        fh.write(fam.astype("<i4").tobytes())
+        fh.write(gid.astype("<i4").tobytes())
+        fh.write((flags & 1).astype("u1").tobytes())
+        fh.write(struct.pack("<i", len(xs)))
+        for x, y, (d0, d1) in zip(xs, ys, dots):
+            keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+            fh.write(struct.pack("<iiII", x, y, len(d0), len(d1)))
+            fh.write(keys.tobytes())
+    return sum(len(a) + len(b) for a, b in dots)
+
+
 def write_tandem_input(trace_path, out_path):
     """Input of tests/emu/emu_tandem: the gene lists of a trace BEFORE tandem remapping (every element: family, gene id,
     strand) with the reference's own Gene::isRemapped() flags as the expected output; pairs traces add the pair sets."""

@@ -109,6 +109,46 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
+EMU_K1 = os.path.join(pl.REPO, "build", "emu", "emu_k1")
+
+
+@pytest.mark.parametrize("name", ["tiny_bf", "tiny_4g", "tiny_ap5"])
+def test_emulated_build_kernels_reproduce_the_reference_dots(emu, tmp_path, name):
+    """K0 / K1 (build_kernels.cu) on the CPU: the join tables of iadh_create built by the table kernels (histograms,
+    1,024-thread scans, scatter, bucket sorts, member records, strand prefix, (family, list) table) equal a plain host
+    construction, and on them both level-2 build paths -- tile kernels (count, tile scan, fill) and family expansion
+    (count, fill through atomic cursors, block sorts) -- give the dot sets of the unmodified reference's buildMatrix
+    for every list pair of the trace."""
+    trace = [p for p in pl.golden_traces("family") if p.endswith(name + ".trace.gz")][0]
+    inp = str(tmp_path / "in.bin")
+    n, dots = emu.write_k1_input(trace, inp)
+    res, err = _run(inp, exe=EMU_K1)
+    assert res["ghms"] == n > 20 and res["dots"] == dots > 2000
+    assert res["table_mismatches"] == 0 and res["tile_mismatching_ghms"] == 0 and res["expansion_mismatching_ghms"] == 0, err[-800:]
+    assert res["expansion_fill_skipped"] == 0
+
+
+@pytest.mark.parametrize("shape", ["d2", "c5", "giant"])
+def test_emulated_build_kernels_on_heavy_dense_and_giant_family_inputs(emu, tmp_path, shape):
+    """The same on what the tiny traces do not have (expected dots from the oracle): the 40 heaviest list pairs of the
+    datasetII-shaped workload (blocks of up to 3,450 keys: the shared-memory block sort), a dense config-5-shaped set
+    (137-member families, 14,000 dots per pair: wide column groups in the tile fill) and families of 3,000 and 10,000
+    members (shared-memory and global-memory bucket sorts of the tables; 1.9 M dots through the tile kernels -- the
+    expansion path hands such blocks to the tile kernels, only its counts are compared)."""
+    inp = str(tmp_path / "in.bin")
+    if shape == "d2":
+        emu.write_k1_workload_input(inp, "d2", 40)
+    elif shape == "c5":
+        from iadhore_b200 import synth
+        emu.write_k1_workload_input(inp, "c5", 12, cfg=synth.config_c5(0.05))
+    else:
+        assert emu.write_k1_giant_input(inp) > 10 ** 6
+    res, err = _run(inp, exe=EMU_K1)
+    assert res["dots"] > 60000
+    assert res["table_mismatches"] == 0 and res["tile_mismatching_ghms"] == 0 and res["expansion_mismatching_ghms"] == 0, err[-800:]
+    assert res["expansion_fill_skipped"] == (1 if shape == "giant" else 0)
+
+
 @pytest.mark.parametrize("name", ["tiny_4g", "tiny_none", "tiny_ap5", "tiny_pairs", "tiny_pairs_fdr"])
 def test_emulated_tandem_kernels_reproduce_the_reference_flags(emu, tmp_path, name):
     """tandem_kernel.cu (partners in parallel, passes 1-2 in closed form, pass 3 one thread per list; family mode and
