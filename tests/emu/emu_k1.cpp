@@ -10,6 +10,9 @@
 //
 // input (little endian): i32 n_lists; i64 list_off[n_lists+1]; i32 fam[T], gid[T]; u8 flags[T] (bit 0 strand);
 //   i32 n_ghm; per GHM: i32 x_list, y_list; u32 cnt0, cnt1; u32 keys[cnt0 + cnt1]  ((x << 16) | y, orientation 0 block first)
+//   optional: i32 n_profiles; per profile: i32 n_masks, n_masks x (i32 list, begin, end) applied before it; i32 S, L;
+//     i32 fam[S*L], gid[S*L]; u8 flags[S*L] (bit 0 strand, bit 1 gap); i32 n_ghm; per GHM: i32 y_list; u32 cnt0, cnt1; keys
+//   3. (that section) the profile x list dot sets through build_kernel<HL> (tiles) and hl_expand_kernel (+ block sorts)
 #define IADH_HOST_EMU 1
 #define EMU_MAX_THREADS 1024
 #define EMU_STACK_BYTES (256 << 10)
@@ -161,7 +164,6 @@ int main(int argc, char** argv)
         want_cnt[2 * i + 1] = c[1];
         tasks[i].seq = i;
     }
-    fclose(f);
     long long dots = 0;
     auto compare = [&](const char* path, const std::vector<GhmTask>& tk, const std::vector<uint32_t>& keys) {
         long long bad = 0;
@@ -235,8 +237,128 @@ int main(int argc, char** argv)
         expand_bad = compare("expansion", tk, keys);
         }
     }
+    // ---- 3. the profile GHMs of the trace (optional section): GHMProfile::buildMatrix (GHMProfile.cpp:17-59) -------
+    // per profile: the masks applied before its search (GeneList::mask, higherLevel.cpp:165-171), the aligned segments,
+    // the lists searched with the reference's dots.  Column groups as profile_groups() of engine.cu builds them.
+    long long hl_ghms = 0, hl_dots = 0, hl_tile_bad = 0, hl_expand_bad = 0;
+    int n_prof = 0;
+    if (rd(f, &n_prof, 1)) {
+        for (int pi = 0; pi < n_prof; pi++) {
+            int nm = 0, S = 0, L = 0, ng = 0;
+            if (!rd(f, &nm, 1)) return 2;
+            for (int k = 0; k < nm; k++) {
+                int m[3];
+                if (!rd(f, m, 3)) return 2;
+                for (int64_t i = list_off[m[0]] + m[1]; i <= list_off[m[0]] + m[2]; i++) dflags[i] |= 4;
+            }
+            if (!rd(f, &S, 1) || !rd(f, &L, 1)) return 2;
+            const size_t SL = (size_t)S * L;
+            std::vector<int32_t> pfam(SL), pgid(SL);
+            std::vector<uint8_t> pflags(SL);
+            if (!rd(f, pfam.data(), SL) || !rd(f, pgid.data(), SL) || !rd(f, pflags.data(), SL) || !rd(f, &ng, 1)) return 2;
+            std::vector<int32_t> col_ptr(L + 1, 0), gfam, ggid;
+            std::vector<uint8_t> gstrand;
+            std::vector<HlGroup> items;
+            for (int x = 0; x < L; x++) {
+                const size_t g0 = gfam.size();
+                for (int sg = 0; sg < S; sg++) {
+                    const size_t k = (size_t)sg * L + x;
+                    if (pflags[k] & 2) continue;
+                    const int fm = pfam[k];
+                    const uint8_t st = pflags[k] & 1;
+                    if (fm < 0 || fm >= n_fam) continue;
+                    size_t g = g0;
+                    for (; g < gfam.size(); g++)
+                        if (gfam[g] == fm && gstrand[g] == st) break;
+                    if (g == gfam.size()) {
+                        gfam.push_back(fm);
+                        ggid.push_back(pgid[k]);
+                        gstrand.push_back(st);
+                    } else if (ggid[g] != pgid[k])
+                        ggid[g] = -1;
+                }
+                col_ptr[x + 1] = (int32_t)gfam.size();
+                for (size_t g = g0; g < gfam.size(); g++) {
+                    HlGroup it;
+                    it.fam = gfam[g];
+                    it.gid = ggid[g];
+                    it.x_strand = (uint32_t)x | (gstrand[g] ? 0x80000000u : 0u);
+                    it.prof = 0;
+                    items.push_back(it);
+                }
+            }
+            ProfileDev pf;
+            memset(&pf, 0, sizeof pf);
+            pf.S = S; pf.L = L;
+            pf.col_ptr = col_ptr.data(); pf.grp_fam = gfam.data(); pf.grp_gid = ggid.data(); pf.grp_strand = gstrand.data();
+            pf.fam = pfam.data(); pf.gid = pgid.data(); pf.num_id = pgid.data(); pf.flags = pflags.data();
+            std::vector<GhmTask> ht(ng);
+            std::vector<std::vector<uint32_t>> hw(ng);
+            std::vector<uint32_t> hwc(2 * (size_t)ng);
+            std::vector<int32_t> task_idx(n_lists, -1);
+            for (int i = 0; i < ng; i++) {
+                memset(&ht[i], 0, sizeof(GhmTask));
+                uint32_t c[2];
+                ht[i].x_list = -1;
+                if (!rd(f, &ht[i].y_list, 1) || !rd(f, c, 2)) return 2;
+                hw[i].resize(c[0] + c[1]);
+                if (!rd(f, hw[i].data(), hw[i].size())) return 2;
+                hwc[2 * i] = c[0]; hwc[2 * i + 1] = c[1];
+                task_idx[ht[i].y_list] = i;
+                hl_dots += c[0] + c[1];
+            }
+            hl_ghms += ng;
+            auto cmp = [&](const std::vector<GhmTask>& tk, const std::vector<uint32_t>& keys) {
+                long long bad = 0;
+                for (int i = 0; i < ng; i++) {
+                    bool ok = tk[i].cnt[0] == hwc[2 * i] && tk[i].cnt[1] == hwc[2 * i + 1];
+                    if (ok) ok = std::equal(hw[i].begin(), hw[i].end(), keys.begin() + tk[i].dot_off);
+                    bad += !ok;
+                }
+                return bad;
+            };
+            {   // tile path (build_kernel<HL>)
+                std::vector<GhmTask> tk(ht);
+                std::vector<int64_t> tile_prefix(ng + 1, 0);
+                for (int i = 0; i < ng; i++) tile_prefix[i + 1] = tile_prefix[i] + (L + 31) / 32;
+                const int64_t n_tiles = tile_prefix[ng];
+                std::vector<uint32_t> tile_cnt(2 * (size_t)n_tiles + 2, 0), tile_off(2 * (size_t)n_tiles + 2, 0);
+                if (n_tiles) emu::launch(GRID, 256, [&]() { build_kernel<true, false>(ds, pf, tk.data(), ng, tile_prefix.data(), n_tiles, tile_cnt.data(), nullptr, nullptr); });
+                if (ng) emu::launch((ng + 7) / 8, 256, [&]() { tile_scan_kernel(tile_prefix.data(), ng, tile_cnt.data(), tile_off.data()); });
+                int64_t total = 0;
+                for (int i = 0; i < ng; i++) {
+                    tk[i].dot_off = total;
+                    total += (int64_t)tk[i].cnt[0] + tk[i].cnt[1];
+                }
+                std::vector<uint32_t> keys((size_t)total + 1, 0xdeadbeefu);
+                if (n_tiles) emu::launch(GRID, 256, [&]() { build_kernel<true, true>(ds, pf, tk.data(), ng, tile_prefix.data(), n_tiles, nullptr, tile_off.data(), keys.data()); });
+                hl_tile_bad += cmp(tk, keys);
+            }
+            {   // family-expansion path (hl_expand_kernel + block sorts)
+                std::vector<GhmTask> tk(ht);
+                const int n_items = (int)items.size();
+                std::vector<uint32_t> cnt(2 * (size_t)ng + 2, 0), cur2(2 * (size_t)ng + 2, 0);
+                if (n_items) emu::launch(GRID, 256, [&]() { hl_expand_kernel<false>(ds, items.data(), n_items, task_idx.data(), nullptr, cnt.data(), nullptr, nullptr, nullptr); });
+                std::vector<int64_t> dot_off(ng + 1, 0);
+                for (int i = 0; i < ng; i++) dot_off[i + 1] = dot_off[i] + cnt[2 * i] + cnt[2 * i + 1];
+                for (int i = 0; i < ng; i++) tk[i].dot_off = dot_off[i];
+                std::vector<uint32_t> keys((size_t)dot_off[ng] + 1, 0xdeadbeefu);
+                if (ng) emu::launch((ng + 255) / 256, 256, [&]() { scatter_cnt_kernel(tk.data(), ng, cnt.data()); });
+                if (n_items) emu::launch(GRID, 256, [&]() { hl_expand_kernel<true>(ds, items.data(), n_items, task_idx.data(), nullptr, cur2.data(), dot_off.data(), cnt.data(), keys.data()); });
+                const int n_seg = 2 * ng;
+                if (ng) {
+                    emu::launch(GRID, 256, [&]() { seg_sort_warp_kernel<8>(n_seg, dot_off.data(), cnt.data(), keys.data()); });
+                    emu::launch(GRID, 256, [&]() { seg_sort_warp_kernel<32>(n_seg, dot_off.data(), cnt.data(), keys.data()); });
+                    emu::launch(GRID, 256, [&]() { seg_sort_cta_kernel(n_seg, dot_off.data(), cnt.data(), keys.data()); });
+                }
+                hl_expand_bad += cmp(tk, keys);
+            }
+        }
+    }
+    fclose(f);
     printf("{\"elements\": %lld, \"families\": %d, \"ghms\": %d, \"dots\": %lld, \"table_mismatches\": %lld, \"tile_mismatching_ghms\": %lld, "
-           "\"expansion_mismatching_ghms\": %lld, \"expansion_fill_skipped\": %d}\n",
-           (long long)T, n_fam, n, dots, table_bad, tile_bad, expand_bad, expand_skipped);
-    return (table_bad || tile_bad || expand_bad) ? 1 : 0;
+           "\"expansion_mismatching_ghms\": %lld, \"expansion_fill_skipped\": %d, \"profiles\": %d, \"profile_ghms\": %lld, \"profile_dots\": %lld, "
+           "\"profile_tile_mismatching_ghms\": %lld, \"profile_expansion_mismatching_ghms\": %lld}\n",
+           (long long)T, n_fam, n, dots, table_bad, tile_bad, expand_bad, expand_skipped, n_prof, hl_ghms, hl_dots, hl_tile_bad, hl_expand_bad);
+    return (table_bad || tile_bad || expand_bad || hl_tile_bad || hl_expand_bad) ? 1 : 0;
 }

@@ -154,6 +154,24 @@ def write_k1_input(trace_path, out_path):
             keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
             fh.write(struct.pack("<iiII", g.x_list, g.y_list, len(d0), len(d1)))
             fh.write(keys.tobytes())
+        # the profile searches: masks applied before each, the aligned profile, its GHMs with the reference's dots
+        import parity_lib as pl
+        searches = pl.trace_searches(tr)
+        fh.write(struct.pack("<i", len(searches)))
+        for masks, pr, ghms in searches:
+            fh.write(struct.pack("<i", len(masks)))
+            for m in masks:
+                fh.write(struct.pack("<iii", *m))
+            fh.write(struct.pack("<ii", pr.S, pr.L))
+            fh.write(np.ascontiguousarray(pr.fam, "<i4").tobytes())
+            fh.write(np.ascontiguousarray(pr.gid, "<i4").tobytes())
+            fh.write(np.ascontiguousarray(pr.flags, "u1").tobytes())
+            fh.write(struct.pack("<i", len(ghms)))
+            for g in ghms:
+                d0, d1 = g.dots
+                keys = np.concatenate([(d[:, 0].astype(np.uint32) << 16) | d[:, 1].astype(np.uint32) for d in (d0, d1)]).astype("<u4")
+                fh.write(struct.pack("<iII", g.y_list, len(d0), len(d1)))
+                fh.write(keys.tobytes())
     return len(l2), sum(len(g.dots[0]) + len(g.dots[1]) for g in l2)
 
 

@@ -118,7 +118,7 @@ def test_emulated_build_kernels_reproduce_the_reference_dots(emu, tmp_path, name
     1,024-thread scans, scatter, bucket sorts, member records, strand prefix, (family, list) table) equal a plain host
     construction, and on them both level-2 build paths -- tile kernels (count, tile scan, fill) and family expansion
     (count, fill through atomic cursors, block sorts) -- give the dot sets of the unmodified reference's buildMatrix
-    for every list pair of the trace."""
+    for every list pair of the trace; then every profile search of the trace the same way."""
     trace = [p for p in pl.golden_traces("family") if p.endswith(name + ".trace.gz")][0]
     inp = str(tmp_path / "in.bin")
     n, dots = emu.write_k1_input(trace, inp)
@@ -126,6 +126,12 @@ def test_emulated_build_kernels_reproduce_the_reference_dots(emu, tmp_path, name
     assert res["ghms"] == n > 20 and res["dots"] == dots > 2000
     assert res["table_mismatches"] == 0 and res["tile_mismatching_ghms"] == 0 and res["expansion_mismatching_ghms"] == 0, err[-800:]
     assert res["expansion_fill_skipped"] == 0
+    # ... and the profile x list dot sets (GHMProfile::buildMatrix, masks applied search by search) through
+    # build_kernel<HL> and through hl_expand_kernel + block sorts
+    tr = read_trace(trace)
+    hl = [e[1] for e in tr.events if e[0] == "hl"]
+    assert res["profile_ghms"] == len(hl) > 50 and res["profile_dots"] == sum(len(g.dots[0]) + len(g.dots[1]) for g in hl)
+    assert res["profile_tile_mismatching_ghms"] == 0 and res["profile_expansion_mismatching_ghms"] == 0, err[-800:]
 
 
 @pytest.mark.parametrize("shape", ["d2", "c5", "giant"])
