@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256) intern_ids_kernel(const int32_t* __restri
 
 }  // namespace
 
+#ifndef IADH_HOST_EMU   // (tests/emu compiles the kernels above for the host)
 // device pointers throughout; table = table_size int32 (-1), cmin = n int32 (INT_MAX); both initialised by the caller
 void launch_intern(const char* blob, const int64_t* off, int64_t n, int32_t* table, uint32_t table_size, int32_t* rep, int32_t* cmin,
                    int32_t* flag_scan, int32_t* block_sum, int32_t* total, int32_t* ids, cudaStream_t st)
@@ -149,3 +150,4 @@ void launch_intern(const char* blob, const int64_t* off, int64_t n, int32_t* tab
     intern_block_scan_kernel<<<1, 1024, 0, st>>>(block_sum, (int)g1024, total);
     intern_ids_kernel<<<g256, 256, 0, st>>>(rep, cmin, flag_scan, block_sum, n, ids);
 }
+#endif  // IADH_HOST_EMU

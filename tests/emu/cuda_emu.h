@@ -176,6 +176,7 @@ inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 // lanes interleave only at collectives, so a plain read-modify-write is atomic here
 template <typename T, typename U> inline T atomicAdd(T* p, U v) { const T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T, typename U> inline T atomicMin(T* p, U v) { const T old = *p; if ((T)v < old) *p = (T)v; return old; }
 template <typename T, typename U> inline T atomicMax(T* p, U v) { const T old = *p; if ((T)v > old) *p = (T)v; return old; }
 template <typename T, typename U, typename V> inline T atomicCAS(T* p, U cmp, V v) { const T old = *p; if (old == (T)cmp) *p = (T)v; return old; }
 template <typename T, typename U> inline T atomicOr(T* p, U v) { const T old = *p; *p = (T)(old | (T)v); return old; }

@@ -109,6 +109,32 @@ def test_emulated_device_code_on_heavy_ghms_matches_the_oracle_bytes(emu, tmp_pa
     assert res["mismatching_ghms"] == 0, err[-800:]
 
 
+def test_emulated_interning_kernels_number_strings_by_first_occurrence(emu, tmp_path):
+    """intern_kernel.cu (hash table of representatives, class minima, flag scan with 1,024-thread blocks, ids) in the
+    order of launch_intern: equal strings, equal ids; ids count the distinct strings in order of first occurrence
+    (the promise of iadh_intern_strings) -- checked inside the harness against a std::unordered_map.  Family-like
+    names with many repeats, gene-like names, empty strings, strings of hundreds of bytes; and the empty input."""
+    import random
+    import struct
+    rng = random.Random(5)
+    names = []
+    for i in range(30000):
+        r = rng.random()
+        names.append("fam%d" % rng.randint(0, 3000) if r < 0.5 else "AT%dG%05d" % (rng.randint(1, 5), rng.randint(0, 99999)) if r < 0.8
+                     else "" if r < 0.82 else "x" * rng.randint(100, 400) if r < 0.85 else "g%d" % i)
+    for case in (names, []):
+        enc = [s.encode() for s in case]
+        off = [0]
+        for b in enc:
+            off.append(off[-1] + len(b))
+        inp = str(tmp_path / "in.bin")
+        with open(inp, "wb") as fh:
+            fh.write(struct.pack("<q", len(enc)) + struct.pack("<%dq" % len(off), *off) + b"".join(enc))
+        res, err = _run(inp, exe=os.path.join(pl.REPO, "build", "emu", "emu_intern"))
+        assert res["strings"] == len(case) and res["distinct"] == len(set(case))
+        assert res["mismatching"] == 0, err[-500:]
+
+
 EMU_K1 = os.path.join(pl.REPO, "build", "emu", "emu_k1")
 
 
