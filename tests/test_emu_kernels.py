@@ -1,5 +1,8 @@
-"""The kernels of cluster_kernel.cu and pack_kernel.cu compiled for the host and run under a one-warp emulation
-(tests/emu/: the threads of a block as fibers, every warp collective and barrier a rendezvous), in a container without a GPU.
+"""The kernel files of the library compiled for the host and run under a thread-block emulation (tests/emu/: the threads
+of a block as fibers, every warp collective and barrier a rendezvous, grids block after block), in a container without a
+GPU.  cluster_kernel.cu + pack_kernel.cu (items 0-2 below; homolog_kernel.cu: tests/test_homolog_filter.py), and at
+the end of this file build_kernels.cu (join tables, level-2 and profile dot sets through both build paths),
+tandem_kernel.cu (the reference's remapped flags) and intern_kernel.cu (first-occurrence ids).
 
 0. End to end: the fused clustering kernel (phase 1, phase 2, K3 measuring pass; 32-, 64-, 128- and 256-thread
    instantiations, i.e. also the cooperative merge / insert / statistics paths and the cross-warp reductions) and
