@@ -3,7 +3,7 @@
 ORACLE against all 500 lists, without and with the homolog-count filter -> tests/golden/bench_profiles_c4.kat.json
 (digest of the 32 packed streams, parity_lib.stream_digest), plus the digest of the whole level-2 call of a bench step
 (125,250 list pairs).  The GPU suite compares the device's batch with it
-(tests/test_gpu_bench_parity.py).  CPU only, about 10 minutes on 8 cores.
+(tests/test_gpu_bench_parity.py, tests/test_workloads_full_size.py).  CPU only, about 10 minutes on 8 cores.
 
     python tests/golden/make_bench_kat.py
 """

@@ -7,10 +7,9 @@ calls under the oracle:
     of >= 3,000 GHMs (the 500 heaviest + 2,500 random ones) are cut out of its stream and compared
     with the oracle's bytes for the same list pairs; the same sample is also run as a call of its own
     on the fused path and with the throughput path forced (IADH_PASS_MIN=1 IADH_PASS_RATIO=0);
-  * the digest of the WHOLE config-4 level-2 stream and of the benched profile batch (the reference's own 32 profiles,
-    without and with the homolog-count filter) against known answers computed by the oracle on the CPU
-    (tests/golden/bench_profiles_c4.kat.json);
-  * the datasetII-shaped workload (d2): the whole level-2 call and 8 profile searches against the oracle;
+  * the digest of the WHOLE config-4 level-2 stream against the known answer computed by the oracle on the CPU
+    (tests/golden/bench_profiles_c4.kat.json; the benched profile batch and the datasetII-shaped workload follow in
+    tests/test_workloads_full_size.py);
   * config 3: the full level-2 call against the oracle on a sample, then 20 profile searches with
     accumulating masks against the oracle;
   * 100 random small datasets with NON-default settings (tools/fuzz_parity.py as a test).
@@ -152,30 +151,6 @@ def test_c4_full_level2_stream_matches_the_oracle_known_answer(c4):
     assert msg is None, msg
 
 
-def test_c4_benched_profile_batch_matches_the_oracle_known_answers(c4):
-    """The profile batch bench.py times -- the reference's own first 32 aligned profiles of config 4 against all 500
-    lists in one iadh_profile_search_batch call -- against the oracle's digest of the same 32 searches
-    (tests/golden/bench_profiles_c4.kat.json, made on the CPU by tests/golden/make_bench_kat.py; the oracle needs
-    minutes for them, so the answers are committed instead of recomputed here).  Then the same batch through
-    iadh_profile_search_batch_filtered (homolog-count filter on the device, the Link sets of the 32 profiles)."""
-    import json
-    sys.path.insert(0, os.path.join(pl.REPO, "tests", "golden"))
-    import make_bench_kat
-    kat = json.load(open(os.path.join(pl.GOLDEN, "bench_profiles_c4.kat.json")))
-    ds, gpu = c4["ds"], c4["gpu"]
-    bp = make_bench_kat.load(ds)
-    assert len(bp) == kat["profiles"]
-    profs, masks = [p for _, p in bp], [m for m, _ in bp]
-    for kind in ("plain", "filtered"):
-        gpu.clear_masks()
-        res = gpu.profile_search_batch(profs, masks) if kind == "plain" else gpu.profile_search_batch_filtered(profs, masks)
-        msg = pl.digest_mismatch(pl.stream_digest([r.bytes for r in res]), kat[kind])
-        assert msg is None, (kind, msg)
-        assert sum(r.stats["n_ghm"] for r in res) == 32 * 500
-    gpu.clear_masks()
-    assert kat["filtered"]["multiplicons"] < kat["plain"]["multiplicons"]
-
-
 def test_c3_level2_and_20_profile_searches_match_oracle():
     cfg = synth.config_c3(1.0)
     ds, gpu, cpu = _engines(cfg)
@@ -196,36 +171,6 @@ def test_c3_level2_and_20_profile_searches_match_oracle():
         assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
         found += a.n_multiplicons
     assert found > 0
-    gpu.close()
-
-
-def test_d2_level2_and_profile_searches_match_oracle():
-    """The datasetII-shaped workload of the bench line (`--workload d2`: 420 ragged lists, 7 ... 9,987 genes, the shipped
-    list-length distribution with synthetic genes): the WHOLE level-2 call (88,410 list pairs, GHMs up to 6,000 dots)
-    byte for byte against the oracle, then 8 profile searches with accumulating masks one call at a time and the same 8
-    as one batch."""
-    import bench
-    cfg = bench.workload_config("d2")
-    ds, gpu, cpu = _engines(cfg)
-    full, want = gpu.level2_all_pairs(), cpu.level2_all_pairs()
-    assert full.stats["n_ghm"] == want.stats["n_ghm"] == 88410 and full.stats["n_dots"] == want.stats["n_dots"]
-    assert capi.compare_packed(full.bytes, want.bytes, pl.P_RTOL) is None
-    assert np.array_equal(full.ghm_index, want.ghm_index)
-    profs = bench.make_profiles(ds, want.bytes, 8)
-    masks = [[(m.x_object_id, m.bounds[0], m.bounds[1]), (m.y_object_id, m.bounds[2], m.bounds[3])] for m, _ in profs]
-    single, found = [], 0
-    for (m, p), mk in zip(profs, masks):
-        for e in (gpu, cpu):
-            for (l, b, e2) in mk:
-                e.mask_range(l, b, e2)
-        a, b = gpu.profile_search(p), cpu.profile_search(p)
-        assert capi.compare_packed(a.bytes, b.bytes, pl.P_RTOL) is None
-        single.append(a.bytes)
-        found += a.n_multiplicons
-    assert found > 50
-    gpu.clear_masks()
-    for k, r in enumerate(gpu.profile_search_batch([p for _, p in profs], masks)):
-        assert r.bytes == single[k], k
     gpu.close()
 
 
