@@ -160,6 +160,11 @@ def test_c3_level2_and_20_profile_searches_match_oracle():
     sel = sample_of(full, len(xs), 500, 2500, seed=3)
     want = cpu.level2_pairs(xs[sel], ys[sel])
     assert capi.compare_packed(blocks_of(full, sel), want.bytes, pl.P_RTOL) is None
+    # ... and the whole stream (8,053 multiplicons) against the oracle's committed digest of the same call
+    import json
+    kat = json.load(open(os.path.join(pl.GOLDEN, "bench_profiles_c4.kat.json")))["c3_level2"]
+    msg = pl.digest_mismatch(pl.stream_digest([full.bytes]), kat)
+    assert msg is None, msg
     import bench
     profs = bench.make_profiles(ds, full.bytes, 20)
     found = 0
